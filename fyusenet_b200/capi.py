@@ -1,0 +1,320 @@
+"""ctypes binding of the C ABI declared in include/fyusenet_b200.h.
+
+This is the Python-side stub a maintainer would use to drive the backend; it is
+what tests/ and bench.py call.  There is no fallback of any kind: if libfyusenet_b200.so is missing
+the import fails loudly, and without a CUDA device `Context()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "lib" / "libfyusenet_b200.so"
+
+# flags / enums (include/fyusenet_b200.h)
+FLAG_RESIDUAL_INPUT, FLAG_RELU_ON_RESIDUAL, FLAG_BATCHNORM_ON_RESIDUAL = 1, 2, 4
+FLAG_POST_BATCHNORM, FLAG_DEEP, FLAG_PRE_RELU, FLAG_PRE_CLIP = 8, 16, 64, 128
+QUIRK_FRAC3_ASYM, QUIRK_FRAC_ACT_FIRST, QUIRK_MAXPOOL3_COL, QUIRKS_REFERENCE = 1, 2, 4, 7
+ORDER_SHALLOW, ORDER_DEEP = 0, 1
+F16, F32 = 0, 1
+BACKEND_AUTO, BACKEND_DIRECT, BACKEND_TC = 0, 1, 2
+
+
+class FynError(RuntimeError):
+    """Non-zero status from the C ABI (the C++ host wrapper throws FynException for the same)."""
+
+
+class TensorDesc(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("padding", C.c_int),
+                ("order", C.c_int), ("dtype", C.c_int), ("batch", C.c_int), ("packing", C.c_int)]
+
+
+class TensorGeom(C.Structure):
+    _fields_ = [("tex_width", C.c_int), ("tex_height", C.c_int), ("planes", C.c_int), ("tiles_x", C.c_int),
+                ("tiles_y", C.c_int), ("packing", C.c_int), ("elem_size", C.c_size_t),
+                ("plane_elems", C.c_size_t), ("image_elems", C.c_size_t), ("bytes", C.c_size_t)]
+
+
+class DeviceInfo(C.Structure):
+    _fields_ = [("device", C.c_int), ("sm_count", C.c_int), ("cc_major", C.c_int), ("cc_minor", C.c_int),
+                ("total_mem", C.c_size_t), ("smem_per_block_optin", C.c_size_t), ("name", C.c_char * 64)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("in_channels", C.c_int), ("out_channels", C.c_int),
+                ("kernel", C.c_int), ("downsample", C.c_int), ("dilation", C.c_int),
+                ("in_padding", C.c_int), ("out_padding", C.c_int), ("res_padding", C.c_int),
+                ("flags", C.c_uint), ("leaky", C.c_float), ("clip_lo", C.c_float), ("clip_hi", C.c_float),
+                ("source_step", C.c_float), ("fractional", C.c_int), ("quirks", C.c_int), ("backend", C.c_int)]
+
+
+class PoolDesc(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("pool_x", C.c_int),
+                ("pool_y", C.c_int), ("downsample", C.c_int), ("in_padding", C.c_int), ("out_padding", C.c_int),
+                ("is_max", C.c_int), ("global_", C.c_int), ("flags", C.c_uint), ("leaky", C.c_float),
+                ("clip_lo", C.c_float), ("clip_hi", C.c_float), ("quirks", C.c_int)]
+
+
+class BnDesc(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("in_padding", C.c_int),
+                ("out_padding", C.c_int), ("flags", C.c_uint), ("leaky", C.c_float), ("clip_lo", C.c_float),
+                ("clip_hi", C.c_float)]
+
+
+UnaryDesc = BnDesc  # identical field layout (fyn_unary_desc)
+
+# every symbol include/fyusenet_b200.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "fyn_abi_version", "fyn_last_error", "fyn_device_count", "fyn_cuda_init", "fyn_cuda_shutdown",
+    "fyn_get_device_info", "fyn_launch_count", "fyn_stream_create", "fyn_stream_destroy", "fyn_stream_sync",
+    "fyn_event_create", "fyn_event_destroy", "fyn_event_record", "fyn_event_sync", "fyn_event_elapsed_ms",
+    "fyn_stream_wait_event", "fyn_host_alloc", "fyn_host_free", "fyn_tensor_geometry", "fyn_tensor_create",
+    "fyn_tensor_wrap", "fyn_tensor_destroy", "fyn_tensor_clear", "fyn_tensor_get_desc", "fyn_tensor_device_ptr",
+    "fyn_upload_f32_async", "fyn_download_f32_async", "fyn_download_f32_elems", "fyn_tensor_write_chw_f32",
+    "fyn_tensor_read_chw_f32", "fyn_conv2d_output_size", "fyn_conv2d_create", "fyn_conv2d_load_weights",
+    "fyn_conv2d_run", "fyn_conv2d_backend", "fyn_pool2d_create", "fyn_pool2d_run", "fyn_batchnorm_create",
+    "fyn_batchnorm_load", "fyn_batchnorm_run", "fyn_sigmoid_create", "fyn_sigmoid_run", "fyn_op_destroy",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libfyusenet_b200.so (built in-tree by __graft_entry__.build() / csrc/Makefile)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                              " (there is no CPU or PyTorch fallback)")
+        L = C.CDLL(str(LIB_PATH))
+        L.fyn_last_error.restype = C.c_char_p
+        L.fyn_tensor_device_ptr.restype = C.c_void_p
+        L.fyn_download_f32_elems.restype = C.c_size_t
+        for name in EXPORTS:
+            getattr(L, name)
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise FynError(f"fyn status {rc}: {lib().fyn_last_error().decode(errors='replace')}")
+
+
+def _fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _s(stream):
+    """cudaStream_t argument: None, a ctypes pointer, or an integer handle (e.g. torch's stream.cuda_stream)."""
+    if stream is None or isinstance(stream, C.c_void_p):
+        return stream
+    return C.c_void_p(int(stream))
+
+
+def tensor_geometry(width, height, channels, padding=0, order=ORDER_SHALLOW, dtype=F16, batch=1, packing=0):
+    d = TensorDesc(width, height, channels, padding, order, dtype, batch, packing)
+    g = TensorGeom()
+    check(lib().fyn_tensor_geometry(C.byref(d), C.byref(g)))
+    return g
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().fyn_cuda_init(int(device), C.byref(self._h)))
+        self.device = device
+
+    def info(self) -> DeviceInfo:
+        i = DeviceInfo()
+        check(lib().fyn_get_device_info(self._h, C.byref(i)))
+        return i
+
+    def launch_count(self, reset=False) -> int:
+        n = C.c_uint64()
+        check(lib().fyn_launch_count(self._h, C.byref(n), int(reset)))
+        return n.value
+
+    def stream_create(self):
+        s = C.c_void_p()
+        check(lib().fyn_stream_create(self._h, C.byref(s)))
+        return s
+
+    def stream_sync(self, stream=None):
+        check(lib().fyn_stream_sync(self._h, _s(stream)))
+
+    def event_create(self):
+        e = C.c_void_p()
+        check(lib().fyn_event_create(self._h, C.byref(e)))
+        return e
+
+    def event_record(self, ev, stream=None):
+        check(lib().fyn_event_record(self._h, ev, _s(stream)))
+
+    def event_sync(self, ev):
+        check(lib().fyn_event_sync(self._h, ev))
+
+    def elapsed_ms(self, a, b) -> float:
+        ms = C.c_float()
+        check(lib().fyn_event_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
+
+    def host_alloc(self, nfloats: int) -> np.ndarray:
+        """Pinned float32 host buffer as a numpy array (kept alive by the context)."""
+        p = C.c_void_p()
+        check(lib().fyn_host_alloc(self._h, C.c_size_t(nfloats * 4), C.byref(p)))
+        buf = (C.c_float * nfloats).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.float32)
+        self._pinned = getattr(self, "_pinned", []) + [(p, buf)]
+        return arr
+
+    def tensor(self, width, height, channels, padding=0, order=ORDER_SHALLOW, dtype=F16, batch=1, packing=0):
+        return Tensor(self, TensorDesc(width, height, channels, padding, order, dtype, batch, packing))
+
+    def close(self):
+        if self._h:
+            for p, _ in getattr(self, "_pinned", []):
+                lib().fyn_host_free(self._h, p)
+            self._pinned = []
+            lib().fyn_cuda_shutdown(self._h)
+            self._h = C.c_void_p()
+
+
+class Tensor:
+    def __init__(self, ctx: Context, desc: TensorDesc, device_ptr=None):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        if device_ptr is None:
+            check(lib().fyn_tensor_create(ctx._h, C.byref(desc), C.byref(self._h)))
+        else:
+            check(lib().fyn_tensor_wrap(ctx._h, C.byref(desc), C.c_void_p(device_ptr), C.byref(self._h)))
+        self.desc, self.geom = TensorDesc(), TensorGeom()
+        check(lib().fyn_tensor_get_desc(self._h, C.byref(self.desc), C.byref(self.geom)))
+
+    @property
+    def device_ptr(self) -> int:
+        return lib().fyn_tensor_device_ptr(self._h)
+
+    def write_chw(self, chw):
+        d = self.desc
+        a = np.ascontiguousarray(chw, np.float32).reshape(d.batch, d.channels, d.height, d.width)
+        check(lib().fyn_tensor_write_chw_f32(self._h, _fptr(a)))
+
+    def read_chw(self) -> np.ndarray:
+        d = self.desc
+        out = np.zeros((d.batch, d.channels, d.height, d.width), np.float32)
+        check(lib().fyn_tensor_read_chw_f32(self._h, _fptr(out)))
+        return out[0] if d.batch == 1 else out
+
+    def upload(self, host_hwc, stream=None):
+        d = self.desc
+        a = np.ascontiguousarray(host_hwc, np.float32)
+        assert a.size == d.batch * d.height * d.width * d.channels, (a.shape, d.batch, d.height, d.width, d.channels)
+        check(lib().fyn_upload_f32_async(self._h, _fptr(a), _s(stream)))
+        return a  # caller keeps it alive until the stream is synchronised
+
+    def download_elems(self) -> int:
+        return lib().fyn_download_f32_elems(self._h)
+
+    def download(self, out=None, stream=None, sync=True) -> np.ndarray:
+        g, d = self.geom, self.desc
+        n = self.download_elems()
+        if out is None:
+            out = np.zeros(n, np.float32)
+        assert out.size == n and out.dtype == np.float32
+        check(lib().fyn_download_f32_async(self._h, _fptr(out), _s(stream)))
+        if sync:
+            self.ctx.stream_sync(stream)
+        if d.order == ORDER_DEEP:
+            return out.reshape(d.batch, g.tex_height, g.tex_width, 4)
+        return out.reshape(d.batch, g.planes, g.tex_height, g.tex_width, 4)
+
+    def clear(self, stream=None):
+        check(lib().fyn_tensor_clear(self._h, _s(stream)))
+
+    def destroy(self):
+        if self._h:
+            lib().fyn_tensor_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class _Op:
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+
+    def destroy(self):
+        if self._h:
+            lib().fyn_op_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def act_flags(act: str | None):
+    return {None: 0, "none": 0, "relu": FLAG_PRE_RELU, "leaky": FLAG_PRE_RELU, "clip": FLAG_PRE_CLIP}[act]
+
+
+class Conv2d(_Op):
+    def __init__(self, ctx, weights, *, width, height, in_channels, out_channels, kernel, downsample=1, dilation=1,
+                 in_padding=0, out_padding=0, res_padding=0, flags=0, leaky=0.0, clip=(0.0, 0.0), source_step=1.0,
+                 fractional=False, quirks=QUIRKS_REFERENCE, backend=BACKEND_AUTO):
+        super().__init__(ctx)
+        self.desc = ConvDesc(width, height, in_channels, out_channels, kernel, downsample, dilation, in_padding,
+                             out_padding, res_padding, flags, leaky, clip[0], clip[1], source_step,
+                             int(bool(fractional)), quirks, backend)
+        w = np.ascontiguousarray(weights, np.float32)
+        need = out_channels + kernel * kernel * in_channels * out_channels + (
+            2 * out_channels if flags & FLAG_POST_BATCHNORM else 0)
+        if w.size < need:
+            raise ValueError(f"weight blob too small: {w.size} < {need}")
+        check(lib().fyn_conv2d_create(ctx._h, C.byref(self.desc), _fptr(w), C.byref(self._h)))
+        ow, oh = C.c_int(), C.c_int()
+        check(lib().fyn_conv2d_output_size(C.byref(self.desc), C.byref(ow), C.byref(oh)))
+        self.out_width, self.out_height = ow.value, oh.value
+
+    @property
+    def backend(self) -> int:
+        return lib().fyn_conv2d_backend(self._h)
+
+    def load_weights(self, weights):
+        w = np.ascontiguousarray(weights, np.float32)
+        check(lib().fyn_conv2d_load_weights(self._h, _fptr(w)))
+
+    def run(self, x: Tensor, out: Tensor, residual: Tensor | None = None, stream=None):
+        check(lib().fyn_conv2d_run(self._h, x._h, residual._h if residual is not None else None, out._h, _s(stream)))
+
+
+class Pool2d(_Op):
+    def __init__(self, ctx, *, width, height, channels, pool=2, downsample=2, in_padding=0, out_padding=0,
+                 is_max=True, global_=False, flags=0, leaky=0.0, quirks=QUIRKS_REFERENCE):
+        super().__init__(ctx)
+        self.desc = PoolDesc(width, height, channels, pool, pool, downsample, in_padding, out_padding,
+                             int(bool(is_max)), int(bool(global_)), flags, leaky, 0.0, 0.0, quirks)
+        check(lib().fyn_pool2d_create(ctx._h, C.byref(self.desc), C.byref(self._h)))
+
+    def run(self, x, out, stream=None):
+        check(lib().fyn_pool2d_run(self._h, x._h, out._h, _s(stream)))
+
+
+class BatchNorm(_Op):
+    def __init__(self, ctx, scale_bias, *, width, height, channels, in_padding=0, out_padding=0, flags=0):
+        super().__init__(ctx)
+        self.desc = BnDesc(width, height, channels, in_padding, out_padding, flags, 0.0, 0.0, 0.0)
+        sb = np.ascontiguousarray(scale_bias, np.float32)
+        assert sb.size >= 2 * channels
+        check(lib().fyn_batchnorm_create(ctx._h, C.byref(self.desc), _fptr(sb), C.byref(self._h)))
+
+    def run(self, x, out, stream=None):
+        check(lib().fyn_batchnorm_run(self._h, x._h, out._h, _s(stream)))
+
+
+class Sigmoid(_Op):
+    def __init__(self, ctx, *, width, height, channels, in_padding=0, out_padding=0, flags=0):
+        super().__init__(ctx)
+        self.desc = UnaryDesc(width, height, channels, in_padding, out_padding, flags, 0.0, 0.0, 0.0)
+        check(lib().fyn_sigmoid_create(ctx._h, C.byref(self.desc), C.byref(self._h)))
+
+    def run(self, x, out, stream=None):
+        check(lib().fyn_sigmoid_run(self._h, x._h, out._h, _s(stream)))

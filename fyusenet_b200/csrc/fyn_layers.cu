@@ -1,0 +1,257 @@
+// fyn_layers.cu -- bandwidth-bound layers: pooling, batch-norm, sigmoid.
+// One thread per output texel (4 channels), 8-byte (fp16) / 16-byte (fp32) vector accesses,
+// consecutive threads on consecutive x so every warp touches contiguous texel runs.
+#include <cmath>
+#include <cstring>
+
+#include "fyn_internal.h"
+
+// ---------------------------------------------------------------------------------------------
+// pooling: DeepMaxPoolLayer / DeepAvgPoolLayer and the shallow MaxPool/AvgPool layers
+//   gpu/deep/deeppoolinglayer.cpp:38-54 (global => pool = downsample = (W,H))
+//   shaders/deep/deepmaxpool.frag:12-61 (window offsets [-P, pool-1-P] around texel P+ds*o; for
+//        pool==3 the third column is fetched without activate(): FYN_QUIRK_MAXPOOL3_COL)
+//   shaders/deep/deepavgpool.frag:15-58 (offsets [0,pool-1]; [-1,1] for pool==3; sum / n)
+// ---------------------------------------------------------------------------------------------
+struct PoolArgs {
+    TView in, out;
+    int px, py, dx, dy, Wo, Ho, tiles, batch, isMax, off, outP, quirk3;
+    float inv;
+    ActParams act;
+};
+
+__global__ void __launch_bounds__(128) k_pool(const PoolArgs a) {
+    unsigned bid = blockIdx.x;
+    const int xBlocks = (a.Wo + 31) / 32, yBlocks = (a.Ho + 3) / 4;
+    const int xb = bid % xBlocks;
+    bid /= xBlocks;
+    const int yb = bid % yBlocks;
+    bid /= yBlocks;
+    const int t = bid % a.tiles;
+    const int n = bid / a.tiles;
+    const int xo = xb * 32 + threadIdx.x, yo = yb * 4 + threadIdx.y;
+    if (xo >= a.Wo || yo >= a.Ho) return;
+    const int bx = a.in.P + a.dx * xo + a.off, by = a.in.P + a.dy * yo + a.off;
+    float4 r = a.isMax ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < a.py; j++)
+        for (int i = 0; i < a.px; i++) {
+            float4 v = fyn_fetch(a.in, n, t, bx + i, by + j);
+            if (!(a.quirk3 && i == 2)) v = fyn_act4(v, a.act);
+            if (a.isMax) {
+                r.x = fmaxf(r.x, v.x);
+                r.y = fmaxf(r.y, v.y);
+                r.z = fmaxf(r.z, v.z);
+                r.w = fmaxf(r.w, v.w);
+            } else {
+                r.x += v.x;
+                r.y += v.y;
+                r.z += v.z;
+                r.w += v.w;
+            }
+        }
+    if (!a.isMax) r = make_float4(r.x * a.inv, r.y * a.inv, r.z * a.inv, r.w * a.inv);
+    fyn_store_texel(a.out, n, t, a.outP + xo, a.outP + yo, r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch-norm and sigmoid
+// ---------------------------------------------------------------------------------------------
+struct EltArgs {
+    TView in, out;
+    const float4 *scale, *bias;  // per tile (bn only)
+    int tiles, batch, outP, mode;  // mode 0 = bn, 1 = sigmoid
+    ActParams act;
+};
+
+__global__ void __launch_bounds__(128) k_eltwise(const EltArgs a) {
+    unsigned bid = blockIdx.x;
+    const int W = a.in.W, H = a.in.H;
+    const int xBlocks = (W + 31) / 32, yBlocks = (H + 3) / 4;
+    const int xb = bid % xBlocks;
+    bid /= xBlocks;
+    const int yb = bid % yBlocks;
+    bid /= yBlocks;
+    const int t = bid % a.tiles;
+    const int n = bid / a.tiles;
+    const int x = xb * 32 + threadIdx.x, y = yb * 4 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    float4 v = fyn_act4(fyn_fetch(a.in, n, t, a.in.P + x, a.in.P + y), a.act);
+    float4 r;
+    if (a.mode == 0) {
+        const float4 s = __ldg(a.scale + t), b = __ldg(a.bias + t);
+        r = make_float4(fmaf(v.x, s.x, b.x), fmaf(v.y, s.y, b.y), fmaf(v.z, s.z, b.z), fmaf(v.w, s.w, b.w));
+    } else {
+        // shaders/sigmoid.frag:10-13
+        r = make_float4(1.f / (1.f + __expf(-v.x)), 1.f / (1.f + __expf(-v.y)), 1.f / (1.f + __expf(-v.z)),
+                        1.f / (1.f + __expf(-v.w)));
+    }
+    fyn_store_texel(a.out, n, t, a.outP + x, a.outP + y, r);
+}
+
+static int check_io(const char *who, const fyn_tensor *t, int w, int h, int c, int pad, bool deep) {
+    if (!t) FYN_FAIL(FYN_ERR_INVALID, "%s: tensor is NULL", who);
+    const fyn_tensor_desc &d = t->desc;
+    bool order_ok = ((d.order == FYN_ORDER_DEEP) == deep) || c <= 4;
+    if (d.width != w || d.height != h || d.channels != c || d.padding != pad || !order_ok)
+        FYN_FAIL(FYN_ERR_INVALID, "%s: tensor mismatch: got %dx%dx%d pad %d, need %dx%dx%d pad %d", who, d.width,
+                 d.height, d.channels, d.padding, w, h, c, pad);
+    return FYN_OK;
+}
+
+static long long grid_blocks(int W, int H, int tiles, int batch) {
+    return (long long)((W + 31) / 32) * ((H + 3) / 4) * tiles * batch;
+}
+
+extern "C" {
+
+int fyn_pool2d_create(fyn_ctx *ctx, const fyn_pool_desc *d, fyn_op **out) {
+    if (!ctx || !d || !out) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (d->width <= 0 || d->height <= 0 || d->channels <= 0) FYN_FAIL(FYN_ERR_INVALID, "pool: bad shape");
+    if (!d->global && (d->pool_x < 1 || d->pool_y < 1 || d->downsample < 1)) FYN_FAIL(FYN_ERR_INVALID, "pool: bad window");
+    fyn_op *op = new fyn_op();
+    op->ctx = ctx;
+    op->kind = FYN_OP_POOL;
+    op->pool = *d;
+    if (d->global) {
+        op->pool.pool_x = d->width;
+        op->pool.pool_y = d->height;
+        op->Wo = op->Ho = 1;
+    } else {
+        op->Wo = d->width / d->downsample;
+        op->Ho = d->height / d->downsample;
+    }
+    *out = op;
+    return FYN_OK;
+}
+
+int fyn_pool2d_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream) {
+    if (!op || op->kind != FYN_OP_POOL) FYN_FAIL(FYN_ERR_INVALID, "not a pool op");
+    const fyn_pool_desc &d = op->pool;
+    const bool deep = (d.flags & FYN_FLAG_DEEP) != 0;
+    int rc = check_io("pool input", in, d.width, d.height, d.channels, d.in_padding, deep);
+    if (rc) return rc;
+    rc = check_io("pool output", out, op->Wo, op->Ho, d.channels, d.out_padding, deep);
+    if (rc) return rc;
+    if (in->desc.batch != out->desc.batch) FYN_FAIL(FYN_ERR_INVALID, "pool: batch mismatch");
+    FYN_CUDA(cudaSetDevice(op->ctx->device));
+    PoolArgs a{};
+    a.in = fyn_make_view(in);
+    a.out = fyn_make_view(out);
+    a.px = d.pool_x;
+    a.py = d.pool_y;
+    a.dx = d.global ? d.width : d.downsample;
+    a.dy = d.global ? d.height : d.downsample;
+    a.Wo = op->Wo;
+    a.Ho = op->Ho;
+    a.tiles = (d.channels + 3) / 4;
+    a.batch = in->desc.batch;
+    a.isMax = d.is_max;
+    const bool p3 = (d.pool_x == 3 && d.pool_y == 3 && !d.global);
+    a.off = d.is_max ? -d.in_padding : (p3 ? -1 : 0);
+    a.quirk3 = d.is_max && p3 && (d.quirks & FYN_QUIRK_MAXPOOL3_COL);
+    a.outP = d.out_padding;
+    a.inv = 1.f / (float)(a.px * a.py);
+    a.act = fyn_act_from_flags(d.flags, d.leaky, d.clip_lo, d.clip_hi);
+    long long blocks = grid_blocks(a.Wo, a.Ho, a.tiles, a.batch);
+    k_pool<<<(unsigned)blocks, dim3(32, 4), 0, (cudaStream_t)stream>>>(a);
+    FYN_CHECK_LAUNCH(op->ctx);
+    return FYN_OK;
+}
+
+int fyn_batchnorm_load(fyn_op *op, const float *sb) {
+    if (!op || op->kind != FYN_OP_BN || !sb) FYN_FAIL(FYN_ERR_INVALID, "bad bn op / data");
+    const int C = op->bn.channels, tiles = (C + 3) / 4;
+    std::vector<float> h((size_t)tiles * 8, 0.f);
+    for (int c = 0; c < C; c++) {
+        h[c] = sb[c];                          // scale block
+        h[(size_t)tiles * 4 + c] = sb[C + c];  // bias block
+    }
+    FYN_CUDA(cudaSetDevice(op->ctx->device));
+    if (!op->d_bias) FYN_CUDA(cudaMalloc((void **)&op->d_bias, h.size() * sizeof(float)));
+    FYN_CUDA(cudaMemcpy(op->d_bias, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return FYN_OK;
+}
+
+int fyn_batchnorm_create(fyn_ctx *ctx, const fyn_bn_desc *d, const float *sb, fyn_op **out) {
+    if (!ctx || !d || !sb || !out) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (d->width <= 0 || d->height <= 0 || d->channels <= 0) FYN_FAIL(FYN_ERR_INVALID, "bn: bad shape");
+    fyn_op *op = new fyn_op();
+    op->ctx = ctx;
+    op->kind = FYN_OP_BN;
+    op->bn = *d;
+    int rc = fyn_batchnorm_load(op, sb);
+    if (rc) {
+        fyn_op_destroy(op);
+        return rc;
+    }
+    *out = op;
+    return FYN_OK;
+}
+
+int fyn_batchnorm_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream) {
+    if (!op || op->kind != FYN_OP_BN) FYN_FAIL(FYN_ERR_INVALID, "not a bn op");
+    const fyn_bn_desc &d = op->bn;
+    const bool deep = (d.flags & FYN_FLAG_DEEP) != 0;
+    int rc = check_io("bn input", in, d.width, d.height, d.channels, d.in_padding, deep);
+    if (rc) return rc;
+    rc = check_io("bn output", out, d.width, d.height, d.channels, d.out_padding, deep);
+    if (rc) return rc;
+    if (in->desc.batch != out->desc.batch) FYN_FAIL(FYN_ERR_INVALID, "bn: batch mismatch");
+    FYN_CUDA(cudaSetDevice(op->ctx->device));
+    EltArgs a{};
+    a.in = fyn_make_view(in);
+    a.out = fyn_make_view(out);
+    a.tiles = (d.channels + 3) / 4;
+    a.batch = in->desc.batch;
+    a.scale = reinterpret_cast<const float4 *>(op->d_bias);
+    a.bias = a.scale + a.tiles;
+    a.outP = d.out_padding;
+    a.mode = 0;
+    // the shallow shader applies no activation (shaders/batchnorm.frag:60-68); the deep one does
+    // (shaders/deep/deepbatchnorm.frag:57-58)
+    a.act = deep ? fyn_act_from_flags(d.flags, d.leaky, d.clip_lo, d.clip_hi) : ActParams{0, 0.f, 0.f, 0.f};
+    long long blocks = grid_blocks(d.width, d.height, a.tiles, a.batch);
+    k_eltwise<<<(unsigned)blocks, dim3(32, 4), 0, (cudaStream_t)stream>>>(a);
+    FYN_CHECK_LAUNCH(op->ctx);
+    return FYN_OK;
+}
+
+int fyn_sigmoid_create(fyn_ctx *ctx, const fyn_unary_desc *d, fyn_op **out) {
+    if (!ctx || !d || !out) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (d->width <= 0 || d->height <= 0 || d->channels <= 0) FYN_FAIL(FYN_ERR_INVALID, "sigmoid: bad shape");
+    fyn_op *op = new fyn_op();
+    op->ctx = ctx;
+    op->kind = FYN_OP_SIGMOID;
+    op->unary = *d;
+    *out = op;
+    return FYN_OK;
+}
+
+int fyn_sigmoid_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream) {
+    if (!op || op->kind != FYN_OP_SIGMOID) FYN_FAIL(FYN_ERR_INVALID, "not a sigmoid op");
+    const fyn_unary_desc &d = op->unary;
+    const bool deep = (d.flags & FYN_FLAG_DEEP) != 0;
+    int rc = check_io("sigmoid input", in, d.width, d.height, d.channels, d.in_padding, deep);
+    if (rc) return rc;
+    rc = check_io("sigmoid output", out, d.width, d.height, d.channels, d.out_padding, deep);
+    if (rc) return rc;
+    if (in->desc.batch != out->desc.batch) FYN_FAIL(FYN_ERR_INVALID, "sigmoid: batch mismatch");
+    FYN_CUDA(cudaSetDevice(op->ctx->device));
+    EltArgs a{};
+    a.in = fyn_make_view(in);
+    a.out = fyn_make_view(out);
+    a.tiles = (d.channels + 3) / 4;
+    a.batch = in->desc.batch;
+    a.outP = d.out_padding;
+    a.mode = 1;
+    a.act = fyn_act_from_flags(d.flags, d.leaky, d.clip_lo, d.clip_hi);
+    long long blocks = grid_blocks(d.width, d.height, a.tiles, a.batch);
+    k_eltwise<<<(unsigned)blocks, dim3(32, 4), 0, (cudaStream_t)stream>>>(a);
+    FYN_CHECK_LAUNCH(op->ctx);
+    return FYN_OK;
+}
+
+}  // extern "C"

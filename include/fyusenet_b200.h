@@ -1,0 +1,259 @@
+/* ---------------------------------------------------------------------------------------------
+ * fyusenet_b200.h -- C ABI of the B200-native GPU-layer backend for FyuseNet.
+ *
+ * This is the drop-in boundary.  The reference has no C ABI on this
+ * path: its seam is the C++ virtual interface
+ *     LayerFactoryBackend::createLayer(LayerType, LayerBuilder*, int)      fyusenet/base/layerfactory.h:149-176
+ * whose products implement LayerBase (fyusenet/base/layerbase.h:109-203), the GPULayerBase
+ * texture-slot API (fyusenet/gpu/gpulayerbase.h:127-142), ConvLayerInterface::loadWeightsAndBiases
+ * (fyusenet/base/convlayerinterface.h:58) and BatchNormInterface::loadScaleAndBias
+ * (fyusenet/base/batchnorminterface.h:48).  The C++ layer classes of the new backend
+ * (fyusenet_b200/host/) implement those interfaces and call ONLY the functions below; every
+ * entry point cites the reference mechanism it replaces.
+ *
+ * Conventions
+ *   - extern "C", POD structs, opaque handles, plain pointers and sizes; no C++/torch types.
+ *   - every function returns 0 (FYN_OK) or a negative fyn_status; fyn_last_error() returns a
+ *     thread-local message for the last failing call (the C++ wrapper turns it into FynException,
+ *     mirroring THROW_EXCEPTION_ARGS, fyusenet/common/fynexception.h:24-25,75-107).
+ *   - a context is bound to one CUDA device; calls on one context must come from one thread at
+ *     a time (the reference's "GL context must be current" rule, base/layerbase.h:106-108).
+ *   - `stream` arguments are cudaStream_t passed as void* (NULL = legacy default stream).  Ops
+ *     only enqueue work; nothing synchronises except the functions documented as blocking.
+ *   - there is NO CPU fallback: without a CUDA device fyn_cuda_init fails.
+ * ------------------------------------------------------------------------------------------- */
+#ifndef FYUSENET_B200_H
+#define FYUSENET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FYN_ABI_VERSION 1
+
+typedef enum {
+    FYN_OK = 0,
+    FYN_ERR_INVALID = -1,   /* bad argument / shape mismatch */
+    FYN_ERR_CUDA = -2,      /* CUDA runtime error (message in fyn_last_error) */
+    FYN_ERR_NOMEM = -3,
+    FYN_ERR_UNSUPPORTED = -4,
+    FYN_ERR_NODEVICE = -5
+} fyn_status;
+
+/* layer flag bits, numerically identical to fyusenet/base/layerflags.h:33-53 */
+enum {
+    FYN_FLAG_RESIDUAL_INPUT = 1,
+    FYN_FLAG_RELU_ON_RESIDUAL = 2,
+    FYN_FLAG_BATCHNORM_ON_RESIDUAL = 4,
+    FYN_FLAG_POST_BATCHNORM = 8,
+    FYN_FLAG_DEEP = 16,
+    FYN_FLAG_PRE_RELU = 64,
+    FYN_FLAG_PRE_CLIP = 128
+};
+
+/* reference shader quirks that the kernels reproduce by default */
+enum {
+    FYN_QUIRK_FRAC3_ASYM = 1,      /* fraconv3x3.frag:14-19: horizontal taps at -2s,-s,0 */
+    FYN_QUIRK_FRAC_ACT_FIRST = 2,  /* fractional.inc:11-12 vs :69-70: activation on the first tap only */
+    FYN_QUIRK_MAXPOOL3_COL = 4,    /* deepmaxpool.frag: 3rd column of a 3x3 max-pool bypasses activate() */
+    FYN_QUIRKS_REFERENCE = 7
+};
+
+typedef enum { FYN_ORDER_SHALLOW = 0, FYN_ORDER_DEEP = 1 } fyn_order;
+typedef enum { FYN_F16 = 0, FYN_F32 = 1 } fyn_dtype;
+
+typedef struct fyn_ctx fyn_ctx;
+typedef struct fyn_tensor fyn_tensor;
+typedef struct fyn_op fyn_op;
+
+/* ----------------------------------------------------------------------------------------- */
+/* context  (replaces GfxContextManager / GfxContextLink, fyusenet/gpu/gfxcontextmanager.h)   */
+/* ----------------------------------------------------------------------------------------- */
+
+typedef struct {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+    size_t total_mem;
+    size_t smem_per_block_optin;
+    char name[64];
+} fyn_device_info;
+
+int fyn_abi_version(void);
+const char *fyn_last_error(void);
+int fyn_device_count(int *count);
+int fyn_cuda_init(int device, fyn_ctx **ctx);
+int fyn_cuda_shutdown(fyn_ctx *ctx);
+int fyn_get_device_info(fyn_ctx *ctx, fyn_device_info *info);
+/* number of kernels this library has launched on the context since the last reset (bench "gpu_launches") */
+int fyn_launch_count(fyn_ctx *ctx, uint64_t *count, int reset);
+
+/* streams / events (replace GLsync fences, fyusenet/base/engine.cpp:779-780; timings :208-233) */
+int fyn_stream_create(fyn_ctx *ctx, void **stream);
+int fyn_stream_destroy(fyn_ctx *ctx, void *stream);
+int fyn_stream_sync(fyn_ctx *ctx, void *stream);              /* blocking */
+int fyn_event_create(fyn_ctx *ctx, void **event);
+int fyn_event_destroy(fyn_ctx *ctx, void *event);
+int fyn_event_record(fyn_ctx *ctx, void *event, void *stream);
+int fyn_event_sync(fyn_ctx *ctx, void *event);                /* blocking */
+int fyn_event_elapsed_ms(fyn_ctx *ctx, void *start, void *stop, float *ms);
+int fyn_stream_wait_event(fyn_ctx *ctx, void *stream, void *event);
+
+/* pinned host memory (replaces PBOPool / ManagedPBO, fyusenet/gl/pbopool.cpp) */
+int fyn_host_alloc(fyn_ctx *ctx, size_t bytes, void **ptr);
+int fyn_host_free(fyn_ctx *ctx, void *ptr);
+
+/* ----------------------------------------------------------------------------------------- */
+/* device tensors  (replace BufferManager::createTexture, fyusenet/base/buffermanager.cpp:650-708) */
+/* ----------------------------------------------------------------------------------------- */
+
+/*
+ * Layout contract (FyuseNet's 4-channel-packed, spatially padded layouts; PIXEL_PACKING = 4,
+ * fyusenet/base/layerflags.h:191):
+ *   SHALLOW: [batch][ceil(C/4)][H+2P][W+2P][packing]   channel c -> plane c/4, lane c%4
+ *            (unit_tests/layertestbase.cpp:281-317).  packing is 4, or 1..3 for a single-plane
+ *            texture with fewer channels (upload textures, convlayerbase_vanilla.cpp:205-210).
+ *   DEEP   : [batch][TH][TW][4] with T = ceil(C/4) tiles on a tx x ty grid
+ *            (cpu/cpubuffershape.cpp:430-447), tile i at pixel (P+(i%tx)(W+P), P+(i/tx)(H+P)),
+ *            TW = tx(W+P)+P, TH = ty(H+P)+P (gpu/deep/deeptiler.cpp:63-95).
+ * Padding texels and unused lanes are zero: they are cleared at creation and no kernel writes them.
+ * dtype F16 is the reference default (RGBA16F), F32 = HIGH_PRECISION (gpu/gpulayerbase.h:100-110).
+ * batch is new (the reference is batch-1, README.md:72); batch=1 reproduces it exactly.
+ */
+typedef struct {
+    int width, height;  /* net size, without padding */
+    int channels;
+    int padding;
+    int order;          /* fyn_order */
+    int dtype;          /* fyn_dtype */
+    int batch;          /* >= 1 */
+    int packing;        /* 0 or 4 = RGBA; 1..3 only for shallow single-plane tensors */
+} fyn_tensor_desc;
+
+typedef struct {
+    int tex_width, tex_height; /* texels per plane (shallow) or of the tiled texture (deep) */
+    int planes;                /* shallow: ceil(C/4); deep: 1 */
+    int tiles_x, tiles_y;      /* deep tiling (1,1 for shallow) */
+    int packing;               /* resolved packing */
+    size_t elem_size;          /* 2 or 4 */
+    size_t plane_elems;        /* elements per plane / tiled texture */
+    size_t image_elems;        /* elements per batch image */
+    size_t bytes;              /* whole tensor */
+} fyn_tensor_geom;
+
+int fyn_tensor_geometry(const fyn_tensor_desc *desc, fyn_tensor_geom *geom); /* host only, no device */
+int fyn_tensor_create(fyn_ctx *ctx, const fyn_tensor_desc *desc, fyn_tensor **tensor);
+/* wrap caller-owned device memory of at least geom.bytes (e.g. a torch allocation); never freed here */
+int fyn_tensor_wrap(fyn_ctx *ctx, const fyn_tensor_desc *desc, void *device_ptr, fyn_tensor **tensor);
+int fyn_tensor_destroy(fyn_tensor *tensor);
+int fyn_tensor_clear(fyn_tensor *tensor, void *stream);
+int fyn_tensor_get_desc(const fyn_tensor *tensor, fyn_tensor_desc *desc, fyn_tensor_geom *geom);
+void *fyn_tensor_device_ptr(const fyn_tensor *tensor);
+
+/* ----------------------------------------------------------------------------------------- */
+/* host <-> device I/O                                                                         */
+/* ----------------------------------------------------------------------------------------- */
+
+/* UploadLayer::syncUpload (fyusenet/gpu/uploadlayer.cpp:360-380): host float32 [batch][H][W][C]
+ * (CPUBuffer GPU_SHALLOW order, C = tensor channels <= 4) -> single-plane shallow tensor.  When the
+ * tensor is F32 with packing == C and padding 0 (the reference's RGB32F upload texture) this is one
+ * cudaMemcpyAsync; otherwise the data goes through a device staging buffer and a convert kernel.
+ * Asynchronous w.r.t. the host when `host` is pinned. */
+int fyn_upload_f32_async(fyn_tensor *tensor, const float *host, void *stream);
+
+/* DownloadLayer::pboBlit + CPUBuffer::readFromPBO (fyusenet/gpu/downloadlayer.cpp:112-131,257-283)
+ * and DeepDownloadLayer (fyusenet/gpu/deep/deepdownloadlayer.cpp:136-160): tensor -> host float32 in
+ * the tensor's own texel order INCLUDING padding: shallow [batch][planes][H+2P][W+2P][4],
+ * deep [batch][TH][TW][4] (CPUBuffer GPU_SHALLOW / GPU_DEEP orders).  F16 tensors are widened by a
+ * convert kernel into a device staging buffer first.  Asynchronous when `host` is pinned. */
+int fyn_download_f32_async(fyn_tensor *tensor, float *host, void *stream);
+size_t fyn_download_f32_elems(const fyn_tensor *tensor);
+
+/* Debug / parity interchange (LayerBase::writeResult format, fyusenet/base/layerbase.h:160-172 and
+ * GPULayerBase::copyResult, fyusenet/gpu/gpulayerbase.cpp:525-560): float32 [batch][C][H][W]
+ * without padding.  Both calls are BLOCKING and go through pageable host memory. */
+int fyn_tensor_write_chw_f32(fyn_tensor *tensor, const float *host_chw);
+int fyn_tensor_read_chw_f32(fyn_tensor *tensor, float *host_chw);
+
+/* ----------------------------------------------------------------------------------------- */
+/* layer ops.  create = repack weights to the device; run = enqueue kernels on `stream`.        */
+/* ----------------------------------------------------------------------------------------- */
+
+/* ConvLayerNxN / ConvLayer1x1 / FractionalConvLayerNxN (fyusenet/gpu/vanilla/) and
+ * DeepConvLayer1x1 / DeepConvLayerNxN / DeepGEMMLayer (fyusenet/gpu/deep/).
+ * Weight blob = ConvLayerInterface::loadWeightsAndBiases format (base/convlayerinterface.h:31-57):
+ * bias[Co], W[Co][Ky][Kx][Ci], then with FYN_FLAG_POST_BATCHNORM bnScale[Co], bnBias[Co]. */
+typedef struct {
+    int width, height;          /* input net size */
+    int in_channels, out_channels;
+    int kernel;                 /* odd, 1..9 */
+    int downsample;             /* isotropic stride (ds) */
+    int dilation;
+    int in_padding, out_padding, res_padding;
+    unsigned flags;             /* FYN_FLAG_* (DEEP selects the tiled layout) */
+    float leaky;                /* with PRE_RELU: leak factor (0 = plain ReLU) */
+    float clip_lo, clip_hi;     /* with PRE_CLIP */
+    float source_step;          /* fractional convs */
+    int fractional;             /* LayerType::FRACCONVOLUTION2D */
+    int quirks;                 /* FYN_QUIRK_* */
+    int backend;                /* 0 = auto, 1 = force direct (CUDA-core) kernel, 2 = force tcgen05 kernel */
+} fyn_conv_desc;
+
+int fyn_conv2d_output_size(const fyn_conv_desc *desc, int *out_width, int *out_height);
+int fyn_conv2d_create(fyn_ctx *ctx, const fyn_conv_desc *desc, const float *bias_weights_bn, fyn_op **op);
+/* hot-swap weights (StyleNet9x9::loadWeightsAndBiases after setup, stylenet9x9.cpp:87-95) */
+int fyn_conv2d_load_weights(fyn_op *op, const float *bias_weights_bn);
+int fyn_conv2d_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *residual, fyn_tensor *out, void *stream);
+/* which kernel family the op resolved to: 1 = direct, 2 = tcgen05 */
+int fyn_conv2d_backend(const fyn_op *op);
+
+/* DeepMaxPoolLayer / DeepAvgPoolLayer / MaxPoolLayer / AvgPoolLayer
+ * (fyusenet/gpu/deep/deeppoolinglayer.cpp:38-54,109-190; shaders deep/deepmaxpool.frag, deepavgpool.frag) */
+typedef struct {
+    int width, height, channels;
+    int pool_x, pool_y, downsample;
+    int in_padding, out_padding;
+    int is_max, global;
+    unsigned flags;             /* PRE_RELU / PRE_CLIP / DEEP */
+    float leaky, clip_lo, clip_hi;
+    int quirks;
+} fyn_pool_desc;
+
+int fyn_pool2d_create(fyn_ctx *ctx, const fyn_pool_desc *desc, fyn_op **op);
+int fyn_pool2d_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream);
+
+/* BatchNormLayer (fyusenet/gpu/batchnormlayer.cpp:71-128, shaders/batchnorm.frag:60-68: x*scale+bias,
+ * no activation) and DeepBatchNormLayer (fyusenet/gpu/deep/deepbatchnormlayer.cpp:78-147,
+ * deep/deepbatchnorm.frag:57-58: act(x)*scale+bias).  Data = scale[C] then bias[C]. */
+typedef struct {
+    int width, height, channels;
+    int in_padding, out_padding;
+    unsigned flags;
+    float leaky, clip_lo, clip_hi;
+} fyn_bn_desc;
+
+int fyn_batchnorm_create(fyn_ctx *ctx, const fyn_bn_desc *desc, const float *scale_bias, fyn_op **op);
+int fyn_batchnorm_load(fyn_op *op, const float *scale_bias);
+int fyn_batchnorm_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream);
+
+/* SigmoidLayer (fyusenet/gpu/sigmoidlayer.cpp:77-112, shaders/sigmoid.frag:10-17): 1/(1+exp(-act(x)))
+ * on every stored lane (unused lanes become 0.5 exactly as in the reference). */
+typedef struct {
+    int width, height, channels;
+    int in_padding, out_padding;
+    unsigned flags;
+    float leaky, clip_lo, clip_hi;
+} fyn_unary_desc;
+
+int fyn_sigmoid_create(fyn_ctx *ctx, const fyn_unary_desc *desc, fyn_op **op);
+int fyn_sigmoid_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream);
+
+int fyn_op_destroy(fyn_op *op);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FYUSENET_B200_H */
