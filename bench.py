@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the FyuseNet-on-B200 hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this backend
+    python bench.py --impl reference --gpus N --steps K ...   # CPU baseline arm (oracle port, host cores)
+
+Workload (BASELINE.json configs[1]): StyleNet 9x9, one 1524x1856 RGB frame per step, synthetic weights/images
+(the reference's data/*.dat are git-LFS stubs).  A "step" = one full forward pass of the network on one frame.
+
+  value  : frames/s with the input frame resident in HBM (network built without upload / download layers),
+           timed with CUDA events on the network's stream over exactly K steps after W warm-ups.
+  e2e    : frames/s through the reference-facing API (StyleNet9x9::forward with upload + download layers):
+           every step copies the frame from pinned host memory to the device and reads the RGBA result back.
+  N > 1  : one process per GPU (torchrun), frame-level replicas -- the path does not shard below a frame at this
+           size ("replicas only"); no data-path collective; weak scaling; time = max over ranks.
+
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "oracle"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+WIDTH, HEIGHT, KSIZE = 1524, 1856, 9
+METRIC = "stylenet9x9_1524x1856_frames_per_s"
+
+# algorithmic work per frame (SURVEY 8d / BASELINE.md section 2; fp16 storage, channels padded to 4)
+FRAME_GFLOP = 95.11
+FRAME_MB = 713.1
+
+
+def layer_algorithmic(ksize=KSIZE, w=WIDTH, h=HEIGHT):
+    """Per-layer algorithmic FLOPs and bytes (input read once + output written once + residual read once +
+    weights once; fp16 activations, fp32 RGB upload texture for conv1, channels padded to multiples of 4)."""
+    def pad4(c):
+        return 4 * ((c + 3) // 4)
+    L = {}
+    def conv(name, k, ci, co, wi, hi, wo, ho, res=False, in_bytes_per_px=None):
+        flops = 2.0 * k * k * ci * co * wo * ho
+        inb = wi * hi * (in_bytes_per_px if in_bytes_per_px else pad4(ci) * 2)
+        outb = wo * ho * pad4(co) * 2
+        wb = (co + k * k * ci * co) * 4
+        L[name] = dict(flops=flops, bytes=inb + outb + wb + (outb if res else 0))
+    conv("conv1", ksize, 3, 12, w, h, w, h, in_bytes_per_px=12)
+    conv("conv2", 3, 12, 20, w, h, w // 2, h // 2)
+    conv("conv3", 3, 20, 40, w // 2, h // 2, w // 4, h // 4)
+    for r in range(1, 6):
+        conv(f"res{r}_1", 3, 40, 40, w // 4, h // 4, w // 4, h // 4)
+        conv(f"res{r}_2", 3, 40, 40, w // 4, h // 4, w // 4, h // 4, res=True)
+    conv("deconv1", 3, 40, 20, w // 4, h // 4, w // 4, h // 4)
+    conv("deconv2", 3, 20, 12, w // 4, h // 4, w // 2, h // 2)
+    conv("deconv3", ksize, 12, 3, w // 2, h // 2, w, h)
+    L["sigmoid"] = dict(flops=0.0, bytes=2 * w * h * 4 * 2)
+    return L
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def cpu_port_frames_per_s(weights, rows: int, repeats: int = 1):
+    """Times the oracle port (oracle/fyn_oracle.c, OpenMP over all host cores, fp32) on a `rows`-high band of the
+    1524-wide frame and scales to full frames.  Returns (frames/s, seconds per sample, sample description)."""
+    import fyn_oracle as fo
+    img = fo.synthetic_image(rows, WIDTH, 0)
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        fo.stylenet_forward(weights, img, KSIZE, prec=fo.FP32)
+    dt = (time.perf_counter() - t0) / repeats
+    frac = rows / HEIGHT
+    return frac / dt, dt, f"{WIDTH}x{rows} band ({frac:.3f} frame), fp32, {repeats} run(s)"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU arm.  The reference's GL shader path cannot run on this box (no EGL/Mesa),
+    so this times the oracle port of the same path on the host cores, bounded to a band of the frame per step."""
+    if rank != 0:
+        return
+    import fyn_oracle as fo
+    fo.lib()
+    weights = fo.stylenet_synthetic_weights(KSIZE)
+    cores = os.cpu_count() or 1
+    rows = 464   # quarter frame per step keeps K+W steps within minutes
+    for _ in range(args.warmup):
+        cpu_port_frames_per_s(weights, rows)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_frames_per_s(weights, rows)
+    dt = time.perf_counter() - t0
+    fps = args.steps * (rows / HEIGHT) / dt
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "StyleNet 9x9 1524x1856 RGB frame (BASELINE configs[1])", "step": f"{WIDTH}x{rows} band per step, scaled to frames"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} x {WIDTH}x{rows} bands, OpenMP oracle port (reference GL path not runnable: no EGL/Mesa)"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import fyn_oracle as fo
+    from fyusenet_b200 import capi, hostapi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    weights = fo.stylenet_synthetic_weights(KSIZE)
+    img = fo.synthetic_image(HEIGHT, WIDTH, rank)
+
+    # ------------------------------------------------------------------ device-resident arm ("value")
+    ctx = capi.Context(local_rank)
+    net = hostapi.StyleNet(KSIZE, WIDTH, HEIGHT, upload=False, download=False, device=local_rank)
+    net.load_weights(weights)
+    tin = ctx.tensor(WIDTH, HEIGHT, 3, 0, capi.ORDER_SHALLOW, capi.F32, 1, packing=3)
+    tin.upload(img)
+    ctx.stream_sync()
+    net.set_input_tensor(tin)
+    net.setup()
+    stream = net.stream
+    for _ in range(args.warmup):
+        net.forward()
+    net.finish()
+    net.enable_timings(True)
+    ev0, ev1 = ctx.event_create(), ctx.event_create()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    n0 = ctx.launch_count()
+    lib_launch0 = _net_launches(net)
+    ctx.event_record(ev0, stream)
+    for _ in range(args.steps):
+        net.forward()
+    ctx.event_record(ev1, stream)
+    net.finish()
+    barrier()
+    clocks = sampler.stop()
+    ms = ctx.elapsed_ms(ev0, ev1)
+    launches = _net_launches(net) - lib_launch0
+    layer_ms = {l["name"]: net.layer_timing(l["number"])[0] / args.steps for l in net.layers()}
+    families = {l["name"]: l["family"] for l in net.layers()}
+    net.enable_timings(False)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.steps / (ms / 1e3)
+
+    # ------------------------------------------------------------------ end-to-end arm ("e2e")
+    net2 = hostapi.StyleNet(KSIZE, WIDTH, HEIGHT, upload=True, download=True, device=local_rank)
+    net2.load_weights(weights)
+    net2.setup()
+    inbuf = net2.input_buffer()            # pinned host memory owned by the network
+    inbuf[:] = img.reshape(-1)
+    for _ in range(args.warmup):
+        net2.forward()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        net2.forward()                      # H2D copy of the frame + all layers + D2H of the RGBA result + sync
+    net2.finish()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    barrier()
+    e2e = world * args.steps / e2e_s
+    out = net2.output_rgba()[0]
+    finite = bool(np.isfinite(out).all())
+
+    if rank == 0:
+        hbm, tf_burst, tf_sust, which = peaks()
+        alg = layer_algorithmic()
+        # dominant kernel = the layer with the largest share of the device time
+        conv_ms = {k: v for k, v in layer_ms.items() if k in alg}
+        top = max(conv_ms, key=conv_ms.get)
+        a = alg[top]
+        t_s = conv_ms[top] / 1e3
+        ai = a["flops"] / a["bytes"]
+        ridge = tf_sust * 1e12 / (hbm * 1e9)
+        if ai > ridge:
+            roof = {"bound": "tensor", "achieved": a["flops"] / t_s / 1e12, "peak": tf_sust, "unit": "TFLOP/s"}
+        else:
+            roof = {"bound": "hbm", "achieved": a["bytes"] / t_s / 1e9, "peak": hbm, "unit": "GB/s"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["traffic"] = None
+        roof["kernel"] = top
+        roof["peak_source"] = f"{which} ({'sustained' if roof['bound'] == 'tensor' else 'copy'} figure, kernel timed inside a long step)"
+        roof["ms_per_launch"] = conv_ms[top]
+        total_layer_ms = sum(layer_ms.values())
+        # whole-network roofline: sum_l max(F_l / P, B_l / BW)
+        t_lb = sum(max(v["flops"] / (tf_sust * 1e12), v["bytes"] / (hbm * 1e9)) for v in alg.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "StyleNet 9x9 (stylenet9x9 layout, synthetic He weights) 1524x1856 RGB frame, BASELINE configs[1]",
+                       "storage": "fp16 activations (reference default), fp32 accumulate", "frames_per_step": 1,
+                       "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "l2": "per-step working set 713 MB >> 126 MB L2, no explicit flush"},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(img.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "finite": finite},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "network_roofline": {"t_lower_bound_ms": 1e3 * t_lb, "frac": (1e3 * t_lb) / (ms / args.steps),
+                                 "gflop_per_frame": FRAME_GFLOP, "mb_per_frame": FRAME_MB},
+            "layers_ms": {k: round(v, 4) for k, v in layer_ms.items()},
+            "layer_kernel_family": families,
+            "layer_ms_sum": total_layer_ms,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            fps, dt, sample = cpu_port_frames_per_s(weights, 464)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": sample + f", {dt:.1f} s (reference GL path not runnable here: no EGL/Mesa)"}
+        print(json.dumps(line), flush=True)
+    net.destroy()
+    net2.destroy()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _net_launches(net) -> int:
+    """Kernel launches counted by the C-ABI library on the network's context."""
+    import ctypes as C
+    from fyusenet_b200 import capi, hostapi
+    h = hostapi.lib().fynhost_net_context(net._h)
+    n = C.c_uint64()
+    capi.check(capi.lib().fyn_launch_count(C.c_void_p(h), C.byref(n), 0))
+    return n.value
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,284 @@
+// hostapi.cpp -- small extern "C" surface over the C++ host engine, in the style of the reference's own C
+// surfaces (samples/web/stylenet.cpp:190-258, samples/android/app/src/main/cpp/styletransfer.cpp:49-140):
+// opaque handle, everything caught, int status.  Used by tests/ and bench.py (ctypes) to drive the same
+// NeuralNetwork::setup()/forward() path a C++ user of the library calls.
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include <fyusenet/fyusenet.h>
+
+#include "../samplenetworks/resnet50.h"
+#include "../samplenetworks/stylenet.h"
+
+using namespace fyusion;
+using namespace fyusion::fyusenet;
+
+namespace {
+thread_local std::string g_error;
+
+struct NetHandle {
+    enum Kind { STYLE, RESNET } kind;
+    std::unique_ptr<StyleNetBase> style;
+    std::unique_ptr<ResNet50> resnet;
+    GfxContextLink ctx;
+    NeuralNetwork *net() { return kind == STYLE ? static_cast<NeuralNetwork *>(style.get()) : resnet.get(); }
+};
+
+template <typename F>
+int guarded(F &&f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception &ex) {
+        g_error = ex.what();
+    } catch (...) {
+        g_error = "unknown exception";
+    }
+    return -1;
+}
+}  // namespace
+
+extern "C" {
+
+const char *fynhost_last_error(void) { return g_error.c_str(); }
+
+// device < 0 in the create calls builds the network object without a device context (layer tables and weight
+// offsets only; setup() then needs a GPU).
+// storage: 0 = fp16 (reference default), 1 = fp32 (HIGH_PRECISION)
+int fynhost_set_storage_precision(int fp32) {
+    return guarded([&] { gpu::setStoragePrecision(fp32 ? BufferSpec::FLOAT32 : BufferSpec::FLOAT16); });
+}
+
+void *fynhost_stylenet_create(int kernel, int width, int height, int upload, int download, int device) {
+    NetHandle *h = nullptr;
+    int rc = guarded([&] {
+        if (kernel != 3 && kernel != 9) THROW_EXCEPTION_ARGS(FynException, "StyleNet kernel must be 3 or 9");
+        std::unique_ptr<NetHandle> nh(new NetHandle());
+        nh->kind = NetHandle::STYLE;
+        if (device >= 0) nh->ctx = GfxContextManager::instance(device)->createMainContext();
+        if (kernel == 3) nh->style.reset(new StyleNet3x3(width, height, upload != 0, download != 0, nh->ctx));
+        else nh->style.reset(new StyleNet9x9(width, height, upload != 0, download != 0, nh->ctx));
+        h = nh.release();
+    });
+    return rc == 0 ? h : nullptr;
+}
+
+void *fynhost_resnet50_create(int device, int batch) {
+    NetHandle *h = nullptr;
+    int rc = guarded([&] {
+        std::unique_ptr<NetHandle> nh(new NetHandle());
+        nh->kind = NetHandle::RESNET;
+        if (device >= 0) nh->ctx = GfxContextManager::instance(device)->createMainContext();
+        nh->resnet.reset(new ResNet50(nh->ctx));
+        nh->resnet->setBatch(batch);
+        h = nh.release();
+    });
+    return rc == 0 ? h : nullptr;
+}
+
+void fynhost_net_destroy(void *handle) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    if (!h) return;
+    guarded([&] { h->net()->cleanup(); });
+    delete h;
+}
+
+size_t fynhost_net_weight_floats(void *handle) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return h->kind == NetHandle::STYLE ? h->style->weightSize() : h->resnet->weightSize();
+}
+
+// float offset of a layer's block inside the weight file, or -1
+long long fynhost_net_weight_offset(void *handle, int layerNumber) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    if (h->kind == NetHandle::STYLE) {
+        auto &m = h->style->weightOffsets();
+        auto it = m.find(layerNumber);
+        return it == m.end() ? -1 : (long long)it->second;
+    }
+    auto &m = h->resnet->weightOffsets();
+    auto it = m.find(layerNumber);
+    return it == m.end() ? -1 : (long long)it->second;
+}
+
+int fynhost_net_load_weights(void *handle, const float *weights, size_t numFloats) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] {
+        if (h->kind == NetHandle::STYLE) h->style->loadWeightsAndBiases(weights, numFloats);
+        else h->resnet->loadWeightsAndBiases(weights, numFloats);
+    });
+}
+
+int fynhost_net_set_batch(void *handle, int batch) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] { h->net()->setBatch(batch); });
+}
+
+int fynhost_net_setup(void *handle) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] { h->net()->setup(); });
+}
+
+// host float32 [batch][H][W][3]; copied into the network's pinned upload buffer
+int fynhost_net_set_input(void *handle, const float *hwc) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] {
+        if (h->kind == NetHandle::STYLE) h->style->setInputBuffer(hwc);
+        else h->resnet->setInputBuffer(hwc);
+    });
+}
+
+// pinned upload buffer of the network (created on first use and attached to the upload layer): callers that
+// write their frames straight into it avoid the extra host copy of setInputBuffer ("one deep-copy operation too
+// many", stylenet_base.cpp:150)
+float *fynhost_net_input_buffer(void *handle, size_t *numFloats) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    float *ptr = nullptr;
+    guarded([&] {
+        cpu::CPUBuffer *buf = h->kind == NetHandle::STYLE ? h->style->inputBuffer() : h->resnet->inputBuffer();
+        if (numFloats) *numFloats = buf->bytes() / sizeof(float);
+        ptr = buf->map<float>();
+        buf->unmap();
+    });
+    return ptr;
+}
+
+int fynhost_net_forward(void *handle) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] {
+        NeuralNetwork::execstate st = h->net()->forward();
+        if (st.status != Engine::EXEC_DONE && st.status != Engine::EXEC_DEFERRED)
+            THROW_EXCEPTION_ARGS(FynException, "forward() returned state %d", (int)st.status);
+    });
+}
+
+int fynhost_net_finish(void *handle) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] { h->net()->finish(); });
+}
+
+// pointer into the download layer's (pinned) CPU buffer; valid until the next forward()
+const float *fynhost_net_output(void *handle, size_t *numFloats) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    const float *ptr = nullptr;
+    guarded([&] {
+        cpu::CPUBuffer *buf = h->kind == NetHandle::STYLE ? h->style->getOutputBuffer() : h->resnet->getOutputBuffer();
+        if (!buf) THROW_EXCEPTION_ARGS(FynException, "Network has no output buffer");
+        if (numFloats) *numFloats = buf->bytes() / sizeof(float);
+        ptr = buf->map<float>();
+        buf->unmap();
+    });
+    return ptr;
+}
+
+// device-resident I/O for networks built without upload / download layers
+int fynhost_stylenet_set_input_tensor(void *handle, fyn_tensor *t) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] {
+        if (h->kind != NetHandle::STYLE) THROW_EXCEPTION_ARGS(FynException, "Not a StyleNet");
+        h->style->setInputTexture(t);
+    });
+}
+
+fyn_tensor *fynhost_stylenet_output_tensor(void *handle) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return h->kind == NetHandle::STYLE ? h->style->getOutputTexture() : nullptr;
+}
+
+fyn_ctx *fynhost_net_context(void *handle) { return static_cast<NetHandle *>(handle)->ctx.handle(); }
+void *fynhost_net_stream(void *handle) { return static_cast<NetHandle *>(handle)->ctx.stream(); }
+
+int fynhost_net_use_stream(void *handle, void *stream) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] { h->ctx.interface()->setStream(stream); });
+}
+
+int fynhost_net_num_layers(void *handle) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    int n = 0;
+    guarded([&] { n = (int)h->net()->engine()->getLayers().size(); });
+    return n;
+}
+
+// layer listing: fills number / channels / width / height / conv backend family for the idx-th layer in
+// execution order; name copied into `name` (cap bytes)
+int fynhost_net_layer_info(void *handle, int idx, int *number, int *channels, int *width, int *height, int *family,
+                           char *name, int cap) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] {
+        CompiledLayers &layers = h->net()->engine()->getLayers();
+        int i = 0;
+        for (auto it = layers.begin(); it != layers.end(); ++it, ++i) {
+            if (i != idx) continue;
+            LayerBase *l = it.second;
+            if (number) *number = l->getNumber();
+            if (channels) *channels = l->numOutputChannels();
+            std::vector<BufferSpec> outs = l->getRequiredOutputBuffers();
+            if (width) *width = outs.empty() ? 0 : outs[0].width_;
+            if (height) *height = outs.empty() ? 0 : outs[0].height_;
+            auto *conv = dynamic_cast<gpu::ConvLayerBase *>(l);
+            if (family) *family = conv ? conv->backendFamily() : 0;
+            if (name && cap > 0) snprintf(name, cap, "%s", l->getName().c_str());
+            return;
+        }
+        THROW_EXCEPTION_ARGS(FynException, "Layer index %d out of range", idx);
+    });
+}
+
+// CHW float32 result of a layer (LayerBase::writeResult / copyResult format), blocking
+int fynhost_net_copy_layer_result(void *handle, int layerNumber, float *chw, size_t capFloats) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] {
+        LayerBase *l = h->net()->engine()->getLayers()[layerNumber];
+        auto *g = dynamic_cast<gpu::GPULayerBase *>(l);
+        if (!g || !g->hasOutputTexture(0)) THROW_EXCEPTION_ARGS(FynException, "Layer %d has no device output", layerNumber);
+        fyn_tensor_desc d{};
+        FYN_ABI_CALL(fyn_tensor_get_desc(g->getOutputTexture(0), &d, nullptr));
+        size_t need = (size_t)d.batch * d.channels * d.height * d.width;
+        if (capFloats < need) THROW_EXCEPTION_ARGS(FynException, "Buffer too small (%zu < %zu)", capFloats, need);
+        g->copyResult(chw, false);
+    });
+}
+
+int fynhost_net_enable_dumps(void *handle, const char *dir) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] { h->net()->engine()->enableIntermediateOutput(dir); });
+}
+
+int fynhost_net_enable_timings(void *handle, int on) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] {
+        if (on) {
+            h->net()->engine()->resetTimings();
+            h->net()->engine()->enableTimings();
+        } else {
+            h->net()->engine()->disableTimings();
+        }
+    });
+}
+
+// accumulated device milliseconds / host microseconds of a layer since timings were enabled
+int fynhost_net_layer_timing(void *handle, int layerNumber, float *deviceMs, unsigned *hostUs) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] {
+        const auto &dev = h->net()->engine()->getDeviceTimings();
+        auto &host = h->net()->engine()->getTimings();
+        auto d = dev.find(layerNumber);
+        auto u = host.find(layerNumber);
+        if (deviceMs) *deviceMs = d == dev.end() ? 0.f : d->second;
+        if (hostUs) *hostUs = u == host.end() ? 0u : u->second;
+    });
+}
+
+size_t fynhost_net_device_bytes(void *handle) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return h->net()->bufferManager() ? h->net()->bufferManager()->estimateTextureMemory() : 0;
+}
+
+int fynhost_net_num_tensors(void *handle) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return h->net()->bufferManager() ? h->net()->bufferManager()->numTensors() : 0;
+}
+
+}  // extern "C"

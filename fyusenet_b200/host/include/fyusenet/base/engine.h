@@ -1,0 +1,68 @@
+// Engine: executes the compiled layers in ascending layer-number order on the network's CUDA stream.
+// Reference: fyusenet/base/engine.cpp:78-158 (setup/cleanup), :247-335 (finish/forwardLayers), :386-683 (execute),
+// :208-233 (timings), :174-181,434-437,602-604 (intermediate dumps).  The synchronous path ends with a stream
+// synchronise after the download layer (the reference's blocking glReadPixels); optional CUDA-graph replay
+// removes per-layer launch latency for static networks.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../gpu/gfxcontextlink.h"
+#include "compiledlayers.h"
+
+namespace fyusion {
+namespace fyusenet {
+
+class NeuralNetwork;
+
+class Engine : public GfxContextTracker {
+ public:
+    enum execstate { EXEC_DONE = 0, EXEC_DEFERRED, EXEC_STOPPED, EXEC_ERROR };
+
+    explicit Engine(const GfxContextLink &ctx = GfxContextLink(), bool async = false);
+    ~Engine();
+    void setup(NeuralNetwork *net);
+    void cleanup();
+    execstate forwardLayers();
+    execstate finish();
+    CompiledLayers &getLayers() { return layers_; }
+    uint64_t nextSequenceNo() const { return sequenceNo_; }
+    uint64_t lastSequenceNo() const { return sequenceNo_ - 1; }
+
+    // host-side microseconds per layer number around each forward() (issue time, not device time: :201-204),
+    // plus device milliseconds from CUDA events when enabled
+    void enableTimings() { timings_ = true; }
+    void disableTimings() { timings_ = false; }
+    void resetTimings();
+    const std::unordered_map<int, uint32_t> &getTimings() const { return timingData_; }
+    const std::unordered_map<int, float> &getDeviceTimings() { collectTimings(true); return deviceTimingData_; }
+    int timedRuns() const { return runs_; }
+    // <dir>/<layername>_<seq>.bin dumps, CHW float32 without padding
+    void enableIntermediateOutput(const std::string &outputDir) { outputDir_ = outputDir; writeResults_ = true; }
+    void disableIntermediateOutput() { writeResults_ = false; }
+    // capture the layer sequence into a CUDA graph on the next forward and replay it afterwards
+    void enableGraph(bool on) { useGraph_ = on; }
+
+ private:
+    execstate execute(uint64_t sequence);
+    void collectTimings(bool sync);
+    struct EventPair { int layer; void *start; void *stop; };
+    std::vector<EventPair> pendingEvents_;
+    std::vector<void *> freeEvents_;
+    CompiledLayers layers_;
+    uint64_t sequenceNo_ = 1;
+    bool setup_ = false;
+    bool async_ = false;
+    bool timings_ = false;
+    bool writeResults_ = false;
+    bool useGraph_ = false;
+    std::string outputDir_;
+    std::unordered_map<int, uint32_t> timingData_;
+    std::unordered_map<int, float> deviceTimingData_;
+    int runs_ = 0;
+};
+
+}  // namespace fyusenet
+}  // namespace fyusion

@@ -1,0 +1,168 @@
+// Concrete device layers of the CUDA backend and the factory backend that creates them.
+// One class per reference layer family; all arithmetic happens in libfyusenet_b200.so behind the C ABI.
+//   ConvLayer        <- vanilla::ConvLayer1x1 / ConvLayerNxN / FractionalConvLayerNxN (gpu/vanilla/*),
+//                       deep::DeepConvLayer1x1 / DeepConvLayerNxN / DeepGEMMLayer (gpu/deep/*)
+//   PoolingLayer     <- deep::DeepMaxPoolLayer / DeepAvgPoolLayer, MaxPoolLayer / AvgPoolLayer
+//   BatchNormLayer   <- BatchNormLayer, deep::DeepBatchNormLayer
+//   SigmoidLayer     <- SigmoidLayer
+//   UploadLayer      <- UploadLayer (gpu/uploadlayer.cpp)
+//   DownloadLayer    <- DownloadLayer, deep::DeepDownloadLayer (gpu/downloadlayer.cpp, deep/deepdownloadlayer.cpp)
+#pragma once
+#include "../base/batchnorminterface.h"
+#include "../base/convlayerinterface.h"
+#include "../base/layerfactory.h"
+#include "../cpu/cpubuffer.h"
+#include "gpulayerbase.h"
+
+namespace fyusion {
+namespace fyusenet {
+namespace gpu {
+
+class ConvLayerBase : public GPULayerBase, public ConvLayerInterface {
+ public:
+    ConvLayerBase(const ConvLayerBuilder &builder, int layerNumber, bool fractional);
+    ConvLayerBase(const GPULayerBuilder &builder, int layerNumber);  // GEMM: 1x1 conv on 1x1 spatial
+    ~ConvLayerBase() override;
+    void setup() override;
+    void cleanup() override;
+    void forward(uint64_t sequence = 0) override;
+    std::vector<BufferSpec> getRequiredInputBuffers() const override;
+    std::vector<BufferSpec> getRequiredOutputBuffers() const override;
+    void loadWeightsAndBiases(const float *biasAndWeights, size_t offset = 0) override;
+    int kernel() const { return desc_.kernel; }
+    int backendFamily() const { return op_ ? fyn_conv2d_backend(op_) : 0; }  // 1 direct, 2 tcgen05
+    const fyn_conv_desc &descriptor() const { return desc_; }
+
+ protected:
+    void init(int kernel, int dilation, float sourceStep, bool fractional);
+    fyn_conv_desc desc_{};
+    fyn_op *op_ = nullptr;
+    std::vector<float> pendingWeights_;  // weights handed over before setup()
+    int outWidth_ = 0, outHeight_ = 0;
+};
+
+namespace vanilla {
+using ConvLayerNxN = gpu::ConvLayerBase;
+using ConvLayer1x1 = gpu::ConvLayerBase;
+using FractionalConvLayerNxN = gpu::ConvLayerBase;
+}  // namespace vanilla
+
+class PoolingLayer : public GPULayerBase {
+ public:
+    PoolingLayer(const PoolLayerBuilder &builder, int layerNumber);
+    void setup() override;
+    void cleanup() override;
+    void forward(uint64_t sequence = 0) override;
+    std::vector<BufferSpec> getRequiredInputBuffers() const override;
+    std::vector<BufferSpec> getRequiredOutputBuffers() const override;
+
+ protected:
+    fyn_pool_desc desc_{};
+    fyn_op *op_ = nullptr;
+    int outWidth_ = 0, outHeight_ = 0;
+};
+
+class BatchNormLayer : public GPULayerBase, public BatchNormInterface {
+ public:
+    BatchNormLayer(const GPULayerBuilder &builder, int layerNumber);
+    void setup() override;
+    void cleanup() override;
+    void forward(uint64_t sequence = 0) override;
+    std::vector<BufferSpec> getRequiredInputBuffers() const override;
+    std::vector<BufferSpec> getRequiredOutputBuffers() const override;
+    void loadScaleAndBias(const float *scaleAndBias, size_t sbOffset = 0) override;
+
+ protected:
+    fyn_bn_desc desc_{};
+    fyn_op *op_ = nullptr;
+    std::vector<float> params_;
+};
+
+class SigmoidLayer : public GPULayerBase {
+ public:
+    SigmoidLayer(const GPULayerBuilder &builder, int layerNumber);
+    void setup() override;
+    void cleanup() override;
+    void forward(uint64_t sequence = 0) override;
+    std::vector<BufferSpec> getRequiredInputBuffers() const override;
+    std::vector<BufferSpec> getRequiredOutputBuffers() const override;
+
+ protected:
+    fyn_unary_desc desc_{};
+    fyn_op *op_ = nullptr;
+};
+
+class UploadLayer : public GPULayerBase, public cpu::CPULayerInterface {
+ public:
+    UploadLayer(const UpDownLayerBuilder &builder, int layerNumber);
+    void setup() override { valid_ = true; }
+    void forward(uint64_t sequence = 0) override;
+    std::vector<BufferSpec> getRequiredInputBuffers() const override;
+    std::vector<BufferSpec> getRequiredOutputBuffers() const override;
+    void setInputBuffer(CPUBuffer *buf, int port) override { (void)port; input_ = buf; }
+    CPUBuffer *getInputBuffer(int = 0) const override { return input_; }
+    void addOutputBuffer(CPUBuffer *, int = 0) override { THROW_EXCEPTION_ARGS(FynException, "Upload layers have no CPU output"); }
+    CPUBuffer *getOutputBuffer(int = 0) const override { return nullptr; }
+    bool hasOutputBuffer(int = 0) const override { return false; }
+    void clearOutputBuffers(int = -1) override {}
+    void clearInputBuffers(int = -1) override { input_ = nullptr; }
+    bool isAsync() const { return async_; }
+
+ protected:
+    CPUBuffer *input_ = nullptr;
+    bool async_ = false;
+    BufferSpec::dtype dataType_ = BufferSpec::FLOAT32;
+    UpDownLayerBuilder::callback_t callback_;
+};
+
+class DownloadLayer : public GPULayerBase, public cpu::CPULayerInterface {
+ public:
+    DownloadLayer(const UpDownLayerBuilder &builder, int layerNumber);
+    void setup() override { valid_ = true; }
+    void forward(uint64_t sequence = 0) override;
+    std::vector<BufferSpec> getRequiredInputBuffers() const override;
+    std::vector<BufferSpec> getRequiredOutputBuffers() const override;
+    void setInputBuffer(CPUBuffer *, int) override { THROW_EXCEPTION_ARGS(FynException, "Download layers have no CPU input"); }
+    CPUBuffer *getInputBuffer(int = 0) const override { return nullptr; }
+    void addOutputBuffer(CPUBuffer *buf, int = 0) override { output_ = buf; }
+    void updateOutputBuffer(CPUBuffer *buf, int = 0) { output_ = buf; }
+    CPUBuffer *getOutputBuffer(int = 0) const override { return output_; }
+    bool hasOutputBuffer(int = 0) const override { return output_ != nullptr; }
+    void clearOutputBuffers(int = -1) override { output_ = nullptr; }
+    void clearInputBuffers(int = -1) override {}
+    void writeResult(const char *fileName, bool includePadding = false) override;
+    bool isAsync() const { return async_; }
+    // the engine synchronises the stream after the last layer unless the download is asynchronous
+    bool needsSync() const { return !async_; }
+
+ protected:
+    CPUBuffer *output_ = nullptr;
+    bool async_ = false;
+    UpDownLayerBuilder::callback_t callback_;
+};
+
+namespace deep {
+using DeepDownloadLayer = gpu::DownloadLayer;
+using DeepConvLayer1x1 = gpu::ConvLayerBase;
+using DeepConvLayerNxN = gpu::ConvLayerBase;
+using DeepGEMMLayer = gpu::ConvLayerBase;
+using DeepMaxPoolLayer = gpu::PoolingLayer;
+using DeepAvgPoolLayer = gpu::PoolingLayer;
+using DeepBatchNormLayer = gpu::BatchNormLayer;
+}  // namespace deep
+
+// The plugin: creates CUDA layers behind LayerFactoryBackend::createLayer.
+// Dispatch restated from GPULayerFactoryBackend::createLayer (gpu/gpulayerfactory.cpp:112-184,358-396,447-457).
+class CUDALayerFactoryBackend : public LayerFactoryBackend {
+ public:
+    explicit CUDALayerFactoryBackend(GfxContextLink ctx = GfxContextLink()) : context_(ctx) {}
+    std::string getName() const override { return "CUDA-sm100a"; }
+    LayerBase *createLayer(LayerType type, LayerBuilder *builder, int layerNumber) override;
+
+ private:
+    GfxContextLink context_;
+};
+
+}  // namespace gpu
+}  // namespace fyusenet
+}  // namespace fyusion

@@ -1,0 +1,350 @@
+// Device layer classes: thin state holders that translate builder parameters into C-ABI descriptors and
+// enqueue the ops on the network stream.
+#include <cstdlib>
+#include <cstring>
+
+#include "fyusenet/gpu/cudalayers.h"
+
+namespace fyusion {
+namespace fyusenet {
+namespace gpu {
+
+static int envInt(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GPULayerBase
+// ------------------------------------------------------------------------------------------------
+int GPULayerBase::outputBatch() const {
+    fyn_tensor_desc d{};
+    FYN_ABI_CALL(fyn_tensor_get_desc(out(), &d, nullptr));
+    return d.batch;
+}
+
+void GPULayerBase::copyResult(float *memory, bool includePadding) {
+    if (includePadding) THROW_EXCEPTION_ARGS(FynException, "Padded result copies are not supported");
+    FYN_ABI_CALL(fyn_stream_sync(context_.handle(), context_.stream()));
+    FYN_ABI_CALL(fyn_tensor_read_chw_f32(out(), memory));
+}
+
+void GPULayerBase::writeResult(const char *fileName, bool includePadding) {
+    fyn_tensor_desc d{};
+    FYN_ABI_CALL(fyn_tensor_get_desc(out(), &d, nullptr));
+    std::vector<float> data((size_t)d.batch * d.channels * d.height * d.width);
+    copyResult(data.data(), includePadding);
+    FILE *f = fopen(fileName, "wb");
+    if (!f) THROW_EXCEPTION_ARGS(FynException, "Cannot open file %s for writing", fileName);
+    fwrite(data.data(), sizeof(float), data.size(), f);
+    fclose(f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ConvLayerBase
+// ------------------------------------------------------------------------------------------------
+void ConvLayerBase::init(int kernel, int dilation, float sourceStep, bool fractional) {
+    desc_.width = width_;
+    desc_.height = height_;
+    desc_.in_channels = inputChannels_;
+    desc_.out_channels = outputChannels_;
+    desc_.kernel = kernel;
+    desc_.dilation = dilation;
+    desc_.in_padding = inputPadding_;
+    desc_.out_padding = outputPadding_;
+    desc_.res_padding = residualPadding_;
+    desc_.flags = flags_ & (LayerFlags::RESIDUAL_INPUT | LayerFlags::RELU_ON_RESIDUAL | LayerFlags::BATCHNORM_ON_RESIDUAL |
+                            LayerFlags::POST_BATCHNORM | LayerFlags::DEEP | LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP);
+    desc_.leaky = leakyReLU_;
+    desc_.clip_lo = lowClip_;
+    desc_.clip_hi = highClip_;
+    desc_.source_step = sourceStep;
+    desc_.fractional = fractional ? 1 : 0;
+    desc_.quirks = envInt("FYN_QUIRKS", FYN_QUIRKS_REFERENCE);
+    desc_.backend = envInt("FYN_CONV_BACKEND", 0);
+    FYN_ABI_CALL(fyn_conv2d_output_size(&desc_, &outWidth_, &outHeight_));
+    viewport_[0] = outWidth_ + 2 * outputPadding_;
+    viewport_[1] = outHeight_ + 2 * outputPadding_;
+}
+
+ConvLayerBase::ConvLayerBase(const ConvLayerBuilder &builder, int layerNumber, bool fractional) : GPULayerBase(builder, layerNumber) {
+    if (builder.downsample_[0] != builder.downsample_[1])
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: anisotropic downsampling not supported", name_.c_str());
+    if (builder.dilation_[0] != builder.dilation_[1])
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: anisotropic dilation not supported", name_.c_str());
+    if (builder.kernel_ < 1 || !(builder.kernel_ & 1))
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: kernel size %d not supported", name_.c_str(), builder.kernel_);
+    if (fractional && builder.dilation_[0] > 1)
+        THROW_EXCEPTION_ARGS(FynException, "Dilations not supported for fractional convolution");
+    desc_.downsample = builder.downsample_[0];
+    init(builder.kernel_, builder.dilation_[0], builder.sourceStep_, fractional);
+}
+
+ConvLayerBase::ConvLayerBase(const GPULayerBuilder &builder, int layerNumber) : GPULayerBase(builder, layerNumber) {
+    // GEMM: generalized matrix/vector product run as a 1x1 convolution (reference: gpu/deep/deepgemmlayer.cpp:66-140)
+    desc_.downsample = 1;
+    init(1, 1, 1.f, false);
+}
+
+ConvLayerBase::~ConvLayerBase() {}
+
+std::vector<BufferSpec> ConvLayerBase::getRequiredInputBuffers() const {
+    std::vector<BufferSpec> r;
+    BufferSpec in0(0, width_, height_, inputChannels_, inputPadding_, order(), storagePrecision(), BufferSpec::CONVOLUTION_SOURCE);
+    // inputs with fewer than 4 channels may come straight from an upload texture (RGB32F):
+    // reference gpu/vanilla/convlayerbase_vanilla.cpp:205-210
+    if (inputChannels_ < PIXEL_PACKING) in0.anyType();
+    r.push_back(in0);
+    if (flags_ & LayerFlags::RESIDUAL_INPUT)
+        r.push_back(BufferSpec(1, outWidth_, outHeight_, outputChannels_, residualPadding_, order(), storagePrecision(), BufferSpec::RESIDUAL_SOURCE));
+    return r;
+}
+
+std::vector<BufferSpec> ConvLayerBase::getRequiredOutputBuffers() const {
+    return {BufferSpec(0, outWidth_, outHeight_, outputChannels_, outputPadding_, order(), storagePrecision(), BufferSpec::CONVOLUTION_DEST)};
+}
+
+void ConvLayerBase::loadWeightsAndBiases(const float *biasAndWeights, size_t offset) {
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    if (!biasAndWeights) THROW_EXCEPTION_ARGS(FynException, "Layer %s: null weight pointer", name_.c_str());
+    size_t n = (size_t)outputChannels_ + (size_t)desc_.kernel * desc_.kernel * inputChannels_ * outputChannels_;
+    if (flags_ & LayerFlags::POST_BATCHNORM) n += 2 * (size_t)outputChannels_;
+    const float *src = biasAndWeights + offset;
+    if (op_) {
+        FYN_ABI_CALL(fyn_conv2d_load_weights(op_, src));  // hot swap (reference: stylenet9x9.cpp:87-95)
+    } else {
+        pendingWeights_.assign(src, src + n);              // weights are only read during the call
+    }
+}
+
+void ConvLayerBase::setup() {
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    if (pendingWeights_.empty())
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: loadWeightsAndBiases() must be called before setup()", name_.c_str());
+    FYN_ABI_CALL(fyn_conv2d_create(context_.handle(), &desc_, pendingWeights_.data(), &op_));
+    pendingWeights_.clear();
+    pendingWeights_.shrink_to_fit();
+    valid_ = true;
+}
+
+void ConvLayerBase::cleanup() {
+    if (op_) fyn_op_destroy(op_);
+    op_ = nullptr;
+    GPULayerBase::cleanup();
+}
+
+void ConvLayerBase::forward(uint64_t) {
+    if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    TensorHandle res = nullptr;
+    if (flags_ & LayerFlags::RESIDUAL_INPUT) {
+        if (residuals_.empty() || !residuals_[0])
+            THROW_EXCEPTION_ARGS(FynException, "Residual flag configured, but no such texture found.");
+        res = residuals_[0];
+    }
+    FYN_ABI_CALL(fyn_conv2d_run(op_, in(0), res, out(), context_.stream()));
+}
+
+// ------------------------------------------------------------------------------------------------
+// PoolingLayer
+// ------------------------------------------------------------------------------------------------
+PoolingLayer::PoolingLayer(const PoolLayerBuilder &b, int layerNumber) : GPULayerBase(b, layerNumber) {
+    desc_.width = width_;
+    desc_.height = height_;
+    desc_.channels = inputChannels_;
+    desc_.global = b.global_ ? 1 : 0;
+    // global pooling: window = stride = spatial size (reference: gpu/deep/deeppoolinglayer.cpp:38-54)
+    desc_.pool_x = b.global_ ? width_ : b.poolsize_[0];
+    desc_.pool_y = b.global_ ? height_ : b.poolsize_[1];
+    if (!b.global_ && b.downsample_[0] != b.downsample_[1])
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: anisotropic pooling stride not supported", name_.c_str());
+    desc_.downsample = b.downsample_[0];
+    desc_.in_padding = inputPadding_;
+    desc_.out_padding = outputPadding_;
+    desc_.is_max = (b.operation_ == PoolLayerBuilder::POOL_MAX) ? 1 : 0;
+    desc_.flags = flags_ & (LayerFlags::DEEP | LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP);
+    desc_.leaky = leakyReLU_;
+    desc_.clip_lo = lowClip_;
+    desc_.clip_hi = highClip_;
+    desc_.quirks = envInt("FYN_QUIRKS", FYN_QUIRKS_REFERENCE);
+    outWidth_ = b.global_ ? 1 : width_ / desc_.downsample;
+    outHeight_ = b.global_ ? 1 : height_ / desc_.downsample;
+    viewport_[0] = outWidth_ + 2 * outputPadding_;
+    viewport_[1] = outHeight_ + 2 * outputPadding_;
+}
+
+std::vector<BufferSpec> PoolingLayer::getRequiredInputBuffers() const {
+    return {BufferSpec(0, width_, height_, inputChannels_, inputPadding_, order(), storagePrecision(), BufferSpec::FUNCTION_SOURCE)};
+}
+std::vector<BufferSpec> PoolingLayer::getRequiredOutputBuffers() const {
+    return {BufferSpec(0, outWidth_, outHeight_, outputChannels_, outputPadding_, order(), storagePrecision(), BufferSpec::FUNCTION_DEST)};
+}
+void PoolingLayer::setup() {
+    FYN_ABI_CALL(fyn_pool2d_create(context_.handle(), &desc_, &op_));
+    valid_ = true;
+}
+void PoolingLayer::cleanup() {
+    if (op_) fyn_op_destroy(op_);
+    op_ = nullptr;
+    GPULayerBase::cleanup();
+}
+void PoolingLayer::forward(uint64_t) {
+    if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    FYN_ABI_CALL(fyn_pool2d_run(op_, in(0), out(), context_.stream()));
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNormLayer
+// ------------------------------------------------------------------------------------------------
+BatchNormLayer::BatchNormLayer(const GPULayerBuilder &b, int layerNumber) : GPULayerBase(b, layerNumber) {
+    desc_.width = width_;
+    desc_.height = height_;
+    desc_.channels = inputChannels_;
+    desc_.in_padding = inputPadding_;
+    desc_.out_padding = outputPadding_;
+    desc_.flags = flags_ & (LayerFlags::DEEP | LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP);
+    desc_.leaky = leakyReLU_;
+    desc_.clip_lo = lowClip_;
+    desc_.clip_hi = highClip_;
+}
+std::vector<BufferSpec> BatchNormLayer::getRequiredInputBuffers() const {
+    BufferSpec s(0, width_, height_, inputChannels_, inputPadding_, order(), storagePrecision(), BufferSpec::FUNCTION_SOURCE);
+    if (inputChannels_ < PIXEL_PACKING) s.anyType();
+    return {s};
+}
+std::vector<BufferSpec> BatchNormLayer::getRequiredOutputBuffers() const {
+    return {BufferSpec(0, width_, height_, outputChannels_, outputPadding_, order(), storagePrecision(), BufferSpec::FUNCTION_DEST)};
+}
+void BatchNormLayer::loadScaleAndBias(const float *scaleAndBias, size_t sbOffset) {
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    if (!scaleAndBias) THROW_EXCEPTION_ARGS(FynException, "Layer %s: null parameter pointer", name_.c_str());
+    params_.assign(scaleAndBias + sbOffset, scaleAndBias + sbOffset + 2 * (size_t)outputChannels_);
+    if (op_) FYN_ABI_CALL(fyn_batchnorm_load(op_, params_.data()));
+}
+void BatchNormLayer::setup() {
+    if (params_.empty()) THROW_EXCEPTION_ARGS(FynException, "Layer %s: loadScaleAndBias() must be called before setup()", name_.c_str());
+    FYN_ABI_CALL(fyn_batchnorm_create(context_.handle(), &desc_, params_.data(), &op_));
+    valid_ = true;
+}
+void BatchNormLayer::cleanup() {
+    if (op_) fyn_op_destroy(op_);
+    op_ = nullptr;
+    GPULayerBase::cleanup();
+}
+void BatchNormLayer::forward(uint64_t) {
+    if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    FYN_ABI_CALL(fyn_batchnorm_run(op_, in(0), out(), context_.stream()));
+}
+
+// ------------------------------------------------------------------------------------------------
+// SigmoidLayer
+// ------------------------------------------------------------------------------------------------
+SigmoidLayer::SigmoidLayer(const GPULayerBuilder &b, int layerNumber) : GPULayerBase(b, layerNumber) {
+    desc_.width = width_;
+    desc_.height = height_;
+    desc_.channels = inputChannels_;
+    desc_.in_padding = inputPadding_;
+    desc_.out_padding = outputPadding_;
+    desc_.flags = flags_ & (LayerFlags::DEEP | LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP);
+    desc_.leaky = leakyReLU_;
+    desc_.clip_lo = lowClip_;
+    desc_.clip_hi = highClip_;
+}
+std::vector<BufferSpec> SigmoidLayer::getRequiredInputBuffers() const {
+    return {BufferSpec(0, width_, height_, inputChannels_, inputPadding_, order(), storagePrecision(), BufferSpec::FUNCTION_SOURCE)};
+}
+std::vector<BufferSpec> SigmoidLayer::getRequiredOutputBuffers() const {
+    return {BufferSpec(0, width_, height_, outputChannels_, outputPadding_, order(), storagePrecision(), BufferSpec::FUNCTION_DEST)};
+}
+void SigmoidLayer::setup() {
+    FYN_ABI_CALL(fyn_sigmoid_create(context_.handle(), &desc_, &op_));
+    valid_ = true;
+}
+void SigmoidLayer::cleanup() {
+    if (op_) fyn_op_destroy(op_);
+    op_ = nullptr;
+    GPULayerBase::cleanup();
+}
+void SigmoidLayer::forward(uint64_t) {
+    if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    FYN_ABI_CALL(fyn_sigmoid_run(op_, in(0), out(), context_.stream()));
+}
+
+// ------------------------------------------------------------------------------------------------
+// UploadLayer: host float32 [H][W][C] -> C-channel float32 texture, verbatim (gpu/uploadlayer.cpp:360-380)
+// ------------------------------------------------------------------------------------------------
+UploadLayer::UploadLayer(const UpDownLayerBuilder &b, int layerNumber)
+    : GPULayerBase(b, layerNumber), async_(b.async_), dataType_(b.dataType_), callback_(b.callback_) {
+    if (inputChannels_ > PIXEL_PACKING)
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: upload supports at most %d channels", name_.c_str(), PIXEL_PACKING);
+}
+std::vector<BufferSpec> UploadLayer::getRequiredInputBuffers() const {
+    return {BufferSpec(0, width_, height_, inputChannels_, 0, BufferSpec::order::GPU_SHALLOW, BufferSpec::FLOAT32, BufferSpec::CPU_SOURCE)
+                .device(BufferSpec::COMP_STOR_CPU)};
+}
+std::vector<BufferSpec> UploadLayer::getRequiredOutputBuffers() const {
+    // RGB32F-style texture: packing == channel count, float32, no padding
+    return {BufferSpec(0, width_, height_, outputChannels_, outputPadding_, order(), BufferSpec::FLOAT32, BufferSpec::GPU_DEST)
+                .packing(outputPadding_ == 0 ? outputChannels_ : 4).async(async_).multi(async_ ? 2 : 1)};
+}
+void UploadLayer::forward(uint64_t sequence) {
+    if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    if (!input_) THROW_EXCEPTION_ARGS(FynException, "No input buffer set for upload layer %s", name_.c_str());
+    const float *src = input_->map<float>();
+    input_->unmap();
+    if (callback_) callback_(sequence, input_, AsyncLayer::UPLOAD_COMMENCED);
+    FYN_ABI_CALL(fyn_upload_f32_async(out(), src, context_.stream()));
+    if (callback_) callback_(sequence, input_, AsyncLayer::UPLOAD_DONE);
+}
+
+// ------------------------------------------------------------------------------------------------
+// DownloadLayer: tensor -> host float32 in texel order (gpu/downloadlayer.cpp:112-131,257-283)
+// ------------------------------------------------------------------------------------------------
+DownloadLayer::DownloadLayer(const UpDownLayerBuilder &b, int layerNumber)
+    : GPULayerBase(b, layerNumber), async_(b.async_), callback_(b.callback_) {
+    if (flags_ & LayerFlags::PRE_ACT_MASK) THROW_EXCEPTION_ARGS(FynException, "Activation on download not implemented yet");
+    if (flags_ & LayerFlags::RESIDUAL_INPUT) THROW_EXCEPTION_ARGS(FynException, "Residual add on download not implemented yet");
+}
+std::vector<BufferSpec> DownloadLayer::getRequiredInputBuffers() const {
+    return {BufferSpec(0, width_, height_, inputChannels_, inputPadding_, order(), storagePrecision(), BufferSpec::FUNCTION_SOURCE)};
+}
+std::vector<BufferSpec> DownloadLayer::getRequiredOutputBuffers() const {
+    return {BufferSpec(0, width_, height_, outputChannels_, inputPadding_, order(), BufferSpec::FLOAT32, BufferSpec::CPU_DEST)
+                .device(BufferSpec::COMP_STOR_CPU)};
+}
+void DownloadLayer::forward(uint64_t sequence) {
+    if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    if (!output_) THROW_EXCEPTION_ARGS(FynException, "No output buffer set for download layer %s", name_.c_str());
+    size_t need = fyn_download_f32_elems(in(0)) * sizeof(float);
+    if (output_->bytes() < need)
+        THROW_EXCEPTION_ARGS(FynException, "Download buffer too small (%zu < %zu bytes)", output_->bytes(), need);
+    float *dst = output_->map<float>();
+    output_->unmap();
+    if (callback_) callback_(sequence, output_, AsyncLayer::DOWNLOAD_COMMENCED);
+    FYN_ABI_CALL(fyn_download_f32_async(in(0), dst, context_.stream()));
+    if (!async_) {
+        // synchronous path blocks like the reference's glReadPixels + readFromPBO
+        FYN_ABI_CALL(fyn_stream_sync(context_.handle(), context_.stream()));
+        output_->setSequence(sequence);
+        if (callback_) callback_(sequence, output_, AsyncLayer::DOWNLOAD_DONE);
+    }
+}
+void DownloadLayer::writeResult(const char *fileName, bool) {
+    if (!output_) return;
+    CPUBuffer *cw = output_->toChannelWise();
+    FILE *f = fopen(fileName, "wb");
+    if (f) {
+        fwrite(cw->raw(), 1, cw->bytes(), f);
+        fclose(f);
+    }
+    delete cw;
+}
+
+}  // namespace gpu
+}  // namespace fyusenet
+}  // namespace fyusion

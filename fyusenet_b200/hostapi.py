@@ -1,0 +1,203 @@
+"""ctypes binding of the C++ host engine's C surface (fyusenet_b200/host/capi/hostapi.cpp).
+
+The host engine mirrors the reference's C++ API (LayerBuilder / LayerFactory / NeuralNetwork / BufferManager /
+the StyleNet and ResNet-50 sample networks); this module lets Python (tests, bench.py) drive exactly the
+call sequence of samples/desktop/stylenet.cpp:148-187 / resnet.cpp:138-160:
+loadWeightsAndBiases -> setup -> setInputBuffer -> forward -> getOutputBuffer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import capi
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfyusenet_host.so"
+_lib = None
+
+
+class HostError(RuntimeError):
+    """A FynException caught at the C surface."""
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        capi.lib()  # libfyusenet_b200.so first (rpath $ORIGIN resolves it as well)
+        if not LIB_PATH.exists():
+            raise ImportError(f"{LIB_PATH} is missing: run __graft_entry__.build()")
+        L = C.CDLL(str(LIB_PATH))
+        L.fynhost_last_error.restype = C.c_char_p
+        L.fynhost_stylenet_create.restype = C.c_void_p
+        L.fynhost_resnet50_create.restype = C.c_void_p
+        L.fynhost_net_weight_floats.restype = C.c_size_t
+        L.fynhost_net_weight_offset.restype = C.c_longlong
+        L.fynhost_net_output.restype = C.POINTER(C.c_float)
+        L.fynhost_net_input_buffer.restype = C.POINTER(C.c_float)
+        L.fynhost_stylenet_output_tensor.restype = C.c_void_p
+        L.fynhost_net_context.restype = C.c_void_p
+        L.fynhost_net_stream.restype = C.c_void_p
+        L.fynhost_net_device_bytes.restype = C.c_size_t
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise HostError(lib().fynhost_last_error().decode(errors="replace"))
+
+
+def selftest():
+    buf = C.create_string_buffer(16384)
+    n = lib().fynhost_selftest(buf, len(buf))
+    return n, buf.value.decode()
+
+
+def set_storage_precision(fp32: bool):
+    _check(lib().fynhost_set_storage_precision(int(bool(fp32))))
+
+
+class Network:
+    """Common driver for the sample networks."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise HostError(lib().fynhost_last_error().decode(errors="replace"))
+        self._h = C.c_void_p(handle)
+        self._setup = False
+
+    # -- weights -------------------------------------------------------------------------------
+    @property
+    def weight_floats(self) -> int:
+        return lib().fynhost_net_weight_floats(self._h)
+
+    def weight_offset(self, layer_number: int) -> int:
+        return lib().fynhost_net_weight_offset(self._h, int(layer_number))
+
+    def load_weights(self, w):
+        w = np.ascontiguousarray(w, np.float32)
+        _check(lib().fynhost_net_load_weights(self._h, w.ctypes.data_as(C.POINTER(C.c_float)), C.c_size_t(w.size)))
+
+    # -- lifecycle -----------------------------------------------------------------------------
+    def set_batch(self, n: int):
+        _check(lib().fynhost_net_set_batch(self._h, int(n)))
+
+    def setup(self):
+        _check(lib().fynhost_net_setup(self._h))
+        self._setup = True
+
+    def set_input(self, hwc):
+        a = np.ascontiguousarray(hwc, np.float32)
+        _check(lib().fynhost_net_set_input(self._h, a.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def input_buffer(self) -> np.ndarray:
+        """The network's pinned upload buffer as a numpy view: fill it in place, then forward()."""
+        n = C.c_size_t()
+        p = lib().fynhost_net_input_buffer(self._h, C.byref(n))
+        if not p:
+            raise HostError(lib().fynhost_last_error().decode(errors="replace"))
+        return np.ctypeslib.as_array(p, shape=(n.value,))
+
+    def forward(self):
+        _check(lib().fynhost_net_forward(self._h))
+
+    def finish(self):
+        _check(lib().fynhost_net_finish(self._h))
+
+    def output(self) -> np.ndarray:
+        n = C.c_size_t()
+        p = lib().fynhost_net_output(self._h, C.byref(n))
+        if not p:
+            raise HostError(lib().fynhost_last_error().decode(errors="replace"))
+        return np.ctypeslib.as_array(p, shape=(n.value,))
+
+    def use_stream(self, stream):
+        _check(lib().fynhost_net_use_stream(self._h, capi._s(stream)))
+
+    @property
+    def stream(self):
+        return C.c_void_p(lib().fynhost_net_stream(self._h))
+
+    # -- introspection -------------------------------------------------------------------------
+    def layers(self):
+        out = []
+        for i in range(lib().fynhost_net_num_layers(self._h)):
+            no, ch, w, h, fam = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+            name = C.create_string_buffer(128)
+            _check(lib().fynhost_net_layer_info(self._h, i, C.byref(no), C.byref(ch), C.byref(w), C.byref(h), C.byref(fam), name, 128))
+            out.append(dict(number=no.value, name=name.value.decode(), channels=ch.value, width=w.value, height=h.value,
+                            family=fam.value))
+        return out
+
+    def layer_result(self, number: int, shape) -> np.ndarray:
+        out = np.zeros(shape, np.float32)
+        _check(lib().fynhost_net_copy_layer_result(self._h, int(number), out.ctypes.data_as(C.POINTER(C.c_float)),
+                                                   C.c_size_t(out.size)))
+        return out
+
+    def enable_dumps(self, directory: str):
+        _check(lib().fynhost_net_enable_dumps(self._h, str(directory).encode()))
+
+    def enable_timings(self, on=True):
+        _check(lib().fynhost_net_enable_timings(self._h, int(on)))
+
+    def layer_timing(self, number: int):
+        ms, us = C.c_float(), C.c_uint()
+        _check(lib().fynhost_net_layer_timing(self._h, int(number), C.byref(ms), C.byref(us)))
+        return ms.value, us.value
+
+    @property
+    def device_bytes(self) -> int:
+        return lib().fynhost_net_device_bytes(self._h)
+
+    @property
+    def num_tensors(self) -> int:
+        return lib().fynhost_net_num_tensors(self._h)
+
+    def destroy(self):
+        if self._h:
+            lib().fynhost_net_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class StyleNet(Network):
+    def __init__(self, kernel: int, width: int, height: int, upload=True, download=True, device=0):
+        super().__init__(lib().fynhost_stylenet_create(int(kernel), int(width), int(height), int(upload), int(download), int(device)))
+        self.kernel, self.width, self.height = kernel, width, height
+
+    def set_input_tensor(self, tensor: capi.Tensor):
+        _check(lib().fynhost_stylenet_set_input_tensor(self._h, tensor._h))
+
+    def output_rgba(self) -> np.ndarray:
+        """download buffer as [batch?][H][W][4] float32 (RGBA, alpha = 0.5: compare RGB only)."""
+        return self.output().reshape(-1, self.height, self.width, 4)
+
+
+class ResNet50(Network):
+    def __init__(self, device=0, batch=1):
+        super().__init__(lib().fynhost_resnet50_create(int(device), int(batch)))
+        self.batch = batch
+
+    def logits(self) -> np.ndarray:
+        """[batch][1000]: the deep 18x14 download texture is channel order for 1x1 spatial (cpubuffer.cpp:131-142)."""
+        return self.output().reshape(self.batch, -1)[:, :1000]
+
+
+def smoke_stylenet(ctx_device=0):
+    """Used by __graft_entry__.smoke(): StyleNet3x3 64x48 through the host engine vs the oracle."""
+    import fyn_oracle as fo
+    w = fo.stylenet_synthetic_weights(3)
+    img = fo.synthetic_image(48, 64, 1)
+    net = StyleNet(3, 64, 48, device=ctx_device)
+    net.load_weights(w)
+    net.setup()
+    net.set_input(img)
+    net.forward()
+    got = net.output_rgba()[0].copy()
+    ref = fo.stylenet_forward(w, img, 3, prec=fo.FP16_STORE)
+    err = float(np.abs(got[..., :3] - ref[..., :3]).max())
+    net.destroy()
+    assert err < 1e-2, f"StyleNet3x3 smoke mismatch {err}"
+    return err

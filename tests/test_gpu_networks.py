@@ -1,0 +1,136 @@
+"""GPU parity tests of the whole hot path through the C++ host engine (LayerBuilder -> LayerFactory ->
+CUDA layers -> NeuralNetwork::setup()/forward()), per layer and end to end, against the CPU oracle.
+
+Whole-network parity is "unpinned" by the reference itself (no golden outputs, LFS-stub weights); the
+oracle is pinned at layer level (tests/test_oracle_kat.py).  Tolerances (fp16 storage = reference default):
+per layer rel-L2 <= 3e-3 and max-abs <= 2e-2 * max|ref| against the fp32 oracle fed with the SAME fp16 history
+(i.e. compared per layer on the oracle's fp16-store trajectory); final RGB max-abs <= 4e-3.
+"""
+import numpy as np
+import pytest
+
+import fyn_oracle as fo
+from fyusenet_b200 import capi, hostapi
+from gpu_util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _style_layer_names(k):
+    nres = 5 if k == 9 else 2
+    return ["conv1", "conv2", "conv3"] + [f"res{r}_{i}" for r in range(1, nres + 1) for i in (1, 2)] + ["deconv1", "deconv2", "deconv3", "sigmoid"]
+
+
+@pytest.mark.parametrize("ksize,w,h", [(3, 64, 48), (9, 80, 64), (3, 512, 624)])
+def test_stylenet_matches_oracle(ksize, w, h):
+    """BASELINE configs[0] (StyleNet 3x3, 512x624) and reduced 3x3 / 9x9 cases, per-layer and final."""
+    weights = fo.stylenet_synthetic_weights(ksize)
+    img = fo.synthetic_image(h, w, 7)
+    net = hostapi.StyleNet(ksize, w, h)
+    net.load_weights(weights)
+    net.setup()
+    net.set_input(img)
+    net.forward()
+    got = net.output_rgba()[0].copy()
+    dump = {}
+    ref = fo.stylenet_forward(weights, img, ksize, prec=fo.FP16_STORE, dump=dump)
+    ref32 = fo.stylenet_forward(weights, img, ksize, prec=fo.FP32)
+    layers = {l["name"]: l for l in net.layers()}
+    worst = {}
+    for name in _style_layer_names(ksize):
+        l = layers[name]
+        y = net.layer_result(l["number"], (l["channels"], l["height"], l["width"]))
+        r = dump[name]
+        assert y.shape == r.shape, name
+        e2, emax = rel_l2(y, r), float(np.abs(y - r).max())
+        worst[name] = (e2, emax)
+        assert e2 <= 3e-3 and emax <= 2e-2 * max(1.0, float(np.abs(r).max())), f"{name}: rel-L2 {e2:.2e} max-abs {emax:.2e}"
+    assert got.shape == ref.shape == (h, w, 4)
+    assert float(np.abs(got[..., :3] - ref[..., :3]).max()) <= 4e-3, worst
+    assert float(np.abs(got[..., :3] - ref32[..., :3]).max()) <= 8e-3
+    np.testing.assert_allclose(got[..., 3], 0.5)   # sigmoid(0) in the unused lane, as in the reference
+    # 8-bit output as the sample writes it ((uint8)(v*255), samples/desktop/stylenet.cpp:57-59): PSNR
+    a, b = (got[..., :3] * 255).astype(np.uint8).astype(np.float64), (ref32[..., :3] * 255).astype(np.uint8).astype(np.float64)
+    mse = float(((a - b) ** 2).mean())
+    assert mse == 0 or 10 * np.log10(255.0 ** 2 / mse) > 45.0
+    # hot-swap the style (stylenet9x9.cpp:87-95) and run again
+    w2 = fo.stylenet_synthetic_weights(ksize, seed=5)
+    net.load_weights(w2)
+    net.forward()
+    got2 = net.output_rgba()[0].copy()
+    ref2 = fo.stylenet_forward(w2, img, ksize, prec=fo.FP16_STORE)
+    assert float(np.abs(got2[..., :3] - ref2[..., :3]).max()) <= 4e-3
+    assert net.num_tensors <= 8, "liveness-based tensor reuse should keep the pool small"
+    net.destroy()
+
+
+def test_stylenet_fp32_storage_mode():
+    """FYN_F32 storage == the reference's HIGH_PRECISION build: tight agreement with the fp32 oracle."""
+    hostapi.set_storage_precision(True)
+    try:
+        weights = fo.stylenet_synthetic_weights(3)
+        img = fo.synthetic_image(48, 64, 3)
+        net = hostapi.StyleNet(3, 64, 48)
+        net.load_weights(weights)
+        net.setup()
+        net.set_input(img)
+        net.forward()
+        got = net.output_rgba()[0].copy()
+        ref = fo.stylenet_forward(weights, img, 3, prec=fo.FP32)
+        assert float(np.abs(got[..., :3] - ref[..., :3]).max()) <= 2e-5
+        net.destroy()
+    finally:
+        hostapi.set_storage_precision(False)
+
+
+def test_stylenet_device_resident_io():
+    """Network without upload / download layers: device tensor in (setInputTexture), device tensor out."""
+    weights = fo.stylenet_synthetic_weights(3)
+    img = fo.synthetic_image(48, 64, 2)
+    net = hostapi.StyleNet(3, 64, 48, upload=False, download=False)
+    net.load_weights(weights)
+    ctx = capi.Context(0)
+    tin = ctx.tensor(64, 48, 3, 0, capi.ORDER_SHALLOW, capi.F32, 1, packing=3)
+    tin.upload(img)
+    ctx.stream_sync()
+    net.set_input_tensor(tin)
+    net.setup()
+    net.forward()
+    net.finish()
+    l = [x for x in net.layers() if x["name"] == "sigmoid"][0]
+    y = net.layer_result(l["number"], (3, 48, 64))
+    ref = fo.stylenet_forward(weights, img, 3, prec=fo.FP16_STORE)
+    assert float(np.abs(np.moveaxis(y, 0, -1) - ref[..., :3]).max()) <= 4e-3
+    net.destroy()
+
+
+@pytest.mark.parametrize("batch", [1, 3])
+def test_resnet50_matches_oracle(batch):
+    """BASELINE configs[2]: ResNet-50 224x224, raw logits and identical top-5 vs the oracle; batch > 1 stacks
+    independent images (new on this backend) and must reproduce the batch-1 result per image."""
+    weights = fo.resnet50_synthetic_weights()
+    imgs = np.stack([fo.synthetic_image(224, 224, 100 + i) for i in range(batch)])
+    net = hostapi.ResNet50(batch=batch)
+    net.load_weights(weights)
+    net.setup()
+    net.set_input(imgs)
+    net.forward()
+    logits = net.logits().copy()
+    assert logits.shape == (batch, 1000)
+    for i in range(batch):
+        dump = {}
+        ref = fo.resnet50_forward(weights, imgs[i], prec=fo.FP16_STORE, dump=dump)
+        ref32 = fo.resnet50_forward(weights, imgs[i], prec=fo.FP32)
+        e2 = rel_l2(logits[i], ref)
+        assert e2 <= 5e-3, f"image {i}: logits rel-L2 vs fp16-store oracle {e2:.2e}"
+        assert rel_l2(logits[i], ref32) <= 2e-2
+        assert set(np.argsort(-logits[i])[:5]) == set(np.argsort(-ref)[:5]) == set(np.argsort(-ref32)[:5])
+        assert int(np.argmax(logits[i])) == int(np.argmax(ref32))
+        if i == 0:
+            for l in net.layers():
+                if l["number"] in dump and l["number"] not in (72,):
+                    shape = (batch, l["channels"], l["height"], l["width"])
+                    y = net.layer_result(l["number"], shape)[0]
+                    r = dump[l["number"]]
+                    assert rel_l2(y, r) <= 4e-3, f"layer {l['name']}: rel-L2 {rel_l2(y, r):.2e}"
+    net.destroy()
