@@ -1,0 +1,129 @@
+"""GPU parity tests of the tcgen05 / TMEM convolution family (fyn_conv_tc.cu) through the C ABI.
+
+The tensor-core kernels multiply fp16 activations with fp16-ROUNDED weights and accumulate in fp32, so the exact
+model is the fp16-store oracle run with half-rounded weights (and a half-rounded input where the kernel converts
+an fp32 upload texture): the kernel must match that within 1 fp16 ulp (+ fp32 summation noise).  Against the
+true-fp32-weight oracle the bound is rel-L2 <= 2e-3 (weight rounding 2^-11 per product, random signs), and the
+tcgen05 result must agree with the in-library direct (CUDA-core) kernel to the same tolerance.
+"""
+import numpy as np
+import pytest
+
+import fyn_oracle as fo
+from fyusenet_b200 import capi
+from gpu_util import assert_close_f16, conv_gpu, ctx, half, random_wb, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _round_weights(wb, co):
+    w = np.array(wb, np.float32, copy=True)
+    w[co:] = half(w[co:])      # conv weights are fp16 operands; bias / BN stay fp32 in the epilogue
+    return w
+
+
+def _run(x, wb, co, k, ds=1, relu=True, residual=None, relu_res=False, in_pad=0, out_pad=0, res_pad=0, post_bn=False,
+         bn_res=False):
+    fl = (capi.FLAG_PRE_RELU if relu else 0) | (capi.FLAG_RELU_ON_RESIDUAL if relu_res else 0) | \
+         (capi.FLAG_POST_BATCHNORM if post_bn else 0) | (capi.FLAG_BATCHNORM_ON_RESIDUAL if bn_res else 0)
+    y, be, _ = conv_gpu(x, wb, out_channels=co, kernel=k, downsample=ds, flags=fl, residual=residual, in_pad=in_pad,
+                        out_pad=out_pad, res_pad=res_pad, backend=capi.BACKEND_TC, want_op=True)
+    assert be == 2, "tcgen05 family must have been selected"
+    yd = conv_gpu(x, wb, out_channels=co, kernel=k, downsample=ds, flags=fl, residual=residual, in_pad=in_pad,
+                  out_pad=out_pad, res_pad=res_pad, backend=capi.BACKEND_DIRECT)
+    ofl = (fo.RELU_ON_RESIDUAL if relu_res else 0) | (fo.POST_BATCHNORM if post_bn else 0) | (fo.BATCHNORM_ON_RESIDUAL if bn_res else 0)
+    okw = dict(downsample=ds, act=fo.ACT_RELU if relu else fo.ACT_NONE, flags=ofl, in_pad=in_pad, out_pad=out_pad)
+
+    def orc(xx, ww, prec):
+        xx = np.asarray(xx, np.float32)
+        if xx.ndim == 4:
+            return np.stack([fo.conv2d(xx[i], ww, co, k, residual=None if residual is None else half(residual[i]), prec=prec, **okw)
+                             for i in range(xx.shape[0])])
+        return fo.conv2d(xx, ww, co, k, residual=None if residual is None else half(residual), prec=prec, **okw)
+
+    xs = half(x)
+    exact = orc(xs, _round_weights(wb, co), fo.FP16_STORE)
+    true32 = orc(xs, wb, fo.FP32)
+    assert_close_f16(y, exact, true32, ulps=1.01, extra_abs=4e-5)
+    assert rel_l2(y, yd) <= 2e-3
+    return y
+
+
+@pytest.mark.parametrize("w,h", [(381, 29), (128, 16), (130, 7), (64, 48), (257, 11)])
+@pytest.mark.parametrize("variant", ["res_1", "res_2_relu", "res_2_plain", "noact"])
+def test_tc_res_layers(w, h, variant):
+    """StyleNet residual convs: 3x3, 40 -> 40, clamp-to-edge, pre-ReLU, residual (+ReLU) -- stylenet9x9.cpp:145-186.
+    Widths that are not multiples of the 128-pixel tile and heights that do not divide into strips."""
+    rng = np.random.default_rng(w * 7 + h)
+    x = rng.normal(size=(40, h, w)).astype(np.float32)
+    wb = random_wb(rng, 40, 40, 3)
+    res = rng.normal(size=(40, h, w)).astype(np.float32) if variant.startswith("res_2") else None
+    _run(x, wb, 40, 3, relu=(variant != "noact"), residual=res, relu_res=(variant == "res_2_relu"))
+
+
+@pytest.mark.parametrize("w,h", [(384, 40), (200, 23), (1524, 12)])
+def test_tc_conv1_9x9_from_upload_texture(w, h):
+    """conv1: 9x9, 3 -> 12 reading the RGB32F upload texture (pixel-pair K-chunks)."""
+    rng = np.random.default_rng(w + h)
+    img = rng.random((h, w, 3), dtype=np.float32)
+    wb = random_wb(rng, 3, 12, 9)
+    c = ctx()
+    ys = {}
+    for be in (capi.BACKEND_TC, capi.BACKEND_DIRECT):
+        op = capi.Conv2d(c, wb, width=w, height=h, in_channels=3, out_channels=12, kernel=9, flags=capi.FLAG_PRE_RELU, backend=be)
+        tin = c.tensor(w, h, 3, 0, capi.ORDER_SHALLOW, capi.F32, 1, packing=3)
+        tout = c.tensor(w, h, 12, 0, capi.ORDER_SHALLOW, capi.F16)
+        tin.upload(img)
+        op.run(tin, tout)
+        ys[be] = tout.read_chw()
+        assert op.backend == be
+        for o in (tin, tout, op):
+            o.destroy()
+    x = fo.upload_hwc(img)
+    exact = fo.conv2d(half(x), _round_weights(wb, 12), 12, 9, act=fo.ACT_RELU, prec=fo.FP16_STORE)
+    true32 = fo.conv2d(x, wb, 12, 9, act=fo.ACT_RELU)
+    assert_close_f16(ys[capi.BACKEND_TC], exact, true32, ulps=1.01, extra_abs=4e-5)
+    assert rel_l2(ys[capi.BACKEND_TC], ys[capi.BACKEND_DIRECT]) <= 2e-3
+
+
+@pytest.mark.parametrize("k,ci,co,w,h", [(3, 12, 20, 260, 24), (3, 20, 40, 380, 18), (3, 12, 20, 1524, 8), (5, 8, 16, 140, 20), (3, 16, 64, 96, 12)])
+def test_tc_stride2(k, ci, co, w, h):
+    """conv2 / conv3: 3x3 stride 2 (stylenet9x9.cpp:139-143) -- even/odd column de-interleave in the ring slots."""
+    rng = np.random.default_rng(k + ci + co + w)
+    x = rng.normal(size=(ci, h, w)).astype(np.float32)
+    _run(x, random_wb(rng, ci, co, k), co, k, ds=2)
+
+
+def test_tc_general_shapes():
+    """Other shapes the family accepts: 3x3 5/7-plane inputs, 5x5 / 7x7 kernels, padding, post-BN, BN on residual, batch."""
+    rng = np.random.default_rng(99)
+    x = rng.normal(size=(2, 24, 13, 150)).astype(np.float32)
+    res = rng.normal(size=(2, 32, 13, 150)).astype(np.float32)
+    _run(x, random_wb(rng, 24, 32, 3, post_bn=True), 32, 3, residual=res, post_bn=True, bn_res=True, in_pad=1, out_pad=2, res_pad=1)
+    x = rng.normal(size=(12, 20, 70)).astype(np.float32)
+    _run(x, random_wb(rng, 12, 8, 5), 8, 5)
+    x = rng.normal(size=(8, 20, 70)).astype(np.float32)
+    _run(x, random_wb(rng, 8, 12, 7), 12, 7, relu=False)
+    x = rng.normal(size=(3, 33, 140)).astype(np.float32)   # fp16 RGBA plane input, 3x3 pixel-pair mode
+    _run(x, random_wb(rng, 3, 12, 3), 12, 3)
+
+
+def test_tc_weight_hot_swap_and_launch_count():
+    c = ctx()
+    rng = np.random.default_rng(4)
+    x = rng.normal(size=(40, 20, 140)).astype(np.float32)
+    w1, w2 = random_wb(rng, 40, 40, 3), random_wb(rng, 40, 40, 3)
+    op = capi.Conv2d(c, w1, width=140, height=20, in_channels=40, out_channels=40, kernel=3, flags=capi.FLAG_PRE_RELU)
+    assert op.backend == 2
+    tin, tout = c.tensor(140, 20, 40), c.tensor(140, 20, 40)
+    tin.write_chw(x)
+    n0 = c.launch_count()
+    op.run(tin, tout)
+    assert c.launch_count() == n0 + 1
+    y1 = tout.read_chw()
+    op.load_weights(w2)
+    op.run(tin, tout)
+    y2 = tout.read_chw()
+    for y, w in ((y1, w1), (y2, w2)):
+        exact = fo.conv2d(half(x), _round_weights(w, 40), 40, 3, act=fo.ACT_RELU, prec=fo.FP16_STORE)
+        assert_close_f16(y, exact, ulps=1.01, extra_abs=4e-5)

@@ -16,13 +16,21 @@ from gpu_util import rel_l2
 pytestmark = pytest.mark.gpu
 
 
+def _read_dump(directory, name, seq, shape):
+    """<dir>/<layername>_<seq>.bin: CHW float32 without padding (Engine::enableIntermediateOutput,
+    reference base/engine.cpp:174-181,434-437).  Dumps are written right after each layer runs, which is the only
+    valid moment: pooled tensors are reused by later layers."""
+    a = np.fromfile(f"{directory}/{name}_{seq}.bin", dtype=np.float32)
+    return a.reshape(shape)
+
+
 def _style_layer_names(k):
     nres = 5 if k == 9 else 2
     return ["conv1", "conv2", "conv3"] + [f"res{r}_{i}" for r in range(1, nres + 1) for i in (1, 2)] + ["deconv1", "deconv2", "deconv3", "sigmoid"]
 
 
 @pytest.mark.parametrize("ksize,w,h", [(3, 64, 48), (9, 80, 64), (3, 512, 624)])
-def test_stylenet_matches_oracle(ksize, w, h):
+def test_stylenet_matches_oracle(ksize, w, h, tmp_path):
     """BASELINE configs[0] (StyleNet 3x3, 512x624) and reduced 3x3 / 9x9 cases, per-layer and final."""
     weights = fo.stylenet_synthetic_weights(ksize)
     img = fo.synthetic_image(h, w, 7)
@@ -30,6 +38,7 @@ def test_stylenet_matches_oracle(ksize, w, h):
     net.load_weights(weights)
     net.setup()
     net.set_input(img)
+    net.enable_dumps(tmp_path)
     net.forward()
     got = net.output_rgba()[0].copy()
     dump = {}
@@ -39,7 +48,7 @@ def test_stylenet_matches_oracle(ksize, w, h):
     worst = {}
     for name in _style_layer_names(ksize):
         l = layers[name]
-        y = net.layer_result(l["number"], (l["channels"], l["height"], l["width"]))
+        y = _read_dump(tmp_path, name, 1, (l["channels"], l["height"], l["width"]))
         r = dump[name]
         assert y.shape == r.shape, name
         e2, emax = rel_l2(y, r), float(np.abs(y - r).max())
@@ -105,7 +114,7 @@ def test_stylenet_device_resident_io():
 
 
 @pytest.mark.parametrize("batch", [1, 3])
-def test_resnet50_matches_oracle(batch):
+def test_resnet50_matches_oracle(batch, tmp_path):
     """BASELINE configs[2]: ResNet-50 224x224, raw logits and identical top-5 vs the oracle; batch > 1 stacks
     independent images (new on this backend) and must reproduce the batch-1 result per image."""
     weights = fo.resnet50_synthetic_weights()
@@ -114,6 +123,7 @@ def test_resnet50_matches_oracle(batch):
     net.load_weights(weights)
     net.setup()
     net.set_input(imgs)
+    net.enable_dumps(tmp_path)
     net.forward()
     logits = net.logits().copy()
     assert logits.shape == (batch, 1000)
@@ -130,7 +140,7 @@ def test_resnet50_matches_oracle(batch):
             for l in net.layers():
                 if l["number"] in dump and l["number"] not in (72,):
                     shape = (batch, l["channels"], l["height"], l["width"])
-                    y = net.layer_result(l["number"], shape)[0]
+                    y = _read_dump(tmp_path, l["name"], 1, shape)[0]
                     r = dump[l["number"]]
                     assert rel_l2(y, r) <= 4e-3, f"layer {l['name']}: rel-L2 {rel_l2(y, r):.2e}"
     net.destroy()
