@@ -499,7 +499,13 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     plan->smemBytes = ((wbytes + 127) & ~(size_t)127) + (size_t)a.nslots * a.slotBytes + (2 * a.nslots + 4) * 8 + 16;
     if (plan->smemBytes > (size_t)op->ctx->prop.sharedMemPerBlockOptin)
         FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 conv needs %zu bytes of shared memory", plan->smemBytes);
-    FYN_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smemBytes));
+    // the attribute is per function, not per launch: keep it at the largest footprint any plan needs
+    static size_t maxSmem[64] = {0};
+    size_t &cur = maxSmem[op->ctx->device & 63];
+    if (plan->smemBytes > cur) {
+        FYN_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smemBytes));
+        cur = plan->smemBytes;
+    }
     return FYN_OK;
 }
 

@@ -16,9 +16,11 @@ from gpu_util import assert_close_f16, conv_gpu, ctx, half, random_wb, rel_l2
 pytestmark = pytest.mark.gpu
 
 
-def _round_weights(wb, co):
+def _round_weights(wb, co, nweights=None):
+    """conv weights are fp16 operands of the MMA; bias and post-BN scale / bias stay fp32 in the epilogue"""
     w = np.array(wb, np.float32, copy=True)
-    w[co:] = half(w[co:])      # conv weights are fp16 operands; bias / BN stay fp32 in the epilogue
+    end = len(w) if nweights is None else co + nweights
+    w[co:end] = half(w[co:end])
     return w
 
 
@@ -42,7 +44,8 @@ def _run(x, wb, co, k, ds=1, relu=True, residual=None, relu_res=False, in_pad=0,
         return fo.conv2d(xx, ww, co, k, residual=None if residual is None else half(residual), prec=prec, **okw)
 
     xs = half(x)
-    exact = orc(xs, _round_weights(wb, co), fo.FP16_STORE)
+    ci = np.asarray(x).shape[-3]
+    exact = orc(xs, _round_weights(wb, co, k * k * ci * co), fo.FP16_STORE)
     true32 = orc(xs, wb, fo.FP32)
     assert_close_f16(y, exact, true32, ulps=1.01, extra_abs=4e-5)
     assert rel_l2(y, yd) <= 2e-3
