@@ -19,6 +19,14 @@
 //   For 3-channel inputs (StyleNet conv1 reading the RGB32F upload texture) a chunk is two horizontally
 //   adjacent pixels x 4 channels ("pixel-pair" mode), i.e. one 16-byte chunk covers taps kx and kx+1.
 //
+// Fractional convolutions (fyusenet/gpu/vanilla/fractionalconvlayerNxN_vanilla.cpp, shaders/vanilla/fraconv*.frag,
+// fractional.inc) are phase-decomposed: with u = sourceStep*downsample = 1/p, output pixel p*j+phi reads source
+// pixel j + delta(phi, tap) with delta = floor(s*(ds*phi + 0.5 + tap)), so every output phase (phi_y, phi_x) is an
+// ordinary small convolution over the source image whose taps that land on the same source texel have their
+// weights summed at plan time.  The reference's quirks are kept: 3x3 taps at -2s,-s,0, and the prefix
+// activation on the first horizontal tap only -- the ring slot then holds two versions of the row (activated and
+// raw) and the first-tap weights are routed to the activated version.
+//
 // Warp roles (416 threads): warps 0-3 epilogue (TMEM -> registers -> bias/BN/residual -> fp16 planes),
 // warps 4-11 loaders (two groups of four warps on alternating input rows, so two rows are always in flight),
 // warp 12 issues tcgen05.mma (one elected lane).
@@ -32,7 +40,7 @@
 
 namespace {
 
-constexpr int kMaxSteps = 48;
+constexpr int kMaxSteps = 128;
 constexpr int kLoaderWarps = 8;                       // two groups of four
 constexpr int kMmaWarp = 4 + kLoaderWarps;
 constexpr int kThreads = (kMmaWarp + 1) * 32;       // 416
@@ -40,11 +48,20 @@ constexpr int kGroupThreads = kLoaderWarps * 16;    // threads per loader group 
 constexpr int kUnroll = 6;                           // (pixel, chunk) items in flight per loader thread
 constexpr int kTileM = 128;
 
+// one tcgen05.mma (M=128, N, K=16)
 struct TcStep {
-    uint32_t a_off;   // byte offset of the first K-chunk inside its ring slot
+    uint32_t a_off;   // byte offset of the first K-chunk inside its ring slot (includes the version offset)
     uint32_t a_lbo;   // byte distance to the second K-chunk
-    int32_t row;      // ring row relative to the first row of the window (ky)
     uint32_t b_off;   // byte offset inside the weight image
+    int8_t row;       // ring row relative to the first row of the job's window
+    uint8_t acc;      // accumulator (x phase)
+    uint8_t first;    // 1 = overwrite the accumulator
+    uint8_t pad;
+};
+
+// the jobs of one y phase: window of input rows and its slice of the step table
+struct TcPhaseY {
+    int dyMin, nrows, stepBegin, stepEnd;
 };
 
 struct TcArgs {
@@ -52,17 +69,21 @@ struct TcArgs {
     const uint4 *wimg;
     const float *bias, *scale;
     uint32_t wbytes, idesc, b_lbo;
-    int nsteps;
+    int py, px;              // output phases per source row / column (1 for regular convs)
+    int rowAdvance;          // input rows the window moves per group of py jobs (stride, 1 for fractional)
+    TcPhaseY phase[2];
     TcStep steps[kMaxSteps];
-    int K, ds, mh;           // kernel, stride, (K-1)/2
-    int W, H, Wo, Ho;        // input / output net size
+    int Wo, Ho;              // output net size
+    int Hj, Wj;              // job-space size: output rows / py, output columns / px
     int inP, outP, resP;
-    int nchunks, rowpx;      // chunks per ring slot, pixels per chunk row
+    int nchunks, rowpx;      // chunks per version, pixels per chunk row
+    int nver, verBytes;      // slot versions: 0 = activated (or the only one), 1 = raw
     int nslots, slotBytes;
-    int SH, nxs;             // output rows per strip, column blocks
+    int SH, nxs;             // job rows per strip, column blocks
     int N, nOutPlanes, nInPlanes;
     int mode;                // 0 = plane-pair chunks (fp16 RGBA planes), 1 = pixel-pair (single plane)
-    int x_lead;              // input pixels to the left of the first output pixel's centre held in a slot
+    int ds;                  // horizontal stride of the slot layout (2 = even/odd split)
+    int x_lead;              // input pixels to the left of job column 0 held in a slot
     ActParams act;
     int hasRes, reluRes, bnRes;
     int batch;
@@ -140,10 +161,51 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
+
+
+__device__ __forceinline__ uint2 relu_h4(uint2 v) {
+    const __half2 z = __float2half2_rn(0.f);
+    __half2 *q = reinterpret_cast<__half2 *>(&v);
+    q[0] = __hmax2(q[0], z);
+    q[1] = __hmax2(q[1], z);
+    return v;
+}
+
+__device__ __forceinline__ uint2 act_h4(uint2 v, const ActParams &a) {
+    if (a.type == 1) return relu_h4(v);
+    if (a.type == 0) return v;
+    __half *q = reinterpret_cast<__half *>(&v);
+    for (int j = 0; j < 4; j++) q[j] = __float2half_rn(fyn_act(__half2float(q[j]), a));
+    return v;
+}
+
+// epilogue for one output texel: acc*scale + bias (+ residual [relu] [*scale])
+__device__ __forceinline__ float4 epilogue4(const TcArgs &a, const uint32_t *r, int p, int n, int xo, int yo) {
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.scale) + p);
+    const float4 bi = __ldg(reinterpret_cast<const float4 *>(a.bias) + p);
+    float4 v = make_float4(fmaf(__uint_as_float(r[0]), sc.x, bi.x), fmaf(__uint_as_float(r[1]), sc.y, bi.y),
+                           fmaf(__uint_as_float(r[2]), sc.z, bi.z), fmaf(__uint_as_float(r[3]), sc.w, bi.w));
+    if (a.hasRes) {
+        float4 rs = fyn_fetch(a.res, n, p, a.resP + xo, a.resP + yo);
+        if (a.reluRes) rs = make_float4(fmaxf(rs.x, 0.f), fmaxf(rs.y, 0.f), fmaxf(rs.z, 0.f), fmaxf(rs.w, 0.f));
+        if (a.bnRes) rs = make_float4(rs.x * sc.x, rs.y * sc.y, rs.z * sc.z, rs.w * sc.w);
+        v.x += rs.x;
+        v.y += rs.y;
+        v.z += rs.z;
+        v.w += rs.w;
+    }
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
 // dynamic shared memory: [weight image][ring slots][barriers][tmem base]
+//
+// Work decomposition.  The output is cut into strips: 128 job columns x SH job rows; one CTA per strip.  A "job"
+// is one accumulation group: for regular convs one output row of the strip (window = K input rows), for
+// fractional convs one (source row, y phase) pair producing px accumulators (one per x phase).  Jobs are
+// processed in order; the window of input rows only moves forward, so the ring of row slots is a FIFO.
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sW = smem;
@@ -161,13 +223,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     int bid = blockIdx.x;
     const int xb = bid % a.nxs;
     bid /= a.nxs;
-    const int nseg = (a.Ho + a.SH - 1) / a.SH;
+    const int nseg = (a.Hj + a.SH - 1) / a.SH;
     const int seg = bid % nseg;
     const int n = bid / nseg;
-    const int ya = seg * a.SH, yb = min(a.Ho, ya + a.SH);
-    const int x0 = xb * kTileM;
-    const int r0 = a.ds * ya - a.mh;                  // first input row of the window (unclamped)
-    const int r1 = a.ds * (yb - 1) + a.mh;            // last input row
+    const int ja = seg * a.SH, jb = min(a.Hj, ja + a.SH);   // job rows [ja, jb)
+    const int njobs = (jb - ja) * a.py;
+    const int j0 = xb * kTileM;                               // first job column
+    // window of job q: first input row = rowAdvance*(ja + q/py) + dyMin[q%py]
+    const int r0 = a.rowAdvance * ja + a.phase[0].dyMin;
+    int r1 = r0;
+    for (int f = 0; f < a.py; f++) r1 = max(r1, a.rowAdvance * (jb - 1) + a.phase[f].dyMin + a.phase[f].nrows - 1);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nslots; s++) {
@@ -195,15 +260,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         const int t = (threadIdx.x - 128) % kGroupThreads;   // thread index inside the group
         const int P = a.inP;
         const __half *src = reinterpret_cast<const __half *>(a.in.ptr);
-        const __half2 hz = __float2half2_rn(0.f);
         for (int r = r0 + grp; r <= r1; r += 2) {
             const int idx = r - r0, slot = idx % a.nslots, fill = idx / a.nslots;
             mbar_wait(&empty[slot], (fill & 1) ^ 1);
             unsigned char *dst = sRing + (size_t)slot * a.slotBytes;
             const int iy = min(max(r + P, 0), a.in.texH - 1);   // texture row, CLAMP_TO_EDGE
             if (a.mode == 0) {
-                // (pixel, chunk) items: two 8-byte plane loads -> one 16-byte chunk store.  All loads of a batch
-                // are issued before the first store so that kUnroll*2 requests per thread are in flight.
+                // (pixel, chunk) items: two 8-byte plane loads -> one 16-byte chunk store per version.  All loads of a
+                // batch are issued before the first store so that kUnroll*2 requests per thread are in flight.
                 const int items = a.rowpx * a.nchunks, half = a.rowpx >> 1;
                 const long long rowBase = (long long)n * a.in.imageElems + (long long)iy * a.in.texW * 4;
                 for (int base = 0; base < items; base += kGroupThreads * kUnroll) {
@@ -215,9 +279,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                         hi[u] = make_uint2(0u, 0u);
                         if (it < items) {
                             const int c = it / a.rowpx, px = it - c * a.rowpx;
-                            // stride 1: slot pixel = image pixel - (x0 - lead); stride 2: slot is [parity][pixel/2]
-                            const int gx = (a.ds == 1) ? x0 - a.x_lead + px
-                                                       : 2 * x0 - a.x_lead + 2 * (px % half) + (px / half);
+                            // stride 1: slot pixel = image pixel - (j0 - lead); stride 2: slot is [parity][pixel/2]
+                            const int gx = (a.ds == 1) ? j0 - a.x_lead + px
+                                                       : 2 * j0 - a.x_lead + 2 * (px % half) + (px / half);
                             const int ix = min(max(gx + P, 0), a.in.texW - 1);
                             const __half *q = src + rowBase + (long long)ix * 4;
                             if (2 * c < a.nInPlanes) lo[u] = __ldg(reinterpret_cast<const uint2 *>(q + (long long)(2 * c) * a.in.planeElems));
@@ -228,27 +292,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                     for (int u = 0; u < kUnroll; u++) {
                         const int it = base + u * kGroupThreads + t;
                         if (it < items) {
-                            if (a.act.type == 1) {
-                                __half2 *q = reinterpret_cast<__half2 *>(&lo[u]);
-                                q[0] = __hmax2(q[0], hz);
-                                q[1] = __hmax2(q[1], hz);
-                                q = reinterpret_cast<__half2 *>(&hi[u]);
-                                q[0] = __hmax2(q[0], hz);
-                                q[1] = __hmax2(q[1], hz);
-                            } else if (a.act.type != 0) {
-                                __half *q = reinterpret_cast<__half *>(&lo[u]);
-                                for (int j = 0; j < 4; j++) q[j] = __float2half_rn(fyn_act(__half2float(q[j]), a.act));
-                                q = reinterpret_cast<__half *>(&hi[u]);
-                                for (int j = 0; j < 4; j++) q[j] = __float2half_rn(fyn_act(__half2float(q[j]), a.act));
-                            }
-                            *reinterpret_cast<uint4 *>(dst + (size_t)it * 16) = make_uint4(lo[u].x, lo[u].y, hi[u].x, hi[u].y);
+                            if (a.nver == 2)   // raw copy for the taps that bypass the activation
+                                *reinterpret_cast<uint4 *>(dst + a.verBytes + (size_t)it * 16) = make_uint4(lo[u].x, lo[u].y, hi[u].x, hi[u].y);
+                            const uint2 l = act_h4(lo[u], a.act), h = act_h4(hi[u], a.act);
+                            *reinterpret_cast<uint4 *>(dst + (size_t)it * 16) = make_uint4(l.x, l.y, h.x, h.y);
                         }
                     }
                 }
             } else {
                 // pixel-pair mode: chunk(px) = [pixel px | pixel px+1], 4 channels each
                 for (int px = t; px <= a.rowpx; px += kGroupThreads) {
-                    const int ix = min(max(x0 - a.x_lead + px + P, 0), a.in.texW - 1);
+                    const int ix = min(max(j0 - a.x_lead + px + P, 0), a.in.texW - 1);
                     float4 v = fyn_act4(fyn_load_texel(a.in, (long long)n * a.in.imageElems + ((long long)iy * a.in.texW + ix) * a.in.packing), a.act);
                     const uint2 h = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
                     if (px < a.rowpx) *reinterpret_cast<uint2 *>(dst + (size_t)px * 16) = h;
@@ -262,66 +316,68 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t wbase = smem_u32(sW), rbase = smem_u32(sRing);
-            for (int y = ya; y < yb; y++) {
-                const int i = y - ya, buf = i & 1, use = i >> 1;
+            int released = 0;
+            for (int q = 0; q < njobs; q++) {
+                const int buf = q & 1, use = q >> 1;
+                const TcPhaseY ph = a.phase[q % a.py];
+                const int first = a.rowAdvance * (ja + q / a.py) + ph.dyMin - r0;
                 mbar_wait(&tempty[buf], (use & 1) ^ 1);
-                // all rows of this output row's window must have landed
-                const int first = a.ds * y - a.mh - r0;
-                for (int k = 0; k < a.K; k++) {
+                // all rows of this job's window must have landed
+                for (int k = 0; k < ph.nrows; k++) {
                     const int idx = first + k;
                     mbar_wait(&full[idx % a.nslots], (idx / a.nslots) & 1);
                 }
                 tc_fence_after();
                 const uint32_t d = tmem + (uint32_t)buf * 64u;
-                for (int s = 0; s < a.nsteps; s++) {
+                for (int s = ph.stepBegin; s < ph.stepEnd; s++) {
                     const TcStep st = a.steps[s];
                     const int idx = first + st.row;
                     const uint32_t aaddr = rbase + (uint32_t)(idx % a.nslots) * (uint32_t)a.slotBytes + st.a_off;
-                    umma_f16(d, make_desc(aaddr, st.a_lbo, 128), make_desc(wbase + st.b_off, a.b_lbo, 128), a.idesc, s > 0);
+                    umma_f16(d + (uint32_t)st.acc * (uint32_t)a.N, make_desc(aaddr, st.a_lbo, 128), make_desc(wbase + st.b_off, a.b_lbo, 128),
+                             a.idesc, st.first ? 0u : 1u);
                 }
                 umma_commit(&tfull[buf]);
-                // rows that no later output row needs go back to the loaders
-                const int keepFrom = (y + 1 < yb) ? a.ds * (y + 1) - a.mh - r0 : (r1 - r0 + 1);
-                for (int idx = first; idx < keepFrom; idx++) umma_commit(&empty[idx % a.nslots]);
+                // rows that no later job needs go back to the loaders
+                int keepFrom = r1 - r0 + 1;
+                if (q + 1 < njobs) keepFrom = a.rowAdvance * (ja + (q + 1) / a.py) + a.phase[(q + 1) % a.py].dyMin - r0;
+                for (; released < keepFrom; released++) umma_commit(&empty[released % a.nslots]);
             }
         }
     } else {
-        // ===================== epilogue: warps 0-3, thread = output pixel =====================
+        // ===================== epilogue: warps 0-3, thread = job column =====================
         const int m = threadIdx.x;           // 0..127 == TMEM lane
-        const int xo = x0 + m;
-        const bool valid = xo < a.Wo;
-        for (int y = ya; y < yb; y++) {
-            const int i = y - ya, buf = i & 1, use = i >> 1;
+        const int jx = j0 + m;
+        const bool valid = jx < a.Wj;
+        for (int q = 0; q < njobs; q++) {
+            const int buf = q & 1, use = q >> 1;
+            const int yo = a.py * (ja + q / a.py) + (q % a.py);
             mbar_wait(&tfull[buf], use & 1);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * 64u;
-            for (int g = 0; g < a.N / 16; g++) {
-                uint32_t r[16];
+            const int groups = a.N / 16;
+            for (int g = 0; g < groups; g++) {
+                uint32_t r[16], r2[16];
                 tmem_ld16(taddr + g * 16, r);
+                if (a.px == 2) tmem_ld16(taddr + a.N + g * 16, r2);
                 tmem_ld_wait();
-                if (g == a.N / 16 - 1) {
-                    // accumulator fully read: hand the buffer back before doing the global-memory work
+                if (g == groups - 1) {
+                    // accumulators fully read: hand the buffer back before doing the global-memory work
                     tc_fence_before();
                     mbar_arrive(&tempty[buf]);
                 }
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int p = g * 4 + q;
+                for (int k = 0; k < 4; k++) {
+                    const int p = g * 4 + k;
                     if (p < a.nOutPlanes && valid) {
-                        const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.scale) + p);
-                        const float4 bi = __ldg(reinterpret_cast<const float4 *>(a.bias) + p);
-                        float4 v = make_float4(fmaf(__uint_as_float(r[4 * q + 0]), sc.x, bi.x), fmaf(__uint_as_float(r[4 * q + 1]), sc.y, bi.y),
-                                               fmaf(__uint_as_float(r[4 * q + 2]), sc.z, bi.z), fmaf(__uint_as_float(r[4 * q + 3]), sc.w, bi.w));
-                        if (a.hasRes) {
-                            float4 rs = fyn_fetch(a.res, n, p, a.resP + xo, a.resP + y);
-                            if (a.reluRes) rs = make_float4(fmaxf(rs.x, 0.f), fmaxf(rs.y, 0.f), fmaxf(rs.z, 0.f), fmaxf(rs.w, 0.f));
-                            if (a.bnRes) rs = make_float4(rs.x * sc.x, rs.y * sc.y, rs.z * sc.z, rs.w * sc.w);
-                            v.x += rs.x;
-                            v.y += rs.y;
-                            v.z += rs.z;
-                            v.w += rs.w;
+                        if (a.px == 1) {
+                            fyn_store_texel(a.out, n, p, a.outP + jx, a.outP + yo, epilogue4(a, r + 4 * k, p, n, jx, yo));
+                        } else {
+                            // two x phases -> two adjacent output texels
+                            const float4 v0 = epilogue4(a, r + 4 * k, p, n, 2 * jx, yo);
+                            const float4 v1 = epilogue4(a, r2 + 4 * k, p, n, 2 * jx + 1, yo);
+                            fyn_store_texel(a.out, n, p, a.outP + 2 * jx, a.outP + yo, v0);
+                            fyn_store_texel(a.out, n, p, a.outP + 2 * jx + 1, a.outP + yo, v1);
                         }
-                        fyn_store_texel(a.out, n, p, a.outP + xo, a.outP + y, v);
                     }
                 }
             }
@@ -335,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-// host side: plan = MMA step table + weight image
+// host side: plan = job phases + MMA step table + weight image
 // ---------------------------------------------------------------------------------------------
 struct ConvTcPlan {
     TcArgs args{};
@@ -345,140 +401,265 @@ struct ConvTcPlan {
     int mode = 0;
 };
 
-static bool tc_shape_ok(const fyn_conv_desc *d, int *mode) {
-    if (d->flags & FYN_FLAG_DEEP) return false;          // deep-tiled family: not yet
-    if (d->fractional) return false;                     // fractional family: not yet
-    if (d->dilation != 1) return false;
-    if (d->out_channels > 64) return false;
-    if (d->downsample != 1 && d->downsample != 2) return false;
-    if (d->kernel < 3) return false;
-    int m;
-    if (d->in_channels <= 4 && d->downsample == 1) m = 1;
-    else if (d->in_channels >= 8) m = 0;
-    else return false;
-    // MMA steps per output row and shared-memory footprint must fit
-    const int K = d->kernel, mh = (K - 1) / 2, N = ((d->out_channels + 15) / 16) * 16;
-    const int nchunks = m == 0 ? ((d->in_channels + 3) / 4 + 1) / 2 : 1;
-    const int chunksPerRow = m == 0 ? K * nchunks : (K + 1) / 2;
-    const int nsteps = ((chunksPerRow + 1) / 2) * K;
-    if (nsteps > kMaxSteps) return false;
-    int rowpx;
-    if (m == 1) rowpx = ((kTileM + 2 * mh + 2) + 3) & ~3;
-    else if (d->downsample == 1) rowpx = ((kTileM + 2 * mh + 1) + 3) & ~3;
-    else rowpx = 2 * (((kTileM + mh + 1) + 3) & ~3);
-    const size_t smem = (size_t)nsteps * 2 * N * 16 + (size_t)(K + 2 * d->downsample + 1) * nchunks * rowpx * 16 + 1024;
-    if (smem > 200 * 1024) return false;
-    *mode = m;
-    return true;
+namespace {
+
+// one source position of a phase: merged weights [Co][Ci] for (version, dy, dx)
+struct Position {
+    int ver, dy, dx;
+    std::vector<float> w;   // [Co][Ci]
+};
+
+struct PhasePlan {
+    std::vector<Position> pos;
+};
+
+struct Geometry {
+    int mode = 0, py = 1, px = 1, rowAdvance = 1, nver = 1, N = 16, nchunks = 1, rowpx = 0, x_lead = 0, ds = 1;
+    int dxMin = 0, dxMax = 0;
+    int dyMin[2] = {0, 0}, dyMax[2] = {0, 0};
+    int nslots = 0, slotBytes = 0, verBytes = 0, nsteps = 0;
+    size_t wbytes = 0, smem = 0;
+    std::vector<PhasePlan> phases;   // [py*px], index fy*px+fx (weights only filled when wb != nullptr)
+    bool ok = false;
+};
+
+int ifloor(float v) { return (int)floorf(v); }
+
+// Builds phases / positions (and merged weights when wb is given) and the shared-memory geometry.
+Geometry plan_geometry(const fyn_conv_desc *d, const float *wb) {
+    Geometry g;
+    if (d->flags & FYN_FLAG_DEEP) return g;          // deep-tiled family: not yet
+    if (d->dilation != 1) return g;
+    if (d->out_channels > 64) return g;
+    const int K = d->kernel, mh = (K - 1) / 2, Ci = d->in_channels, Co = d->out_channels;
+    g.N = ((Co + 15) / 16) * 16;
+    const bool hasAct = (d->flags & (FYN_FLAG_PRE_RELU | FYN_FLAG_PRE_CLIP)) != 0;
+    std::vector<int> tapx(K), tapy(K);
+    for (int k = 0; k < K; k++) tapx[k] = tapy[k] = k - mh;
+    if (d->fractional) {
+        if (Ci < 8) return g;
+        const float s = d->source_step, u = s * (float)d->downsample;
+        int p;
+        if (u == 1.0f) p = 1;
+        else if (u == 0.5f) p = 2;
+        else return g;                                // other ratios: direct kernel
+        if (p == 2 && g.N > 32) return g;             // two accumulators share a 64-column TMEM buffer
+        if (K == 3 && (d->quirks & FYN_QUIRK_FRAC3_ASYM)) {
+            tapx[0] = -2;
+            tapx[1] = -1;
+            tapx[2] = 0;
+        }
+        const bool actFirstOnly = hasAct && (d->quirks & FYN_QUIRK_FRAC_ACT_FIRST);
+        g.py = g.px = p;
+        g.rowAdvance = 1;
+        g.nver = actFirstOnly ? 2 : 1;
+        g.ds = 1;
+        g.mode = 0;
+        g.phases.resize((size_t)p * p);
+        g.dxMin = 1 << 20;
+        g.dxMax = -(1 << 20);
+        for (int fy = 0; fy < p; fy++) {
+            g.dyMin[fy] = 1 << 20;
+            g.dyMax[fy] = -(1 << 20);
+            for (int fx = 0; fx < p; fx++) {
+                PhasePlan &pp = g.phases[(size_t)fy * p + fx];
+                for (int ky = 0; ky < K; ky++)
+                    for (int kx = 0; kx < K; kx++) {
+                        // delta = floor(s*(ds*phi + 0.5 + tap)) -- gpu/vanilla/convlayerbase_vanilla.cpp:352-371 + fraconv*.frag
+                        const int dy = ifloor(s * ((float)(d->downsample * fy) + 0.5f + (float)tapy[ky]));
+                        const int dx = ifloor(s * ((float)(d->downsample * fx) + 0.5f + (float)tapx[kx]));
+                        const int ver = (actFirstOnly && kx > 0) ? 1 : 0;
+                        g.dyMin[fy] = std::min(g.dyMin[fy], dy);
+                        g.dyMax[fy] = std::max(g.dyMax[fy], dy);
+                        g.dxMin = std::min(g.dxMin, dx);
+                        g.dxMax = std::max(g.dxMax, dx);
+                        Position *hit = nullptr;
+                        for (Position &q : pp.pos)
+                            if (q.ver == ver && q.dy == dy && q.dx == dx) hit = &q;
+                        if (!hit) {
+                            pp.pos.push_back({ver, dy, dx, {}});
+                            hit = &pp.pos.back();
+                            if (wb) hit->w.assign((size_t)Co * Ci, 0.f);
+                        }
+                        if (wb) {
+                            const float *W = wb + Co;
+                            for (int o = 0; o < Co; o++)
+                                for (int c = 0; c < Ci; c++) hit->w[(size_t)o * Ci + c] += W[(((size_t)o * K + ky) * K + kx) * Ci + c];
+                        }
+                    }
+            }
+        }
+    } else {
+        if (d->downsample != 1 && d->downsample != 2) return g;
+        if (K < 3) return g;
+        if (Ci <= 4 && d->downsample == 1) g.mode = 1;
+        else if (Ci >= 8) g.mode = 0;
+        else return g;
+        g.py = g.px = 1;
+        g.rowAdvance = d->downsample;
+        g.ds = d->downsample;
+        g.nver = 1;
+        g.dyMin[0] = -mh;
+        g.dyMax[0] = mh;
+        g.dxMin = -mh;
+        g.dxMax = mh;
+        g.phases.resize(1);
+        for (int ky = 0; ky < K; ky++)
+            for (int kx = 0; kx < K; kx++) {
+                Position q{0, ky - mh, kx - mh, {}};
+                if (wb) {
+                    const float *W = wb + Co;
+                    q.w.resize((size_t)Co * Ci);
+                    for (int o = 0; o < Co; o++)
+                        for (int c = 0; c < Ci; c++) q.w[(size_t)o * Ci + c] = W[(((size_t)o * K + ky) * K + kx) * Ci + c];
+                }
+                g.phases[0].pos.push_back(std::move(q));
+            }
+    }
+    // slot geometry
+    const int span = g.dxMax - g.dxMin;
+    g.x_lead = -g.dxMin;
+    if (g.mode == 1) {
+        g.nchunks = 1;
+        g.rowpx = ((kTileM + span + 2) + 3) & ~3;
+    } else {
+        g.nchunks = ((Ci + 3) / 4 + 1) / 2;
+        if (g.ds == 1) g.rowpx = ((kTileM + span + 1) + 3) & ~3;
+        else g.rowpx = 2 * (((kTileM + span / 2 + 1) + 3) & ~3);
+    }
+    g.verBytes = g.nchunks * g.rowpx * 16;
+    g.slotBytes = g.verBytes * g.nver;
+    int maxRows = 0;
+    for (int f = 0; f < g.py; f++) maxRows = std::max(maxRows, g.dyMax[f] - g.dyMin[f] + 1);
+    g.nslots = maxRows + 2 * g.rowAdvance + 1;
+    // steps: per phase, chunks of the same window row are paired in address order
+    int nsteps = 0;
+    for (const PhasePlan &pp : g.phases) {
+        std::vector<int> perRow(32, 0);
+        for (const Position &q : pp.pos) {
+            const int chunks = (g.mode == 1) ? 0 : g.nchunks;
+            perRow[q.dy + 16] += chunks;
+        }
+        if (g.mode == 1) {
+            // pixel-pair: ceil(K/2) chunks per kernel row
+            for (int ky = 0; ky < K; ky++) nsteps += (((K + 1) / 2) + 1) / 2;
+        } else {
+            for (int c : perRow) nsteps += (c + 1) / 2;
+        }
+    }
+    g.nsteps = nsteps;
+    if (nsteps > kMaxSteps) return g;
+    g.wbytes = (size_t)nsteps * 2 * g.N * 16;
+    g.smem = ((g.wbytes + 127) & ~(size_t)127) + (size_t)g.nslots * g.slotBytes + (2 * g.nslots + 4) * 8 + 16;
+    if (g.smem > 220 * 1024) return g;
+    g.ok = true;
+    return g;
 }
 
-int fyn_conv_tc_supported(const fyn_conv_desc *d, int) {
-    int mode;
-    return tc_shape_ok(d, &mode) ? 1 : 0;
-}
+}  // namespace
+
+int fyn_conv_tc_supported(const fyn_conv_desc *d, int) { return plan_geometry(d, nullptr).ok ? 1 : 0; }
 
 int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     const fyn_conv_desc &d = op->conv;
-    int mode = 0;
-    if (!tc_shape_ok(&d, &mode)) FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 family does not cover this conv");
+    Geometry g = plan_geometry(&d, wb);
+    if (!g.ok) FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 family does not cover this conv");
     ConvTcPlan *plan = op->tc ? op->tc : new ConvTcPlan();
     op->tc = plan;
-    plan->mode = mode;
+    plan->mode = g.mode;
     TcArgs &a = plan->args;
-    const int K = d.kernel, Ci = d.in_channels, Co = d.out_channels, ds = d.downsample, mh = (K - 1) / 2;
-    const int N = ((Co + 15) / 16) * 16;
-    a.K = K;
-    a.ds = ds;
-    a.mh = mh;
+    const int K = d.kernel, Ci = d.in_channels, Co = d.out_channels, N = g.N;
     a.N = N;
     a.nOutPlanes = (Co + 3) / 4;
     a.nInPlanes = (Ci + 3) / 4;
-    a.mode = mode;
+    a.mode = g.mode;
+    a.py = g.py;
+    a.px = g.px;
+    a.rowAdvance = g.rowAdvance;
+    a.ds = g.ds;
+    a.nver = g.nver;
+    a.verBytes = g.verBytes;
+    a.nchunks = g.nchunks;
+    a.rowpx = g.rowpx;
+    a.x_lead = g.x_lead;
+    a.nslots = g.nslots;
+    a.slotBytes = g.slotBytes;
     a.idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);  // F32 accum, F16 x F16, K-major A/B
     a.b_lbo = (uint32_t)N * 16u;
+    a.wbytes = (uint32_t)g.wbytes;
 
-    // ---- ring-slot geometry and the chunk list of one kernel row -------------------------------------
-    // a "chunk" is 16 bytes of K for every pixel; chunkOff[] is its byte offset for output pixel m = 0
-    struct Chunk { uint32_t off; int kx; int sub; };   // sub: chunk index inside the tap
-    std::vector<Chunk> chunks;
-    if (mode == 0) {
-        a.nchunks = (a.nInPlanes + 1) / 2;
-        a.x_lead = mh;
-        if (ds == 1) {
-            a.rowpx = ((kTileM + 2 * mh + 1) + 3) & ~3;
-            for (int kx = 0; kx < K; kx++)
-                for (int c = 0; c < a.nchunks; c++) chunks.push_back({(uint32_t)((c * a.rowpx + kx) * 16), kx, c});
-        } else {
-            // stride 2: [parity][pixel/2]; slot pixel j = 2m + kx  ->  parity kx&1, index m + kx/2
-            const int half = ((kTileM + mh + 1) + 3) & ~3;
-            a.rowpx = 2 * half;
-            for (int kx = 0; kx < K; kx++)
-                for (int c = 0; c < a.nchunks; c++)
-                    chunks.push_back({(uint32_t)((c * a.rowpx + (kx & 1) * half + kx / 2) * 16), kx, c});
-        }
-    } else {
-        a.nchunks = 1;
-        a.x_lead = mh;
-        a.rowpx = ((kTileM + 2 * mh + 2) + 3) & ~3;
-        for (int kx = 0; kx < K; kx += 2) chunks.push_back({(uint32_t)(kx * 16), kx, 0});
-    }
-    a.slotBytes = a.nchunks * a.rowpx * 16;
-    a.nslots = K + 2 * ds + 1;
-
-    // ---- pair chunks into K=16 steps (second chunk must lie at a higher address) ----------------------
-    // greedy: sort by offset, pair neighbours; an unpaired chunk is paired with itself against zero weights
-    std::vector<int> order(chunks.size());
-    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
-    std::sort(order.begin(), order.end(), [&](int x, int y) { return chunks[x].off < chunks[y].off; });
-    struct Pair { int c0, c1; };
-    std::vector<Pair> pairs;
-    for (size_t i = 0; i < order.size(); i += 2) {
-        if (i + 1 < order.size()) pairs.push_back({order[i], order[i + 1]});
-        else pairs.push_back({order[i], -1});
-    }
-    const int stepsPerRow = (int)pairs.size();
-    a.nsteps = stepsPerRow * K;
-    if (a.nsteps > kMaxSteps) FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 conv: %d MMA steps exceed the table (%d)", a.nsteps, kMaxSteps);
-
-    // ---- weight image: per step two chunks of [N][8] fp16 ----------------------------------------------
-    const size_t wbytes = (size_t)a.nsteps * 2 * N * 16;
-    std::vector<__half> img(wbytes / 2, __float2half(0.f));
-    const float *W = wb + Co;  // [Co][K][K][Ci]
-    auto fill_chunk = [&](size_t chunkIdx, int ky, const Chunk &c) {
-        for (int nn = 0; nn < Co; nn++)
-            for (int e = 0; e < 8; e++) {
-                float v = 0.f;
-                if (mode == 0) {
-                    const int ci = c.sub * 8 + e;
-                    if (ci < Ci) v = W[(((size_t)nn * K + ky) * K + c.kx) * Ci + ci];
-                } else {
-                    const int kx = c.kx + e / 4, ci = e % 4;
-                    if (kx < K && ci < Ci) v = W[(((size_t)nn * K + ky) * K + kx) * Ci + ci];
-                }
-                img[(chunkIdx * N + nn) * 8 + e] = __float2half_rn(v);
-            }
+    std::vector<__half> img(g.wbytes / 2, __float2half(0.f));
+    // byte offset inside a slot of chunk c at source offset dx (output job column 0)
+    auto aoff = [&](int ver, int c, int dx) -> uint32_t {
+        const int j = dx + g.x_lead;   // slot pixel for job column 0
+        int px;
+        if (g.ds == 1) px = j;
+        else px = (j & 1) * (g.rowpx / 2) + j / 2;
+        return (uint32_t)(ver * g.verBytes + (c * g.rowpx + px) * 16);
     };
+    struct Chunk { uint32_t off; const Position *pos; int sub; int kx; };
     int s = 0;
-    for (int ky = 0; ky < K; ky++)
-        for (const Pair &p : pairs) {
-            TcStep &st = a.steps[s];
-            st.row = ky;
-            st.a_off = chunks[p.c0].off;
-            st.b_off = (uint32_t)((size_t)s * 2 * N * 16);
-            fill_chunk((size_t)s * 2, ky, chunks[p.c0]);
-            if (p.c1 >= 0) {
-                st.a_lbo = chunks[p.c1].off - chunks[p.c0].off;
-                fill_chunk((size_t)s * 2 + 1, ky, chunks[p.c1]);
-            } else {
-                st.a_lbo = 16;  // second half reads the neighbouring pixel against all-zero weights
+    for (int fy = 0; fy < g.py; fy++) {
+        a.phase[fy].dyMin = g.dyMin[fy];
+        a.phase[fy].nrows = g.dyMax[fy] - g.dyMin[fy] + 1;
+        a.phase[fy].stepBegin = s;
+        for (int fx = 0; fx < g.px; fx++) {
+            const PhasePlan &pp = g.phases[(size_t)fy * g.px + fx];
+            bool firstOfAcc = true;
+            for (int dy = g.dyMin[fy]; dy <= g.dyMax[fy]; dy++) {
+                std::vector<Chunk> chunks;
+                if (g.mode == 0) {
+                    for (const Position &q : pp.pos)
+                        if (q.dy == dy)
+                            for (int c = 0; c < g.nchunks; c++) chunks.push_back({aoff(q.ver, c, q.dx), &q, c, 0});
+                } else {
+                    // pixel-pair: chunk at tap kx covers taps kx, kx+1 (weights taken from the two positions)
+                    for (int kx = 0; kx < K; kx += 2) chunks.push_back({(uint32_t)(kx * 16), nullptr, 0, kx});
+                }
+                std::sort(chunks.begin(), chunks.end(), [](const Chunk &x, const Chunk &y) { return x.off < y.off; });
+                auto fill = [&](size_t chunkIdx, const Chunk &c) {
+                    for (int nn = 0; nn < Co; nn++)
+                        for (int e = 0; e < 8; e++) {
+                            float v = 0.f;
+                            if (g.mode == 0) {
+                                const int ci = c.sub * 8 + e;
+                                if (ci < Ci) v = c.pos->w[(size_t)nn * Ci + ci];
+                            } else {
+                                const int kx = c.kx + e / 4, ci = e % 4, ky = dy + (K - 1) / 2;
+                                if (kx < K && ci < Ci) v = wb[Co + (((size_t)nn * K + ky) * K + kx) * Ci + ci];
+                            }
+                            img[(chunkIdx * N + nn) * 8 + e] = __float2half_rn(v);
+                        }
+                };
+                for (size_t i = 0; i < chunks.size(); i += 2) {
+                    TcStep &st = a.steps[s];
+                    st.row = (int8_t)(dy - g.dyMin[fy]);
+                    st.acc = (uint8_t)fx;
+                    st.first = firstOfAcc ? 1 : 0;
+                    st.pad = 0;
+                    firstOfAcc = false;
+                    st.a_off = chunks[i].off;
+                    st.b_off = (uint32_t)((size_t)s * 2 * N * 16);
+                    fill((size_t)s * 2, chunks[i]);
+                    if (i + 1 < chunks.size()) {
+                        st.a_lbo = chunks[i + 1].off - chunks[i].off;
+                        fill((size_t)s * 2 + 1, chunks[i + 1]);
+                        if (st.a_lbo == 0 || st.a_lbo >= (1u << 18))
+                            FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 conv: operand stride %u not encodable", st.a_lbo);
+                    } else {
+                        st.a_lbo = 16;  // second half reads the neighbouring pixel against all-zero weights
+                    }
+                    s++;
+                }
             }
-            s++;
         }
-    a.wbytes = (uint32_t)wbytes;
+        a.phase[fy].stepEnd = s;
+    }
+    if (s != g.nsteps) FYN_FAIL(FYN_ERR_INVALID, "tcgen05 conv: internal step count mismatch (%d vs %d)", s, g.nsteps);
 
     FYN_CUDA(cudaSetDevice(op->ctx->device));
-    if (!plan->d_wimg) FYN_CUDA(cudaMalloc((void **)&plan->d_wimg, wbytes));
-    FYN_CUDA(cudaMemcpy(plan->d_wimg, img.data(), wbytes, cudaMemcpyHostToDevice));
+    if (!plan->d_wimg) FYN_CUDA(cudaMalloc((void **)&plan->d_wimg, g.wbytes));
+    FYN_CUDA(cudaMemcpy(plan->d_wimg, img.data(), g.wbytes, cudaMemcpyHostToDevice));
     // epilogue parameters padded to N
     std::vector<float> eb((size_t)2 * N, 0.f);
     const float *bn = wb + Co + (size_t)K * K * Ci * Co;
@@ -496,7 +677,7 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     a.wimg = plan->d_wimg;
     a.bias = plan->d_bias;
     a.scale = plan->d_bias + N;
-    plan->smemBytes = ((wbytes + 127) & ~(size_t)127) + (size_t)a.nslots * a.slotBytes + (2 * a.nslots + 4) * 8 + 16;
+    plan->smemBytes = g.smem;
     if (plan->smemBytes > (size_t)op->ctx->prop.sharedMemPerBlockOptin)
         FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 conv needs %zu bytes of shared memory", plan->smemBytes);
     // the attribute is per function, not per launch: keep it at the largest footprint any plan needs
@@ -520,10 +701,11 @@ int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn
     a.in = fyn_make_view(in);
     a.out = fyn_make_view(out);
     a.res = fyn_make_view(res);
-    a.W = d.width;
-    a.H = d.height;
     a.Wo = op->Wo;
     a.Ho = op->Ho;
+    if (a.Wo % a.px || a.Ho % a.py) return 1;   // phase decomposition needs whole periods
+    a.Wj = a.Wo / a.px;
+    a.Hj = a.Ho / a.py;
     a.inP = d.in_padding;
     a.outP = d.out_padding;
     a.resP = d.res_padding;
@@ -532,15 +714,14 @@ int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn
     a.reluRes = (d.flags & FYN_FLAG_RELU_ON_RESIDUAL) != 0;
     a.bnRes = (d.flags & FYN_FLAG_BATCHNORM_ON_RESIDUAL) != 0;
     a.batch = in->desc.batch;
-    a.nxs = (a.Wo + kTileM - 1) / kTileM;
+    a.nxs = (a.Wj + kTileM - 1) / kTileM;
     // strip height: one strip per SM (the kernel's register / shared-memory footprint allows one CTA per SM),
-    // at least 4 rows so the prologue (weight image, TMEM allocation) amortises
+    // at least 4 job rows so the prologue (weight image, TMEM allocation) amortises
     const int sms = op->ctx->prop.multiProcessorCount;
-    long long target = 1LL * sms;
     long long cols = (long long)a.nxs * a.batch;
-    int segs = (int)std::max<long long>(1, target / std::max<long long>(1, cols));
-    a.SH = std::max(4, (a.Ho + segs - 1) / segs);
-    const int nseg = (a.Ho + a.SH - 1) / a.SH;
+    int segs = (int)std::max<long long>(1, (long long)sms / std::max<long long>(1, cols));
+    a.SH = std::max(4, (a.Hj + segs - 1) / segs);
+    const int nseg = (a.Hj + a.SH - 1) / a.SH;
     const long long blocks = (long long)a.nxs * nseg * a.batch;
     k_conv_tc<<<(unsigned)blocks, kThreads, plan->smemBytes, stream>>>(a);
     FYN_CHECK_LAUNCH(op->ctx);

@@ -130,3 +130,31 @@ def test_tc_weight_hot_swap_and_launch_count():
     for y, w in ((y1, w1), (y2, w2)):
         exact = fo.conv2d(half(x), _round_weights(w, 40), 40, 3, act=fo.ACT_RELU, prec=fo.FP16_STORE)
         assert_close_f16(y, exact, ulps=1.01, extra_abs=4e-5)
+
+
+@pytest.mark.parametrize("quirks", [capi.QUIRKS_REFERENCE, 0])
+@pytest.mark.parametrize("k,ci,co,step,ds,relu,w,h", [
+    (3, 40, 20, 0.5, 2, False, 381, 24),    # deconv1: same resolution, taps collapse onto a 2x2 support
+    (3, 20, 12, 0.25, 2, True, 381, 20),    # deconv2: 2x upsample, activation on the first tap only (Q2)
+    (9, 12, 3, 0.5, 1, True, 200, 18),      # deconv3: 9x9, 2x upsample
+    (3, 16, 16, 0.5, 1, True, 130, 9),
+    (5, 8, 24, 0.5, 2, False, 64, 33),
+])
+def test_tc_fractional(k, ci, co, step, ds, relu, w, h, quirks):
+    """StyleNet deconv1..3 (stylenet9x9.cpp:192-202) on the tcgen05 family via phase decomposition, with the
+    reference quirks on (default) and off.  Merged taps are summed in fp32 and rounded to fp16 once, so the
+    comparison is against the fp32-weight oracle: rel-L2 <= 2e-3, element-wise <= 2 fp16 ulp + 2e-3."""
+    rng = np.random.default_rng(k * 31 + ci + co + w)
+    x = rng.normal(size=(ci, h, w)).astype(np.float32)
+    wb = random_wb(rng, ci, co, k)
+    fl = capi.FLAG_PRE_RELU if relu else 0
+    kw = dict(out_channels=co, kernel=k, downsample=ds, source_step=step, fractional=True, flags=fl, quirks=quirks)
+    y, be, _ = conv_gpu(x, wb, backend=capi.BACKEND_TC, want_op=True, **kw)
+    assert be == 2
+    yd = conv_gpu(x, wb, backend=capi.BACKEND_DIRECT, **kw)
+    okw = dict(downsample=ds, source_step=step, fractional=True, act=fo.ACT_RELU if relu else fo.ACT_NONE, quirks=quirks)
+    ref_s = fo.conv2d(half(x), wb, co, k, prec=fo.FP16_STORE, **okw)
+    ref_f = fo.conv2d(half(x), wb, co, k, prec=fo.FP32, **okw)
+    assert y.shape == ref_s.shape
+    assert_close_f16(y, ref_s, ref_f, ulps=2.0, extra_abs=2e-3)
+    assert rel_l2(y, yd) <= 2e-3
