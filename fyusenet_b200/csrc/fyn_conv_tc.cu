@@ -44,8 +44,7 @@ constexpr int kMaxSteps = 128;
 constexpr int kLoaderWarps = 8;                       // two groups of four
 constexpr int kMmaWarp = 4 + kLoaderWarps;
 constexpr int kThreads = (kMmaWarp + 1) * 32;       // 416
-constexpr int kGroupThreads = kLoaderWarps * 16;    // threads per loader group (128)
-constexpr int kUnroll = 6;                           // (pixel, chunk) items in flight per loader thread
+constexpr int kUnroll = 7;                           // (pixel, chunk) items per loader thread and row (all in flight)
 constexpr int kTileM = 128;
 
 // one tcgen05.mma (M=128, N, K=16)
@@ -69,6 +68,7 @@ struct TcArgs {
     const uint4 *wimg;
     const float *bias, *scale;
     uint32_t wbytes, idesc, b_lbo;
+    int nsteps, groupWarps;  // MMA steps in the table; warps per loader group (1, 2 or 4)
     int py, px;              // output phases per source row / column (1 for regular convs)
     int rowAdvance;          // input rows the window moves per group of py jobs (stride, 1 for fractional)
     TcPhaseY phase[2];
@@ -148,13 +148,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE ("interleave"): core matrix = 8 rows x 16 bytes stored
-// contiguously (rows 16 B apart); SBO = distance between 8-row groups, LBO = distance between the two 16-byte
-// K chunks of one K=16 instruction; bits [46,48) = 1 (sm_100 descriptor version).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
-           (1ull << 46);
-}
+// UMMA shared-memory descriptors (K-major, SWIZZLE_NONE "interleave"): core matrix = 8 rows x 16 bytes stored
+// contiguously (rows 16 B apart).  Low word: start address >> 4 in bits [0,14), LBO >> 4 in bits [16,30) (distance
+// between the two 16-byte K chunks of one K=16 instruction).  High word: SBO >> 4 in bits [0,14) (distance between
+// 8-row groups, 128 B here) and the sm_100 descriptor version 1 in bits [14,16).
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
@@ -179,38 +176,43 @@ __device__ __forceinline__ uint2 act_h4(uint2 v, const ActParams &a) {
     return v;
 }
 
-// epilogue for one output texel: acc*scale + bias (+ residual [relu] [*scale])
-__device__ __forceinline__ float4 epilogue4(const TcArgs &a, const uint32_t *r, int p, int n, int xo, int yo) {
-    const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.scale) + p);
-    const float4 bi = __ldg(reinterpret_cast<const float4 *>(a.bias) + p);
-    float4 v = make_float4(fmaf(__uint_as_float(r[0]), sc.x, bi.x), fmaf(__uint_as_float(r[1]), sc.y, bi.y),
-                           fmaf(__uint_as_float(r[2]), sc.z, bi.z), fmaf(__uint_as_float(r[3]), sc.w, bi.w));
-    if (a.hasRes) {
-        float4 rs = fyn_fetch(a.res, n, p, a.resP + xo, a.resP + yo);
-        if (a.reluRes) rs = make_float4(fmaxf(rs.x, 0.f), fmaxf(rs.y, 0.f), fmaxf(rs.z, 0.f), fmaxf(rs.w, 0.f));
-        if (a.bnRes) rs = make_float4(rs.x * sc.x, rs.y * sc.y, rs.z * sc.z, rs.w * sc.w);
-        v.x += rs.x;
-        v.y += rs.y;
-        v.z += rs.z;
-        v.w += rs.w;
-    }
-    return v;
-}
-
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-// dynamic shared memory: [weight image][ring slots][barriers][tmem base]
+// dynamic shared memory: [weight image][ring slots][step table][epilogue params][barriers][tmem base]
 //
 // Work decomposition.  The output is cut into strips: 128 job columns x SH job rows; one CTA per strip.  A "job"
 // is one accumulation group: for regular convs one output row of the strip (window = K input rows), for
 // fractional convs one (source row, y phase) pair producing px accumulators (one per x phase).  Jobs are
 // processed in order; the window of input rows only moves forward, so the ring of row slots is a FIFO.
+
+// step as the MMA thread consumes it: everything that does not depend on the ring position is pre-encoded
+struct SmemStep {
+    uint32_t a_lo;    // (LBO >> 4) << 16 | (a_off >> 4): add (slot base >> 4) to get the descriptor's low word
+    uint32_t b_lo;    // low word of the B descriptor (start address and LBO)
+    uint32_t tmemOff; // accumulator column offset
+    uint32_t rowAcc;  // row | first << 8
+};
+
+// position in the ring without divisions
+struct RingPos {
+    int slot, fill;
+    __device__ __forceinline__ void advance(int d, int nslots) {
+        slot += d;
+        while (slot >= nslots) {
+            slot -= nslots;
+            fill++;
+        }
+    }
+};
+
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sW = smem;
     unsigned char *sRing = smem + ((a.wbytes + 127) & ~127u);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sRing + (size_t)a.nslots * a.slotBytes);
+    SmemStep *sSteps = reinterpret_cast<SmemStep *>(sRing + (size_t)a.nslots * a.slotBytes);
+    float4 *sEpi = reinterpret_cast<float4 *>(sSteps + kMaxSteps);        // [16] bias planes then [16] scale planes
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sEpi + 32);
     uint64_t *full = bars;                     // [nslots]
     uint64_t *empty = bars + a.nslots;         // [nslots]
     uint64_t *tfull = bars + 2 * a.nslots;     // [2]
@@ -234,9 +236,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     int r1 = r0;
     for (int f = 0; f < a.py; f++) r1 = max(r1, a.rowAdvance * (jb - 1) + a.phase[f].dyMin + a.phase[f].nrows - 1);
 
+    const int groupThreads = a.groupWarps * 32;
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nslots; s++) {
-            mbar_init(&full[s], kGroupThreads);   // every thread of the loading group arrives
+            mbar_init(&full[s], groupThreads);   // every thread of the loading group arrives
             mbar_init(&empty[s], 1);
         }
         mbar_init(&tfull[0], 1);
@@ -248,6 +251,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     if (warp == kMmaWarp) tmem_alloc(tmemBase, 128);
     // weight image -> shared memory (all threads, 16-byte copies), visible to the async proxy
     for (uint32_t i = threadIdx.x; i < a.wbytes / 16; i += kThreads) reinterpret_cast<uint4 *>(sW)[i] = __ldg(a.wimg + i);
+    {
+        const uint32_t wbase = smem_u32(sW);
+        for (int i = threadIdx.x; i < a.nsteps; i += kThreads) {
+            const TcStep st = a.steps[i];
+            SmemStep o;
+            o.a_lo = ((st.a_lbo >> 4) << 16) | (st.a_off >> 4);
+            o.b_lo = (((wbase + st.b_off) >> 4) & 0x3FFF) | ((a.b_lbo >> 4) << 16);
+            o.tmemOff = (uint32_t)st.acc * (uint32_t)a.N;
+            o.rowAcc = (uint32_t)(uint8_t)st.row | ((uint32_t)st.first << 8);
+            sSteps[i] = o;
+        }
+        for (int i = threadIdx.x; i < 32; i += kThreads) {
+            const int p = i & 15;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p * 4 < a.N) v = __ldg(reinterpret_cast<const float4 *>(i < 16 ? a.bias : a.scale) + p);
+            sEpi[i] = v;
+        }
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -255,92 +276,143 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     const uint32_t tmem = *tmemBase;
 
     if (warp >= 4 && warp < kMmaWarp) {
-        // ===================== loaders: two groups on alternating rows =====================
-        const int grp = (warp - 4) / (kLoaderWarps / 2);
-        const int t = (threadIdx.x - 128) % kGroupThreads;   // thread index inside the group
+        // ===================== loaders: kLoaderWarps/groupWarps groups, group g takes rows g, g+G, ... ==========
+        const int ngroups = kLoaderWarps / a.groupWarps;
+        const int grp = (warp - 4) / a.groupWarps;
+        const int t = (threadIdx.x - 128) - grp * groupThreads;   // thread index inside the group
         const int P = a.inP;
-        const __half *src = reinterpret_cast<const __half *>(a.in.ptr);
-        for (int r = r0 + grp; r <= r1; r += 2) {
-            const int idx = r - r0, slot = idx % a.nslots, fill = idx / a.nslots;
-            mbar_wait(&empty[slot], (fill & 1) ^ 1);
-            unsigned char *dst = sRing + (size_t)slot * a.slotBytes;
-            const int iy = min(max(r + P, 0), a.in.texH - 1);   // texture row, CLAMP_TO_EDGE
-            if (a.mode == 0) {
-                // (pixel, chunk) items: two 8-byte plane loads -> one 16-byte chunk store per version.  All loads of a
-                // batch are issued before the first store so that kUnroll*2 requests per thread are in flight.
-                const int items = a.rowpx * a.nchunks, half = a.rowpx >> 1;
-                const long long rowBase = (long long)n * a.in.imageElems + (long long)iy * a.in.texW * 4;
-                for (int base = 0; base < items; base += kGroupThreads * kUnroll) {
-                    uint2 lo[kUnroll], hi[kUnroll];
+        RingPos pos{0, 0};
+        pos.advance(grp, a.nslots);
+        if (a.mode == 0) {
+            // Per-thread item table (row independent): item = (pixel, chunk) -> two 8-byte plane loads and one
+            // 16-byte chunk store per version.  All loads of a row are issued before the first store.
+            const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems;
+            const int items = a.rowpx * a.nchunks, half = a.rowpx >> 1;
+            int gofs[kUnroll], sofs[kUnroll];
 #pragma unroll
-                    for (int u = 0; u < kUnroll; u++) {
-                        const int it = base + u * kGroupThreads + t;
-                        lo[u] = make_uint2(0u, 0u);
-                        hi[u] = make_uint2(0u, 0u);
-                        if (it < items) {
-                            const int c = it / a.rowpx, px = it - c * a.rowpx;
-                            // stride 1: slot pixel = image pixel - (j0 - lead); stride 2: slot is [parity][pixel/2]
-                            const int gx = (a.ds == 1) ? j0 - a.x_lead + px
-                                                       : 2 * j0 - a.x_lead + 2 * (px % half) + (px / half);
-                            const int ix = min(max(gx + P, 0), a.in.texW - 1);
-                            const __half *q = src + rowBase + (long long)ix * 4;
-                            if (2 * c < a.nInPlanes) lo[u] = __ldg(reinterpret_cast<const uint2 *>(q + (long long)(2 * c) * a.in.planeElems));
-                            if (2 * c + 1 < a.nInPlanes) hi[u] = __ldg(reinterpret_cast<const uint2 *>(q + (long long)(2 * c + 1) * a.in.planeElems));
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < kUnroll; u++) {
-                        const int it = base + u * kGroupThreads + t;
-                        if (it < items) {
-                            if (a.nver == 2)   // raw copy for the taps that bypass the activation
-                                *reinterpret_cast<uint4 *>(dst + a.verBytes + (size_t)it * 16) = make_uint4(lo[u].x, lo[u].y, hi[u].x, hi[u].y);
-                            const uint2 l = act_h4(lo[u], a.act), h = act_h4(hi[u], a.act);
-                            *reinterpret_cast<uint4 *>(dst + (size_t)it * 16) = make_uint4(l.x, l.y, h.x, h.y);
-                        }
-                    }
-                }
-            } else {
-                // pixel-pair mode: chunk(px) = [pixel px | pixel px+1], 4 channels each
-                for (int px = t; px <= a.rowpx; px += kGroupThreads) {
-                    const int ix = min(max(j0 - a.x_lead + px + P, 0), a.in.texW - 1);
-                    float4 v = fyn_act4(fyn_load_texel(a.in, (long long)n * a.in.imageElems + ((long long)iy * a.in.texW + ix) * a.in.packing), a.act);
-                    const uint2 h = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
-                    if (px < a.rowpx) *reinterpret_cast<uint2 *>(dst + (size_t)px * 16) = h;
-                    if (px > 0) *reinterpret_cast<uint2 *>(dst + (size_t)(px - 1) * 16 + 8) = h;
+            for (int u = 0; u < kUnroll; u++) {
+                const int it = u * groupThreads + t;
+                gofs[u] = -1;
+                sofs[u] = it * 16;
+                if (it < items) {
+                    const int c = it / a.rowpx, px = it - c * a.rowpx;
+                    // stride 1: slot pixel = image pixel - (j0 - lead); stride 2: slot is [parity][pixel/2]
+                    const int gx = (a.ds == 1) ? j0 - a.x_lead + px : 2 * j0 - a.x_lead + 2 * (px % half) + (px / half);
+                    const int ix = min(max(gx + P, 0), a.in.texW - 1);
+                    // bit 0 flags "second plane present"; offsets are multiples of 4 elements
+                    gofs[u] = (int)((long long)(2 * c) * a.in.planeElems + (long long)ix * 4) | ((2 * c + 1 < a.nInPlanes) ? 1 : 0);
                 }
             }
-            fence_proxy_async();
-            mbar_arrive(&full[slot]);
+            const int planeEl = (int)a.in.planeElems;
+            for (int r = r0 + grp; r <= r1; r += ngroups) {
+                mbar_wait(&empty[pos.slot], (pos.fill & 1) ^ 1);
+                unsigned char *dst = sRing + (size_t)pos.slot * a.slotBytes;
+                const int iy = min(max(r + P, 0), a.in.texH - 1);   // texture row, CLAMP_TO_EDGE
+                const __half *rowp = src + (long long)iy * a.in.texW * 4;
+                uint2 lo[kUnroll], hi[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; u++) {
+                    lo[u] = make_uint2(0u, 0u);
+                    hi[u] = make_uint2(0u, 0u);
+                    if (gofs[u] >= 0) {
+                        const __half *q = rowp + (gofs[u] & ~1);
+                        lo[u] = __ldg(reinterpret_cast<const uint2 *>(q));
+                        if (gofs[u] & 1) hi[u] = __ldg(reinterpret_cast<const uint2 *>(q + planeEl));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; u++) {
+                    if (gofs[u] >= 0) {
+                        if (a.nver == 2)   // raw copy for the taps that bypass the activation
+                            *reinterpret_cast<uint4 *>(dst + a.verBytes + sofs[u]) = make_uint4(lo[u].x, lo[u].y, hi[u].x, hi[u].y);
+                        const uint2 l = act_h4(lo[u], a.act), h = act_h4(hi[u], a.act);
+                        *reinterpret_cast<uint4 *>(dst + sofs[u]) = make_uint4(l.x, l.y, h.x, h.y);
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&full[pos.slot]);
+                pos.advance(ngroups, a.nslots);
+            }
+        } else {
+            // pixel-pair mode: chunk(px) = [pixel px | pixel px+1], 4 channels each; thread item = one pixel
+            constexpr int kPix = 5;
+            int xofs[kPix];
+#pragma unroll
+            for (int u = 0; u < kPix; u++) {
+                const int px = u * groupThreads + t;
+                xofs[u] = (px <= a.rowpx) ? min(max(j0 - a.x_lead + px + P, 0), a.in.texW - 1) * a.in.packing : -1;
+            }
+            for (int r = r0 + grp; r <= r1; r += ngroups) {
+                mbar_wait(&empty[pos.slot], (pos.fill & 1) ^ 1);
+                unsigned char *dst = sRing + (size_t)pos.slot * a.slotBytes;
+                const int iy = min(max(r + P, 0), a.in.texH - 1);
+                const long long rowBase = (long long)n * a.in.imageElems + (long long)iy * a.in.texW * a.in.packing;
+                float4 v[kPix];
+#pragma unroll
+                for (int u = 0; u < kPix; u++)
+                    if (xofs[u] >= 0) v[u] = fyn_load_texel(a.in, rowBase + xofs[u]);
+#pragma unroll
+                for (int u = 0; u < kPix; u++) {
+                    if (xofs[u] >= 0) {
+                        const int px = u * groupThreads + t;
+                        const float4 w = fyn_act4(v[u], a.act);
+                        const uint2 h = make_uint2(pack_half2(w.x, w.y), pack_half2(w.z, w.w));
+                        if (px < a.rowpx) *reinterpret_cast<uint2 *>(dst + (size_t)px * 16) = h;
+                        if (px > 0) *reinterpret_cast<uint2 *>(dst + (size_t)(px - 1) * 16 + 8) = h;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&full[pos.slot]);
+                pos.advance(ngroups, a.nslots);
+            }
         }
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t wbase = smem_u32(sW), rbase = smem_u32(sRing);
-            int released = 0;
+            const uint32_t rbase16 = smem_u32(sRing) >> 4, slot16 = (uint32_t)a.slotBytes >> 4;
+            const uint32_t hiA = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1 (upper word)
+            RingPos win{0, 0};     // ring position of the current window's first row
+            RingPos rel{0, 0};     // next row to hand back
+            int winIdx = 0, released = 0;
             for (int q = 0; q < njobs; q++) {
                 const int buf = q & 1, use = q >> 1;
-                const TcPhaseY ph = a.phase[q % a.py];
-                const int first = a.rowAdvance * (ja + q / a.py) + ph.dyMin - r0;
+                const int fy = (a.py == 1) ? 0 : (q & 1);
+                const TcPhaseY ph = a.phase[fy];
+                const int first = a.rowAdvance * (ja + (a.py == 1 ? q : (q >> 1))) + ph.dyMin - r0;
+                win.advance(first - winIdx, a.nslots);
+                winIdx = first;
                 mbar_wait(&tempty[buf], (use & 1) ^ 1);
                 // all rows of this job's window must have landed
-                for (int k = 0; k < ph.nrows; k++) {
-                    const int idx = first + k;
-                    mbar_wait(&full[idx % a.nslots], (idx / a.nslots) & 1);
+                {
+                    RingPos w = win;
+                    for (int k = 0; k < ph.nrows; k++) {
+                        mbar_wait(&full[w.slot], w.fill & 1);
+                        w.advance(1, a.nslots);
+                    }
                 }
                 tc_fence_after();
                 const uint32_t d = tmem + (uint32_t)buf * 64u;
+                SmemStep st = sSteps[ph.stepBegin];
                 for (int s = ph.stepBegin; s < ph.stepEnd; s++) {
-                    const TcStep st = a.steps[s];
-                    const int idx = first + st.row;
-                    const uint32_t aaddr = rbase + (uint32_t)(idx % a.nslots) * (uint32_t)a.slotBytes + st.a_off;
-                    umma_f16(d + (uint32_t)st.acc * (uint32_t)a.N, make_desc(aaddr, st.a_lbo, 128), make_desc(wbase + st.b_off, a.b_lbo, 128),
-                             a.idesc, st.first ? 0u : 1u);
+                    const SmemStep nx = sSteps[min(s + 1, ph.stepEnd - 1)];
+                    int sl = win.slot + (int)(st.rowAcc & 0xff);
+                    if (sl >= a.nslots) sl -= a.nslots;
+                    const uint64_t adesc = ((uint64_t)hiA << 32) | (uint64_t)(st.a_lo + rbase16 + (uint32_t)sl * slot16);
+                    const uint64_t bdesc = ((uint64_t)hiA << 32) | (uint64_t)st.b_lo;
+                    umma_f16(d + st.tmemOff, adesc, bdesc, a.idesc, (st.rowAcc >> 8) ? 0u : 1u);
+                    st = nx;
                 }
                 umma_commit(&tfull[buf]);
                 // rows that no later job needs go back to the loaders
                 int keepFrom = r1 - r0 + 1;
-                if (q + 1 < njobs) keepFrom = a.rowAdvance * (ja + (q + 1) / a.py) + a.phase[(q + 1) % a.py].dyMin - r0;
-                for (; released < keepFrom; released++) umma_commit(&empty[released % a.nslots]);
+                if (q + 1 < njobs) {
+                    const int q1 = q + 1, fy1 = (a.py == 1) ? 0 : (q1 & 1);
+                    keepFrom = a.rowAdvance * (ja + (a.py == 1 ? q1 : (q1 >> 1))) + a.phase[fy1].dyMin - r0;
+                }
+                for (; released < keepFrom; released++) {
+                    umma_commit(&empty[rel.slot]);
+                    rel.advance(1, a.nslots);
+                }
             }
         }
     } else {
@@ -348,35 +420,65 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         const int m = threadIdx.x;           // 0..127 == TMEM lane
         const int jx = j0 + m;
         const bool valid = jx < a.Wj;
+        const int groups = a.N >> 4;
+        const bool resFast = a.hasRes && a.px == 1 && a.res.dtype == FYN_F16 && a.res.packing == 4 && !a.res.deep;
         for (int q = 0; q < njobs; q++) {
             const int buf = q & 1, use = q >> 1;
-            const int yo = a.py * (ja + q / a.py) + (q % a.py);
+            const int yo = (a.py == 1) ? ja + q : 2 * (ja + (q >> 1)) + (q & 1);
+            // residual texels are fetched before waiting for the accumulator so their latency hides behind the MMAs
+            uint2 rres[16];
+            if (resFast && valid) {
+                const __half *rp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems +
+                                   ((long long)(a.resP + yo) * a.res.texW + a.resP + jx) * 4;
+#pragma unroll
+                for (int p = 0; p < 16; p++)
+                    if (p < a.nOutPlanes) rres[p] = __ldg(reinterpret_cast<const uint2 *>(rp + (long long)p * a.res.planeElems));
+            }
             mbar_wait(&tfull[buf], use & 1);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * 64u;
-            const int groups = a.N / 16;
-            for (int g = 0; g < groups; g++) {
-                uint32_t r[16], r2[16];
-                tmem_ld16(taddr + g * 16, r);
-                if (a.px == 2) tmem_ld16(taddr + a.N + g * 16, r2);
-                tmem_ld_wait();
-                if (g == groups - 1) {
-                    // accumulators fully read: hand the buffer back before doing the global-memory work
-                    tc_fence_before();
-                    mbar_arrive(&tempty[buf]);
-                }
+            uint32_t acc[4][16];
+            const int total = groups * a.px;    // 16-column groups in this buffer (accumulators are contiguous)
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int p = g * 4 + k;
-                    if (p < a.nOutPlanes && valid) {
-                        if (a.px == 1) {
-                            fyn_store_texel(a.out, n, p, a.outP + jx, a.outP + yo, epilogue4(a, r + 4 * k, p, n, jx, yo));
-                        } else {
-                            // two x phases -> two adjacent output texels
-                            const float4 v0 = epilogue4(a, r + 4 * k, p, n, 2 * jx, yo);
-                            const float4 v1 = epilogue4(a, r2 + 4 * k, p, n, 2 * jx + 1, yo);
-                            fyn_store_texel(a.out, n, p, a.outP + 2 * jx, a.outP + yo, v0);
-                            fyn_store_texel(a.out, n, p, a.outP + 2 * jx + 1, a.outP + yo, v1);
+            for (int g = 0; g < 4; g++)
+                if (g < total) tmem_ld16(taddr + g * 16, acc[g]);
+            tmem_ld_wait();
+            // accumulators are in registers: hand the TMEM buffer back before the global-memory work
+            tc_fence_before();
+            mbar_arrive(&tempty[buf]);
+            if (valid) {
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    if (g < total) {
+                        const int fx = (g >= groups) ? 1 : 0;          // x phase of this group
+                        const int gp = g - fx * groups;                // group inside the accumulator
+                        const int xo = a.px * jx + fx;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int p = gp * 4 + k;
+                            if (p < a.nOutPlanes) {
+                                const float4 bi = sEpi[p], sc = sEpi[16 + p];
+                                float4 v = make_float4(fmaf(__uint_as_float(acc[g][4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[g][4 * k + 1]), sc.y, bi.y),
+                                                       fmaf(__uint_as_float(acc[g][4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[g][4 * k + 3]), sc.w, bi.w));
+                                if (a.hasRes) {
+                                    float4 rs;
+                                    if (resFast) {
+                                        const uint2 raw = rres[p];
+                                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+                                        const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+                                        rs = make_float4(f0.x, f0.y, f1.x, f1.y);
+                                    } else {
+                                        rs = fyn_fetch(a.res, n, p, a.resP + xo, a.resP + yo);
+                                    }
+                                    if (a.reluRes) rs = make_float4(fmaxf(rs.x, 0.f), fmaxf(rs.y, 0.f), fmaxf(rs.z, 0.f), fmaxf(rs.w, 0.f));
+                                    if (a.bnRes) rs = make_float4(rs.x * sc.x, rs.y * sc.y, rs.z * sc.z, rs.w * sc.w);
+                                    v.x += rs.x;
+                                    v.y += rs.y;
+                                    v.z += rs.z;
+                                    v.w += rs.w;
+                                }
+                                fyn_store_texel(a.out, n, p, a.outP + xo, a.outP + yo, v);
+                            }
                         }
                     }
                 }
@@ -417,7 +519,7 @@ struct Geometry {
     int mode = 0, py = 1, px = 1, rowAdvance = 1, nver = 1, N = 16, nchunks = 1, rowpx = 0, x_lead = 0, ds = 1;
     int dxMin = 0, dxMax = 0;
     int dyMin[2] = {0, 0}, dyMax[2] = {0, 0};
-    int nslots = 0, slotBytes = 0, verBytes = 0, nsteps = 0;
+    int nslots = 0, slotBytes = 0, verBytes = 0, nsteps = 0, groupWarps = 4;
     size_t wbytes = 0, smem = 0;
     std::vector<PhasePlan> phases;   // [py*px], index fy*px+fx (weights only filled when wb != nullptr)
     bool ok = false;
@@ -531,7 +633,12 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb) {
     g.slotBytes = g.verBytes * g.nver;
     int maxRows = 0;
     for (int f = 0; f < g.py; f++) maxRows = std::max(maxRows, g.dyMax[f] - g.dyMin[f] + 1);
-    g.nslots = maxRows + 2 * g.rowAdvance + 1;
+    // loader groups: small rows (pixel-pair mode) are loaded one warp per row so that many rows are in flight
+    g.groupWarps = (g.mode == 1) ? 1 : 4;
+    const int ngroups = kLoaderWarps / g.groupWarps;
+    if (g.mode == 0 && g.rowpx * g.nchunks > kUnroll * g.groupWarps * 32) return g;   // a row must fit one batch
+    if (g.mode == 1 && g.rowpx + 1 > 5 * g.groupWarps * 32) return g;
+    g.nslots = maxRows + std::max(ngroups, 2) * g.rowAdvance + 1;
     // steps: per phase, chunks of the same window row are paired in address order
     int nsteps = 0;
     for (const PhasePlan &pp : g.phases) {
@@ -550,7 +657,7 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb) {
     g.nsteps = nsteps;
     if (nsteps > kMaxSteps) return g;
     g.wbytes = (size_t)nsteps * 2 * g.N * 16;
-    g.smem = ((g.wbytes + 127) & ~(size_t)127) + (size_t)g.nslots * g.slotBytes + (2 * g.nslots + 4) * 8 + 16;
+    g.smem = ((g.wbytes + 127) & ~(size_t)127) + (size_t)g.nslots * g.slotBytes + (size_t)kMaxSteps * 16 + 32 * 16 + (2 * g.nslots + 4) * 8 + 16;
     if (g.smem > 220 * 1024) return g;
     g.ok = true;
     return g;
@@ -583,6 +690,8 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     a.rowpx = g.rowpx;
     a.x_lead = g.x_lead;
     a.nslots = g.nslots;
+    a.nsteps = g.nsteps;
+    a.groupWarps = g.groupWarps;
     a.slotBytes = g.slotBytes;
     a.idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);  // F32 accum, F16 x F16, K-major A/B
     a.b_lbo = (uint32_t)N * 16u;

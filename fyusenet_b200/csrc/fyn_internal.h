@@ -151,6 +151,8 @@ __device__ __forceinline__ long long fyn_texel_index(const TView &v, int n, int 
     return base + ((long long)y * v.texW + x) * v.packing;
 }
 
+// texel load; packing < 4 (upload textures) reads the stored lanes only, missing lanes are 0.  Written without
+// dynamically indexed temporaries so everything stays in registers.
 __device__ __forceinline__ float4 fyn_load_texel(const TView &v, long long idx) {
     if (v.dtype == FYN_F16) {
         const __half *p = reinterpret_cast<const __half *>(v.ptr) + idx;
@@ -160,15 +162,17 @@ __device__ __forceinline__ float4 fyn_load_texel(const TView &v, long long idx) 
             float2 fa = __half22float2(a), fb = __half22float2(b);
             return make_float4(fa.x, fa.y, fb.x, fb.y);
         }
-        float r[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int i = 0; i < v.packing; i++) r[i] = __half2float(p[i]);
-        return make_float4(r[0], r[1], r[2], r[3]);
+        const float x = __half2float(p[0]);
+        const float y = v.packing > 1 ? __half2float(p[1]) : 0.f;
+        const float z = v.packing > 2 ? __half2float(p[2]) : 0.f;
+        return make_float4(x, y, z, 0.f);
     }
     const float *p = reinterpret_cast<const float *>(v.ptr) + idx;
     if (v.packing == 4) return __ldg(reinterpret_cast<const float4 *>(p));
-    float r[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int i = 0; i < v.packing; i++) r[i] = __ldg(p + i);
-    return make_float4(r[0], r[1], r[2], r[3]);
+    const float x = __ldg(p);
+    const float y = v.packing > 1 ? __ldg(p + 1) : 0.f;
+    const float z = v.packing > 2 ? __ldg(p + 2) : 0.f;
+    return make_float4(x, y, z, 0.f);
 }
 
 __device__ __forceinline__ float4 fyn_fetch(const TView &v, int n, int pt, int x, int y) {
