@@ -47,15 +47,12 @@ constexpr int kThreads = (kMmaWarp + 1) * 32;       // 416
 constexpr int kUnroll = 7;                           // (pixel, chunk) items per loader thread and row (all in flight)
 constexpr int kTileM = 128;
 
-// one tcgen05.mma (M=128, N, K=16)
-struct TcStep {
-    uint32_t a_off;   // byte offset of the first K-chunk inside its ring slot (includes the version offset)
-    uint32_t a_lbo;   // byte distance to the second K-chunk
-    uint32_t b_off;   // byte offset inside the weight image
-    int8_t row;       // ring row relative to the first row of the job's window
-    uint8_t acc;      // accumulator (x phase)
-    uint8_t first;    // 1 = overwrite the accumulator
-    uint8_t pad;
+// one tcgen05.mma (M=128, N, K=16), pre-encoded for the issuing warp (16 bytes: one constant-bank load)
+struct __align__(16) TcStep {
+    uint32_t a_lo;    // (LBO >> 4) << 16 | (a_off >> 4): add (slot base >> 4) to get the A descriptor's low word
+    uint32_t b_off16; // byte offset inside the weight image >> 4
+    uint32_t tmemOff; // accumulator column offset inside the TMEM buffer
+    uint32_t rowFirst; // ring row relative to the first row of the job's window | (first ? 256 : 0)
 };
 
 // the jobs of one y phase: window of input rows and its slice of the step table
@@ -146,6 +143,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// one deterministic leader lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptors (K-major, SWIZZLE_NONE "interleave"): core matrix = 8 rows x 16 bytes stored
@@ -186,14 +195,6 @@ __device__ __forceinline__ uint2 act_h4(uint2 v, const ActParams &a) {
 // fractional convs one (source row, y phase) pair producing px accumulators (one per x phase).  Jobs are
 // processed in order; the window of input rows only moves forward, so the ring of row slots is a FIFO.
 
-// step as the MMA thread consumes it: everything that does not depend on the ring position is pre-encoded
-struct SmemStep {
-    uint32_t a_lo;    // (LBO >> 4) << 16 | (a_off >> 4): add (slot base >> 4) to get the descriptor's low word
-    uint32_t b_lo;    // low word of the B descriptor (start address and LBO)
-    uint32_t tmemOff; // accumulator column offset
-    uint32_t rowAcc;  // row | first << 8
-};
-
 // position in the ring without divisions
 struct RingPos {
     int slot, fill;
@@ -210,8 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sW = smem;
     unsigned char *sRing = smem + ((a.wbytes + 127) & ~127u);
-    SmemStep *sSteps = reinterpret_cast<SmemStep *>(sRing + (size_t)a.nslots * a.slotBytes);
-    float4 *sEpi = reinterpret_cast<float4 *>(sSteps + kMaxSteps);        // [16] bias planes then [16] scale planes
+    float4 *sEpi = reinterpret_cast<float4 *>(sRing + (size_t)a.nslots * a.slotBytes);   // [16] bias planes, [16] scale planes
     uint64_t *bars = reinterpret_cast<uint64_t *>(sEpi + 32);
     uint64_t *full = bars;                     // [nslots]
     uint64_t *empty = bars + a.nslots;         // [nslots]
@@ -219,7 +219,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     uint64_t *tempty = tfull + 2;              // [2]
     uint32_t *tmemBase = reinterpret_cast<uint32_t *>(tempty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a broadcast so the compiler treats the role dispatch (and everything derived from it) as
+    // warp-uniform; lane is only used by the loaders / epilogue
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    (void)lane;
 
     // strip decode: blockIdx.x -> (image, column block, row segment)
     int bid = blockIdx.x;
@@ -252,16 +255,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     // weight image -> shared memory (all threads, 16-byte copies), visible to the async proxy
     for (uint32_t i = threadIdx.x; i < a.wbytes / 16; i += kThreads) reinterpret_cast<uint4 *>(sW)[i] = __ldg(a.wimg + i);
     {
-        const uint32_t wbase = smem_u32(sW);
-        for (int i = threadIdx.x; i < a.nsteps; i += kThreads) {
-            const TcStep st = a.steps[i];
-            SmemStep o;
-            o.a_lo = ((st.a_lbo >> 4) << 16) | (st.a_off >> 4);
-            o.b_lo = (((wbase + st.b_off) >> 4) & 0x3FFF) | ((a.b_lbo >> 4) << 16);
-            o.tmemOff = (uint32_t)st.acc * (uint32_t)a.N;
-            o.rowAcc = (uint32_t)(uint8_t)st.row | ((uint32_t)st.first << 8);
-            sSteps[i] = o;
-        }
         for (int i = threadIdx.x; i < 32; i += kThreads) {
             const int p = i & 15;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -368,52 +361,57 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         }
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t rbase16 = smem_u32(sRing) >> 4, slot16 = (uint32_t)a.slotBytes >> 4;
-            const uint32_t hiA = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1 (upper word)
-            RingPos win{0, 0};     // ring position of the current window's first row
-            RingPos rel{0, 0};     // next row to hand back
-            int winIdx = 0, released = 0;
-            for (int q = 0; q < njobs; q++) {
-                const int buf = q & 1, use = q >> 1;
-                const int fy = (a.py == 1) ? 0 : (q & 1);
-                const TcPhaseY ph = a.phase[fy];
-                const int first = a.rowAdvance * (ja + (a.py == 1 ? q : (q >> 1))) + ph.dyMin - r0;
-                win.advance(first - winIdx, a.nslots);
-                winIdx = first;
+        // The whole warp runs this loop with warp-uniform values (step table in parameter space, ring position
+        // derived from block-uniform data) so the descriptors are built in uniform registers; lane 0 waits on the
+        // barriers and issues the tcgen05 instructions.
+        const uint32_t rbase16 = smem_u32(sRing) >> 4, slot16 = (uint32_t)a.slotBytes >> 4;
+        const uint32_t wbase16 = smem_u32(sW) >> 4, blbo = (a.b_lbo >> 4) << 16;
+        const uint64_t hiA = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
+        RingPos win{0, 0};     // ring position of the current window's first row
+        RingPos rel{0, 0};     // next row to hand back
+        int winIdx = 0, released = 0, waited = 0;
+        for (int q = 0; q < njobs; q++) {
+            const int buf = q & 1, use = q >> 1;
+            const int fy = (a.py == 1) ? 0 : (q & 1);
+            const int first = a.rowAdvance * (ja + (a.py == 1 ? q : (q >> 1))) + a.phase[fy].dyMin - r0;
+            const int nrows = a.phase[fy].nrows, sBegin = a.phase[fy].stepBegin, sEnd = a.phase[fy].stepEnd;
+            win.advance(first - winIdx, a.nslots);
+            winIdx = first;
+            const bool leader = elect_one();
+            if (leader) {
                 mbar_wait(&tempty[buf], (use & 1) ^ 1);
-                // all rows of this job's window must have landed
-                {
-                    RingPos w = win;
-                    for (int k = 0; k < ph.nrows; k++) {
-                        mbar_wait(&full[w.slot], w.fill & 1);
-                        w.advance(1, a.nslots);
-                    }
-                }
-                tc_fence_after();
-                const uint32_t d = tmem + (uint32_t)buf * 64u;
-                SmemStep st = sSteps[ph.stepBegin];
-                for (int s = ph.stepBegin; s < ph.stepEnd; s++) {
-                    const SmemStep nx = sSteps[min(s + 1, ph.stepEnd - 1)];
-                    int sl = win.slot + (int)(st.rowAcc & 0xff);
-                    if (sl >= a.nslots) sl -= a.nslots;
-                    const uint64_t adesc = ((uint64_t)hiA << 32) | (uint64_t)(st.a_lo + rbase16 + (uint32_t)sl * slot16);
-                    const uint64_t bdesc = ((uint64_t)hiA << 32) | (uint64_t)st.b_lo;
-                    umma_f16(d + st.tmemOff, adesc, bdesc, a.idesc, (st.rowAcc >> 8) ? 0u : 1u);
-                    st = nx;
-                }
-                umma_commit(&tfull[buf]);
-                // rows that no later job needs go back to the loaders
-                int keepFrom = r1 - r0 + 1;
-                if (q + 1 < njobs) {
-                    const int q1 = q + 1, fy1 = (a.py == 1) ? 0 : (q1 & 1);
-                    keepFrom = a.rowAdvance * (ja + (a.py == 1 ? q1 : (q1 >> 1))) + a.phase[fy1].dyMin - r0;
-                }
-                for (; released < keepFrom; released++) {
-                    umma_commit(&empty[rel.slot]);
-                    rel.advance(1, a.nslots);
+                // rows of this job's window that no earlier job has waited for
+                RingPos w = win;
+                for (int k = 0; k < nrows; k++) {
+                    if (first + k >= waited) mbar_wait(&full[w.slot], w.fill & 1);
+                    w.advance(1, a.nslots);
                 }
             }
+            waited = max(waited, first + nrows);
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t d = tmem + (uint32_t)buf * 64u;
+#pragma unroll 4
+            for (int s = sBegin; s < sEnd; s++) {
+                const TcStep st = a.steps[s];
+                int sl = win.slot + (int)(st.rowFirst & 0xffu);
+                if (sl >= a.nslots) sl -= a.nslots;
+                const uint64_t adesc = hiA | (uint64_t)(st.a_lo + rbase16 + (uint32_t)sl * slot16);
+                const uint64_t bdesc = hiA | (uint64_t)((wbase16 + st.b_off16) | blbo);
+                if (leader) umma_f16(d + st.tmemOff, adesc, bdesc, a.idesc, (st.rowFirst >> 8) ? 0u : 1u);
+            }
+            // rows that no later job needs go back to the loaders
+            int keepFrom = r1 - r0 + 1;
+            if (q + 1 < njobs) {
+                const int q1 = q + 1, fy1 = (a.py == 1) ? 0 : (q1 & 1);
+                keepFrom = a.rowAdvance * (ja + (a.py == 1 ? q1 : (q1 >> 1))) + a.phase[fy1].dyMin - r0;
+            }
+            if (leader) umma_commit(&tfull[buf]);
+            for (; released < keepFrom; released++) {
+                if (leader) umma_commit(&empty[rel.slot]);
+                rel.advance(1, a.nslots);
+            }
+            __syncwarp();
         }
     } else {
         // ===================== epilogue: warps 0-3, thread = job column =====================
@@ -657,7 +655,7 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb) {
     g.nsteps = nsteps;
     if (nsteps > kMaxSteps) return g;
     g.wbytes = (size_t)nsteps * 2 * g.N * 16;
-    g.smem = ((g.wbytes + 127) & ~(size_t)127) + (size_t)g.nslots * g.slotBytes + (size_t)kMaxSteps * 16 + 32 * 16 + (2 * g.nslots + 4) * 8 + 16;
+    g.smem = ((g.wbytes + 127) & ~(size_t)127) + (size_t)g.nslots * g.slotBytes + 32 * 16 + (2 * g.nslots + 4) * 8 + 16;
     if (g.smem > 220 * 1024) return g;
     g.ok = true;
     return g;
@@ -742,22 +740,18 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
                 };
                 for (size_t i = 0; i < chunks.size(); i += 2) {
                     TcStep &st = a.steps[s];
-                    st.row = (int8_t)(dy - g.dyMin[fy]);
-                    st.acc = (uint8_t)fx;
-                    st.first = firstOfAcc ? 1 : 0;
-                    st.pad = 0;
+                    st.rowFirst = (uint32_t)(dy - g.dyMin[fy]) | (firstOfAcc ? 256u : 0u);
+                    st.tmemOff = (uint32_t)(fx * N);
                     firstOfAcc = false;
-                    st.a_off = chunks[i].off;
-                    st.b_off = (uint32_t)((size_t)s * 2 * N * 16);
+                    st.b_off16 = (uint32_t)(((size_t)s * 2 * N * 16) >> 4);
                     fill((size_t)s * 2, chunks[i]);
+                    uint32_t lbo = 16;  // unpaired: second half reads the neighbouring pixel against all-zero weights
                     if (i + 1 < chunks.size()) {
-                        st.a_lbo = chunks[i + 1].off - chunks[i].off;
+                        lbo = chunks[i + 1].off - chunks[i].off;
                         fill((size_t)s * 2 + 1, chunks[i + 1]);
-                        if (st.a_lbo == 0 || st.a_lbo >= (1u << 18))
-                            FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 conv: operand stride %u not encodable", st.a_lbo);
-                    } else {
-                        st.a_lbo = 16;  // second half reads the neighbouring pixel against all-zero weights
+                        if (lbo == 0 || lbo >= (1u << 18)) FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 conv: operand stride %u not encodable", lbo);
                     }
+                    st.a_lo = ((lbo >> 4) << 16) | (chunks[i].off >> 4);
                     s++;
                 }
             }
