@@ -27,6 +27,13 @@
 // activation on the first horizontal tap only -- the ring slot then holds two versions of the row (activated and
 // raw) and the first-tap weights are routed to the activated version.
 //
+// Phase stacking.  A tcgen05.mma with M=128, K=16 costs ~(4096 + 32 N)/128 cycles for N <= 64 because its A tile
+// (4 KB) comes from shared memory (measured: 46 cycles for N = 16..48, tools/ubench/umma_issue.cu), so thin
+// layers are bound by the NUMBER of MMAs, not by their FLOPs.  All output phases that read the same source window
+// are therefore stacked along N: n = phase * Cq + co.  One GEMM row then produces p_y x p_x output pixels
+// (fractional convs) or four horizontally adjacent pixels (the 3-channel pixel-pair mode), with structural zeros in
+// the weight image where a phase does not use a tap.
+//
 // Warp roles (416 threads): warps 0-3 epilogue (TMEM -> registers -> bias/BN/residual -> fp16 planes),
 // warps 4-11 loaders (two groups of four warps on alternating input rows, so two rows are always in flight),
 // warp 12 issues tcgen05.mma (one elected lane).
@@ -40,46 +47,54 @@
 
 namespace {
 
-constexpr int kMaxSteps = 128;
-constexpr int kLoaderWarps = 8;                       // two groups of four
+#ifdef FYN_TC_PROFILE
+#define PROF_DECL(n) long long n = 0
+#define PROF_T() clock64()
+#define PROF_ADD(acc, t0) acc += clock64() - (t0)
+#else
+#define PROF_DECL(n)
+#define PROF_T() 0
+#define PROF_ADD(acc, t0)
+#endif
+
+constexpr int kMaxSteps = 96;
+constexpr int kLoaderWarps = 8;
 constexpr int kMmaWarp = 4 + kLoaderWarps;
 constexpr int kThreads = (kMmaWarp + 1) * 32;       // 416
 constexpr int kUnroll = 7;                           // (pixel, chunk) items per loader thread and row (all in flight)
+constexpr int kPix = 9;                              // pixels per loader thread and row in pixel-pair mode
 constexpr int kTileM = 128;
+constexpr int kMaxRows = 11;
 
 // one tcgen05.mma (M=128, N, K=16), pre-encoded for the issuing warp (16 bytes: one constant-bank load)
 struct __align__(16) TcStep {
-    uint32_t a_lo;    // (LBO >> 4) << 16 | (a_off >> 4): add (slot base >> 4) to get the A descriptor's low word
-    uint32_t b_off16; // byte offset inside the weight image >> 4
-    uint32_t tmemOff; // accumulator column offset inside the TMEM buffer
-    uint32_t rowFirst; // ring row relative to the first row of the job's window | (first ? 256 : 0)
-};
-
-// the jobs of one y phase: window of input rows and its slice of the step table
-struct TcPhaseY {
-    int dyMin, nrows, stepBegin, stepEnd;
+    uint32_t a_lo;       // (LBO >> 4) << 16 | ((window row * slot bytes + chunk offset) >> 4): add the window base >> 4
+    uint32_t b_off16;    // byte offset inside the weight image >> 4
+    uint32_t accumulate; // 0 = overwrite the accumulator (first step of a job), 1 = accumulate
+    uint32_t pad;
 };
 
 struct TcArgs {
     TView in, out, res;
     const uint4 *wimg;
-    const float *bias, *scale;
+    const float *bias, *scale;   // [16 planes] float4 each, indexed by output plane
     uint32_t wbytes, idesc, b_lbo;
-    int nsteps, groupWarps;  // MMA steps in the table; warps per loader group (1, 2 or 4)
-    int py, px;              // output phases per source row / column (1 for regular convs)
-    int rowAdvance;          // input rows the window moves per group of py jobs (stride, 1 for fractional)
-    TcPhaseY phase[2];
+    int nsteps, groupWarps;  // MMA steps per job; warps per loader group (1, 2 or 4)
+    int rowAdvance;          // input rows the window moves per job (stride; 1 for fractional)
+    int dyMin, nrows;        // window: input rows [rowAdvance*i + dyMin, +nrows)
     TcStep steps[kMaxSteps];
+    int opx, opy;            // output phases stacked along N (output pixel = (opx*j + fx, opy*i + fy))
+    int planesPerPhase;      // 4-channel planes per phase (Cq / 4)
     int Wo, Ho;              // output net size
-    int Hj, Wj;              // job-space size: output rows / py, output columns / px
+    int Hj, Wj;              // job-space size: ceil(Ho / opy) rows, ceil(Wo / opx) columns
     int inP, outP, resP;
-    int nchunks, rowpx;      // chunks per version, pixels per chunk row
+    int nchunks, rowpx;      // mode 0: chunks per version and pixels per chunk row; mode 1: rowpx = chunks per slot
     int nver, verBytes;      // slot versions: 0 = activated (or the only one), 1 = raw
-    int nslots, slotBytes;
+    int nslots, slotBytes;   // logical ring slots; the first nrows-1 slots are mirrored behind the ring
     int SH, nxs;             // job rows per strip, column blocks
-    int N, nOutPlanes, nInPlanes;
-    int mode;                // 0 = plane-pair chunks (fp16 RGBA planes), 1 = pixel-pair (single plane)
-    int ds;                  // horizontal stride of the slot layout (2 = even/odd split)
+    int N, nInPlanes;
+    int mode;                // 0 = plane-pair chunks (fp16 RGBA planes), 1 = pixel-pair chunks (single plane, 4 px per GEMM row)
+    int ds;                  // mode 0: horizontal stride of the slot layout (2 = even/odd split)
     int x_lead;              // input pixels to the left of job column 0 held in a slot
     ActParams act;
     int hasRes, reluRes, bnRes;
@@ -97,16 +112,18 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Blocking wait with a large suspend-time hint: the warp sleeps in hardware until the phase completes instead of
+// polling (12 polling warps otherwise compete with the tensor core for shared-memory bandwidth).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -167,8 +184,6 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-
-
 __device__ __forceinline__ uint2 relu_h4(uint2 v) {
     const __half2 z = __float2half2_rn(0.f);
     __half2 *q = reinterpret_cast<__half2 *>(&v);
@@ -180,20 +195,10 @@ __device__ __forceinline__ uint2 relu_h4(uint2 v) {
 __device__ __forceinline__ uint2 act_h4(uint2 v, const ActParams &a) {
     if (a.type == 1) return relu_h4(v);
     if (a.type == 0) return v;
-    __half *q = reinterpret_cast<__half *>(&v);
-    for (int j = 0; j < 4; j++) q[j] = __float2half_rn(fyn_act(__half2float(q[j]), a));
-    return v;
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&v.x));
+    const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&v.y));
+    return make_uint2(pack_half2(fyn_act(f0.x, a), fyn_act(f0.y, a)), pack_half2(fyn_act(f1.x, a), fyn_act(f1.y, a)));
 }
-
-// ---------------------------------------------------------------------------------------------
-// kernel
-// ---------------------------------------------------------------------------------------------
-// dynamic shared memory: [weight image][ring slots][step table][epilogue params][barriers][tmem base]
-//
-// Work decomposition.  The output is cut into strips: 128 job columns x SH job rows; one CTA per strip.  A "job"
-// is one accumulation group: for regular convs one output row of the strip (window = K input rows), for
-// fractional convs one (source row, y phase) pair producing px accumulators (one per x phase).  Jobs are
-// processed in order; the window of input rows only moves forward, so the ring of row slots is a FIFO.
 
 // position in the ring without divisions
 struct RingPos {
@@ -207,11 +212,21 @@ struct RingPos {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+// dynamic shared memory: [weight image][ring slots + mirror slots][epilogue params][barriers][tmem base]
+//
+// Work decomposition.  The job space (output rows / opy, output columns / opx) is cut into strips of 128 job
+// columns x SH job rows; one CTA per strip.  A job is one GEMM accumulation: 128 job columns of one job row, i.e.
+// 128 x opx output pixels of opy output rows, reading a window of `nrows` input rows that only moves forward, so
+// the ring of row slots is a FIFO.  The first nrows-1 slots are mirrored behind the ring so that every window is
+// contiguous in shared memory and the A descriptor of a step is (window base + constant).
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sW = smem;
     unsigned char *sRing = smem + ((a.wbytes + 127) & ~127u);
-    float4 *sEpi = reinterpret_cast<float4 *>(sRing + (size_t)a.nslots * a.slotBytes);   // [16] bias planes, [16] scale planes
+    float4 *sEpi = reinterpret_cast<float4 *>(sRing + (size_t)(a.nslots + a.nrows - 1) * a.slotBytes);   // [16] bias, [16] scale
     uint64_t *bars = reinterpret_cast<uint64_t *>(sEpi + 32);
     uint64_t *full = bars;                     // [nslots]
     uint64_t *empty = bars + a.nslots;         // [nslots]
@@ -220,9 +235,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     uint32_t *tmemBase = reinterpret_cast<uint32_t *>(tempty + 2);
 
     // warp index through a broadcast so the compiler treats the role dispatch (and everything derived from it) as
-    // warp-uniform; lane is only used by the loaders / epilogue
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    (void)lane;
+    // warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
 
     // strip decode: blockIdx.x -> (image, column block, row segment)
     int bid = blockIdx.x;
@@ -232,12 +246,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     const int seg = bid % nseg;
     const int n = bid / nseg;
     const int ja = seg * a.SH, jb = min(a.Hj, ja + a.SH);   // job rows [ja, jb)
-    const int njobs = (jb - ja) * a.py;
+    const int njobs = jb - ja;
     const int j0 = xb * kTileM;                               // first job column
-    // window of job q: first input row = rowAdvance*(ja + q/py) + dyMin[q%py]
-    const int r0 = a.rowAdvance * ja + a.phase[0].dyMin;
-    int r1 = r0;
-    for (int f = 0; f < a.py; f++) r1 = max(r1, a.rowAdvance * (jb - 1) + a.phase[f].dyMin + a.phase[f].nrows - 1);
+    const int r0 = a.rowAdvance * ja + a.dyMin;               // first / last input row of the strip (unclamped)
+    const int r1 = a.rowAdvance * (jb - 1) + a.dyMin + a.nrows - 1;
 
     const int groupThreads = a.groupWarps * 32;
     if (threadIdx.x == 0) {
@@ -254,14 +266,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     if (warp == kMmaWarp) tmem_alloc(tmemBase, 128);
     // weight image -> shared memory (all threads, 16-byte copies), visible to the async proxy
     for (uint32_t i = threadIdx.x; i < a.wbytes / 16; i += kThreads) reinterpret_cast<uint4 *>(sW)[i] = __ldg(a.wimg + i);
-    {
-        for (int i = threadIdx.x; i < 32; i += kThreads) {
-            const int p = i & 15;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p * 4 < a.N) v = __ldg(reinterpret_cast<const float4 *>(i < 16 ? a.bias : a.scale) + p);
-            sEpi[i] = v;
-        }
-    }
+    for (int i = threadIdx.x; i < 32; i += kThreads)
+        sEpi[i] = __ldg(reinterpret_cast<const float4 *>(i < 16 ? a.bias : a.scale) + (i & 15));
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -274,8 +280,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         const int grp = (warp - 4) / a.groupWarps;
         const int t = (threadIdx.x - 128) - grp * groupThreads;   // thread index inside the group
         const int P = a.inP;
+        const int mirrorOff = a.nslots * a.slotBytes;             // slots < nrows-1 are also written behind the ring
         RingPos pos{0, 0};
         pos.advance(grp, a.nslots);
+        PROF_DECL(pLdWait);
+        [[maybe_unused]] const long long pLdStart = PROF_T();
         if (a.mode == 0) {
             // Per-thread item table (row independent): item = (pixel, chunk) -> two 8-byte plane loads and one
             // 16-byte chunk store per version.  All loads of a row are issued before the first store.
@@ -298,8 +307,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             }
             const int planeEl = (int)a.in.planeElems;
             for (int r = r0 + grp; r <= r1; r += ngroups) {
+                [[maybe_unused]] const long long pt = PROF_T();
                 mbar_wait(&empty[pos.slot], (pos.fill & 1) ^ 1);
+                PROF_ADD(pLdWait, pt);
                 unsigned char *dst = sRing + (size_t)pos.slot * a.slotBytes;
+                const bool mirror = pos.slot < a.nrows - 1;
                 const int iy = min(max(r + P, 0), a.in.texH - 1);   // texture row, CLAMP_TO_EDGE
                 const __half *rowp = src + (long long)iy * a.in.texW * 4;
                 uint2 lo[kUnroll], hi[kUnroll];
@@ -316,10 +328,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
 #pragma unroll
                 for (int u = 0; u < kUnroll; u++) {
                     if (gofs[u] >= 0) {
-                        if (a.nver == 2)   // raw copy for the taps that bypass the activation
-                            *reinterpret_cast<uint4 *>(dst + a.verBytes + sofs[u]) = make_uint4(lo[u].x, lo[u].y, hi[u].x, hi[u].y);
+                        const uint4 raw = make_uint4(lo[u].x, lo[u].y, hi[u].x, hi[u].y);
                         const uint2 l = act_h4(lo[u], a.act), h = act_h4(hi[u], a.act);
-                        *reinterpret_cast<uint4 *>(dst + sofs[u]) = make_uint4(l.x, l.y, h.x, h.y);
+                        const uint4 av = make_uint4(l.x, l.y, h.x, h.y);
+                        *reinterpret_cast<uint4 *>(dst + sofs[u]) = av;
+                        if (a.nver == 2) *reinterpret_cast<uint4 *>(dst + a.verBytes + sofs[u]) = raw;   // taps that bypass the activation
+                        if (mirror) {
+                            *reinterpret_cast<uint4 *>(dst + mirrorOff + sofs[u]) = av;
+                            if (a.nver == 2) *reinterpret_cast<uint4 *>(dst + mirrorOff + a.verBytes + sofs[u]) = raw;
+                        }
                     }
                 }
                 fence_proxy_async();
@@ -327,17 +344,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                 pos.advance(ngroups, a.nslots);
             }
         } else {
-            // pixel-pair mode: chunk(px) = [pixel px | pixel px+1], 4 channels each; thread item = one pixel
-            constexpr int kPix = 5;
-            int xofs[kPix];
+            // pixel-pair mode: chunk = two adjacent pixels x 4 channels; chunks are split by parity so that GEMM rows
+            // (4 pixels = 2 chunks apart) are 16 bytes apart: slot = [even chunks][odd chunks].  Thread item = pixel.
+            const int halfBytes = (a.rowpx >> 1) * 16, npx = 2 * a.rowpx;
+            int xofs[kPix], sofs[kPix];
 #pragma unroll
             for (int u = 0; u < kPix; u++) {
                 const int px = u * groupThreads + t;
-                xofs[u] = (px <= a.rowpx) ? min(max(j0 - a.x_lead + px + P, 0), a.in.texW - 1) * a.in.packing : -1;
+                xofs[u] = (px < npx) ? min(max(4 * j0 - a.x_lead + px + P, 0), a.in.texW - 1) * a.in.packing : -1;
+                const int cidx = px >> 1;
+                sofs[u] = (cidx & 1) * halfBytes + (cidx >> 1) * 16 + (px & 1) * 8;
             }
             for (int r = r0 + grp; r <= r1; r += ngroups) {
+                [[maybe_unused]] const long long pt = PROF_T();
                 mbar_wait(&empty[pos.slot], (pos.fill & 1) ^ 1);
+                PROF_ADD(pLdWait, pt);
                 unsigned char *dst = sRing + (size_t)pos.slot * a.slotBytes;
+                const bool mirror = pos.slot < a.nrows - 1;
                 const int iy = min(max(r + P, 0), a.in.texH - 1);
                 const long long rowBase = (long long)n * a.in.imageElems + (long long)iy * a.in.texW * a.in.packing;
                 float4 v[kPix];
@@ -347,11 +370,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
 #pragma unroll
                 for (int u = 0; u < kPix; u++) {
                     if (xofs[u] >= 0) {
-                        const int px = u * groupThreads + t;
                         const float4 w = fyn_act4(v[u], a.act);
                         const uint2 h = make_uint2(pack_half2(w.x, w.y), pack_half2(w.z, w.w));
-                        if (px < a.rowpx) *reinterpret_cast<uint2 *>(dst + (size_t)px * 16) = h;
-                        if (px > 0) *reinterpret_cast<uint2 *>(dst + (size_t)(px - 1) * 16 + 8) = h;
+                        *reinterpret_cast<uint2 *>(dst + sofs[u]) = h;
+                        if (mirror) *reinterpret_cast<uint2 *>(dst + mirrorOff + sofs[u]) = h;
                     }
                 }
                 fence_proxy_async();
@@ -359,129 +381,153 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                 pos.advance(ngroups, a.nslots);
             }
         }
+#ifdef FYN_TC_PROFILE
+        if (blockIdx.x == 0 && t == 0)
+            printf("[tc prof] loader grp %d: total %lld waitEmpty %lld\n", grp, (long long)(clock64() - pLdStart), pLdWait);
+#endif
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
         // The whole warp runs this loop with warp-uniform values (step table in parameter space, ring position
-        // derived from block-uniform data) so the descriptors are built in uniform registers; lane 0 waits on the
-        // barriers and issues the tcgen05 instructions.
+        // derived from block-uniform data) so the descriptors are built in uniform registers; one elected lane
+        // waits on the barriers and issues the tcgen05 instructions.
         const uint32_t rbase16 = smem_u32(sRing) >> 4, slot16 = (uint32_t)a.slotBytes >> 4;
-        const uint32_t wbase16 = smem_u32(sW) >> 4, blbo = (a.b_lbo >> 4) << 16;
-        const uint64_t hiA = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
+        const uint32_t bconst = (smem_u32(sW) >> 4) | ((a.b_lbo >> 4) << 16);   // B descriptor low word minus the step offset
+        const uint64_t hiA = (uint64_t)((128u >> 4) | (1u << 14)) << 32;          // SBO = 128 B, descriptor version 1
         RingPos win{0, 0};     // ring position of the current window's first row
-        RingPos rel{0, 0};     // next row to hand back
-        int winIdx = 0, released = 0, waited = 0;
+        RingPos nxt{0, 0};     // ring position of the first row no job has waited for yet
+        int waited = 0;
+        PROF_DECL(pWaitT); PROF_DECL(pWaitF); PROF_DECL(pIssue); PROF_DECL(pCommit);
+        [[maybe_unused]] const long long pStart = PROF_T();
         for (int q = 0; q < njobs; q++) {
             const int buf = q & 1, use = q >> 1;
-            const int fy = (a.py == 1) ? 0 : (q & 1);
-            const int first = a.rowAdvance * (ja + (a.py == 1 ? q : (q >> 1))) + a.phase[fy].dyMin - r0;
-            const int nrows = a.phase[fy].nrows, sBegin = a.phase[fy].stepBegin, sEnd = a.phase[fy].stepEnd;
-            win.advance(first - winIdx, a.nslots);
-            winIdx = first;
-            const bool leader = elect_one();
-            if (leader) {
+            const int first = a.rowAdvance * q;          // window start relative to r0
+            const int needTo = first + a.nrows;          // rows [waited, needTo) are new for this job
+            const int relTo = (q + 1 < njobs) ? first + a.rowAdvance : r1 - r0 + 1;   // rows [first, relTo) retire with this job
+            if (elect_one()) {
+                [[maybe_unused]] long long pt = PROF_T();
                 mbar_wait(&tempty[buf], (use & 1) ^ 1);
-                // rows of this job's window that no earlier job has waited for
-                RingPos w = win;
-                for (int k = 0; k < nrows; k++) {
-                    if (first + k >= waited) mbar_wait(&full[w.slot], w.fill & 1);
+                PROF_ADD(pWaitT, pt);
+                pt = PROF_T();
+                RingPos w = nxt;
+                for (int k = waited; k < needTo; k++) {
+                    mbar_wait(&full[w.slot], w.fill & 1);
                     w.advance(1, a.nslots);
                 }
-            }
-            waited = max(waited, first + nrows);
-            __syncwarp();
-            tc_fence_after();
-            const uint32_t d = tmem + (uint32_t)buf * 64u;
+                PROF_ADD(pWaitF, pt);
+                pt = PROF_T();
+                tc_fence_after();
+                const uint32_t d = tmem + (uint32_t)buf * 64u;
+                const uint32_t winBase = rbase16 + (uint32_t)win.slot * slot16;
 #pragma unroll 4
-            for (int s = sBegin; s < sEnd; s++) {
-                const TcStep st = a.steps[s];
-                int sl = win.slot + (int)(st.rowFirst & 0xffu);
-                if (sl >= a.nslots) sl -= a.nslots;
-                const uint64_t adesc = hiA | (uint64_t)(st.a_lo + rbase16 + (uint32_t)sl * slot16);
-                const uint64_t bdesc = hiA | (uint64_t)((wbase16 + st.b_off16) | blbo);
-                if (leader) umma_f16(d + st.tmemOff, adesc, bdesc, a.idesc, (st.rowFirst >> 8) ? 0u : 1u);
+                for (int s = 0; s < a.nsteps; s++) {
+                    const TcStep st = a.steps[s];
+                    umma_f16(d, hiA | (uint64_t)(st.a_lo + winBase), hiA | (uint64_t)(st.b_off16 + bconst), a.idesc, st.accumulate);
+                }
+                PROF_ADD(pIssue, pt);
+                pt = PROF_T();
+                umma_commit(&tfull[buf]);
+                // rows that no later job needs go back to the loaders
+                RingPos rp = win;
+                for (int i = first; i < relTo; i++) {
+                    umma_commit(&empty[rp.slot]);
+                    rp.advance(1, a.nslots);
+                }
+                PROF_ADD(pCommit, pt);
             }
-            // rows that no later job needs go back to the loaders
-            int keepFrom = r1 - r0 + 1;
-            if (q + 1 < njobs) {
-                const int q1 = q + 1, fy1 = (a.py == 1) ? 0 : (q1 & 1);
-                keepFrom = a.rowAdvance * (ja + (a.py == 1 ? q1 : (q1 >> 1))) + a.phase[fy1].dyMin - r0;
+            if (needTo > waited) {
+                nxt.advance(needTo - waited, a.nslots);
+                waited = needTo;
             }
-            if (leader) umma_commit(&tfull[buf]);
-            for (; released < keepFrom; released++) {
-                if (leader) umma_commit(&empty[rel.slot]);
-                rel.advance(1, a.nslots);
-            }
+            win.advance(a.rowAdvance, a.nslots);
             __syncwarp();
         }
+#ifdef FYN_TC_PROFILE
+        if (blockIdx.x == 0 && elect_one())
+            printf("[tc prof] mma: jobs %d steps %d total %lld waitTempty %lld waitFull %lld issue %lld commit %lld (cycles)\n", njobs, a.nsteps,
+                   (long long)(clock64() - pStart), pWaitT, pWaitF, pIssue, pCommit);
+#endif
     } else {
         // ===================== epilogue: warps 0-3, thread = job column =====================
         const int m = threadIdx.x;           // 0..127 == TMEM lane
         const int jx = j0 + m;
-        const bool valid = jx < a.Wj;
         const int groups = a.N >> 4;
-        const bool resFast = a.hasRes && a.px == 1 && a.res.dtype == FYN_F16 && a.res.packing == 4 && !a.res.deep;
+        const bool single = a.opx == 1 && a.opy == 1;
+        const bool resFast = a.hasRes && single && a.res.dtype == FYN_F16 && a.res.packing == 4 && !a.res.deep;
+        const int ppp = a.planesPerPhase;
+        // output / residual pointers of this thread's job column (row added per job)
+        __half *outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((long long)a.outP * a.out.texW + a.outP + a.opx * jx) * 4;
+        const long long outRow = (long long)a.out.texW * 4, outPlane = a.out.planeElems;
+        PROF_DECL(pEpWait);
+        [[maybe_unused]] const long long pEpStart = PROF_T();
         for (int q = 0; q < njobs; q++) {
             const int buf = q & 1, use = q >> 1;
-            const int yo = (a.py == 1) ? ja + q : 2 * (ja + (q >> 1)) + (q & 1);
+            const int i = ja + q;                    // job row
             // residual texels are fetched before waiting for the accumulator so their latency hides behind the MMAs
             uint2 rres[16];
-            if (resFast && valid) {
+            if (resFast && jx < a.Wj) {
                 const __half *rp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems +
-                                   ((long long)(a.resP + yo) * a.res.texW + a.resP + jx) * 4;
+                                   ((long long)(a.resP + i) * a.res.texW + a.resP + jx) * 4;
 #pragma unroll
                 for (int p = 0; p < 16; p++)
-                    if (p < a.nOutPlanes) rres[p] = __ldg(reinterpret_cast<const uint2 *>(rp + (long long)p * a.res.planeElems));
+                    if (p < ppp) rres[p] = __ldg(reinterpret_cast<const uint2 *>(rp + (long long)p * a.res.planeElems));
             }
+            [[maybe_unused]] const long long pt = PROF_T();
             mbar_wait(&tfull[buf], use & 1);
+            PROF_ADD(pEpWait, pt);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * 64u;
             uint32_t acc[4][16];
-            const int total = groups * a.px;    // 16-column groups in this buffer (accumulators are contiguous)
 #pragma unroll
             for (int g = 0; g < 4; g++)
-                if (g < total) tmem_ld16(taddr + g * 16, acc[g]);
+                if (g < groups) tmem_ld16(taddr + g * 16, acc[g]);
             tmem_ld_wait();
             // accumulators are in registers: hand the TMEM buffer back before the global-memory work
             tc_fence_before();
             mbar_arrive(&tempty[buf]);
-            if (valid) {
+            __half *orow = outp + (long long)(a.opy * i) * outRow;
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    if (g < total) {
-                        const int fx = (g >= groups) ? 1 : 0;          // x phase of this group
-                        const int gp = g - fx * groups;                // group inside the accumulator
-                        const int xo = a.px * jx + fx;
+            for (int g = 0; g < 4; g++) {
+                if (g < groups) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int p = gp * 4 + k;
-                            if (p < a.nOutPlanes) {
-                                const float4 bi = sEpi[p], sc = sEpi[16 + p];
-                                float4 v = make_float4(fmaf(__uint_as_float(acc[g][4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[g][4 * k + 1]), sc.y, bi.y),
-                                                       fmaf(__uint_as_float(acc[g][4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[g][4 * k + 3]), sc.w, bi.w));
-                                if (a.hasRes) {
-                                    float4 rs;
-                                    if (resFast) {
-                                        const uint2 raw = rres[p];
-                                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
-                                        const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
-                                        rs = make_float4(f0.x, f0.y, f1.x, f1.y);
-                                    } else {
-                                        rs = fyn_fetch(a.res, n, p, a.resP + xo, a.resP + yo);
-                                    }
-                                    if (a.reluRes) rs = make_float4(fmaxf(rs.x, 0.f), fmaxf(rs.y, 0.f), fmaxf(rs.z, 0.f), fmaxf(rs.w, 0.f));
-                                    if (a.bnRes) rs = make_float4(rs.x * sc.x, rs.y * sc.y, rs.z * sc.z, rs.w * sc.w);
-                                    v.x += rs.x;
-                                    v.y += rs.y;
-                                    v.z += rs.z;
-                                    v.w += rs.w;
+                    for (int k = 0; k < 4; k++) {
+                        // stacked plane index -> (phase, plane); all uniform across the warp
+                        const int pn = g * 4 + k;
+                        const int phase = pn / ppp;
+                        const int p = pn - phase * ppp;
+                        const int fy = phase / a.opx, fx = phase - fy * a.opx;
+                        const int xo = a.opx * jx + fx, yo = a.opy * i + fy;
+                        if (phase < a.opx * a.opy && xo < a.Wo && yo < a.Ho) {
+                            const float4 bi = sEpi[p], sc = sEpi[16 + p];
+                            float4 v = make_float4(fmaf(__uint_as_float(acc[g][4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[g][4 * k + 1]), sc.y, bi.y),
+                                                   fmaf(__uint_as_float(acc[g][4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[g][4 * k + 3]), sc.w, bi.w));
+                            if (a.hasRes) {
+                                float4 rs;
+                                if (resFast) {
+                                    const uint2 raw = rres[p];
+                                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+                                    const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+                                    rs = make_float4(f0.x, f0.y, f1.x, f1.y);
+                                } else {
+                                    rs = fyn_fetch(a.res, n, p, a.resP + xo, a.resP + yo);
                                 }
-                                fyn_store_texel(a.out, n, p, a.outP + xo, a.outP + yo, v);
+                                if (a.reluRes) rs = make_float4(fmaxf(rs.x, 0.f), fmaxf(rs.y, 0.f), fmaxf(rs.z, 0.f), fmaxf(rs.w, 0.f));
+                                if (a.bnRes) rs = make_float4(rs.x * sc.x, rs.y * sc.y, rs.z * sc.z, rs.w * sc.w);
+                                v.x += rs.x;
+                                v.y += rs.y;
+                                v.z += rs.z;
+                                v.w += rs.w;
                             }
+                            *reinterpret_cast<uint2 *>(orow + (long long)p * outPlane + (long long)fy * outRow + fx * 4) =
+                                make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
                         }
                     }
                 }
             }
         }
+#ifdef FYN_TC_PROFILE
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            printf("[tc prof] epilogue: total %lld waitTfull %lld\n", (long long)(clock64() - pEpStart), pEpWait);
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -491,51 +537,59 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-// host side: plan = job phases + MMA step table + weight image
+// host side: plan = window + MMA step table + weight image
 // ---------------------------------------------------------------------------------------------
 struct ConvTcPlan {
     TcArgs args{};
     uint4 *d_wimg = nullptr;
-    float *d_bias = nullptr;  // [2 * Npad]: bias then scale
+    float *d_bias = nullptr;  // [16 planes x 4] bias then [16 x 4] scale
     size_t smemBytes = 0;
     int mode = 0;
 };
 
 namespace {
 
-// one source position of a phase: merged weights [Co][Ci] for (version, dy, dx)
+// one source position of the GEMM: (version, window row dy, source offset dx) with the weights of every phase that
+// reads it, w[(phase * Cq + co) * Ci + ci] (merged taps summed)
 struct Position {
     int ver, dy, dx;
-    std::vector<float> w;   // [Co][Ci]
-};
-
-struct PhasePlan {
-    std::vector<Position> pos;
+    std::vector<float> w;
 };
 
 struct Geometry {
-    int mode = 0, py = 1, px = 1, rowAdvance = 1, nver = 1, N = 16, nchunks = 1, rowpx = 0, x_lead = 0, ds = 1;
-    int dxMin = 0, dxMax = 0;
-    int dyMin[2] = {0, 0}, dyMax[2] = {0, 0};
+    int mode = 0, opx = 1, opy = 1, rowAdvance = 1, nver = 1, N = 16, Cq = 4, nchunks = 1, rowpx = 0, x_lead = 0, ds = 1;
+    int dxMin = 0, dxMax = 0, dyMin = 0, dyMax = 0;
     int nslots = 0, slotBytes = 0, verBytes = 0, nsteps = 0, groupWarps = 4;
     size_t wbytes = 0, smem = 0;
-    std::vector<PhasePlan> phases;   // [py*px], index fy*px+fx (weights only filled when wb != nullptr)
+    std::vector<Position> pos;
     bool ok = false;
 };
 
 int ifloor(float v) { return (int)floorf(v); }
+int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
-// Builds phases / positions (and merged weights when wb is given) and the shared-memory geometry.
+Position &find_pos(std::vector<Position> &pos, int ver, int dy, int dx, size_t wsize, bool wantW) {
+    for (Position &q : pos)
+        if (q.ver == ver && q.dy == dy && q.dx == dx) return q;
+    pos.push_back({ver, dy, dx, {}});
+    if (wantW) pos.back().w.assign(wsize, 0.f);
+    return pos.back();
+}
+
+// Builds the positions (and stacked, merged weights when wb is given) and the shared-memory geometry.
 Geometry plan_geometry(const fyn_conv_desc *d, const float *wb) {
     Geometry g;
     if (d->flags & FYN_FLAG_DEEP) return g;          // deep-tiled family: not yet
     if (d->dilation != 1) return g;
-    if (d->out_channels > 64) return g;
     const int K = d->kernel, mh = (K - 1) / 2, Ci = d->in_channels, Co = d->out_channels;
-    g.N = ((Co + 15) / 16) * 16;
+    if (K > 9) return g;
+    g.Cq = 4 * ((Co + 3) / 4);
     const bool hasAct = (d->flags & (FYN_FLAG_PRE_RELU | FYN_FLAG_PRE_CLIP)) != 0;
+    const float *W = wb ? wb + Co : nullptr;          // [Co][K][K][Ci]
     std::vector<int> tapx(K), tapy(K);
     for (int k = 0; k < K; k++) tapx[k] = tapy[k] = k - mh;
+    g.dxMin = g.dyMin = 1 << 20;
+    g.dxMax = g.dyMax = -(1 << 20);
     if (d->fractional) {
         if (Ci < 8) return g;
         const float s = d->source_step, u = s * (float)d->downsample;
@@ -543,119 +597,119 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb) {
         if (u == 1.0f) p = 1;
         else if (u == 0.5f) p = 2;
         else return g;                                // other ratios: direct kernel
-        if (p == 2 && g.N > 32) return g;             // two accumulators share a 64-column TMEM buffer
         if (K == 3 && (d->quirks & FYN_QUIRK_FRAC3_ASYM)) {
             tapx[0] = -2;
             tapx[1] = -1;
             tapx[2] = 0;
         }
         const bool actFirstOnly = hasAct && (d->quirks & FYN_QUIRK_FRAC_ACT_FIRST);
-        g.py = g.px = p;
+        g.opx = g.opy = p;
         g.rowAdvance = 1;
         g.nver = actFirstOnly ? 2 : 1;
         g.ds = 1;
         g.mode = 0;
-        g.phases.resize((size_t)p * p);
-        g.dxMin = 1 << 20;
-        g.dxMax = -(1 << 20);
-        for (int fy = 0; fy < p; fy++) {
-            g.dyMin[fy] = 1 << 20;
-            g.dyMax[fy] = -(1 << 20);
-            for (int fx = 0; fx < p; fx++) {
-                PhasePlan &pp = g.phases[(size_t)fy * p + fx];
+        const size_t wsize = (size_t)p * p * g.Cq * Ci;
+        for (int fy = 0; fy < p; fy++)
+            for (int fx = 0; fx < p; fx++)
                 for (int ky = 0; ky < K; ky++)
                     for (int kx = 0; kx < K; kx++) {
                         // delta = floor(s*(ds*phi + 0.5 + tap)) -- gpu/vanilla/convlayerbase_vanilla.cpp:352-371 + fraconv*.frag
                         const int dy = ifloor(s * ((float)(d->downsample * fy) + 0.5f + (float)tapy[ky]));
                         const int dx = ifloor(s * ((float)(d->downsample * fx) + 0.5f + (float)tapx[kx]));
                         const int ver = (actFirstOnly && kx > 0) ? 1 : 0;
-                        g.dyMin[fy] = std::min(g.dyMin[fy], dy);
-                        g.dyMax[fy] = std::max(g.dyMax[fy], dy);
-                        g.dxMin = std::min(g.dxMin, dx);
-                        g.dxMax = std::max(g.dxMax, dx);
-                        Position *hit = nullptr;
-                        for (Position &q : pp.pos)
-                            if (q.ver == ver && q.dy == dy && q.dx == dx) hit = &q;
-                        if (!hit) {
-                            pp.pos.push_back({ver, dy, dx, {}});
-                            hit = &pp.pos.back();
-                            if (wb) hit->w.assign((size_t)Co * Ci, 0.f);
-                        }
+                        Position &q = find_pos(g.pos, ver, dy, dx, wsize, wb != nullptr);
                         if (wb) {
-                            const float *W = wb + Co;
+                            const int phase = fy * p + fx;
                             for (int o = 0; o < Co; o++)
-                                for (int c = 0; c < Ci; c++) hit->w[(size_t)o * Ci + c] += W[(((size_t)o * K + ky) * K + kx) * Ci + c];
+                                for (int c = 0; c < Ci; c++)
+                                    q.w[((size_t)phase * g.Cq + o) * Ci + c] += W[(((size_t)o * K + ky) * K + kx) * Ci + c];
                         }
                     }
+    } else if (Ci <= 4 && d->downsample == 1 && K >= 3) {
+        // pixel-pair mode: one GEMM row = 4 adjacent output pixels (phases), chunks = pixel pairs.  Position.dx is the
+        // chunk offset e relative to chunk 2*j; element (half h, channel c) of chunk e belongs to tap kx = 2e + h - fx + mh.
+        g.mode = 1;
+        g.opx = 4;
+        g.opy = 1;
+        g.rowAdvance = 1;
+        g.ds = 1;
+        const size_t wsize = (size_t)4 * g.Cq * 8;    // [phase][co][8 chunk elements]
+        int e0 = floordiv2(-mh);
+        if (e0 & 1) e0 -= 1;   // the slot starts on an even chunk so that chunk parity == (e - e0) parity; extra chunk has zero weights
+        for (int ky = 0; ky < K; ky++)
+            for (int e = e0; e <= floordiv2(3 + K - 1 - mh); e++) {
+                Position &q = find_pos(g.pos, 0, ky - mh, e, wsize, wb != nullptr);
+                if (wb)
+                    for (int fx = 0; fx < 4; fx++)
+                        for (int o = 0; o < Co; o++)
+                            for (int h = 0; h < 2; h++)
+                                for (int c = 0; c < Ci; c++) {
+                                    const int kx = 2 * e + h - fx + mh;
+                                    if (kx >= 0 && kx < K) q.w[((size_t)fx * g.Cq + o) * 8 + h * 4 + c] = W[(((size_t)o * K + ky) * K + kx) * Ci + c];
+                                }
             }
-        }
     } else {
         if (d->downsample != 1 && d->downsample != 2) return g;
-        if (K < 3) return g;
-        if (Ci <= 4 && d->downsample == 1) g.mode = 1;
-        else if (Ci >= 8) g.mode = 0;
-        else return g;
-        g.py = g.px = 1;
+        if (K < 3 || Ci < 8) return g;
+        g.mode = 0;
+        g.opx = g.opy = 1;
         g.rowAdvance = d->downsample;
         g.ds = d->downsample;
-        g.nver = 1;
-        g.dyMin[0] = -mh;
-        g.dyMax[0] = mh;
-        g.dxMin = -mh;
-        g.dxMax = mh;
-        g.phases.resize(1);
+        const size_t wsize = (size_t)g.Cq * Ci;
         for (int ky = 0; ky < K; ky++)
             for (int kx = 0; kx < K; kx++) {
-                Position q{0, ky - mh, kx - mh, {}};
-                if (wb) {
-                    const float *W = wb + Co;
-                    q.w.resize((size_t)Co * Ci);
+                Position &q = find_pos(g.pos, 0, ky - mh, kx - mh, wsize, wb != nullptr);
+                if (wb)
                     for (int o = 0; o < Co; o++)
                         for (int c = 0; c < Ci; c++) q.w[(size_t)o * Ci + c] = W[(((size_t)o * K + ky) * K + kx) * Ci + c];
-                }
-                g.phases[0].pos.push_back(std::move(q));
             }
     }
+    const int ntot = g.opx * g.opy * g.Cq;
+    g.N = ((ntot + 15) / 16) * 16;
+    if (g.N > 64) return g;                           // one 64-column TMEM buffer per job
+    for (const Position &q : g.pos) {
+        g.dxMin = std::min(g.dxMin, q.dx);
+        g.dxMax = std::max(g.dxMax, q.dx);
+        g.dyMin = std::min(g.dyMin, q.dy);
+        g.dyMax = std::max(g.dyMax, q.dy);
+    }
+    const int nrows = g.dyMax - g.dyMin + 1, span = g.dxMax - g.dxMin;
+    if (nrows > kMaxRows) return g;
     // slot geometry
-    const int span = g.dxMax - g.dxMin;
-    g.x_lead = -g.dxMin;
     if (g.mode == 1) {
+        // chunks 2*j + e, e in [dxMin, dxMax]: per parity (128 + span/2 + 1) chunks, rounded up
+        const int halfChunks = ((kTileM + span / 2 + 2) + 3) & ~3;
         g.nchunks = 1;
-        g.rowpx = ((kTileM + span + 2) + 3) & ~3;
+        g.rowpx = 2 * halfChunks;                     // chunks per slot
+        g.x_lead = -2 * g.dxMin;                      // pixels (dxMin is even-aligned below)
+        if (g.dxMin & 1) return g;
+        g.verBytes = g.rowpx * 16;
+        g.groupWarps = 2;
+        if (2 * g.rowpx > kPix * g.groupWarps * 32) return g;
     } else {
         g.nchunks = ((Ci + 3) / 4 + 1) / 2;
+        g.x_lead = -g.dxMin;
         if (g.ds == 1) g.rowpx = ((kTileM + span + 1) + 3) & ~3;
         else g.rowpx = 2 * (((kTileM + span / 2 + 1) + 3) & ~3);
+        g.verBytes = g.nchunks * g.rowpx * 16;
+        g.groupWarps = 4;
+        if (g.rowpx * g.nchunks > kUnroll * g.groupWarps * 32) return g;   // a row must fit one batch
     }
-    g.verBytes = g.nchunks * g.rowpx * 16;
     g.slotBytes = g.verBytes * g.nver;
-    int maxRows = 0;
-    for (int f = 0; f < g.py; f++) maxRows = std::max(maxRows, g.dyMax[f] - g.dyMin[f] + 1);
-    // loader groups: small rows (pixel-pair mode) are loaded one warp per row so that many rows are in flight
-    g.groupWarps = (g.mode == 1) ? 1 : 4;
     const int ngroups = kLoaderWarps / g.groupWarps;
-    if (g.mode == 0 && g.rowpx * g.nchunks > kUnroll * g.groupWarps * 32) return g;   // a row must fit one batch
-    if (g.mode == 1 && g.rowpx + 1 > 5 * g.groupWarps * 32) return g;
-    g.nslots = maxRows + std::max(ngroups, 2) * g.rowAdvance + 1;
-    // steps: per phase, chunks of the same window row are paired in address order
+    g.nslots = nrows + std::max(ngroups, 2) * g.rowAdvance + 1;
+    // steps: chunks of the same window row are paired in address order
     int nsteps = 0;
-    for (const PhasePlan &pp : g.phases) {
-        std::vector<int> perRow(32, 0);
-        for (const Position &q : pp.pos) {
-            const int chunks = (g.mode == 1) ? 0 : g.nchunks;
-            perRow[q.dy + 16] += chunks;
-        }
-        if (g.mode == 1) {
-            // pixel-pair: ceil(K/2) chunks per kernel row
-            for (int ky = 0; ky < K; ky++) nsteps += (((K + 1) / 2) + 1) / 2;
-        } else {
-            for (int c : perRow) nsteps += (c + 1) / 2;
-        }
+    for (int dy = g.dyMin; dy <= g.dyMax; dy++) {
+        int chunks = 0;
+        for (const Position &q : g.pos)
+            if (q.dy == dy) chunks += g.nchunks;
+        nsteps += (chunks + 1) / 2;
     }
     g.nsteps = nsteps;
     if (nsteps > kMaxSteps) return g;
     g.wbytes = (size_t)nsteps * 2 * g.N * 16;
-    g.smem = ((g.wbytes + 127) & ~(size_t)127) + (size_t)g.nslots * g.slotBytes + 32 * 16 + (2 * g.nslots + 4) * 8 + 16;
+    g.smem = ((g.wbytes + 127) & ~(size_t)127) + (size_t)(g.nslots + nrows - 1) * g.slotBytes + 32 * 16 + (2 * g.nslots + 4) * 8 + 16;
     if (g.smem > 220 * 1024) return g;
     g.ok = true;
     return g;
@@ -674,13 +728,16 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     plan->mode = g.mode;
     TcArgs &a = plan->args;
     const int K = d.kernel, Ci = d.in_channels, Co = d.out_channels, N = g.N;
+    const int nphase = g.opx * g.opy;
     a.N = N;
-    a.nOutPlanes = (Co + 3) / 4;
     a.nInPlanes = (Ci + 3) / 4;
     a.mode = g.mode;
-    a.py = g.py;
-    a.px = g.px;
+    a.opx = g.opx;
+    a.opy = g.opy;
+    a.planesPerPhase = g.Cq / 4;
     a.rowAdvance = g.rowAdvance;
+    a.dyMin = g.dyMin;
+    a.nrows = g.dyMax - g.dyMin + 1;
     a.ds = g.ds;
     a.nver = g.nver;
     a.verBytes = g.verBytes;
@@ -696,75 +753,59 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     a.wbytes = (uint32_t)g.wbytes;
 
     std::vector<__half> img(g.wbytes / 2, __float2half(0.f));
-    // byte offset inside a slot of chunk c at source offset dx (output job column 0)
-    auto aoff = [&](int ver, int c, int dx) -> uint32_t {
-        const int j = dx + g.x_lead;   // slot pixel for job column 0
-        int px;
-        if (g.ds == 1) px = j;
-        else px = (j & 1) * (g.rowpx / 2) + j / 2;
-        return (uint32_t)(ver * g.verBytes + (c * g.rowpx + px) * 16);
+    // byte offset inside a slot of chunk c of the position (GEMM row 0)
+    auto aoff = [&](const Position &q, int c) -> uint32_t {
+        const int j = q.dx - g.dxMin;   // slot pixel (mode 0) / slot chunk (mode 1) for job column 0
+        if (g.mode == 1) return (uint32_t)((j & 1) * (g.rowpx / 2) * 16 + (j >> 1) * 16);
+        const int px = (g.ds == 1) ? j : (j & 1) * (g.rowpx / 2) + j / 2;
+        return (uint32_t)(q.ver * g.verBytes + (c * g.rowpx + px) * 16);
     };
-    struct Chunk { uint32_t off; const Position *pos; int sub; int kx; };
-    int s = 0;
-    for (int fy = 0; fy < g.py; fy++) {
-        a.phase[fy].dyMin = g.dyMin[fy];
-        a.phase[fy].nrows = g.dyMax[fy] - g.dyMin[fy] + 1;
-        a.phase[fy].stepBegin = s;
-        for (int fx = 0; fx < g.px; fx++) {
-            const PhasePlan &pp = g.phases[(size_t)fy * g.px + fx];
-            bool firstOfAcc = true;
-            for (int dy = g.dyMin[fy]; dy <= g.dyMax[fy]; dy++) {
-                std::vector<Chunk> chunks;
-                if (g.mode == 0) {
-                    for (const Position &q : pp.pos)
-                        if (q.dy == dy)
-                            for (int c = 0; c < g.nchunks; c++) chunks.push_back({aoff(q.ver, c, q.dx), &q, c, 0});
-                } else {
-                    // pixel-pair: chunk at tap kx covers taps kx, kx+1 (weights taken from the two positions)
-                    for (int kx = 0; kx < K; kx += 2) chunks.push_back({(uint32_t)(kx * 16), nullptr, 0, kx});
-                }
-                std::sort(chunks.begin(), chunks.end(), [](const Chunk &x, const Chunk &y) { return x.off < y.off; });
-                auto fill = [&](size_t chunkIdx, const Chunk &c) {
-                    for (int nn = 0; nn < Co; nn++)
-                        for (int e = 0; e < 8; e++) {
-                            float v = 0.f;
-                            if (g.mode == 0) {
-                                const int ci = c.sub * 8 + e;
-                                if (ci < Ci) v = c.pos->w[(size_t)nn * Ci + ci];
-                            } else {
-                                const int kx = c.kx + e / 4, ci = e % 4, ky = dy + (K - 1) / 2;
-                                if (kx < K && ci < Ci) v = wb[Co + (((size_t)nn * K + ky) * K + kx) * Ci + ci];
-                            }
-                            img[(chunkIdx * N + nn) * 8 + e] = __float2half_rn(v);
-                        }
-                };
-                for (size_t i = 0; i < chunks.size(); i += 2) {
-                    TcStep &st = a.steps[s];
-                    st.rowFirst = (uint32_t)(dy - g.dyMin[fy]) | (firstOfAcc ? 256u : 0u);
-                    st.tmemOff = (uint32_t)(fx * N);
-                    firstOfAcc = false;
-                    st.b_off16 = (uint32_t)(((size_t)s * 2 * N * 16) >> 4);
-                    fill((size_t)s * 2, chunks[i]);
-                    uint32_t lbo = 16;  // unpaired: second half reads the neighbouring pixel against all-zero weights
-                    if (i + 1 < chunks.size()) {
-                        lbo = chunks[i + 1].off - chunks[i].off;
-                        fill((size_t)s * 2 + 1, chunks[i + 1]);
-                        if (lbo == 0 || lbo >= (1u << 18)) FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 conv: operand stride %u not encodable", lbo);
+    struct Chunk { uint32_t off; const Position *pos; int sub; };
+    auto fill = [&](size_t chunkIdx, const Chunk &c) {
+        for (int ph = 0; ph < nphase; ph++)
+            for (int o = 0; o < Co; o++)
+                for (int e = 0; e < 8; e++) {
+                    float v = 0.f;
+                    if (g.mode == 1) {
+                        v = c.pos->w[((size_t)ph * g.Cq + o) * 8 + e];
+                    } else {
+                        const int ci = c.sub * 8 + e;
+                        if (ci < Ci) v = c.pos->w[((size_t)ph * g.Cq + o) * Ci + ci];
                     }
-                    st.a_lo = ((lbo >> 4) << 16) | (chunks[i].off >> 4);
-                    s++;
+                    img[(chunkIdx * N + (size_t)ph * g.Cq + o) * 8 + e] = __float2half_rn(v);
                 }
+    };
+    int s = 0;
+    for (int dy = g.dyMin; dy <= g.dyMax; dy++) {
+        std::vector<Chunk> chunks;
+        for (const Position &q : g.pos)
+            if (q.dy == dy)
+                for (int c = 0; c < g.nchunks; c++) chunks.push_back({aoff(q, c), &q, c});
+        std::sort(chunks.begin(), chunks.end(), [](const Chunk &x, const Chunk &y) { return x.off < y.off; });
+        const uint32_t rowOff = (uint32_t)(dy - g.dyMin) * (uint32_t)g.slotBytes;
+        for (size_t i = 0; i < chunks.size(); i += 2) {
+            TcStep &st = a.steps[s];
+            st.accumulate = s == 0 ? 0u : 1u;
+            st.pad = 0;
+            st.b_off16 = (uint32_t)(((size_t)s * 2 * N * 16) >> 4);
+            fill((size_t)s * 2, chunks[i]);
+            uint32_t lbo = 16;  // unpaired: second half reads the neighbouring chunk against all-zero weights
+            if (i + 1 < chunks.size()) {
+                lbo = chunks[i + 1].off - chunks[i].off;
+                fill((size_t)s * 2 + 1, chunks[i + 1]);
+                if (lbo == 0 || lbo >= (1u << 18)) FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 conv: operand stride %u not encodable", lbo);
             }
+            st.a_lo = ((lbo >> 4) << 16) | ((rowOff + chunks[i].off) >> 4);
+            s++;
         }
-        a.phase[fy].stepEnd = s;
     }
     if (s != g.nsteps) FYN_FAIL(FYN_ERR_INVALID, "tcgen05 conv: internal step count mismatch (%d vs %d)", s, g.nsteps);
 
     FYN_CUDA(cudaSetDevice(op->ctx->device));
     if (!plan->d_wimg) FYN_CUDA(cudaMalloc((void **)&plan->d_wimg, g.wbytes));
     FYN_CUDA(cudaMemcpy(plan->d_wimg, img.data(), g.wbytes, cudaMemcpyHostToDevice));
-    // epilogue parameters padded to N
-    std::vector<float> eb((size_t)2 * N, 0.f);
+    // epilogue parameters per output plane: [16][4] bias then [16][4] scale
+    std::vector<float> eb(128, 0.f);
     const float *bn = wb + Co + (size_t)K * K * Ci * Co;
     for (int o = 0; o < Co; o++) {
         float b = wb[o], sc = 1.f;
@@ -773,13 +814,13 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
             b = b * sc + bn[Co + o];
         }
         eb[o] = b;
-        eb[N + o] = sc;
+        eb[64 + o] = sc;
     }
     if (!plan->d_bias) FYN_CUDA(cudaMalloc((void **)&plan->d_bias, eb.size() * sizeof(float)));
     FYN_CUDA(cudaMemcpy(plan->d_bias, eb.data(), eb.size() * sizeof(float), cudaMemcpyHostToDevice));
     a.wimg = plan->d_wimg;
     a.bias = plan->d_bias;
-    a.scale = plan->d_bias + N;
+    a.scale = plan->d_bias + 64;
     plan->smemBytes = g.smem;
     if (plan->smemBytes > (size_t)op->ctx->prop.sharedMemPerBlockOptin)
         FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 conv needs %zu bytes of shared memory", plan->smemBytes);
@@ -797,7 +838,7 @@ int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn
     ConvTcPlan *plan = op->tc;
     const fyn_conv_desc &d = op->conv;
     // tensor formats this family reads / writes
-    if (out->desc.dtype != FYN_F16 || (res && res->desc.dtype != FYN_F16)) return 1;
+    if (out->desc.dtype != FYN_F16 || out->desc.order != FYN_ORDER_SHALLOW || (res && res->desc.dtype != FYN_F16)) return 1;
     if (plan->mode == 0 && (in->desc.dtype != FYN_F16 || in->geom.packing != 4)) return 1;
     if (in->desc.order != FYN_ORDER_SHALLOW && in->desc.channels > 4) return 1;
     TcArgs a = plan->args;
@@ -806,9 +847,8 @@ int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn
     a.res = fyn_make_view(res);
     a.Wo = op->Wo;
     a.Ho = op->Ho;
-    if (a.Wo % a.px || a.Ho % a.py) return 1;   // phase decomposition needs whole periods
-    a.Wj = a.Wo / a.px;
-    a.Hj = a.Ho / a.py;
+    a.Wj = (a.Wo + a.opx - 1) / a.opx;
+    a.Hj = (a.Ho + a.opy - 1) / a.opy;
     a.inP = d.in_padding;
     a.outP = d.out_padding;
     a.resP = d.res_padding;
