@@ -34,9 +34,9 @@
 // (fractional convs) or four horizontally adjacent pixels (the 3-channel pixel-pair mode), with structural zeros in
 // the weight image where a phase does not use a tap.
 //
-// Warp roles (416 threads): warps 0-3 epilogue (TMEM -> registers -> bias/BN/residual -> fp16 planes),
-// warps 4-11 loaders (two groups of four warps on alternating input rows, so two rows are always in flight),
-// warp 12 issues tcgen05.mma (one elected lane).
+// Warp roles (544 threads): warps 0-7 epilogue (TMEM -> registers -> bias/BN/residual -> fp16 planes; warp w reads
+// TMEM lane quarter w%4 and the 16-column groups w/4, w/4+2), warps 8-15 loaders (groups of 1, 2 or 4 warps on
+// interleaved input rows, so several rows are always in flight), warp 16 issues tcgen05.mma (one elected lane).
 // Pipelines: full/empty mbarriers per ring slot (loader <-> MMA), tmem_full/tmem_empty per accumulator
 // buffer (MMA <-> epilogue, two buffers so the epilogue of row y overlaps the MMAs of row y+1).
 #include <algorithm>
@@ -58,9 +58,10 @@ namespace {
 #endif
 
 constexpr int kMaxSteps = 96;
+constexpr int kEpiWarps = 8;                         // two warps per TMEM lane quarter, each takes every other column group
 constexpr int kLoaderWarps = 8;
-constexpr int kMmaWarp = 4 + kLoaderWarps;
-constexpr int kThreads = (kMmaWarp + 1) * 32;       // 416
+constexpr int kMmaWarp = kEpiWarps + kLoaderWarps;
+constexpr int kThreads = (kMmaWarp + 1) * 32;       // 544
 constexpr int kUnroll = 7;                           // (pixel, chunk) items per loader thread and row (all in flight)
 constexpr int kPix = 9;                              // pixels per loader thread and row in pixel-pair mode
 constexpr int kTileM = 128;
@@ -259,8 +260,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         }
         mbar_init(&tfull[0], 1);
         mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], 128);
-        mbar_init(&tempty[1], 128);
+        mbar_init(&tempty[0], kEpiWarps * 32);
+        mbar_init(&tempty[1], kEpiWarps * 32);
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(tmemBase, 128);
@@ -274,11 +275,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     tc_fence_after();
     const uint32_t tmem = *tmemBase;
 
-    if (warp >= 4 && warp < kMmaWarp) {
+    if (warp >= kEpiWarps && warp < kMmaWarp) {
         // ===================== loaders: kLoaderWarps/groupWarps groups, group g takes rows g, g+G, ... ==========
         const int ngroups = kLoaderWarps / a.groupWarps;
-        const int grp = (warp - 4) / a.groupWarps;
-        const int t = (threadIdx.x - 128) - grp * groupThreads;   // thread index inside the group
+        const int grp = (warp - kEpiWarps) / a.groupWarps;
+        const int t = (threadIdx.x - kEpiWarps * 32) - grp * groupThreads;   // thread index inside the group
         const int P = a.inP;
         const int mirrorOff = a.nslots * a.slotBytes;             // slots < nrows-1 are also written behind the ring
         RingPos pos{0, 0};
@@ -447,79 +448,90 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                    (long long)(clock64() - pStart), pWaitT, pWaitF, pIssue, pCommit);
 #endif
     } else {
-        // ===================== epilogue: warps 0-3, thread = job column =====================
-        const int m = threadIdx.x;           // 0..127 == TMEM lane
+        // ===================== epilogue: warps 0-7, thread = job column x half of the column groups ==========
+        const int m = threadIdx.x & 127;     // TMEM lane == job column inside the tile
+        const int chalf = warp >> 2;         // this warp handles 16-column groups chalf and chalf + 2
         const int jx = j0 + m;
+        const bool valid = jx < a.Wj;
         const int groups = a.N >> 4;
         const bool single = a.opx == 1 && a.opy == 1;
         const bool resFast = a.hasRes && single && a.res.dtype == FYN_F16 && a.res.packing == 4 && !a.res.deep;
-        const int ppp = a.planesPerPhase;
-        // output / residual pointers of this thread's job column (row added per job)
+        const int ppp = a.planesPerPhase, nphase = a.opx * a.opy;
+        // Per (group, plane-in-group) constants, hoisted out of the job loop: output element offset relative to the
+        // job's first output texel (-1 = nothing to store) and the output plane (bias / scale / residual index).
+        int poff[2][4], pidx[2][4];
+#pragma unroll
+        for (int gi = 0; gi < 2; gi++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int pn = (chalf + 2 * gi) * 4 + k;   // stacked plane index
+                const int phase = pn / ppp, p = pn - phase * ppp;
+                const int fy = phase / a.opx, fx = phase - fy * a.opx;
+                pidx[gi][k] = p;
+                poff[gi][k] = (phase < nphase && chalf + 2 * gi < groups && valid)
+                                  ? (int)((long long)p * a.out.planeElems + (long long)fy * a.out.texW * 4 + fx * 4) : -1;
+            }
         __half *outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((long long)a.outP * a.out.texW + a.outP + a.opx * jx) * 4;
-        const long long outRow = (long long)a.out.texW * 4, outPlane = a.out.planeElems;
+        const long long outRow = (long long)a.out.texW * 4 * a.opy;   // elements per job row
+        const __half *resp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems + ((long long)a.resP * a.res.texW + a.resP + jx) * 4;
+        const int resPlane = (int)a.res.planeElems;
         PROF_DECL(pEpWait);
         [[maybe_unused]] const long long pEpStart = PROF_T();
         for (int q = 0; q < njobs; q++) {
             const int buf = q & 1, use = q >> 1;
             const int i = ja + q;                    // job row
             // residual texels are fetched before waiting for the accumulator so their latency hides behind the MMAs
-            uint2 rres[16];
-            if (resFast && jx < a.Wj) {
-                const __half *rp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems +
-                                   ((long long)(a.resP + i) * a.res.texW + a.resP + jx) * 4;
+            uint2 rres[2][4];
+            if (resFast) {
+                const __half *rp = resp + (long long)i * a.res.texW * 4;
 #pragma unroll
-                for (int p = 0; p < 16; p++)
-                    if (p < ppp) rres[p] = __ldg(reinterpret_cast<const uint2 *>(rp + (long long)p * a.res.planeElems));
+                for (int gi = 0; gi < 2; gi++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (poff[gi][k] >= 0) rres[gi][k] = __ldg(reinterpret_cast<const uint2 *>(rp + pidx[gi][k] * resPlane));
             }
             [[maybe_unused]] const long long pt = PROF_T();
             mbar_wait(&tfull[buf], use & 1);
             PROF_ADD(pEpWait, pt);
             tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * 64u;
-            uint32_t acc[4][16];
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * 64u;
+            uint32_t acc[2][16];
 #pragma unroll
-            for (int g = 0; g < 4; g++)
-                if (g < groups) tmem_ld16(taddr + g * 16, acc[g]);
+            for (int gi = 0; gi < 2; gi++)
+                if (chalf + 2 * gi < groups) tmem_ld16(taddr + (chalf + 2 * gi) * 16, acc[gi]);
             tmem_ld_wait();
             // accumulators are in registers: hand the TMEM buffer back before the global-memory work
             tc_fence_before();
             mbar_arrive(&tempty[buf]);
-            __half *orow = outp + (long long)(a.opy * i) * outRow;
+            __half *orow = outp + (long long)i * outRow;
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-                if (g < groups) {
+            for (int gi = 0; gi < 2; gi++) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        // stacked plane index -> (phase, plane); all uniform across the warp
-                        const int pn = g * 4 + k;
-                        const int phase = pn / ppp;
-                        const int p = pn - phase * ppp;
-                        const int fy = phase / a.opx, fx = phase - fy * a.opx;
-                        const int xo = a.opx * jx + fx, yo = a.opy * i + fy;
-                        if (phase < a.opx * a.opy && xo < a.Wo && yo < a.Ho) {
-                            const float4 bi = sEpi[p], sc = sEpi[16 + p];
-                            float4 v = make_float4(fmaf(__uint_as_float(acc[g][4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[g][4 * k + 1]), sc.y, bi.y),
-                                                   fmaf(__uint_as_float(acc[g][4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[g][4 * k + 3]), sc.w, bi.w));
-                            if (a.hasRes) {
-                                float4 rs;
-                                if (resFast) {
-                                    const uint2 raw = rres[p];
-                                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
-                                    const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
-                                    rs = make_float4(f0.x, f0.y, f1.x, f1.y);
-                                } else {
-                                    rs = fyn_fetch(a.res, n, p, a.resP + xo, a.resP + yo);
-                                }
-                                if (a.reluRes) rs = make_float4(fmaxf(rs.x, 0.f), fmaxf(rs.y, 0.f), fmaxf(rs.z, 0.f), fmaxf(rs.w, 0.f));
-                                if (a.bnRes) rs = make_float4(rs.x * sc.x, rs.y * sc.y, rs.z * sc.z, rs.w * sc.w);
-                                v.x += rs.x;
-                                v.y += rs.y;
-                                v.z += rs.z;
-                                v.w += rs.w;
+                for (int k = 0; k < 4; k++) {
+                    if (poff[gi][k] >= 0) {
+                        const int p = pidx[gi][k];
+                        const float4 bi = sEpi[p], sc = sEpi[16 + p];
+                        float4 v = make_float4(fmaf(__uint_as_float(acc[gi][4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[gi][4 * k + 1]), sc.y, bi.y),
+                                               fmaf(__uint_as_float(acc[gi][4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[gi][4 * k + 3]), sc.w, bi.w));
+                        if (a.hasRes) {
+                            float4 rs;
+                            if (resFast) {
+                                const uint2 raw = rres[gi][k];
+                                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+                                const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+                                rs = make_float4(f0.x, f0.y, f1.x, f1.y);
+                            } else {
+                                const int pn = (chalf + 2 * gi) * 4 + k, phase = pn / ppp, fy = phase / a.opx, fx = phase - fy * a.opx;
+                                rs = fyn_fetch(a.res, n, p, a.resP + a.opx * jx + fx, a.resP + a.opy * i + fy);
                             }
-                            *reinterpret_cast<uint2 *>(orow + (long long)p * outPlane + (long long)fy * outRow + fx * 4) =
-                                make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
+                            if (a.reluRes) rs = make_float4(fmaxf(rs.x, 0.f), fmaxf(rs.y, 0.f), fmaxf(rs.z, 0.f), fmaxf(rs.w, 0.f));
+                            if (a.bnRes) rs = make_float4(rs.x * sc.x, rs.y * sc.y, rs.z * sc.z, rs.w * sc.w);
+                            v.x += rs.x;
+                            v.y += rs.y;
+                            v.z += rs.z;
+                            v.w += rs.w;
                         }
+                        *reinterpret_cast<uint2 *>(orow + poff[gi][k]) = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
                     }
                 }
             }
@@ -847,8 +859,9 @@ int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn
     a.res = fyn_make_view(res);
     a.Wo = op->Wo;
     a.Ho = op->Ho;
-    a.Wj = (a.Wo + a.opx - 1) / a.opx;
-    a.Hj = (a.Ho + a.opy - 1) / a.opy;
+    if (a.Wo % a.opx || a.Ho % a.opy) return 1;   // phases must tile the output exactly (else: direct kernel)
+    a.Wj = a.Wo / a.opx;
+    a.Hj = a.Ho / a.opy;
     a.inP = d.in_padding;
     a.outP = d.out_padding;
     a.resP = d.res_padding;
