@@ -71,7 +71,8 @@ EXPORTS = [
     "fyn_abi_version", "fyn_last_error", "fyn_device_count", "fyn_cuda_init", "fyn_cuda_shutdown",
     "fyn_get_device_info", "fyn_launch_count", "fyn_stream_create", "fyn_stream_destroy", "fyn_stream_sync",
     "fyn_event_create", "fyn_event_destroy", "fyn_event_record", "fyn_event_sync", "fyn_event_elapsed_ms",
-    "fyn_stream_wait_event", "fyn_host_alloc", "fyn_host_free", "fyn_tensor_geometry", "fyn_tensor_create",
+    "fyn_stream_wait_event", "fyn_stream_add_callback", "fyn_host_alloc", "fyn_host_free", "fyn_device_alloc", "fyn_device_free",
+    "fyn_memcpy_async", "fyn_download_convert", "fyn_tensor_geometry", "fyn_tensor_create",
     "fyn_tensor_wrap", "fyn_tensor_destroy", "fyn_tensor_clear", "fyn_tensor_get_desc", "fyn_tensor_device_ptr",
     "fyn_upload_f32_async", "fyn_download_f32_async", "fyn_download_f32_elems", "fyn_tensor_write_chw_f32",
     "fyn_tensor_read_chw_f32", "fyn_conv2d_output_size", "fyn_conv2d_create", "fyn_conv2d_load_weights",

@@ -148,6 +148,31 @@ int fyn_stream_wait_event(fyn_ctx *ctx, void *stream, void *event) {
     return FYN_OK;
 }
 
+int fyn_stream_add_callback(fyn_ctx *ctx, void *stream, fyn_host_fn fn, void *user) {
+    if (!ctx || !fn) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
+    FYN_CUDA(cudaLaunchHostFunc((cudaStream_t)stream, (cudaHostFn_t)fn, user));
+    return FYN_OK;
+}
+
+int fyn_device_alloc(fyn_ctx *ctx, size_t bytes, void **ptr) {
+    if (!ctx || !ptr) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
+    FYN_CUDA(cudaSetDevice(ctx->device));
+    FYN_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
+    return FYN_OK;
+}
+
+int fyn_device_free(fyn_ctx *ctx, void *ptr) {
+    if (!ctx) FYN_FAIL(FYN_ERR_INVALID, "ctx is NULL");
+    if (ptr) FYN_CUDA(cudaFree(ptr));
+    return FYN_OK;
+}
+
+int fyn_memcpy_async(fyn_ctx *ctx, void *dst, const void *src, size_t bytes, int device_to_host, void *stream) {
+    if (!ctx || !dst || !src) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
+    FYN_CUDA(cudaMemcpyAsync(dst, src, bytes, device_to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return FYN_OK;
+}
+
 int fyn_host_alloc(fyn_ctx *ctx, size_t bytes, void **ptr) {
     if (!ctx || !ptr) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
     FYN_CUDA(cudaSetDevice(ctx->device));

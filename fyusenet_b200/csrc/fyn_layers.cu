@@ -63,6 +63,16 @@ struct EltArgs {
     ActParams act;
 };
 
+__device__ __forceinline__ float4 elt_apply(const EltArgs &a, float4 v, int t) {
+    v = fyn_act4(v, a.act);
+    if (a.mode == 0) {
+        const float4 s = __ldg(a.scale + t), b = __ldg(a.bias + t);
+        return make_float4(fmaf(v.x, s.x, b.x), fmaf(v.y, s.y, b.y), fmaf(v.z, s.z, b.z), fmaf(v.w, s.w, b.w));
+    }
+    // shaders/sigmoid.frag:10-13
+    return make_float4(1.f / (1.f + __expf(-v.x)), 1.f / (1.f + __expf(-v.y)), 1.f / (1.f + __expf(-v.z)), 1.f / (1.f + __expf(-v.w)));
+}
+
 __global__ void __launch_bounds__(128) k_eltwise(const EltArgs a) {
     unsigned bid = blockIdx.x;
     const int W = a.in.W, H = a.in.H;
@@ -75,17 +85,72 @@ __global__ void __launch_bounds__(128) k_eltwise(const EltArgs a) {
     const int n = bid / a.tiles;
     const int x = xb * 32 + threadIdx.x, y = yb * 4 + threadIdx.y;
     if (x >= W || y >= H) return;
-    float4 v = fyn_act4(fyn_fetch(a.in, n, t, a.in.P + x, a.in.P + y), a.act);
-    float4 r;
-    if (a.mode == 0) {
-        const float4 s = __ldg(a.scale + t), b = __ldg(a.bias + t);
-        r = make_float4(fmaf(v.x, s.x, b.x), fmaf(v.y, s.y, b.y), fmaf(v.z, s.z, b.z), fmaf(v.w, s.w, b.w));
-    } else {
-        // shaders/sigmoid.frag:10-13
-        r = make_float4(1.f / (1.f + __expf(-v.x)), 1.f / (1.f + __expf(-v.y)), 1.f / (1.f + __expf(-v.z)),
-                        1.f / (1.f + __expf(-v.w)));
+    const float4 v = fyn_fetch(a.in, n, t, a.in.P + x, a.in.P + y);
+    fyn_store_texel(a.out, n, t, a.outP + x, a.outP + y, elt_apply(a, v, t));
+}
+
+// fp16 shallow fast path: two texels (16 bytes) per access, 4 accesses in flight per thread, persistent grid.
+// Requires even texture widths / paddings so that every texel pair is 16-byte aligned.
+__global__ void __launch_bounds__(256) k_eltwise_h8(const EltArgs a, long long pairsPerRow, long long rows) {
+    const long long total = pairsPerRow * rows;   // rows = batch * tiles * H
+    const int H = a.in.H;
+    for (long long base = (long long)blockIdx.x * blockDim.x * 4 + threadIdx.x; base < total; base += (long long)gridDim.x * blockDim.x * 4) {
+        uint4 raw[4];
+        long long oidx[4];
+        int tl[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = base + (long long)u * blockDim.x;
+            oidx[u] = -1;
+            if (i < total) {
+                const long long row = i / pairsPerRow;
+                const int xp = (int)(i - row * pairsPerRow);
+                const int y = (int)(row % H);
+                const long long nt = row / H;                 // image * tiles + tile
+                const int t = (int)(nt % a.tiles);
+                const long long n = nt / a.tiles;
+                tl[u] = t;
+                const long long iidx = n * a.in.imageElems + (long long)t * a.in.planeElems + ((long long)(y + a.in.P) * a.in.texW + a.in.P + 2 * xp) * 4;
+                oidx[u] = n * a.out.imageElems + (long long)t * a.out.planeElems + ((long long)(y + a.outP) * a.out.texW + a.outP + 2 * xp) * 4;
+                raw[u] = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(a.in.ptr) + iidx));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (oidx[u] >= 0) {
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[u].x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[u].y));
+                const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[u].z)), f3 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[u].w));
+                const float4 r0 = elt_apply(a, make_float4(f0.x, f0.y, f1.x, f1.y), tl[u]);
+                const float4 r1 = elt_apply(a, make_float4(f2.x, f2.y, f3.x, f3.y), tl[u]);
+                __half2 h0 = __floats2half2_rn(r0.x, r0.y), h1 = __floats2half2_rn(r0.z, r0.w), h2 = __floats2half2_rn(r1.x, r1.y), h3 = __floats2half2_rn(r1.z, r1.w);
+                uint4 o;
+                o.x = *reinterpret_cast<unsigned *>(&h0);
+                o.y = *reinterpret_cast<unsigned *>(&h1);
+                o.z = *reinterpret_cast<unsigned *>(&h2);
+                o.w = *reinterpret_cast<unsigned *>(&h3);
+                *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(a.out.ptr) + oidx[u]) = o;
+            }
+        }
     }
-    fyn_store_texel(a.out, n, t, a.outP + x, a.outP + y, r);
+}
+
+// launches the fast path when its alignment conditions hold, else the generic kernel
+static int launch_eltwise(fyn_ctx *ctx, const EltArgs &a, int W, int H, cudaStream_t stream) {
+    const bool fast = a.in.dtype == FYN_F16 && a.out.dtype == FYN_F16 && a.in.packing == 4 && a.out.packing == 4 && !a.in.deep &&
+                      !a.out.deep && (W % 2 == 0) && (a.in.texW % 2 == 0) && (a.out.texW % 2 == 0) && (a.in.P % 2 == 0) && (a.outP % 2 == 0) &&
+                      (a.in.planeElems % 8 == 0) && (a.out.planeElems % 8 == 0);
+    if (fast) {
+        const long long pairsPerRow = W / 2, rows = (long long)a.batch * a.tiles * H;
+        const long long total = pairsPerRow * rows;
+        long long blocks = (total + 1023) / 1024;
+        const long long cap = (long long)ctx->prop.multiProcessorCount * 8;
+        if (blocks > cap) blocks = cap;
+        k_eltwise_h8<<<(unsigned)blocks, 256, 0, stream>>>(a, pairsPerRow, rows);
+    } else {
+        long long blocks = (long long)((W + 31) / 32) * ((H + 3) / 4) * a.tiles * a.batch;
+        k_eltwise<<<(unsigned)blocks, dim3(32, 4), 0, stream>>>(a);
+    }
+    return 0;
 }
 
 static int check_io(const char *who, const fyn_tensor *t, int w, int h, int c, int pad, bool deep) {
@@ -212,8 +277,7 @@ int fyn_batchnorm_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *s
     // the shallow shader applies no activation (shaders/batchnorm.frag:60-68); the deep one does
     // (shaders/deep/deepbatchnorm.frag:57-58)
     a.act = deep ? fyn_act_from_flags(d.flags, d.leaky, d.clip_lo, d.clip_hi) : ActParams{0, 0.f, 0.f, 0.f};
-    long long blocks = grid_blocks(d.width, d.height, a.tiles, a.batch);
-    k_eltwise<<<(unsigned)blocks, dim3(32, 4), 0, (cudaStream_t)stream>>>(a);
+    launch_eltwise(op->ctx, a, d.width, d.height, (cudaStream_t)stream);
     FYN_CHECK_LAUNCH(op->ctx);
     return FYN_OK;
 }
@@ -248,8 +312,7 @@ int fyn_sigmoid_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *str
     a.outP = d.out_padding;
     a.mode = 1;
     a.act = fyn_act_from_flags(d.flags, d.leaky, d.clip_lo, d.clip_hi);
-    long long blocks = grid_blocks(d.width, d.height, a.tiles, a.batch);
-    k_eltwise<<<(unsigned)blocks, dim3(32, 4), 0, (cudaStream_t)stream>>>(a);
+    launch_eltwise(op->ctx, a, d.width, d.height, (cudaStream_t)stream);
     FYN_CHECK_LAUNCH(op->ctx);
     return FYN_OK;
 }

@@ -213,6 +213,22 @@ size_t fyn_download_f32_elems(const fyn_tensor *t) {
     return (size_t)t->geom.tex_width * t->geom.tex_height * t->geom.planes * t->desc.batch * 4;
 }
 
+int fyn_download_convert(fyn_tensor *t, float *device_staging, void *stream) {
+    if (!t || !device_staging) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t elems = fyn_download_f32_elems(t);
+    if (t->desc.dtype == FYN_F32 && t->geom.packing == 4) {
+        FYN_CUDA(cudaMemcpyAsync(device_staging, t->dptr, elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        return FYN_OK;
+    }
+    const long long texels = (long long)(elems / 4);
+    const int block = 256;
+    const long long grid = (texels + block - 1) / block;
+    k_download_widen<<<(unsigned)grid, block, 0, s>>>(fyn_make_view(t), (float4 *)device_staging, texels);
+    FYN_CHECK_LAUNCH(t->ctx);
+    return FYN_OK;
+}
+
 int fyn_download_f32_async(fyn_tensor *t, float *host, void *stream) {
     if (!t || !host) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
     cudaStream_t s = (cudaStream_t)stream;

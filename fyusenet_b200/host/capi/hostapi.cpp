@@ -2,9 +2,11 @@
 // surfaces (samples/web/stylenet.cpp:190-258, samples/android/app/src/main/cpp/styletransfer.cpp:49-140):
 // opaque handle, everything caught, int status.  Used by tests/ and bench.py (ctypes) to drive the same
 // NeuralNetwork::setup()/forward() path a C++ user of the library calls.
+#include <atomic>
 #include <cstring>
 #include <memory>
 #include <string>
+#include <unordered_map>
 
 #include <fyusenet/fyusenet.h>
 
@@ -38,6 +40,16 @@ int guarded(F &&f) {
     return -1;
 }
 }  // namespace
+
+// asynchronous (pipelined) operation; must be called before setup.  Completed sequences are counted and the last
+// delivered download buffer is remembered (both updated from the engine's completion callback).
+struct AsyncState {
+    std::atomic<uint64_t> completed{0};
+    std::atomic<uint64_t> lastSequence{0};
+    std::atomic<const float *> lastData{nullptr};
+};
+static std::unordered_map<void *, std::shared_ptr<AsyncState>> g_async;
+
 
 extern "C" {
 
@@ -81,6 +93,7 @@ void fynhost_net_destroy(void *handle) {
     NetHandle *h = static_cast<NetHandle *>(handle);
     if (!h) return;
     guarded([&] { h->net()->cleanup(); });
+    g_async.erase(handle);
     delete h;
 }
 
@@ -108,6 +121,43 @@ int fynhost_net_load_weights(void *handle, const float *weights, size_t numFloat
         if (h->kind == NetHandle::STYLE) h->style->loadWeightsAndBiases(weights, numFloats);
         else h->resnet->loadWeightsAndBiases(weights, numFloats);
     });
+}
+
+int fynhost_net_asynchronous(void *handle) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] {
+        auto st = std::make_shared<AsyncState>();
+        g_async[handle] = st;
+        NeuralNetwork::AsyncAdapter adapter;
+        adapter.downloadReady([st](const std::string &, uint64_t seq, cpu::CPUBuffer *buf) {
+            st->lastSequence = seq;
+            st->lastData = buf ? static_cast<const float *>(buf->raw()) : nullptr;
+            st->completed++;
+        });
+        h->net()->asynchronous(adapter);
+    });
+}
+
+// number of sequences whose download has been delivered; *lastSequence / *data describe the most recent one
+uint64_t fynhost_net_async_completed(void *handle, uint64_t *lastSequence, const float **data) {
+    auto it = g_async.find(handle);
+    if (it == g_async.end()) return 0;
+    if (lastSequence) *lastSequence = it->second->lastSequence;
+    if (data) *data = it->second->lastData;
+    return it->second->completed;
+}
+
+// pinned input buffer `slot` (0/1) of an asynchronous StyleNet: sequence s uploads from slot s & 1
+float *fynhost_stylenet_input_buffer_slot(void *handle, int slot, size_t *numFloats) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    float *ptr = nullptr;
+    guarded([&] {
+        if (h->kind != NetHandle::STYLE) THROW_EXCEPTION_ARGS(FynException, "Not a StyleNet");
+        cpu::CPUBuffer *buf = h->style->inputBuffer(slot);
+        if (numFloats) *numFloats = buf->bytes() / sizeof(float);
+        ptr = static_cast<float *>(buf->raw());
+    });
+    return ptr;
 }
 
 int fynhost_net_set_batch(void *handle, int batch) {

@@ -4,12 +4,16 @@
 // synchronise after the download layer (the reference's blocking glReadPixels); optional CUDA-graph replay
 // removes per-layer launch latency for static networks.
 #pragma once
+#include <condition_variable>
 #include <cstdint>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
 
 #include "../gpu/gfxcontextlink.h"
+#include "../cpu/cpubuffer.h"
 #include "compiledlayers.h"
 
 namespace fyusion {
@@ -20,6 +24,7 @@ class NeuralNetwork;
 class Engine : public GfxContextTracker {
  public:
     enum execstate { EXEC_DONE = 0, EXEC_DEFERRED, EXEC_STOPPED, EXEC_ERROR };
+    struct Completion { Engine *engine; uint64_t sequence; cpu::CPUBuffer *buffer; };
 
     explicit Engine(const GfxContextLink &ctx = GfxContextLink(), bool async = false);
     ~Engine();
@@ -44,9 +49,26 @@ class Engine : public GfxContextTracker {
     void disableIntermediateOutput() { writeResults_ = false; }
     // capture the layer sequence into a CUDA graph on the next forward and replay it afterwards
     void enableGraph(bool on) { useGraph_ = on; }
+    // asynchronous operation: callbacks fired from a driver thread when a sequence's download has landed
+    using DownloadCallback = std::function<void(uint64_t sequence, cpu::CPUBuffer *buffer)>;
+    void setDownloadCallback(const DownloadCallback &cb) { downloadCallback_ = cb; }
+    bool isAsync() const { return async_; }
+    int sequencesInFlight();
+    // host-side completion hook (called through fyn_stream_add_callback)
+    void sequenceCompleted(uint64_t sequence, cpu::CPUBuffer *buffer);
 
  private:
     execstate execute(uint64_t sequence);
+    execstate executeAsync(uint64_t sequence);
+    // pipeline state of the asynchronous path: at most two sequences in flight (reference: engine.cpp:314-316)
+    constexpr static int MAX_IN_FLIGHT = 2;
+    void *uploadDone_[2] = {nullptr, nullptr}, *computeDone_[2] = {nullptr, nullptr}, *copyDone_[2] = {nullptr, nullptr};
+    bool slotUsed_[2] = {false, false};
+    Completion completions_[2];
+    std::mutex flightLock_;
+    std::condition_variable flightCv_;
+    int inFlight_ = 0;
+    DownloadCallback downloadCallback_;
     void collectTimings(bool sync);
     struct EventPair { int layer; void *start; void *stop; };
     std::vector<EventPair> pendingEvents_;

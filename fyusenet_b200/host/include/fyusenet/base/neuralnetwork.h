@@ -30,6 +30,21 @@ class NeuralNetwork : public GfxContextTracker {
     virtual void setup();
     virtual execstate forward();
     virtual execstate finish();
+    // Asynchronous operation (reference: neuralnetwork.h:96-160, neuralnetwork.cpp:205-211).  Must be called before
+    // setup().  forward() then only enqueues (EXEC_DEFERRED, at most two sequences in flight) and the adapter's
+    // callbacks fire from a driver thread when an upload buffer may be refilled / a download has landed.
+    class AsyncAdapter {
+     public:
+        AsyncAdapter &newSequence(const std::function<void(uint64_t)> &cb) { newSeq_ = cb; return *this; }
+        AsyncAdapter &sequenceDone(const std::function<void(uint64_t)> &cb) { seqDone_ = cb; return *this; }
+        AsyncAdapter &downloadReady(const std::function<void(const std::string &, uint64_t, cpu::CPUBuffer *)> &cb) { downReady_ = cb; return *this; }
+        AsyncAdapter &uploadReady(const std::function<void(const std::string &, uint64_t)> &cb) { upReady_ = cb; return *this; }
+        std::function<void(uint64_t)> newSeq_, seqDone_;
+        std::function<void(const std::string &, uint64_t, cpu::CPUBuffer *)> downReady_;
+        std::function<void(const std::string &, uint64_t)> upReady_;
+    };
+    virtual void asynchronous(const AsyncAdapter &adapter = AsyncAdapter());
+    bool isAsynchronous() const { return async_; }
     uint64_t nextSequenceNo() const { return engine_ ? engine_->nextSequenceNo() : 0; }
     uint64_t lastSequenceNo() const { return engine_ ? engine_->lastSequenceNo() : 0; }
     // batch is new on this backend (the reference is batch-1, README.md:72); must be set before setup()
@@ -46,6 +61,7 @@ class NeuralNetwork : public GfxContextTracker {
     virtual void connectLayers(CompiledLayers &layers, BufferManager *buffers) = 0;
 
     bool async_ = false;
+    AsyncAdapter asyncCallbacks_;
     Engine *engine_ = nullptr;
     BufferManager *bufferMgr_ = nullptr;
     bool setup_ = false;

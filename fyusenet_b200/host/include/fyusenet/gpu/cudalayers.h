@@ -107,6 +107,9 @@ class UploadLayer : public GPULayerBase, public cpu::CPULayerInterface {
     void clearOutputBuffers(int = -1) override {}
     void clearInputBuffers(int = -1) override { input_ = nullptr; }
     bool isAsync() const { return async_; }
+    // asynchronous path (reference: gpu/uploadlayer.cpp:395-541): copy the current input buffer into output buffer
+    // `slot` on `stream`; returns the tensor that now carries the sequence
+    TensorHandle asyncUpload(uint64_t sequence, int slot, void *stream);
 
  protected:
     CPUBuffer *input_ = nullptr;
@@ -134,9 +137,18 @@ class DownloadLayer : public GPULayerBase, public cpu::CPULayerInterface {
     bool isAsync() const { return async_; }
     // the engine synchronises the stream after the last layer unless the download is asynchronous
     bool needsSync() const { return !async_; }
+    // asynchronous path (reference: gpu/downloadlayer.cpp:139-157,307-323), split in its device and host halves:
+    // convert the input tensor into device staging buffer `slot` (compute stream), then copy staging -> host buffer
+    // `slot` (download stream).  Both staging and the second host buffer are created on first use.
+    void asyncConvert(int slot, void *stream);
+    CPUBuffer *asyncCopy(uint64_t sequence, int slot, void *stream);
+    CPUBuffer *asyncBuffer(int slot);
+    void cleanup() override;
 
  protected:
     CPUBuffer *output_ = nullptr;
+    CPUBuffer *asyncOutputs_[2] = {nullptr, nullptr};
+    float *staging_[2] = {nullptr, nullptr};
     bool async_ = false;
     UpDownLayerBuilder::callback_t callback_;
 };

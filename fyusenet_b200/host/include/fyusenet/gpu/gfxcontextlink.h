@@ -29,9 +29,20 @@ class CudaContext {
     }
     ~CudaContext() {
         if (ctx_) {
+            if (uploadStream_) fyn_stream_destroy(ctx_, uploadStream_);
+            if (downloadStream_) fyn_stream_destroy(ctx_, downloadStream_);
             fyn_stream_destroy(ctx_, stream_);
             fyn_cuda_shutdown(ctx_);
         }
+    }
+    // side streams of the asynchronous engine (the role of the AsyncPool's shared GL contexts, gl/asyncpool.h:28-50)
+    void *uploadStream() {
+        if (!uploadStream_) FYN_ABI_CALL(fyn_stream_create(ctx_, &uploadStream_));
+        return uploadStream_;
+    }
+    void *downloadStream() {
+        if (!downloadStream_) FYN_ABI_CALL(fyn_stream_create(ctx_, &downloadStream_));
+        return downloadStream_;
     }
     CudaContext(const CudaContext &) = delete;
     CudaContext &operator=(const CudaContext &) = delete;
@@ -45,6 +56,7 @@ class CudaContext {
     int device_ = 0;
     fyn_ctx *ctx_ = nullptr;
     void *stream_ = nullptr;
+    void *uploadStream_ = nullptr, *downloadStream_ = nullptr;
     void *externalStream_ = nullptr;
     bool useExternal_ = false;
 };

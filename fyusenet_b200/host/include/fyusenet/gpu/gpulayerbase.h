@@ -52,6 +52,17 @@ class GPULayerBase : public LayerBase, public GfxContextTracker {
     virtual bool hasOutputTexture(int index = 0) const { return index < (int)outputs_.size() && outputs_[index]; }
     virtual TensorHandle getOutputTexture(int index = 0) const { return hasOutputTexture(index) ? outputs_[index] : nullptr; }
     virtual TensorHandle getInputTexture(int port = 0) const { return hasInputTexture(port) ? inputs_[port] : nullptr; }
+    // output tensor of buffer `slot` (0 = primary, >0 = shadow buffers of asynchronous producers)
+    TensorHandle getOutputTexture(int index, int slot) const {
+        if (slot == 0) return getOutputTexture(index);
+        return (slot - 1 < (int)shadowOutputs_.size()) ? shadowOutputs_[slot - 1] : nullptr;
+    }
+    // layers reading this layer's output (needed to re-point them at a shadow buffer)
+    void addOutputConnection(int port, LayerBase *receiver, int receiverPort) override {
+        LayerBase::addOutputConnection(port, receiver, receiverPort);
+        if (receiver) receivers_.push_back({receiver, receiverPort});
+    }
+    const std::vector<std::pair<LayerBase *, int>> &receivers() const { return receivers_; }
 
     // float32 [C][H][W] dump without padding (reference: layerbase.h:160-172, gpulayerbase.cpp:443-523)
     void writeResult(const char *fileName, bool includePadding = false) override;
@@ -76,6 +87,7 @@ class GPULayerBase : public LayerBase, public GfxContextTracker {
     BufferSpec::order order() const { return (flags_ & LayerFlags::DEEP) ? BufferSpec::order::GPU_DEEP : BufferSpec::order::GPU_SHALLOW; }
 
     std::vector<TensorHandle> inputs_, residuals_, outputs_, shadowOutputs_;
+    std::vector<std::pair<LayerBase *, int>> receivers_;
     int viewport_[2] = {0, 0};
     std::recursive_mutex processingLock_;  // reference: gpulayerbase.h:191
 };

@@ -43,6 +43,30 @@ StyleNetBase::StyleNetBase(int kernel, int resBlocks, int width, int height, boo
 StyleNetBase::~StyleNetBase() {
     cleanup();
     delete inBuffer_;
+    delete inBuffers_[0];
+    delete inBuffers_[1];
+}
+
+// In asynchronous mode the upload layer reads input buffer (sequence & 1): the caller fills inputBuffer(slot) for
+// the next sequence while the previous one is still being processed (the reference cycles two upload buffers the
+// same way, stylenet_base.cpp:110-155).
+NeuralNetwork::execstate StyleNetBase::forward() {
+    if (async_ && upload_ && setup_) {
+        const int slot = (int)(engine_->nextSequenceNo() & 1);
+        static_cast<gpu::UploadLayer *>(engine_->getLayers()["upload"])->setInputBuffer(inputBuffer(slot), 0);
+    }
+    return NeuralNetwork::forward();
+}
+
+StyleNetBase::CPUBuffer *StyleNetBase::inputBuffer(int slot) {
+    if (!setup_) THROW_EXCEPTION_ARGS(FynException, "Please run setup() before setting input buffers");
+    if (!upload_) THROW_EXCEPTION_ARGS(FynException, "Network was created without an upload layer");
+    if (slot < 0 || slot > 1) THROW_EXCEPTION_ARGS(FynException, "Illegal input buffer %d", slot);
+    if (!inBuffers_[slot]) {
+        cpu::CPUBufferShape shape(height_, width_, 3, 0, cpu::CPUBufferShape::FLOAT32, BufferSpec::order::GPU_SHALLOW, batch_);
+        inBuffers_[slot] = shape.createBuffer(context());
+    }
+    return inBuffers_[slot];
 }
 
 void StyleNetBase::loadWeightsAndBiases(const float *weightsAndBiases, size_t size) {
@@ -63,6 +87,7 @@ CompiledLayers StyleNetBase::buildLayers() {
     if (upload_) {
         auto *up = new gpu::UpDownLayerBuilder(gpu::UpDownLayerBuilder::UPLOAD, "upload");
         up->shape(3, height_, width_, 3).context(context()).number(UPLOAD);
+        if (async_) up->async();
         up->push(factory);
     }
     for (size_t i = 0; i < convs_.size(); i++) {
@@ -84,6 +109,7 @@ CompiledLayers StyleNetBase::buildLayers() {
     if (download_) {
         auto *down = new gpu::UpDownLayerBuilder(gpu::UpDownLayerBuilder::DOWNLOAD, "download");
         down->shape(4, height_, width_, 4).context(context()).number(downloadLayer_);
+        if (async_) down->async();
         down->push(factory);
     }
     return factory->compileLayers();
@@ -120,7 +146,7 @@ StyleNetBase::CPUBuffer *StyleNetBase::inputBuffer() {
 }
 
 void StyleNetBase::setInputBuffer(const float *data) {
-    CPUBuffer *buf = inputBuffer();
+    CPUBuffer *buf = async_ ? inputBuffer((int)(engine_->nextSequenceNo() & 1)) : inputBuffer();
     float *tgt = buf->map<float>();
     memcpy(tgt, data, buf->bytes());
     buf->unmap();

@@ -23,10 +23,18 @@ void Engine::setup(NeuralNetwork *net) {
 
 void Engine::cleanup() {
     if (setup_) {
+        if (async_) finish();
         FYN_ABI_CALL(fyn_stream_sync(context_.handle(), context_.stream()));
         collectTimings(false);
         for (void *e : freeEvents_) fyn_event_destroy(context_.handle(), e);
         freeEvents_.clear();
+        for (int i = 0; i < 2; i++) {
+            if (uploadDone_[i]) fyn_event_destroy(context_.handle(), uploadDone_[i]);
+            if (computeDone_[i]) fyn_event_destroy(context_.handle(), computeDone_[i]);
+            if (copyDone_[i]) fyn_event_destroy(context_.handle(), copyDone_[i]);
+            uploadDone_[i] = computeDone_[i] = copyDone_[i] = nullptr;
+            slotUsed_[i] = false;
+        }
         layers_.cleanup();
     }
     layers_ = CompiledLayers();
@@ -42,8 +50,91 @@ void Engine::resetTimings() {
 
 Engine::execstate Engine::forwardLayers() {
     if (!setup_) return EXEC_ERROR;
+    if (async_) {
+        // back-pressure: wait until fewer than two sequences are in flight (reference: engine.cpp:310-329)
+        std::unique_lock<std::mutex> lck(flightLock_);
+        flightCv_.wait(lck, [this]() { return inFlight_ < MAX_IN_FLIGHT; });
+        inFlight_++;
+        lck.unlock();
+        uint64_t seq = sequenceNo_++;
+        return executeAsync(seq);
+    }
     uint64_t seq = sequenceNo_++;
     return execute(seq);
+}
+
+int Engine::sequencesInFlight() {
+    std::lock_guard<std::mutex> lck(flightLock_);
+    return inFlight_;
+}
+
+void Engine::sequenceCompleted(uint64_t sequence, cpu::CPUBuffer *buffer) {
+    if (buffer) buffer->setSequence(sequence);
+    if (downloadCallback_) downloadCallback_(sequence, buffer);
+    {
+        std::lock_guard<std::mutex> lck(flightLock_);
+        inFlight_--;
+    }
+    flightCv_.notify_all();
+}
+
+static void engineCompletionTrampoline(void *user) {
+    auto *c = static_cast<Engine::Completion *>(user);
+    c->engine->sequenceCompleted(c->sequence, c->buffer);
+}
+
+// Pipelined execution on three streams (upload / compute / download), double-buffered at both ends:
+//   upload(n+1)  ||  layers(n)  ||  host copy(n-1)
+// The reference gets the same overlap from PBO uploads on AsyncPool threads with shadow textures
+// (gpu/uploadlayer.cpp:395-541) and fenced PBO read-backs (gpu/downloadlayer.cpp:139-157,307-323).
+Engine::execstate Engine::executeAsync(uint64_t sequence) {
+    fyn_ctx *ctx = context_.handle();
+    CudaContext *cc = context_.interface();
+    void *sC = context_.stream(), *sU = cc->uploadStream(), *sD = cc->downloadStream();
+    const int slot = (int)(sequence & 1);
+    for (int i = 0; i < 2; i++) {
+        if (!uploadDone_[i]) {
+            FYN_ABI_CALL(fyn_event_create(ctx, &uploadDone_[i]));
+            FYN_ABI_CALL(fyn_event_create(ctx, &computeDone_[i]));
+            FYN_ABI_CALL(fyn_event_create(ctx, &copyDone_[i]));
+        }
+    }
+    gpu::UploadLayer *upload = nullptr;
+    gpu::DownloadLayer *download = nullptr;
+    for (auto it = layers_.begin(); it != layers_.end(); ++it) {
+        if (!upload) upload = dynamic_cast<gpu::UploadLayer *>(it.second);
+        if (auto *d = dynamic_cast<gpu::DownloadLayer *>(it.second)) download = d;
+    }
+    // ---- upload: buffer `slot` is free once the layers of sequence-2 have consumed it
+    if (upload) {
+        if (slotUsed_[slot]) FYN_ABI_CALL(fyn_stream_wait_event(ctx, sU, computeDone_[slot]));
+        gpu::TensorHandle t = upload->asyncUpload(sequence, slot, sU);
+        FYN_ABI_CALL(fyn_event_record(ctx, uploadDone_[slot], sU));
+        FYN_ABI_CALL(fyn_stream_wait_event(ctx, sC, uploadDone_[slot]));
+        for (auto &rcv : upload->receivers())
+            if (auto *g = dynamic_cast<gpu::GPULayerBase *>(rcv.first)) g->updateInputTexture(t, rcv.second);
+    }
+    // ---- layers on the compute stream
+    for (auto it = layers_.begin(); it != layers_.end(); ++it) {
+        LayerBase *layer = it.second;
+        if (layer == upload || layer == download) continue;
+        layer->forward(sequence);
+    }
+    // ---- download: device half on the compute stream (staging buffer `slot` is free once copy(sequence-2) is done),
+    //      host half on the download stream
+    cpu::CPUBuffer *buffer = nullptr;
+    if (download) {
+        if (slotUsed_[slot]) FYN_ABI_CALL(fyn_stream_wait_event(ctx, sC, copyDone_[slot]));
+        download->asyncConvert(slot, sC);
+    }
+    FYN_ABI_CALL(fyn_event_record(ctx, computeDone_[slot], sC));
+    FYN_ABI_CALL(fyn_stream_wait_event(ctx, sD, computeDone_[slot]));
+    if (download) buffer = download->asyncCopy(sequence, slot, sD);
+    FYN_ABI_CALL(fyn_event_record(ctx, copyDone_[slot], sD));
+    completions_[slot] = Completion{this, sequence, buffer};
+    FYN_ABI_CALL(fyn_stream_add_callback(ctx, sD, engineCompletionTrampoline, &completions_[slot]));
+    slotUsed_[slot] = true;
+    return EXEC_DEFERRED;
 }
 
 // strict ascending-layer-number execution (reference: engine.cpp:386-683, hot loop 1).
@@ -99,6 +190,11 @@ void Engine::collectTimings(bool sync) {
 
 Engine::execstate Engine::finish() {
     if (!setup_) return EXEC_ERROR;
+    if (async_) {
+        // all deferred sequences must have delivered their download (reference: engine.cpp:264-274, 5 s timeout there)
+        std::unique_lock<std::mutex> lck(flightLock_);
+        flightCv_.wait(lck, [this]() { return inFlight_ == 0; });
+    }
     FYN_ABI_CALL(fyn_stream_sync(context_.handle(), context_.stream()));
     collectTimings(false);
     return EXEC_DONE;
@@ -117,6 +213,12 @@ NeuralNetwork::~NeuralNetwork() {
     if (engine_ || bufferMgr_) cleanup();
 }
 
+void NeuralNetwork::asynchronous(const AsyncAdapter &adapter) {
+    if (setup_) THROW_EXCEPTION_ARGS(FynException, "Cannot switch to asynchronous operation after setup()");
+    async_ = true;
+    asyncCallbacks_ = adapter;
+}
+
 void NeuralNetwork::setBatch(int batch) {
     if (setup_) THROW_EXCEPTION_ARGS(FynException, "Batch size must be set before setup()");
     if (batch < 1) THROW_EXCEPTION_ARGS(FynException, "Illegal batch size %d", batch);
@@ -128,6 +230,13 @@ void NeuralNetwork::setup() {
     if (!context_.isValid()) setContext(GfxContextManager::instance(0)->createMainContext());
     engine_ = new Engine(context_, async_);
     engine_->setup(this);
+    if (async_) {
+        AsyncAdapter cbs = asyncCallbacks_;
+        engine_->setDownloadCallback([cbs](uint64_t seq, cpu::CPUBuffer *buf) {
+            if (cbs.downReady_) cbs.downReady_("download", seq, buf);
+            if (cbs.seqDone_) cbs.seqDone_(seq);
+        });
+    }
     setup_ = true;
 }
 
@@ -152,6 +261,7 @@ NeuralNetwork::execstate NeuralNetwork::forward() {
         return st;
     }
     st.sequenceNo = engine_->nextSequenceNo();
+    if (async_ && asyncCallbacks_.newSeq_) asyncCallbacks_.newSeq_(st.sequenceNo);
     st.status = engine_->forwardLayers();
     return st;
 }

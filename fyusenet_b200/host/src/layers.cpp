@@ -301,6 +301,19 @@ void UploadLayer::forward(uint64_t sequence) {
     if (callback_) callback_(sequence, input_, AsyncLayer::UPLOAD_DONE);
 }
 
+TensorHandle UploadLayer::asyncUpload(uint64_t sequence, int slot, void *stream) {
+    if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    if (!input_) THROW_EXCEPTION_ARGS(FynException, "No input buffer set for upload layer %s", name_.c_str());
+    TensorHandle target = getOutputTexture(0, slot);
+    if (!target) THROW_EXCEPTION_ARGS(FynException, "Upload layer %s has no output buffer %d", name_.c_str(), slot);
+    const float *src = input_->map<float>();
+    input_->unmap();
+    if (callback_) callback_(sequence, input_, AsyncLayer::UPLOAD_COMMENCED);
+    FYN_ABI_CALL(fyn_upload_f32_async(target, src, stream));
+    return target;
+}
+
 // ------------------------------------------------------------------------------------------------
 // DownloadLayer: tensor -> host float32 in texel order (gpu/downloadlayer.cpp:112-131,257-283)
 // ------------------------------------------------------------------------------------------------
@@ -334,6 +347,44 @@ void DownloadLayer::forward(uint64_t sequence) {
         if (callback_) callback_(sequence, output_, AsyncLayer::DOWNLOAD_DONE);
     }
 }
+CPUBuffer *DownloadLayer::asyncBuffer(int slot) {
+    if (slot == 0) return output_;
+    if (!asyncOutputs_[slot]) {
+        if (!output_) THROW_EXCEPTION_ARGS(FynException, "No output buffer set for download layer %s", name_.c_str());
+        asyncOutputs_[slot] = output_->shape().createBuffer(context_);   // second pinned buffer for the pipeline
+    }
+    return asyncOutputs_[slot];
+}
+
+void DownloadLayer::asyncConvert(int slot, void *stream) {
+    if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    if (!staging_[slot]) {
+        void *p = nullptr;
+        FYN_ABI_CALL(fyn_device_alloc(context_.handle(), fyn_download_f32_elems(in(0)) * sizeof(float), &p));
+        staging_[slot] = static_cast<float *>(p);
+    }
+    FYN_ABI_CALL(fyn_download_convert(in(0), staging_[slot], stream));
+}
+
+CPUBuffer *DownloadLayer::asyncCopy(uint64_t sequence, int slot, void *stream) {
+    CPUBuffer *buf = asyncBuffer(slot);
+    const size_t bytes = fyn_download_f32_elems(in(0)) * sizeof(float);
+    if (buf->bytes() < bytes) THROW_EXCEPTION_ARGS(FynException, "Download buffer too small (%zu < %zu bytes)", buf->bytes(), bytes);
+    if (callback_) callback_(sequence, buf, AsyncLayer::DOWNLOAD_COMMENCED);
+    FYN_ABI_CALL(fyn_memcpy_async(context_.handle(), buf->raw(), staging_[slot], bytes, 1, stream));
+    return buf;
+}
+
+void DownloadLayer::cleanup() {
+    for (int i = 0; i < 2; i++) {
+        if (staging_[i]) fyn_device_free(context_.handle(), staging_[i]);
+        staging_[i] = nullptr;
+        delete asyncOutputs_[i];
+        asyncOutputs_[i] = nullptr;
+    }
+    GPULayerBase::cleanup();
+}
+
 void DownloadLayer::writeResult(const char *fileName, bool) {
     if (!output_) return;
     CPUBuffer *cw = output_->toChannelWise();

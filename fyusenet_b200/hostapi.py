@@ -36,6 +36,8 @@ def lib():
         L.fynhost_net_weight_offset.restype = C.c_longlong
         L.fynhost_net_output.restype = C.POINTER(C.c_float)
         L.fynhost_net_input_buffer.restype = C.POINTER(C.c_float)
+        L.fynhost_stylenet_input_buffer_slot.restype = C.POINTER(C.c_float)
+        L.fynhost_net_async_completed.restype = C.c_uint64
         L.fynhost_stylenet_output_tensor.restype = C.c_void_p
         L.fynhost_net_context.restype = C.c_void_p
         L.fynhost_net_stream.restype = C.c_void_p
@@ -106,6 +108,17 @@ class Network:
     def finish(self):
         _check(lib().fynhost_net_finish(self._h))
 
+    # -- asynchronous (pipelined) operation ---------------------------------------------------
+    def asynchronous(self):
+        """NeuralNetwork::asynchronous(): call before setup(); forward() then only enqueues (<= 2 sequences in flight)."""
+        _check(lib().fynhost_net_asynchronous(self._h))
+
+    def async_completed(self):
+        """(number of delivered sequences, last delivered sequence number, pointer to its host buffer or None)"""
+        seq, data = C.c_uint64(), C.POINTER(C.c_float)()
+        n = lib().fynhost_net_async_completed(self._h, C.byref(seq), C.byref(data))
+        return int(n), int(seq.value), data
+
     def output(self) -> np.ndarray:
         n = C.c_size_t()
         p = lib().fynhost_net_output(self._h, C.byref(n))
@@ -169,6 +182,14 @@ class StyleNet(Network):
 
     def set_input_tensor(self, tensor: capi.Tensor):
         _check(lib().fynhost_stylenet_set_input_tensor(self._h, tensor._h))
+
+    def input_buffer_slot(self, slot: int) -> np.ndarray:
+        """Pinned input buffer 0/1 of an asynchronous network (sequence s reads slot s & 1)."""
+        n = C.c_size_t()
+        p = lib().fynhost_stylenet_input_buffer_slot(self._h, int(slot), C.byref(n))
+        if not p:
+            raise HostError(lib().fynhost_last_error().decode(errors="replace"))
+        return np.ctypeslib.as_array(p, shape=(n.value,))
 
     def output_rgba(self) -> np.ndarray:
         """download buffer as [batch?][H][W][4] float32 (RGBA, alpha = 0.5: compare RGB only)."""

@@ -102,9 +102,18 @@ int fyn_event_sync(fyn_ctx *ctx, void *event);                /* blocking */
 int fyn_event_elapsed_ms(fyn_ctx *ctx, void *start, void *stop, float *ms);
 int fyn_stream_wait_event(fyn_ctx *ctx, void *stream, void *event);
 
+/* host function executed in stream order (replaces the GLsync waiter threads of the asynchronous download,
+ * fyusenet/gpu/downloadlayer.cpp:307-323): fn(user) runs on a driver thread once all prior work of `stream` is done */
+typedef void (*fyn_host_fn)(void *user);
+int fyn_stream_add_callback(fyn_ctx *ctx, void *stream, fyn_host_fn fn, void *user);
+
 /* pinned host memory (replaces PBOPool / ManagedPBO, fyusenet/gl/pbopool.cpp) */
 int fyn_host_alloc(fyn_ctx *ctx, size_t bytes, void **ptr);
 int fyn_host_free(fyn_ctx *ctx, void *ptr);
+/* raw device staging memory + asynchronous copies for the pipelined (asynchronous) upload / download path */
+int fyn_device_alloc(fyn_ctx *ctx, size_t bytes, void **ptr);
+int fyn_device_free(fyn_ctx *ctx, void *ptr);
+int fyn_memcpy_async(fyn_ctx *ctx, void *dst, const void *src, size_t bytes, int device_to_host, void *stream);
 
 /* ----------------------------------------------------------------------------------------- */
 /* device tensors  (replace BufferManager::createTexture, fyusenet/base/buffermanager.cpp:650-708) */
@@ -171,6 +180,9 @@ int fyn_upload_f32_async(fyn_tensor *tensor, const float *host, void *stream);
  * convert kernel into a device staging buffer first.  Asynchronous when `host` is pinned. */
 int fyn_download_f32_async(fyn_tensor *tensor, float *host, void *stream);
 size_t fyn_download_f32_elems(const fyn_tensor *tensor);
+/* the device half of a download: tensor -> float32 RGBA texels in DEVICE memory `device_staging`
+ * (fyn_download_f32_elems floats); the host copy is then a plain fyn_memcpy_async on another stream */
+int fyn_download_convert(fyn_tensor *tensor, float *device_staging, void *stream);
 
 /* Debug / parity interchange (LayerBase::writeResult format, fyusenet/base/layerbase.h:160-172 and
  * GPULayerBase::copyResult, fyusenet/gpu/gpulayerbase.cpp:525-560): float32 [batch][C][H][W]

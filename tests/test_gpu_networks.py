@@ -145,3 +145,43 @@ def test_resnet50_matches_oracle(batch, tmp_path):
                     r = dump[l["number"]]
                     assert rel_l2(y, r) <= 4e-3, f"layer {l['name']}: rel-L2 {rel_l2(y, r):.2e}"
     net.destroy()
+
+
+def test_stylenet_asynchronous_pipeline():
+    """NeuralNetwork::asynchronous(): forward() only enqueues (<= 2 sequences in flight), upload / layers / download
+    run on three streams with double buffering, downloads are delivered per sequence (unit_tests/asynctests.cpp runs
+    the same scenario without a pass criterion; here every delivered frame must equal the synchronous result)."""
+    import time
+    weights = fo.stylenet_synthetic_weights(3)
+    w, h = 128, 96
+    imgs = [fo.synthetic_image(h, w, 20 + i) for i in range(2)]
+    sync = hostapi.StyleNet(3, w, h)
+    sync.load_weights(weights)
+    sync.setup()
+    want = []
+    for im in imgs:
+        sync.set_input(im)
+        sync.forward()
+        want.append(sync.output_rgba()[0].copy())
+    sync.destroy()
+    net = hostapi.StyleNet(3, w, h)
+    net.asynchronous()
+    net.load_weights(weights)
+    net.setup()
+    for k in range(2):
+        net.input_buffer_slot(k)[:] = imgs[k].reshape(-1)       # sequence s uploads from slot s & 1; sequences start at 1
+    nseq = 9
+    for s in range(nseq):
+        net.forward()
+    net.finish()
+    done, last_seq, data = net.async_completed()
+    assert done == nseq and last_seq == nseq
+    got = np.ctypeslib.as_array(data, shape=(h, w, 4)).copy()
+    np.testing.assert_array_equal(got, want[nseq & 1])         # slot of the last sequence
+    # the other buffer still holds sequence nseq-1
+    net.forward()
+    net.finish()
+    done, last_seq, data = net.async_completed()
+    assert (done, last_seq) == (nseq + 1, nseq + 1)
+    np.testing.assert_array_equal(np.ctypeslib.as_array(data, shape=(h, w, 4)), want[(nseq + 1) & 1])
+    net.destroy()
