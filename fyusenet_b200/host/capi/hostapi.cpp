@@ -147,7 +147,7 @@ uint64_t fynhost_net_async_completed(void *handle, uint64_t *lastSequence, const
     return it->second->completed;
 }
 
-// pinned input buffer `slot` (0/1) of an asynchronous StyleNet: sequence s uploads from slot s & 1
+// pinned input buffer `slot` of an asynchronous StyleNet: sequence s uploads from slot s % fynhost_async_slots()
 float *fynhost_stylenet_input_buffer_slot(void *handle, int slot, size_t *numFloats) {
     NetHandle *h = static_cast<NetHandle *>(handle);
     float *ptr = nullptr;
@@ -159,6 +159,8 @@ float *fynhost_stylenet_input_buffer_slot(void *handle, int slot, size_t *numFlo
     });
     return ptr;
 }
+
+int fynhost_async_slots(void) { return Engine::ASYNC_SLOTS; }
 
 int fynhost_net_set_batch(void *handle, int batch) {
     NetHandle *h = static_cast<NetHandle *>(handle);

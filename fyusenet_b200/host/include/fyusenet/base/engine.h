@@ -24,6 +24,8 @@ class NeuralNetwork;
 class Engine : public GfxContextTracker {
  public:
     enum execstate { EXEC_DONE = 0, EXEC_DEFERRED, EXEC_STOPPED, EXEC_ERROR };
+    constexpr static int ASYNC_SLOTS = 3;       // buffers per pipeline interface == max sequences in flight
+    constexpr static int MAX_IN_FLIGHT = ASYNC_SLOTS;
     struct Completion { Engine *engine; uint64_t sequence; cpu::CPUBuffer *buffer; };
 
     explicit Engine(const GfxContextLink &ctx = GfxContextLink(), bool async = false);
@@ -60,11 +62,11 @@ class Engine : public GfxContextTracker {
  private:
     execstate execute(uint64_t sequence);
     execstate executeAsync(uint64_t sequence);
-    // pipeline state of the asynchronous path: at most two sequences in flight (reference: engine.cpp:314-316)
-    constexpr static int MAX_IN_FLIGHT = 2;
-    void *uploadDone_[2] = {nullptr, nullptr}, *computeDone_[2] = {nullptr, nullptr}, *copyDone_[2] = {nullptr, nullptr};
-    bool slotUsed_[2] = {false, false};
-    Completion completions_[2];
+    // pipeline state of the asynchronous path.  The reference allows two sequences in flight (engine.cpp:314-316);
+    // with three pipeline stages (upload / layers / host copy) three slots are needed to keep all of them busy.
+    void *uploadDone_[ASYNC_SLOTS] = {}, *computeDone_[ASYNC_SLOTS] = {}, *copyDone_[ASYNC_SLOTS] = {};
+    bool slotUsed_[ASYNC_SLOTS] = {};
+    Completion completions_[ASYNC_SLOTS];
     std::mutex flightLock_;
     std::condition_variable flightCv_;
     int inFlight_ = 0;

@@ -10,6 +10,7 @@
 #pragma once
 #include "../base/batchnorminterface.h"
 #include "../base/convlayerinterface.h"
+#include "../base/engine.h"
 #include "../base/layerfactory.h"
 #include "../cpu/cpubuffer.h"
 #include "gpulayerbase.h"
@@ -147,8 +148,8 @@ class DownloadLayer : public GPULayerBase, public cpu::CPULayerInterface {
 
  protected:
     CPUBuffer *output_ = nullptr;
-    CPUBuffer *asyncOutputs_[2] = {nullptr, nullptr};
-    float *staging_[2] = {nullptr, nullptr};
+    CPUBuffer *asyncOutputs_[Engine::ASYNC_SLOTS] = {};
+    float *staging_[Engine::ASYNC_SLOTS] = {};
     bool async_ = false;
     UpDownLayerBuilder::callback_t callback_;
 };

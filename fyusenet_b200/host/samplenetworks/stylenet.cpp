@@ -43,16 +43,15 @@ StyleNetBase::StyleNetBase(int kernel, int resBlocks, int width, int height, boo
 StyleNetBase::~StyleNetBase() {
     cleanup();
     delete inBuffer_;
-    delete inBuffers_[0];
-    delete inBuffers_[1];
+    for (CPUBuffer *b : inBuffers_) delete b;
 }
 
-// In asynchronous mode the upload layer reads input buffer (sequence & 1): the caller fills inputBuffer(slot) for
+// In asynchronous mode the upload layer reads input buffer (sequence % ASYNC_SLOTS): the caller fills inputBuffer(slot) for
 // the next sequence while the previous one is still being processed (the reference cycles two upload buffers the
 // same way, stylenet_base.cpp:110-155).
 NeuralNetwork::execstate StyleNetBase::forward() {
     if (async_ && upload_ && setup_) {
-        const int slot = (int)(engine_->nextSequenceNo() & 1);
+        const int slot = (int)(engine_->nextSequenceNo() % Engine::ASYNC_SLOTS);
         static_cast<gpu::UploadLayer *>(engine_->getLayers()["upload"])->setInputBuffer(inputBuffer(slot), 0);
     }
     return NeuralNetwork::forward();
@@ -61,7 +60,7 @@ NeuralNetwork::execstate StyleNetBase::forward() {
 StyleNetBase::CPUBuffer *StyleNetBase::inputBuffer(int slot) {
     if (!setup_) THROW_EXCEPTION_ARGS(FynException, "Please run setup() before setting input buffers");
     if (!upload_) THROW_EXCEPTION_ARGS(FynException, "Network was created without an upload layer");
-    if (slot < 0 || slot > 1) THROW_EXCEPTION_ARGS(FynException, "Illegal input buffer %d", slot);
+    if (slot < 0 || slot >= Engine::ASYNC_SLOTS) THROW_EXCEPTION_ARGS(FynException, "Illegal input buffer %d", slot);
     if (!inBuffers_[slot]) {
         cpu::CPUBufferShape shape(height_, width_, 3, 0, cpu::CPUBufferShape::FLOAT32, BufferSpec::order::GPU_SHALLOW, batch_);
         inBuffers_[slot] = shape.createBuffer(context());
@@ -146,7 +145,7 @@ StyleNetBase::CPUBuffer *StyleNetBase::inputBuffer() {
 }
 
 void StyleNetBase::setInputBuffer(const float *data) {
-    CPUBuffer *buf = async_ ? inputBuffer((int)(engine_->nextSequenceNo() & 1)) : inputBuffer();
+    CPUBuffer *buf = async_ ? inputBuffer((int)(engine_->nextSequenceNo() % Engine::ASYNC_SLOTS)) : inputBuffer();
     float *tgt = buf->map<float>();
     memcpy(tgt, data, buf->bytes());
     buf->unmap();

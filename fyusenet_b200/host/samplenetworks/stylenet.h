@@ -25,7 +25,7 @@ class StyleNetBase : public fyusion::fyusenet::NeuralNetwork {
     CPUBuffer *getOutputBuffer();
     // the pinned host buffer the upload layer reads from (created on demand and attached to the upload layer)
     CPUBuffer *inputBuffer();
-    // asynchronous operation keeps two input buffers; `slot` 0/1 (the buffer used by sequence s is slot s & 1)
+    // asynchronous operation keeps Engine::ASYNC_SLOTS input buffers; sequence s uploads from slot s % ASYNC_SLOTS
     CPUBuffer *inputBuffer(int slot);
     // device-tensor in / out (the reference's setInputTexture / getOutputTexture, stylenet_base.cpp:188-233)
     void setInputTexture(fyn_tensor *texture);
@@ -60,7 +60,7 @@ class StyleNetBase : public fyusion::fyusenet::NeuralNetwork {
     int sigmoidLayer_ = 0, downloadLayer_ = 0, lastLayer_ = 0;
     std::vector<float> wbData_;
     CPUBuffer *inBuffer_ = nullptr;
-    CPUBuffer *inBuffers_[2] = {nullptr, nullptr};
+    CPUBuffer *inBuffers_[fyusion::fyusenet::Engine::ASYNC_SLOTS] = {};
     fyn_tensor *inputTexture_ = nullptr;
 };
 

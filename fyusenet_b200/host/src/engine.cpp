@@ -28,7 +28,7 @@ void Engine::cleanup() {
         collectTimings(false);
         for (void *e : freeEvents_) fyn_event_destroy(context_.handle(), e);
         freeEvents_.clear();
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < ASYNC_SLOTS; i++) {
             if (uploadDone_[i]) fyn_event_destroy(context_.handle(), uploadDone_[i]);
             if (computeDone_[i]) fyn_event_destroy(context_.handle(), computeDone_[i]);
             if (copyDone_[i]) fyn_event_destroy(context_.handle(), copyDone_[i]);
@@ -91,8 +91,8 @@ Engine::execstate Engine::executeAsync(uint64_t sequence) {
     fyn_ctx *ctx = context_.handle();
     CudaContext *cc = context_.interface();
     void *sC = context_.stream(), *sU = cc->uploadStream(), *sD = cc->downloadStream();
-    const int slot = (int)(sequence & 1);
-    for (int i = 0; i < 2; i++) {
+    const int slot = (int)(sequence % ASYNC_SLOTS);
+    for (int i = 0; i < ASYNC_SLOTS; i++) {
         if (!uploadDone_[i]) {
             FYN_ABI_CALL(fyn_event_create(ctx, &uploadDone_[i]));
             FYN_ABI_CALL(fyn_event_create(ctx, &computeDone_[i]));
@@ -105,7 +105,7 @@ Engine::execstate Engine::executeAsync(uint64_t sequence) {
         if (!upload) upload = dynamic_cast<gpu::UploadLayer *>(it.second);
         if (auto *d = dynamic_cast<gpu::DownloadLayer *>(it.second)) download = d;
     }
-    // ---- upload: buffer `slot` is free once the layers of sequence-2 have consumed it
+    // ---- upload: buffer `slot` is free once the layers of sequence-ASYNC_SLOTS have consumed it
     if (upload) {
         if (slotUsed_[slot]) FYN_ABI_CALL(fyn_stream_wait_event(ctx, sU, computeDone_[slot]));
         gpu::TensorHandle t = upload->asyncUpload(sequence, slot, sU);

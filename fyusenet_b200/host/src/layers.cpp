@@ -288,7 +288,7 @@ std::vector<BufferSpec> UploadLayer::getRequiredInputBuffers() const {
 std::vector<BufferSpec> UploadLayer::getRequiredOutputBuffers() const {
     // RGB32F-style texture: packing == channel count, float32, no padding
     return {BufferSpec(0, width_, height_, outputChannels_, outputPadding_, order(), BufferSpec::FLOAT32, BufferSpec::GPU_DEST)
-                .packing(outputPadding_ == 0 ? outputChannels_ : 4).async(async_).multi(async_ ? 2 : 1)};
+                .packing(outputPadding_ == 0 ? outputChannels_ : 4).async(async_).multi(async_ ? Engine::ASYNC_SLOTS : 1)};
 }
 void UploadLayer::forward(uint64_t sequence) {
     if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
@@ -376,7 +376,7 @@ CPUBuffer *DownloadLayer::asyncCopy(uint64_t sequence, int slot, void *stream) {
 }
 
 void DownloadLayer::cleanup() {
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < Engine::ASYNC_SLOTS; i++) {
         if (staging_[i]) fyn_device_free(context_.handle(), staging_[i]);
         staging_[i] = nullptr;
         delete asyncOutputs_[i];
