@@ -51,6 +51,11 @@ def _check(rc):
         raise HostError(lib().fynhost_last_error().decode(errors="replace"))
 
 
+def async_slots() -> int:
+    """Buffers per pipeline interface == max sequences in flight of the asynchronous engine."""
+    return lib().fynhost_async_slots()
+
+
 def selftest():
     buf = C.create_string_buffer(16384)
     n = lib().fynhost_selftest(buf, len(buf))
@@ -110,7 +115,7 @@ class Network:
 
     # -- asynchronous (pipelined) operation ---------------------------------------------------
     def asynchronous(self):
-        """NeuralNetwork::asynchronous(): call before setup(); forward() then only enqueues (<= 2 sequences in flight)."""
+        """NeuralNetwork::asynchronous(): call before setup(); forward() then only enqueues (<= async_slots() sequences in flight)."""
         _check(lib().fynhost_net_asynchronous(self._h))
 
     def async_completed(self):
@@ -184,7 +189,7 @@ class StyleNet(Network):
         _check(lib().fynhost_stylenet_set_input_tensor(self._h, tensor._h))
 
     def input_buffer_slot(self, slot: int) -> np.ndarray:
-        """Pinned input buffer 0/1 of an asynchronous network (sequence s reads slot s & 1)."""
+        """Pinned input buffer `slot` of an asynchronous network (sequence s reads slot s % async_slots())."""
         n = C.c_size_t()
         p = lib().fynhost_stylenet_input_buffer_slot(self._h, int(slot), C.byref(n))
         if not p:

@@ -148,8 +148,8 @@ def test_resnet50_matches_oracle(batch, tmp_path):
 
 
 def test_stylenet_asynchronous_pipeline():
-    """NeuralNetwork::asynchronous(): forward() only enqueues (<= 2 sequences in flight), upload / layers / download
-    run on three streams with double buffering, downloads are delivered per sequence (unit_tests/asynctests.cpp runs
+    """NeuralNetwork::asynchronous(): forward() only enqueues (bounded number of sequences in flight), upload / layers /
+    download run on three streams with one buffer set per slot, downloads are delivered per sequence (unit_tests/asynctests.cpp runs
     the same scenario without a pass criterion; here every delivered frame must equal the synchronous result)."""
     import time
     weights = fo.stylenet_synthetic_weights(3)
@@ -168,20 +168,20 @@ def test_stylenet_asynchronous_pipeline():
     net.asynchronous()
     net.load_weights(weights)
     net.setup()
-    for k in range(2):
-        net.input_buffer_slot(k)[:] = imgs[k].reshape(-1)       # sequence s uploads from slot s & 1; sequences start at 1
-    nseq = 9
+    ns = hostapi.async_slots()
+    for k in range(ns):
+        net.input_buffer_slot(k)[:] = imgs[k % 2].reshape(-1)   # sequence s uploads from slot s % ns; sequences start at 1
+    nseq = 10
     for s in range(nseq):
         net.forward()
     net.finish()
     done, last_seq, data = net.async_completed()
     assert done == nseq and last_seq == nseq
     got = np.ctypeslib.as_array(data, shape=(h, w, 4)).copy()
-    np.testing.assert_array_equal(got, want[nseq & 1])         # slot of the last sequence
-    # the other buffer still holds sequence nseq-1
+    np.testing.assert_array_equal(got, want[(nseq % ns) % 2])   # frame held by the last sequence's slot
     net.forward()
     net.finish()
     done, last_seq, data = net.async_completed()
     assert (done, last_seq) == (nseq + 1, nseq + 1)
-    np.testing.assert_array_equal(np.ctypeslib.as_array(data, shape=(h, w, 4)), want[(nseq + 1) & 1])
+    np.testing.assert_array_equal(np.ctypeslib.as_array(data, shape=(h, w, 4)), want[((nseq + 1) % ns) % 2])
     net.destroy()
