@@ -190,8 +190,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    import fyn_oracle as fo
-    from fyusenet_b200 import capi, hostapi
+    from fyusenet_b200 import capi, hostapi, synthetic      # the product arm never imports oracle/
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -204,8 +203,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    weights = fo.stylenet_synthetic_weights(KSIZE)
-    img = fo.synthetic_image(HEIGHT, WIDTH, rank)
+    weights = synthetic.stylenet_weights(KSIZE)
+    img = synthetic.image(HEIGHT, WIDTH, rank)
 
     # ------------------------------------------------------------------ device-resident arm ("value")
     ctx = capi.Context(local_rank)

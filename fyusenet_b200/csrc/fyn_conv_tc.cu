@@ -62,7 +62,9 @@ constexpr int kEpiWarps = 8;                         // two warps per TMEM lane 
 constexpr int kLoaderWarps = 8;
 constexpr int kMmaWarp = kEpiWarps + kLoaderWarps;
 constexpr int kThreads = (kMmaWarp + 1) * 32;       // 544
-constexpr int kUnroll = 7;                           // (pixel, chunk) items per loader thread and row (all in flight)
+constexpr int kIssueWarps = 4;                       // mode 0: loader warps that issue the asynchronous row copies
+constexpr int kItems = 8;                            // mode 0: (pixel, chunk) items per issuing thread and row
+constexpr int kMaxDepth = 4;                         // mode 0: input rows in flight per CTA
 constexpr int kPix = 9;                              // pixels per loader thread and row in pixel-pair mode
 constexpr int kTileM = 128;
 constexpr int kMaxRows = 11;
@@ -80,7 +82,8 @@ struct TcArgs {
     const uint4 *wimg;
     const float *bias, *scale;   // [16 planes] float4 each, indexed by output plane
     uint32_t wbytes, idesc, b_lbo;
-    int nsteps, groupWarps;  // MMA steps per job; warps per loader group (1, 2 or 4)
+    int nsteps, groupWarps;  // MMA steps per job; warps per loader group (mode 1: 2, mode 0: all 8)
+    int depth;               // mode 0: rows in flight (asynchronous copies), <= nslots - nrows - rowAdvance + 1
     int rowAdvance;          // input rows the window moves per job (stride; 1 for fractional)
     int dyMin, nrows;        // window: input rows [rowAdvance*i + dyMin, +nrows)
     TcStep steps[kMaxSteps];
@@ -127,6 +130,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
 }
+// weights: one bulk copy (TMA unit, async proxy) that completes on an mbarrier
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// 8-byte asynchronous copy global -> shared; src_bytes = 0 zero-fills
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on the barrier once all cp.async issued so far by this thread have landed (does not change the pending count)
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// programmatic dependent launch: everything before grid_dep_wait() overlaps the tail of the previous kernel
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -193,12 +217,19 @@ __device__ __forceinline__ uint2 relu_h4(uint2 v) {
     return v;
 }
 
+__device__ __forceinline__ uint4 act_h8(uint4 v, const ActParams &a);
+
 __device__ __forceinline__ uint2 act_h4(uint2 v, const ActParams &a) {
     if (a.type == 1) return relu_h4(v);
     if (a.type == 0) return v;
     const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&v.x));
     const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&v.y));
     return make_uint2(pack_half2(fyn_act(f0.x, a), fyn_act(f0.y, a)), pack_half2(fyn_act(f1.x, a), fyn_act(f1.y, a)));
+}
+
+__device__ __forceinline__ uint4 act_h8(uint4 v, const ActParams &a) {
+    const uint2 l = act_h4(make_uint2(v.x, v.y), a), h = act_h4(make_uint2(v.z, v.w), a);
+    return make_uint4(l.x, l.y, h.x, h.y);
 }
 
 // position in the ring without divisions
@@ -233,11 +264,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     uint64_t *empty = bars + a.nslots;         // [nslots]
     uint64_t *tfull = bars + 2 * a.nslots;     // [2]
     uint64_t *tempty = tfull + 2;              // [2]
-    uint32_t *tmemBase = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint64_t *wbar = tempty + 2;               // weight image landed
+    uint64_t *landed = wbar + 1;               // [nslots] mode 0: raw row copies have landed (issuers -> finishers)
+    uint32_t *tmemBase = reinterpret_cast<uint32_t *>(landed + a.nslots);
 
     // warp index through a broadcast so the compiler treats the role dispatch (and everything derived from it) as
     // warp-uniform
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    [[maybe_unused]] const long long pK0 = PROF_T();
 
     // strip decode: blockIdx.x -> (image, column block, row segment)
     int bid = blockIdx.x;
@@ -255,31 +289,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     const int groupThreads = a.groupWarps * 32;
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nslots; s++) {
-            mbar_init(&full[s], groupThreads);   // every thread of the loading group arrives
+            mbar_init(&full[s], groupThreads);   // every thread of the loading / finishing group arrives
             mbar_init(&empty[s], 1);
+            mbar_init(&landed[s], kIssueWarps * 32);
         }
         mbar_init(&tfull[0], 1);
         mbar_init(&tfull[1], 1);
         mbar_init(&tempty[0], kEpiWarps * 32);
         mbar_init(&tempty[1], kEpiWarps * 32);
+        mbar_init(wbar, 1);
         fence_barrier_init();
+        // weight image -> shared memory: one bulk copy, the MMA warp waits for it before its first step
+        mbar_expect_tx(wbar, a.wbytes);
+        bulk_g2s(sW, a.wimg, a.wbytes, wbar);
     }
     if (warp == kMmaWarp) tmem_alloc(tmemBase, 128);
-    // weight image -> shared memory (all threads, 16-byte copies), visible to the async proxy
-    for (uint32_t i = threadIdx.x; i < a.wbytes / 16; i += kThreads) reinterpret_cast<uint4 *>(sW)[i] = __ldg(a.wimg + i);
     for (int i = threadIdx.x; i < 32; i += kThreads)
         sEpi[i] = __ldg(reinterpret_cast<const float4 *>(i < 16 ? a.bias : a.scale) + (i & 15));
-    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmemBase;
+    // Nothing above reads or writes a tensor: under programmatic dependent launch it overlaps the previous layer's
+    // tail.  Every role waits for the previous grid before it touches tensor memory (reads AND writes: the buffer
+    // pool may hand this layer an output buffer the previous layer still reads).
+    [[maybe_unused]] const long long pK1 = PROF_T();
+    grid_dep_launch();
+    grid_dep_wait();
+    [[maybe_unused]] const long long pK2 = PROF_T();
 
     if (warp >= kEpiWarps && warp < kMmaWarp) {
         // ===================== loaders: kLoaderWarps/groupWarps groups, group g takes rows g, g+G, ... ==========
         const int ngroups = kLoaderWarps / a.groupWarps;
-        const int grp = (warp - kEpiWarps) / a.groupWarps;
-        const int t = (threadIdx.x - kEpiWarps * 32) - grp * groupThreads;   // thread index inside the group
+        const int grp = (a.mode == 1) ? (warp - kEpiWarps) / a.groupWarps : 0;   // mode 0: every warp sees every row
+        const int t = (threadIdx.x - kEpiWarps * 32) - grp * groupThreads;       // mode 1: thread index inside the group
         const int P = a.inP;
         const int mirrorOff = a.nslots * a.slotBytes;             // slots < nrows-1 are also written behind the ring
         RingPos pos{0, 0};
@@ -287,62 +330,79 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         PROF_DECL(pLdWait);
         [[maybe_unused]] const long long pLdStart = PROF_T();
         if (a.mode == 0) {
-            // Per-thread item table (row independent): item = (pixel, chunk) -> two 8-byte plane loads and one
-            // 16-byte chunk store per version.  All loads of a row are issued before the first store.
-            const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems;
-            const int items = a.rowpx * a.nchunks, half = a.rowpx >> 1;
-            int gofs[kUnroll], sofs[kUnroll];
+            // Rows travel global -> shared as asynchronous 8-byte copies: a (pixel, chunk) item is two plane texels
+            // copied straight into the two halves of a 16-byte chunk (zero-fill when the second plane does not
+            // exist).  The first kIssueWarps warps only issue copies, as far ahead as free ring slots allow (a.depth
+            // rows beyond the window), so the loaders are bound by bandwidth, not by the latency of a row.  The other
+            // warps finish a row once it has landed: activation at fetch, the raw version for taps that bypass the
+            // activation, the mirror slots, the generic -> async proxy fence, and the hand-over to the MMA warp.
+            // (Threads with copies in flight never execute the proxy fence: it would wait for all of them.)
+            const int R = r1 - r0 + 1;
+            const uint32_t landOff = (a.nver == 2) ? (uint32_t)a.verBytes : 0u;   // raw texels land in version 1 if there are two
+            const int items = a.rowpx * a.nchunks;
+            if (warp < kEpiWarps + kIssueWarps) {
+                const int ti = threadIdx.x - kEpiWarps * 32;
+                const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems;
+                const int half = a.rowpx >> 1;
+                int gofs[kItems];
 #pragma unroll
-            for (int u = 0; u < kUnroll; u++) {
-                const int it = u * groupThreads + t;
-                gofs[u] = -1;
-                sofs[u] = it * 16;
-                if (it < items) {
-                    const int c = it / a.rowpx, px = it - c * a.rowpx;
-                    // stride 1: slot pixel = image pixel - (j0 - lead); stride 2: slot is [parity][pixel/2]
-                    const int gx = (a.ds == 1) ? j0 - a.x_lead + px : 2 * j0 - a.x_lead + 2 * (px % half) + (px / half);
-                    const int ix = min(max(gx + P, 0), a.in.texW - 1);
-                    // bit 0 flags "second plane present"; offsets are multiples of 4 elements
-                    gofs[u] = (int)((long long)(2 * c) * a.in.planeElems + (long long)ix * 4) | ((2 * c + 1 < a.nInPlanes) ? 1 : 0);
-                }
-            }
-            const int planeEl = (int)a.in.planeElems;
-            for (int r = r0 + grp; r <= r1; r += ngroups) {
-                [[maybe_unused]] const long long pt = PROF_T();
-                mbar_wait(&empty[pos.slot], (pos.fill & 1) ^ 1);
-                PROF_ADD(pLdWait, pt);
-                unsigned char *dst = sRing + (size_t)pos.slot * a.slotBytes;
-                const bool mirror = pos.slot < a.nrows - 1;
-                const int iy = min(max(r + P, 0), a.in.texH - 1);   // texture row, CLAMP_TO_EDGE
-                const __half *rowp = src + (long long)iy * a.in.texW * 4;
-                uint2 lo[kUnroll], hi[kUnroll];
-#pragma unroll
-                for (int u = 0; u < kUnroll; u++) {
-                    lo[u] = make_uint2(0u, 0u);
-                    hi[u] = make_uint2(0u, 0u);
-                    if (gofs[u] >= 0) {
-                        const __half *q = rowp + (gofs[u] & ~1);
-                        lo[u] = __ldg(reinterpret_cast<const uint2 *>(q));
-                        if (gofs[u] & 1) hi[u] = __ldg(reinterpret_cast<const uint2 *>(q + planeEl));
+                for (int u = 0; u < kItems; u++) {
+                    const int it = u * (kIssueWarps * 32) + ti;
+                    gofs[u] = -1;
+                    if (it < items) {
+                        const int c = it / a.rowpx, px = it - c * a.rowpx;
+                        // stride 1: slot pixel = image pixel - (j0 - lead); stride 2: slot is [parity][pixel/2]
+                        const int gx = (a.ds == 1) ? j0 - a.x_lead + px : 2 * j0 - a.x_lead + 2 * (px % half) + (px / half);
+                        const int ix = min(max(gx + P, 0), a.in.texW - 1);
+                        // bit 0 flags "second plane present"; offsets are multiples of 4 elements
+                        gofs[u] = (int)((long long)(2 * c) * a.in.planeElems + (long long)ix * 4) | ((2 * c + 1 < a.nInPlanes) ? 1 : 0);
                     }
                 }
+                const int planeEl = (int)a.in.planeElems;
+                const uint32_t ring32 = smem_u32(sRing) + landOff + (uint32_t)ti * 16u;
+                for (int r = 0; r < R; r++) {
+                    [[maybe_unused]] const long long pt = PROF_T();
+                    mbar_wait(&empty[pos.slot], (pos.fill & 1) ^ 1);
+                    PROF_ADD(pLdWait, pt);
+                    const int iy = min(max(r0 + r + P, 0), a.in.texH - 1);   // texture row, CLAMP_TO_EDGE
+                    const __half *rowp = src + (long long)iy * a.in.texW * 4;
+                    const uint32_t dst = ring32 + (uint32_t)pos.slot * (uint32_t)a.slotBytes;
 #pragma unroll
-                for (int u = 0; u < kUnroll; u++) {
-                    if (gofs[u] >= 0) {
-                        const uint4 raw = make_uint4(lo[u].x, lo[u].y, hi[u].x, hi[u].y);
-                        const uint2 l = act_h4(lo[u], a.act), h = act_h4(hi[u], a.act);
-                        const uint4 av = make_uint4(l.x, l.y, h.x, h.y);
-                        *reinterpret_cast<uint4 *>(dst + sofs[u]) = av;
-                        if (a.nver == 2) *reinterpret_cast<uint4 *>(dst + a.verBytes + sofs[u]) = raw;   // taps that bypass the activation
-                        if (mirror) {
-                            *reinterpret_cast<uint4 *>(dst + mirrorOff + sofs[u]) = av;
-                            if (a.nver == 2) *reinterpret_cast<uint4 *>(dst + mirrorOff + a.verBytes + sofs[u]) = raw;
+                    for (int u = 0; u < kItems; u++) {
+                        if (gofs[u] >= 0) {
+                            const __half *q = rowp + (gofs[u] & ~1);
+                            cp_async8(dst + u * (kIssueWarps * 32 * 16), q, 8u);
+                            cp_async8(dst + u * (kIssueWarps * 32 * 16) + 8u, (gofs[u] & 1) ? q + planeEl : q, (gofs[u] & 1) ? 8u : 0u);
                         }
                     }
+                    cp_async_arrive(&landed[pos.slot]);
+                    pos.advance(1, a.nslots);
                 }
-                fence_proxy_async();
-                mbar_arrive(&full[pos.slot]);
-                pos.advance(ngroups, a.nslots);
+            } else {
+                const int tf = threadIdx.x - (kEpiWarps + kIssueWarps) * 32;
+                const int nfin = (kLoaderWarps - kIssueWarps) * 32;
+                const bool hasAct = a.act.type != 0;
+                for (int r = 0; r < R; r++) {
+                    [[maybe_unused]] const long long pt = PROF_T();
+                    mbar_wait(&landed[pos.slot], pos.fill & 1);
+                    PROF_ADD(pLdWait, pt);
+                    unsigned char *slot = sRing + (size_t)pos.slot * a.slotBytes;
+                    const bool mirror = pos.slot < a.nrows - 1;
+                    if (hasAct || mirror) {
+                        for (int it = tf; it < items; it += nfin) {
+                            const uint4 raw = *reinterpret_cast<const uint4 *>(slot + landOff + it * 16);
+                            const uint4 av = act_h8(raw, a.act);
+                            if (hasAct || a.nver == 2) *reinterpret_cast<uint4 *>(slot + it * 16) = av;
+                            if (mirror) {
+                                *reinterpret_cast<uint4 *>(slot + mirrorOff + it * 16) = av;
+                                if (a.nver == 2) *reinterpret_cast<uint4 *>(slot + mirrorOff + a.verBytes + it * 16) = raw;
+                            }
+                        }
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(&full[pos.slot]);
+                    pos.advance(1, a.nslots);
+                }
             }
         } else {
             // pixel-pair mode: chunk = two adjacent pixels x 4 channels; chunks are split by parity so that GEMM rows
@@ -383,8 +443,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             }
         }
 #ifdef FYN_TC_PROFILE
-        if (blockIdx.x == 0 && t == 0)
-            printf("[tc prof] loader grp %d: total %lld waitEmpty %lld\n", grp, (long long)(clock64() - pLdStart), pLdWait);
+        if (blockIdx.x == 0 && (a.mode == 1 ? t == 0 : (threadIdx.x & 127) == 0))
+            printf("[tc prof] loader warp %d: total %lld wait %lld\n", warp, (long long)(clock64() - pLdStart), pLdWait);
 #endif
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
@@ -414,6 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                     mbar_wait(&full[w.slot], w.fill & 1);
                     w.advance(1, a.nslots);
                 }
+                if (q == 0) mbar_wait(wbar, 0);       // weight image
                 PROF_ADD(pWaitF, pt);
                 pt = PROF_T();
                 tc_fence_after();
@@ -456,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         const int groups = a.N >> 4;
         const bool single = a.opx == 1 && a.opy == 1;
         const bool resFast = a.hasRes && single && a.res.dtype == FYN_F16 && a.res.packing == 4 && !a.res.deep;
-        const int ppp = a.planesPerPhase, nphase = a.opx * a.opy;
+        const int ppp = a.planesPerPhase;
         // Per (group, plane-in-group) constants, hoisted out of the job loop: output element offset relative to the
         // job's first output texel (-1 = nothing to store) and the output plane (bias / scale / residual index).
         int poff[2][4], pidx[2][4];
@@ -464,15 +525,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         for (int gi = 0; gi < 2; gi++)
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int pn = (chalf + 2 * gi) * 4 + k;   // stacked plane index
-                const int phase = pn / ppp, p = pn - phase * ppp;
-                const int fy = phase / a.opx, fx = phase - fy * a.opx;
+                // stacked plane index -> (fy, plane, fx): the phases of one output row are adjacent columns so that a
+                // thread's texels of one plane are contiguous in memory (opx * 8 bytes)
+                const int pn = (chalf + 2 * gi) * 4 + k;
+                const int fx = pn % a.opx, tq = pn / a.opx;
+                const int fy = tq / ppp, p = tq - fy * ppp;
                 pidx[gi][k] = p;
-                poff[gi][k] = (phase < nphase && chalf + 2 * gi < groups && valid)
+                poff[gi][k] = (fy < a.opy && chalf + 2 * gi < groups && valid)
                                   ? (int)((long long)p * a.out.planeElems + (long long)fy * a.out.texW * 4 + fx * 4) : -1;
             }
         __half *outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((long long)a.outP * a.out.texW + a.outP + a.opx * jx) * 4;
         const long long outRow = (long long)a.out.texW * 4 * a.opy;   // elements per job row
+        // 16-byte stores need every job's first texel on a 16-byte boundary in every output row
+        const bool aligned16 = ((a.outP & 1) == 0 || (a.out.texW & 1) == 0) && ((a.outP + a.opx * jx) & 1) == 0 && (a.out.texW & 1) == 0 &&
+                               (a.out.planeElems & 7) == 0 && (a.out.imageElems & 7) == 0;
+        const int wide = (aligned16 && (a.opx == 2 || a.opx == 4)) ? a.opx : 1;
         const __half *resp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems + ((long long)a.resP * a.res.texW + a.resP + jx) * 4;
         const int resPlane = (int)a.res.planeElems;
         PROF_DECL(pEpWait);
@@ -506,8 +573,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             __half *orow = outp + (long long)i * outRow;
 #pragma unroll
             for (int gi = 0; gi < 2; gi++) {
+                uint2 o[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
+                    o[k] = make_uint2(0u, 0u);
                     if (poff[gi][k] >= 0) {
                         const int p = pidx[gi][k];
                         const float4 bi = sEpi[p], sc = sEpi[16 + p];
@@ -521,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                                 const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
                                 rs = make_float4(f0.x, f0.y, f1.x, f1.y);
                             } else {
-                                const int pn = (chalf + 2 * gi) * 4 + k, phase = pn / ppp, fy = phase / a.opx, fx = phase - fy * a.opx;
+                                const int pn = (chalf + 2 * gi) * 4 + k, fx = pn % a.opx, fy = (pn / a.opx) / ppp;
                                 rs = fyn_fetch(a.res, n, p, a.resP + a.opx * jx + fx, a.resP + a.opy * i + fy);
                             }
                             if (a.reluRes) rs = make_float4(fmaxf(rs.x, 0.f), fmaxf(rs.y, 0.f), fmaxf(rs.z, 0.f), fmaxf(rs.w, 0.f));
@@ -531,8 +600,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                             v.z += rs.z;
                             v.w += rs.w;
                         }
-                        *reinterpret_cast<uint2 *>(orow + poff[gi][k]) = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
+                        o[k] = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
                     }
+                }
+                // texels of adjacent phases are adjacent in memory: 16-byte stores where the row alignment allows
+                if (wide == 4) {
+                    if (poff[gi][0] >= 0) {
+                        *reinterpret_cast<uint4 *>(orow + poff[gi][0]) = make_uint4(o[0].x, o[0].y, o[1].x, o[1].y);
+                        *reinterpret_cast<uint4 *>(orow + poff[gi][2]) = make_uint4(o[2].x, o[2].y, o[3].x, o[3].y);
+                    }
+                } else if (wide == 2) {
+                    if (poff[gi][0] >= 0) *reinterpret_cast<uint4 *>(orow + poff[gi][0]) = make_uint4(o[0].x, o[0].y, o[1].x, o[1].y);
+                    if (poff[gi][2] >= 0) *reinterpret_cast<uint4 *>(orow + poff[gi][2]) = make_uint4(o[2].x, o[2].y, o[3].x, o[3].y);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (poff[gi][k] >= 0) *reinterpret_cast<uint2 *>(orow + poff[gi][k]) = o[k];
                 }
             }
         }
@@ -544,6 +627,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     tc_fence_before();
     __syncthreads();
     if (warp == kMmaWarp) tmem_dealloc(tmem, 128);
+#ifdef FYN_TC_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        printf("[tc prof] kernel: prologue %lld depwait %lld body %lld (cycles), grid %d\n", pK1 - pK0, pK2 - pK1, (long long)(clock64() - pK2), (int)gridDim.x);
+#endif
 }
 
 }  // namespace
@@ -571,7 +658,7 @@ struct Position {
 struct Geometry {
     int mode = 0, opx = 1, opy = 1, rowAdvance = 1, nver = 1, N = 16, Cq = 4, nchunks = 1, rowpx = 0, x_lead = 0, ds = 1;
     int dxMin = 0, dxMax = 0, dyMin = 0, dyMax = 0;
-    int nslots = 0, slotBytes = 0, verBytes = 0, nsteps = 0, groupWarps = 4;
+    int nslots = 0, slotBytes = 0, verBytes = 0, nsteps = 0, groupWarps = 4, depth = 1;
     size_t wbytes = 0, smem = 0;
     std::vector<Position> pos;
     bool ok = false;
@@ -704,12 +791,19 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb) {
         if (g.ds == 1) g.rowpx = ((kTileM + span + 1) + 3) & ~3;
         else g.rowpx = 2 * (((kTileM + span / 2 + 1) + 3) & ~3);
         g.verBytes = g.nchunks * g.rowpx * 16;
-        g.groupWarps = 4;
-        if (g.rowpx * g.nchunks > kUnroll * g.groupWarps * 32) return g;   // a row must fit one batch
+        g.groupWarps = kLoaderWarps - kIssueWarps;                         // finishing warps arrive on the full barriers
+        if (g.rowpx * g.nchunks > kItems * kIssueWarps * 32) return g;     // a row must fit one batch of copies
     }
     g.slotBytes = g.verBytes * g.nver;
-    const int ngroups = kLoaderWarps / g.groupWarps;
-    g.nslots = nrows + std::max(ngroups, 2) * g.rowAdvance + 1;
+    if (g.mode == 1) {
+        const int ngroups = kLoaderWarps / g.groupWarps;
+        g.nslots = nrows + std::max(ngroups, 2) * g.rowAdvance + 1;
+    } else {
+        // `depth` rows in flight beyond what the current job holds: nslots = nrows + rowAdvance - 1 + depth keeps the
+        // issue side from ever waiting for a slot whose release depends on a row it has not published yet
+        g.depth = kMaxDepth;
+        g.nslots = nrows + g.rowAdvance - 1 + g.depth;
+    }
     // steps: chunks of the same window row are paired in address order
     int nsteps = 0;
     for (int dy = g.dyMin; dy <= g.dyMax; dy++) {
@@ -721,7 +815,7 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb) {
     g.nsteps = nsteps;
     if (nsteps > kMaxSteps) return g;
     g.wbytes = (size_t)nsteps * 2 * g.N * 16;
-    g.smem = ((g.wbytes + 127) & ~(size_t)127) + (size_t)(g.nslots + nrows - 1) * g.slotBytes + 32 * 16 + (2 * g.nslots + 4) * 8 + 16;
+    g.smem = ((g.wbytes + 127) & ~(size_t)127) + (size_t)(g.nslots + nrows - 1) * g.slotBytes + 32 * 16 + (3 * g.nslots + 5) * 8 + 16;
     if (g.smem > 220 * 1024) return g;
     g.ok = true;
     return g;
@@ -759,6 +853,7 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     a.nslots = g.nslots;
     a.nsteps = g.nsteps;
     a.groupWarps = g.groupWarps;
+    a.depth = g.depth;
     a.slotBytes = g.slotBytes;
     a.idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);  // F32 accum, F16 x F16, K-major A/B
     a.b_lbo = (uint32_t)N * 16u;
@@ -784,7 +879,10 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
                         const int ci = c.sub * 8 + e;
                         if (ci < Ci) v = c.pos->w[((size_t)ph * g.Cq + o) * Ci + ci];
                     }
-                    img[(chunkIdx * N + (size_t)ph * g.Cq + o) * 8 + e] = __float2half_rn(v);
+                    // column order [fy][plane][fx][channel]: see the epilogue
+                    const int fy = ph / g.opx, fx = ph % g.opx, ppp = g.Cq / 4;
+                    const size_t col = (((size_t)fy * ppp + o / 4) * g.opx + fx) * 4 + (o & 3);
+                    img[(chunkIdx * N + col) * 8 + e] = __float2half_rn(v);
                 }
     };
     int s = 0;
@@ -879,7 +977,18 @@ int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn
     a.SH = std::max(4, (a.Hj + segs - 1) / segs);
     const int nseg = (a.Hj + a.SH - 1) / a.SH;
     const long long blocks = (long long)a.nxs * nseg * a.batch;
-    k_conv_tc<<<(unsigned)blocks, kThreads, plan->smemBytes, stream>>>(a);
+    // programmatic dependent launch: the prologue (barriers, TMEM, weight image) overlaps the previous kernel's tail
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = plan->smemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FYN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc, a));
     FYN_CHECK_LAUNCH(op->ctx);
     return FYN_OK;
 }

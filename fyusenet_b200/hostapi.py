@@ -209,21 +209,3 @@ class ResNet50(Network):
     def logits(self) -> np.ndarray:
         """[batch][1000]: the deep 18x14 download texture is channel order for 1x1 spatial (cpubuffer.cpp:131-142)."""
         return self.output().reshape(self.batch, -1)[:, :1000]
-
-
-def smoke_stylenet(ctx_device=0):
-    """Used by __graft_entry__.smoke(): StyleNet3x3 64x48 through the host engine vs the oracle."""
-    import fyn_oracle as fo
-    w = fo.stylenet_synthetic_weights(3)
-    img = fo.synthetic_image(48, 64, 1)
-    net = StyleNet(3, 64, 48, device=ctx_device)
-    net.load_weights(w)
-    net.setup()
-    net.set_input(img)
-    net.forward()
-    got = net.output_rgba()[0].copy()
-    ref = fo.stylenet_forward(w, img, 3, prec=fo.FP16_STORE)
-    err = float(np.abs(got[..., :3] - ref[..., :3]).max())
-    net.destroy()
-    assert err < 1e-2, f"StyleNet3x3 smoke mismatch {err}"
-    return err
