@@ -40,7 +40,9 @@
 // Pipelines: full/empty mbarriers per ring slot (loader <-> MMA), tmem_full/tmem_empty per accumulator
 // buffer (MMA <-> epilogue, two buffers so the epilogue of row y overlaps the MMAs of row y+1).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "fyn_internal.h"
@@ -62,10 +64,9 @@ constexpr int kEpiWarps = 8;                         // two warps per TMEM lane 
 constexpr int kLoaderWarps = 8;
 constexpr int kMmaWarp = kEpiWarps + kLoaderWarps;
 constexpr int kThreads = (kMmaWarp + 1) * 32;       // 544
-constexpr int kIssueWarps = 4;                       // mode 0: loader warps that issue the asynchronous row copies
-constexpr int kItems = 8;                            // mode 0: (pixel, chunk) items per issuing thread and row
-constexpr int kMaxDepth = 4;                         // mode 0: input rows in flight per CTA
-constexpr int kPix = 9;                              // pixels per loader thread and row in pixel-pair mode
+constexpr int kFinBatch = 4;                         // items a finishing lane keeps in flight
+constexpr int kMaxItems = 1152;                      // (pixel, chunk) items / pixels of one input row
+constexpr int kMaxStages = 8;                        // staged input rows in flight per CTA (as many as shared memory allows)
 constexpr int kTileM = 128;
 constexpr int kMaxRows = 11;
 
@@ -82,8 +83,11 @@ struct TcArgs {
     const uint4 *wimg;
     const float *bias, *scale;   // [16 planes] float4 each, indexed by output plane
     uint32_t wbytes, idesc, b_lbo;
-    int nsteps, groupWarps;  // MMA steps per job; warps per loader group (mode 1: 2, mode 0: all 8)
-    int depth;               // mode 0: rows in flight (asynchronous copies), <= nslots - nrows - rowAdvance + 1
+    int nsteps;              // MMA steps per job
+    int stageBytes;          // bytes of one staged input row (all planes)
+    int nstages;             // staged rows in flight (multiple of finGroups)
+    int finGroups;           // loader groups (2 or 4) working on different rows; nslots and nstages are multiples of it
+    int nitems;              // entries of the row item table
     int rowAdvance;          // input rows the window moves per job (stride; 1 for fractional)
     int dyMin, nrows;        // window: input rows [rowAdvance*i + dyMin, +nrows)
     TcStep steps[kMaxSteps];
@@ -139,14 +143,24 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// 8-byte asynchronous copy global -> shared; src_bytes = 0 zero-fills
-__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+// shared-memory accesses through 32-bit shared-window addresses (keeps the loaders' address arithmetic in 32 bits)
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
 }
-// arrive on the barrier once all cp.async issued so far by this thread have landed (does not change the pending count)
-__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+
 // programmatic dependent launch: everything before grid_dep_wait() overlaps the tail of the previous kernel
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -232,6 +246,24 @@ __device__ __forceinline__ uint4 act_h8(uint4 v, const ActParams &a) {
     return make_uint4(l.x, l.y, h.x, h.y);
 }
 
+// compile-time activation selection (ACT: 0 none, 1 ReLU, 2 leaky / clip through fp32): the kernel is instantiated per
+// activation and residual flavour so that every role's loop stays small (the instruction caches are 6 KB / 32 KB)
+template <int ACT>
+__device__ __forceinline__ uint4 act_h8_t(uint4 v, const ActParams &a) {
+    if (ACT == 0) return v;
+    if (ACT == 1) {
+        const uint2 l = relu_h4(make_uint2(v.x, v.y)), h = relu_h4(make_uint2(v.z, v.w));
+        return make_uint4(l.x, l.y, h.x, h.y);
+    }
+    return act_h8(v, a);
+}
+template <int ACT>
+__device__ __forceinline__ float4 act_f4_t(float4 v, const ActParams &a) {
+    if (ACT == 0) return v;
+    if (ACT == 1) return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    return fyn_act4(v, a);
+}
+
 // position in the ring without divisions
 struct RingPos {
     int slot, fill;
@@ -254,19 +286,25 @@ struct RingPos {
 // 128 x opx output pixels of opy output rows, reading a window of `nrows` input rows that only moves forward, so
 // the ring of row slots is a FIFO.  The first nrows-1 slots are mirrored behind the ring so that every window is
 // contiguous in shared memory and the A descriptor of a step is (window base + constant).
+// MODE: 0 plane-pair chunks, 1 pixel-pair chunks.  ACT: see act_h8_t.  RES: 0 no residual, 1 fp16 shallow residual of a
+// single-phase layer (prefetched), 2 any other residual tensor (generic fetch).
+template <int MODE, int ACT, int RES>
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sW = smem;
     unsigned char *sRing = smem + ((a.wbytes + 127) & ~127u);
-    float4 *sEpi = reinterpret_cast<float4 *>(sRing + (size_t)(a.nslots + a.nrows - 1) * a.slotBytes);   // [16] bias, [16] scale
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sEpi + 32);
-    uint64_t *full = bars;                     // [nslots]
-    uint64_t *empty = bars + a.nslots;         // [nslots]
+    unsigned char *sStage = sRing + (size_t)(a.nslots + a.nrows - 1) * a.slotBytes;                       // [nstages] raw input rows
+    float4 *sEpi = reinterpret_cast<float4 *>(sStage + (size_t)a.nstages * a.stageBytes);                 // [16] bias, [16] scale
+    int2 *sTab = reinterpret_cast<int2 *>(sEpi + 32);                                                     // [nitems] row item table
+    uint64_t *sZero = reinterpret_cast<uint64_t *>(sTab + a.nitems);                                      // 16 zero bytes (missing second plane)
+    uint64_t *bars = sZero + 2;
+    uint64_t *full = bars;                     // [nslots] row is ready for the MMA warp        (finishers -> MMA)
+    uint64_t *empty = bars + a.nslots;         // [nslots] all MMAs reading the row have retired (MMA -> finishers)
     uint64_t *tfull = bars + 2 * a.nslots;     // [2]
     uint64_t *tempty = tfull + 2;              // [2]
     uint64_t *wbar = tempty + 2;               // weight image landed
-    uint64_t *landed = wbar + 1;               // [nslots] mode 0: raw row copies have landed (issuers -> finishers)
-    uint32_t *tmemBase = reinterpret_cast<uint32_t *>(landed + a.nslots);
+    uint64_t *landed = wbar + 1;               // [nstages] raw row copy has landed            (bulk copies -> loaders)
+    uint32_t *tmemBase = reinterpret_cast<uint32_t *>(landed + a.nstages);
 
     // warp index through a broadcast so the compiler treats the role dispatch (and everything derived from it) as
     // warp-uniform
@@ -286,13 +324,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     const int r0 = a.rowAdvance * ja + a.dyMin;               // first / last input row of the strip (unclamped)
     const int r1 = a.rowAdvance * (jb - 1) + a.dyMin + a.nrows - 1;
 
-    const int groupThreads = a.groupWarps * 32;
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nslots; s++) {
-            mbar_init(&full[s], groupThreads);   // every thread of the loading / finishing group arrives
+            mbar_init(&full[s], 1);              // the leader of the loader group that finished the row
             mbar_init(&empty[s], 1);
-            mbar_init(&landed[s], kIssueWarps * 32);
         }
+        for (int s = 0; s < a.nstages; s++) mbar_init(&landed[s], 1);   // one arrive.expect_tx + the bytes of the bulk copies
         mbar_init(&tfull[0], 1);
         mbar_init(&tfull[1], 1);
         mbar_init(&tempty[0], kEpiWarps * 32);
@@ -306,6 +343,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     if (warp == kMmaWarp) tmem_alloc(tmemBase, 128);
     for (int i = threadIdx.x; i < 32; i += kThreads)
         sEpi[i] = __ldg(reinterpret_cast<const float4 *>(i < 16 ? a.bias : a.scale) + (i & 15));
+    // Row geometry (independent of the row): the texel run [xa, xz] of a texture row that this strip reads, and per
+    // item the byte offset inside the staged row and inside the ring slot.
+    const int esize = (a.in.dtype == FYN_F16) ? 2 : 4, bpp = a.in.packing * esize;   // bytes per texel
+    const int gx0 = (MODE == 1) ? 4 * j0 - a.x_lead : ((a.ds == 1) ? j0 - a.x_lead : 2 * j0 - a.x_lead);
+    const int npx = (MODE == 1) ? 2 * a.rowpx : a.rowpx;
+    const int xa = min(max(gx0 + a.inP, 0), a.in.texW - 1), xz = min(max(gx0 + a.inP + npx - 1, 0), a.in.texW - 1);
+    const int ncopy = (MODE == 1) ? 1 : a.nInPlanes;                      // bulk copies per row
+    const int stagePlane = a.stageBytes / ncopy;                           // staged bytes per plane (multiple of 16)
+    if (threadIdx.x < 2) sZero[threadIdx.x] = 0ull;
+    for (int it = threadIdx.x; it < a.nitems; it += kThreads) {
+        int2 e;
+        if (MODE == 0) {
+            // item = (slot pixel, chunk): x = staged offset of the chunk's first plane texel | "second plane present"
+            const int c = it / a.rowpx, px = it - c * a.rowpx, half = a.rowpx >> 1;
+            // stride 1: slot pixel = image pixel - (j0 - lead); stride 2: slot is [parity][pixel/2]
+            const int gx = (a.ds == 1) ? gx0 + px : gx0 + 2 * (px % half) + (px / half);
+            const int ix = min(max(gx + a.inP, 0), a.in.texW - 1);      // CLAMP_TO_EDGE
+            e.x = (2 * c * stagePlane + (ix - xa) * 8) | ((2 * c + 1 < a.nInPlanes) ? 1 : 0);
+            e.y = it * 16;
+        } else {
+            // item = pixel; chunk = two adjacent pixels x 4 channels, chunks split by parity so that GEMM rows (4 pixels
+            // = 2 chunks apart) are 16 bytes apart: slot = [even chunks][odd chunks]
+            const int cidx = it >> 1;
+            e.x = (min(max(gx0 + it + a.inP, 0), a.in.texW - 1) - xa) * bpp;
+            e.y = (cidx & 1) * (a.rowpx >> 1) * 16 + (cidx >> 1) * 16 + (it & 1) * 8;
+        }
+        sTab[it] = e;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -319,132 +384,158 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     [[maybe_unused]] const long long pK2 = PROF_T();
 
     if (warp >= kEpiWarps && warp < kMmaWarp) {
-        // ===================== loaders: kLoaderWarps/groupWarps groups, group g takes rows g, g+G, ... ==========
-        const int ngroups = kLoaderWarps / a.groupWarps;
-        const int grp = (a.mode == 1) ? (warp - kEpiWarps) / a.groupWarps : 0;   // mode 0: every warp sees every row
-        const int t = (threadIdx.x - kEpiWarps * 32) - grp * groupThreads;       // mode 1: thread index inside the group
+        // ===================== loaders =====================
+        // Input rows travel global -> shared as bulk copies (TMA unit, no registers, no load/store-unit traffic): per
+        // row one copy per 4-channel plane of the contiguous texel run the strip needs.  The loader warps then turn a
+        // staged row into the UMMA operand layout: clamp-to-edge addressing (base/buffermanager.cpp:657-670),
+        // activation at fetch (shaders/activation.inc), fp32 -> fp16, the transpose of two 4-channel planes into one
+        // 8-channel chunk, the raw version for taps that bypass the activation and the mirror slots -- and publish
+        // the row to the MMA warp.
+        // The warps form finGroups groups; group g owns rows g, g + G, ..., the stages s = g (mod G) and the ring slots
+        // s = g (mod G), so every barrier is waited on by one group in program order (parity waits stay one phase
+        // apart) while G rows are being finished concurrently and nstages rows are in flight.
         const int P = a.inP;
-        const int mirrorOff = a.nslots * a.slotBytes;             // slots < nrows-1 are also written behind the ring
-        RingPos pos{0, 0};
-        pos.advance(grp, a.nslots);
-        PROF_DECL(pLdWait);
+        const int G = a.finGroups, groupThreads = (kLoaderWarps * 32) / G;
+        const int tl = threadIdx.x - kEpiWarps * 32, g = tl / groupThreads, tg = tl - g * groupThreads;
+        const bool leader = tg < 32;                                  // first warp of the group issues the copies
+        const int runBytes = (xz - xa + 1) * bpp;
+        const unsigned long long base = reinterpret_cast<unsigned long long>(a.in.ptr) + (unsigned long long)n * a.in.imageElems * esize;
+        const unsigned long long planeBytes = (unsigned long long)a.in.planeElems * esize;
+        const int R = r1 - r0 + 1;
+        const int mirrorOff = a.nslots * a.slotBytes;                 // slots < nrows-1 are also written behind the ring
+        const uint32_t base15 = (uint32_t)(base & 15ull), plane15 = (uint32_t)(planeBytes & 15ull);
+        const int pk = a.in.packing;
+        const bool f16in = a.in.dtype == FYN_F16;
+        const bool fastIn = !f16in && pk == 3;
+        const uint32_t zeroA = smem_u32(sZero);
+        PROF_DECL(pLdWait); PROF_DECL(pFinProc); PROF_DECL(pFinFence); PROF_DECL(pFinWaitE);
         [[maybe_unused]] const long long pLdStart = PROF_T();
-        if (a.mode == 0) {
-            // Rows travel global -> shared as asynchronous 8-byte copies: a (pixel, chunk) item is two plane texels
-            // copied straight into the two halves of a 16-byte chunk (zero-fill when the second plane does not
-            // exist).  The first kIssueWarps warps only issue copies, as far ahead as free ring slots allow (a.depth
-            // rows beyond the window), so the loaders are bound by bandwidth, not by the latency of a row.  The other
-            // warps finish a row once it has landed: activation at fetch, the raw version for taps that bypass the
-            // activation, the mirror slots, the generic -> async proxy fence, and the hand-over to the MMA warp.
-            // (Threads with copies in flight never execute the proxy fence: it would wait for all of them.)
-            const int R = r1 - r0 + 1;
-            const uint32_t landOff = (a.nver == 2) ? (uint32_t)a.verBytes : 0u;   // raw texels land in version 1 if there are two
-            const int items = a.rowpx * a.nchunks;
-            if (warp < kEpiWarps + kIssueWarps) {
-                const int ti = threadIdx.x - kEpiWarps * 32;
-                const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems;
-                const int half = a.rowpx >> 1;
-                int gofs[kItems];
+        // lane q of the leader copies plane q of row r into stage r % nstages
+        auto issue_row = [&](int r) {
+            const int st = r % a.nstages;
+            const int iy = min(max(r0 + r + P, 0), a.in.texH - 1);   // texture row, CLAMP_TO_EDGE
+            unsigned long long src = base + (unsigned long long)tg * planeBytes + ((unsigned long long)iy * a.in.texW + xa) * bpp;
+            const uint32_t sh = (uint32_t)(src & 15ull);              // copies start on a 16-byte boundary
+            const uint32_t bytes = (tg < ncopy) ? ((sh + runBytes + 15u) & ~15u) : 0u;
+            const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+            if (tg == 0) mbar_expect_tx(&landed[st], total);
+            __syncwarp();
+            if (tg < ncopy) bulk_g2s(sStage + (size_t)st * a.stageBytes + (size_t)tg * stagePlane, reinterpret_cast<const void *>(src - sh), bytes, &landed[st]);
+        };
+        if (leader)
+            for (int r = g; r < R && r < a.nstages; r += G) issue_row(r);
+        for (int r = g; r < R; r += G) {
+            const int st = r % a.nstages, use = r / a.nstages;
+            const int slotIdx = r % a.nslots, fill = r / a.nslots;
+            const int iy = min(max(r0 + r + P, 0), a.in.texH - 1);
+            // a staged plane starts at (address of its run) & 15: in mode 0 that is 0 or 8 bytes, alternating with
+            // the plane when a plane holds an odd number of texels
+            const uint32_t sh0 = (base15 + (uint32_t)((((unsigned long long)iy * a.in.texW + xa) * (unsigned long long)bpp) & 15ull)) & 15u;
+            const uint32_t sh1 = (sh0 + plane15) & 15u;
+            const uint32_t hiDelta = (uint32_t)stagePlane + sh1 - sh0;   // first plane texel -> second plane texel of a chunk
+            [[maybe_unused]] long long pt = PROF_T();
+            mbar_wait(&landed[st], use & 1);
+            PROF_ADD(pLdWait, pt);
+            pt = PROF_T();
+            mbar_wait(&empty[slotIdx], (fill & 1) ^ 1);
+            PROF_ADD(pFinWaitE, pt);
+            pt = PROF_T();
+            const uint32_t stgA = smem_u32(sStage) + (uint32_t)st * (uint32_t)a.stageBytes + sh0;
+            const uint32_t slotA = smem_u32(sRing) + (uint32_t)slotIdx * (uint32_t)a.slotBytes;
+            const bool mirror = slotIdx < a.nrows - 1;
+            // The body is written without data-dependent branches (the loaders are bound by instruction latency, not
+            // by bandwidth): whole units of groupThreads items in batches of kFinBatch, then single units, then the
+            // guarded partial unit.  `nv2` / `mir` are uniform per row and select one of four straight-line variants.
+            auto run_row = [&](auto nv2, auto mir) {
+                constexpr bool NV2 = decltype(nv2)::value, MIR = decltype(mir)::value;
+                auto batch = [&](auto nb, int it0, bool guard) {
+                    constexpr int B = decltype(nb)::value;
+                    int2 e[B];
+                    bool ok[B];
 #pragma unroll
-                for (int u = 0; u < kItems; u++) {
-                    const int it = u * (kIssueWarps * 32) + ti;
-                    gofs[u] = -1;
-                    if (it < items) {
-                        const int c = it / a.rowpx, px = it - c * a.rowpx;
-                        // stride 1: slot pixel = image pixel - (j0 - lead); stride 2: slot is [parity][pixel/2]
-                        const int gx = (a.ds == 1) ? j0 - a.x_lead + px : 2 * j0 - a.x_lead + 2 * (px % half) + (px / half);
-                        const int ix = min(max(gx + P, 0), a.in.texW - 1);
-                        // bit 0 flags "second plane present"; offsets are multiples of 4 elements
-                        gofs[u] = (int)((long long)(2 * c) * a.in.planeElems + (long long)ix * 4) | ((2 * c + 1 < a.nInPlanes) ? 1 : 0);
+                    for (int u = 0; u < B; u++) {
+                        const int it = it0 + groupThreads * u;
+                        ok[u] = !guard || it < a.nitems;
+                        e[u] = ok[u] ? sTab[it] : make_int2(0, 0);
                     }
-                }
-                const int planeEl = (int)a.in.planeElems;
-                const uint32_t ring32 = smem_u32(sRing) + landOff + (uint32_t)ti * 16u;
-                for (int r = 0; r < R; r++) {
-                    [[maybe_unused]] const long long pt = PROF_T();
-                    mbar_wait(&empty[pos.slot], (pos.fill & 1) ^ 1);
-                    PROF_ADD(pLdWait, pt);
-                    const int iy = min(max(r0 + r + P, 0), a.in.texH - 1);   // texture row, CLAMP_TO_EDGE
-                    const __half *rowp = src + (long long)iy * a.in.texW * 4;
-                    const uint32_t dst = ring32 + (uint32_t)pos.slot * (uint32_t)a.slotBytes;
+                    if (MODE == 0) {
+                        uint2 lo[B], hi[B];
 #pragma unroll
-                    for (int u = 0; u < kItems; u++) {
-                        if (gofs[u] >= 0) {
-                            const __half *q = rowp + (gofs[u] & ~1);
-                            cp_async8(dst + u * (kIssueWarps * 32 * 16), q, 8u);
-                            cp_async8(dst + u * (kIssueWarps * 32 * 16) + 8u, (gofs[u] & 1) ? q + planeEl : q, (gofs[u] & 1) ? 8u : 0u);
+                        for (int u = 0; u < B; u++) {
+                            const uint32_t la = stgA + (uint32_t)(e[u].x & ~1);
+                            lo[u] = lds64(la);
+                            hi[u] = lds64((e[u].x & 1) ? la + hiDelta : zeroA);   // select, not a branch
                         }
-                    }
-                    cp_async_arrive(&landed[pos.slot]);
-                    pos.advance(1, a.nslots);
-                }
-            } else {
-                const int tf = threadIdx.x - (kEpiWarps + kIssueWarps) * 32;
-                const int nfin = (kLoaderWarps - kIssueWarps) * 32;
-                const bool hasAct = a.act.type != 0;
-                for (int r = 0; r < R; r++) {
-                    [[maybe_unused]] const long long pt = PROF_T();
-                    mbar_wait(&landed[pos.slot], pos.fill & 1);
-                    PROF_ADD(pLdWait, pt);
-                    unsigned char *slot = sRing + (size_t)pos.slot * a.slotBytes;
-                    const bool mirror = pos.slot < a.nrows - 1;
-                    if (hasAct || mirror) {
-                        for (int it = tf; it < items; it += nfin) {
-                            const uint4 raw = *reinterpret_cast<const uint4 *>(slot + landOff + it * 16);
-                            const uint4 av = act_h8(raw, a.act);
-                            if (hasAct || a.nver == 2) *reinterpret_cast<uint4 *>(slot + it * 16) = av;
-                            if (mirror) {
-                                *reinterpret_cast<uint4 *>(slot + mirrorOff + it * 16) = av;
-                                if (a.nver == 2) *reinterpret_cast<uint4 *>(slot + mirrorOff + a.verBytes + it * 16) = raw;
+#pragma unroll
+                        for (int u = 0; u < B; u++) {
+                            if (ok[u]) {
+                                const uint4 raw = make_uint4(lo[u].x, lo[u].y, hi[u].x, hi[u].y);
+                                const uint4 av = act_h8_t<ACT>(raw, a.act);
+                                const uint32_t d = slotA + (uint32_t)e[u].y;
+                                sts128(d, av);
+                                if (NV2) sts128(d + (uint32_t)a.verBytes, raw);          // taps that bypass the activation
+                                if (MIR) {
+                                    sts128(d + (uint32_t)mirrorOff, av);
+                                    if (NV2) sts128(d + (uint32_t)(mirrorOff + a.verBytes), raw);
+                                }
+                            }
+                        }
+                    } else {
+                        float4 v[B];
+#pragma unroll
+                        for (int u = 0; u < B; u++) {
+                            const uint32_t q = stgA + (uint32_t)e[u].x;
+                            if (fastIn) {                                   // fp32 RGB upload texture
+                                v[u] = make_float4(lds32f(q), lds32f(q + 4), lds32f(q + 8), 0.f);
+                            } else if (f16in) {
+                                const __half *hq = reinterpret_cast<const __half *>(__cvta_shared_to_generic(q));
+                                v[u] = make_float4(__half2float(hq[0]), pk > 1 ? __half2float(hq[1]) : 0.f, pk > 2 ? __half2float(hq[2]) : 0.f,
+                                                   pk > 3 ? __half2float(hq[3]) : 0.f);
+                            } else {
+                                v[u] = make_float4(lds32f(q), pk > 1 ? lds32f(q + 4) : 0.f, pk > 2 ? lds32f(q + 8) : 0.f, pk > 3 ? lds32f(q + 12) : 0.f);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < B; u++) {
+                            if (ok[u]) {
+                                const float4 w = act_f4_t<ACT>(v[u], a.act);
+                                const uint2 h = make_uint2(pack_half2(w.x, w.y), pack_half2(w.z, w.w));
+                                sts64(slotA + (uint32_t)e[u].y, h);
+                                if (MIR) sts64(slotA + (uint32_t)(mirrorOff + e[u].y), h);
                             }
                         }
                     }
-                    fence_proxy_async();
-                    mbar_arrive(&full[pos.slot]);
-                    pos.advance(1, a.nslots);
-                }
+                };
+                const int unitsEnd = (a.nitems / groupThreads) * groupThreads;          // items in whole units
+                int it0 = tg;
+                for (; it0 + (kFinBatch - 1) * groupThreads < unitsEnd; it0 += kFinBatch * groupThreads) batch(std::integral_constant<int, kFinBatch>{}, it0, false);
+                for (; it0 + groupThreads < unitsEnd; it0 += 2 * groupThreads) batch(std::integral_constant<int, 2>{}, it0, false);
+                for (; it0 < unitsEnd; it0 += groupThreads) batch(std::integral_constant<int, 1>{}, it0, false);
+                if (unitsEnd < a.nitems) batch(std::integral_constant<int, 1>{}, it0, true);
+            };
+            if (a.nver == 2) {
+                if (mirror) run_row(std::true_type{}, std::true_type{});
+                else run_row(std::true_type{}, std::false_type{});
+            } else {
+                if (mirror) run_row(std::false_type{}, std::true_type{});
+                else run_row(std::false_type{}, std::false_type{});
             }
-        } else {
-            // pixel-pair mode: chunk = two adjacent pixels x 4 channels; chunks are split by parity so that GEMM rows
-            // (4 pixels = 2 chunks apart) are 16 bytes apart: slot = [even chunks][odd chunks].  Thread item = pixel.
-            const int halfBytes = (a.rowpx >> 1) * 16, npx = 2 * a.rowpx;
-            int xofs[kPix], sofs[kPix];
-#pragma unroll
-            for (int u = 0; u < kPix; u++) {
-                const int px = u * groupThreads + t;
-                xofs[u] = (px < npx) ? min(max(4 * j0 - a.x_lead + px + P, 0), a.in.texW - 1) * a.in.packing : -1;
-                const int cidx = px >> 1;
-                sofs[u] = (cidx & 1) * halfBytes + (cidx >> 1) * 16 + (px & 1) * 8;
+            PROF_ADD(pFinProc, pt);
+            pt = PROF_T();
+            // every thread orders its stores (generic proxy) before the tensor core's reads (async proxy); after the
+            // group barrier the leader publishes the row and refills the stage, which nobody reads any more
+            fence_proxy_async();
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(groupThreads) : "memory");
+            if (leader) {
+                if (tg == 0) mbar_arrive(&full[slotIdx]);
+                if (r + a.nstages < R) issue_row(r + a.nstages);
             }
-            for (int r = r0 + grp; r <= r1; r += ngroups) {
-                [[maybe_unused]] const long long pt = PROF_T();
-                mbar_wait(&empty[pos.slot], (pos.fill & 1) ^ 1);
-                PROF_ADD(pLdWait, pt);
-                unsigned char *dst = sRing + (size_t)pos.slot * a.slotBytes;
-                const bool mirror = pos.slot < a.nrows - 1;
-                const int iy = min(max(r + P, 0), a.in.texH - 1);
-                const long long rowBase = (long long)n * a.in.imageElems + (long long)iy * a.in.texW * a.in.packing;
-                float4 v[kPix];
-#pragma unroll
-                for (int u = 0; u < kPix; u++)
-                    if (xofs[u] >= 0) v[u] = fyn_load_texel(a.in, rowBase + xofs[u]);
-#pragma unroll
-                for (int u = 0; u < kPix; u++) {
-                    if (xofs[u] >= 0) {
-                        const float4 w = fyn_act4(v[u], a.act);
-                        const uint2 h = make_uint2(pack_half2(w.x, w.y), pack_half2(w.z, w.w));
-                        *reinterpret_cast<uint2 *>(dst + sofs[u]) = h;
-                        if (mirror) *reinterpret_cast<uint2 *>(dst + mirrorOff + sofs[u]) = h;
-                    }
-                }
-                fence_proxy_async();
-                mbar_arrive(&full[pos.slot]);
-                pos.advance(ngroups, a.nslots);
-            }
+            PROF_ADD(pFinFence, pt);
         }
 #ifdef FYN_TC_PROFILE
-        if (blockIdx.x == 0 && (a.mode == 1 ? t == 0 : (threadIdx.x & 127) == 0))
-            printf("[tc prof] loader warp %d: total %lld wait %lld\n", warp, (long long)(clock64() - pLdStart), pLdWait);
+        if (blockIdx.x == 0 && tg == 0)
+            printf("[tc prof] loader group %d: total %lld waitLanded %lld waitEmpty %lld process %lld publish %lld\n", g, (long long)(clock64() - pLdStart),
+                   pLdWait, pFinWaitE, pFinProc, pFinFence);
 #endif
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
@@ -515,8 +606,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         const int jx = j0 + m;
         const bool valid = jx < a.Wj;
         const int groups = a.N >> 4;
-        const bool single = a.opx == 1 && a.opy == 1;
-        const bool resFast = a.hasRes && single && a.res.dtype == FYN_F16 && a.res.packing == 4 && !a.res.deep;
         const int ppp = a.planesPerPhase;
         // Per (group, plane-in-group) constants, hoisted out of the job loop: output element offset relative to the
         // job's first output texel (-1 = nothing to store) and the output plane (bias / scale / residual index).
@@ -549,7 +638,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             const int i = ja + q;                    // job row
             // residual texels are fetched before waiting for the accumulator so their latency hides behind the MMAs
             uint2 rres[2][4];
-            if (resFast) {
+            if (RES == 1) {
                 const __half *rp = resp + (long long)i * a.res.texW * 4;
 #pragma unroll
                 for (int gi = 0; gi < 2; gi++)
@@ -582,9 +671,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                         const float4 bi = sEpi[p], sc = sEpi[16 + p];
                         float4 v = make_float4(fmaf(__uint_as_float(acc[gi][4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[gi][4 * k + 1]), sc.y, bi.y),
                                                fmaf(__uint_as_float(acc[gi][4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[gi][4 * k + 3]), sc.w, bi.w));
-                        if (a.hasRes) {
+                        if (RES != 0) {
                             float4 rs;
-                            if (resFast) {
+                            if (RES == 1) {
                                 const uint2 raw = rres[gi][k];
                                 const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
                                 const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
@@ -658,7 +747,7 @@ struct Position {
 struct Geometry {
     int mode = 0, opx = 1, opy = 1, rowAdvance = 1, nver = 1, N = 16, Cq = 4, nchunks = 1, rowpx = 0, x_lead = 0, ds = 1;
     int dxMin = 0, dxMax = 0, dyMin = 0, dyMax = 0;
-    int nslots = 0, slotBytes = 0, verBytes = 0, nsteps = 0, groupWarps = 4, depth = 1;
+    int nslots = 0, slotBytes = 0, verBytes = 0, nsteps = 0, stageBytes = 0, nstages = 0, nitems = 0, finGroups = 2;
     size_t wbytes = 0, smem = 0;
     std::vector<Position> pos;
     bool ok = false;
@@ -783,27 +872,20 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb) {
         g.x_lead = -2 * g.dxMin;                      // pixels (dxMin is even-aligned below)
         if (g.dxMin & 1) return g;
         g.verBytes = g.rowpx * 16;
-        g.groupWarps = 2;
-        if (2 * g.rowpx > kPix * g.groupWarps * 32) return g;
+        if (2 * g.rowpx > kMaxItems) return g;
+        g.nitems = 2 * g.rowpx;
+        g.stageBytes = (2 * g.rowpx * 16 + 16 + 15) & ~15;             // raw texels: up to 16 bytes each (fp32 RGBA)
     } else {
         g.nchunks = ((Ci + 3) / 4 + 1) / 2;
         g.x_lead = -g.dxMin;
         if (g.ds == 1) g.rowpx = ((kTileM + span + 1) + 3) & ~3;
         else g.rowpx = 2 * (((kTileM + span / 2 + 1) + 3) & ~3);
         g.verBytes = g.nchunks * g.rowpx * 16;
-        g.groupWarps = kLoaderWarps - kIssueWarps;                         // finishing warps arrive on the full barriers
-        if (g.rowpx * g.nchunks > kItems * kIssueWarps * 32) return g;     // a row must fit one batch of copies
+        if (g.rowpx * g.nchunks > kMaxItems || (Ci + 3) / 4 > 32) return g;   // one bulk copy per plane and lane
+        g.nitems = g.rowpx * g.nchunks;
+        g.stageBytes = ((Ci + 3) / 4) * ((g.rowpx * 8 + 16 + 15) & ~15);   // per plane: the texel run + alignment slack
     }
     g.slotBytes = g.verBytes * g.nver;
-    if (g.mode == 1) {
-        const int ngroups = kLoaderWarps / g.groupWarps;
-        g.nslots = nrows + std::max(ngroups, 2) * g.rowAdvance + 1;
-    } else {
-        // `depth` rows in flight beyond what the current job holds: nslots = nrows + rowAdvance - 1 + depth keeps the
-        // issue side from ever waiting for a slot whose release depends on a row it has not published yet
-        g.depth = kMaxDepth;
-        g.nslots = nrows + g.rowAdvance - 1 + g.depth;
-    }
     // steps: chunks of the same window row are paired in address order
     int nsteps = 0;
     for (int dy = g.dyMin; dy <= g.dyMax; dy++) {
@@ -815,10 +897,58 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb) {
     g.nsteps = nsteps;
     if (nsteps > kMaxSteps) return g;
     g.wbytes = (size_t)nsteps * 2 * g.N * 16;
-    g.smem = ((g.wbytes + 127) & ~(size_t)127) + (size_t)(g.nslots + nrows - 1) * g.slotBytes + 32 * 16 + (3 * g.nslots + 5) * 8 + 16;
-    if (g.smem > 220 * 1024) return g;
-    g.ok = true;
+    // Loader groups, ring slots and staged rows.  The ring holds the window, the rows the next job adds and one more
+    // job's worth of slack, rounded up to a multiple of the group count G (slot and stage ownership, see the kernel).
+    // Measured on B200 (StyleNet layers, 1524x1856): rows finished concurrently matter more than staged rows per
+    // group (res 3x3 40->40: G=1 20.6 us, G=2 18.2 us, G=4 16.1 us), so: four groups if they fit at all, else two.
+    const size_t budget = 220 * 1024;
+    // (FYN_TC_GROUPS=1|2|4 overrides the choice: tuning knob)
+    int gmax = 4, gmin = 2;
+    if (const char *e = getenv("FYN_TC_GROUPS")) gmax = gmin = std::max(1, std::min(4, atoi(e)));
+    for (int G = gmax; G >= gmin && !g.ok; G = (G == 4 ? 2 : G - 1)) {
+        const int need = nrows + 2 * g.rowAdvance;
+        const int nslots = ((need + G - 1) / G) * G;
+        const size_t fixed = ((g.wbytes + 127) & ~(size_t)127) + (size_t)(nslots + nrows - 1) * g.slotBytes + 32 * 16 + (size_t)g.nitems * 8 +
+                             (2 * nslots + 5 + kMaxStages) * 8 + 16 + 16;   // + the 16 zero bytes
+        if (fixed + (size_t)G * g.stageBytes > budget) continue;
+        const int m = (int)std::min<size_t>(kMaxStages / G, (budget - fixed) / ((size_t)G * g.stageBytes));
+        g.finGroups = G;
+        g.nslots = nslots;
+        g.nstages = m * G;
+        g.smem = fixed + (size_t)g.nstages * g.stageBytes;
+        g.ok = true;
+    }
     return g;
+}
+
+}  // namespace
+
+namespace {
+
+using TcKernel = void (*)(TcArgs);
+
+// kernel instantiations: [mode][act][res]
+TcKernel tc_kernel(int mode, int act, int res) {
+    static const TcKernel table[2][3][3] = {
+        {{k_conv_tc<0, 0, 0>, k_conv_tc<0, 0, 1>, k_conv_tc<0, 0, 2>},
+         {k_conv_tc<0, 1, 0>, k_conv_tc<0, 1, 1>, k_conv_tc<0, 1, 2>},
+         {k_conv_tc<0, 2, 0>, k_conv_tc<0, 2, 1>, k_conv_tc<0, 2, 2>}},
+        {{k_conv_tc<1, 0, 0>, k_conv_tc<1, 0, 2>, k_conv_tc<1, 0, 2>},
+         {k_conv_tc<1, 1, 0>, k_conv_tc<1, 1, 2>, k_conv_tc<1, 1, 2>},
+         {k_conv_tc<1, 2, 0>, k_conv_tc<1, 2, 2>, k_conv_tc<1, 2, 2>}}};
+    return table[mode][act][res];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function and device, not per launch: keep it at the largest
+// footprint any plan has needed so far
+int tc_ensure_smem(TcKernel fn, int mode, int act, int res, int device, size_t bytes) {
+    static size_t cur[64][2][3][3] = {};
+    size_t &c = cur[device & 63][mode][act][res];
+    if (bytes > c) {
+        FYN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        c = bytes;
+    }
+    return FYN_OK;
 }
 
 }  // namespace
@@ -852,8 +982,10 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     a.x_lead = g.x_lead;
     a.nslots = g.nslots;
     a.nsteps = g.nsteps;
-    a.groupWarps = g.groupWarps;
-    a.depth = g.depth;
+    a.stageBytes = g.stageBytes;
+    a.nstages = g.nstages;
+    a.finGroups = g.finGroups;
+    a.nitems = g.nitems;
     a.slotBytes = g.slotBytes;
     a.idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);  // F32 accum, F16 x F16, K-major A/B
     a.b_lbo = (uint32_t)N * 16u;
@@ -934,13 +1066,6 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     plan->smemBytes = g.smem;
     if (plan->smemBytes > (size_t)op->ctx->prop.sharedMemPerBlockOptin)
         FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 conv needs %zu bytes of shared memory", plan->smemBytes);
-    // the attribute is per function, not per launch: keep it at the largest footprint any plan needs
-    static size_t maxSmem[64] = {0};
-    size_t &cur = maxSmem[op->ctx->device & 63];
-    if (plan->smemBytes > cur) {
-        FYN_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smemBytes));
-        cur = plan->smemBytes;
-    }
     return FYN_OK;
 }
 
@@ -951,6 +1076,11 @@ int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn
     if (out->desc.dtype != FYN_F16 || out->desc.order != FYN_ORDER_SHALLOW || (res && res->desc.dtype != FYN_F16)) return 1;
     if (plan->mode == 0 && (in->desc.dtype != FYN_F16 || in->geom.packing != 4)) return 1;
     if (in->desc.order != FYN_ORDER_SHALLOW && in->desc.channels > 4) return 1;
+    // rows are staged with 16-byte-granular bulk copies that may run up to 15 bytes past the last texel of a row:
+    // fine inside the tensor and for tensors this library allocated (16 bytes of slack); wrapped memory must end on a
+    // 16-byte boundary
+    if (!in->owns && (((uintptr_t)in->dptr + in->geom.bytes) & 15u) != 0) return 1;
+    if (((uintptr_t)in->dptr & 7u) != 0) return 1;
     TcArgs a = plan->args;
     a.in = fyn_make_view(in);
     a.out = fyn_make_view(out);
@@ -978,6 +1108,11 @@ int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn
     const int nseg = (a.Hj + a.SH - 1) / a.SH;
     const long long blocks = (long long)a.nxs * nseg * a.batch;
     // programmatic dependent launch: the prologue (barriers, TMEM, weight image) overlaps the previous kernel's tail
+    const int actSel = a.act.type == 0 ? 0 : (a.act.type == 1 ? 1 : 2);
+    int resSel = 0;
+    if (a.hasRes) resSel = (a.mode == 0 && a.opx == 1 && a.opy == 1 && res->desc.dtype == FYN_F16 && res->geom.packing == 4 && res->desc.order == FYN_ORDER_SHALLOW) ? 1 : 2;
+    TcKernel fn = tc_kernel(a.mode, actSel, resSel);
+    if (int rc = tc_ensure_smem(fn, a.mode, actSel, resSel, op->ctx->device, plan->smemBytes)) return rc;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)blocks);
     cfg.blockDim = dim3(kThreads);
@@ -988,7 +1123,7 @@ int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    FYN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc, a));
+    FYN_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
     FYN_CHECK_LAUNCH(op->ctx);
     return FYN_OK;
 }

@@ -94,7 +94,8 @@ static int tensor_new(fyn_ctx *ctx, const fyn_tensor_desc *desc, void *wrap, fyn
         t->dptr = wrap;
         t->owns = false;
     } else {
-        cudaError_t e = cudaMalloc(&t->dptr, g.bytes);
+        // 16 bytes of slack: the tcgen05 conv family stages rows with 16-byte-granular bulk copies
+        cudaError_t e = cudaMalloc(&t->dptr, g.bytes + 16);
         if (e != cudaSuccess) {
             delete t;
             FYN_FAIL(FYN_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", g.bytes, cudaGetErrorString(e));
