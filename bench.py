@@ -219,12 +219,10 @@ def main():
     for _ in range(args.warmup):
         net.forward()
     net.finish()
-    net.enable_timings(True)
     ev0, ev1 = ctx.event_create(), ctx.event_create()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    n0 = ctx.launch_count()
     lib_launch0 = _net_launches(net)
     ctx.event_record(ev0, stream)
     for _ in range(args.steps):
@@ -235,6 +233,12 @@ def main():
     clocks = sampler.stop()
     ms = ctx.elapsed_ms(ev0, ev1)
     launches = _net_launches(net) - lib_launch0
+    # per-layer times: a second pass with the engine's event pairs between the layers (they cost a few percent, so
+    # they stay out of the timed region above)
+    net.enable_timings(True)
+    for _ in range(args.steps):
+        net.forward()
+    net.finish()
     layer_ms = {l["name"]: net.layer_timing(l["number"])[0] / args.steps for l in net.layers()}
     families = {l["name"]: l["family"] for l in net.layers()}
     net.enable_timings(False)
@@ -306,7 +310,16 @@ def main():
         else:
             roof = {"bound": "hbm", "achieved": a["bytes"] / t_s / 1e9, "peak": hbm, "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
-        roof["traffic"] = None
+        roof["traffic"] = None      # dram bytes read + written per launch of that kernel, from the committed ncu capture
+        roof["traffic_source"] = None
+        for f in sorted((ROOT / "profiles").glob("r*_top_kernel_ncu.json"), reverse=True):
+            cap = json.loads(f.read_text())
+            if cap.get("layer") == top:
+                roof["traffic"] = cap["traffic_bytes_per_launch"]
+                roof["traffic_source"] = f"profiles/{f.name} (ncu --set full, one launch)"
+                break
+        roof["algorithmic_bytes_per_launch"] = a["bytes"]
+        roof["algorithmic_flops_per_launch"] = a["flops"]
         roof["kernel"] = top
         roof["peak_source"] = f"{which} ({'sustained' if roof['bound'] == 'tensor' else 'copy'} figure, kernel timed inside a long step)"
         roof["ms_per_launch"] = conv_ms[top]
