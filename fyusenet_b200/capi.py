@@ -67,6 +67,8 @@ class BnDesc(C.Structure):
 UnaryDesc = BnDesc  # identical field layout (fyn_unary_desc)
 
 # every symbol include/fyusenet_b200.h declares (tests check that the library exports all of them)
+EPILOGUE_NONE, EPILOGUE_SIGMOID = 0, 1
+
 EXPORTS = [
     "fyn_abi_version", "fyn_last_error", "fyn_device_count", "fyn_cuda_init", "fyn_cuda_shutdown",
     "fyn_get_device_info", "fyn_launch_count", "fyn_stream_create", "fyn_stream_destroy", "fyn_stream_sync",
@@ -76,7 +78,7 @@ EXPORTS = [
     "fyn_tensor_wrap", "fyn_tensor_destroy", "fyn_tensor_clear", "fyn_tensor_get_desc", "fyn_tensor_device_ptr",
     "fyn_upload_f32_async", "fyn_download_f32_async", "fyn_download_f32_elems", "fyn_tensor_write_chw_f32",
     "fyn_tensor_read_chw_f32", "fyn_conv2d_output_size", "fyn_conv2d_create", "fyn_conv2d_load_weights",
-    "fyn_conv2d_run", "fyn_conv2d_backend", "fyn_pool2d_create", "fyn_pool2d_run", "fyn_batchnorm_create",
+    "fyn_conv2d_run", "fyn_conv2d_backend", "fyn_conv2d_set_epilogue", "fyn_pool2d_create", "fyn_pool2d_run", "fyn_batchnorm_create",
     "fyn_batchnorm_load", "fyn_batchnorm_run", "fyn_sigmoid_create", "fyn_sigmoid_run", "fyn_op_destroy",
 ]
 
@@ -282,6 +284,10 @@ class Conv2d(_Op):
     def load_weights(self, weights):
         w = np.ascontiguousarray(weights, np.float32)
         check(lib().fyn_conv2d_load_weights(self._h, _fptr(w)))
+
+    def set_epilogue(self, function: int):
+        """Fuse the element-wise layer that follows (EPILOGUE_SIGMOID) into the convolution's epilogue."""
+        check(lib().fyn_conv2d_set_epilogue(self._h, int(function)))
 
     def run(self, x: Tensor, out: Tensor, residual: Tensor | None = None, stream=None):
         check(lib().fyn_conv2d_run(self._h, x._h, residual._h if residual is not None else None, out._h, _s(stream)))

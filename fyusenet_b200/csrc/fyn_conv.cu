@@ -150,6 +150,13 @@ int fyn_conv2d_create(fyn_ctx *ctx, const fyn_conv_desc *desc, const float *wb, 
 
 int fyn_conv2d_backend(const fyn_op *op) { return (op && op->kind == FYN_OP_CONV) ? op->backend : 0; }
 
+int fyn_conv2d_set_epilogue(fyn_op *op, int function) {
+    if (!op || op->kind != FYN_OP_CONV) FYN_FAIL(FYN_ERR_INVALID, "not a convolution op");
+    if (function != FYN_EPILOGUE_NONE && function != FYN_EPILOGUE_SIGMOID) FYN_FAIL(FYN_ERR_INVALID, "conv: unknown epilogue function %d", function);
+    op->epilogue = function;
+    return FYN_OK;
+}
+
 static int check_tensor(const fyn_tensor *t, const char *what, int w, int h, int c, int pad, bool deep) {
     if (!t) FYN_FAIL(FYN_ERR_INVALID, "conv: %s tensor is NULL", what);
     const fyn_tensor_desc &d = t->desc;

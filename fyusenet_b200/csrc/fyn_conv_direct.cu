@@ -26,6 +26,7 @@ struct DirectConvArgs {
     int Wo, Ho, nIn, nOut, batch, outP, resP, xBlocks, yBlocks;
     ActParams act;
     int actFirstOnly, hasRes, reluRes, bnRes;
+    int epilogue;         // FYN_EPILOGUE_*
 };
 
 __global__ void __launch_bounds__(128) k_conv_direct(const DirectConvArgs a) {
@@ -74,6 +75,11 @@ __global__ void __launch_bounds__(128) k_conv_direct(const DirectConvArgs a) {
         r.z += q.z;
         r.w += q.w;
     }
+    if (a.epilogue == FYN_EPILOGUE_SIGMOID) {
+        // fused FunctionLayer: same values as storing the convolution and running the sigmoid layer on the stored texel
+        if (a.out.dtype == FYN_F16) r = make_float4(fyn_round_half(r.x), fyn_round_half(r.y), fyn_round_half(r.z), fyn_round_half(r.w));
+        r = make_float4(fyn_sigmoid(r.x), fyn_sigmoid(r.y), fyn_sigmoid(r.z), fyn_sigmoid(r.w));
+    }
     fyn_store_texel(a.out, n, op, a.outP + xo, a.outP + yo, r);
 }
 
@@ -112,6 +118,7 @@ int fyn_conv_direct_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res,
     a.hasRes = (d.flags & FYN_FLAG_RESIDUAL_INPUT) != 0;
     a.reluRes = (d.flags & FYN_FLAG_RELU_ON_RESIDUAL) != 0;
     a.bnRes = (d.flags & FYN_FLAG_BATCHNORM_ON_RESIDUAL) != 0;
+    a.epilogue = op->epilogue;
     a.xBlocks = (a.Wo + 31) / 32;
     a.yBlocks = (a.Ho + 3) / 4;
     long long blocks = (long long)a.xBlocks * a.yBlocks * a.nOut * a.batch;

@@ -106,6 +106,7 @@ struct TcArgs {
     int x_lead;              // input pixels to the left of job column 0 held in a slot
     ActParams act;
     int hasRes, reluRes, bnRes;
+    int epilogue;            // FYN_EPILOGUE_*: element-wise function fused behind the convolution
     int batch;
 };
 
@@ -198,6 +199,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
 }
 // one deterministic leader lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
@@ -600,35 +607,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                    (long long)(clock64() - pStart), pWaitT, pWaitF, pIssue, pCommit);
 #endif
     } else {
-        // ===================== epilogue: warps 0-7, thread = job column x half of the column groups ==========
-        const int m = threadIdx.x & 127;     // TMEM lane == job column inside the tile
-        const int chalf = warp >> 2;         // this warp handles 16-column groups chalf and chalf + 2
+        // ===================== epilogue: warps 0-7 =====================
+        // Thread = job column (TMEM lane); the two warps of a lane quarter split the accumulator columns evenly in
+        // units of 8 columns (an "octet" = two 4-channel texels): warp half h takes octets [h * N/16, (h+1) * N/16).
+        // Column order is [fy][plane][fx][channel] (see the weight image), so with 2 or 4 phases along x an octet is two
+        // horizontally adjacent output texels of one plane -> one 16-byte store.
+        const int m = threadIdx.x & 127;
+        const int chalf = warp >> 2;
         const int jx = j0 + m;
         const bool valid = jx < a.Wj;
-        const int groups = a.N >> 4;
+        const int nOct = a.N >> 4;           // octets per thread (1..4)
         const int ppp = a.planesPerPhase;
-        // Per (group, plane-in-group) constants, hoisted out of the job loop: output element offset relative to the
-        // job's first output texel (-1 = nothing to store) and the output plane (bias / scale / residual index).
-        int poff[2][4], pidx[2][4];
+        // per texel, hoisted out of the job loop: output element offset relative to the job's first output texel
+        // (-1 = nothing to store) and the output plane (bias / scale / residual index)
+        int poff[4][2], pidx[4][2];
 #pragma unroll
-        for (int gi = 0; gi < 2; gi++)
+        for (int o = 0; o < 4; o++)
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                // stacked plane index -> (fy, plane, fx): the phases of one output row are adjacent columns so that a
-                // thread's texels of one plane are contiguous in memory (opx * 8 bytes)
-                const int pn = (chalf + 2 * gi) * 4 + k;
+            for (int k = 0; k < 2; k++) {
+                const int pn = (chalf * nOct + o) * 2 + k;   // stacked plane index
                 const int fx = pn % a.opx, tq = pn / a.opx;
                 const int fy = tq / ppp, p = tq - fy * ppp;
-                pidx[gi][k] = p;
-                poff[gi][k] = (fy < a.opy && chalf + 2 * gi < groups && valid)
-                                  ? (int)((long long)p * a.out.planeElems + (long long)fy * a.out.texW * 4 + fx * 4) : -1;
+                pidx[o][k] = p;
+                poff[o][k] = (o < nOct && fy < a.opy && valid) ? (int)((long long)p * a.out.planeElems + (long long)fy * a.out.texW * 4 + fx * 4) : -1;
             }
         __half *outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((long long)a.outP * a.out.texW + a.outP + a.opx * jx) * 4;
         const long long outRow = (long long)a.out.texW * 4 * a.opy;   // elements per job row
         // 16-byte stores need every job's first texel on a 16-byte boundary in every output row
-        const bool aligned16 = ((a.outP & 1) == 0 || (a.out.texW & 1) == 0) && ((a.outP + a.opx * jx) & 1) == 0 && (a.out.texW & 1) == 0 &&
-                               (a.out.planeElems & 7) == 0 && (a.out.imageElems & 7) == 0;
-        const int wide = (aligned16 && (a.opx == 2 || a.opx == 4)) ? a.opx : 1;
+        const bool aligned16 = (a.outP & 1) == 0 && (a.out.texW & 1) == 0 && (a.out.planeElems & 7) == 0 && (a.out.imageElems & 7) == 0;
+        const bool wide = aligned16 && (a.opx == 2 || a.opx == 4);
         const __half *resp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems + ((long long)a.resP * a.res.texW + a.resP + jx) * 4;
         const int resPlane = (int)a.res.planeElems;
         PROF_DECL(pEpWait);
@@ -637,49 +644,50 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             const int buf = q & 1, use = q >> 1;
             const int i = ja + q;                    // job row
             // residual texels are fetched before waiting for the accumulator so their latency hides behind the MMAs
-            uint2 rres[2][4];
+            uint2 rres[4][2];
             if (RES == 1) {
                 const __half *rp = resp + (long long)i * a.res.texW * 4;
 #pragma unroll
-                for (int gi = 0; gi < 2; gi++)
+                for (int o = 0; o < 4; o++)
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (poff[gi][k] >= 0) rres[gi][k] = __ldg(reinterpret_cast<const uint2 *>(rp + pidx[gi][k] * resPlane));
+                    for (int k = 0; k < 2; k++)
+                        if (poff[o][k] >= 0) rres[o][k] = __ldg(reinterpret_cast<const uint2 *>(rp + pidx[o][k] * resPlane));
             }
             [[maybe_unused]] const long long pt = PROF_T();
             mbar_wait(&tfull[buf], use & 1);
             PROF_ADD(pEpWait, pt);
             tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * 64u;
-            uint32_t acc[2][16];
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * 64u + (uint32_t)(chalf * nOct) * 8u;
+            uint32_t acc[4][8];
 #pragma unroll
-            for (int gi = 0; gi < 2; gi++)
-                if (chalf + 2 * gi < groups) tmem_ld16(taddr + (chalf + 2 * gi) * 16, acc[gi]);
+            for (int o = 0; o < 4; o++)
+                if (o < nOct) tmem_ld8(taddr + o * 8, acc[o]);
             tmem_ld_wait();
             // accumulators are in registers: hand the TMEM buffer back before the global-memory work
             tc_fence_before();
             mbar_arrive(&tempty[buf]);
             __half *orow = outp + (long long)i * outRow;
 #pragma unroll
-            for (int gi = 0; gi < 2; gi++) {
-                uint2 o[4];
+            for (int o = 0; o < 4; o++) {
+                if (o >= nOct) break;
+                uint2 t[2];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    o[k] = make_uint2(0u, 0u);
-                    if (poff[gi][k] >= 0) {
-                        const int p = pidx[gi][k];
+                for (int k = 0; k < 2; k++) {
+                    t[k] = make_uint2(0u, 0u);
+                    if (poff[o][k] >= 0) {
+                        const int p = pidx[o][k];
                         const float4 bi = sEpi[p], sc = sEpi[16 + p];
-                        float4 v = make_float4(fmaf(__uint_as_float(acc[gi][4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[gi][4 * k + 1]), sc.y, bi.y),
-                                               fmaf(__uint_as_float(acc[gi][4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[gi][4 * k + 3]), sc.w, bi.w));
+                        float4 v = make_float4(fmaf(__uint_as_float(acc[o][4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[o][4 * k + 1]), sc.y, bi.y),
+                                               fmaf(__uint_as_float(acc[o][4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[o][4 * k + 3]), sc.w, bi.w));
                         if (RES != 0) {
                             float4 rs;
                             if (RES == 1) {
-                                const uint2 raw = rres[gi][k];
+                                const uint2 raw = rres[o][k];
                                 const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
                                 const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
                                 rs = make_float4(f0.x, f0.y, f1.x, f1.y);
                             } else {
-                                const int pn = (chalf + 2 * gi) * 4 + k, fx = pn % a.opx, fy = (pn / a.opx) / ppp;
+                                const int pn = (chalf * nOct + o) * 2 + k, fx = pn % a.opx, fy = (pn / a.opx) / ppp;
                                 rs = fyn_fetch(a.res, n, p, a.resP + a.opx * jx + fx, a.resP + a.opy * i + fy);
                             }
                             if (a.reluRes) rs = make_float4(fmaxf(rs.x, 0.f), fmaxf(rs.y, 0.f), fmaxf(rs.z, 0.f), fmaxf(rs.w, 0.f));
@@ -689,22 +697,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                             v.z += rs.z;
                             v.w += rs.w;
                         }
-                        o[k] = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
+                        t[k] = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
+                        if (a.epilogue == FYN_EPILOGUE_SIGMOID) {
+                            // fused FunctionLayer, evaluated on the fp16-rounded convolution result like the unfused pair
+                            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&t[k].x));
+                            const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&t[k].y));
+                            t[k] = make_uint2(pack_half2(fyn_sigmoid(f0.x), fyn_sigmoid(f0.y)), pack_half2(fyn_sigmoid(f1.x), fyn_sigmoid(f1.y)));
+                        }
                     }
                 }
-                // texels of adjacent phases are adjacent in memory: 16-byte stores where the row alignment allows
-                if (wide == 4) {
-                    if (poff[gi][0] >= 0) {
-                        *reinterpret_cast<uint4 *>(orow + poff[gi][0]) = make_uint4(o[0].x, o[0].y, o[1].x, o[1].y);
-                        *reinterpret_cast<uint4 *>(orow + poff[gi][2]) = make_uint4(o[2].x, o[2].y, o[3].x, o[3].y);
-                    }
-                } else if (wide == 2) {
-                    if (poff[gi][0] >= 0) *reinterpret_cast<uint4 *>(orow + poff[gi][0]) = make_uint4(o[0].x, o[0].y, o[1].x, o[1].y);
-                    if (poff[gi][2] >= 0) *reinterpret_cast<uint4 *>(orow + poff[gi][2]) = make_uint4(o[2].x, o[2].y, o[3].x, o[3].y);
+                // with phases along x the two texels are adjacent in memory: one 16-byte store where alignment allows
+                if (wide) {
+                    if (poff[o][0] >= 0) *reinterpret_cast<uint4 *>(orow + poff[o][0]) = make_uint4(t[0].x, t[0].y, t[1].x, t[1].y);
                 } else {
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (poff[gi][k] >= 0) *reinterpret_cast<uint2 *>(orow + poff[gi][k]) = o[k];
+                    if (poff[o][0] >= 0) *reinterpret_cast<uint2 *>(orow + poff[o][0]) = t[0];
+                    if (poff[o][1] >= 0) *reinterpret_cast<uint2 *>(orow + poff[o][1]) = t[1];
                 }
             }
         }
@@ -1097,6 +1104,7 @@ int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn
     a.hasRes = (d.flags & FYN_FLAG_RESIDUAL_INPUT) != 0;
     a.reluRes = (d.flags & FYN_FLAG_RELU_ON_RESIDUAL) != 0;
     a.bnRes = (d.flags & FYN_FLAG_BATCHNORM_ON_RESIDUAL) != 0;
+    a.epilogue = op->epilogue;
     a.batch = in->desc.batch;
     a.nxs = (a.Wj + kTileM - 1) / kTileM;
     // strip height: one strip per SM (the kernel's register / shared-memory footprint allows one CTA per SM),

@@ -97,6 +97,7 @@ struct fyn_op {
     float *d_bias = nullptr;   // [nOut*4] folded bias
     float *d_scale = nullptr;  // [nOut*4] BN scale (1 without post-BN)
     int backend = 0;           // 1 direct, 2 tcgen05
+    int epilogue = 0;          // FYN_EPILOGUE_*: element-wise function fused behind the convolution
     ConvTcPlan *tc = nullptr;
     // pool
     fyn_pool_desc pool{};
@@ -130,6 +131,10 @@ __device__ __forceinline__ float fyn_act(float v, const ActParams &a) {
     if (a.type == 3) return fminf(a.hi, fmaxf(a.lo, v));
     return v;
 }
+
+// shaders/sigmoid.frag:10-13
+__device__ __forceinline__ float fyn_sigmoid(float v) { return 1.f / (1.f + __expf(-v)); }
+__device__ __forceinline__ float fyn_round_half(float v) { return __half2float(__float2half_rn(v)); }
 
 __device__ __forceinline__ float4 fyn_act4(float4 v, const ActParams &a) {
     return make_float4(fyn_act(v.x, a), fyn_act(v.y, a), fyn_act(v.z, a), fyn_act(v.w, a));

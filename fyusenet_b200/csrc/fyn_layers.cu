@@ -70,7 +70,7 @@ __device__ __forceinline__ float4 elt_apply(const EltArgs &a, float4 v, int t) {
         return make_float4(fmaf(v.x, s.x, b.x), fmaf(v.y, s.y, b.y), fmaf(v.z, s.z, b.z), fmaf(v.w, s.w, b.w));
     }
     // shaders/sigmoid.frag:10-13
-    return make_float4(1.f / (1.f + __expf(-v.x)), 1.f / (1.f + __expf(-v.y)), 1.f / (1.f + __expf(-v.z)), 1.f / (1.f + __expf(-v.w)));
+    return make_float4(fyn_sigmoid(v.x), fyn_sigmoid(v.y), fyn_sigmoid(v.z), fyn_sigmoid(v.w));
 }
 
 __global__ void __launch_bounds__(128) k_eltwise(const EltArgs a) {

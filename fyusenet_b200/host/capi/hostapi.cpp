@@ -298,6 +298,19 @@ int fynhost_net_enable_dumps(void *handle, const char *dir) {
     return guarded([&] { h->net()->engine()->enableIntermediateOutput(dir); });
 }
 
+// layer fusion (conv + sigmoid in one kernel): on by default, suspended while dumps are written
+int fynhost_net_enable_fusion(void *handle, int on) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] { h->net()->engine()->enableFusion(on != 0); });
+}
+
+int fynhost_net_fused_layers(void *handle) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    int n = -1;
+    guarded([&] { n = h->net()->engine()->fusedLayers(); });
+    return n;
+}
+
 int fynhost_net_enable_timings(void *handle, int on) {
     NetHandle *h = static_cast<NetHandle *>(handle);
     return guarded([&] {

@@ -47,8 +47,12 @@ class Engine : public GfxContextTracker {
     const std::unordered_map<int, float> &getDeviceTimings() { collectTimings(true); return deviceTimingData_; }
     int timedRuns() const { return runs_; }
     // <dir>/<layername>_<seq>.bin dumps, CHW float32 without padding
-    void enableIntermediateOutput(const std::string &outputDir) { outputDir_ = outputDir; writeResults_ = true; }
-    void disableIntermediateOutput() { writeResults_ = false; }
+    void enableIntermediateOutput(const std::string &outputDir) { outputDir_ = outputDir; writeResults_ = true; updateFusion(); }
+    void disableIntermediateOutput() { writeResults_ = false; updateFusion(); }
+    // Layer fusion (conv + element-wise function in one kernel) is on by default and suspended while intermediate
+    // results are written, so that every layer's dump shows that layer's own output.
+    void enableFusion(bool on) { fusion_ = on; updateFusion(); }
+    int fusedLayers() const { return fusedLayers_; }
     // capture the layer sequence into a CUDA graph on the next forward and replay it afterwards
     void enableGraph(bool on) { useGraph_ = on; }
     // asynchronous operation: callbacks fired from a driver thread when a sequence's download has landed
@@ -81,6 +85,9 @@ class Engine : public GfxContextTracker {
     bool async_ = false;
     bool timings_ = false;
     bool writeResults_ = false;
+    bool fusion_ = true;
+    int fusedLayers_ = 0;
+    void updateFusion();
     bool useGraph_ = false;
     std::string outputDir_;
     std::unordered_map<int, uint32_t> timingData_;

@@ -33,9 +33,17 @@ class ConvLayerBase : public GPULayerBase, public ConvLayerInterface {
     int kernel() const { return desc_.kernel; }
     int backendFamily() const { return op_ ? fyn_conv2d_backend(op_) : 0; }  // 1 direct, 2 tcgen05
     const fyn_conv_desc &descriptor() const { return desc_; }
+    // Engine-level layer fusion: evaluate the element-wise FunctionLayer that consumes this layer in the convolution's
+    // epilogue and write straight into that layer's output tensor (the reference runs one render pass per layer,
+    // gpu/functionlayer.cpp:145-179).  Returns false when the pair cannot be fused.
+    bool fuseFunction(int function, TensorHandle target);
+    void unfuse();
+    bool fused() const { return fusedTarget_ != nullptr; }
 
  protected:
     void init(int kernel, int dilation, float sourceStep, bool fractional);
+    int fusedFunction_ = 0;
+    TensorHandle fusedTarget_ = nullptr;
     fyn_conv_desc desc_{};
     fyn_op *op_ = nullptr;
     std::vector<float> pendingWeights_;  // weights handed over before setup()
@@ -87,10 +95,16 @@ class SigmoidLayer : public GPULayerBase {
     void forward(uint64_t sequence = 0) override;
     std::vector<BufferSpec> getRequiredInputBuffers() const override;
     std::vector<BufferSpec> getRequiredOutputBuffers() const override;
+    // fusion support: a sigmoid without prefix activation can be evaluated by its producer (ConvLayerBase::fuseFunction);
+    // a bypassed layer does nothing in forward(), its output tensor is written by the producer
+    bool plainFunction() const { return (flags_ & (LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP)) == 0; }
+    void setBypass(bool on) { bypass_ = on; }
+    bool bypassed() const { return bypass_; }
 
  protected:
     fyn_unary_desc desc_{};
     fyn_op *op_ = nullptr;
+    bool bypass_ = false;
 };
 
 class UploadLayer : public GPULayerBase, public cpu::CPULayerInterface {

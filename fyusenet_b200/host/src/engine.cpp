@@ -19,6 +19,29 @@ void Engine::setup(NeuralNetwork *net) {
     assertContext();
     layers_ = net->glSetup();
     setup_ = true;
+    updateFusion();
+}
+
+// Fuses conv -> sigmoid pairs (the only consumer of the convolution is a plain sigmoid layer): the convolution's
+// epilogue evaluates the function and writes the sigmoid layer's output tensor, the sigmoid layer is bypassed.
+void Engine::updateFusion() {
+    if (!setup_) return;
+    if (async_) finish();
+    const bool want = fusion_ && !writeResults_;
+    fusedLayers_ = 0;
+    for (auto it = layers_.begin(); it != layers_.end(); ++it) {
+        auto *conv = dynamic_cast<gpu::ConvLayerBase *>(it.second);
+        if (!conv) continue;
+        const auto &recv = conv->receivers();
+        auto *sig = recv.size() == 1 ? dynamic_cast<gpu::SigmoidLayer *>(recv[0].first) : nullptr;
+        if (!sig) continue;
+        conv->unfuse();
+        sig->setBypass(false);
+        if (want && sig->plainFunction() && sig->hasOutputTexture(0) && conv->fuseFunction(FYN_EPILOGUE_SIGMOID, sig->getOutputTexture(0))) {
+            sig->setBypass(true);
+            fusedLayers_++;
+        }
+    }
 }
 
 void Engine::cleanup() {

@@ -142,7 +142,27 @@ void ConvLayerBase::forward(uint64_t) {
             THROW_EXCEPTION_ARGS(FynException, "Residual flag configured, but no such texture found.");
         res = residuals_[0];
     }
-    FYN_ABI_CALL(fyn_conv2d_run(op_, in(0), res, out(), context_.stream()));
+    FYN_ABI_CALL(fyn_conv2d_run(op_, in(0), res, fusedTarget_ ? fusedTarget_ : out(), context_.stream()));
+}
+
+bool ConvLayerBase::fuseFunction(int function, TensorHandle target) {
+    if (!op_ || !target || !hasOutputTexture(0)) return false;
+    // the consumer's output must be laid out exactly like ours and must not alias anything this layer reads
+    fyn_tensor_desc mine{}, theirs{};
+    FYN_ABI_CALL(fyn_tensor_get_desc(out(), &mine, nullptr));
+    FYN_ABI_CALL(fyn_tensor_get_desc(target, &theirs, nullptr));
+    if (memcmp(&mine, &theirs, sizeof(mine)) != 0) return false;
+    if (target == in(0) || (!residuals_.empty() && target == residuals_[0])) return false;
+    if (fyn_conv2d_set_epilogue(op_, function) != 0) return false;
+    fusedFunction_ = function;
+    fusedTarget_ = target;
+    return true;
+}
+
+void ConvLayerBase::unfuse() {
+    if (op_) fyn_conv2d_set_epilogue(op_, FYN_EPILOGUE_NONE);
+    fusedFunction_ = 0;
+    fusedTarget_ = nullptr;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -270,6 +290,7 @@ void SigmoidLayer::cleanup() {
 void SigmoidLayer::forward(uint64_t) {
     if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
     std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    if (bypass_) return;   // evaluated in the producer's epilogue
     FYN_ABI_CALL(fyn_sigmoid_run(op_, in(0), out(), context_.stream()));
 }
 

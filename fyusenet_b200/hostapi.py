@@ -158,6 +158,14 @@ class Network:
     def enable_dumps(self, directory: str):
         _check(lib().fynhost_net_enable_dumps(self._h, str(directory).encode()))
 
+    def enable_fusion(self, on=True):
+        """Engine-level layer fusion (conv + sigmoid in one kernel); on by default, suspended while dumps are written."""
+        _check(lib().fynhost_net_enable_fusion(self._h, int(on)))
+
+    @property
+    def fused_layers(self) -> int:
+        return lib().fynhost_net_fused_layers(self._h)
+
     def enable_timings(self, on=True):
         _check(lib().fynhost_net_enable_timings(self._h, int(on)))
 

@@ -221,6 +221,14 @@ int fyn_conv2d_load_weights(fyn_op *op, const float *bias_weights_bn);
 int fyn_conv2d_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *residual, fyn_tensor *out, void *stream);
 /* which kernel family the op resolved to: 1 = direct, 2 = tcgen05 */
 int fyn_conv2d_backend(const fyn_op *op);
+/* Fuses the element-wise FunctionLayer that consumes this convolution into its epilogue (engine-level layer
+ * fusion; the reference runs it as its own render pass, fyusenet/gpu/functionlayer.cpp:145-179).  `function`:
+ * FYN_EPILOGUE_NONE or FYN_EPILOGUE_SIGMOID (fyusenet/gpu/sigmoidlayer.cpp:77-112, shaders/sigmoid.frag:10-17).
+ * The convolution result is first rounded to the storage type of the output tensor, so the values equal those of
+ * the unfused layer pair. */
+#define FYN_EPILOGUE_NONE 0
+#define FYN_EPILOGUE_SIGMOID 1
+int fyn_conv2d_set_epilogue(fyn_op *op, int function);
 
 /* DeepMaxPoolLayer / DeepAvgPoolLayer / MaxPoolLayer / AvgPoolLayer
  * (fyusenet/gpu/deep/deeppoolinglayer.cpp:38-54,109-190; shaders deep/deepmaxpool.frag, deepavgpool.frag) */

@@ -308,3 +308,40 @@ def test_error_behaviour():
     good = c.tensor(16, 16, 8)
     op.run(tin, good)
     assert c.launch_count() == n0 + 1
+
+
+@pytest.mark.parametrize("backend", [capi.BACKEND_DIRECT, capi.BACKEND_TC])
+@pytest.mark.parametrize("dtype", [capi.F16, capi.F32])
+def test_conv_fused_sigmoid_epilogue(backend, dtype):
+    """fyn_conv2d_set_epilogue(SIGMOID): one kernel must give exactly what the conv layer followed by the sigmoid
+    layer gives (StyleNet deconv3 -> sigmoid, fractional 9x9 12->3), on both kernel families."""
+    if backend == capi.BACKEND_TC and dtype == capi.F32:
+        pytest.skip("the tcgen05 family stores fp16")
+    c = ctx()
+    rng = np.random.default_rng(17)
+    h, w, ci, co = 24, 136, 12, 3
+    x = rng.normal(size=(ci, h, w)).astype(np.float32)
+    wb = random_wb(rng, ci, co, 9)
+    kw = dict(width=w, height=h, in_channels=ci, out_channels=co, kernel=9, flags=capi.FLAG_PRE_RELU, source_step=0.5,
+              fractional=True, backend=backend)
+    conv = capi.Conv2d(c, wb, **kw)
+    ow, oh = conv.out_width, conv.out_height
+    tin = c.tensor(w, h, ci, 0, capi.ORDER_SHALLOW, dtype)
+    tmid = c.tensor(ow, oh, co, 0, capi.ORDER_SHALLOW, dtype)
+    t2 = c.tensor(ow, oh, co, 0, capi.ORDER_SHALLOW, dtype)
+    t1 = c.tensor(ow, oh, co, 0, capi.ORDER_SHALLOW, dtype)
+    tin.write_chw(x)
+    sig = capi.Sigmoid(c, width=ow, height=oh, channels=co)
+    conv.run(tin, tmid)
+    sig.run(tmid, t2)
+    want = t2.download().copy()            # raw texels including the padding lane (sigmoid(0) = 0.5)
+    conv.set_epilogue(capi.EPILOGUE_SIGMOID)
+    conv.run(tin, t1)
+    got = t1.download()
+    assert conv.backend == backend
+    np.testing.assert_array_equal(got, want)
+    conv.set_epilogue(capi.EPILOGUE_NONE)
+    conv.run(tin, t1)
+    np.testing.assert_array_equal(t1.download(), tmid.download())
+    for o in (tin, tmid, t1, t2, conv, sig):
+        o.destroy()

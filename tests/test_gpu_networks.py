@@ -185,3 +185,32 @@ def test_stylenet_asynchronous_pipeline():
     assert (done, last_seq) == (nseq + 1, nseq + 1)
     np.testing.assert_array_equal(np.ctypeslib.as_array(data, shape=(h, w, 4)), want[((nseq + 1) % ns) % 2])
     net.destroy()
+
+
+def test_stylenet_layer_fusion():
+    """Engine-level fusion of deconv3 + sigmoid: identical frames with and without it, suspended while dumps are on."""
+    import tempfile
+    weights = fo.stylenet_synthetic_weights(9)
+    w, h = 256, 160
+    img = fo.synthetic_image(h, w, 5)
+    net = hostapi.StyleNet(9, w, h)
+    net.load_weights(weights)
+    net.setup()
+    assert net.fused_layers == 1
+    net.set_input(img)
+    net.forward()
+    fused = net.output_rgba()[0].copy()
+    net.enable_fusion(False)
+    assert net.fused_layers == 0
+    net.forward()
+    np.testing.assert_array_equal(net.output_rgba()[0], fused)
+    net.enable_fusion(True)
+    assert net.fused_layers == 1
+    with tempfile.TemporaryDirectory() as d:
+        net.enable_dumps(d)                      # every layer must show its own output again
+        assert net.fused_layers == 0
+        net.forward()
+        np.testing.assert_array_equal(net.output_rgba()[0], fused)
+    net.destroy()
+    ref = fo.stylenet_forward(weights, img, 9, prec=fo.FP16_STORE)
+    assert np.abs(fused[..., :3] - ref[..., :3]).max() <= 6e-3
