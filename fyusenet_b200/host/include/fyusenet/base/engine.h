@@ -69,6 +69,11 @@ class Engine : public GfxContextTracker {
     // pipeline state of the asynchronous path.  The reference allows two sequences in flight (engine.cpp:314-316);
     // with three pipeline stages (upload / layers / host copy) three slots are needed to keep all of them busy.
     void *uploadDone_[ASYNC_SLOTS] = {}, *computeDone_[ASYNC_SLOTS] = {}, *copyDone_[ASYNC_SLOTS] = {};
+    // FYN_ASYNC_TRACE=1: per-sequence stage boundaries (events) printed by finish(); a tuning aid
+    struct TraceEntry { uint64_t seq; void *ev[6]; };
+    std::vector<TraceEntry> trace_;
+    void *traceBase_ = nullptr;
+    void dumpTrace();
     bool slotUsed_[ASYNC_SLOTS] = {};
     Completion completions_[ASYNC_SLOTS];
     std::mutex flightLock_;

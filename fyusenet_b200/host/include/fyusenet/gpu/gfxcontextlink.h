@@ -31,6 +31,7 @@ class CudaContext {
         if (ctx_) {
             if (uploadStream_) fyn_stream_destroy(ctx_, uploadStream_);
             if (downloadStream_) fyn_stream_destroy(ctx_, downloadStream_);
+            if (notifyStream_) fyn_stream_destroy(ctx_, notifyStream_);
             fyn_stream_destroy(ctx_, stream_);
             fyn_cuda_shutdown(ctx_);
         }
@@ -44,6 +45,12 @@ class CudaContext {
         if (!downloadStream_) FYN_ABI_CALL(fyn_stream_create(ctx_, &downloadStream_));
         return downloadStream_;
     }
+    // carries only the host notifications of completed downloads: a host function blocks its stream until the driver
+    // thread has run it (~0.4 ms under load on the B200 boxes), which must not delay the next device-to-host copy
+    void *notifyStream() {
+        if (!notifyStream_) FYN_ABI_CALL(fyn_stream_create(ctx_, &notifyStream_));
+        return notifyStream_;
+    }
     CudaContext(const CudaContext &) = delete;
     CudaContext &operator=(const CudaContext &) = delete;
     fyn_ctx *handle() const { return ctx_; }
@@ -56,7 +63,7 @@ class CudaContext {
     int device_ = 0;
     fyn_ctx *ctx_ = nullptr;
     void *stream_ = nullptr;
-    void *uploadStream_ = nullptr, *downloadStream_ = nullptr;
+    void *uploadStream_ = nullptr, *downloadStream_ = nullptr, *notifyStream_ = nullptr;
     void *externalStream_ = nullptr;
     bool useExternal_ = false;
 };

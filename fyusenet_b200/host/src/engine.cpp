@@ -1,4 +1,6 @@
 // Engine + NeuralNetwork.
+#include <cstdlib>
+#include <cstdio>
 #include "fyusenet/base/engine.h"
 
 #include <cstdio>
@@ -128,7 +130,19 @@ Engine::execstate Engine::executeAsync(uint64_t sequence) {
         if (!upload) upload = dynamic_cast<gpu::UploadLayer *>(it.second);
         if (auto *d = dynamic_cast<gpu::DownloadLayer *>(it.second)) download = d;
     }
+    static const bool traceOn = getenv("FYN_ASYNC_TRACE") != nullptr;
+    TraceEntry te{sequence, {}};
+    auto mark = [&](int k, void *stream) {
+        if (!traceOn) return;
+        FYN_ABI_CALL(fyn_event_create(ctx, &te.ev[k]));
+        FYN_ABI_CALL(fyn_event_record(ctx, te.ev[k], stream));
+    };
+    if (traceOn && !traceBase_) {
+        FYN_ABI_CALL(fyn_event_create(ctx, &traceBase_));
+        FYN_ABI_CALL(fyn_event_record(ctx, traceBase_, sC));
+    }
     // ---- upload: buffer `slot` is free once the layers of sequence-ASYNC_SLOTS have consumed it
+    mark(0, sU);
     if (upload) {
         if (slotUsed_[slot]) FYN_ABI_CALL(fyn_stream_wait_event(ctx, sU, computeDone_[slot]));
         gpu::TensorHandle t = upload->asyncUpload(sequence, slot, sU);
@@ -137,7 +151,9 @@ Engine::execstate Engine::executeAsync(uint64_t sequence) {
         for (auto &rcv : upload->receivers())
             if (auto *g = dynamic_cast<gpu::GPULayerBase *>(rcv.first)) g->updateInputTexture(t, rcv.second);
     }
+    mark(1, sU);
     // ---- layers on the compute stream
+    mark(2, sC);
     for (auto it = layers_.begin(); it != layers_.end(); ++it) {
         LayerBase *layer = it.second;
         if (layer == upload || layer == download) continue;
@@ -150,12 +166,18 @@ Engine::execstate Engine::executeAsync(uint64_t sequence) {
         if (slotUsed_[slot]) FYN_ABI_CALL(fyn_stream_wait_event(ctx, sC, copyDone_[slot]));
         download->asyncConvert(slot, sC);
     }
+    mark(3, sC);
     FYN_ABI_CALL(fyn_event_record(ctx, computeDone_[slot], sC));
     FYN_ABI_CALL(fyn_stream_wait_event(ctx, sD, computeDone_[slot]));
+    mark(4, sD);
     if (download) buffer = download->asyncCopy(sequence, slot, sD);
+    mark(5, sD);
+    if (traceOn) trace_.push_back(te);
     FYN_ABI_CALL(fyn_event_record(ctx, copyDone_[slot], sD));
     completions_[slot] = Completion{this, sequence, buffer};
-    FYN_ABI_CALL(fyn_stream_add_callback(ctx, sD, engineCompletionTrampoline, &completions_[slot]));
+    void *sN = cc->notifyStream();
+    FYN_ABI_CALL(fyn_stream_wait_event(ctx, sN, copyDone_[slot]));
+    FYN_ABI_CALL(fyn_stream_add_callback(ctx, sN, engineCompletionTrampoline, &completions_[slot]));
     slotUsed_[slot] = true;
     return EXEC_DEFERRED;
 }
@@ -220,7 +242,26 @@ Engine::execstate Engine::finish() {
     }
     FYN_ABI_CALL(fyn_stream_sync(context_.handle(), context_.stream()));
     collectTimings(false);
+    if (!trace_.empty()) dumpTrace();
     return EXEC_DONE;
+}
+
+void Engine::dumpTrace() {
+    fyn_ctx *ctx = context_.handle();
+    CudaContext *cc = context_.interface();
+    fyn_stream_sync(ctx, cc->uploadStream());
+    fyn_stream_sync(ctx, cc->downloadStream());
+    fyn_stream_sync(ctx, cc->notifyStream());
+    fprintf(stderr, "[async trace] ms since first sequence: seq | upload begin-end | layers begin-end | host copy begin-end\n");
+    for (TraceEntry &t : trace_) {
+        float v[6] = {};
+        for (int k = 0; k < 6; k++) {
+            fyn_event_elapsed_ms(ctx, traceBase_, t.ev[k], &v[k]);
+            fyn_event_destroy(ctx, t.ev[k]);
+        }
+        fprintf(stderr, "[async trace] %4llu | %8.3f %8.3f | %8.3f %8.3f | %8.3f %8.3f\n", (unsigned long long)t.seq, v[0], v[1], v[2], v[3], v[4], v[5]);
+    }
+    trace_.clear();
 }
 
 // ------------------------------------------------------------------------------------------------
