@@ -1,0 +1,86 @@
+"""Multi-GPU plumbing for the hot path: one process per GPU, torch.distributed for the rendezvous.
+
+The reference is a single-GPU, batch-1 engine (README.md:72); scaling out is therefore either
+  * replicas      -- StyleNet frames <= 1524x1856 and ResNet-50 batch 1: independent requests per GPU, no collective;
+  * batch shards  -- ResNet-50 batch B: contiguous image ranges per rank, weights replicated, one all-gather of the
+                     [B/world, 1000] logits at the end (NCCL on GPUs, gloo in the CPU tests);
+  * row bands     -- StyleNet 4096x4096: horizontal bands with per-layer halo rows (the plan is computed here; the
+                     exchange itself is a later round).
+Only host logic lives here; it never touches the oracle and never falls back to CPU compute.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous [begin, end) of `total` independent units (images, frames) owned by `rank`; sizes differ by at most 1."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, rem = divmod(total, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Step time of the job = the slowest rank (bench.py contract)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_logits(local: np.ndarray, total: int, device=None) -> np.ndarray:
+    """All-gather of the per-rank logits [n_local, classes] into [total, classes] in image order.  Shards may differ
+    by one image (shard_range), so every rank pads to the largest shard before the collective."""
+    import torch
+    import torch.distributed as dist
+    local = np.ascontiguousarray(local, np.float32)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        assert local.shape[0] == total
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = [shard_range(total, r, world) for r in range(world)]
+    nmax = max(e - b for b, e in sizes)
+    assert local.shape[0] == sizes[rank][1] - sizes[rank][0], "local logits do not match this rank's shard"
+    pad = torch.zeros((nmax, local.shape[1]), dtype=torch.float32, device=device)
+    pad[:local.shape[0]] = torch.from_numpy(local).to(pad.device)
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    return np.concatenate([parts[r][:sizes[r][1] - sizes[r][0]].cpu().numpy() for r in range(world)], axis=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# StyleNet row bands: halo rows every layer needs from its band neighbours, at that layer's INPUT
+# resolution, derived from the tap geometry of the reference's shaders (fyusenet/gpu/vanilla/convlayerbase_vanilla.cpp:
+# 347-371, fractionalconvlayerNxN_vanilla.cpp:43-51).
+# ------------------------------------------------------------------------------------------------
+
+def stylenet_halo_plan(ksize: int = 9):
+    """[(layer, input scale divisor, halo rows above, halo rows below)] for a band whose first row is a multiple of 4."""
+    m = (ksize - 1) // 2
+    nres = 5 if ksize == 9 else 2
+    plan = [("conv1", 1, m, m), ("conv2", 1, 1, 0), ("conv3", 2, 1, 0)]
+    for r in range(1, nres + 1):
+        plan += [(f"res{r}_1", 4, 1, 1), (f"res{r}_2", 4, 1, 1)]
+    # fractional convs: source row of tap t for output row o is floor(s*(ds*o + 0.5 + t)), t = ky - m
+    # deconv3 (s = 0.5, ds = 1): output rows 2j and 2j+1 read source rows floor(j + 0.25 + t/2) and floor(j + 0.75 + t/2)
+    above, below = int(np.ceil(m / 2 - 0.25)), int(np.floor(0.75 + m / 2))
+    plan += [("deconv1", 4, 1, 0), ("deconv2", 4, 1, 0), ("deconv3", 2, above, below), ("sigmoid", 1, 0, 0)]
+    return plan
+
+
+def band_rows(height: int, world: int, align: int = 4) -> list[tuple[int, int]]:
+    """Full-resolution row range [begin, end) per rank; every interior boundary is a multiple of `align` so that the /2
+    and /4 levels and the 2x / 4x fractional upsamplers stay on integer rows."""
+    if height % align:
+        raise ValueError(f"height {height} is not a multiple of {align}")
+    units = height // align
+    out = []
+    for r in range(world):
+        b, e = shard_range(units, r, world)
+        out.append((b * align, e * align))
+    return out
