@@ -144,7 +144,7 @@ def run_reference(args, rank, world):
     import fyn_oracle as fo
     fo.lib()
     weights = fo.stylenet_synthetic_weights(KSIZE)
-    cores = os.cpu_count() or 1
+    cores = fo.set_num_threads(os.cpu_count() or 1)      # all host threads (torchrun exports OMP_NUM_THREADS=1)
     _, dt_q, _ = cpu_port_frames_per_s(weights, 464)            # quarter frame: estimates the frame time
     t_frame = 4.0 * dt_q
     rows = HEIGHT
@@ -349,10 +349,12 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             # bounded sample: full frames until ~12 s of CPU work have been spent
+            import fyn_oracle as fo
+            cores = fo.set_num_threads(os.cpu_count() or 1)
             _, dt1, _ = cpu_port_frames_per_s(weights, HEIGHT)
             reps = int(min(12, max(2, round(12.0 / max(dt1, 1e-3)))))
             fps, dt, sample = cpu_port_frames_per_s(weights, HEIGHT, repeats=reps)
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                     "sample": sample + f", {dt * reps:.1f} s total (reference GL path not runnable here: no EGL/Mesa)"}
         print(json.dumps(line), flush=True)
     net.destroy()

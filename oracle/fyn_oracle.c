@@ -597,3 +597,17 @@ void fyo_download_shallow(const float *chw, int C, int H, int W, float fill, flo
                     host[(((size_t)p * H + y) * W + x) * 4 + l] = c < C ? chw[((size_t)c * H + y) * W + x] : fill;
                 }
 }
+
+/* Thread control for the timed CPU baseline (bench.py): launchers such as torchrun export OMP_NUM_THREADS=1. */
+#ifdef _OPENMP
+#include <omp.h>
+int fyo_set_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
+#else
+int fyo_set_threads(int n) {
+    (void)n;
+    return 1;
+}
+#endif

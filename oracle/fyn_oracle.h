@@ -82,4 +82,7 @@ void fyo_download_shallow(const float *chw, int C, int H, int W, float fill, flo
 #ifdef __cplusplus
 }
 #endif
+/* sets (n > 0) and returns the number of OpenMP threads the oracle uses */
+int fyo_set_threads(int n);
+
 #endif

@@ -509,4 +509,10 @@ def resnet50_forward(weights, img_hwc, *, prec=FP32, quirks=QUIRKS_REFERENCE, du
 
 
 def num_threads() -> int:
-    return int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    """OpenMP threads the oracle library currently uses."""
+    return int(lib().fyo_set_threads(0))
+
+
+def set_num_threads(n: int) -> int:
+    """Overrides OMP_NUM_THREADS (torchrun exports 1); returns the thread count in effect."""
+    return int(lib().fyo_set_threads(int(n)))
