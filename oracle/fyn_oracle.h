@@ -78,11 +78,11 @@ int fyo_batchnorm(const float *in_chw, int C, int H, int W, const float *scaleBi
 int fyo_sigmoid(const float *in_chw, size_t n, const fyo_act *act, int prec, float *out_chw);
 void fyo_upload_hwc_to_chw(const float *hwc, int C, int H, int W, float *chw);
 void fyo_download_shallow(const float *chw, int C, int H, int W, float fill, float *host);
+/* sets (n > 0) and returns the number of OpenMP threads the oracle uses */
+int fyo_set_threads(int n);
 
 #ifdef __cplusplus
 }
 #endif
-/* sets (n > 0) and returns the number of OpenMP threads the oracle uses */
-int fyo_set_threads(int n);
 
 #endif
