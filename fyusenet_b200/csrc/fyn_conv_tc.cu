@@ -34,11 +34,11 @@
 // (fractional convs) or four horizontally adjacent pixels (the 3-channel pixel-pair mode), with structural zeros in
 // the weight image where a phase does not use a tap.
 //
-// Warp roles (544 threads): warps 0-7 epilogue (TMEM -> registers -> bias/BN/residual -> fp16 planes; warp w reads
-// TMEM lane quarter w%4 and the 16-column groups w/4, w/4+2), warps 8-15 loaders (groups of 1, 2 or 4 warps on
-// interleaved input rows, so several rows are always in flight), warp 16 issues tcgen05.mma (one elected lane).
-// Pipelines: full/empty mbarriers per ring slot (loader <-> MMA), tmem_full/tmem_empty per accumulator
-// buffer (MMA <-> epilogue, two buffers so the epilogue of row y overlaps the MMAs of row y+1).
+// Warp roles (576 threads): warps 0-7 epilogue (TMEM -> registers -> bias/BN/residual[/sigmoid] -> fp16 planes; the two
+// warps of a TMEM lane quarter split the accumulator columns), warps 8-15 loaders (bulk-copy issue + row finishing in
+// 2 or 4 groups that work on different rows), warps 16-17 issue tcgen05.mma for even / odd jobs (one elected lane each).
+// Pipelines: landed (bulk copy -> loaders), full/empty mbarriers per ring slot (loaders <-> MMA), tmem_full/tmem_empty
+// per accumulator buffer (MMA <-> epilogue, two buffers so the epilogue of job q overlaps the MMAs of job q+1).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -49,6 +49,9 @@
 
 namespace {
 
+#ifndef FYN_TC_WAIT
+#define FYN_TC_WAIT 0   // mbarrier wait flavour: 0 = try_wait with suspend hint, 1 = test_wait polling, 2 = try_wait without hint
+#endif
 #ifdef FYN_TC_PROFILE
 #define PROF_DECL(n) long long n = 0
 #define PROF_T() clock64()
@@ -62,8 +65,9 @@ namespace {
 constexpr int kMaxSteps = 96;
 constexpr int kEpiWarps = 8;                         // two warps per TMEM lane quarter, each takes every other column group
 constexpr int kLoaderWarps = 8;
-constexpr int kMmaWarp = kEpiWarps + kLoaderWarps;
-constexpr int kThreads = (kMmaWarp + 1) * 32;       // 544
+constexpr int kMmaWarp = kEpiWarps + kLoaderWarps;  // first of the two MMA warps (even / odd jobs)
+constexpr int kMmaWarps = 2;
+constexpr int kThreads = (kMmaWarp + kMmaWarps) * 32;   // 576
 constexpr int kFinBatch = 4;                         // items a finishing lane keeps in flight
 constexpr int kMaxItems = 1152;                      // (pixel, chunk) items / pixels of one input row
 constexpr int kMaxStages = 8;                        // staged input rows in flight per CTA (as many as shared memory allows)
@@ -124,6 +128,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // Blocking wait with a large suspend-time hint: the warp sleeps in hardware until the phase completes instead of
 // polling (12 polling warps otherwise compete with the tensor core for shared-memory bandwidth).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#if FYN_TC_WAIT == 1
+    // experiment: poll (no hardware suspend)
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#elif FYN_TC_WAIT == 2
+    // experiment: try_wait without a suspend-time hint
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
@@ -134,6 +151,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "WAIT_DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
+#endif
 }
 // weights: one bulk copy (TMA unit, async proxy) that completes on an mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
@@ -313,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     uint64_t *landed = wbar + 1;               // [nstages] raw row copy has landed            (bulk copies -> loaders)
     uint32_t *tmemBase = reinterpret_cast<uint32_t *>(landed + a.nstages);
 
+    // (MMA warp 0 owns the TMEM allocation)
     // warp index through a broadcast so the compiler treats the role dispatch (and everything derived from it) as
     // warp-uniform
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -334,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nslots; s++) {
             mbar_init(&full[s], 1);              // the leader of the loader group that finished the row
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], kMmaWarps);     // both MMA warps must have retired the row
         }
         for (int s = 0; s < a.nstages; s++) mbar_init(&landed[s], 1);   // one arrive.expect_tx + the bytes of the bulk copies
         mbar_init(&tfull[0], 1);
@@ -544,27 +563,38 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             printf("[tc prof] loader group %d: total %lld waitLanded %lld waitEmpty %lld process %lld publish %lld\n", g, (long long)(clock64() - pLdStart),
                    pLdWait, pFinWaitE, pFinProc, pFinFence);
 #endif
-    } else if (warp == kMmaWarp) {
-        // ===================== MMA issuer =====================
-        // The whole warp runs this loop with warp-uniform values (step table in parameter space, ring position
-        // derived from block-uniform data) so the descriptors are built in uniform registers; one elected lane
-        // waits on the barriers and issues the tcgen05 instructions.
+    } else if (warp >= kMmaWarp) {
+        // ===================== MMA issuers =====================
+        // Two warps: warp w issues jobs w, w + 2, ... into TMEM buffer w, so the per-job bookkeeping of one (barrier
+        // waits, commits, ring arithmetic: ~0.9k cycles, measured) hides behind the other's tcgen05.mma stream.  Each
+        // warp runs its loop with warp-uniform values (step table in parameter space, ring position derived from
+        // block-uniform data) so the descriptors are built in uniform registers; one elected lane waits on the
+        // barriers and issues the tcgen05 instructions.
+        // A ring slot goes back to the loaders when BOTH warps have retired the row (empty barriers count 2): after
+        // its job q a warp releases every row below the window of its next job q + 2 (all remaining rows after its
+        // last job).  Neither warp can run a full ring ahead of the other: a row can only be published into a slot
+        // that both have released.
+        const int mw = warp - kMmaWarp;
         const uint32_t rbase16 = smem_u32(sRing) >> 4, slot16 = (uint32_t)a.slotBytes >> 4;
         const uint32_t bconst = (smem_u32(sW) >> 4) | ((a.b_lbo >> 4) << 16);   // B descriptor low word minus the step offset
         const uint64_t hiA = (uint64_t)((128u >> 4) | (1u << 14)) << 32;          // SBO = 128 B, descriptor version 1
+        const int R = r1 - r0 + 1;
         RingPos win{0, 0};     // ring position of the current window's first row
-        RingPos nxt{0, 0};     // ring position of the first row no job has waited for yet
-        int waited = 0;
-        PROF_DECL(pWaitT); PROF_DECL(pWaitF); PROF_DECL(pIssue); PROF_DECL(pCommit);
+        win.advance(a.rowAdvance * mw, a.nslots);
+        RingPos nxt{0, 0};     // ring position of the first row this warp has not waited for yet
+        RingPos rel{0, 0};     // ring position of the first row this warp has not released yet
+        int waited = 0, released = 0;
+        PROF_DECL(pWaitT); PROF_DECL(pWaitF); PROF_DECL(pIssue); PROF_DECL(pCommit); PROF_DECL(pBlock);
         [[maybe_unused]] const long long pStart = PROF_T();
-        for (int q = 0; q < njobs; q++) {
-            const int buf = q & 1, use = q >> 1;
+        for (int q = mw; q < njobs; q += kMmaWarps) {
+            const int use = q >> 1;
             const int first = a.rowAdvance * q;          // window start relative to r0
-            const int needTo = first + a.nrows;          // rows [waited, needTo) are new for this job
-            const int relTo = (q + 1 < njobs) ? first + a.rowAdvance : r1 - r0 + 1;   // rows [first, relTo) retire with this job
+            const int needTo = first + a.nrows;          // rows [waited, needTo) have not been waited for by this warp
+            const int relTo = (q + kMmaWarps < njobs) ? first + kMmaWarps * a.rowAdvance : R;   // rows [released, relTo) retire now
             if (elect_one()) {
                 [[maybe_unused]] long long pt = PROF_T();
-                mbar_wait(&tempty[buf], (use & 1) ^ 1);
+                [[maybe_unused]] const long long ptB = pt;
+                mbar_wait(&tempty[mw], (use & 1) ^ 1);
                 PROF_ADD(pWaitT, pt);
                 pt = PROF_T();
                 RingPos w = nxt;
@@ -572,11 +602,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                     mbar_wait(&full[w.slot], w.fill & 1);
                     w.advance(1, a.nslots);
                 }
-                if (q == 0) mbar_wait(wbar, 0);       // weight image
+                if (q == mw) mbar_wait(wbar, 0);       // weight image
                 PROF_ADD(pWaitF, pt);
                 pt = PROF_T();
                 tc_fence_after();
-                const uint32_t d = tmem + (uint32_t)buf * 64u;
+                const uint32_t d = tmem + (uint32_t)mw * 64u;
                 const uint32_t winBase = rbase16 + (uint32_t)win.slot * slot16;
 #pragma unroll 4
                 for (int s = 0; s < a.nsteps; s++) {
@@ -585,26 +615,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                 }
                 PROF_ADD(pIssue, pt);
                 pt = PROF_T();
-                umma_commit(&tfull[buf]);
-                // rows that no later job needs go back to the loaders
-                RingPos rp = win;
-                for (int i = first; i < relTo; i++) {
+                umma_commit(&tfull[mw]);
+                RingPos rp = rel;
+                for (int i = released; i < relTo; i++) {
                     umma_commit(&empty[rp.slot]);
                     rp.advance(1, a.nslots);
                 }
                 PROF_ADD(pCommit, pt);
+                PROF_ADD(pBlock, ptB);
             }
             if (needTo > waited) {
                 nxt.advance(needTo - waited, a.nslots);
                 waited = needTo;
             }
-            win.advance(a.rowAdvance, a.nslots);
+            if (relTo > released) {
+                rel.advance(relTo - released, a.nslots);
+                released = relTo;
+            }
+            win.advance(kMmaWarps * a.rowAdvance, a.nslots);
             __syncwarp();
         }
+        // a warp without jobs (single-job strips) still owes its share of every release: R <= nslots then, no slot is reused
+        if (mw >= njobs && elect_one())
+            for (int i = 0; i < R; i++) mbar_arrive(&empty[i % a.nslots]);
 #ifdef FYN_TC_PROFILE
         if (blockIdx.x == 0 && elect_one())
-            printf("[tc prof] mma: jobs %d steps %d total %lld waitTempty %lld waitFull %lld issue %lld commit %lld (cycles)\n", njobs, a.nsteps,
-                   (long long)(clock64() - pStart), pWaitT, pWaitF, pIssue, pCommit);
+            printf("[tc prof] mma %d: jobs %d steps %d total %lld waitTempty %lld waitFull %lld issue %lld commit %lld electedBlock %lld (cycles)\n", mw, njobs, a.nsteps,
+                   (long long)(clock64() - pStart), pWaitT, pWaitF, pIssue, pCommit, pBlock);
 #endif
     } else {
         // ===================== epilogue: warps 0-7 =====================
@@ -989,6 +1026,7 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     a.x_lead = g.x_lead;
     a.nslots = g.nslots;
     a.nsteps = g.nsteps;
+    if (const char *e = getenv("FYN_TC_DEBUG_STEPS")) a.nsteps = std::max(1, std::min(g.nsteps, atoi(e)));   // ablation: wrong results, timing only
     a.stageBytes = g.stageBytes;
     a.nstages = g.nstages;
     a.finGroups = g.finGroups;
