@@ -53,12 +53,15 @@ namespace {
 #define FYN_TC_WAIT 0   // mbarrier wait flavour: 0 = try_wait with suspend hint, 1 = test_wait polling, 2 = try_wait without hint
 #endif
 #ifdef FYN_TC_PROFILE
+__device__ long long g_trace[4][64][2];   // [role: 0 loader publish, 1 mma issue begin/end, 2 epilogue begin/end][index][begin, end]
+#define TRACE(role, idx, which) do { if (blockIdx.x == 0 && (idx) < 64) g_trace[role][idx][which] = clock64() - pK0; } while (0)
 #define PROF_DECL(n) long long n = 0
 #define PROF_T() clock64()
 #define PROF_ADD(acc, t0) acc += clock64() - (t0)
 #else
 #define PROF_DECL(n)
 #define PROF_T() 0
+#define TRACE(role, idx, which)
 #define PROF_ADD(acc, t0)
 #endif
 
@@ -111,6 +114,7 @@ struct TcArgs {
     ActParams act;
     int hasRes, reluRes, bnRes;
     int epilogue;            // FYN_EPILOGUE_*: element-wise function fused behind the convolution
+    int debug;               // FYN_TC_DEBUG bits (timing ablations only): 1 = epilogue without global stores
     int batch;
 };
 
@@ -312,8 +316,9 @@ struct RingPos {
 // the ring of row slots is a FIFO.  The first nrows-1 slots are mirrored behind the ring so that every window is
 // contiguous in shared memory and the A descriptor of a step is (window base + constant).
 // MODE: 0 plane-pair chunks, 1 pixel-pair chunks.  ACT: see act_h8_t.  RES: 0 no residual, 1 fp16 shallow residual of a
-// single-phase layer (prefetched), 2 any other residual tensor (generic fetch).
-template <int MODE, int ACT, int RES>
+// single-phase layer (prefetched), 2 any other residual tensor (generic fetch).  EPI: FYN_EPILOGUE_* function fused behind
+// the convolution (instantiated for RES == 0 only; other combinations run on the direct kernel).
+template <int MODE, int ACT, int RES, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sW = smem;
@@ -462,6 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             [[maybe_unused]] long long pt = PROF_T();
             mbar_wait(&landed[st], use & 1);
             PROF_ADD(pLdWait, pt);
+            if (tg == 0) TRACE(0, r, 0);
             pt = PROF_T();
             mbar_wait(&empty[slotIdx], (fill & 1) ^ 1);
             PROF_ADD(pFinWaitE, pt);
@@ -553,7 +559,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             fence_proxy_async();
             asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(groupThreads) : "memory");
             if (leader) {
-                if (tg == 0) mbar_arrive(&full[slotIdx]);
+                if (tg == 0) {
+                    mbar_arrive(&full[slotIdx]);
+                    TRACE(0, r, 1);
+                }
                 if (r + a.nstages < R) issue_row(r + a.nstages);
             }
             PROF_ADD(pFinFence, pt);
@@ -606,6 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                 PROF_ADD(pWaitF, pt);
                 pt = PROF_T();
                 tc_fence_after();
+                TRACE(1, q, 0);
                 const uint32_t d = tmem + (uint32_t)mw * 64u;
                 const uint32_t winBase = rbase16 + (uint32_t)win.slot * slot16;
 #pragma unroll 4
@@ -614,6 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                     umma_f16(d, hiA | (uint64_t)(st.a_lo + winBase), hiA | (uint64_t)(st.b_off16 + bconst), a.idesc, st.accumulate);
                 }
                 PROF_ADD(pIssue, pt);
+                TRACE(1, q, 1);
                 pt = PROF_T();
                 umma_commit(&tfull[mw]);
                 RingPos rp = rel;
@@ -681,6 +692,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             const int buf = q & 1, use = q >> 1;
             const int i = ja + q;                    // job row
             // residual texels are fetched before waiting for the accumulator so their latency hides behind the MMAs
+            // (requesting the next job's texels one iteration ahead was measured slower: 18.2 vs 17.3 us on res+residual)
             uint2 rres[4][2];
             if (RES == 1) {
                 const __half *rp = resp + (long long)i * a.res.texW * 4;
@@ -693,6 +705,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             [[maybe_unused]] const long long pt = PROF_T();
             mbar_wait(&tfull[buf], use & 1);
             PROF_ADD(pEpWait, pt);
+            if (threadIdx.x == 0) TRACE(2, q, 0);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * 64u + (uint32_t)(chalf * nOct) * 8u;
             uint32_t acc[4][8];
@@ -735,7 +748,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                             v.w += rs.w;
                         }
                         t[k] = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
-                        if (a.epilogue == FYN_EPILOGUE_SIGMOID) {
+                        if (EPI == FYN_EPILOGUE_SIGMOID) {
                             // fused FunctionLayer, evaluated on the fp16-rounded convolution result like the unfused pair
                             const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&t[k].x));
                             const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&t[k].y));
@@ -743,6 +756,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                         }
                     }
                 }
+                if ((a.debug & 1) && t[0].x != 0x7fff7fffu) continue;   // ablation: no stores (never true for real data paths)
                 // with phases along x the two texels are adjacent in memory: one 16-byte store where alignment allows
                 if (wide) {
                     if (poff[o][0] >= 0) *reinterpret_cast<uint4 *>(orow + poff[o][0]) = make_uint4(t[0].x, t[0].y, t[1].x, t[1].y);
@@ -751,6 +765,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                     if (poff[o][1] >= 0) *reinterpret_cast<uint2 *>(orow + poff[o][1]) = t[1];
                 }
             }
+            if (threadIdx.x == 0) TRACE(2, q, 1);
         }
 #ifdef FYN_TC_PROFILE
         if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -763,6 +778,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
 #ifdef FYN_TC_PROFILE
     if (blockIdx.x == 0 && threadIdx.x == 0)
         printf("[tc prof] kernel: prologue %lld depwait %lld body %lld (cycles), grid %d\n", pK1 - pK0, pK2 - pK1, (long long)(clock64() - pK2), (int)gridDim.x);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {   // event trace of block 0 (cycles since kernel start)
+        const int R = r1 - r0 + 1;
+        for (int r = 0; r < R && r < 64; r++) printf("[tc trace] row %2d landed %6lld published %6lld\n", r, g_trace[0][r][0], g_trace[0][r][1]);
+        for (int q = 0; q < njobs && q < 64; q++)
+            printf("[tc trace] job %2d mma issue %6lld - %6lld   epilogue %6lld - %6lld\n", q, g_trace[1][q][0], g_trace[1][q][1], g_trace[2][q][0], g_trace[2][q][1]);
+    }
 #endif
 }
 
@@ -971,23 +992,25 @@ namespace {
 
 using TcKernel = void (*)(TcArgs);
 
-// kernel instantiations: [mode][act][res]
-TcKernel tc_kernel(int mode, int act, int res) {
+// kernel instantiations: [mode][act][res] without fused function, [mode][act] with the fused sigmoid (no residual)
+TcKernel tc_kernel(int mode, int act, int res, int epi) {
     static const TcKernel table[2][3][3] = {
-        {{k_conv_tc<0, 0, 0>, k_conv_tc<0, 0, 1>, k_conv_tc<0, 0, 2>},
-         {k_conv_tc<0, 1, 0>, k_conv_tc<0, 1, 1>, k_conv_tc<0, 1, 2>},
-         {k_conv_tc<0, 2, 0>, k_conv_tc<0, 2, 1>, k_conv_tc<0, 2, 2>}},
-        {{k_conv_tc<1, 0, 0>, k_conv_tc<1, 0, 2>, k_conv_tc<1, 0, 2>},
-         {k_conv_tc<1, 1, 0>, k_conv_tc<1, 1, 2>, k_conv_tc<1, 1, 2>},
-         {k_conv_tc<1, 2, 0>, k_conv_tc<1, 2, 2>, k_conv_tc<1, 2, 2>}}};
-    return table[mode][act][res];
+        {{k_conv_tc<0, 0, 0, 0>, k_conv_tc<0, 0, 1, 0>, k_conv_tc<0, 0, 2, 0>},
+         {k_conv_tc<0, 1, 0, 0>, k_conv_tc<0, 1, 1, 0>, k_conv_tc<0, 1, 2, 0>},
+         {k_conv_tc<0, 2, 0, 0>, k_conv_tc<0, 2, 1, 0>, k_conv_tc<0, 2, 2, 0>}},
+        {{k_conv_tc<1, 0, 0, 0>, k_conv_tc<1, 0, 2, 0>, k_conv_tc<1, 0, 2, 0>},
+         {k_conv_tc<1, 1, 0, 0>, k_conv_tc<1, 1, 2, 0>, k_conv_tc<1, 1, 2, 0>},
+         {k_conv_tc<1, 2, 0, 0>, k_conv_tc<1, 2, 2, 0>, k_conv_tc<1, 2, 2, 0>}}};
+    static const TcKernel sig[2][3] = {{k_conv_tc<0, 0, 0, 1>, k_conv_tc<0, 1, 0, 1>, k_conv_tc<0, 2, 0, 1>},
+                                       {k_conv_tc<1, 0, 0, 1>, k_conv_tc<1, 1, 0, 1>, k_conv_tc<1, 2, 0, 1>}};
+    return epi ? sig[mode][act] : table[mode][act][res];
 }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per function and device, not per launch: keep it at the largest
 // footprint any plan has needed so far
-int tc_ensure_smem(TcKernel fn, int mode, int act, int res, int device, size_t bytes) {
-    static size_t cur[64][2][3][3] = {};
-    size_t &c = cur[device & 63][mode][act][res];
+int tc_ensure_smem(TcKernel fn, int mode, int act, int res, int epi, int device, size_t bytes) {
+    static size_t cur[64][2][3][4] = {};
+    size_t &c = cur[device & 63][mode][act][epi ? 3 : res];
     if (bytes > c) {
         FYN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         c = bytes;
@@ -1143,6 +1166,7 @@ int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn
     a.reluRes = (d.flags & FYN_FLAG_RELU_ON_RESIDUAL) != 0;
     a.bnRes = (d.flags & FYN_FLAG_BATCHNORM_ON_RESIDUAL) != 0;
     a.epilogue = op->epilogue;
+    if (const char *e = getenv("FYN_TC_DEBUG")) a.debug = atoi(e);
     a.batch = in->desc.batch;
     a.nxs = (a.Wj + kTileM - 1) / kTileM;
     // strip height: one strip per SM (the kernel's register / shared-memory footprint allows one CTA per SM),
@@ -1157,8 +1181,9 @@ int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn
     const int actSel = a.act.type == 0 ? 0 : (a.act.type == 1 ? 1 : 2);
     int resSel = 0;
     if (a.hasRes) resSel = (a.mode == 0 && a.opx == 1 && a.opy == 1 && res->desc.dtype == FYN_F16 && res->geom.packing == 4 && res->desc.order == FYN_ORDER_SHALLOW) ? 1 : 2;
-    TcKernel fn = tc_kernel(a.mode, actSel, resSel);
-    if (int rc = tc_ensure_smem(fn, a.mode, actSel, resSel, op->ctx->device, plan->smemBytes)) return rc;
+    if (op->epilogue != FYN_EPILOGUE_NONE && resSel != 0) return 1;   // fused function + residual: direct kernel
+    TcKernel fn = tc_kernel(a.mode, actSel, resSel, op->epilogue);
+    if (int rc = tc_ensure_smem(fn, a.mode, actSel, resSel, op->epilogue, op->ctx->device, plan->smemBytes)) return rc;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)blocks);
     cfg.blockDim = dim3(kThreads);

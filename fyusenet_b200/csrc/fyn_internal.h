@@ -133,7 +133,9 @@ __device__ __forceinline__ float fyn_act(float v, const ActParams &a) {
 }
 
 // shaders/sigmoid.frag:10-13
-__device__ __forceinline__ float fyn_sigmoid(float v) { return 1.f / (1.f + __expf(-v)); }
+// (fast reciprocal: 2 ulp in fp32, far below the fp16 / 1e-5 parity tolerances; shared by the sigmoid layer and the
+// fused conv epilogue so that both give identical values)
+__device__ __forceinline__ float fyn_sigmoid(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 __device__ __forceinline__ float fyn_round_half(float v) { return __half2float(__float2half_rn(v)); }
 
 __device__ __forceinline__ float4 fyn_act4(float4 v, const ActParams &a) {
