@@ -16,6 +16,7 @@ import sys
 from pathlib import Path
 
 launches, rep, bench, tag = sys.argv[1:5]
+layer_override = sys.argv[5] if len(sys.argv) > 5 else None      # capture of a layer other than the bench's dominant one
 out = Path(__file__).resolve().parent.parent / "profiles"
 shutil.copy(launches, out / f"{tag}_launches.csv")
 
@@ -24,17 +25,19 @@ hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 idx = {n: i for i, n in enumerate(rows[hi])}
 data = [(r[idx["Kernel Name"]], float(r[idx["Metric Value"]]) / 1e3, r[idx["Grid Size"]]) for r in rows[hi + 1:] if len(r) > idx["Metric Value"]]
 b = json.load(open(bench))
-names = list(b["layers_ms"].keys())                       # conv1 ... sigmoid, in execution order
-n = len(names)
-# the device-resident arm runs first: its forwards are consecutive groups of n launches
+# one forward = the launches between two occurrences of the first kernel (conv1); layers that launch nothing (a sigmoid
+# fused into its producer) are dropped from the bench's layer list by their ~0 event time
+period = next(i for i in range(1, len(data)) if data[i][0] == data[0][0] and data[i][2] == data[0][2])
+names = [k for k, v in b["layers_ms"].items() if v > 0.005]
+n = period
+assert len(names) == n, f"{len(names)} timed layers vs {n} launches per forward"
 fw = [data[i * n:(i + 1) * n] for i in range(len(data) // n)]
-first = next(k for k, g in enumerate(fw) if all("k_conv_tc" in x[0] for x in g[:-1]) and "eltwise" in g[-1][0])
-use = fw[first + 1:first + 4]                             # skip the very first forward (cold instruction caches)
+use = [g for g in fw[1:4] if g[0][0] == data[0][0]]       # skip the very first forward (cold instruction caches)
 avg = [sum(g[i][1] for g in use) / len(use) for i in range(n)]
-tot_ncu, tot_ev = sum(avg), sum(b["layers_ms"].values()) * 1e3
+tot_ncu, tot_ev = sum(avg), sum(b["layers_ms"][k] for k in names) * 1e3
 lines = [f"# {tag}: kernel launches of one StyleNet-9x9 1524x1856 forward", "",
          "`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py --steps 2 --warmup 3` (cold cache, serialised),",
-         f"mean of {len(use)} forwards, beside the per-layer CUDA-event times of the bench run (`{Path(bench).name}`, includes launch gaps).", "",
+         f"mean of {len(use)} forwards, beside the per-layer CUDA-event times of the bench run (`{Path(bench).name}`; an event pair per layer adds\n~5 us and breaks the dependent-launch overlap, which is why the frame time below is smaller than the event sum).", "",
          "| layer | kernel | grid | ncu us | ncu share | event us | event share |", "|---|---|---|---:|---:|---:|---:|"]
 for i, nm in enumerate(names):
     k = use[0][i][0].replace("void <unnamed>::", "").replace("(<unnamed>::TcArgs)", "")
@@ -58,9 +61,10 @@ for i, name in enumerate(h):
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 traffic = sum(m[k]["value"] * scale[m[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
 kname = v[h.index("Kernel Name")] if "Kernel Name" in h else ""
-summary = {"kernel": kname, "layer": b["roofline"]["kernel"], "report": Path(rep).name, "traffic_bytes_per_launch": traffic, "metrics": m,
+summary = {"kernel": kname, "layer": layer_override or b["roofline"]["kernel"], "report": Path(rep).name, "traffic_bytes_per_launch": traffic, "metrics": m,
            "note": "one launch, ncu --set full --clock-control none; DRAM writes are below the algorithmic output bytes because the 126 MB L2 "
-                   "absorbs the 68 MB output (written back after the kernel)"}
-(out / f"{tag}_top_kernel_ncu.json").write_text(json.dumps(summary, indent=1) + "\n")
+                   "absorbs most of the output (written back after the kernel)"}
+name = f"{tag}_top_kernel_ncu.json" if not layer_override else f"{tag}_{layer_override}_kernel_ncu.json"
+(out / name).write_text(json.dumps(summary, indent=1) + "\n")
 print((out / f"{tag}_launches_summary.md").read_text())
 print(json.dumps(summary)[:600])
