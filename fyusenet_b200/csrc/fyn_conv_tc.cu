@@ -114,6 +114,8 @@ struct TcArgs {
     ActParams act;
     int hasRes, reluRes, bnRes;
     int epilogue;            // FYN_EPILOGUE_*: element-wise function fused behind the convolution
+    int biasFolded;          // 1: the bias enters the accumulator as one more MMA step (A = ones region behind the weight image)
+    uint32_t biasB16, onesOff;   // weight-image offsets: bias step (>> 4) and the ones region (bytes)
     int debug;               // FYN_TC_DEBUG bits (timing ablations only): 1 = epilogue without global stores
     int batch;
 };
@@ -587,6 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         const uint32_t rbase16 = smem_u32(sRing) >> 4, slot16 = (uint32_t)a.slotBytes >> 4;
         const uint32_t bconst = (smem_u32(sW) >> 4) | ((a.b_lbo >> 4) << 16);   // B descriptor low word minus the step offset
         const uint64_t hiA = (uint64_t)((128u >> 4) | (1u << 14)) << 32;          // SBO = 128 B, descriptor version 1
+        const uint32_t onesDesc = ((smem_u32(sW) + a.onesOff) >> 4) | ((16u >> 4) << 16);   // second K chunk = next row (zero weights)
         const int R = r1 - r0 + 1;
         RingPos win{0, 0};     // ring position of the current window's first row
         win.advance(a.rowAdvance * mw, a.nslots);
@@ -623,6 +626,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                     const TcStep st = a.steps[s];
                     umma_f16(d, hiA | (uint64_t)(st.a_lo + winBase), hiA | (uint64_t)(st.b_off16 + bconst), a.idesc, st.accumulate);
                 }
+                // folded bias: A = rows of (1, 1, 0, ...), B = (bias_hi, bias_lo, 0, ...) per output column
+                if (a.biasFolded) umma_f16(d, hiA | (uint64_t)onesDesc, hiA | (uint64_t)(a.biasB16 + bconst), a.idesc, 1u);
                 PROF_ADD(pIssue, pt);
                 TRACE(1, q, 1);
                 pt = PROF_T();
@@ -726,9 +731,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                     t[k] = make_uint2(0u, 0u);
                     if (poff[o][k] >= 0) {
                         const int p = pidx[o][k];
-                        const float4 bi = sEpi[p], sc = sEpi[16 + p];
-                        float4 v = make_float4(fmaf(__uint_as_float(acc[o][4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[o][4 * k + 1]), sc.y, bi.y),
-                                               fmaf(__uint_as_float(acc[o][4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[o][4 * k + 3]), sc.w, bi.w));
+                        float4 v = make_float4(__uint_as_float(acc[o][4 * k + 0]), __uint_as_float(acc[o][4 * k + 1]), __uint_as_float(acc[o][4 * k + 2]),
+                                               __uint_as_float(acc[o][4 * k + 3]));
+                        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+                        if (!a.biasFolded) {               // post-BN scale (or long step tables): bias and scale from shared memory
+                            const float4 bi = sEpi[p];
+                            sc = sEpi[16 + p];
+                            v = make_float4(fmaf(v.x, sc.x, bi.x), fmaf(v.y, sc.y, bi.y), fmaf(v.z, sc.z, bi.z), fmaf(v.w, sc.w, bi.w));
+                        }
                         if (RES != 0) {
                             float4 rs;
                             if (RES == 1) {
@@ -813,6 +823,7 @@ struct Geometry {
     int mode = 0, opx = 1, opy = 1, rowAdvance = 1, nver = 1, N = 16, Cq = 4, nchunks = 1, rowpx = 0, x_lead = 0, ds = 1;
     int dxMin = 0, dxMax = 0, dyMin = 0, dyMax = 0;
     int nslots = 0, slotBytes = 0, verBytes = 0, nsteps = 0, stageBytes = 0, nstages = 0, nitems = 0, finGroups = 2;
+    bool biasFold = false;
     size_t wbytes = 0, smem = 0;
     std::vector<Position> pos;
     bool ok = false;
@@ -962,6 +973,11 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb) {
     g.nsteps = nsteps;
     if (nsteps > kMaxSteps) return g;
     g.wbytes = (size_t)nsteps * 2 * g.N * 16;
+    // Folded bias (layers without post-BN scale whose epilogue, not the MMA stream, is the busy role -- short step
+    // tables): one more MMA step adds the bias to the accumulator, so the epilogue only converts and stores.  The
+    // weight image grows by the step's B chunks and by the A operand of that step, 130 rows of (1, 1, 0, ..., 0).
+    g.biasFold = !(d->flags & FYN_FLAG_POST_BATCHNORM) && nsteps <= 24;
+    if (g.biasFold) g.wbytes += (size_t)2 * g.N * 16 + 130 * 16;
     // Loader groups, ring slots and staged rows.  The ring holds the window, the rows the next job adds and one more
     // job's worth of slack, rounded up to a multiple of the group count G (slot and stage ownership, see the kernel).
     // Measured on B200 (StyleNet layers, 1524x1856): rows finished concurrently matter more than staged rows per
@@ -1110,6 +1126,23 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
         }
     }
     if (s != g.nsteps) FYN_FAIL(FYN_ERR_INVALID, "tcgen05 conv: internal step count mismatch (%d vs %d)", s, g.nsteps);
+    a.biasFolded = g.biasFold ? 1 : 0;
+    if (g.biasFold) {
+        // bias step: B chunk 0 holds (hi, lo) halves of the fp32 bias in k = 0, 1 for every phase's column, chunk 1 is zero
+        const size_t stepBase = (size_t)g.nsteps * 2 * N * 8;           // in halves
+        a.biasB16 = (uint32_t)((stepBase * 2) >> 4);
+        for (int ph = 0; ph < nphase; ph++)
+            for (int o = 0; o < Co; o++) {
+                const int fy = ph / g.opx, fx = ph % g.opx, ppp = g.Cq / 4;
+                const size_t col = (((size_t)fy * ppp + o / 4) * g.opx + fx) * 4 + (o & 3);
+                const __half hi = __float2half_rn(wb[o]);
+                img[stepBase + col * 8 + 0] = hi;
+                img[stepBase + col * 8 + 1] = __float2half_rn(wb[o] - __half2float(hi));
+            }
+        const size_t onesBase = stepBase + (size_t)2 * N * 8;
+        a.onesOff = (uint32_t)(onesBase * 2);
+        for (int r = 0; r < 130; r++) img[onesBase + (size_t)r * 8 + 0] = img[onesBase + (size_t)r * 8 + 1] = __float2half(1.f);
+    }
 
     FYN_CUDA(cudaSetDevice(op->ctx->device));
     if (!plan->d_wimg) FYN_CUDA(cudaMalloc((void **)&plan->d_wimg, g.wbytes));
