@@ -841,7 +841,9 @@ Position &find_pos(std::vector<Position> &pos, int ver, int dy, int dx, size_t w
 }
 
 // Builds the positions (and stacked, merged weights when wb is given) and the shared-memory geometry.
-Geometry plan_geometry(const fyn_conv_desc *d, const float *wb) {
+// `ys` = output job rows stacked along N (1 or 2): fewer, fatter jobs amortise the per-job costs of every role
+// (barrier hand-overs, commits, epilogue set-up) and reuse the window rows the stacked outputs share.
+Geometry plan_geometry(const fyn_conv_desc *d, const float *wb, int ys) {
     Geometry g;
     if (d->flags & FYN_FLAG_DEEP) return g;          // deep-tiled family: not yet
     if (d->dilation != 1) return g;
@@ -867,13 +869,14 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb) {
             tapx[2] = 0;
         }
         const bool actFirstOnly = hasAct && (d->quirks & FYN_QUIRK_FRAC_ACT_FIRST);
-        g.opx = g.opy = p;
-        g.rowAdvance = 1;
+        g.opx = p;
+        g.opy = p * ys;                               // p output rows per source row, ys source rows per job
+        g.rowAdvance = ys;
         g.nver = actFirstOnly ? 2 : 1;
         g.ds = 1;
         g.mode = 0;
-        const size_t wsize = (size_t)p * p * g.Cq * Ci;
-        for (int fy = 0; fy < p; fy++)
+        const size_t wsize = (size_t)g.opy * p * g.Cq * Ci;
+        for (int fy = 0; fy < g.opy; fy++)
             for (int fx = 0; fx < p; fx++)
                 for (int ky = 0; ky < K; ky++)
                     for (int kx = 0; kx < K; kx++) {
@@ -894,39 +897,44 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb) {
         // chunk offset e relative to chunk 2*j; element (half h, channel c) of chunk e belongs to tap kx = 2e + h - fx + mh.
         g.mode = 1;
         g.opx = 4;
-        g.opy = 1;
-        g.rowAdvance = 1;
+        g.opy = ys;
+        g.rowAdvance = ys;
         g.ds = 1;
-        const size_t wsize = (size_t)4 * g.Cq * 8;    // [phase][co][8 chunk elements]
+        const size_t wsize = (size_t)ys * 4 * g.Cq * 8;    // [phase][co][8 chunk elements]
         int e0 = floordiv2(-mh);
         if (e0 & 1) e0 -= 1;   // the slot starts on an even chunk so that chunk parity == (e - e0) parity; extra chunk has zero weights
-        for (int ky = 0; ky < K; ky++)
-            for (int e = e0; e <= floordiv2(3 + K - 1 - mh); e++) {
-                Position &q = find_pos(g.pos, 0, ky - mh, e, wsize, wb != nullptr);
-                if (wb)
-                    for (int fx = 0; fx < 4; fx++)
-                        for (int o = 0; o < Co; o++)
-                            for (int h = 0; h < 2; h++)
-                                for (int c = 0; c < Ci; c++) {
-                                    const int kx = 2 * e + h - fx + mh;
-                                    if (kx >= 0 && kx < K) q.w[((size_t)fx * g.Cq + o) * 8 + h * 4 + c] = W[(((size_t)o * K + ky) * K + kx) * Ci + c];
-                                }
-            }
+        for (int fy = 0; fy < ys; fy++)
+            for (int ky = 0; ky < K; ky++)
+                for (int e = e0; e <= floordiv2(3 + K - 1 - mh); e++) {
+                    Position &q = find_pos(g.pos, 0, fy + ky - mh, e, wsize, wb != nullptr);
+                    if (wb)
+                        for (int fx = 0; fx < 4; fx++)
+                            for (int o = 0; o < Co; o++)
+                                for (int h = 0; h < 2; h++)
+                                    for (int c = 0; c < Ci; c++) {
+                                        const int kx = 2 * e + h - fx + mh;
+                                        if (kx >= 0 && kx < K)
+                                            q.w[((size_t)(fy * 4 + fx) * g.Cq + o) * 8 + h * 4 + c] = W[(((size_t)o * K + ky) * K + kx) * Ci + c];
+                                    }
+                }
     } else {
         if (d->downsample != 1 && d->downsample != 2) return g;
         if (K < 3 || Ci < 8) return g;
         g.mode = 0;
-        g.opx = g.opy = 1;
-        g.rowAdvance = d->downsample;
+        g.opx = 1;
+        g.opy = ys;
+        g.rowAdvance = ys * d->downsample;
         g.ds = d->downsample;
-        const size_t wsize = (size_t)g.Cq * Ci;
-        for (int ky = 0; ky < K; ky++)
-            for (int kx = 0; kx < K; kx++) {
-                Position &q = find_pos(g.pos, 0, ky - mh, kx - mh, wsize, wb != nullptr);
-                if (wb)
-                    for (int o = 0; o < Co; o++)
-                        for (int c = 0; c < Ci; c++) q.w[(size_t)o * Ci + c] = W[(((size_t)o * K + ky) * K + kx) * Ci + c];
-            }
+        const size_t wsize = (size_t)ys * g.Cq * Ci;
+        for (int fy = 0; fy < ys; fy++)
+            for (int ky = 0; ky < K; ky++)
+                for (int kx = 0; kx < K; kx++) {
+                    // output row ys*i + fy reads input rows ds*(ys*i + fy) + ky - mh: window row fy*ds + ky - mh
+                    Position &q = find_pos(g.pos, 0, fy * d->downsample + ky - mh, kx - mh, wsize, wb != nullptr);
+                    if (wb)
+                        for (int o = 0; o < Co; o++)
+                            for (int c = 0; c < Ci; c++) q.w[((size_t)fy * g.Cq + o) * Ci + c] = W[(((size_t)o * K + ky) * K + kx) * Ci + c];
+                }
     }
     const int ntot = g.opx * g.opy * g.Cq;
     g.N = ((ntot + 15) / 16) * 16;
@@ -1036,11 +1044,19 @@ int tc_ensure_smem(TcKernel fn, int mode, int act, int res, int epi, int device,
 
 }  // namespace
 
-int fyn_conv_tc_supported(const fyn_conv_desc *d, int) { return plan_geometry(d, nullptr).ok ? 1 : 0; }
+int fyn_conv_tc_supported(const fyn_conv_desc *d, int) { return plan_geometry(d, nullptr, 1).ok ? 1 : 0; }
 
 int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     const fyn_conv_desc &d = op->conv;
-    Geometry g = plan_geometry(&d, wb);
+    // Two job rows stacked along N when the output height allows it and the plan fits (N <= 64, shared memory) without
+    // giving up loader groups -- measured on StyleNet 9x9 @1524x1856: deconv3 40.1 -> 30.7 us, deconv1 10.9 -> 9.9 us, but
+    // conv2, whose stacked plan only fits with two loader groups, 34.4 -> 44.8 us.
+    Geometry g = plan_geometry(&d, wb, 1);
+    {
+        Geometry g2 = plan_geometry(&d, wb, 2);
+        if (const char *e = getenv("FYN_TC_STACK")) { if (atoi(e) < 2) g2.ok = false; }   // tuning knob
+        if (g2.ok && op->Ho % g2.opy == 0 && (!g.ok || g2.finGroups >= g.finGroups)) g = g2;
+    }
     if (!g.ok) FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 family does not cover this conv");
     ConvTcPlan *plan = op->tc ? op->tc : new ConvTcPlan();
     op->tc = plan;
