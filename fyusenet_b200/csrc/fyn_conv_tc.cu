@@ -88,7 +88,6 @@ struct __align__(16) TcStep {
 struct TcArgs {
     TView in, out, res;
     const uint4 *wimg;
-    const float *bias, *scale;   // [16 planes] float4 each, indexed by output plane
     uint32_t wbytes, idesc, b_lbo;
     int nsteps;              // MMA steps per job
     int stageBytes;          // bytes of one staged input row (all planes)
@@ -116,6 +115,7 @@ struct TcArgs {
     int epilogue;            // FYN_EPILOGUE_*: element-wise function fused behind the convolution
     int biasFolded;          // 1: the bias enters the accumulator as one more MMA step (A = ones region behind the weight image)
     uint32_t biasB16, onesOff;   // weight-image offsets: bias step (>> 4) and the ones region (bytes)
+    uint32_t epiOff;             // weight-image offset of the epilogue parameters ([16] bias float4, [16] scale float4)
     int debug;               // FYN_TC_DEBUG bits (timing ablations only): 1 = epilogue without global stores
     int batch;
 };
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     unsigned char *sW = smem;
     unsigned char *sRing = smem + ((a.wbytes + 127) & ~127u);
     unsigned char *sStage = sRing + (size_t)(a.nslots + a.nrows - 1) * a.slotBytes;                       // [nstages] raw input rows
-    float4 *sEpi = reinterpret_cast<float4 *>(sStage + (size_t)a.nstages * a.stageBytes);                 // [16] bias, [16] scale
+    float4 *sEpi = reinterpret_cast<float4 *>(sStage + (size_t)a.nstages * a.stageBytes);                 // [16] bias, [16] scale (copied from the weight image's tail)
     int2 *sTab = reinterpret_cast<int2 *>(sEpi + 32);                                                     // [nitems] row item table
     uint64_t *sZero = reinterpret_cast<uint64_t *>(sTab + a.nitems);                                      // 16 zero bytes (missing second plane)
     uint64_t *bars = sZero + 2;
@@ -374,8 +374,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         bulk_g2s(sW, a.wimg, a.wbytes, wbar);
     }
     if (warp == kMmaWarp) tmem_alloc(tmemBase, 128);
-    for (int i = threadIdx.x; i < 32; i += kThreads)
-        sEpi[i] = __ldg(reinterpret_cast<const float4 *>(i < 16 ? a.bias : a.scale) + (i & 15));
     // Row geometry (independent of the row): the texel run [xa, xz] of a texture row that this strip reads, and per
     // item the byte offset inside the staged row and inside the ring slot.
     const int esize = (a.in.dtype == FYN_F16) ? 2 : 4, bpp = a.in.packing * esize;   // bytes per texel
@@ -693,6 +691,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         const int resPlane = (int)a.res.planeElems;
         PROF_DECL(pEpWait);
         [[maybe_unused]] const long long pEpStart = PROF_T();
+        // The epilogue parameters arrive with the weight image (no global load in the prologue); they are moved out of
+        // the weight region once: generic loads from the region the tensor core streams its B operand from were
+        // measured to slow the epilogue by ~700 cycles per job (conv1: 36.5 -> 50.0 us).
+        mbar_wait(wbar, 0);
+        if (threadIdx.x < 32) sEpi[threadIdx.x] = reinterpret_cast<const float4 *>(sW + a.epiOff)[threadIdx.x];
+        asm volatile("bar.sync 15, %0;" ::"n"(kEpiWarps * 32) : "memory");
         for (int q = 0; q < njobs; q++) {
             const int buf = q & 1, use = q >> 1;
             const int i = ja + q;                    // job row
@@ -805,7 +809,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
 struct ConvTcPlan {
     TcArgs args{};
     uint4 *d_wimg = nullptr;
-    float *d_bias = nullptr;  // [16 planes x 4] bias then [16 x 4] scale
+    size_t wimgBytes = 0;
     size_t smemBytes = 0;
     int mode = 0;
 };
@@ -986,6 +990,7 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb, int ys) {
     // weight image grows by the step's B chunks and by the A operand of that step, 130 rows of (1, 1, 0, ..., 0).
     g.biasFold = !(d->flags & FYN_FLAG_POST_BATCHNORM) && nsteps <= 24;
     if (g.biasFold) g.wbytes += (size_t)2 * g.N * 16 + 130 * 16;
+    g.wbytes += 32 * 16;                              // epilogue parameters ride along
     // Loader groups, ring slots and staged rows.  The ring holds the window, the rows the next job adds and one more
     // job's worth of slack, rounded up to a multiple of the group count G (slot and stage ownership, see the kernel).
     // Measured on B200 (StyleNet layers, 1524x1856): rows finished concurrently matter more than staged rows per
@@ -1160,26 +1165,33 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
         for (int r = 0; r < 130; r++) img[onesBase + (size_t)r * 8 + 0] = img[onesBase + (size_t)r * 8 + 1] = __float2half(1.f);
     }
 
-    FYN_CUDA(cudaSetDevice(op->ctx->device));
-    if (!plan->d_wimg) FYN_CUDA(cudaMalloc((void **)&plan->d_wimg, g.wbytes));
-    FYN_CUDA(cudaMemcpy(plan->d_wimg, img.data(), g.wbytes, cudaMemcpyHostToDevice));
-    // epilogue parameters per output plane: [16][4] bias then [16][4] scale
-    std::vector<float> eb(128, 0.f);
-    const float *bn = wb + Co + (size_t)K * K * Ci * Co;
-    for (int o = 0; o < Co; o++) {
-        float b = wb[o], sc = 1.f;
-        if (d.flags & FYN_FLAG_POST_BATCHNORM) {
-            sc = bn[o];
-            b = b * sc + bn[Co + o];
+    // epilogue parameters per output plane, [16][4] bias then [16][4] scale, at the tail of the weight image
+    {
+        float eb[128] = {};
+        const float *bn = wb + Co + (size_t)K * K * Ci * Co;
+        for (int o = 0; o < Co; o++) {
+            float b = wb[o], sc = 1.f;
+            if (d.flags & FYN_FLAG_POST_BATCHNORM) {
+                sc = bn[o];
+                b = b * sc + bn[Co + o];
+            }
+            eb[o] = b;
+            eb[64 + o] = sc;
         }
-        eb[o] = b;
-        eb[64 + o] = sc;
+        a.epiOff = (uint32_t)(g.wbytes - sizeof(eb));
+        memcpy(reinterpret_cast<unsigned char *>(img.data()) + a.epiOff, eb, sizeof(eb));
     }
-    if (!plan->d_bias) FYN_CUDA(cudaMalloc((void **)&plan->d_bias, eb.size() * sizeof(float)));
-    FYN_CUDA(cudaMemcpy(plan->d_bias, eb.data(), eb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    FYN_CUDA(cudaSetDevice(op->ctx->device));
+    if (plan->d_wimg && plan->wimgBytes < g.wbytes) {
+        cudaFree(plan->d_wimg);
+        plan->d_wimg = nullptr;
+    }
+    if (!plan->d_wimg) {
+        FYN_CUDA(cudaMalloc((void **)&plan->d_wimg, g.wbytes));
+        plan->wimgBytes = g.wbytes;
+    }
+    FYN_CUDA(cudaMemcpy(plan->d_wimg, img.data(), g.wbytes, cudaMemcpyHostToDevice));
     a.wimg = plan->d_wimg;
-    a.bias = plan->d_bias;
-    a.scale = plan->d_bias + 64;
     plan->smemBytes = g.smem;
     if (plan->smemBytes > (size_t)op->ctx->prop.sharedMemPerBlockOptin)
         FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 conv needs %zu bytes of shared memory", plan->smemBytes);
@@ -1251,7 +1263,6 @@ int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn
 void fyn_conv_tc_destroy(fyn_op *op) {
     if (!op->tc) return;
     if (op->tc->d_wimg) cudaFree(op->tc->d_wimg);
-    if (op->tc->d_bias) cudaFree(op->tc->d_bias);
     delete op->tc;
     op->tc = nullptr;
 }
