@@ -580,9 +580,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         // block-uniform data) so the descriptors are built in uniform registers; one elected lane waits on the
         // barriers and issues the tcgen05 instructions.
         // A ring slot goes back to the loaders when BOTH warps have retired the row (empty barriers count 2): after
-        // its job q a warp releases every row below the window of its next job q + 2 (all remaining rows after its
-        // last job).  Neither warp can run a full ring ahead of the other: a row can only be published into a slot
-        // that both have released.
+        // its job q a warp releases the rows below the window of its next job q + 2 that it has already waited for.
+        // Neither warp can run a full ring ahead of the other: a row can only be published into a slot that both
+        // have released, and a warp only releases rows whose "full" phase it has observed.
         const int mw = warp - kMmaWarp;
         const uint32_t rbase16 = smem_u32(sRing) >> 4, slot16 = (uint32_t)a.slotBytes >> 4;
         const uint32_t bconst = (smem_u32(sW) >> 4) | ((a.b_lbo >> 4) << 16);   // B descriptor low word minus the step offset
@@ -600,7 +600,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             const int use = q >> 1;
             const int first = a.rowAdvance * q;          // window start relative to r0
             const int needTo = first + a.nrows;          // rows [waited, needTo) have not been waited for by this warp
-            const int relTo = (q + kMmaWarps < njobs) ? first + kMmaWarps * a.rowAdvance : R;   // rows [released, relTo) retire now
+            // Rows [released, relTo) retire now: everything below the window of this warp's next job -- but never a row
+            // this warp has not waited for yet (windows shorter than two row advances): releasing it could let its
+            // slot be refilled, and its barrier pass a second phase, before this warp's parity wait for the first.
+            const int relTo = min((q + kMmaWarps < njobs) ? first + kMmaWarps * a.rowAdvance : R, needTo);
             if (elect_one()) {
                 [[maybe_unused]] long long pt = PROF_T();
                 [[maybe_unused]] const long long ptB = pt;
@@ -1255,6 +1258,8 @@ int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    static const bool noPdl = getenv("FYN_TC_NO_PDL") != nullptr;   // debugging aid: plain stream-ordered launches
+    if (noPdl) cfg.numAttrs = 0;
     FYN_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
     FYN_CHECK_LAUNCH(op->ctx);
     return FYN_OK;

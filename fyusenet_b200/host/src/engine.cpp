@@ -210,6 +210,14 @@ Engine::execstate Engine::execute(uint64_t sequence) {
         } else {
             layer->forward(sequence);
         }
+        // FYN_DEBUG_SYNC=1: synchronise after every layer and name it (finds the layer a device fault or hang belongs to)
+        static const bool debugSync = getenv("FYN_DEBUG_SYNC") != nullptr;
+        if (debugSync) {
+            fprintf(stderr, "[fyn debug] seq %llu layer %s ...", (unsigned long long)sequence, layer->getName().c_str());
+            fflush(stderr);
+            FYN_ABI_CALL(fyn_stream_sync(context_.handle(), context_.stream()));
+            fprintf(stderr, " done\n");
+        }
         if (writeResults_) {
             char fname[1024];
             snprintf(fname, sizeof(fname), "%s/%s_%llu.bin", outputDir_.c_str(), layer->getName().c_str(), (unsigned long long)sequence);

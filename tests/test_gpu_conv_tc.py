@@ -158,3 +158,35 @@ def test_tc_fractional(k, ci, co, step, ds, relu, w, h, quirks):
     assert y.shape == ref_s.shape
     assert_close_f16(y, ref_s, ref_f, ulps=2.0, extra_abs=2e-3)
     assert rel_l2(y, yd) <= 2e-3
+
+
+@pytest.mark.parametrize("case", ["stride2", "frac_stacked", "frac9_stacked"])
+def test_tc_long_strips_repeated(case):
+    """Many jobs per strip, launched back to back (programmatic dependent launch), against the direct kernel.  Regression
+    for a pipeline deadlock: with two MMA-issuing warps a warp released ring rows it had not waited for yet whenever
+    the window is shorter than two row advances (stride-2 3x3 convs, stacked fractional 3x3), so a slot could be
+    refilled -- and its barrier pass a second phase -- before that warp's parity wait (found at 4096x4096)."""
+    c = ctx()
+    rng = np.random.default_rng(5)
+    if case == "stride2":
+        ci, co, k, w, h, kw = 12, 20, 3, 640, 1024, dict(downsample=2)
+    elif case == "frac_stacked":
+        ci, co, k, w, h, kw = 40, 20, 3, 384, 512, dict(downsample=2, source_step=0.5, fractional=True)
+    else:
+        ci, co, k, w, h, kw = 12, 3, 9, 384, 512, dict(source_step=0.5, fractional=True)
+    x = rng.normal(size=(ci, h, w)).astype(np.float32)
+    wb = random_wb(rng, ci, co, k)
+    outs = {}
+    for backend in (capi.BACKEND_TC, capi.BACKEND_DIRECT):
+        op = capi.Conv2d(c, wb, width=w, height=h, in_channels=ci, out_channels=co, kernel=k, flags=capi.FLAG_PRE_RELU, backend=backend, **kw)
+        tin = c.tensor(w, h, ci)
+        tout = c.tensor(op.out_width, op.out_height, co)
+        tin.write_chw(x)
+        for _ in range(25 if backend == capi.BACKEND_TC else 1):
+            op.run(tin, tout)
+        c.stream_sync()
+        assert op.backend == backend
+        outs[backend] = tout.read_chw()
+        for o in (tin, tout, op):
+            o.destroy()
+    assert rel_l2(outs[capi.BACKEND_TC], outs[capi.BACKEND_DIRECT]) <= 2e-3

@@ -55,9 +55,10 @@ def resnet(batch, steps):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    import faulthandler
+    faulthandler.dump_traceback_later(40, exit=True)        # a stuck configuration reports where instead of hanging the box
+    which = sys.argv[1:] if len(sys.argv) > 1 else ["all"]
     jobs = {"s3": lambda: stylenet(3, 512, 624, 200), "s9": lambda: stylenet(9, 1524, 1856, 50), "s9_4096": lambda: stylenet(9, 4096, 4096, 10),
             "r1": lambda: resnet(1, 20), "r32": lambda: resnet(32, 5)}
-    for k, f in jobs.items():
-        if which in ("all", k):
-            print(json.dumps(f()), flush=True)
+    for k in (list(jobs) if which == ["all"] else which):
+        print(json.dumps(jobs[k]()), flush=True)
