@@ -242,6 +242,16 @@ def main():
     layer_ms = {l["name"]: net.layer_timing(l["number"])[0] / args.steps for l in net.layers()}
     families = {l["name"]: l["family"] for l in net.layers()}
     net.enable_timings(False)
+    # the dominant layer once more with an event pair around it alone: the other layers then keep their dependent-launch
+    # overlap, which is the situation of the timed region above
+    top_name = max(layer_ms, key=layer_ms.get)
+    top_no = next(l["number"] for l in net.layers() if l["name"] == top_name)
+    net.enable_layer_timing(top_no)
+    for _ in range(args.steps):
+        net.forward()
+    net.finish()
+    top_ms = net.layer_timing(top_no)[0] / args.steps
+    net.enable_timings(False)
     if world > 1:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -300,9 +310,9 @@ def main():
         alg = layer_algorithmic()
         # dominant kernel = the layer with the largest share of the device time
         conv_ms = {k: v for k, v in layer_ms.items() if k in alg}
-        top = max(conv_ms, key=conv_ms.get)
+        top = top_name if top_name in alg else max(conv_ms, key=conv_ms.get)
         a = alg[top]
-        t_s = conv_ms[top] / 1e3
+        t_s = (top_ms if top == top_name else conv_ms[top]) / 1e3
         ai = a["flops"] / a["bytes"]
         ridge = tf_sust * 1e12 / (hbm * 1e9)
         if ai > ridge:
@@ -322,7 +332,8 @@ def main():
         roof["algorithmic_flops_per_launch"] = a["flops"]
         roof["kernel"] = top
         roof["peak_source"] = f"{which} ({'sustained' if roof['bound'] == 'tensor' else 'copy'} figure, kernel timed inside a long step)"
-        roof["ms_per_launch"] = conv_ms[top]
+        roof["ms_per_launch"] = t_s * 1e3
+        roof["ms_per_launch_all_layers_timed"] = conv_ms[top]
         total_layer_ms = sum(layer_ms.values())
         # whole-network roofline: sum_l max(F_l / P, B_l / BW)
         t_lb = sum(max(v["flops"] / (tf_sust * 1e12), v["bytes"] / (hbm * 1e9)) for v in alg.values())

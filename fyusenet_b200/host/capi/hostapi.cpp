@@ -311,6 +311,15 @@ int fynhost_net_fused_layers(void *handle) {
     return n;
 }
 
+// like fynhost_net_enable_timings(handle, 1) but with an event pair around one layer only
+int fynhost_net_enable_layer_timing(void *handle, int layerNumber) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] {
+        h->net()->engine()->resetTimings();
+        h->net()->engine()->enableTimings(layerNumber);
+    });
+}
+
 int fynhost_net_enable_timings(void *handle, int on) {
     NetHandle *h = static_cast<NetHandle *>(handle);
     return guarded([&] {

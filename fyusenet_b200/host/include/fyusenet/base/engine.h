@@ -40,7 +40,9 @@ class Engine : public GfxContextTracker {
 
     // host-side microseconds per layer number around each forward() (issue time, not device time: :201-204),
     // plus device milliseconds from CUDA events when enabled
-    void enableTimings() { timings_ = true; }
+    void enableTimings() { timings_ = true; timingOnly_ = -1; }
+    // time a single layer: its event pair is the only one in the stream, so the other layers keep their dependent-launch overlap
+    void enableTimings(int layerNumber) { timings_ = true; timingOnly_ = layerNumber; }
     void disableTimings() { timings_ = false; }
     void resetTimings();
     const std::unordered_map<int, uint32_t> &getTimings() const { return timingData_; }
@@ -89,6 +91,7 @@ class Engine : public GfxContextTracker {
     bool setup_ = false;
     bool async_ = false;
     bool timings_ = false;
+    int timingOnly_ = -1;
     bool writeResults_ = false;
     bool fusion_ = true;
     int fusedLayers_ = 0;

@@ -190,7 +190,7 @@ Engine::execstate Engine::execute(uint64_t sequence) {
     size_t slot = 0;
     for (auto it = layers_.begin(); it != layers_.end(); ++it) {
         LayerBase *layer = it.second;
-        if (timings_) {
+        if (timings_ && (timingOnly_ < 0 || timingOnly_ == it.first)) {
             if (pendingEvents_.size() >= 4096) collectTimings(true);
             void *evA = nullptr, *evB = nullptr;
             if (freeEvents_.size() >= 2) {

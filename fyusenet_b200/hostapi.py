@@ -169,6 +169,10 @@ class Network:
     def enable_timings(self, on=True):
         _check(lib().fynhost_net_enable_timings(self._h, int(on)))
 
+    def enable_layer_timing(self, number: int):
+        """Event pair around one layer only (the others keep their dependent-launch overlap); read with layer_timing()."""
+        _check(lib().fynhost_net_enable_layer_timing(self._h, int(number)))
+
     def layer_timing(self, number: int):
         ms, us = C.c_float(), C.c_uint()
         _check(lib().fynhost_net_layer_timing(self._h, int(number), C.byref(ms), C.byref(us)))
