@@ -12,10 +12,10 @@
 //   canonical K-major, non-swizzled layout, [8-channel chunk][pixel][8 x fp16] (16 bytes per (chunk, pixel)).
 //   The A operand of tap (ky, kx) is then simply the same shared-memory image with the descriptor start
 //   address moved by kx*16 bytes (one pixel) and the ring slot chosen by ky: rows of a core matrix stay
-//   16 bytes apart, so the canonical layout still holds.  Activation-at-fetch (fyusenet/base/layerbase.h:50-59,
-//   shaders/activation.inc) and clamp-to-edge addressing (base/buffermanager.cpp:657-670) are applied by the
-//   loader warps while they transpose 4-channel planes into 8-channel chunks, which is why the operands are
-//   staged by threads (generic proxy + fence.proxy.async) instead of TMA.
+//   16 bytes apart, so the canonical layout still holds.  Rows arrive as bulk copies (TMA unit) of raw plane texels;
+//   activation-at-fetch (fyusenet/base/layerbase.h:50-59, shaders/activation.inc) and clamp-to-edge addressing
+//   (base/buffermanager.cpp:657-670) are applied by the loader warps while they transpose 4-channel planes into
+//   8-channel chunks (generic proxy + fence.proxy.async) -- the transform is why TMA cannot write the operand image.
 //   For 3-channel inputs (StyleNet conv1 reading the RGB32F upload texture) a chunk is two horizontally
 //   adjacent pixels x 4 channels ("pixel-pair" mode), i.e. one 16-byte chunk covers taps kx and kx+1.
 //
@@ -32,7 +32,8 @@
 // layers are bound by the NUMBER of MMAs, not by their FLOPs.  All output phases that read the same source window
 // are therefore stacked along N: n = phase * Cq + co.  One GEMM row then produces p_y x p_x output pixels
 // (fractional convs) or four horizontally adjacent pixels (the 3-channel pixel-pair mode), with structural zeros in
-// the weight image where a phase does not use a tap.
+// the weight image where a phase does not use a tap.  Where shared memory allows, two job rows are stacked the same
+// way (plan_geometry's `ys`), and the bias of layers without post-BN scale is one more MMA step.
 //
 // Warp roles (576 threads): warps 0-7 epilogue (TMEM -> registers -> bias/BN/residual[/sigmoid] -> fp16 planes; the two
 // warps of a TMEM lane quarter split the accumulator columns), warps 8-15 loaders (bulk-copy issue + row finishing in
