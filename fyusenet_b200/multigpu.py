@@ -84,3 +84,38 @@ def band_rows(height: int, world: int, align: int = 4) -> list[tuple[int, int]]:
         b, e = shard_range(units, r, world)
         out.append((b * align, e * align))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# StyleNet row bands without an exchange: overlapped bands ("recompute halo")
+# ------------------------------------------------------------------------------------------------
+
+def stylenet_margin(ksize: int = 9) -> int:
+    """Full-resolution rows of context above / below a band that make every output row of the band exact.
+
+    Walking the halo plan backwards from the output (deconv3 reads +-2 rows at /2, deconv2 and deconv1 one row above
+    at /4, ten residual convs +-1 at /4, conv3 / conv2 2o-1..2o+1, conv1 +-m) gives 59 rows above and 51 below for the
+    9x9 network (43 / 35 for 3x3); rounded up to a multiple of 4 so that the /2 and /4 levels stay aligned."""
+    m = (ksize - 1) // 2
+    nres = 5 if ksize == 9 else 2
+    d3_above = int(np.ceil(m / 2 - 0.25))            # deconv3, at /2
+    d3_below = int(np.floor(0.75 + m / 2))
+    # /4 level: deconv2 (floor(o/2) - 1 .. floor(o/2)), deconv1 (o - 1 .. o), 2 * nres residual convs (+-1)
+    a4 = (d3_above + 1) // 2 + 1 + 1 + 2 * nres
+    b4 = (d3_below + 1) // 2 + 2 * nres
+    above = 2 * (2 * a4 + 1) + 1 + m                 # conv3 and conv2: 2o - 1; conv1: m
+    below = 2 * (2 * b4 + 1) + 1 + m
+    return ((max(above, below) + 3) // 4) * 4
+
+
+def stylenet_band_plan(height: int, world: int, ksize: int = 9, margin: int | None = None):
+    """Per rank: (input row begin, input row end, first output row to keep, rows to keep).  Every rank runs the whole
+    network on its band plus `margin` rows of context on each side (clipped at the true image border, where the
+    reference's clamp-to-edge applies) and keeps the rows of its own band; no data crosses GPUs."""
+    if margin is None:
+        margin = stylenet_margin(ksize)
+    plan = []
+    for b, e in band_rows(height, world):
+        ib, ie = max(0, b - margin), min(height, e + margin)
+        plan.append((ib, ie, b - ib, e - b))
+    return plan

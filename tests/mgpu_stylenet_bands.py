@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""StyleNet 9x9 on one large frame split into row bands over the GPUs of one node, by hand:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 \
+        tests/mgpu_stylenet_bands.py --width 4096 --height 4096 --steps 5
+
+Overlapped bands (fyusenet_b200.multigpu.stylenet_band_plan): rank r uploads its band plus 60 rows of context per side
+from the host frame, runs the whole network on it and keeps its own rows; nothing crosses GPUs on the data path.
+Rank 0 gathers the bands' checksums (NCCL all_gather) and, with --verify, compares its band with the rows of a
+whole-frame run on its own GPU (bit-exact).  Throughput = frames / max-over-ranks device time.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT)]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--width", type=int, default=4096)
+    ap.add_argument("--height", type=int, default=4096)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--verify", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+
+    from fyusenet_b200 import hostapi, multigpu, synthetic
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    weights = synthetic.stylenet_weights(9)
+    img = synthetic.image(args.height, args.width, 7)
+    ib, ie, skip, keep = multigpu.stylenet_band_plan(args.height, world)[rank]
+    net = hostapi.StyleNet(9, args.width, ie - ib, device=local)
+    net.load_weights(weights)
+    net.setup()
+    net.set_input(img[ib:ie])
+    net.forward()
+    band = net.output_rgba()[0][skip:skip + keep].copy()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        net.forward()                                    # upload of the band + layers + download, synchronous API
+    torch.cuda.synchronize()
+    ms = multigpu.max_over_ranks((time.perf_counter() - t0) * 1e3, device=dev)
+    net.destroy()
+    sums = torch.tensor([float(band[..., :3].astype(np.float64).sum())], dtype=torch.float64, device=dev)
+    parts = [torch.zeros_like(sums) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(parts, sums)
+    else:
+        parts = [sums]
+    exact = None
+    if args.verify:
+        whole = hostapi.StyleNet(9, args.width, args.height, device=local)
+        whole.load_weights(weights)
+        whole.setup()
+        whole.set_input(img)
+        whole.forward()
+        ref = whole.output_rgba()[0][ib + skip:ib + skip + keep]
+        exact = bool(np.array_equal(ref, band))
+        whole.destroy()
+        flag = torch.tensor([1 if exact else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exact = bool(flag.item())
+    if rank == 0:
+        print(json.dumps({"workload": f"StyleNet 9x9 {args.width}x{args.height}, {world} overlapped row bands", "n_gpus": world,
+                          "frames_per_s": args.steps / (ms / 1e3), "ms_per_frame": ms / args.steps, "band_rows": keep, "context_rows": multigpu.stylenet_margin(9),
+                          "rgb_checksum": float(sum(p.item() for p in parts)), "bit_exact_vs_whole_frame": exact}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

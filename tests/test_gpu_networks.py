@@ -214,3 +214,31 @@ def test_stylenet_layer_fusion():
     net.destroy()
     ref = fo.stylenet_forward(weights, img, 9, prec=fo.FP16_STORE)
     assert np.abs(fused[..., :3] - ref[..., :3]).max() <= 6e-3
+
+
+@pytest.mark.parametrize("ksize,w,h,world", [(9, 256, 384, 2), (9, 192, 512, 3), (3, 160, 256, 2)])
+def test_stylenet_overlapped_bands_are_exact(ksize, w, h, world):
+    """SURVEY 8e, StyleNet row bands: every rank runs the network on its band plus stylenet_margin() rows of context and
+    keeps its own rows -- the stitched frame must equal the whole-frame result bit for bit (here the bands run one
+    after the other on one GPU; tests/mgpu_stylenet_bands.py runs them on one GPU each)."""
+    from fyusenet_b200 import multigpu
+    weights = fo.stylenet_synthetic_weights(ksize)
+    img = fo.synthetic_image(h, w, 31)
+    net = hostapi.StyleNet(ksize, w, h)
+    net.load_weights(weights)
+    net.setup()
+    net.set_input(img)
+    net.forward()
+    whole = net.output_rgba()[0].copy()
+    net.destroy()
+    stitched = np.zeros_like(whole)
+    for ib, ie, skip, keep in multigpu.stylenet_band_plan(h, world, ksize):
+        band = hostapi.StyleNet(ksize, w, ie - ib)
+        band.load_weights(weights)
+        band.setup()
+        band.set_input(img[ib:ie])
+        band.forward()
+        out = band.output_rgba()[0]
+        stitched[ib + skip:ib + skip + keep] = out[skip:skip + keep]
+        band.destroy()
+    np.testing.assert_array_equal(stitched, whole)

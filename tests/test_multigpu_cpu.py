@@ -36,6 +36,10 @@ def test_band_rows_and_halo_plan():
     plan3 = {n: (d, a, b) for n, d, a, b in multigpu.stylenet_halo_plan(3)}
     assert plan3["deconv3"] == (2, 1, 1) and plan3["conv1"] == (1, 1, 1)
     assert len(plan3) == 3 + 4 + 4
+    # overlapped bands: 59 rows of context are needed above a band of the 9x9 network (51 below), rounded to 60
+    assert multigpu.stylenet_margin(9) == 60 and multigpu.stylenet_margin(3) % 4 == 0
+    bp = multigpu.stylenet_band_plan(4096, 4)
+    assert bp[0] == (0, 1084, 0, 1024) and bp[1] == (964, 2108, 60, 1024) and bp[3] == (3012, 4096, 60, 1024)
 
 
 def _worker(rank, world, port, total, q):
