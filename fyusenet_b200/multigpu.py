@@ -4,8 +4,9 @@ The reference is a single-GPU, batch-1 engine (README.md:72); scaling out is the
   * replicas      -- StyleNet frames <= 1524x1856 and ResNet-50 batch 1: independent requests per GPU, no collective;
   * batch shards  -- ResNet-50 batch B: contiguous image ranges per rank, weights replicated, one all-gather of the
                      [B/world, 1000] logits at the end (NCCL on GPUs, gloo in the CPU tests);
-  * row bands     -- StyleNet 4096x4096: horizontal bands with per-layer halo rows (the plan is computed here; the
-                     exchange itself is a later round).
+  * row bands     -- StyleNet 4096x4096: horizontal bands.  Implemented as overlapped bands (every rank recomputes
+                     the 60 rows of context its band needs, no exchange); the per-layer halo table for an NVLink
+                     exchange is computed here as well.
 Only host logic lives here; it never touches the oracle and never falls back to CPU compute.
 """
 from __future__ import annotations
