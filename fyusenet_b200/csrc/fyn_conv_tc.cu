@@ -1001,18 +1001,20 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb, int ys) {
     // group (res 3x3 40->40: G=1 20.6 us, G=2 18.2 us, G=4 16.1 us), so: four groups if they fit at all, else two.
     const size_t budget = 220 * 1024;
     // (FYN_TC_GROUPS=1|2|4 overrides the choice: tuning knob)
-    int gmax = 4, gmin = 2;
-    if (const char *e = getenv("FYN_TC_GROUPS")) gmax = gmin = std::max(1, std::min(4, atoi(e)));
+    // (pixel-pair rows are light: eight single-warp groups were measured faster there, conv1 38.1 -> 35.9 us, and slower
+    // or not fitting elsewhere)
+    int gmax = (g.mode == 1) ? 8 : 4, gmin = 2;
+    if (const char *e = getenv("FYN_TC_GROUPS")) gmax = gmin = std::max(1, std::min(8, atoi(e)));
     // Ring size: the window, the rows the next job adds and one more job's worth of slack ("full"); if that does not
     // fit with four groups, a ring with one job of look-ahead ("tight") is tried before giving up groups.  Lower bound
     // for progress with two MMA warps: max(nrows, 2 * rowAdvance) slots (see the release rule in the kernel).
     const int needFull = nrows + 2 * g.rowAdvance;
     const int needTight = std::max(nrows, 2 * g.rowAdvance) + g.rowAdvance;
-    for (int attempt = 0; attempt < 4 && !g.ok; attempt++) {
-        const int G = (attempt < 2) ? gmax : gmin;
+    for (int attempt = 0; !g.ok; attempt++) {
+        const int G = gmax >> (attempt / 2);             // group counts from gmax down to gmin, each with the full, then the tight ring
+        if (G < gmin) break;
         const int need = (attempt & 1) ? needTight : needFull;
         if ((attempt & 1) && needTight >= needFull) continue;
-        if (attempt >= 2 && gmin == gmax) break;
         const int nslots = ((need + G - 1) / G) * G;
         const size_t fixed = ((g.wbytes + 127) & ~(size_t)127) + (size_t)(nslots + nrows - 1) * g.slotBytes + 32 * 16 + (size_t)g.nitems * 8 +
                              (2 * nslots + 5 + kMaxStages) * 8 + 16 + 16;   // + the 16 zero bytes
