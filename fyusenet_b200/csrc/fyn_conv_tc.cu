@@ -105,7 +105,8 @@ struct TcArgs {
     int inP, outP, resP;
     int nchunks, rowpx;      // mode 0: chunks per version and pixels per chunk row; mode 1: rowpx = chunks per slot
     int nver, verBytes;      // slot versions: 0 = activated (or the only one), 1 = raw
-    int nslots, slotBytes;   // logical ring slots; the first nrows-1 slots are mirrored behind the ring
+    int nslots, slotBytes;   // logical ring slots; the first nmirror slots are mirrored behind the ring
+    int nmirror;             // windows start at multiples of rowAdvance: nrows - rowAdvance mirror slots when that divides nslots, else nrows - 1
     int SH, nxs;             // job rows per strip, column blocks
     int N, nInPlanes;
     int mode;                // 0 = plane-pair chunks (fp16 RGBA planes), 1 = pixel-pair chunks (single plane, 4 px per GEMM row)
@@ -316,7 +317,7 @@ struct RingPos {
 // Work decomposition.  The job space (output rows / opy, output columns / opx) is cut into strips of 128 job
 // columns x SH job rows; one CTA per strip.  A job is one GEMM accumulation: 128 job columns of one job row, i.e.
 // 128 x opx output pixels of opy output rows, reading a window of `nrows` input rows that only moves forward, so
-// the ring of row slots is a FIFO.  The first nrows-1 slots are mirrored behind the ring so that every window is
+// the ring of row slots is a FIFO.  The first nmirror slots are mirrored behind the ring so that every window is
 // contiguous in shared memory and the A descriptor of a step is (window base + constant).
 // MODE: 0 plane-pair chunks, 1 pixel-pair chunks.  ACT: see act_h8_t.  RES: 0 no residual, 1 fp16 shallow residual of a
 // single-phase layer (prefetched), 2 any other residual tensor (generic fetch).  EPI: FYN_EPILOGUE_* function fused behind
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sW = smem;
     unsigned char *sRing = smem + ((a.wbytes + 127) & ~127u);
-    unsigned char *sStage = sRing + (size_t)(a.nslots + a.nrows - 1) * a.slotBytes;                       // [nstages] raw input rows
+    unsigned char *sStage = sRing + (size_t)(a.nslots + a.nmirror) * a.slotBytes;                       // [nstages] raw input rows
     float4 *sEpi = reinterpret_cast<float4 *>(sStage + (size_t)a.nstages * a.stageBytes);                 // [16] bias, [16] scale (copied from the weight image's tail)
     int2 *sTab = reinterpret_cast<int2 *>(sEpi + 32);                                                     // [nitems] row item table
     uint64_t *sZero = reinterpret_cast<uint64_t *>(sTab + a.nitems);                                      // 16 zero bytes (missing second plane)
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         const unsigned long long base = reinterpret_cast<unsigned long long>(a.in.ptr) + (unsigned long long)n * a.in.imageElems * esize;
         const unsigned long long planeBytes = (unsigned long long)a.in.planeElems * esize;
         const int R = r1 - r0 + 1;
-        const int mirrorOff = a.nslots * a.slotBytes;                 // slots < nrows-1 are also written behind the ring
+        const int mirrorOff = a.nslots * a.slotBytes;                 // the first nmirror slots are also written behind the ring
         const uint32_t base15 = (uint32_t)(base & 15ull), plane15 = (uint32_t)(planeBytes & 15ull);
         const int pk = a.in.packing;
         const bool f16in = a.in.dtype == FYN_F16;
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             pt = PROF_T();
             const uint32_t stgA = smem_u32(sStage) + (uint32_t)st * (uint32_t)a.stageBytes + sh0;
             const uint32_t slotA = smem_u32(sRing) + (uint32_t)slotIdx * (uint32_t)a.slotBytes;
-            const bool mirror = slotIdx < a.nrows - 1;
+            const bool mirror = slotIdx < a.nmirror;
             // The body is written without data-dependent branches (the loaders are bound by instruction latency, not
             // by bandwidth): whole units of groupThreads items in batches of kFinBatch, then single units, then the
             // guarded partial unit.  `nv2` / `mir` are uniform per row and select one of four straight-line variants.
@@ -830,7 +831,7 @@ struct Position {
 struct Geometry {
     int mode = 0, opx = 1, opy = 1, rowAdvance = 1, nver = 1, N = 16, Cq = 4, nchunks = 1, rowpx = 0, x_lead = 0, ds = 1;
     int dxMin = 0, dxMax = 0, dyMin = 0, dyMax = 0;
-    int nslots = 0, slotBytes = 0, verBytes = 0, nsteps = 0, stageBytes = 0, nstages = 0, nitems = 0, finGroups = 2;
+    int nslots = 0, slotBytes = 0, verBytes = 0, nsteps = 0, stageBytes = 0, nstages = 0, nitems = 0, finGroups = 2, nmirror = 0;
     bool biasFold = false;
     size_t wbytes = 0, smem = 0;
     std::vector<Position> pos;
@@ -1006,24 +1007,35 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb, int ys) {
     int gmax = (g.mode == 1) ? 8 : 4, gmin = 2;
     if (const char *e = getenv("FYN_TC_GROUPS")) gmax = gmin = std::max(1, std::min(8, atoi(e)));
     // Ring size: the window, the rows the next job adds and one more job's worth of slack ("full"); if that does not
-    // fit with four groups, a ring with one job of look-ahead ("tight") is tried before giving up groups.  Lower bound
+    // fit with four groups, a ring with about one job of look-ahead ("tight") is considered as well.  Lower bound
     // for progress with two MMA warps: max(nrows, 2 * rowAdvance) slots (see the release rule in the kernel).
     const int needFull = nrows + 2 * g.rowAdvance;
-    const int needTight = std::max(nrows, 2 * g.rowAdvance) + g.rowAdvance;
-    for (int attempt = 0; !g.ok; attempt++) {
-        const int G = gmax >> (attempt / 2);             // group counts from gmax down to gmin, each with the full, then the tight ring
-        if (G < gmin) break;
-        const int need = (attempt & 1) ? needTight : needFull;
-        if ((attempt & 1) && needTight >= needFull) continue;
-        const int nslots = ((need + G - 1) / G) * G;
-        const size_t fixed = ((g.wbytes + 127) & ~(size_t)127) + (size_t)(nslots + nrows - 1) * g.slotBytes + 32 * 16 + (size_t)g.nitems * 8 +
-                             (2 * nslots + 5 + kMaxStages) * 8 + 16 + 16;   // + the 16 zero bytes
-        if (fixed + (size_t)G * g.stageBytes > budget) continue;
-        const int m = (int)std::min<size_t>(kMaxStages / G, (budget - fixed) / ((size_t)G * g.stageBytes));
+    const int needTight = std::max(nrows, 2 * g.rowAdvance) + std::max(g.rowAdvance, 3);   // (a single slot of look-ahead was measured slower: res 13.4 -> 16.2 us)
+    // Per group count (from gmax down): the full ring if every group still gets two staged rows (a copy in flight while
+    // it finishes a row), else the tight ring if that one does, else whichever fits.  Measured on the stacked stride-2
+    // conv: tight ring + 8 stages 31.3 us, full ring + 4 stages 37.5 us.
+    auto fit = [&](int G, int need, int &nslots, int &nmirror, size_t &fixed) -> int {
+        nslots = ((need + G - 1) / G) * G;
+        // slots mirrored behind the ring so that every window is contiguous: windows start at multiples of rowAdvance
+        nmirror = (nslots % g.rowAdvance == 0) ? std::max(0, nrows - g.rowAdvance) : nrows - 1;
+        fixed = ((g.wbytes + 127) & ~(size_t)127) + (size_t)(nslots + nmirror) * g.slotBytes + 32 * 16 + (size_t)g.nitems * 8 +
+                (2 * nslots + 5 + kMaxStages) * 8 + 16 + 16;   // + the 16 zero bytes
+        if (fixed + (size_t)G * g.stageBytes > budget) return 0;
+        return (int)std::min<size_t>(kMaxStages / G, (budget - fixed) / ((size_t)G * g.stageBytes));   // staged rows per group
+    };
+    for (int G = gmax; G >= gmin && !g.ok; G >>= 1) {
+        int nsF, nmF, nsT, nmT;
+        size_t fxF, fxT;
+        const int mF = fit(G, needFull, nsF, nmF, fxF);
+        const int mT = (needTight < needFull) ? fit(G, needTight, nsT, nmT, fxT) : 0;
+        const bool tight = (mF < 2 && mT >= 2) || (mF == 0 && mT > 0);
+        const int m = tight ? mT : mF;
+        if (m == 0) continue;
         g.finGroups = G;
-        g.nslots = nslots;
+        g.nslots = tight ? nsT : nsF;
+        g.nmirror = tight ? nmT : nmF;
         g.nstages = m * G;
-        g.smem = fixed + (size_t)g.nstages * g.stageBytes;
+        g.smem = (tight ? fxT : fxF) + (size_t)g.nstages * g.stageBytes;
         g.ok = true;
     }
     return g;
@@ -1099,6 +1111,7 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     a.rowpx = g.rowpx;
     a.x_lead = g.x_lead;
     a.nslots = g.nslots;
+    a.nmirror = g.nmirror;
     a.nsteps = g.nsteps;
     if (const char *e = getenv("FYN_TC_DEBUG_STEPS")) a.nsteps = std::max(1, std::min(g.nsteps, atoi(e)));   // ablation: wrong results, timing only
     a.stageBytes = g.stageBytes;
