@@ -67,9 +67,8 @@ __device__ long long g_trace[4][64][2];   // [role: 0 loader publish, 1 mma issu
 #endif
 
 constexpr int kMaxSteps = 96;
-constexpr int kEpiWarps = 8;                         // two warps per TMEM lane quarter, each takes every other column group
-constexpr int kLoaderWarps = 8;
-constexpr int kMmaWarp = kEpiWarps + kLoaderWarps;  // first of the two MMA warps (even / odd jobs)
+constexpr int kWorkWarps = 16;                       // epilogue + loader warps; the split (8 + 8 or 12 + 4) is part of the plan
+constexpr int kMmaWarp = kWorkWarps;                 // first of the two MMA warps (even / odd jobs)
 constexpr int kMmaWarps = 2;
 constexpr int kThreads = (kMmaWarp + kMmaWarps) * 32;   // 576
 constexpr int kFinBatch = 4;                         // items a finishing lane keeps in flight
@@ -93,7 +92,8 @@ struct TcArgs {
     int nsteps;              // MMA steps per job
     int stageBytes;          // bytes of one staged input row (all planes)
     int nstages;             // staged rows in flight (multiple of finGroups)
-    int finGroups;           // loader groups (2 or 4) working on different rows; nslots and nstages are multiples of it
+    int finGroups;           // loader groups working on different rows; nslots and nstages are multiples of it
+    int epiWarps;            // 8 or 12 epilogue warps (the remaining work warps are loaders)
     int nitems;              // entries of the row item table
     int rowAdvance;          // input rows the window moves per job (stride; 1 for fractional)
     int dyMin, nrows;        // window: input rows [rowAdvance*i + dyMin, +nrows)
@@ -367,8 +367,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         for (int s = 0; s < a.nstages; s++) mbar_init(&landed[s], 1);   // one arrive.expect_tx + the bytes of the bulk copies
         mbar_init(&tfull[0], 1);
         mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], kEpiWarps * 32);
-        mbar_init(&tempty[1], kEpiWarps * 32);
+        mbar_init(&tempty[0], a.epiWarps * 32);
+        mbar_init(&tempty[1], a.epiWarps * 32);
         mbar_init(wbar, 1);
         fence_barrier_init();
         // weight image -> shared memory: one bulk copy, the MMA warp waits for it before its first step
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     grid_dep_wait();
     [[maybe_unused]] const long long pK2 = PROF_T();
 
-    if (warp >= kEpiWarps && warp < kMmaWarp) {
+    if (warp >= a.epiWarps && warp < kMmaWarp) {
         // ===================== loaders =====================
         // Input rows travel global -> shared as bulk copies (TMA unit, no registers, no load/store-unit traffic): per
         // row one copy per 4-channel plane of the contiguous texel run the strip needs.  The loader warps then turn a
@@ -428,8 +428,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         // s = g (mod G), so every barrier is waited on by one group in program order (parity waits stay one phase
         // apart) while G rows are being finished concurrently and nstages rows are in flight.
         const int P = a.inP;
-        const int G = a.finGroups, groupThreads = (kLoaderWarps * 32) / G;
-        const int tl = threadIdx.x - kEpiWarps * 32, g = tl / groupThreads, tg = tl - g * groupThreads;
+        const int G = a.finGroups, groupThreads = ((kWorkWarps - a.epiWarps) * 32) / G;
+        const int tl = threadIdx.x - a.epiWarps * 32, g = tl / groupThreads, tg = tl - g * groupThreads;
         const bool leader = tg < 32;                                  // first warp of the group issues the copies
         const int runBytes = (xz - xa + 1) * bpp;
         const unsigned long long base = reinterpret_cast<unsigned long long>(a.in.ptr) + (unsigned long long)n * a.in.imageElems * esize;
@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         const int chalf = warp >> 2;
         const int jx = j0 + m;
         const bool valid = jx < a.Wj;
-        const int nOct = a.N >> 4;           // octets per thread (1..4)
+        const int nOct = (a.N >> 3) / (a.epiWarps >> 2);   // octets per thread (1..4): the warps of a lane quarter split the columns
         const int ppp = a.planesPerPhase;
         // per texel, hoisted out of the job loop: output element offset relative to the job's first output texel
         // (-1 = nothing to store) and the output plane (bias / scale / residual index)
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         // measured to slow the epilogue by ~700 cycles per job (conv1: 36.5 -> 50.0 us).
         mbar_wait(wbar, 0);
         if (threadIdx.x < 32) sEpi[threadIdx.x] = reinterpret_cast<const float4 *>(sW + a.epiOff)[threadIdx.x];
-        asm volatile("bar.sync 15, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        asm volatile("bar.sync 15, %0;" ::"r"(a.epiWarps * 32) : "memory");
         for (int q = 0; q < njobs; q++) {
             const int buf = q & 1, use = q >> 1;
             const int i = ja + q;                    // job row
@@ -831,7 +831,7 @@ struct Position {
 struct Geometry {
     int mode = 0, opx = 1, opy = 1, rowAdvance = 1, nver = 1, N = 16, Cq = 4, nchunks = 1, rowpx = 0, x_lead = 0, ds = 1;
     int dxMin = 0, dxMax = 0, dyMin = 0, dyMax = 0;
-    int nslots = 0, slotBytes = 0, verBytes = 0, nsteps = 0, stageBytes = 0, nstages = 0, nitems = 0, finGroups = 2, nmirror = 0;
+    int nslots = 0, slotBytes = 0, verBytes = 0, nsteps = 0, stageBytes = 0, nstages = 0, nitems = 0, finGroups = 2, nmirror = 0, epiWarps = 8;
     bool biasFold = false;
     size_t wbytes = 0, smem = 0;
     std::vector<Position> pos;
@@ -1005,6 +1005,16 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb, int ys) {
     // (pixel-pair rows are light: eight single-warp groups were measured faster there, conv1 38.1 -> 35.9 us, and slower
     // or not fitting elsewhere)
     int gmax = (g.mode == 1) ? 8 : 4, gmin = 2;
+    // Warp split: 12 epilogue + 4 loader warps where the epilogue is the busy role and the rows are light for the
+    // loaders -- measured: the 3x3 40-channel conv with residual 17.2 -> 15.3 us; without residual no change, and
+    // loader-heavy layers get slower (conv1 36 -> 43 us).  The accumulator columns must split three ways.
+    // (FYN_TC_EPI=8|12: tuning knob)
+    g.epiWarps = (g.mode == 0 && (d->flags & FYN_FLAG_RESIDUAL_INPUT) && ((g.N >> 3) % 3) == 0 && g.nitems * g.rowAdvance <= 800) ? 12 : 8;
+    if (const char *e = getenv("FYN_TC_EPI")) {
+        const int want = atoi(e);
+        if (want == 8 || (want == 12 && ((g.N >> 3) % 3) == 0)) g.epiWarps = want;
+    }
+    gmax = std::min(gmax, kWorkWarps - g.epiWarps);
     if (const char *e = getenv("FYN_TC_GROUPS")) gmax = gmin = std::max(1, std::min(8, atoi(e)));
     // Ring size: the window, the rows the next job adds and one more job's worth of slack ("full"); if that does not
     // fit with four groups, a ring with about one job of look-ahead ("tight") is considered as well.  Lower bound
@@ -1117,6 +1127,7 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     a.stageBytes = g.stageBytes;
     a.nstages = g.nstages;
     a.finGroups = g.finGroups;
+    a.epiWarps = g.epiWarps;
     a.nitems = g.nitems;
     a.slotBytes = g.slotBytes;
     a.idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);  // F32 accum, F16 x F16, K-major A/B
