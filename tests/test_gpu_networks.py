@@ -216,11 +216,12 @@ def test_stylenet_layer_fusion():
     assert np.abs(fused[..., :3] - ref[..., :3]).max() <= 6e-3
 
 
-@pytest.mark.parametrize("ksize,w,h,world", [(9, 256, 384, 2), (9, 192, 512, 3), (3, 160, 256, 2)])
+@pytest.mark.parametrize("ksize,w,h,world", [(9, 256, 384, 2), (9, 192, 512, 3), (3, 160, 256, 2), (9, 1524, 1856, 2)])
 def test_stylenet_overlapped_bands_are_exact(ksize, w, h, world):
     """SURVEY 8e, StyleNet row bands: every rank runs the network on its band plus stylenet_margin() rows of context and
     keeps its own rows -- the stitched frame must equal the whole-frame result bit for bit (here the bands run one
-    after the other on one GPU; tests/mgpu_stylenet_bands.py runs them on one GPU each)."""
+    after the other on one GPU; tests/mgpu_stylenet_bands.py runs them on one GPU each).  The last case is the
+    headline size (BASELINE configs[1], 1524x1856): a size-independent property where the CPU oracle would take minutes."""
     from fyusenet_b200 import multigpu
     weights = fo.stylenet_synthetic_weights(ksize)
     img = fo.synthetic_image(h, w, 31)
