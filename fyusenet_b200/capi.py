@@ -43,6 +43,12 @@ class DeviceInfo(C.Structure):
                 ("total_mem", C.c_size_t), ("smem_per_block_optin", C.c_size_t), ("name", C.c_char * 64)]
 
 
+class ConvPlanInfo(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("mode", "n", "steps", "window_rows", "row_advance", "phases_x", "phases_y", "ring_slots",
+                                       "mirror_slots", "slot_bytes", "staged_rows", "stage_bytes", "row_items", "loader_groups",
+                                       "epilogue_warps", "bias_folded")] + [("weight_image_bytes", C.c_size_t), ("shared_bytes", C.c_size_t)]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("in_channels", C.c_int), ("out_channels", C.c_int),
                 ("kernel", C.c_int), ("downsample", C.c_int), ("dilation", C.c_int),
@@ -78,7 +84,7 @@ EXPORTS = [
     "fyn_tensor_wrap", "fyn_tensor_destroy", "fyn_tensor_clear", "fyn_tensor_get_desc", "fyn_tensor_device_ptr",
     "fyn_upload_f32_async", "fyn_download_f32_async", "fyn_download_f32_elems", "fyn_tensor_write_chw_f32",
     "fyn_tensor_read_chw_f32", "fyn_conv2d_output_size", "fyn_conv2d_create", "fyn_conv2d_load_weights",
-    "fyn_conv2d_run", "fyn_conv2d_backend", "fyn_conv2d_set_epilogue", "fyn_pool2d_create", "fyn_pool2d_run", "fyn_batchnorm_create",
+    "fyn_conv2d_run", "fyn_conv2d_backend", "fyn_conv2d_set_epilogue", "fyn_conv2d_plan_query", "fyn_pool2d_create", "fyn_pool2d_run", "fyn_batchnorm_create",
     "fyn_batchnorm_load", "fyn_batchnorm_run", "fyn_sigmoid_create", "fyn_sigmoid_run", "fyn_op_destroy",
 ]
 
@@ -253,6 +259,18 @@ class _Op:
         if self._h:
             lib().fyn_op_destroy(self._h)
             self._h = C.c_void_p()
+
+
+def conv_plan_query(stack_rows=1, **desc):
+    """Device-free: the tcgen05 family's shared-memory plan for a conv descriptor (ConvDesc fields as keywords), or None if
+    the family does not cover the layer."""
+    d = ConvDesc()
+    defaults = dict(downsample=1, dilation=1, source_step=1.0, quirks=QUIRKS_REFERENCE)
+    for k, v in {**defaults, **desc}.items():
+        setattr(d, k, v)
+    info = ConvPlanInfo()
+    rc = lib().fyn_conv2d_plan_query(C.byref(d), int(stack_rows), C.byref(info))
+    return info if rc == 0 else None
 
 
 def act_flags(act: str | None):

@@ -1087,6 +1087,32 @@ int tc_ensure_smem(TcKernel fn, int mode, int act, int res, int epi, int device,
 
 int fyn_conv_tc_supported(const fyn_conv_desc *d, int) { return plan_geometry(d, nullptr, 1).ok ? 1 : 0; }
 
+int fyn_conv2d_plan_query(const fyn_conv_desc *desc, int stack_rows, fyn_conv_plan_info *info) {
+    if (!desc || !info || stack_rows < 1 || stack_rows > 2) FYN_FAIL(FYN_ERR_INVALID, "plan query: bad argument");
+    const Geometry g = plan_geometry(desc, nullptr, stack_rows);
+    if (!g.ok) FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 family does not cover this conv");
+    *info = fyn_conv_plan_info{};
+    info->mode = g.mode;
+    info->n = g.N;
+    info->steps = g.nsteps;
+    info->window_rows = g.dyMax - g.dyMin + 1;
+    info->row_advance = g.rowAdvance;
+    info->phases_x = g.opx;
+    info->phases_y = g.opy;
+    info->ring_slots = g.nslots;
+    info->mirror_slots = g.nmirror;
+    info->slot_bytes = g.slotBytes;
+    info->staged_rows = g.nstages;
+    info->stage_bytes = g.stageBytes;
+    info->row_items = g.nitems;
+    info->loader_groups = g.finGroups;
+    info->epilogue_warps = g.epiWarps;
+    info->bias_folded = g.biasFold ? 1 : 0;
+    info->weight_image_bytes = g.wbytes;
+    info->shared_bytes = g.smem;
+    return FYN_OK;
+}
+
 int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     const fyn_conv_desc &d = op->conv;
     // Two job rows stacked along N when the output height allows it and the plan fits (N <= 64, shared memory) without

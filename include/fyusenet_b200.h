@@ -230,6 +230,21 @@ int fyn_conv2d_backend(const fyn_op *op);
 #define FYN_EPILOGUE_SIGMOID 1
 int fyn_conv2d_set_epilogue(fyn_op *op, int function);
 
+/* Diagnostics (no device needed): the shared-memory plan the tcgen05 family would use for `desc`.  `stack_rows` = 1 or 2
+ * job rows per accumulator.  Returns FYN_ERR_UNSUPPORTED if the family does not cover the layer (the direct kernel runs
+ * it).  Used by the device-free planner tests and by tools. */
+typedef struct {
+    int mode;            /* 0 = plane-pair chunks, 1 = pixel-pair chunks (<= 4 input channels) */
+    int n;               /* accumulator columns (output channels x stacked phases, padded to 16) */
+    int steps;           /* tcgen05.mma instructions per job (without the folded-bias step) */
+    int window_rows, row_advance, phases_x, phases_y;
+    int ring_slots, mirror_slots, slot_bytes;
+    int staged_rows, stage_bytes, row_items;
+    int loader_groups, epilogue_warps, bias_folded;
+    size_t weight_image_bytes, shared_bytes;
+} fyn_conv_plan_info;
+int fyn_conv2d_plan_query(const fyn_conv_desc *desc, int stack_rows, fyn_conv_plan_info *info);
+
 /* DeepMaxPoolLayer / DeepAvgPoolLayer / MaxPoolLayer / AvgPoolLayer
  * (fyusenet/gpu/deep/deeppoolinglayer.cpp:38-54,109-190; shaders deep/deepmaxpool.frag, deepavgpool.frag) */
 typedef struct {
