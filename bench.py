@@ -252,6 +252,26 @@ def main():
     net.finish()
     top_ms = net.layer_timing(top_no)[0] / args.steps
     net.enable_timings(False)
+    # ... and as a kernel timed alone: the same layer (same shape, weights and input tensor layout) launched back to back
+    # through the C ABI between two events -- no event pairs inside the stream, dependent launches overlap as in the frame
+    iso_ms = None
+    if top_name == "conv1":
+        lay = synthetic.stylenet_file_layers(KSIZE)[0]
+        nb = lay[3] + lay[3] * lay[1] * lay[1] * lay[2]
+        op1 = capi.Conv2d(ctx, weights[:nb], width=WIDTH, height=HEIGHT, in_channels=3, out_channels=lay[3], kernel=lay[1], flags=capi.FLAG_PRE_RELU)
+        t1 = ctx.tensor(WIDTH, HEIGHT, lay[3])
+        for _ in range(5):
+            op1.run(tin, t1)
+        ctx.stream_sync()
+        ea, eb = ctx.event_create(), ctx.event_create()
+        ctx.event_record(ea)
+        for _ in range(args.steps):
+            op1.run(tin, t1)
+        ctx.event_record(eb)
+        ctx.event_sync(eb)
+        iso_ms = ctx.elapsed_ms(ea, eb) / args.steps
+        op1.destroy()
+        t1.destroy()
     if world > 1:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -334,6 +354,9 @@ def main():
         roof["peak_source"] = f"{which} ({'sustained' if roof['bound'] == 'tensor' else 'copy'} figure, kernel timed inside a long step)"
         roof["ms_per_launch"] = t_s * 1e3
         roof["ms_per_launch_all_layers_timed"] = conv_ms[top]
+        if iso_ms is not None:
+            roof["ms_per_launch_kernel_alone"] = iso_ms
+            roof["frac_kernel_alone"] = (a["bytes"] / (iso_ms / 1e3) / 1e9) / hbm if roof["bound"] == "hbm" else (a["flops"] / (iso_ms / 1e3) / 1e12) / tf_burst
         total_layer_ms = sum(layer_ms.values())
         # whole-network roofline: sum_l max(F_l / P, B_l / BW)
         t_lb = sum(max(v["flops"] / (tf_sust * 1e12), v["bytes"] / (hbm * 1e9)) for v in alg.values())
