@@ -27,9 +27,15 @@ struct DirectConvArgs {
     ActParams act;
     int actFirstOnly, hasRes, reluRes, bnRes;
     int epilogue;         // FYN_EPILOGUE_*
+    int ksplit;           // input planes are split over blockDim.z slices and reduced through shared memory (small grids)
 };
 
-__global__ void __launch_bounds__(128) k_conv_direct(const DirectConvArgs a) {
+// Small grids (ResNet-50's 7x7 and 14x14 layers at batch 1: ~128 blocks whose threads each walk 128 input planes x 9 taps)
+// are bound by the serial depth of that loop, so the input planes are split over blockDim.z slices whose partial sums
+// meet in shared memory (fp32, fixed order: slice 0 + 1 + ... -- deterministic).
+template <bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 1024 : 128) k_conv_direct(const DirectConvArgs a) {
+    __shared__ float4 partial[SPLIT ? 7 : 1][128];
     // linear block index -> (image, output plane, y block, x block); grid.x only (no 65535 limits)
     unsigned bid = blockIdx.x;
     const int xb = bid % a.xBlocks;
@@ -40,12 +46,15 @@ __global__ void __launch_bounds__(128) k_conv_direct(const DirectConvArgs a) {
     const int n = bid / a.nOut;
     const int xo = xb * 32 + threadIdx.x;
     const int yo = yb * 4 + threadIdx.y;
-    if (xo >= a.Wo || yo >= a.Ho) return;
+    const bool active = xo < a.Wo && yo < a.Ho;
+    if (!active && !SPLIT) return;
     const int P = a.in.P;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float cx = (float)P + a.step * ((float)(a.ds * xo) + 0.5f);
     const float cy = (float)P + a.step * ((float)(a.ds * yo) + 0.5f);
-    for (int ip = 0; ip < a.nIn; ip++) {
+    const int per = SPLIT ? (a.nIn + a.ksplit - 1) / a.ksplit : a.nIn;
+    const int ip0 = SPLIT ? threadIdx.z * per : 0, ip1 = min(a.nIn, ip0 + per);
+    for (int ip = ip0; active && ip < ip1; ip++) {
         const float4 *wp = a.w + (size_t)(op * a.nIn + ip) * a.K * a.K * 4;
         for (int ky = 0; ky < a.K; ky++) {
             const int iy = a.fractional ? (int)floorf(cy + a.step * (float)(ky - a.m))
@@ -62,6 +71,19 @@ __global__ void __launch_bounds__(128) k_conv_direct(const DirectConvArgs a) {
                 acc.z = fmaf(v.x, w0.z, fmaf(v.y, w1.z, fmaf(v.z, w2.z, fmaf(v.w, w3.z, acc.z))));
                 acc.w = fmaf(v.x, w0.w, fmaf(v.y, w1.w, fmaf(v.z, w2.w, fmaf(v.w, w3.w, acc.w))));
             }
+        }
+    }
+    if (SPLIT) {
+        const int t = threadIdx.y * 32 + threadIdx.x;
+        if (threadIdx.z > 0) partial[threadIdx.z - 1][t] = acc;
+        __syncthreads();
+        if (threadIdx.z > 0 || !active) return;
+        for (int z = 1; z < a.ksplit; z++) {
+            const float4 q = partial[z - 1][t];
+            acc.x += q.x;
+            acc.y += q.y;
+            acc.z += q.z;
+            acc.w += q.w;
         }
     }
     const float4 s = __ldg(a.scale + op), b = __ldg(a.bias + op);
@@ -123,8 +145,14 @@ int fyn_conv_direct_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res,
     a.yBlocks = (a.Ho + 3) / 4;
     long long blocks = (long long)a.xBlocks * a.yBlocks * a.nOut * a.batch;
     if (blocks > 0x7fffffffLL) FYN_FAIL(FYN_ERR_UNSUPPORTED, "direct conv: %lld blocks exceed the grid limit", blocks);
-    dim3 block(32, 4), grid((unsigned)blocks);
-    k_conv_direct<<<grid, block, 0, s>>>(a);
+    // split the input planes when the grid alone cannot fill the GPU and the reduction is deep
+    a.ksplit = 1;
+    const long long depth = (long long)a.nIn * a.K * a.K;
+    const int sms = op->ctx->prop.multiProcessorCount;
+    while (a.ksplit < 8 && blocks * a.ksplit < 4LL * sms && depth / (a.ksplit * 2) >= 36 && a.nIn >= a.ksplit * 2) a.ksplit *= 2;
+    dim3 block(32, 4, a.ksplit), grid((unsigned)blocks);
+    if (a.ksplit > 1) k_conv_direct<true><<<grid, block, 0, s>>>(a);
+    else k_conv_direct<false><<<grid, block, 0, s>>>(a);
     FYN_CHECK_LAUNCH(op->ctx);
     return FYN_OK;
 }
