@@ -110,7 +110,8 @@ int fyn_conv2d_load_weights(fyn_op *op, const float *wb) {
     if (rc) return rc;
     op->d_scale = op->d_bias + (size_t)nOut * 4;
     if (op->backend == 2) {
-        rc = fyn_conv_tc_create(op, wb);  // (re)packs the fp16 operand images of the tcgen05 family
+        // (re)packs the fp16 operand images of the tcgen05 families
+        rc = deep ? fyn_conv_deep_tc_create(op, wb) : fyn_conv_tc_create(op, wb);
         if (rc) return rc;
     }
     return FYN_OK;
@@ -133,7 +134,7 @@ int fyn_conv2d_create(fyn_ctx *ctx, const fyn_conv_desc *desc, const float *wb, 
         FYN_FAIL(FYN_ERR_INVALID, "conv: empty output %dx%d", wo, ho);
     }
     op->backend = 1;
-    if (desc->backend != 1 && fyn_conv_tc_supported(desc, FYN_F16)) {
+    if (desc->backend != 1 && (fyn_conv_tc_supported(desc, FYN_F16) || fyn_conv_deep_tc_supported(desc))) {
         op->backend = 2;
     } else if (desc->backend == 2) {
         delete op;
@@ -188,9 +189,9 @@ int fyn_conv2d_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn_
     if (in->desc.batch != out->desc.batch) FYN_FAIL(FYN_ERR_INVALID, "conv: batch mismatch %d vs %d", in->desc.batch, out->desc.batch);
     FYN_CUDA(cudaSetDevice(op->ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
-    if (op->backend == 2 && op->tc) {
+    if (op->backend == 2 && (op->tc || op->dtc)) {
         // > 0 means "tensor formats not covered by the tcgen05 family": use the direct kernel
-        rc = fyn_conv_tc_run(op, in, res, out, s);
+        rc = op->dtc ? fyn_conv_deep_tc_run(op, in, res, out, s) : fyn_conv_tc_run(op, in, res, out, s);
         if (rc <= 0) return rc;
     }
     // direct family; deep layers on fp16 tensors use the fp16-truncated weight / fp16 bias sets
@@ -208,6 +209,7 @@ int fyn_op_destroy(fyn_op *op) {
     if (!op) return FYN_OK;
     cudaSetDevice(op->ctx->device);
     if (op->tc) fyn_conv_tc_destroy(op);
+    if (op->dtc) fyn_conv_deep_tc_destroy(op);
     if (op->d_w) cudaFree(op->d_w);
     if (op->d_bias) cudaFree(op->d_bias);
     delete op;

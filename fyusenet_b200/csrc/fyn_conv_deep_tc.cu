@@ -1,0 +1,383 @@
+// fyn_conv_deep_tc.cu -- tcgen05 / TMEM implicit GEMM for the DEEP-tiled convolution layers (ResNet-50).
+//
+// Replaces the instanced blend passes of DeepConvLayer1x1 / DeepConvLayerNxN / DeepGEMMLayer
+// (fyusenet/gpu/deep/deepconvlayer1x1.cpp:67-123, deepconvlayerNxN.cpp:81-211, deepgemmlayer.cpp:66-236: one pass per
+// input tile and kernel row, each touching every output tile) by one GEMM per layer:
+//   D[m][n] = sum_{tap, ci} act(in[pixel(m) + tap][ci]) * W[n][tap][ci]      m = flattened output pixel (image, y, x)
+// Deep images are small (7x7 ... 56x56) and wide (64 ... 2048 channels), so unlike the row-ring kernel of the shallow
+// family (fyn_conv_tc.cu) the M dimension runs over flattened pixels of the whole batch and K is walked in stages of
+// one kernel tap x 64 input channels:
+//   * A stage (128 pixels x 64 channels, 16 KB): loader thread m gathers its pixel's 16 plane texels (8 bytes each; the
+//     tiles of the deep layout, fyusenet/gpu/deep/deeptiler.cpp:63-95), applies the activation at fetch
+//     (shaders/activation.inc) and writes eight 16-byte chunks in the UMMA K-major SWIZZLE_NONE layout
+//     [8-channel chunk][pixel][8 x fp16].  The tile padding of the deep layout supplies the zero border
+//     (gpu/gpulayerbase.h:84-90), so 3x3 taps simply read the neighbouring texels.
+//   * B stage (N x 64 weights, fp16 TRUNCATED like the reference's RGBA32UI weight texture,
+//     deepconvlayerbase.cpp:338-349): pre-packed per (N tile, stage) and fetched with one bulk copy (TMA).
+//   * four tcgen05.mma (M = 128, N <= 128, K = 16) per stage accumulate in TMEM; after the last stage the loader
+//     warps turn into the epilogue: tcgen05.ld -> *bnScale + bias (fp16-rounded like the reference's RGBA16F bias
+//     texture, deepconvlayerbase.cpp:371-394) (+ residual [ReLU] [*bnScale]) -> fp16 texels of the output tiles.
+// One CTA = one (128-pixel, N-tile) output tile; 4 loader/epilogue warps + 1 MMA warp; 4-stage ring.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "fyn_internal.h"
+
+namespace {
+
+constexpr int kM = 128;          // pixels per CTA
+constexpr int kKC = 64;          // input channels per stage (16 planes)
+constexpr int kStages = 4;
+constexpr int kLoadWarps = 4;
+constexpr int kThreadsDeep = (kLoadWarps + 1) * 32;
+constexpr int kAStageBytes = kM * kKC * 2;   // 16 KB
+
+struct DeepTcArgs {
+    TView in, out, res;
+    const uint4 *wimg;           // [ntile][stage][8 chunks][NT][8 halfs]
+    const float *bias, *scale;   // per output channel (padded to planes), the fp16-rounded parameter set
+    int K, ds, mh, Wo, Ho, batch;
+    int nInPlanes, Cout4;        // input planes; output channels rounded up to a multiple of 4
+    int NT, nstages, kcs;        // columns per N tile, stages = K*K*kcs, kcs = Cin / 64
+    long long Mtotal;            // batch * Ho * Wo
+    uint32_t idesc;
+    ActParams act;
+    int hasRes, reluRes, bnRes;
+    int inP, outP, resP;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "DWAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra DWAIT_DONE;\n\t"
+        "bra DWAIT_LOOP;\n\t"
+        "DWAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ uint2 act_h4(uint2 v, const ActParams &a) {
+    if (a.type == 0) return v;
+    if (a.type == 1) {
+        const __half2 z = __float2half2_rn(0.f);
+        __half2 *q = reinterpret_cast<__half2 *>(&v);
+        q[0] = __hmax2(q[0], z);
+        q[1] = __hmax2(q[1], z);
+        return v;
+    }
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&v.x));
+    const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&v.y));
+    return make_uint2(pack_half2(fyn_act(f0.x, a), fyn_act(f0.y, a)), pack_half2(fyn_act(f1.x, a), fyn_act(f1.y, a)));
+}
+
+// dynamic shared memory: [A stages][B stages][plane origin tables][barriers][tmem base]
+__global__ void __launch_bounds__(kThreadsDeep, 1) k_conv_deep_tc(const __grid_constant__ DeepTcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int bStageBytes = a.NT * kKC * 2;
+    unsigned char *sA = smem;
+    unsigned char *sB = sA + kStages * kAStageBytes;
+    int *inOrigin = reinterpret_cast<int *>(sB + kStages * bStageBytes);   // [nInPlanes] element offset of a tile's origin
+    int *outOrigin = inOrigin + a.nInPlanes;                               // [NT/4] (output tensor), then [NT/4] (residual tensor)
+    int *resOrigin = outOrigin + (a.NT >> 2);
+    uint64_t *full = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(resOrigin + (a.NT >> 2)) + 7) & ~uintptr_t(7));
+    uint64_t *empty = full + kStages;
+    uint64_t *done = empty + kStages;
+    uint32_t *tmemBase = reinterpret_cast<uint32_t *>(done + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int ntile = blockIdx.y;
+    const long long m0 = (long long)blockIdx.x * kM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(&full[s], kLoadWarps * 32 + 1);   // every loader thread + the expect_tx arrival of the weight copy
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == kLoadWarps) tmem_alloc(tmemBase, 128);
+    // tile origins: plane q sits at tile (q % tx, q / tx), tiles are tileW x tileH texels apart (deeptiler.cpp:91-94)
+    for (int q = threadIdx.x; q < a.nInPlanes; q += kThreadsDeep) inOrigin[q] = ((q / a.in.tx) * a.in.tileH * a.in.texW + (q % a.in.tx) * a.in.tileW) * 4;
+    for (int k = threadIdx.x; k < (a.NT >> 2); k += kThreadsDeep) {
+        const int p = ntile * (a.NT >> 2) + k;
+        outOrigin[k] = ((p / a.out.tx) * a.out.tileH * a.out.texW + (p % a.out.tx) * a.out.tileW) * 4;
+        resOrigin[k] = a.hasRes ? ((p / a.res.tx) * a.res.tileH * a.res.texW + (p % a.res.tx) * a.res.tileW) * 4 : 0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmemBase;
+
+    if (warp < kLoadWarps) {
+        // ===================== loaders (then epilogue): thread = GEMM row = output pixel =====================
+        const int t = threadIdx.x;
+        const long long m = m0 + t;
+        const bool valid = m < a.Mtotal;
+        const int hw = a.Ho * a.Wo;
+        const int n = valid ? (int)(m / hw) : 0;
+        const int rem = valid ? (int)(m - (long long)n * hw) : 0;
+        const int yo = rem / a.Wo, xo = rem - yo * a.Wo;
+        const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems;
+        const uint4 *wsrc = a.wimg + (size_t)ntile * a.nstages * (bStageBytes >> 4);
+        for (int s = 0; s < a.nstages; s++) {
+            const int st = s % kStages, use = s / kStages;
+            const int tap = s / a.kcs, kc = s - tap * a.kcs;
+            const int ky = tap / a.K, kx = tap - ky * a.K;
+            mbar_wait(&empty[st], (use & 1) ^ 1);
+            if (t == 0) {
+                mbar_expect_tx(&full[st], (uint32_t)bStageBytes);
+                bulk_g2s(sB + (size_t)st * bStageBytes, wsrc + (size_t)s * (bStageBytes >> 4), (uint32_t)bStageBytes, &full[st]);
+            }
+            // texel of this pixel and tap, in tile-local coordinates (origin = the tile's top-left padding texel)
+            const int iy = a.inP + a.ds * yo + ky - a.mh, ix = a.inP + a.ds * xo + kx - a.mh;
+            const __half *px = src + (iy * a.in.texW + ix) * 4;
+            const int *org = inOrigin + kc * (kKC / 4);
+            uint2 v[kKC / 4];
+#pragma unroll
+            for (int j = 0; j < kKC / 4; j++) v[j] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + org[j])) : make_uint2(0u, 0u);
+            unsigned char *dst = sA + (size_t)st * kAStageBytes + t * 16;
+#pragma unroll
+            for (int c = 0; c < kKC / 8; c++) {
+                const uint2 lo = act_h4(v[2 * c], a.act), hi = act_h4(v[2 * c + 1], a.act);
+                *reinterpret_cast<uint4 *>(dst + c * (kM * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            }
+            fence_proxy_async();
+            mbar_arrive(&full[st]);
+        }
+        // ===================== epilogue =====================
+        mbar_wait(done, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        __half *outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((a.outP + yo) * a.out.texW + a.outP + xo) * 4;
+        const __half *resp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems + ((a.resP + yo) * a.res.texW + a.resP + xo) * 4;
+        for (int cg = 0; cg < (a.NT >> 4); cg++) {
+            uint32_t acc[16];
+            tmem_ld16(taddr + cg * 16, acc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int c0 = ntile * a.NT + cg * 16 + 4 * k;      // first channel of this texel
+                if (!valid || c0 >= a.Cout4) continue;
+                const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.scale + c0)), bi = __ldg(reinterpret_cast<const float4 *>(a.bias + c0));
+                float4 r = make_float4(fmaf(__uint_as_float(acc[4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[4 * k + 1]), sc.y, bi.y),
+                                       fmaf(__uint_as_float(acc[4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[4 * k + 3]), sc.w, bi.w));
+                const int pk = cg * 4 + k;                             // plane inside this N tile
+                if (a.hasRes) {
+                    const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(resp + resOrigin[pk]));
+                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+                    const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+                    float4 q = make_float4(f0.x, f0.y, f1.x, f1.y);
+                    if (a.reluRes) q = make_float4(fmaxf(q.x, 0.f), fmaxf(q.y, 0.f), fmaxf(q.z, 0.f), fmaxf(q.w, 0.f));
+                    if (a.bnRes) q = make_float4(q.x * sc.x, q.y * sc.y, q.z * sc.z, q.w * sc.w);
+                    r.x += q.x;
+                    r.y += q.y;
+                    r.z += q.z;
+                    r.w += q.w;
+                }
+                *reinterpret_cast<uint2 *>(outp + outOrigin[pk]) = make_uint2(pack_half2(r.x, r.y), pack_half2(r.z, r.w));
+            }
+        }
+    } else {
+        // ===================== MMA issuer =====================
+        const uint64_t hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
+        const uint32_t aLbo = ((uint32_t)(kM * 16) >> 4) << 16, bLbo = ((uint32_t)(a.NT * 16) >> 4) << 16;
+        for (int s = 0; s < a.nstages; s++) {
+            const int st = s % kStages, use = s / kStages;
+            if (elect_one()) {
+                mbar_wait(&full[st], use & 1);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(sA + (size_t)st * kAStageBytes) >> 4, b0 = smem_u32(sB + (size_t)st * bStageBytes) >> 4;
+#pragma unroll
+                for (int j = 0; j < kKC / 16; j++)
+                    umma_f16(tmem, hi | (uint64_t)(aLbo | (a0 + (uint32_t)(j * 2 * kM))), hi | (uint64_t)(bLbo | (b0 + (uint32_t)(j * 2 * a.NT))), a.idesc,
+                             (s > 0 || j > 0) ? 1u : 0u);
+                umma_commit(&empty[st]);
+                if (s == a.nstages - 1) umma_commit(done);
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kLoadWarps) tmem_dealloc(tmem, 128);
+}
+
+}  // namespace
+
+struct DeepTcPlan {
+    DeepTcArgs args{};
+    uint4 *d_wimg = nullptr;
+    size_t wimgBytes = 0;
+    size_t smemBytes = 0;
+    int ntiles = 0;
+};
+
+int fyn_conv_deep_tc_supported(const fyn_conv_desc *d) {
+    if (!(d->flags & FYN_FLAG_DEEP) || d->fractional || d->dilation != 1) return 0;
+    if (d->kernel != 1 && d->kernel != 3) return 0;
+    if (d->downsample != 1 && d->downsample != 2) return 0;
+    if (d->in_channels % kKC != 0) return 0;
+    if (d->in_padding < (d->kernel - 1) / 2) return 0;       // the tile padding must supply the border zeros
+    if (d->flags & FYN_FLAG_PRE_CLIP) return 0;
+    return 1;
+}
+
+int fyn_conv_deep_tc_create(fyn_op *op, const float *wb) {
+    const fyn_conv_desc &d = op->conv;
+    DeepTcPlan *plan = op->dtc ? op->dtc : new DeepTcPlan();
+    op->dtc = plan;
+    DeepTcArgs &a = plan->args;
+    const int K = d.kernel, Ci = d.in_channels, Co = d.out_channels;
+    const int co16 = ((Co + 15) / 16) * 16;
+    a.NT = std::min(128, co16);
+    plan->ntiles = (co16 + a.NT - 1) / a.NT;
+    a.K = K;
+    a.ds = d.downsample;
+    a.mh = (K - 1) / 2;
+    a.kcs = Ci / kKC;
+    a.nstages = K * K * a.kcs;
+    a.nInPlanes = (Ci + 3) / 4;
+    a.Cout4 = ((Co + 3) / 4) * 4;
+    a.idesc = (1u << 4) | ((uint32_t)(a.NT >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);   // F32 accum, F16 x F16, K-major A/B
+    // weight image [ntile][stage = (tap, kc)][chunk][n][8], fp16 truncated (gpu/floatconversion.cpp:44-58)
+    const size_t stageHalfs = (size_t)8 * a.NT * 8;
+    std::vector<__half> img((size_t)plan->ntiles * a.nstages * stageHalfs, __float2half(0.f));
+    const float *W = wb + Co;   // [Co][K][K][Ci]
+    for (int nt = 0; nt < plan->ntiles; nt++)
+        for (int tap = 0; tap < K * K; tap++)
+            for (int kc = 0; kc < a.kcs; kc++) {
+                __half *dst = img.data() + ((size_t)nt * a.nstages + (size_t)tap * a.kcs + kc) * stageHalfs;
+                for (int n = 0; n < a.NT; n++) {
+                    const int o = nt * a.NT + n;
+                    if (o >= Co) continue;
+                    const float *w = W + ((size_t)o * K * K + tap) * Ci + (size_t)kc * kKC;
+                    for (int c = 0; c < 8; c++)
+                        for (int e = 0; e < 8; e++) dst[((size_t)c * a.NT + n) * 8 + e] = __float2half_rz(fyn_half_trunc_host(w[c * 8 + e]));
+                }
+            }
+    const size_t bytes = img.size() * sizeof(__half);
+    FYN_CUDA(cudaSetDevice(op->ctx->device));
+    if (plan->d_wimg && plan->wimgBytes < bytes) {
+        cudaFree(plan->d_wimg);
+        plan->d_wimg = nullptr;
+    }
+    if (!plan->d_wimg) {
+        FYN_CUDA(cudaMalloc((void **)&plan->d_wimg, bytes));
+        plan->wimgBytes = bytes;
+    }
+    FYN_CUDA(cudaMemcpy(plan->d_wimg, img.data(), bytes, cudaMemcpyHostToDevice));
+    a.wimg = plan->d_wimg;
+    plan->smemBytes = (size_t)kStages * kAStageBytes + (size_t)kStages * a.NT * kKC * 2 + ((size_t)a.nInPlanes + 2 * (a.NT / 4)) * 4 + 8 + (2 * kStages + 1) * 8 + 16;
+    static size_t maxSmem[64] = {0};
+    size_t &cur = maxSmem[op->ctx->device & 63];
+    if (plan->smemBytes > cur) {
+        FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smemBytes));
+        cur = plan->smemBytes;
+    }
+    return FYN_OK;
+}
+
+int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn_tensor *out, cudaStream_t stream) {
+    DeepTcPlan *plan = op->dtc;
+    const fyn_conv_desc &d = op->conv;
+    if (in->desc.dtype != FYN_F16 || out->desc.dtype != FYN_F16 || (res && res->desc.dtype != FYN_F16)) return 1;   // fp32 storage: direct kernel
+    if (in->desc.order != FYN_ORDER_DEEP || out->desc.order != FYN_ORDER_DEEP || in->geom.packing != 4) return 1;
+    if (op->epilogue != FYN_EPILOGUE_NONE) return 1;
+    DeepTcArgs a = plan->args;
+    a.in = fyn_make_view(in);
+    a.out = fyn_make_view(out);
+    a.res = fyn_make_view(res);
+    a.Wo = op->Wo;
+    a.Ho = op->Ho;
+    a.batch = in->desc.batch;
+    a.Mtotal = (long long)a.batch * a.Wo * a.Ho;
+    a.inP = d.in_padding;
+    a.outP = d.out_padding;
+    a.resP = d.res_padding;
+    a.act = fyn_act_from_flags(d.flags, d.leaky, d.clip_lo, d.clip_hi);
+    a.hasRes = (d.flags & FYN_FLAG_RESIDUAL_INPUT) != 0;
+    a.reluRes = (d.flags & FYN_FLAG_RELU_ON_RESIDUAL) != 0;
+    a.bnRes = (d.flags & FYN_FLAG_BATCHNORM_ON_RESIDUAL) != 0;
+    // the fp16-rounded parameter set of the deep family (fyn_conv.cu: second half of d_bias)
+    const int nOut = (d.out_channels + 3) / 4;
+    a.bias = op->d_bias + (size_t)nOut * 8;
+    a.scale = a.bias + (size_t)nOut * 4;
+    const long long mtiles = (a.Mtotal + kM - 1) / kM;
+    dim3 grid((unsigned)mtiles, (unsigned)plan->ntiles);
+    k_conv_deep_tc<<<grid, kThreadsDeep, plan->smemBytes, stream>>>(a);
+    FYN_CHECK_LAUNCH(op->ctx);
+    return FYN_OK;
+}
+
+void fyn_conv_deep_tc_destroy(fyn_op *op) {
+    if (!op->dtc) return;
+    if (op->dtc->d_wimg) cudaFree(op->dtc->d_wimg);
+    delete op->dtc;
+    op->dtc = nullptr;
+}

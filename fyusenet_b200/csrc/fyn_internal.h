@@ -86,6 +86,7 @@ struct ActParams {
 ActParams fyn_act_from_flags(unsigned flags, float leaky, float lo, float hi);
 
 struct ConvTcPlan;  // tcgen05 plan (fyn_conv_tc.cu)
+struct DeepTcPlan;  // tcgen05 plan of the deep-tiled family (fyn_conv_deep_tc.cu)
 
 struct fyn_op {
     fyn_ctx *ctx = nullptr;
@@ -99,6 +100,7 @@ struct fyn_op {
     int backend = 0;           // 1 direct, 2 tcgen05
     int epilogue = 0;          // FYN_EPILOGUE_*: element-wise function fused behind the convolution
     ConvTcPlan *tc = nullptr;
+    DeepTcPlan *dtc = nullptr;
     // pool
     fyn_pool_desc pool{};
     // bn
@@ -112,6 +114,12 @@ int fyn_conv_tc_supported(const fyn_conv_desc *d, int dtype_hint);
 int fyn_conv_tc_create(fyn_op *op, const float *wb);
 int fyn_conv_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn_tensor *out, cudaStream_t s);
 void fyn_conv_tc_destroy(fyn_op *op);
+
+// tcgen05 path for deep-tiled tensors (fyn_conv_deep_tc.cu)
+int fyn_conv_deep_tc_supported(const fyn_conv_desc *d);
+int fyn_conv_deep_tc_create(fyn_op *op, const float *wb);
+int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn_tensor *out, cudaStream_t s);
+void fyn_conv_deep_tc_destroy(fyn_op *op);
 
 // direct path (fyn_conv_direct.cu)
 int fyn_conv_direct_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn_tensor *out, cudaStream_t s);
