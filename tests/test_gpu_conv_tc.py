@@ -190,3 +190,36 @@ def test_tc_long_strips_repeated(case):
         for o in (tin, tout, op):
             o.destroy()
     assert rel_l2(outs[capi.BACKEND_TC], outs[capi.BACKEND_DIRECT]) <= 2e-3
+
+
+@pytest.mark.parametrize("k,ds,ci,co,inp,outp,postbn,res,relures,bnres,size,batch", [
+    (1, 1, 64, 256, 0, 0, True, False, False, False, 14, 2),     # bottleneck expand, 1x1
+    (1, 1, 256, 64, 0, 1, True, False, False, False, 14, 1),     # reduce, output padded for the following 3x3
+    (3, 1, 64, 64, 1, 0, True, False, False, False, 28, 2),      # 3x3 on padded tiles
+    (3, 2, 128, 128, 1, 0, True, False, False, False, 14, 3),    # 3x3 stride 2
+    (1, 2, 256, 512, 0, 0, False, False, False, False, 14, 2),   # projection shortcut, stride 2
+    (1, 1, 128, 512, 0, 0, True, True, True, True, 7, 3),        # residual + ReLU + BN on the residual
+    (1, 1, 2048, 1000, 0, 0, False, False, False, False, 1, 3),  # GEMM72: 1x1 spatial, N tile with a ragged tail
+    (3, 1, 512, 512, 1, 0, True, False, False, False, 7, 1),     # deepest 3x3: 72 K stages
+])
+def test_deep_conv_tcgen05(k, ds, ci, co, inp, outp, postbn, res, relures, bnres, size, batch):
+    """Deep-tiled convolutions on the tensor cores (fyn_conv_deep_tc.cu) against the oracle's deep semantics (fp16-truncated
+    weights, fp16 bias / BN parameters, zero border from the tile padding) and against the direct kernel."""
+    rng = np.random.default_rng(k * 100 + ci + co + size)
+    x = rng.normal(size=(batch, ci, size, size)).astype(np.float32)
+    wb = random_wb(rng, ci, co, k, post_bn=postbn)
+    so = size // ds
+    residual = rng.normal(size=(batch, co, so, so)).astype(np.float32) if res else None
+    fl = capi.FLAG_PRE_RELU | (capi.FLAG_POST_BATCHNORM if postbn else 0) | (capi.FLAG_RELU_ON_RESIDUAL if relures else 0) | \
+         (capi.FLAG_BATCHNORM_ON_RESIDUAL if bnres else 0)
+    kw = dict(out_channels=co, kernel=k, downsample=ds, in_pad=inp, out_pad=outp, flags=fl, residual=residual, deep=True)
+    y, be, _ = conv_gpu(x, wb, backend=capi.BACKEND_TC, want_op=True, **kw)
+    assert be == 2
+    yd = conv_gpu(x, wb, backend=capi.BACKEND_DIRECT, **kw)
+    ofl = (fo.POST_BATCHNORM if postbn else 0) | (fo.RELU_ON_RESIDUAL if relures else 0) | (fo.BATCHNORM_ON_RESIDUAL if bnres else 0)
+    xs = half(x)
+    ref = np.stack([fo.conv2d(xs[i], wb, co, k, downsample=ds, in_pad=inp, out_pad=outp, act=fo.ACT_RELU, flags=ofl, deep=True,
+                              residual=None if residual is None else half(residual[i]), prec=fo.FP16_STORE) for i in range(batch)])
+    # same operands as the oracle (truncated fp16 weights, fp16 activations), fp32 accumulation in a different order
+    assert_close_f16(y, ref, None, ulps=1.01, extra_abs=1e-4 * max(1.0, float(np.abs(ref).max()) / 8))
+    assert rel_l2(y, yd) <= 1e-3
