@@ -17,7 +17,8 @@
 //   * four tcgen05.mma (M = 128, N <= 128, K = 16) per stage accumulate in TMEM; after the last stage the loader
 //     warps turn into the epilogue: tcgen05.ld -> *bnScale + bias (fp16-rounded like the reference's RGBA16F bias
 //     texture, deepconvlayerbase.cpp:371-394) (+ residual [ReLU] [*bnScale]) -> fp16 texels of the output tiles.
-// One CTA = one (128-pixel, N-tile) output tile; 4 loader/epilogue warps + 1 MMA warp; 4-stage ring.
+// One CTA = one (128-pixel, N-tile) output tile; 4 loader/epilogue warps + 1 MMA warp; stage ring of min(4, stages)
+// entries, so that the many short-K layers (1x1 convs on 64 channels: a single stage) fit several CTAs per SM.
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -28,7 +29,7 @@ namespace {
 
 constexpr int kM = 128;          // pixels per CTA
 constexpr int kKC = 64;          // input channels per stage (16 planes)
-constexpr int kStages = 4;
+constexpr int kMaxRing = 4;      // stage ring depth (fewer for layers with fewer stages: more CTAs fit an SM)
 constexpr int kLoadWarps = 4;
 constexpr int kThreadsDeep = (kLoadWarps + 1) * 32;
 constexpr int kAStageBytes = kM * kKC * 2;   // 16 KB
@@ -40,6 +41,7 @@ struct DeepTcArgs {
     int K, ds, mh, Wo, Ho, batch;
     int nInPlanes, Cout4;        // input planes; output channels rounded up to a multiple of 4
     int NT, nstages, kcs;        // columns per N tile, stages = K*K*kcs, kcs = Cin / 64
+    int ring;                    // stage ring depth = min(kMaxRing, nstages)
     long long Mtotal;            // batch * Ho * Wo
     uint32_t idesc;
     ActParams act;
@@ -136,17 +138,17 @@ __device__ __forceinline__ uint2 act_h4(uint2 v, const ActParams &a) {
 }
 
 // dynamic shared memory: [A stages][B stages][plane origin tables][barriers][tmem base]
-__global__ void __launch_bounds__(kThreadsDeep, 1) k_conv_deep_tc(const __grid_constant__ DeepTcArgs a) {
+__global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_constant__ DeepTcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int bStageBytes = a.NT * kKC * 2;
     unsigned char *sA = smem;
-    unsigned char *sB = sA + kStages * kAStageBytes;
-    int *inOrigin = reinterpret_cast<int *>(sB + kStages * bStageBytes);   // [nInPlanes] element offset of a tile's origin
+    unsigned char *sB = sA + a.ring * kAStageBytes;
+    int *inOrigin = reinterpret_cast<int *>(sB + a.ring * bStageBytes);   // [nInPlanes] element offset of a tile's origin
     int *outOrigin = inOrigin + a.nInPlanes;                               // [NT/4] (output tensor), then [NT/4] (residual tensor)
     int *resOrigin = outOrigin + (a.NT >> 2);
     uint64_t *full = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(resOrigin + (a.NT >> 2)) + 7) & ~uintptr_t(7));
-    uint64_t *empty = full + kStages;
-    uint64_t *done = empty + kStages;
+    uint64_t *empty = full + kMaxRing;
+    uint64_t *done = empty + kMaxRing;
     uint32_t *tmemBase = reinterpret_cast<uint32_t *>(done + 1);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(kThreadsDeep, 1) k_conv_deep_tc(const __grid_c
     const long long m0 = (long long)blockIdx.x * kM;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) {
+        for (int s = 0; s < a.ring; s++) {
             mbar_init(&full[s], kLoadWarps * 32 + 1);   // every loader thread + the expect_tx arrival of the weight copy
             mbar_init(&empty[s], 1);
         }
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(kThreadsDeep, 1) k_conv_deep_tc(const __grid_c
         const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems;
         const uint4 *wsrc = a.wimg + (size_t)ntile * a.nstages * (bStageBytes >> 4);
         for (int s = 0; s < a.nstages; s++) {
-            const int st = s % kStages, use = s / kStages;
+            const int st = s % a.ring, use = s / a.ring;
             const int tap = s / a.kcs, kc = s - tap * a.kcs;
             const int ky = tap / a.K, kx = tap - ky * a.K;
             mbar_wait(&empty[st], (use & 1) ^ 1);
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(kThreadsDeep, 1) k_conv_deep_tc(const __grid_c
         const uint64_t hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
         const uint32_t aLbo = ((uint32_t)(kM * 16) >> 4) << 16, bLbo = ((uint32_t)(a.NT * 16) >> 4) << 16;
         for (int s = 0; s < a.nstages; s++) {
-            const int st = s % kStages, use = s / kStages;
+            const int st = s % a.ring, use = s / a.ring;
             if (elect_one()) {
                 mbar_wait(&full[st], use & 1);
                 tc_fence_after();
@@ -333,7 +335,8 @@ int fyn_conv_deep_tc_create(fyn_op *op, const float *wb) {
     }
     FYN_CUDA(cudaMemcpy(plan->d_wimg, img.data(), bytes, cudaMemcpyHostToDevice));
     a.wimg = plan->d_wimg;
-    plan->smemBytes = (size_t)kStages * kAStageBytes + (size_t)kStages * a.NT * kKC * 2 + ((size_t)a.nInPlanes + 2 * (a.NT / 4)) * 4 + 8 + (2 * kStages + 1) * 8 + 16;
+    a.ring = std::min(kMaxRing, a.nstages);
+    plan->smemBytes = (size_t)a.ring * kAStageBytes + (size_t)a.ring * a.NT * kKC * 2 + ((size_t)a.nInPlanes + 2 * (a.NT / 4)) * 4 + 8 + (2 * kMaxRing + 1) * 8 + 16;
     static size_t maxSmem[64] = {0};
     size_t &cur = maxSmem[op->ctx->device & 63];
     if (plan->smemBytes > cur) {

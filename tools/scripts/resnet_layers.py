@@ -3,7 +3,7 @@ sys.path.insert(0, '.')
 import numpy as np
 from fyusenet_b200 import hostapi
 rng = np.random.default_rng(0)
-for batch in (1, 8):
+for batch in (1, 32):
     net = hostapi.ResNet50(batch=batch)
     net.load_weights((rng.standard_normal(25576046) * 0.01).astype(np.float32))
     net.setup()
