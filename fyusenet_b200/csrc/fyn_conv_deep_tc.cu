@@ -42,6 +42,7 @@ struct DeepTcArgs {
     int nInPlanes, Cout4;        // input planes; output channels rounded up to a multiple of 4
     int NT, nstages, kcs;        // columns per N tile, stages = K*K*kcs, kcs = Cin / 64
     int ring;                    // stage ring depth = min(kMaxRing, nstages)
+    int tapPacked;               // 1: single input plane (<= 4 channels): a stage holds 16 kernel taps x 4 channels (ResNet stem)
     long long Mtotal;            // batch * Ho * Wo
     uint32_t idesc;
     ActParams act;
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_cons
     }
     if (warp == kLoadWarps) tmem_alloc(tmemBase, 128);
     // tile origins: plane q sits at tile (q % tx, q / tx), tiles are tileW x tileH texels apart (deeptiler.cpp:91-94)
-    for (int q = threadIdx.x; q < a.nInPlanes; q += kThreadsDeep) inOrigin[q] = ((q / a.in.tx) * a.in.tileH * a.in.texW + (q % a.in.tx) * a.in.tileW) * 4;
+    for (int q = threadIdx.x; q < a.nInPlanes && !a.tapPacked; q += kThreadsDeep) inOrigin[q] = ((q / a.in.tx) * a.in.tileH * a.in.texW + (q % a.in.tx) * a.in.tileW) * 4;
     for (int k = threadIdx.x; k < (a.NT >> 2); k += kThreadsDeep) {
         const int p = ntile * (a.NT >> 2) + k;
         outOrigin[k] = ((p / a.out.tx) * a.out.tileH * a.out.texW + (p % a.out.tx) * a.out.tileW) * 4;
@@ -196,13 +197,26 @@ __global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_cons
                 mbar_expect_tx(&full[st], (uint32_t)bStageBytes);
                 bulk_g2s(sB + (size_t)st * bStageBytes, wsrc + (size_t)s * (bStageBytes >> 4), (uint32_t)bStageBytes, &full[st]);
             }
-            // texel of this pixel and tap, in tile-local coordinates (origin = the tile's top-left padding texel)
-            const int iy = a.inP + a.ds * yo + ky - a.mh, ix = a.inP + a.ds * xo + kx - a.mh;
-            const __half *px = src + (iy * a.in.texW + ix) * 4;
-            const int *org = inOrigin + kc * (kKC / 4);
             uint2 v[kKC / 4];
+            if (!a.tapPacked) {
+                // texel of this pixel and tap, in tile-local coordinates (origin = the tile's top-left padding texel)
+                const int iy = a.inP + a.ds * yo + ky - a.mh, ix = a.inP + a.ds * xo + kx - a.mh;
+                const __half *px = src + (iy * a.in.texW + ix) * 4;
+                const int *org = inOrigin + kc * (kKC / 4);
 #pragma unroll
-            for (int j = 0; j < kKC / 4; j++) v[j] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + org[j])) : make_uint2(0u, 0u);
+                for (int j = 0; j < kKC / 4; j++) v[j] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + org[j])) : make_uint2(0u, 0u);
+            } else {
+                // one plane, sixteen taps per stage; the texture clamps at its edge (base/buffermanager.cpp:657-670), which is
+                // how the under-padded 7x7 stem (P = 1 < 3) still sees a zero border: the outermost texels are padding
+#pragma unroll
+                for (int j = 0; j < kKC / 4; j++) {
+                    const int tp = min(s * (kKC / 4) + j, a.K * a.K - 1);          // taps beyond K*K carry zero weights
+                    const int tky = tp / a.K, tkx = tp - tky * a.K;
+                    const int iy = min(max(a.inP + a.ds * yo + tky - a.mh, 0), a.in.texH - 1);
+                    const int ix = min(max(a.inP + a.ds * xo + tkx - a.mh, 0), a.in.texW - 1);
+                    v[j] = valid ? __ldg(reinterpret_cast<const uint2 *>(src + (iy * a.in.texW + ix) * 4)) : make_uint2(0u, 0u);
+                }
+            }
             unsigned char *dst = sA + (size_t)st * kAStageBytes + t * 16;
 #pragma unroll
             for (int c = 0; c < kKC / 8; c++) {
@@ -282,10 +296,14 @@ struct DeepTcPlan {
 
 int fyn_conv_deep_tc_supported(const fyn_conv_desc *d) {
     if (!(d->flags & FYN_FLAG_DEEP) || d->fractional || d->dilation != 1) return 0;
-    if (d->kernel != 1 && d->kernel != 3) return 0;
     if (d->downsample != 1 && d->downsample != 2) return 0;
-    if (d->in_channels % kKC != 0) return 0;
-    if (d->in_padding < (d->kernel - 1) / 2) return 0;       // the tile padding must supply the border zeros
+    if (d->in_channels <= 4) {
+        if (d->kernel > 7) return 0;                          // tap-packed mode (single plane): <= 49 taps = 4 stages
+    } else {
+        if (d->kernel != 1 && d->kernel != 3) return 0;
+        if (d->in_channels % kKC != 0) return 0;
+        if (d->in_padding < (d->kernel - 1) / 2) return 0;   // the tile padding must supply the border zeros
+    }
     if (d->flags & FYN_FLAG_PRE_CLIP) return 0;
     return 1;
 }
@@ -302,8 +320,9 @@ int fyn_conv_deep_tc_create(fyn_op *op, const float *wb) {
     a.K = K;
     a.ds = d.downsample;
     a.mh = (K - 1) / 2;
-    a.kcs = Ci / kKC;
-    a.nstages = K * K * a.kcs;
+    a.tapPacked = Ci <= 4 ? 1 : 0;
+    a.kcs = a.tapPacked ? 1 : Ci / kKC;
+    a.nstages = a.tapPacked ? (K * K + 15) / 16 : K * K * a.kcs;
     a.nInPlanes = (Ci + 3) / 4;
     a.Cout4 = ((Co + 3) / 4) * 4;
     a.idesc = (1u << 4) | ((uint32_t)(a.NT >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);   // F32 accum, F16 x F16, K-major A/B
@@ -311,7 +330,21 @@ int fyn_conv_deep_tc_create(fyn_op *op, const float *wb) {
     const size_t stageHalfs = (size_t)8 * a.NT * 8;
     std::vector<__half> img((size_t)plan->ntiles * a.nstages * stageHalfs, __float2half(0.f));
     const float *W = wb + Co;   // [Co][K][K][Ci]
-    for (int nt = 0; nt < plan->ntiles; nt++)
+    if (a.tapPacked) {
+        // k index inside a stage = (tap % 16) * 4 + channel: chunk c holds taps 2c, 2c+1 of the stage
+        for (int nt = 0; nt < plan->ntiles; nt++)
+            for (int tap = 0; tap < K * K; tap++) {
+                __half *dst = img.data() + ((size_t)nt * a.nstages + tap / 16) * stageHalfs;
+                const int j = tap % 16;
+                for (int n = 0; n < a.NT; n++) {
+                    const int o = nt * a.NT + n;
+                    if (o >= Co) continue;
+                    for (int c = 0; c < Ci; c++)
+                        dst[((size_t)(j / 2) * a.NT + n) * 8 + (j & 1) * 4 + c] = __float2half_rz(fyn_half_trunc_host(W[((size_t)o * K * K + tap) * Ci + c]));
+                }
+            }
+    }
+    for (int nt = 0; nt < plan->ntiles && !a.tapPacked; nt++)
         for (int tap = 0; tap < K * K; tap++)
             for (int kc = 0; kc < a.kcs; kc++) {
                 __half *dst = img.data() + ((size_t)nt * a.nstages + (size_t)tap * a.kcs + kc) * stageHalfs;
@@ -350,7 +383,8 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     DeepTcPlan *plan = op->dtc;
     const fyn_conv_desc &d = op->conv;
     if (in->desc.dtype != FYN_F16 || out->desc.dtype != FYN_F16 || (res && res->desc.dtype != FYN_F16)) return 1;   // fp32 storage: direct kernel
-    if (in->desc.order != FYN_ORDER_DEEP || out->desc.order != FYN_ORDER_DEEP || in->geom.packing != 4) return 1;
+    // (a single-plane input is laid out identically as a shallow and as a deep tensor: the stem reads the shallow BN output)
+    if ((in->desc.order != FYN_ORDER_DEEP && !plan->args.tapPacked) || out->desc.order != FYN_ORDER_DEEP || in->geom.packing != 4) return 1;
     if (op->epilogue != FYN_EPILOGUE_NONE) return 1;
     DeepTcArgs a = plan->args;
     a.in = fyn_make_view(in);

@@ -201,6 +201,8 @@ def test_tc_long_strips_repeated(case):
     (1, 1, 128, 512, 0, 0, True, True, True, True, 7, 3),        # residual + ReLU + BN on the residual
     (1, 1, 2048, 1000, 0, 0, False, False, False, False, 1, 3),  # GEMM72: 1x1 spatial, N tile with a ragged tail
     (3, 1, 512, 512, 1, 0, True, False, False, False, 7, 1),     # deepest 3x3: 72 K stages
+    (7, 2, 3, 64, 1, 1, True, False, False, False, 32, 2),       # the stem: one input plane, 49 taps packed 16 per stage, under-padded
+    (3, 1, 4, 24, 1, 0, False, False, False, False, 9, 1),       # tap-packed, four channels
 ])
 def test_deep_conv_tcgen05(k, ds, ci, co, inp, outp, postbn, res, relures, bnres, size, batch):
     """Deep-tiled convolutions on the tensor cores (fyn_conv_deep_tc.cu) against the oracle's deep semantics (fp16-truncated
