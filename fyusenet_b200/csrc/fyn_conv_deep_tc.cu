@@ -17,7 +17,8 @@
 //   * four tcgen05.mma (M = 128, N <= 128, K = 16) per stage accumulate in TMEM; after the last stage the loader
 //     warps turn into the epilogue: tcgen05.ld -> *bnScale + bias (fp16-rounded like the reference's RGBA16F bias
 //     texture, deepconvlayerbase.cpp:371-394) (+ residual [ReLU] [*bnScale]) -> fp16 texels of the output tiles.
-// One CTA = one (128-pixel, N-tile) output tile; 4 loader/epilogue warps + 1 MMA warp; stage ring of min(4, stages)
+// One CTA = one (128-pixel, N-tile) output tile; 2 x 4 loader/epilogue warps (alternate stages, so that two gathers
+// are in flight) + 1 MMA warp; stage ring of min(4, stages)
 // entries, so that the many short-K layers (1x1 convs on 64 channels: a single stage) fit several CTAs per SM.
 #include <algorithm>
 #include <cstring>
@@ -30,7 +31,8 @@ namespace {
 constexpr int kM = 128;          // pixels per CTA
 constexpr int kKC = 64;          // input channels per stage (16 planes)
 constexpr int kMaxRing = 4;      // stage ring depth (fewer for layers with fewer stages: more CTAs fit an SM)
-constexpr int kLoadWarps = 4;
+constexpr int kLoadSets = 2;     // two sets of four loader warps take alternate stages: two gathers are in flight per CTA
+constexpr int kLoadWarps = 4 * kLoadSets;
 constexpr int kThreadsDeep = (kLoadWarps + 1) * 32;
 constexpr int kAStageBytes = kM * kKC * 2;   // 16 KB
 
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_cons
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.ring; s++) {
-            mbar_init(&full[s], kLoadWarps * 32 + 1);   // every loader thread + the expect_tx arrival of the weight copy
+            mbar_init(&full[s], kM + 1);   // the 128 threads of the set that loads the stage + the expect_tx arrival of its weight copy
             mbar_init(&empty[s], 1);
         }
         mbar_init(done, 1);
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_cons
 
     if (warp < kLoadWarps) {
         // ===================== loaders (then epilogue): thread = GEMM row = output pixel =====================
-        const int t = threadIdx.x;
+        const int t = threadIdx.x & (kM - 1), set = warp >> 2;
         const long long m = m0 + t;
         const bool valid = m < a.Mtotal;
         const int hw = a.Ho * a.Wo;
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_cons
         const int yo = rem / a.Wo, xo = rem - yo * a.Wo;
         const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems;
         const uint4 *wsrc = a.wimg + (size_t)ntile * a.nstages * (bStageBytes >> 4);
-        for (int s = 0; s < a.nstages; s++) {
+        for (int s = set; s < a.nstages; s += kLoadSets) {
             const int st = s % a.ring, use = s / a.ring;
             const int tap = s / a.kcs, kc = s - tap * a.kcs;
             const int ky = tap / a.K, kx = tap - ky * a.K;
@@ -229,10 +231,10 @@ __global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_cons
         // ===================== epilogue =====================
         mbar_wait(done, 0);
         tc_fence_after();
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // TMEM lane quarter of this warp
         __half *outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((a.outP + yo) * a.out.texW + a.outP + xo) * 4;
         const __half *resp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems + ((a.resP + yo) * a.res.texW + a.resP + xo) * 4;
-        for (int cg = 0; cg < (a.NT >> 4); cg++) {
+        for (int cg = set; cg < (a.NT >> 4); cg += kLoadSets) {           // the two sets split the column groups
             uint32_t acc[16];
             tmem_ld16(taddr + cg * 16, acc);
             tmem_ld_wait();
