@@ -20,6 +20,8 @@ struct PoolArgs {
     ActParams act;
 };
 
+// PX/PY > 0: compile-time window (all fetches of a texel in flight at once); 0: run-time window
+template <int PX, int PY>
 __global__ void __launch_bounds__(128) k_pool(const PoolArgs a) {
     unsigned bid = blockIdx.x;
     const int xBlocks = (a.Wo + 31) / 32, yBlocks = (a.Ho + 3) / 4;
@@ -33,8 +35,11 @@ __global__ void __launch_bounds__(128) k_pool(const PoolArgs a) {
     if (xo >= a.Wo || yo >= a.Ho) return;
     const int bx = a.in.P + a.dx * xo + a.off, by = a.in.P + a.dy * yo + a.off;
     float4 r = a.isMax ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < a.py; j++)
-        for (int i = 0; i < a.px; i++) {
+    const int px = PX ? PX : a.px, py = PY ? PY : a.py;
+#pragma unroll
+    for (int j = 0; j < py; j++)
+#pragma unroll
+        for (int i = 0; i < px; i++) {
             float4 v = fyn_fetch(a.in, n, t, bx + i, by + j);
             if (!(a.quirk3 && i == 2)) v = fyn_act4(v, a.act);
             if (a.isMax) {
@@ -51,6 +56,55 @@ __global__ void __launch_bounds__(128) k_pool(const PoolArgs a) {
         }
     if (!a.isMax) r = make_float4(r.x * a.inv, r.y * a.inv, r.z * a.inv, r.w * a.inv);
     fyn_store_texel(a.out, n, t, a.outP + xo, a.outP + yo, r);
+}
+
+// large windows (global pooling): one warp per output texel, lanes stride over the window, shuffle reduction
+__global__ void __launch_bounds__(128) k_pool_warp(const PoolArgs a) {
+    const long long o = (long long)blockIdx.x * 4 + threadIdx.y;
+    const long long perImage = (long long)a.Wo * a.Ho * a.tiles;
+    if (o >= perImage * a.batch) return;
+    const int n = (int)(o / perImage);
+    int r = (int)(o - (long long)n * perImage);
+    const int t = r / (a.Wo * a.Ho);
+    r -= t * a.Wo * a.Ho;
+    const int yo = r / a.Wo, xo = r - yo * a.Wo;
+    const int bx = a.in.P + a.dx * xo + a.off, by = a.in.P + a.dy * yo + a.off;
+    float4 acc = a.isMax ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int win = a.px * a.py;
+    for (int e = threadIdx.x; e < win; e += 32) {
+        const int j = e / a.px, i = e - j * a.px;
+        float4 v = fyn_act4(fyn_fetch(a.in, n, t, bx + i, by + j), a.act);
+        if (a.isMax) {
+            acc.x = fmaxf(acc.x, v.x);
+            acc.y = fmaxf(acc.y, v.y);
+            acc.z = fmaxf(acc.z, v.z);
+            acc.w = fmaxf(acc.w, v.w);
+        } else {
+            acc.x += v.x;
+            acc.y += v.y;
+            acc.z += v.z;
+            acc.w += v.w;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const float x = __shfl_xor_sync(~0u, acc.x, d), y = __shfl_xor_sync(~0u, acc.y, d);
+        const float z = __shfl_xor_sync(~0u, acc.z, d), w = __shfl_xor_sync(~0u, acc.w, d);
+        if (a.isMax) {
+            acc.x = fmaxf(acc.x, x);
+            acc.y = fmaxf(acc.y, y);
+            acc.z = fmaxf(acc.z, z);
+            acc.w = fmaxf(acc.w, w);
+        } else {
+            acc.x += x;
+            acc.y += y;
+            acc.z += z;
+            acc.w += w;
+        }
+    }
+    if (threadIdx.x) return;
+    if (!a.isMax) acc = make_float4(acc.x * a.inv, acc.y * a.inv, acc.z * a.inv, acc.w * a.inv);
+    fyn_store_texel(a.out, n, t, a.outP + xo, a.outP + yo, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -134,6 +188,58 @@ __global__ void __launch_bounds__(256) k_eltwise_h8(const EltArgs a, long long p
     }
 }
 
+// fp16 path for everything else (deep-tiled textures, odd paddings): a block owns a chunk of one 4-channel plane, so the
+// plane / tile arithmetic is block-uniform and a texel costs one division; one texel (8 bytes) per access, U accesses
+// in flight per thread.
+template <int U>
+__global__ void __launch_bounds__(256) k_eltwise_h4(const EltArgs a, unsigned W, unsigned HW, unsigned chunks) {
+    unsigned bid = blockIdx.x;
+    const unsigned chunk = bid % chunks;
+    bid /= chunks;
+    const unsigned t = bid % (unsigned)a.tiles, n = bid / (unsigned)a.tiles;
+    long long ib = (long long)n * a.in.imageElems, ob = (long long)n * a.out.imageElems;
+    unsigned ix0 = a.in.P, iy0 = a.in.P, ox0 = a.outP, oy0 = a.outP;
+    if (a.in.deep) {
+        ix0 += (t % a.in.tx) * a.in.tileW;
+        iy0 += (t / a.in.tx) * a.in.tileH;
+    } else {
+        ib += (long long)t * a.in.planeElems;
+    }
+    if (a.out.deep) {
+        ox0 += (t % a.out.tx) * a.out.tileW;
+        oy0 += (t / a.out.tx) * a.out.tileH;
+    } else {
+        ob += (long long)t * a.out.planeElems;
+    }
+    const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + ib + ((long long)iy0 * a.in.texW + ix0) * 4;
+    __half *dst = reinterpret_cast<__half *>(a.out.ptr) + ob + ((long long)oy0 * a.out.texW + ox0) * 4;
+    const unsigned p0 = chunk * (256u * U) + threadIdx.x;
+    uint2 raw[U];
+    unsigned oo[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const unsigned p = p0 + u * 256u;
+        oo[u] = ~0u;
+        if (p < HW) {
+            const unsigned y = p / W, x = p - y * W;
+            oo[u] = (y * a.out.texW + x) * 4;
+            raw[u] = __ldg(reinterpret_cast<const uint2 *>(src + (y * a.in.texW + x) * 4));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (oo[u] != ~0u) {
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[u].x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[u].y));
+            const float4 r = elt_apply(a, make_float4(f0.x, f0.y, f1.x, f1.y), (int)t);
+            __half2 h0 = __floats2half2_rn(r.x, r.y), h1 = __floats2half2_rn(r.z, r.w);
+            uint2 o;
+            o.x = *reinterpret_cast<unsigned *>(&h0);
+            o.y = *reinterpret_cast<unsigned *>(&h1);
+            *reinterpret_cast<uint2 *>(dst + oo[u]) = o;
+        }
+    }
+}
+
 // launches the fast path when its alignment conditions hold, else the generic kernel
 static int launch_eltwise(fyn_ctx *ctx, const EltArgs &a, int W, int H, cudaStream_t stream) {
     const bool fast = a.in.dtype == FYN_F16 && a.out.dtype == FYN_F16 && a.in.packing == 4 && a.out.packing == 4 && !a.in.deep &&
@@ -146,6 +252,16 @@ static int launch_eltwise(fyn_ctx *ctx, const EltArgs &a, int W, int H, cudaStre
         const long long cap = (long long)ctx->prop.multiProcessorCount * 8;
         if (blocks > cap) blocks = cap;
         k_eltwise_h8<<<(unsigned)blocks, 256, 0, stream>>>(a, pairsPerRow, rows);
+    } else if (a.in.dtype == FYN_F16 && a.out.dtype == FYN_F16 && a.in.packing == 4 && a.out.packing == 4 &&
+               (long long)a.in.texW * a.in.texH < (1 << 28) && (long long)a.out.texW * a.out.texH < (1 << 28)) {
+        const unsigned HW = (unsigned)W * (unsigned)H;
+        const int U = HW > 1024 ? 8 : (HW > 512 ? 4 : (HW > 256 ? 2 : 1));
+        const unsigned chunks = (HW + 256u * U - 1) / (256u * U);
+        const unsigned blocks = chunks * (unsigned)a.tiles * (unsigned)a.batch;
+        if (U == 8) k_eltwise_h4<8><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks);
+        else if (U == 4) k_eltwise_h4<4><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks);
+        else if (U == 2) k_eltwise_h4<2><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks);
+        else k_eltwise_h4<1><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks);
     } else {
         long long blocks = (long long)((W + 31) / 32) * ((H + 3) / 4) * a.tiles * a.batch;
         k_eltwise<<<(unsigned)blocks, dim3(32, 4), 0, stream>>>(a);
@@ -219,7 +335,15 @@ int fyn_pool2d_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stre
     a.inv = 1.f / (float)(a.px * a.py);
     a.act = fyn_act_from_flags(d.flags, d.leaky, d.clip_lo, d.clip_hi);
     long long blocks = grid_blocks(a.Wo, a.Ho, a.tiles, a.batch);
-    k_pool<<<(unsigned)blocks, dim3(32, 4), 0, (cudaStream_t)stream>>>(a);
+    const long long outs = (long long)a.Wo * a.Ho * a.tiles * a.batch;
+    if (a.px * a.py >= 32 && !a.quirk3)
+        k_pool_warp<<<(unsigned)((outs + 3) / 4), dim3(32, 4), 0, (cudaStream_t)stream>>>(a);
+    else if (a.px == 3 && a.py == 3)
+        k_pool<3, 3><<<(unsigned)blocks, dim3(32, 4), 0, (cudaStream_t)stream>>>(a);
+    else if (a.px == 2 && a.py == 2)
+        k_pool<2, 2><<<(unsigned)blocks, dim3(32, 4), 0, (cudaStream_t)stream>>>(a);
+    else
+        k_pool<0, 0><<<(unsigned)blocks, dim3(32, 4), 0, (cudaStream_t)stream>>>(a);
     FYN_CHECK_LAUNCH(op->ctx);
     return FYN_OK;
 }
