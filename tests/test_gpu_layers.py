@@ -185,7 +185,9 @@ def test_batchnorm_and_sigmoid(dtype):
     c = ctx()
     rng = np.random.default_rng(3)
     prec = fo.FP16_STORE if dtype == capi.F16 else fo.FP32
-    for deep, ch, size, outp in [(False, 3, 20, 1), (True, 64, 9, 0), (True, 31, 6, 0), (False, 23, 6, 0)]:
+    # the larger cases walk the 2 / 4 / 8 texels-per-thread variants of the fp16 plane-chunk kernel
+    for deep, ch, size, outp in [(False, 3, 20, 1), (True, 64, 9, 0), (True, 31, 6, 0), (False, 23, 6, 0),
+                                 (True, 8, 20, 0), (False, 7, 30, 1), (True, 20, 40, 0), (True, 12, 57, 1)]:
         order = capi.ORDER_DEEP if deep else capi.ORDER_SHALLOW
         x = rng.uniform(-10, 10, (2, ch, size, size + 3)).astype(np.float32)
         sb = rng.uniform(-2, 2, 2 * ch).astype(np.float32)
