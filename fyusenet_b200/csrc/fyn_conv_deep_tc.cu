@@ -21,6 +21,7 @@
 // are in flight) + 1 MMA warp; stage ring of min(4, stages)
 // entries, so that the many short-K layers (1x1 convs on 64 channels: a single stage) fit several CTAs per SM.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -31,7 +32,7 @@ namespace {
 constexpr int kM = 128;          // pixels per CTA
 constexpr int kKC = 64;          // input channels per stage (16 planes)
 constexpr int kMaxRing = 4;      // stage ring depth (fewer for layers with fewer stages: more CTAs fit an SM)
-constexpr int kLoadSets = 4;     // sets of four loader warps take the stages round robin: that many gathers are in flight per CTA (1 set: 5.8k, 2: 9.3k, 4: 11.0k img/s at batch 32)
+constexpr int kLoadSets = 4;     // at most this many sets of four loader warps; they take the stages round robin: that many gathers are in flight per CTA
 constexpr int kLoadWarps = 4 * kLoadSets;
 constexpr int kThreadsDeep = (kLoadWarps + 1) * 32;
 constexpr int kAStageBytes = kM * kKC * 2;   // 16 KB
@@ -43,7 +44,8 @@ struct DeepTcArgs {
     int K, ds, mh, Wo, Ho, batch;
     int nInPlanes, Cout4;        // input planes; output channels rounded up to a multiple of 4
     int NT, nstages, kcs;        // columns per N tile, stages = K*K*kcs, kcs = Cin / 64
-    int ring;                    // stage ring depth = min(kMaxRing, nstages)
+    int ring;                    // stage ring depth <= min(kMaxRing, nstages)
+    int nsets;                   // loader sets of this layer (<= kLoadSets, <= nstages): blockDim = (4 * nsets + 1) warps
     int tapPacked;               // 1: single input plane (<= 4 channels): a stage holds 16 kernel taps x 4 channels (ResNet stem)
     long long Mtotal;            // batch * Ho * Wo
     uint32_t idesc;
@@ -149,12 +151,14 @@ __global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_cons
     int *inOrigin = reinterpret_cast<int *>(sB + a.ring * bStageBytes);   // [nInPlanes] element offset of a tile's origin
     int *outOrigin = inOrigin + a.nInPlanes;                               // [NT/4] (output tensor), then [NT/4] (residual tensor)
     int *resOrigin = outOrigin + (a.NT >> 2);
-    uint64_t *full = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(resOrigin + (a.NT >> 2)) + 7) & ~uintptr_t(7));
+    int *tapTab = resOrigin + (a.NT >> 2);                                 // [64] (ky | kx << 8) of tap-packed stages
+    uint64_t *full = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(tapTab + 64) + 7) & ~uintptr_t(7));
     uint64_t *empty = full + kMaxRing;
     uint64_t *done = empty + kMaxRing;
     uint32_t *tmemBase = reinterpret_cast<uint32_t *>(done + 1);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int loadWarps = 4 * a.nsets, nthreads = (loadWarps + 1) * 32;
     const int ntile = blockIdx.y;
     const long long m0 = (long long)blockIdx.x * kM;
 
@@ -166,20 +170,24 @@ __global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_cons
         mbar_init(done, 1);
         fence_barrier_init();
     }
-    if (warp == kLoadWarps) tmem_alloc(tmemBase, 128);
+    if (warp == loadWarps) tmem_alloc(tmemBase, 128);
     // tile origins: plane q sits at tile (q % tx, q / tx), tiles are tileW x tileH texels apart (deeptiler.cpp:91-94)
-    for (int q = threadIdx.x; q < a.nInPlanes && !a.tapPacked; q += kThreadsDeep) inOrigin[q] = ((q / a.in.tx) * a.in.tileH * a.in.texW + (q % a.in.tx) * a.in.tileW) * 4;
-    for (int k = threadIdx.x; k < (a.NT >> 2); k += kThreadsDeep) {
+    for (int q = threadIdx.x; q < a.nInPlanes && !a.tapPacked; q += nthreads) inOrigin[q] = ((q / a.in.tx) * a.in.tileH * a.in.texW + (q % a.in.tx) * a.in.tileW) * 4;
+    for (int k = threadIdx.x; k < (a.NT >> 2); k += nthreads) {
         const int p = ntile * (a.NT >> 2) + k;
         outOrigin[k] = ((p / a.out.tx) * a.out.tileH * a.out.texW + (p % a.out.tx) * a.out.tileW) * 4;
         resOrigin[k] = a.hasRes ? ((p / a.res.tx) * a.res.tileH * a.res.texW + (p % a.res.tx) * a.res.tileW) * 4 : 0;
+    }
+    if (a.tapPacked && threadIdx.x < 64) {
+        const int tp = min((int)threadIdx.x, a.K * a.K - 1);                  // taps beyond K*K carry zero weights
+        tapTab[threadIdx.x] = (tp / a.K) | ((tp % a.K) << 8);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmemBase;
 
-    if (warp < kLoadWarps) {
+    if (warp < loadWarps) {
         // ===================== loaders (then epilogue): thread = GEMM row = output pixel =====================
         const int t = threadIdx.x & (kM - 1), set = warp >> 2;
         const long long m = m0 + t;
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_cons
         const int yo = rem / a.Wo, xo = rem - yo * a.Wo;
         const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems;
         const uint4 *wsrc = a.wimg + (size_t)ntile * a.nstages * (bStageBytes >> 4);
-        for (int s = set; s < a.nstages; s += kLoadSets) {
+        for (int s = set; s < a.nstages; s += a.nsets) {
             const int st = s % a.ring, use = s / a.ring;
             const int tap = s / a.kcs, kc = s - tap * a.kcs;
             const int ky = tap / a.K, kx = tap - ky * a.K;
@@ -212,8 +220,8 @@ __global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_cons
                 // how the under-padded 7x7 stem (P = 1 < 3) still sees a zero border: the outermost texels are padding
 #pragma unroll
                 for (int j = 0; j < kKC / 4; j++) {
-                    const int tp = min(s * (kKC / 4) + j, a.K * a.K - 1);          // taps beyond K*K carry zero weights
-                    const int tky = tp / a.K, tkx = tp - tky * a.K;
+                    const int tt = tapTab[s * (kKC / 4) + j];
+                    const int tky = tt & 255, tkx = tt >> 8;
                     const int iy = min(max(a.inP + a.ds * yo + tky - a.mh, 0), a.in.texH - 1);
                     const int ix = min(max(a.inP + a.ds * xo + tkx - a.mh, 0), a.in.texW - 1);
                     v[j] = valid ? __ldg(reinterpret_cast<const uint2 *>(src + (iy * a.in.texW + ix) * 4)) : make_uint2(0u, 0u);
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_cons
         const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // TMEM lane quarter of this warp
         __half *outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((a.outP + yo) * a.out.texW + a.outP + xo) * 4;
         const __half *resp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems + ((a.resP + yo) * a.res.texW + a.resP + xo) * 4;
-        for (int cg = set; cg < (a.NT >> 4); cg += kLoadSets) {           // the two sets split the column groups
+        for (int cg = set; cg < (a.NT >> 4); cg += a.nsets) {             // the sets split the column groups
             uint32_t acc[16];
             tmem_ld16(taddr + cg * 16, acc);
             tmem_ld_wait();
@@ -283,7 +291,7 @@ __global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kLoadWarps) tmem_dealloc(tmem, 128);
+    if (warp == loadWarps) tmem_dealloc(tmem, 128);
 }
 
 }  // namespace
@@ -370,8 +378,12 @@ int fyn_conv_deep_tc_create(fyn_op *op, const float *wb) {
     }
     FYN_CUDA(cudaMemcpy(plan->d_wimg, img.data(), bytes, cudaMemcpyHostToDevice));
     a.wimg = plan->d_wimg;
+    // loader sets / ring depth: registers allow two CTAs of 4 sets, four of 2 sets; a ring entry is 16 KB + NT * 128 bytes
+    a.nsets = std::min(kLoadSets, a.nstages);
     a.ring = std::min(kMaxRing, a.nstages);
-    plan->smemBytes = (size_t)a.ring * kAStageBytes + (size_t)a.ring * a.NT * kKC * 2 + ((size_t)a.nInPlanes + 2 * (a.NT / 4)) * 4 + 8 + (2 * kMaxRing + 1) * 8 + 16;
+    if (const char *e = getenv("FYN_DEEP_SETS")) a.nsets = std::max(1, std::min(std::min(kLoadSets, a.nstages), atoi(e)));
+    if (const char *e = getenv("FYN_DEEP_RING")) a.ring = std::max(a.nsets, std::min(std::min(kMaxRing, a.nstages), atoi(e)));
+    plan->smemBytes = (size_t)a.ring * kAStageBytes + (size_t)a.ring * a.NT * kKC * 2 + ((size_t)a.nInPlanes + 2 * (a.NT / 4) + 64) * 4 + 8 + (2 * kMaxRing + 1) * 8 + 16;
     static size_t maxSmem[64] = {0};
     size_t &cur = maxSmem[op->ctx->device & 63];
     if (plan->smemBytes > cur) {
@@ -409,7 +421,7 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     a.scale = a.bias + (size_t)nOut * 4;
     const long long mtiles = (a.Mtotal + kM - 1) / kM;
     dim3 grid((unsigned)mtiles, (unsigned)plan->ntiles);
-    k_conv_deep_tc<<<grid, kThreadsDeep, plan->smemBytes, stream>>>(a);
+    k_conv_deep_tc<<<grid, (4 * a.nsets + 1) * 32, plan->smemBytes, stream>>>(a);
     FYN_CHECK_LAUNCH(op->ctx);
     return FYN_OK;
 }
