@@ -72,6 +72,31 @@ class BnDesc(C.Structure):
 
 UnaryDesc = BnDesc  # identical field layout (fyn_unary_desc)
 
+
+class ScaleDesc(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("in_padding", C.c_int),
+                ("out_padding", C.c_int), ("upsample_x", C.c_int), ("upsample_y", C.c_int), ("downsample_x", C.c_int),
+                ("downsample_y", C.c_int), ("linear", C.c_int), ("flags", C.c_uint), ("leaky", C.c_float),
+                ("clip_lo", C.c_float), ("clip_hi", C.c_float)]
+
+
+class ArithDesc(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("in_padding", C.c_int),
+                ("out_padding", C.c_int), ("op", C.c_int), ("singleton", C.c_int), ("operand", C.c_float),
+                ("flags", C.c_uint), ("leaky", C.c_float), ("clip_lo", C.c_float), ("clip_hi", C.c_float)]
+
+
+CONCAT_MAX_INPUTS = 8
+
+
+class ConcatDesc(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("num_inputs", C.c_int), ("channels", C.c_int * CONCAT_MAX_INPUTS),
+                ("in_padding", C.c_int), ("out_padding", C.c_int), ("flags", C.c_uint), ("leaky", C.c_float),
+                ("clip_lo", C.c_float), ("clip_hi", C.c_float)]
+
+
+ARITH_ADD, ARITH_SUB, ARITH_MUL, ARITH_DIV = 0, 1, 2, 3
+
 # every symbol include/fyusenet_b200.h declares (tests check that the library exports all of them)
 EPILOGUE_NONE, EPILOGUE_SIGMOID = 0, 1
 
@@ -86,6 +111,8 @@ EXPORTS = [
     "fyn_tensor_read_chw_f32", "fyn_conv2d_output_size", "fyn_conv2d_create", "fyn_conv2d_load_weights",
     "fyn_conv2d_run", "fyn_conv2d_backend", "fyn_conv2d_set_epilogue", "fyn_conv2d_plan_query", "fyn_pool2d_create", "fyn_pool2d_run", "fyn_batchnorm_create",
     "fyn_batchnorm_load", "fyn_batchnorm_run", "fyn_sigmoid_create", "fyn_sigmoid_run", "fyn_op_destroy",
+    "fyn_scale_create", "fyn_scale_out_size", "fyn_scale_run", "fyn_arith_create", "fyn_arith_run", "fyn_concat_create",
+    "fyn_concat_run", "fyn_rgb2bgr_create", "fyn_rgb2bgr_run", "fyn_relayout_create", "fyn_relayout_run",
 ]
 
 _lib = None
@@ -343,3 +370,67 @@ class Sigmoid(_Op):
 
     def run(self, x, out, stream=None):
         check(lib().fyn_sigmoid_run(self._h, x._h, out._h, _s(stream)))
+
+
+class Scale(_Op):
+    """ScaleLayer / DeepScaleLayer (also PADDING2D / RELU / CLIP with all factors 1)."""
+
+    def __init__(self, ctx, *, width, height, channels, in_padding=0, out_padding=0, up=(1, 1), down=(1, 1), linear=False,
+                 flags=0, leaky=0.0, clip_lo=0.0, clip_hi=0.0):
+        super().__init__(ctx)
+        self.desc = ScaleDesc(width, height, channels, in_padding, out_padding, up[0], up[1], down[0], down[1], int(linear),
+                              flags, leaky, clip_lo, clip_hi)
+        check(lib().fyn_scale_create(ctx._h, C.byref(self.desc), C.byref(self._h)))
+        w, h = C.c_int(), C.c_int()
+        check(lib().fyn_scale_out_size(C.byref(self.desc), C.byref(w), C.byref(h)))
+        self.out_width, self.out_height = w.value, h.value
+
+    def run(self, x, out, stream=None):
+        check(lib().fyn_scale_run(self._h, x._h, out._h, _s(stream)))
+
+
+class Arith(_Op):
+    """AddSubLayer (two tensors, ADD / SUB) and SingletonArithmeticLayer (tensor op scalar)."""
+
+    def __init__(self, ctx, *, width, height, channels, op, operand=None, in_padding=0, out_padding=0, flags=0):
+        super().__init__(ctx)
+        self.desc = ArithDesc(width, height, channels, in_padding, out_padding, op, int(operand is not None),
+                              0.0 if operand is None else float(operand), flags, 0.0, 0.0, 0.0)
+        check(lib().fyn_arith_create(ctx._h, C.byref(self.desc), C.byref(self._h)))
+
+    def run(self, a, b, out, stream=None):
+        check(lib().fyn_arith_run(self._h, a._h, b._h if b is not None else None, out._h, _s(stream)))
+
+
+class Concat(_Op):
+    def __init__(self, ctx, *, width, height, channels, in_padding=0, out_padding=0, flags=0):
+        super().__init__(ctx)
+        ch = (C.c_int * CONCAT_MAX_INPUTS)(*list(channels)[:CONCAT_MAX_INPUTS])
+        self.desc = ConcatDesc(width, height, len(channels), ch, in_padding, out_padding, flags, 0.0, 0.0, 0.0)
+        check(lib().fyn_concat_create(ctx._h, C.byref(self.desc), C.byref(self._h)))
+
+    def run(self, inputs, out, stream=None):
+        arr = (C.c_void_p * len(inputs))(*[t._h for t in inputs])
+        check(lib().fyn_concat_run(self._h, arr, len(inputs), out._h, _s(stream)))
+
+
+class RGB2BGR(_Op):
+    def __init__(self, ctx, *, width, height, channels, in_padding=0, out_padding=0, flags=0):
+        super().__init__(ctx)
+        self.desc = UnaryDesc(width, height, channels, in_padding, out_padding, flags, 0.0, 0.0, 0.0)
+        check(lib().fyn_rgb2bgr_create(ctx._h, C.byref(self.desc), C.byref(self._h)))
+
+    def run(self, x, out, stream=None):
+        check(lib().fyn_rgb2bgr_run(self._h, x._h, out._h, _s(stream)))
+
+
+class Relayout(_Op):
+    """Shallow2DeepLayer / Deep2ShallowLayer: the direction follows from the tensors' orders."""
+
+    def __init__(self, ctx, *, width, height, channels, in_padding=0, out_padding=0, flags=0):
+        super().__init__(ctx)
+        self.desc = UnaryDesc(width, height, channels, in_padding, out_padding, flags, 0.0, 0.0, 0.0)
+        check(lib().fyn_relayout_create(ctx._h, C.byref(self.desc), C.byref(self._h)))
+
+    def run(self, x, out, stream=None):
+        check(lib().fyn_relayout_run(self._h, x._h, out._h, _s(stream)))

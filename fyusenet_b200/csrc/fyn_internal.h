@@ -61,7 +61,7 @@ struct fyn_tensor {
     size_t staging_bytes = 0;
 };
 
-enum fyn_op_kind { FYN_OP_CONV = 1, FYN_OP_POOL, FYN_OP_BN, FYN_OP_SIGMOID };
+enum fyn_op_kind { FYN_OP_CONV = 1, FYN_OP_POOL, FYN_OP_BN, FYN_OP_SIGMOID, FYN_OP_SCALE, FYN_OP_ARITH, FYN_OP_CONCAT, FYN_OP_RGB2BGR, FYN_OP_RELAYOUT };
 
 // Device-side view of a tensor: everything a kernel needs to address texels.
 struct TView {
@@ -107,6 +107,10 @@ struct fyn_op {
     fyn_bn_desc bn{};
     // unary
     fyn_unary_desc unary{};
+    // scale / arithmetic / concat (fyn_gather.cu)
+    fyn_scale_desc scale{};
+    fyn_arith_desc arith{};
+    fyn_concat_desc concat{};
 };
 
 // tcgen05 path (fyn_conv_tc.cu)

@@ -286,6 +286,76 @@ typedef struct {
 int fyn_sigmoid_create(fyn_ctx *ctx, const fyn_unary_desc *desc, fyn_op **op);
 int fyn_sigmoid_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream);
 
+/* ScaleLayer / DeepScaleLayer (fyusenet/gpu/scalelayer.cpp:40-60,120-140, gpu/deep/deepscalelayer.cpp:30-75,
+ * shaders/scaling.frag, geometry of gpu/functionlayer.cpp:194-204): output texel o samples the input at the
+ * texel-space coordinate P + (o + 0.5) * W / Wo, with Wo = (int)(W * up / down) (scalelayer.cpp:44-47).
+ * NEAREST takes the texel that contains the coordinate, LINEAR (GL_LINEAR) blends the four texels around it --
+ * including the padding texels / clamped texture edge exactly like the sampler -- and the activation is applied
+ * to the sampled value.  Deep layers of 1-texel width or height always sample NEAREST (deepscalelayer.cpp:34).
+ * With all factors 1 this is also the reference's PADDING2D / RELU / CLIP pseudo-layer
+ * (gpu/gpulayerfactory.cpp:125-140,317-322).  Rotation is not supported. */
+typedef struct {
+    int width, height, channels;          /* input size */
+    int in_padding, out_padding;
+    int upsample_x, upsample_y;           /* integer factors (gpu/scalelayerbuilder.h:60-95) */
+    int downsample_x, downsample_y;
+    int linear;                           /* 0 = ScalingType::NEAREST, 1 = ScalingType::LINEAR */
+    unsigned flags;                       /* FYN_FLAG_DEEP, FYN_FLAG_PRE_* */
+    float leaky, clip_lo, clip_hi;
+} fyn_scale_desc;
+
+int fyn_scale_create(fyn_ctx *ctx, const fyn_scale_desc *desc, fyn_op **op);
+int fyn_scale_out_size(const fyn_scale_desc *desc, int *width, int *height);
+int fyn_scale_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream);
+
+/* AddSubLayer (fyusenet/gpu/addsublayer.cpp:60-120, shaders/add.frag:84-135: act(a) +/- act(b)) and
+ * SingletonArithmeticLayer (fyusenet/gpu/singleton_arithlayer.cpp, shaders/singleton_arith.frag:
+ * act(x) (+|-|*|/) operand).  Known answers: unit_tests/arithtests.cpp:97-250. */
+#define FYN_ARITH_ADD 0
+#define FYN_ARITH_SUB 1
+#define FYN_ARITH_MUL 2
+#define FYN_ARITH_DIV 3
+typedef struct {
+    int width, height, channels;
+    int in_padding, out_padding;
+    int op;                               /* FYN_ARITH_*; two-tensor form: ADD / SUB only */
+    int singleton;                        /* 1: second operand is the scalar `operand` */
+    float operand;
+    unsigned flags;
+    float leaky, clip_lo, clip_hi;
+} fyn_arith_desc;
+
+int fyn_arith_create(fyn_ctx *ctx, const fyn_arith_desc *desc, fyn_op **op);
+int fyn_arith_run(fyn_op *op, const fyn_tensor *in1, const fyn_tensor *in2, fyn_tensor *out, void *stream);
+
+/* ConcatLayer / DeepConcatLayer (fyusenet/gpu/concatlayer.cpp:60-75,112-180, gpu/deep/deepconcatlayer.cpp,
+ * shaders/vanilla/concat.frag): the output holds the inputs' channels back to back (inputs whose channel count is
+ * not a multiple of 4 are shifted across texels: the reference's "consolidation render"); the activation applies
+ * to every input (the reference supports ReLU on all inputs or none, concatlayer.cpp:20-26). */
+#define FYN_CONCAT_MAX_INPUTS 8
+typedef struct {
+    int width, height;
+    int num_inputs;
+    int channels[FYN_CONCAT_MAX_INPUTS];
+    int in_padding, out_padding;
+    unsigned flags;
+    float leaky, clip_lo, clip_hi;
+} fyn_concat_desc;
+
+int fyn_concat_create(fyn_ctx *ctx, const fyn_concat_desc *desc, fyn_op **op);
+int fyn_concat_run(fyn_op *op, const fyn_tensor *const *inputs, int num_inputs, fyn_tensor *out, void *stream);
+
+/* RGB2BGRLayer (fyusenet/gpu/rgb2bgrlayer.cpp, shaders/rgb2bgr.frag: every texel becomes val.bgra, no
+ * activation). */
+int fyn_rgb2bgr_create(fyn_ctx *ctx, const fyn_unary_desc *desc, fyn_op **op);
+int fyn_rgb2bgr_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream);
+
+/* Shallow2DeepLayer / Deep2ShallowLayer (fyusenet/gpu/shallow2deep.cpp, gpu/deep2shallow.cpp,
+ * shaders/shallow2deep.frag, deep2shallow.frag): layout conversion between the per-plane and the tiled texture
+ * format with the activation applied at the fetch.  The direction follows from the two tensors' orders. */
+int fyn_relayout_create(fyn_ctx *ctx, const fyn_unary_desc *desc, fyn_op **op);
+int fyn_relayout_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream);
+
 int fyn_op_destroy(fyn_op *op);
 
 #ifdef __cplusplus

@@ -573,6 +573,117 @@ int fyo_sigmoid(const float *in_chw, size_t n, const fyo_act *act, int prec, flo
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* scaling, arithmetic, concatenation, swizzle                               */
+/* ------------------------------------------------------------------------------------------- */
+
+/* One texel lane of channel c's texture at ABSOLUTE texture coordinates (X, Y), with the sampler's clamp to the
+ * texture edge (base/buffermanager.cpp:657-670).  Shallow: plane c/4 of (W+2P)x(H+2P), interior at (P,P).
+ * Deep: tile (c/4) of the tiled texture (gpu/deep/deeptiler.cpp:63-95); a coordinate that leaves the tile lands in the
+ * padding gap (zero) or in the NEIGHBOURING tile, exactly as a GL sampler would see it. */
+static float tex_lane(const float *chw, int C, int H, int W, int P, int deep, int c, int X, int Y) {
+    if (!deep) {
+        int tw = W + 2 * P, th = H + 2 * P;
+        X = X < 0 ? 0 : (X >= tw ? tw - 1 : X);
+        Y = Y < 0 ? 0 : (Y >= th ? th - 1 : Y);
+        int x = X - P, y = Y - P;
+        if (x < 0 || x >= W || y < 0 || y >= H) return 0.f;
+        return chw[((size_t)c * H + y) * W + x];
+    }
+    int tx, ty, tw, th;
+    fyo_deep_tiling(C, &tx, &ty);
+    fyo_deep_texture_size(C, W, H, P, &tw, &th);
+    X = X < 0 ? 0 : (X >= tw ? tw - 1 : X);
+    Y = Y < 0 ? 0 : (Y >= th ? th - 1 : Y);
+    if (X < P || Y < P) return 0.f;
+    int col = (X - P) / (W + P), row = (Y - P) / (H + P);
+    int x = (X - P) - col * (W + P), y = (Y - P) - row * (H + P);
+    if (x >= W || y >= H || col >= tx || row >= ty) return 0.f;
+    int ch = (row * tx + col) * 4 + (c & 3);
+    if (ch >= C || (row * tx + col) >= (C + 3) / 4) return 0.f;
+    return chw[((size_t)ch * H + y) * W + x];
+}
+
+static int floor_div(int num, int den) { return num >= 0 ? num / den : -((-num + den - 1) / den); }
+
+void fyo_scale_outdims(int W, int H, int upx, int upy, int dnx, int dny, int *Wo, int *Ho) {
+    /* gpu/scalelayer.cpp:44-47 */
+    *Wo = (int)(((float)upx / (float)dnx) * (float)W);
+    *Ho = (int)(((float)upy / (float)dny) * (float)H);
+}
+
+/* ScaleLayer / DeepScaleLayer: gpu/scalelayer.cpp:40-60, gpu/deep/deepscalelayer.cpp:30-75, shaders/scaling.frag
+ * (activate(texture(...))), quad geometry gpu/functionlayer.cpp:194-204: output texel o samples texel-space
+ * coordinate P + (o+0.5)*W/Wo of its channel's texture; NEAREST = the texel containing it, LINEAR = GL_LINEAR. */
+int fyo_scale(const float *in_chw, int C, int H, int W, int in_pad, int deep, int upx, int upy, int dnx, int dny,
+              int linear, const fyo_act *act, int prec, float *out_chw) {
+    fyo_act none = {FYO_ACT_NONE, 0, 0, 0};
+    const fyo_act *a = act ? act : &none;
+    int Wo, Ho;
+    if (upx < 1 || upy < 1 || dnx < 1 || dny < 1) return -1;
+    fyo_scale_outdims(W, H, upx, upy, dnx, dny, &Wo, &Ho);
+    if (Wo < 1 || Ho < 1) return -1;
+    if (deep && (W == 1 || H == 1)) linear = 0; /* deepscalelayer.cpp:34 */
+    int tx = 1, ty = 1;
+    if (deep) fyo_deep_tiling(C, &tx, &ty);
+    for (int c = 0; c < C; c++) {
+        int t = c / 4;
+        int ox = deep ? in_pad + (t % tx) * (W + in_pad) : in_pad;
+        int oy = deep ? in_pad + (t / tx) * (H + in_pad) : in_pad;
+        for (int yo = 0; yo < Ho; yo++)
+            for (int xo = 0; xo < Wo; xo++) {
+                float v;
+                if (!linear) {
+                    int sx = ((2 * xo + 1) * W) / (2 * Wo), sy = ((2 * yo + 1) * H) / (2 * Ho);
+                    v = tex_lane(in_chw, C, H, W, in_pad, deep, c, ox + sx, oy + sy);
+                } else {
+                    int nx = (2 * xo + 1) * W - Wo, ny = (2 * yo + 1) * H - Ho;
+                    int ix = floor_div(nx, 2 * Wo), iy = floor_div(ny, 2 * Ho);
+                    float fx = (float)(nx - ix * 2 * Wo) / (float)(2 * Wo), fy = (float)(ny - iy * 2 * Ho) / (float)(2 * Ho);
+                    float v00 = tex_lane(in_chw, C, H, W, in_pad, deep, c, ox + ix, oy + iy);
+                    float v10 = tex_lane(in_chw, C, H, W, in_pad, deep, c, ox + ix + 1, oy + iy);
+                    float v01 = tex_lane(in_chw, C, H, W, in_pad, deep, c, ox + ix, oy + iy + 1);
+                    float v11 = tex_lane(in_chw, C, H, W, in_pad, deep, c, ox + ix + 1, oy + iy + 1);
+                    float top = v00 + (v10 - v00) * fx, bot = v01 + (v11 - v01) * fx;
+                    v = top + (bot - top) * fy;
+                }
+                out_chw[((size_t)c * Ho + yo) * Wo + xo] = store(act1(v, a), prec);
+            }
+    }
+    return 0;
+}
+
+/* AddSubLayer: gpu/addsublayer.cpp + shaders/add.frag:84-135 (fetch = activate(texture)); SingletonArithmeticLayer:
+ * gpu/singleton_arithlayer.cpp + shaders/singleton_arith.frag (activate(texture) op operand).
+ * op: 0 add, 1 sub, 2 mul, 3 div; in2 == NULL: scalar operand. */
+int fyo_arith(const float *in1, const float *in2, size_t n, int op, float operand, const fyo_act *act, int prec, float *out) {
+    fyo_act none = {FYO_ACT_NONE, 0, 0, 0};
+    const fyo_act *a = act ? act : &none;
+    if (op < 0 || op > 3 || (in2 && op > 1)) return -1;
+    for (size_t i = 0; i < n; i++) {
+        float p = act1(in1[i], a), q = in2 ? act1(in2[i], a) : operand, r;
+        switch (op) {
+        case 0: r = p + q; break;
+        case 1: r = p - q; break;
+        case 2: r = p * q; break;
+        default: r = p / q; break;
+        }
+        out[i] = store(r, prec);
+    }
+    return 0;
+}
+
+/* RGB2BGRLayer: shaders/rgb2bgr.frag (val.bgra per texel): lanes 0 and 2 of every 4-channel group trade places; a
+ * lane that does not exist in the tensor reads as 0 and a value moved to a non-existing lane is dropped. */
+int fyo_rgb2bgr(const float *in_chw, int C, int H, int W, int prec, float *out_chw) {
+    size_t hw = (size_t)H * W;
+    for (int c = 0; c < C; c++) {
+        int l = c & 3, src = (l == 0) ? c + 2 : (l == 2 ? c - 2 : c);
+        for (size_t i = 0; i < hw; i++) out_chw[(size_t)c * hw + i] = src < C ? store(in_chw[(size_t)src * hw + i], prec) : 0.f;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* host <-> texture conversions                                                                */
 /* ------------------------------------------------------------------------------------------- */
 

@@ -76,6 +76,11 @@ int fyo_pool2d(const fyo_pool *p, const float *in_chw, float *out_chw);
 int fyo_batchnorm(const float *in_chw, int C, int H, int W, const float *scaleBias, int deep,
                   const fyo_act *act, int prec, float *out_chw);
 int fyo_sigmoid(const float *in_chw, size_t n, const fyo_act *act, int prec, float *out_chw);
+void fyo_scale_outdims(int W, int H, int upx, int upy, int dnx, int dny, int *Wo, int *Ho);
+int fyo_scale(const float *in_chw, int C, int H, int W, int in_pad, int deep, int upx, int upy, int dnx, int dny,
+              int linear, const fyo_act *act, int prec, float *out_chw);
+int fyo_arith(const float *in1, const float *in2, size_t n, int op, float operand, const fyo_act *act, int prec, float *out);
+int fyo_rgb2bgr(const float *in_chw, int C, int H, int W, int prec, float *out_chw);
 void fyo_upload_hwc_to_chw(const float *hwc, int C, int H, int W, float *chw);
 void fyo_download_shallow(const float *chw, int C, int H, int W, float fill, float *host);
 /* sets (n > 0) and returns the number of OpenMP threads the oracle uses */

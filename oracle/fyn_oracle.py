@@ -227,6 +227,53 @@ def sigmoid(x, *, act=ACT_NONE, prec=FP32):
     return out
 
 
+def scale(x, *, up=(1, 1), down=(1, 1), linear=False, in_pad=0, deep=False, act=ACT_NONE, lo=0.0, hi=0.0, prec=FP32):
+    """ScaleLayer / DeepScaleLayer (scalelayer.cpp:40-60, scaling.frag); all factors 1 = PADDING2D / RELU / CLIP."""
+    x = _f32(x)
+    c, h, w = x.shape
+    wo, ho = C.c_int(), C.c_int()
+    lib().fyo_scale_outdims(w, h, up[0], up[1], down[0], down[1], C.byref(wo), C.byref(ho))
+    out = np.zeros((c, ho.value, wo.value), np.float32)
+    a = _act(act, 0.0, lo, hi)
+    rc = lib().fyo_scale(_fp(x), c, h, w, int(in_pad), int(bool(deep)), up[0], up[1], down[0], down[1], int(bool(linear)),
+                         C.byref(a), int(prec), _fp(out))
+    if rc != 0:
+        raise RuntimeError(f"fyo_scale failed rc={rc}")
+    return out
+
+
+ARITH_ADD, ARITH_SUB, ARITH_MUL, ARITH_DIV = 0, 1, 2, 3
+
+
+def arith(a, b, op, *, act=ACT_NONE, prec=FP32):
+    """AddSubLayer (b = array, ADD / SUB) or SingletonArithmeticLayer (b = scalar)."""
+    a = _f32(a)
+    out = np.zeros_like(a)
+    ac = _act(act)
+    if np.isscalar(b):
+        rc = lib().fyo_arith(_fp(a), None, C.c_size_t(a.size), int(op), C.c_float(float(b)), C.byref(ac), int(prec), _fp(out))
+    else:
+        b = _f32(b)
+        assert b.shape == a.shape
+        rc = lib().fyo_arith(_fp(a), _fp(b), C.c_size_t(a.size), int(op), C.c_float(0.0), C.byref(ac), int(prec), _fp(out))
+    if rc != 0:
+        raise RuntimeError(f"fyo_arith failed rc={rc}")
+    return out
+
+
+def concat(inputs, *, act=ACT_NONE, prec=FP32):
+    """ConcatLayer / DeepConcatLayer: channels back to back (concatlayer.cpp:60-75), activation on every input."""
+    return np.concatenate([scale(x, act=act, prec=prec) for x in inputs], axis=0)
+
+
+def rgb2bgr(x, *, prec=FP32):
+    x = _f32(x)
+    c, h, w = x.shape
+    out = np.zeros_like(x)
+    lib().fyo_rgb2bgr(_fp(x), c, h, w, int(prec), _fp(out))
+    return out
+
+
 def upload_hwc(hwc):
     """gpu/uploadlayer.cpp:360-380: host [H][W][C] float32 -> C-channel float32 texture (CHW here)."""
     hwc = _f32(hwc)
