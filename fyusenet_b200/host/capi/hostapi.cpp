@@ -10,6 +10,7 @@
 
 #include <fyusenet/fyusenet.h>
 
+#include "../samplenetworks/layerzoo.h"
 #include "../samplenetworks/resnet50.h"
 #include "../samplenetworks/stylenet.h"
 
@@ -20,11 +21,23 @@ namespace {
 thread_local std::string g_error;
 
 struct NetHandle {
-    enum Kind { STYLE, RESNET } kind;
+    enum Kind { STYLE, RESNET, ZOO } kind;
     std::unique_ptr<StyleNetBase> style;
     std::unique_ptr<ResNet50> resnet;
+    std::unique_ptr<LayerZoo> zoo;
     GfxContextLink ctx;
-    NeuralNetwork *net() { return kind == STYLE ? static_cast<NeuralNetwork *>(style.get()) : resnet.get(); }
+    NeuralNetwork *net() {
+        if (kind == STYLE) return style.get();
+        if (kind == RESNET) return resnet.get();
+        return zoo.get();
+    }
+    void setInput(const float *hwc) {
+        if (kind == STYLE) style->setInputBuffer(hwc);
+        else if (kind == RESNET) resnet->setInputBuffer(hwc);
+        else zoo->setInputBuffer(hwc);
+    }
+    cpu::CPUBuffer *inputBuffer() { return kind == STYLE ? style->inputBuffer() : (kind == RESNET ? resnet->inputBuffer() : zoo->inputBuffer()); }
+    cpu::CPUBuffer *outputBuffer() { return kind == STYLE ? style->getOutputBuffer() : (kind == RESNET ? resnet->getOutputBuffer() : zoo->getOutputBuffer()); }
 };
 
 template <typename F>
@@ -84,6 +97,19 @@ void *fynhost_resnet50_create(int device, int batch) {
         if (device >= 0) nh->ctx = GfxContextManager::instance(device)->createMainContext();
         nh->resnet.reset(new ResNet50(nh->ctx));
         nh->resnet->setBatch(batch);
+        h = nh.release();
+    });
+    return rc == 0 ? h : nullptr;
+}
+
+// LayerZoo (samplenetworks/layerzoo.h): every SURVEY 8f rank-2 layer in one weight-free network
+void *fynhost_layerzoo_create(int width, int height, int device) {
+    NetHandle *h = nullptr;
+    int rc = guarded([&] {
+        std::unique_ptr<NetHandle> nh(new NetHandle());
+        nh->kind = NetHandle::ZOO;
+        if (device >= 0) nh->ctx = GfxContextManager::instance(device)->createMainContext();
+        nh->zoo.reset(new LayerZoo(width, height, nh->ctx));
         h = nh.release();
     });
     return rc == 0 ? h : nullptr;
@@ -176,8 +202,7 @@ int fynhost_net_setup(void *handle) {
 int fynhost_net_set_input(void *handle, const float *hwc) {
     NetHandle *h = static_cast<NetHandle *>(handle);
     return guarded([&] {
-        if (h->kind == NetHandle::STYLE) h->style->setInputBuffer(hwc);
-        else h->resnet->setInputBuffer(hwc);
+        h->setInput(hwc);
     });
 }
 
@@ -188,7 +213,7 @@ float *fynhost_net_input_buffer(void *handle, size_t *numFloats) {
     NetHandle *h = static_cast<NetHandle *>(handle);
     float *ptr = nullptr;
     guarded([&] {
-        cpu::CPUBuffer *buf = h->kind == NetHandle::STYLE ? h->style->inputBuffer() : h->resnet->inputBuffer();
+        cpu::CPUBuffer *buf = h->inputBuffer();
         if (numFloats) *numFloats = buf->bytes() / sizeof(float);
         ptr = buf->map<float>();
         buf->unmap();
@@ -215,7 +240,7 @@ const float *fynhost_net_output(void *handle, size_t *numFloats) {
     NetHandle *h = static_cast<NetHandle *>(handle);
     const float *ptr = nullptr;
     guarded([&] {
-        cpu::CPUBuffer *buf = h->kind == NetHandle::STYLE ? h->style->getOutputBuffer() : h->resnet->getOutputBuffer();
+        cpu::CPUBuffer *buf = h->outputBuffer();
         if (!buf) THROW_EXCEPTION_ARGS(FynException, "Network has no output buffer");
         if (numFloats) *numFloats = buf->bytes() / sizeof(float);
         ptr = buf->map<float>();

@@ -133,6 +133,32 @@ extern "C" int fynhost_selftest(char *report, int cap) {
         r.check(throws([&] { backend.createLayer(LayerType::CONVOLUTION2D, reinterpret_cast<LayerBuilder *>(&noctx), 1); }),
                 "layer without a context throws");
     }
+    // ---- scale / concat / singleton builders (gpu/scalelayerbuilder.h:60-95, concatlayerbuilder.h:45-55)
+    {
+        gpu::ScaleLayerBuilder up("up");
+        up.scale(2.0f, 3.0f);
+        r.check(up.type_ == LayerType::SCALE2D && up.upsample_[0] == 2 && up.upsample_[1] == 3 && up.downsample_[0] == 1 && !up.equal(),
+                "ScaleLayerBuilder::scale(2,3) -> integer upsample factors");
+        gpu::ScaleLayerBuilder dn("dn");
+        dn.scale(0.5f).scaleType(ScalingType::LINEAR);
+        r.check(dn.downsample_[0] == 2 && dn.downsample_[1] == 2 && dn.equal() && dn.scaleType_ == ScalingType::LINEAR, "scale(0.5) -> downsample 2");
+        gpu::ScaleLayerBuilder third("third");
+        third.scale(1.0f / 3.0f);
+        r.check(third.downsample_[0] == 3, "scale(1/3) -> downsample 3");
+        r.check(throws([&] { gpu::ScaleLayerBuilder("x").scale(1.5f); }), "fractional upscale throws");
+        r.check(throws([&] { gpu::ScaleLayerBuilder("x").scale(0.4f); }), "non-integer downscale throws");
+        gpu::ConcatLayerBuilder cat("cat");
+        cat.input(3, 1).input(8, 1, LayerFlags::PRE_RELU);
+        r.check(cat.type_ == LayerType::CONCAT && cat.inputs_.size() == 2 && cat.inputChannels_ == 11 && cat.inputs_[1].flags == LayerFlags::PRE_RELU,
+                "ConcatLayerBuilder collects its inputs");
+        gpu::SingletonArithLayerBuilder mul("mul", ArithType::MUL);
+        mul.operand(2.5f);
+        r.check(mul.type_ == LayerType::SINGLETON_ARITH && mul.opType_ == ArithType::MUL && mul.operand_ == 2.5f, "SingletonArithLayerBuilder");
+        gpu::CUDALayerFactoryBackend backend;
+        gpu::GPULayerBuilder plain("cat2");
+        plain.shape(8, 4, 4, 8).type(LayerType::CONCAT).number(1);
+        r.check(throws([&] { backend.createLayer(LayerType::CONCAT, reinterpret_cast<LayerBuilder *>(&plain), 1); }), "concat needs a ConcatLayerBuilder");
+    }
     // ---- host tensors (cpubuffershape.cpp:430-447, cpubuffer.cpp:121-158)
     {
         r.check(cpu::CPUBufferShape::computeDeepTiling(64) == std::make_pair(4, 4), "deep tiling 64 ch -> 4x4");

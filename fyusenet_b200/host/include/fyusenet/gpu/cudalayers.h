@@ -5,6 +5,9 @@
 //   PoolingLayer     <- deep::DeepMaxPoolLayer / DeepAvgPoolLayer, MaxPoolLayer / AvgPoolLayer
 //   BatchNormLayer   <- BatchNormLayer, deep::DeepBatchNormLayer
 //   SigmoidLayer     <- SigmoidLayer
+//   ScaleLayer       <- ScaleLayer, deep::DeepScaleLayer (also the PADDING2D / RELU / CLIP pseudo-layers)
+//   AddSubLayer, SingletonArithmeticLayer, ConcatLayer (deep::DeepConcatLayer), RGB2BGRLayer,
+//   Shallow2DeepLayer / Deep2ShallowLayer
 //   UploadLayer      <- UploadLayer (gpu/uploadlayer.cpp)
 //   DownloadLayer    <- DownloadLayer, deep::DeepDownloadLayer (gpu/downloadlayer.cpp, deep/deepdownloadlayer.cpp)
 #pragma once
@@ -107,6 +110,82 @@ class SigmoidLayer : public GPULayerBase {
     bool bypass_ = false;
 };
 
+// ScaleLayer / deep::DeepScaleLayer (gpu/scalelayer.cpp:40-75, gpu/deep/deepscalelayer.cpp:30-45); constructed from a plain
+// GPULayerBuilder it is the identity-size copy that implements PADDING2D / RELU / CLIP (gpu/gpulayerfactory.cpp:125-140)
+class ScaleLayer : public GPULayerBase {
+ public:
+    ScaleLayer(const ScaleLayerBuilder &builder, int layerNumber);
+    ScaleLayer(const GPULayerBuilder &builder, int layerNumber);
+    void setup() override;
+    void cleanup() override;
+    void forward(uint64_t sequence = 0) override;
+    std::vector<BufferSpec> getRequiredInputBuffers() const override;
+    std::vector<BufferSpec> getRequiredOutputBuffers() const override;
+
+ protected:
+    void init(int upx, int upy, int dnx, int dny, ScalingType type);
+    fyn_scale_desc desc_{};
+    fyn_op *op_ = nullptr;
+    int outWidth_ = 0, outHeight_ = 0;
+};
+
+// AddSubLayer (gpu/addsublayer.cpp) and SingletonArithmeticLayer (gpu/singleton_arithlayer.cpp)
+class ArithLayer : public GPULayerBase {
+ public:
+    ArithLayer(const GPULayerBuilder &builder, int layerNumber);                 // LayerType::ADD / SUB: ports 0 and 1
+    ArithLayer(const SingletonArithLayerBuilder &builder, int layerNumber);     // port 0 (op) operand
+    void setup() override;
+    void cleanup() override;
+    void forward(uint64_t sequence = 0) override;
+    std::vector<BufferSpec> getRequiredInputBuffers() const override;
+    std::vector<BufferSpec> getRequiredOutputBuffers() const override;
+    int numInputPorts() const override { return desc_.singleton ? 1 : 2; }
+
+ protected:
+    void init();
+    fyn_arith_desc desc_{};
+    fyn_op *op_ = nullptr;
+};
+using AddSubLayer = ArithLayer;
+using SingletonArithmeticLayer = ArithLayer;
+
+// ConcatLayer / deep::DeepConcatLayer (gpu/concatlayer.cpp:60-110): one input port per concatenated tensor
+class ConcatLayer : public GPULayerBase {
+ public:
+    ConcatLayer(const ConcatLayerBuilder &builder, int layerNumber);
+    void setup() override;
+    void cleanup() override;
+    void forward(uint64_t sequence = 0) override;
+    std::vector<BufferSpec> getRequiredInputBuffers() const override;
+    std::vector<BufferSpec> getRequiredOutputBuffers() const override;
+    int numInputPorts() const override { return desc_.num_inputs; }
+    int numInputChannels(int port = 0) const override;
+
+ protected:
+    fyn_concat_desc desc_{};
+    fyn_op *op_ = nullptr;
+};
+
+// RGB2BGRLayer (gpu/rgb2bgrlayer.cpp), Shallow2DeepLayer (gpu/shallow2deep.cpp), Deep2ShallowLayer (gpu/deep2shallow.cpp)
+class UnaryCopyLayer : public GPULayerBase {
+ public:
+    enum Kind { RGB2BGR, SHALLOW2DEEP, DEEP2SHALLOW };
+    UnaryCopyLayer(const GPULayerBuilder &builder, int layerNumber, Kind kind);
+    void setup() override;
+    void cleanup() override;
+    void forward(uint64_t sequence = 0) override;
+    std::vector<BufferSpec> getRequiredInputBuffers() const override;
+    std::vector<BufferSpec> getRequiredOutputBuffers() const override;
+
+ protected:
+    Kind kind_;
+    fyn_unary_desc desc_{};
+    fyn_op *op_ = nullptr;
+};
+using RGB2BGRLayer = UnaryCopyLayer;
+using Shallow2DeepLayer = UnaryCopyLayer;
+using Deep2ShallowLayer = UnaryCopyLayer;
+
 class UploadLayer : public GPULayerBase, public cpu::CPULayerInterface {
  public:
     UploadLayer(const UpDownLayerBuilder &builder, int layerNumber);
@@ -176,6 +255,8 @@ using DeepGEMMLayer = gpu::ConvLayerBase;
 using DeepMaxPoolLayer = gpu::PoolingLayer;
 using DeepAvgPoolLayer = gpu::PoolingLayer;
 using DeepBatchNormLayer = gpu::BatchNormLayer;
+using DeepScaleLayer = gpu::ScaleLayer;
+using DeepConcatLayer = gpu::ConcatLayer;
 }  // namespace deep
 
 // The plugin: creates CUDA layers behind LayerFactoryBackend::createLayer.

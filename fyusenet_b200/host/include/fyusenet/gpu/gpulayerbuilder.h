@@ -1,8 +1,12 @@
-// GPU layer builders: GPULayerBuilder, ConvLayerBuilder, PoolLayerBuilder, UpDownLayerBuilder.
-// Reference: fyusenet/gpu/gpulayerbuilder.h, convlayerbuilder.h, poollayerbuilder.h, updownlayerbuilder.h.
+// GPU layer builders: GPULayerBuilder, ConvLayerBuilder, PoolLayerBuilder, UpDownLayerBuilder, ScaleLayerBuilder,
+// ConcatLayerBuilder, SingletonArithLayerBuilder.
+// Reference: fyusenet/gpu/gpulayerbuilder.h, convlayerbuilder.h, poollayerbuilder.h, updownlayerbuilder.h,
+// scalelayerbuilder.h, concatlayerbuilder.h, singleton_arithlayerbuilder.h.
 #pragma once
 #include <functional>
+#include <cmath>
 #include <string>
+#include <vector>
 
 #include "../base/bufferspec.h"
 #include "../base/layerbuilder.h"
@@ -93,6 +97,78 @@ struct UpDownLayerBuilderTempl : GPULayerBuilderTempl<D> {
 
 struct UpDownLayerBuilder : UpDownLayerBuilderTempl<UpDownLayerBuilder> {
     UpDownLayerBuilder(dir direction, const std::string &name) : UpDownLayerBuilderTempl<UpDownLayerBuilder>(direction, name) {}
+};
+
+// scaling type, integer up / down factors, rotation (reference: gpu/scalelayerbuilder.h:36-120)
+template <typename D = LayerBuilderTempl<>>
+struct ScaleLayerBuilderTempl : GPULayerBuilderTempl<D> {
+    explicit ScaleLayerBuilderTempl(const std::string &name) : GPULayerBuilderTempl<D>(name) { LayerBuilderData::type_ = LayerType::SCALE2D; }
+    FYN_FLUENT(scaleType(ScalingType typ), scaleType_ = typ)
+    FYN_FLUENT(rotate(int angle), rotation_ = angle)
+    D &scale(float sc) { return scale(sc, sc); }
+    D &scale(float scaleX, float scaleY) {
+        setFactor(scaleX, 0);
+        setFactor(scaleY, 1);
+        return *static_cast<D *>(this);
+    }
+    bool equal() const {
+        return LayerBuilderData::upsample_[0] == LayerBuilderData::upsample_[1] && LayerBuilderData::downsample_[0] == LayerBuilderData::downsample_[1];
+    }
+    ScalingType scaleType_ = ScalingType::NEAREST;
+    int rotation_ = 0;
+
+ private:
+    void setFactor(float sc, int axis) {
+        if (sc > 1.0f) {
+            LayerBuilderData::upsample_[axis] = (short)sc;
+            if (std::fabs((float)LayerBuilderData::upsample_[axis] - sc) > 1e-4f) THROW_EXCEPTION_ARGS(FynException, "Only supporting integer upscales for now");
+        } else if (sc < 1.0f) {
+            const float dn = 1.0f / sc;
+            LayerBuilderData::downsample_[axis] = (short)(dn + 1e-4f);
+            if (std::fabs((float)LayerBuilderData::downsample_[axis] - dn) > 1e-3f) THROW_EXCEPTION_ARGS(FynException, "Only supporting integer downscales for now");
+        }
+    }
+};
+
+struct ScaleLayerBuilder : ScaleLayerBuilderTempl<ScaleLayerBuilder> {
+    explicit ScaleLayerBuilder(const std::string &name) : ScaleLayerBuilderTempl<ScaleLayerBuilder>(name) {}
+};
+
+// one entry per concatenated input (reference: gpu/concatlayerbuilder.h:36-75)
+template <typename D = LayerBuilderTempl<>>
+struct ConcatLayerBuilderTempl : GPULayerBuilderTempl<D> {
+    struct Input {
+        Input(short chan, short pad, int fl) : channels(chan), padding(pad), flags((layerflags)fl) {}
+        short channels;
+        short padding;
+        layerflags flags;
+    };
+    explicit ConcatLayerBuilderTempl(const std::string &name) : GPULayerBuilderTempl<D>(name) { LayerBuilderData::type_ = LayerType::CONCAT; }
+    D &input(short channels, short padding, int flags = LayerFlags::NO_LAYER_FLAGS) {
+        inputs_.push_back(Input(channels, padding, flags));
+        LayerBuilderData::inputChannels_ = (uint16_t)(LayerBuilderData::inputChannels_ + channels);
+        return *static_cast<D *>(this);
+    }
+    std::vector<Input> inputs_;
+};
+
+struct ConcatLayerBuilder : ConcatLayerBuilderTempl<ConcatLayerBuilder> {
+    explicit ConcatLayerBuilder(const std::string &name) : ConcatLayerBuilderTempl<ConcatLayerBuilder>(name) {}
+};
+
+// tensor (op) scalar (reference: gpu/singleton_arithlayerbuilder.h:36-70)
+template <typename D = LayerBuilderTempl<>>
+struct SingletonArithLayerBuilderTempl : GPULayerBuilderTempl<D> {
+    SingletonArithLayerBuilderTempl(const std::string &name, ArithType type) : GPULayerBuilderTempl<D>(name), opType_(type) {
+        LayerBuilderData::type_ = LayerType::SINGLETON_ARITH;
+    }
+    FYN_FLUENT(operand(float opd), operand_ = opd)
+    ArithType opType_;
+    float operand_ = 0.0f;
+};
+
+struct SingletonArithLayerBuilder : SingletonArithLayerBuilderTempl<SingletonArithLayerBuilder> {
+    SingletonArithLayerBuilder(const std::string &name, ArithType type) : SingletonArithLayerBuilderTempl<SingletonArithLayerBuilder>(name, type) {}
 };
 
 }  // namespace gpu

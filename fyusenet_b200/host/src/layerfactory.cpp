@@ -72,6 +72,35 @@ LayerBase *CUDALayerFactoryBackend::createLayer(LayerType type, LayerBuilder *bu
             return new SigmoidLayer(as<GPULayerBuilder>(data, "GPULayerBuilder"), layerNumber);
         case LayerType::GEMM:
             return new ConvLayerBase(as<GPULayerBuilder>(data, "GPULayerBuilder"), layerNumber);
+        // the reference emulates padding / ReLU / clip with a scaling layer (gpu/gpulayerfactory.cpp:125-140,317-322)
+        case LayerType::PADDING2D:
+            return new ScaleLayer(as<GPULayerBuilder>(data, "GPULayerBuilder"), layerNumber);
+        case LayerType::RELU:
+        case LayerType::CLIP:
+        case LayerType::SCALE2D: {
+            if (ScaleLayerBuilder *sb = dynamic_cast<ScaleLayerBuilder *>(data)) {
+                if (type == LayerType::RELU) sb->prefixAct(ActType::RELU);
+                if (type == LayerType::CLIP) sb->prefixAct(ActType::CLIP);
+                return new ScaleLayer(*sb, layerNumber);
+            }
+            GPULayerBuilder &gb = const_cast<GPULayerBuilder &>(as<GPULayerBuilder>(data, "ScaleLayerBuilder or GPULayerBuilder"));
+            if (type == LayerType::RELU) gb.prefixAct(ActType::RELU);
+            if (type == LayerType::CLIP) gb.prefixAct(ActType::CLIP);
+            return new ScaleLayer(gb, layerNumber);
+        }
+        case LayerType::ADD:
+        case LayerType::SUB:
+            return new ArithLayer(as<GPULayerBuilder>(data, "GPULayerBuilder"), layerNumber);
+        case LayerType::SINGLETON_ARITH:
+            return new ArithLayer(as<SingletonArithLayerBuilder>(data, "SingletonArithLayerBuilder"), layerNumber);
+        case LayerType::CONCAT:
+            return new ConcatLayer(as<ConcatLayerBuilder>(data, "ConcatLayerBuilder"), layerNumber);
+        case LayerType::RGB2BGR:
+            return new UnaryCopyLayer(as<GPULayerBuilder>(data, "GPULayerBuilder"), layerNumber, UnaryCopyLayer::RGB2BGR);
+        case LayerType::SHALLOW2DEEP:
+            return new UnaryCopyLayer(as<GPULayerBuilder>(data, "GPULayerBuilder"), layerNumber, UnaryCopyLayer::SHALLOW2DEEP);
+        case LayerType::DEEP2SHALLOW:
+            return new UnaryCopyLayer(as<GPULayerBuilder>(data, "GPULayerBuilder"), layerNumber, UnaryCopyLayer::DEEP2SHALLOW);
         case LayerType::UPLOAD:
             return new UploadLayer(as<UpDownLayerBuilder>(data, "UpDownLayerBuilder"), layerNumber);
         case LayerType::DOWNLOAD:

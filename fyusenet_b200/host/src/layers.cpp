@@ -295,6 +295,205 @@ void SigmoidLayer::forward(uint64_t) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// ScaleLayer (+ PADDING2D / RELU / CLIP), ArithLayer, ConcatLayer, UnaryCopyLayer
+// ------------------------------------------------------------------------------------------------
+static unsigned gatherFlags(layerflags f) { return f & (LayerFlags::DEEP | LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP); }
+
+void ScaleLayer::init(int upx, int upy, int dnx, int dny, ScalingType type) {
+    desc_.width = width_;
+    desc_.height = height_;
+    desc_.channels = inputChannels_;
+    desc_.in_padding = inputPadding_;
+    desc_.out_padding = outputPadding_;
+    desc_.upsample_x = upx;
+    desc_.upsample_y = upy;
+    desc_.downsample_x = dnx;
+    desc_.downsample_y = dny;
+    desc_.linear = type == ScalingType::LINEAR;
+    desc_.flags = gatherFlags(flags_);
+    desc_.leaky = leakyReLU_;
+    desc_.clip_lo = lowClip_;
+    desc_.clip_hi = highClip_;
+    if (inputChannels_ != outputChannels_)
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: scaling cannot change the channel count (%d -> %d)", name_.c_str(), inputChannels_, outputChannels_);
+    FYN_ABI_CALL(fyn_scale_out_size(&desc_, &outWidth_, &outHeight_));
+    viewport_[0] = outWidth_ + 2 * outputPadding_;   // gpu/scalelayer.cpp:44-47
+    viewport_[1] = outHeight_ + 2 * outputPadding_;
+}
+ScaleLayer::ScaleLayer(const ScaleLayerBuilder &b, int layerNumber) : GPULayerBase(b, layerNumber) {
+    if (b.rotation_ != 0) THROW_EXCEPTION_ARGS(FynException, "Layer %s: rotation is not supported by the CUDA backend", name_.c_str());
+    init(b.upsample_[0], b.upsample_[1], b.downsample_[0], b.downsample_[1], b.scaleType_);
+}
+ScaleLayer::ScaleLayer(const GPULayerBuilder &b, int layerNumber) : GPULayerBase(b, layerNumber) { init(1, 1, 1, 1, ScalingType::NEAREST); }
+std::vector<BufferSpec> ScaleLayer::getRequiredInputBuffers() const {
+    return {BufferSpec(0, width_, height_, inputChannels_, inputPadding_, order(), storagePrecision(), BufferSpec::FUNCTION_SOURCE).anyType()};
+}
+std::vector<BufferSpec> ScaleLayer::getRequiredOutputBuffers() const {
+    return {BufferSpec(0, outWidth_, outHeight_, outputChannels_, outputPadding_, order(), storagePrecision(), BufferSpec::FUNCTION_DEST)};
+}
+void ScaleLayer::setup() {
+    FYN_ABI_CALL(fyn_scale_create(context_.handle(), &desc_, &op_));
+    valid_ = true;
+}
+void ScaleLayer::cleanup() {
+    if (op_) fyn_op_destroy(op_);
+    op_ = nullptr;
+    GPULayerBase::cleanup();
+}
+void ScaleLayer::forward(uint64_t) {
+    if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    FYN_ABI_CALL(fyn_scale_run(op_, in(0), out(), context_.stream()));
+}
+
+void ArithLayer::init() {
+    desc_.width = width_;
+    desc_.height = height_;
+    desc_.channels = inputChannels_;
+    desc_.in_padding = inputPadding_;
+    desc_.out_padding = outputPadding_;
+    desc_.flags = gatherFlags(flags_);
+    desc_.leaky = leakyReLU_;
+    desc_.clip_lo = lowClip_;
+    desc_.clip_hi = highClip_;
+    if (flags_ & LayerFlags::POST_BATCHNORM)
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: post-batchnorm on arithmetic layers is not supported by the CUDA backend", name_.c_str());
+}
+ArithLayer::ArithLayer(const GPULayerBuilder &b, int layerNumber) : GPULayerBase(b, layerNumber) {
+    if (b.type_ != LayerType::ADD && b.type_ != LayerType::SUB)
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: unsupported operation (only ADD / SUB)", name_.c_str());   // gpu/addsublayer.cpp
+    desc_.op = b.type_ == LayerType::ADD ? FYN_ARITH_ADD : FYN_ARITH_SUB;
+    desc_.singleton = 0;
+    init();
+}
+ArithLayer::ArithLayer(const SingletonArithLayerBuilder &b, int layerNumber) : GPULayerBase(b, layerNumber) {
+    desc_.op = (int)b.opType_;   // ArithType and FYN_ARITH_* share their numbering
+    desc_.singleton = 1;
+    desc_.operand = b.operand_;
+    init();
+}
+std::vector<BufferSpec> ArithLayer::getRequiredInputBuffers() const {
+    std::vector<BufferSpec> specs;
+    for (int port = 0; port < numInputPorts(); port++)
+        specs.push_back(BufferSpec(port, width_, height_, inputChannels_, inputPadding_, order(), storagePrecision(), BufferSpec::FUNCTION_SOURCE).anyType());
+    return specs;
+}
+std::vector<BufferSpec> ArithLayer::getRequiredOutputBuffers() const {
+    return {BufferSpec(0, width_, height_, outputChannels_, outputPadding_, order(), storagePrecision(), BufferSpec::FUNCTION_DEST)};
+}
+void ArithLayer::setup() {
+    FYN_ABI_CALL(fyn_arith_create(context_.handle(), &desc_, &op_));
+    valid_ = true;
+}
+void ArithLayer::cleanup() {
+    if (op_) fyn_op_destroy(op_);
+    op_ = nullptr;
+    GPULayerBase::cleanup();
+}
+void ArithLayer::forward(uint64_t) {
+    if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    FYN_ABI_CALL(fyn_arith_run(op_, in(0), desc_.singleton ? nullptr : in(1), out(), context_.stream()));
+}
+
+ConcatLayer::ConcatLayer(const ConcatLayerBuilder &b, int layerNumber) : GPULayerBase(b, layerNumber) {
+    if (b.inputs_.empty()) THROW_EXCEPTION_ARGS(FynException, "No inputs allocated, please use input()");
+    if ((int)b.inputs_.size() > FYN_CONCAT_MAX_INPUTS)
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: at most %d inputs", name_.c_str(), FYN_CONCAT_MAX_INPUTS);
+    desc_.width = width_;
+    desc_.height = height_;
+    desc_.num_inputs = (int)b.inputs_.size();
+    int total = 0, relu = 0;
+    for (size_t i = 0; i < b.inputs_.size(); i++) {
+        // gpu/concatlayer.cpp:60-64
+        if (b.inputs_[i].padding != inputPadding_)
+            THROW_EXCEPTION_ARGS(FynException, "Mismatch on input padding (%d vs %d)", inputPadding_, b.inputs_[i].padding);
+        desc_.channels[i] = b.inputs_[i].channels;
+        total += b.inputs_[i].channels;
+        if (b.inputs_[i].flags & LayerFlags::PRE_RELU) relu++;
+    }
+    // ReLU on all inputs or on none (gpu/concatlayer.cpp:20-26)
+    if (relu == desc_.num_inputs) flags_ |= LayerFlags::PRE_RELU;
+    else if (relu > 0) THROW_EXCEPTION_ARGS(FynException, "Layer %s: reLU/non-reLU concats are not supported", name_.c_str());
+    if (outputChannels_ != total)
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: %d output channels, inputs add up to %d", name_.c_str(), outputChannels_, total);
+    inputChannels_ = total;
+    desc_.in_padding = inputPadding_;
+    desc_.out_padding = outputPadding_;
+    desc_.flags = gatherFlags(flags_);
+    desc_.leaky = leakyReLU_;
+    desc_.clip_lo = lowClip_;
+    desc_.clip_hi = highClip_;
+}
+int ConcatLayer::numInputChannels(int port) const {
+    if (port < 0 || port >= desc_.num_inputs) THROW_EXCEPTION_ARGS(FynException, "Illegal input port %d specified", port);
+    return desc_.channels[port];
+}
+std::vector<BufferSpec> ConcatLayer::getRequiredInputBuffers() const {
+    std::vector<BufferSpec> specs;
+    for (int port = 0; port < desc_.num_inputs; port++)
+        specs.push_back(BufferSpec(port, width_, height_, desc_.channels[port], inputPadding_, order(), storagePrecision(), BufferSpec::FUNCTION_SOURCE).anyType());
+    return specs;
+}
+std::vector<BufferSpec> ConcatLayer::getRequiredOutputBuffers() const {
+    return {BufferSpec(0, width_, height_, outputChannels_, outputPadding_, order(), storagePrecision(), BufferSpec::FUNCTION_DEST)};
+}
+void ConcatLayer::setup() {
+    FYN_ABI_CALL(fyn_concat_create(context_.handle(), &desc_, &op_));
+    valid_ = true;
+}
+void ConcatLayer::cleanup() {
+    if (op_) fyn_op_destroy(op_);
+    op_ = nullptr;
+    GPULayerBase::cleanup();
+}
+void ConcatLayer::forward(uint64_t) {
+    if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    const fyn_tensor *ins[FYN_CONCAT_MAX_INPUTS];
+    for (int port = 0; port < desc_.num_inputs; port++) ins[port] = in(port);
+    FYN_ABI_CALL(fyn_concat_run(op_, ins, desc_.num_inputs, out(), context_.stream()));
+}
+
+UnaryCopyLayer::UnaryCopyLayer(const GPULayerBuilder &b, int layerNumber, Kind kind) : GPULayerBase(b, layerNumber), kind_(kind) {
+    desc_.width = width_;
+    desc_.height = height_;
+    desc_.channels = inputChannels_;
+    desc_.in_padding = inputPadding_;
+    desc_.out_padding = outputPadding_;
+    desc_.flags = gatherFlags(flags_);
+    desc_.leaky = leakyReLU_;
+    desc_.clip_lo = lowClip_;
+    desc_.clip_hi = highClip_;
+    if (inputChannels_ != outputChannels_)
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: channel count must not change (%d -> %d)", name_.c_str(), inputChannels_, outputChannels_);
+}
+std::vector<BufferSpec> UnaryCopyLayer::getRequiredInputBuffers() const {
+    const BufferSpec::order ord = kind_ == SHALLOW2DEEP ? BufferSpec::order::GPU_SHALLOW : (kind_ == DEEP2SHALLOW ? BufferSpec::order::GPU_DEEP : order());
+    return {BufferSpec(0, width_, height_, inputChannels_, inputPadding_, ord, storagePrecision(), BufferSpec::FUNCTION_SOURCE).anyType()};
+}
+std::vector<BufferSpec> UnaryCopyLayer::getRequiredOutputBuffers() const {
+    const BufferSpec::order ord = kind_ == SHALLOW2DEEP ? BufferSpec::order::GPU_DEEP : (kind_ == DEEP2SHALLOW ? BufferSpec::order::GPU_SHALLOW : order());
+    return {BufferSpec(0, width_, height_, outputChannels_, outputPadding_, ord, storagePrecision(), BufferSpec::FUNCTION_DEST)};
+}
+void UnaryCopyLayer::setup() {
+    if (kind_ == RGB2BGR) FYN_ABI_CALL(fyn_rgb2bgr_create(context_.handle(), &desc_, &op_));
+    else FYN_ABI_CALL(fyn_relayout_create(context_.handle(), &desc_, &op_));
+    valid_ = true;
+}
+void UnaryCopyLayer::cleanup() {
+    if (op_) fyn_op_destroy(op_);
+    op_ = nullptr;
+    GPULayerBase::cleanup();
+}
+void UnaryCopyLayer::forward(uint64_t) {
+    if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    if (kind_ == RGB2BGR) FYN_ABI_CALL(fyn_rgb2bgr_run(op_, in(0), out(), context_.stream()));
+    else FYN_ABI_CALL(fyn_relayout_run(op_, in(0), out(), context_.stream()));
+}
+
+// ------------------------------------------------------------------------------------------------
 // UploadLayer: host float32 [H][W][C] -> C-channel float32 texture, verbatim (gpu/uploadlayer.cpp:360-380)
 // ------------------------------------------------------------------------------------------------
 UploadLayer::UploadLayer(const UpDownLayerBuilder &b, int layerNumber)

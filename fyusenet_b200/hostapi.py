@@ -32,6 +32,7 @@ def lib():
         L.fynhost_last_error.restype = C.c_char_p
         L.fynhost_stylenet_create.restype = C.c_void_p
         L.fynhost_resnet50_create.restype = C.c_void_p
+        L.fynhost_layerzoo_create.restype = C.c_void_p
         L.fynhost_net_weight_floats.restype = C.c_size_t
         L.fynhost_net_weight_offset.restype = C.c_longlong
         L.fynhost_net_output.restype = C.POINTER(C.c_float)
@@ -221,3 +222,15 @@ class ResNet50(Network):
     def logits(self) -> np.ndarray:
         """[batch][1000]: the deep 18x14 download texture is channel order for 1x1 spatial (cpubuffer.cpp:131-142)."""
         return self.output().reshape(self.batch, -1)[:, :1000]
+
+
+class LayerZoo(Network):
+    """samplenetworks/layerzoo.h: upload -> rgb2bgr -> scale x2 (linear) -> *2 -> sub -> concat -> clip -> shallow2deep ->
+    deep scale /2 -> deep2shallow -> padding -> add -> download; no weights."""
+    LAYERS = ("upload", "bgr", "upscale", "twice", "diff", "concat", "clip", "todeep", "downscale", "toshallow", "pad", "sum",
+              "download")
+    CLIP = (0.2, 0.7)
+
+    def __init__(self, width: int, height: int, device=0):
+        super().__init__(lib().fynhost_layerzoo_create(int(width), int(height), int(device)))
+        self.width, self.height = width, height

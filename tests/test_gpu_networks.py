@@ -243,3 +243,58 @@ def test_stylenet_overlapped_bands_are_exact(ksize, w, h, world):
         stitched[ib + skip:ib + skip + keep] = out[skip:skip + keep]
         band.destroy()
     np.testing.assert_array_equal(stitched, whole)
+
+
+@pytest.mark.parametrize("fp32", [False, True])
+def test_layerzoo_network_matches_oracle(fp32, tmp_path):
+    """Every SURVEY 8f rank-2 layer through builders -> factory -> buffer manager -> engine (samplenetworks/layerzoo.cpp),
+    per layer against the oracle chain.  These layers copy / combine stored values: <= 1 fp16 ulp per layer with fp16
+    storage (the bilinear up-scale and the arithmetic round once), 1e-6 with fp32 storage."""
+    w, h = 22, 14
+    hostapi.set_storage_precision(fp32)
+    try:
+        img = fo.synthetic_image(h, w, 4)
+        net = hostapi.LayerZoo(w, h)
+        net.setup()
+        net.set_input(img)
+        net.enable_dumps(tmp_path)
+        net.forward()
+        out = net.output().copy()
+        prec = fo.FP32 if fp32 else fo.FP16_STORE
+        lo, hi = hostapi.LayerZoo.CLIP
+        ref = {}
+        ref["bgr"] = fo.rgb2bgr(fo.upload_hwc(img), prec=prec)
+        ref["upscale"] = fo.scale(ref["bgr"], up=(2, 2), linear=True, prec=prec)
+        ref["twice"] = fo.arith(ref["upscale"], 2.0, fo.ARITH_MUL, prec=prec)
+        ref["diff"] = fo.arith(ref["twice"], ref["upscale"], fo.ARITH_SUB, prec=prec)
+        ref["concat"] = fo.concat([ref["upscale"], ref["diff"], ref["twice"]], prec=prec)
+        ref["clip"] = fo.scale(ref["concat"], act=fo.ACT_CLIP, lo=lo, hi=hi, prec=prec)
+        ref["todeep"] = ref["clip"]
+        ref["downscale"] = fo.scale(ref["todeep"], down=(2, 2), in_pad=1, deep=True, prec=prec)
+        ref["toshallow"] = ref["downscale"]
+        ref["pad"] = ref["toshallow"]
+        ref["sum"] = fo.arith(ref["pad"], ref["pad"], fo.ARITH_ADD, prec=prec)
+        assert ref["sum"].shape == (9, h, w)
+        layers = {l["name"]: l for l in net.layers()}
+        assert [l["name"] for l in net.layers()] == list(hostapi.LayerZoo.LAYERS)
+        for name in hostapi.LayerZoo.LAYERS[1:-1]:
+            l = layers[name]
+            y = _read_dump(tmp_path, name, 1, (l["channels"], l["height"], l["width"]))
+            assert y.shape == ref[name].shape, name
+            if fp32:
+                np.testing.assert_allclose(y, ref[name], rtol=1e-6, atol=1e-6, err_msg=name)
+            else:
+                tol = 2.0 ** (np.floor(np.log2(np.maximum(np.abs(ref[name]), 2.0 ** -14))) - 10)
+                assert np.all(np.abs(y - ref[name]) <= tol), name
+        # the clip really clipped, the difference of 2x and x is x again
+        assert ref["clip"].min() >= np.float32(lo) - 1e-3 and ref["clip"].max() <= np.float32(hi) + 1e-3
+        # download = [planes][H][W][4] (gpu/downloadlayer.cpp:257-283).  The unused lanes of the last plane went through the
+        # same shader arithmetic as in the reference: clip(0) = lo, doubled by the final add (cf. sigmoid(0) = 0.5, SURVEY A.5)
+        z = fo.scale(np.zeros((1, 1, 1), np.float32), act=fo.ACT_CLIP, lo=lo, hi=hi, prec=prec)
+        fill = float(fo.arith(z, z, fo.ARITH_ADD, prec=prec)[0, 0, 0])
+        got = out.reshape(3, h, w, 4)
+        want = fo.download_shallow(ref["sum"], fill).reshape(3, h, w, 4)
+        np.testing.assert_allclose(got, want, rtol=1e-6 if fp32 else 1e-3, atol=1e-6 if fp32 else 1e-3)
+        net.destroy()
+    finally:
+        hostapi.set_storage_precision(False)
