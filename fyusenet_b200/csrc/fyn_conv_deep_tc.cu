@@ -45,7 +45,7 @@ struct DeepTcArgs {
     int nInPlanes, Cout4;        // input planes; output channels rounded up to a multiple of 4
     int NT, nstages, kcs;        // columns per N tile, stages = K*K*kcs, kcs = Cin / 64
     int ring;                    // stage ring depth <= min(kMaxRing, nstages)
-    int nsets;                   // loader sets of this layer (<= kLoadSets, <= nstages): blockDim = (4 * nsets + 1) warps
+    int nsets;                   // loader sets of this layer (<= kLoadSets): blockDim = (4 * nsets + 1) warps
     int tapPacked;               // 1: single input plane (<= 4 channels): a stage holds 16 kernel taps x 4 channels (ResNet stem)
     long long Mtotal;            // batch * Ho * Wo
     uint32_t idesc;
@@ -379,10 +379,12 @@ int fyn_conv_deep_tc_create(fyn_op *op, const float *wb) {
     FYN_CUDA(cudaMemcpy(plan->d_wimg, img.data(), bytes, cudaMemcpyHostToDevice));
     a.wimg = plan->d_wimg;
     // loader sets / ring depth: registers allow two CTAs of 4 sets, four of 2 sets; a ring entry is 16 KB + NT * 128 bytes
-    a.nsets = std::min(kLoadSets, a.nstages);
+    // (all sets also for single-stage layers: the sets split the epilogue's column groups -- 1x1 64->256 @56x56 with residual
+    // takes 68 us with four sets, 98 us with one)
+    a.nsets = kLoadSets;
     a.ring = std::min(kMaxRing, a.nstages);
-    if (const char *e = getenv("FYN_DEEP_SETS")) a.nsets = std::max(1, std::min(std::min(kLoadSets, a.nstages), atoi(e)));
-    if (const char *e = getenv("FYN_DEEP_RING")) a.ring = std::max(a.nsets, std::min(std::min(kMaxRing, a.nstages), atoi(e)));
+    if (const char *e = getenv("FYN_DEEP_SETS")) a.nsets = std::max(1, std::min(kLoadSets, atoi(e)));
+    if (const char *e = getenv("FYN_DEEP_RING")) a.ring = std::max(1, std::min(std::min(kMaxRing, a.nstages), atoi(e)));
     plan->smemBytes = (size_t)a.ring * kAStageBytes + (size_t)a.ring * a.NT * kKC * 2 + ((size_t)a.nInPlanes + 2 * (a.NT / 4) + 64) * 4 + 8 + (2 * kMaxRing + 1) * 8 + 16;
     static size_t maxSmem[64] = {0};
     size_t &cur = maxSmem[op->ctx->device & 63];

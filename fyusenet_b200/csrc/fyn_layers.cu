@@ -33,14 +33,18 @@ __global__ void __launch_bounds__(128) k_pool(const PoolArgs a) {
     const int n = bid / a.tiles;
     const int xo = xb * 32 + threadIdx.x, yo = yb * 4 + threadIdx.y;
     if (xo >= a.Wo || yo >= a.Ho) return;
-    const int bx = a.in.P + a.dx * xo + a.off, by = a.in.P + a.dy * yo + a.off;
+    // window origin in texture coordinates (tile origin hoisted out of the window loop), 32-bit texel index inside the image
+    const int bx = a.in.P + a.dx * xo + a.off + (a.in.deep ? (t % a.in.tx) * a.in.tileW : 0);
+    const int by = a.in.P + a.dy * yo + a.off + (a.in.deep ? (t / a.in.tx) * a.in.tileH : 0);
+    const long long base = (long long)n * a.in.imageElems + (a.in.deep ? 0ll : (long long)t * a.in.planeElems);
     float4 r = a.isMax ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
     const int px = PX ? PX : a.px, py = PY ? PY : a.py;
 #pragma unroll
     for (int j = 0; j < py; j++)
 #pragma unroll
         for (int i = 0; i < px; i++) {
-            float4 v = fyn_fetch(a.in, n, t, bx + i, by + j);
+            const int X = min(max(bx + i, 0), a.in.texW - 1), Y = min(max(by + j, 0), a.in.texH - 1);
+            float4 v = fyn_load_texel(a.in, base + (long long)((Y * a.in.texW + X) * a.in.packing));
             if (!(a.quirk3 && i == 2)) v = fyn_act4(v, a.act);
             if (a.isMax) {
                 r.x = fmaxf(r.x, v.x);
