@@ -158,6 +158,13 @@ extern "C" int fynhost_selftest(char *report, int cap) {
         gpu::GPULayerBuilder plain("cat2");
         plain.shape(8, 4, 4, 8).type(LayerType::CONCAT).number(1);
         r.check(throws([&] { backend.createLayer(LayerType::CONCAT, reinterpret_cast<LayerBuilder *>(&plain), 1); }), "concat needs a ConcatLayerBuilder");
+        // grouped convolutions: only depthwise 3x3 with channel multiplier 1 (gpu/gpulayerfactory.cpp:358-396)
+        gpu::ConvLayerBuilder grouped(3, "grouped");
+        grouped.groupSize(4).shape(8, 4, 4, 8).type(LayerType::CONVOLUTION2D).number(1);
+        r.check(throws([&] { backend.createLayer(LayerType::CONVOLUTION2D, reinterpret_cast<LayerBuilder *>(&grouped), 1); }), "grouped (non-depthwise) convolution throws");
+        gpu::ConvLayerBuilder dw5(5, "dw5");
+        dw5.groupSize(8).shape(8, 4, 4, 8).type(LayerType::CONVOLUTION2D).number(1);
+        r.check(throws([&] { backend.createLayer(LayerType::CONVOLUTION2D, reinterpret_cast<LayerBuilder *>(&dw5), 1); }), "5x5 depthwise convolution throws");
     }
     // ---- host tensors (cpubuffershape.cpp:430-447, cpubuffer.cpp:121-158)
     {

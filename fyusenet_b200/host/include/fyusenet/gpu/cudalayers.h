@@ -2,6 +2,7 @@
 // One class per reference layer family; all arithmetic happens in libfyusenet_b200.so behind the C ABI.
 //   ConvLayer        <- vanilla::ConvLayer1x1 / ConvLayerNxN / FractionalConvLayerNxN (gpu/vanilla/*),
 //                       deep::DeepConvLayer1x1 / DeepConvLayerNxN / DeepGEMMLayer (gpu/deep/*)
+//   DepthwiseConvLayer <- vanilla::DepthwiseConvLayer3x3, deep::DeepDepthwiseConvLayer3x3
 //   PoolingLayer     <- deep::DeepMaxPoolLayer / DeepAvgPoolLayer, MaxPoolLayer / AvgPoolLayer
 //   BatchNormLayer   <- BatchNormLayer, deep::DeepBatchNormLayer
 //   SigmoidLayer     <- SigmoidLayer
@@ -53,11 +54,32 @@ class ConvLayerBase : public GPULayerBase, public ConvLayerInterface {
     int outWidth_ = 0, outHeight_ = 0;
 };
 
+class DepthwiseConvLayer;
 namespace vanilla {
 using ConvLayerNxN = gpu::ConvLayerBase;
 using ConvLayer1x1 = gpu::ConvLayerBase;
 using FractionalConvLayerNxN = gpu::ConvLayerBase;
+using DepthwiseConvLayer3x3 = gpu::DepthwiseConvLayer;
 }  // namespace vanilla
+
+// vanilla::DepthwiseConvLayer3x3 (gpu/vanilla/convlayer_dw_3x3_vanilla.cpp) / deep::DeepDepthwiseConvLayer3x3
+// (gpu/deep/deepdwconvlayer3x3.cpp): selected by the factory when groupSize == input channels (gpulayerfactory.cpp:358-396)
+class DepthwiseConvLayer : public GPULayerBase, public ConvLayerInterface {
+ public:
+    DepthwiseConvLayer(const ConvLayerBuilder &builder, int layerNumber);
+    void setup() override;
+    void cleanup() override;
+    void forward(uint64_t sequence = 0) override;
+    std::vector<BufferSpec> getRequiredInputBuffers() const override;
+    std::vector<BufferSpec> getRequiredOutputBuffers() const override;
+    void loadWeightsAndBiases(const float *biasAndWeights, size_t offset = 0) override;
+
+ protected:
+    fyn_dwconv_desc desc_{};
+    fyn_op *op_ = nullptr;
+    std::vector<float> pendingWeights_;
+    int outWidth_ = 0, outHeight_ = 0;
+};
 
 class PoolingLayer : public GPULayerBase {
  public:
@@ -255,6 +277,7 @@ using DeepGEMMLayer = gpu::ConvLayerBase;
 using DeepMaxPoolLayer = gpu::PoolingLayer;
 using DeepAvgPoolLayer = gpu::PoolingLayer;
 using DeepBatchNormLayer = gpu::BatchNormLayer;
+using DeepDepthwiseConvLayer3x3 = gpu::DepthwiseConvLayer;
 using DeepScaleLayer = gpu::ScaleLayer;
 using DeepConcatLayer = gpu::ConcatLayer;
 }  // namespace deep

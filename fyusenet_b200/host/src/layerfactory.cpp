@@ -54,8 +54,12 @@ LayerBase *CUDALayerFactoryBackend::createLayer(LayerType type, LayerBuilder *bu
     switch (type) {
         case LayerType::CONVOLUTION2D: {
             const ConvLayerBuilder &cb = as<ConvLayerBuilder>(data, "ConvLayerBuilder");
-            if (cb.groupSize_ != 1)
-                THROW_EXCEPTION_ARGS(FynException, "Layer %s: grouped / depthwise convolution is not part of this backend yet", data->name_.c_str());
+            // depthwise when the group size equals the input channel count (gpu/gpulayerfactory.cpp:358-396)
+            if (cb.groupSize_ != 1) {
+                if (cb.groupSize_ == (short)data->inputChannels_ && cb.kernel_ == 3) return new DepthwiseConvLayer(cb, layerNumber);
+                THROW_EXCEPTION_ARGS(FynException, "Layer %s: grouped convolution (group size %d, kernel %d) is not supported", data->name_.c_str(),
+                                     (int)cb.groupSize_, (int)cb.kernel_);
+            }
             return new ConvLayerBase(cb, layerNumber, false);
         }
         case LayerType::FRACCONVOLUTION2D: {

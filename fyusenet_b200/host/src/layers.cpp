@@ -295,6 +295,72 @@ void SigmoidLayer::forward(uint64_t) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// DepthwiseConvLayer
+// ------------------------------------------------------------------------------------------------
+DepthwiseConvLayer::DepthwiseConvLayer(const ConvLayerBuilder &b, int layerNumber) : GPULayerBase(b, layerNumber) {
+    if (b.kernel_ != 3) THROW_EXCEPTION_ARGS(FynException, "Layer %s: depthwise convolution supports 3x3 kernels only", name_.c_str());
+    // channel multiplier = outputs / group size (convlayer_dw_3x3_vanilla.cpp:24-25)
+    if (b.groupSize_ != inputChannels_ || outputChannels_ != inputChannels_)
+        THROW_EXCEPTION_ARGS(FynException, "Channel multipliers are currently not supported");
+    if (b.downsample_[0] != b.downsample_[1] || b.dilation_[0] != b.dilation_[1])
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: anisotropic downsampling / dilation not supported", name_.c_str());
+    if (flags_ & LayerFlags::RESIDUAL_INPUT)
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: residual input on depthwise convolutions is not supported by the CUDA backend", name_.c_str());
+    desc_.width = width_;
+    desc_.height = height_;
+    desc_.channels = inputChannels_;
+    desc_.downsample = b.downsample_[0];
+    desc_.dilation = b.dilation_[0];
+    desc_.in_padding = inputPadding_;
+    desc_.out_padding = outputPadding_;
+    desc_.flags = flags_ & (LayerFlags::POST_BATCHNORM | LayerFlags::DEEP | LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP);
+    desc_.leaky = leakyReLU_;
+    desc_.clip_lo = lowClip_;
+    desc_.clip_hi = highClip_;
+    desc_.quirks = envInt("FYN_QUIRKS", FYN_QUIRKS_REFERENCE);
+    outWidth_ = width_ / desc_.downsample;
+    outHeight_ = height_ / desc_.downsample;
+    viewport_[0] = outWidth_ + 2 * outputPadding_;
+    viewport_[1] = outHeight_ + 2 * outputPadding_;
+}
+std::vector<BufferSpec> DepthwiseConvLayer::getRequiredInputBuffers() const {
+    BufferSpec in0(0, width_, height_, inputChannels_, inputPadding_, order(), storagePrecision(), BufferSpec::CONVOLUTION_SOURCE);
+    if (inputChannels_ < PIXEL_PACKING) in0.anyType();
+    return {in0};
+}
+std::vector<BufferSpec> DepthwiseConvLayer::getRequiredOutputBuffers() const {
+    return {BufferSpec(0, outWidth_, outHeight_, outputChannels_, outputPadding_, order(), storagePrecision(), BufferSpec::CONVOLUTION_DEST)};
+}
+void DepthwiseConvLayer::loadWeightsAndBiases(const float *biasAndWeights, size_t offset) {
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    if (!biasAndWeights) THROW_EXCEPTION_ARGS(FynException, "Layer %s: null weight pointer", name_.c_str());
+    size_t n = (size_t)outputChannels_ * 10;
+    if (flags_ & LayerFlags::POST_BATCHNORM) n += 2 * (size_t)outputChannels_;
+    const float *src = biasAndWeights + offset;
+    if (op_) FYN_ABI_CALL(fyn_dwconv3x3_load_weights(op_, src));
+    else pendingWeights_.assign(src, src + n);
+}
+void DepthwiseConvLayer::setup() {
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    if (pendingWeights_.empty())
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: loadWeightsAndBiases() must be called before setup()", name_.c_str());
+    FYN_ABI_CALL(fyn_dwconv3x3_create(context_.handle(), &desc_, pendingWeights_.data(), &op_));
+    pendingWeights_.clear();
+    pendingWeights_.shrink_to_fit();
+    valid_ = true;
+}
+void DepthwiseConvLayer::cleanup() {
+    if (op_) fyn_op_destroy(op_);
+    op_ = nullptr;
+    GPULayerBase::cleanup();
+}
+void DepthwiseConvLayer::forward(uint64_t) {
+    if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    FYN_ABI_CALL(fyn_dwconv3x3_run(op_, in(0), out(), context_.stream()));
+}
+
+// ------------------------------------------------------------------------------------------------
 // ScaleLayer (+ PADDING2D / RELU / CLIP), ArithLayer, ConcatLayer, UnaryCopyLayer
 // ------------------------------------------------------------------------------------------------
 static unsigned gatherFlags(layerflags f) { return f & (LayerFlags::DEEP | LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP); }

@@ -59,7 +59,8 @@ enum {
     FYN_QUIRK_FRAC3_ASYM = 1,      /* fraconv3x3.frag:14-19: horizontal taps at -2s,-s,0 */
     FYN_QUIRK_FRAC_ACT_FIRST = 2,  /* fractional.inc:11-12 vs :69-70: activation on the first tap only */
     FYN_QUIRK_MAXPOOL3_COL = 4,    /* deepmaxpool.frag: 3rd column of a 3x3 max-pool bypasses activate() */
-    FYN_QUIRKS_REFERENCE = 7
+    FYN_QUIRK_DW_BN_OFFSET = 8,    /* convlayer_dw_3x3_vanilla.cpp:66: the shallow depthwise layer reads its post-BN data at the block start */
+    FYN_QUIRKS_REFERENCE = 15
 };
 
 typedef enum { FYN_ORDER_SHALLOW = 0, FYN_ORDER_DEEP = 1 } fyn_order;
@@ -285,6 +286,29 @@ typedef struct {
 
 int fyn_sigmoid_create(fyn_ctx *ctx, const fyn_unary_desc *desc, fyn_op **op);
 int fyn_sigmoid_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream);
+
+/* Depthwise 3x3 convolution (channel multiplier 1): vanilla::DepthwiseConvLayer3x3
+ * (fyusenet/gpu/vanilla/convlayer_dw_3x3_vanilla.cpp:22-75, shaders/vanilla/conv_dw_3x3.frag, weights
+ * gpu/convweightarray_dw_KxKxNxM.cpp:120-150) and deep::DeepDepthwiseConvLayer3x3
+ * (gpu/deep/deepdwconvlayer3x3.cpp, deepdwconvlayerbase.cpp:40-75, shaders/deep/deepconv_dw3x3_tiled.frag):
+ *   out[c,yo,xo] = s[c] * sum_{ky,kx} W[c][ky][kx] * act(in[c, ds*yo + (ky-1)*dil, ds*xo + (kx-1)*dil]) + b'[c]
+ * with the clamp-to-edge / zero-padding sampling of the regular convolutions.  Data: bias[C], W[C][3][3], then with
+ * POST_BATCHNORM bnScale[C], bnBias[C]; b' = b*s + beta.  The shallow shader has no dilation (taps are +-1 texel);
+ * the deep variant keeps its weights fp16-truncated and its bias / scale fp16-rounded with fp16 storage, like the deep
+ * convolutions.  FYN_QUIRK_DW_BN_OFFSET reproduces the shallow layer's batch-norm read position (block start instead
+ * of behind the weights).  The residual input of these layers is not supported. */
+typedef struct {
+    int width, height, channels;
+    int downsample, dilation;
+    int in_padding, out_padding;
+    unsigned flags;
+    float leaky, clip_lo, clip_hi;
+    int quirks;
+} fyn_dwconv_desc;
+
+int fyn_dwconv3x3_create(fyn_ctx *ctx, const fyn_dwconv_desc *desc, const float *bias_weights_bn, fyn_op **op);
+int fyn_dwconv3x3_load_weights(fyn_op *op, const float *bias_weights_bn);
+int fyn_dwconv3x3_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream);
 
 /* ScaleLayer / DeepScaleLayer (fyusenet/gpu/scalelayer.cpp:40-60,120-140, gpu/deep/deepscalelayer.cpp:30-75,
  * shaders/scaling.frag, geometry of gpu/functionlayer.cpp:194-204): output texel o samples the input at the

@@ -652,6 +652,59 @@ int fyo_scale(const float *in_chw, int C, int H, int W, int in_pad, int deep, in
     return 0;
 }
 
+/* Depthwise 3x3 convolution, channel multiplier 1.
+ * shallow: gpu/vanilla/convlayer_dw_3x3_vanilla.cpp:22-75 + shaders/vanilla/conv_dw_3x3.frag (taps +-1 texel via
+ *          textureOffset, accu += act(pix)*coeff in (ky,kx) order, then *= bnscale, += bias), weights
+ *          gpu/convweightarray_dw_KxKxNxM.cpp:120-150 (W[c][ky][kx]), bias fold :84-95; quirk bit 8: the layer passes the
+ *          block start as batch-norm offset (convlayer_dw_3x3_vanilla.cpp:66), so scale = blob[0..C), beta = blob[C..2C).
+ * deep   : gpu/deep/deepdwconvlayer3x3.cpp + shaders/deep/deepconv_dw3x3_tiled.frag (taps +-dilation, row sums added up,
+ *          applyBN then += bias), weights fp16-truncated and bias / scale through an RGBA16F texture when prec != FP32
+ *          (gpu/deep/deepdwconvlayerbase.cpp:40-75,255-262).
+ * data: bias[C], W[C][3][3], (bnScale[C], bnBias[C]). */
+int fyo_dwconv3x3(const float *in_chw, int C, int H, int W, int in_pad, int deep, int ds, int dil, int post_bn, int quirks,
+                  const float *wb, const fyo_act *act, int prec, float *out_chw) {
+    fyo_act none = {FYO_ACT_NONE, 0, 0, 0};
+    const fyo_act *a = act ? act : &none;
+    if (ds < 1 || dil < 1 || (!deep && dil != 1)) return -1;
+    int Wo = W / ds, Ho = H / ds;
+    if (Wo < 1 || Ho < 1) return -1;
+    int tx = 1, ty = 1;
+    if (deep) fyo_deep_tiling(C, &tx, &ty);
+    const float *bn = (!deep && (quirks & 8)) ? wb : wb + C + (size_t)C * 9;
+    int reduced = deep && prec != FYO_FP32;
+    for (int c = 0; c < C; c++) {
+        int t = c / 4;
+        int ox = deep ? in_pad + (t % tx) * (W + in_pad) : in_pad;
+        int oy = deep ? in_pad + (t / tx) * (H + in_pad) : in_pad;
+        float b = wb[c], s = 1.f;
+        if (post_bn) {
+            s = bn[c];
+            b = b * s + bn[C + c];
+        }
+        if (reduced) {
+            b = h_rn(b);
+            s = h_rn(s);
+        }
+        for (int yo = 0; yo < Ho; yo++)
+            for (int xo = 0; xo < Wo; xo++) {
+                float acc = 0.f;
+                for (int ky = 0; ky < 3; ky++) {
+                    float row = 0.f;
+                    for (int kx = 0; kx < 3; kx++) {
+                        float w = wb[C + (size_t)c * 9 + ky * 3 + kx];
+                        if (reduced) w = fyo_half_trunc(w);
+                        float v = act1(tex_lane(in_chw, C, H, W, in_pad, deep, c, ox + ds * xo + (kx - 1) * dil, oy + ds * yo + (ky - 1) * dil), a);
+                        if (deep) row += v * w;
+                        else acc += v * w;
+                    }
+                    if (deep) acc += row;
+                }
+                out_chw[((size_t)c * Ho + yo) * Wo + xo] = store(acc * s + b, prec);
+            }
+    }
+    return 0;
+}
+
 /* AddSubLayer: gpu/addsublayer.cpp + shaders/add.frag:84-135 (fetch = activate(texture)); SingletonArithmeticLayer:
  * gpu/singleton_arithlayer.cpp + shaders/singleton_arith.frag (activate(texture) op operand).
  * op: 0 add, 1 sub, 2 mul, 3 div; in2 == NULL: scalar operand. */

@@ -28,7 +28,8 @@ enum {
     FYO_Q1_FRAC3_ASYM = 1,      /* fraconv3x3.frag:14-19 horizontal taps -2s,-s,0 */
     FYO_Q2_FRAC_ACT_FIRST = 2,  /* fractional.inc:11-12 vs :69-70 activation on first tap only */
     FYO_Q7_MAXPOOL3_COL = 4,    /* deepmaxpool.frag: 3rd column of a 3x3 max-pool not activated */
-    FYO_QUIRKS_REFERENCE = 7
+    FYO_Q8_DW_BN_OFFSET = 8,    /* convlayer_dw_3x3_vanilla.cpp:66: shallow depthwise conv reads its BN data at the block start */
+    FYO_QUIRKS_REFERENCE = 15
 };
 
 typedef struct {
@@ -80,6 +81,8 @@ void fyo_scale_outdims(int W, int H, int upx, int upy, int dnx, int dny, int *Wo
 int fyo_scale(const float *in_chw, int C, int H, int W, int in_pad, int deep, int upx, int upy, int dnx, int dny,
               int linear, const fyo_act *act, int prec, float *out_chw);
 int fyo_arith(const float *in1, const float *in2, size_t n, int op, float operand, const fyo_act *act, int prec, float *out);
+int fyo_dwconv3x3(const float *in_chw, int C, int H, int W, int in_pad, int deep, int ds, int dil, int post_bn, int quirks,
+                  const float *wb, const fyo_act *act, int prec, float *out_chw);
 int fyo_rgb2bgr(const float *in_chw, int C, int H, int W, int prec, float *out_chw);
 void fyo_upload_hwc_to_chw(const float *hwc, int C, int H, int W, float *chw);
 void fyo_download_shallow(const float *chw, int C, int H, int W, float fill, float *host);

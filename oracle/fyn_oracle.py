@@ -31,7 +31,7 @@ _LIB_PATH = _HERE / "_build" / "libfyn_oracle.so"
 RESIDUAL_INPUT, RELU_ON_RESIDUAL, BATCHNORM_ON_RESIDUAL, POST_BATCHNORM, DEEP = 1, 2, 4, 8, 16
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_CLIP = 0, 1, 2, 3
 FP32, FP16_STORE, FP16_BLEND = 0, 1, 2
-Q1_FRAC3_ASYM, Q2_FRAC_ACT_FIRST, Q7_MAXPOOL3_COL, QUIRKS_REFERENCE = 1, 2, 4, 7
+Q1_FRAC3_ASYM, Q2_FRAC_ACT_FIRST, Q7_MAXPOOL3_COL, QUIRKS_REFERENCE = 1, 2, 4, 15
 
 
 class _Act(C.Structure):
@@ -243,6 +243,22 @@ def scale(x, *, up=(1, 1), down=(1, 1), linear=False, in_pad=0, deep=False, act=
 
 
 ARITH_ADD, ARITH_SUB, ARITH_MUL, ARITH_DIV = 0, 1, 2, 3
+QUIRK_DW_BN_OFFSET = 8
+
+
+def dwconv3x3(x, wb, *, downsample=1, dilation=1, in_pad=0, deep=False, post_bn=False, quirks=0, act=ACT_NONE, leak=0.0, prec=FP32):
+    """Depthwise 3x3 convolution (convlayer_dw_3x3_vanilla.cpp / deepdwconvlayer3x3.cpp); wb = bias[C], W[C][3][3], (bn)."""
+    x = _f32(x)
+    wb = _f32(wb)
+    c, h, w = x.shape
+    assert wb.size >= c * 10 + (2 * c if post_bn and not (quirks & QUIRK_DW_BN_OFFSET and not deep) else 0)
+    out = np.zeros((c, h // downsample, w // downsample), np.float32)
+    a = _act(act, leak)
+    rc = lib().fyo_dwconv3x3(_fp(x), c, h, w, int(in_pad), int(bool(deep)), int(downsample), int(dilation), int(bool(post_bn)),
+                             int(quirks), _fp(wb), C.byref(a), int(prec), _fp(out))
+    if rc != 0:
+        raise RuntimeError(f"fyo_dwconv3x3 failed rc={rc}")
+    return out
 
 
 def arith(a, b, op, *, act=ACT_NONE, prec=FP32):

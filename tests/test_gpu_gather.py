@@ -179,3 +179,56 @@ def test_rgb2bgr_and_relayout(dtype):
         np.testing.assert_array_equal(tex, fo.pack_deep(np.maximum(xs[0], 0), op_).reshape(-1))
         for o in (ts, td, tb, s2d, d2s):
             o.destroy()
+
+
+@pytest.mark.parametrize("dtype", [capi.F16, capi.F32])
+@pytest.mark.parametrize("deep", [False, True])
+def test_depthwise_conv3x3(deep, dtype):
+    """vanilla::DepthwiseConvLayer3x3 / deep::DeepDepthwiseConvLayer3x3 against the oracle (itself checked against the pinned
+    regular-convolution oracle with a diagonal weight matrix).  Tolerance: FYN_F32 2e-5 (summation order), FYN_F16 1 fp16 ulp
+    of the fp16-store oracle + 2e-5."""
+    c = ctx()
+    rng = np.random.default_rng(21)
+    cases = [dict(ch=10, h=9, w=12, ds=1, dil=1, ip=1, op=0, bn=False, relu=False, quirks=None),
+             dict(ch=24, h=16, w=20, ds=2, dil=1, ip=1, op=1, bn=False, relu=True, quirks=None),
+             dict(ch=7, h=8, w=8, ds=1, dil=1, ip=1, op=0, bn=True, relu=False, quirks=None),     # reference BN read position (shallow)
+             dict(ch=7, h=8, w=8, ds=1, dil=1, ip=1, op=0, bn=True, relu=False, quirks=0),
+             dict(ch=12, h=11, w=13, ds=1, dil=1, ip=0, op=0, bn=False, relu=False, quirks=None),  # clamp-to-edge / tile bleed
+             dict(ch=64, h=28, w=28, ds=1, dil=2, ip=2, op=1, bn=True, relu=True, quirks=None)]    # dilation: deep only
+    for cs in cases:
+        if cs["dil"] > 1 and not deep:
+            with pytest.raises(capi.FynError):
+                capi.DwConv3x3(c, np.zeros(cs["ch"] * 12, np.float32), width=cs["w"], height=cs["h"], channels=cs["ch"], dilation=cs["dil"])
+            continue
+        ch = cs["ch"]
+        x = rng.normal(size=(2, ch, cs["h"], cs["w"])).astype(np.float32)
+        wb = np.concatenate([rng.uniform(0.5, 1.5, ch), rng.normal(size=ch * 9) * 0.4, rng.uniform(0.5, 1.5, ch), rng.uniform(-0.2, 0.2, ch)]).astype(np.float32)
+        flags = (capi.FLAG_DEEP if deep else 0) | (capi.FLAG_POST_BATCHNORM if cs["bn"] else 0) | (capi.FLAG_PRE_RELU if cs["relu"] else 0)
+        op = capi.DwConv3x3(c, wb, width=cs["w"], height=cs["h"], channels=ch, downsample=cs["ds"], dilation=cs["dil"], in_padding=cs["ip"],
+                            out_padding=cs["op"], flags=flags, quirks=cs["quirks"])
+        tin = c.tensor(cs["w"], cs["h"], ch, cs["ip"], ORDER[deep], dtype, 2)
+        tout = c.tensor(op.out_width, op.out_height, ch, cs["op"], ORDER[deep], dtype, 2)
+        tin.write_chw(x)
+        op.run(tin, tout)
+        y = tout.read_chw()
+        xs, prec = _prep(x, dtype)
+        q = capi.QUIRKS_REFERENCE if cs["quirks"] is None else cs["quirks"]
+        kw = dict(downsample=cs["ds"], dilation=cs["dil"], in_pad=cs["ip"], deep=deep, post_bn=cs["bn"], quirks=q,
+                  act=fo.ACT_RELU if cs["relu"] else fo.ACT_NONE)
+        ref = np.stack([fo.dwconv3x3(xs[i], wb, prec=prec, **kw) for i in range(2)])
+        assert y.shape == ref.shape
+        if dtype == capi.F32:
+            np.testing.assert_allclose(y, ref, rtol=2e-5, atol=2e-5)
+        else:
+            assert_close_f16(y, ref, np.stack([fo.dwconv3x3(xs[i], wb, prec=fo.FP32, **kw) for i in range(2)]), rl2=3e-3)
+        # hot-swap the weights
+        wb2 = (wb * 0.5).astype(np.float32)
+        op.load_weights(wb2)
+        op.run(tin, tout)
+        ref2 = np.stack([fo.dwconv3x3(xs[i], wb2, prec=prec, **kw) for i in range(2)])
+        if dtype == capi.F32:
+            np.testing.assert_allclose(tout.read_chw(), ref2, rtol=2e-5, atol=2e-5)
+        else:
+            assert_close_f16(tout.read_chw(), ref2)
+        for o in (tin, tout, op):
+            o.destroy()

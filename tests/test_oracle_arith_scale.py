@@ -97,3 +97,52 @@ def test_concat_and_rgb2bgr():
     x5 = x[:5]
     y5 = fo.rgb2bgr(x5)   # channel 4 sits in lane 0 of the second texel: it trades places with the non-existing lane 2
     assert np.all(y5[4] == 0)
+
+
+@pytest.mark.parametrize("deep", [False, True])
+def test_dwconv_equals_block_diagonal_convolution(deep):
+    """The depthwise restatement against the regular-convolution oracle (which the reference's convolution known-answer
+    tests pin, tests/test_oracle_kat.py): a depthwise 3x3 is a 3x3 convolution whose weight matrix is diagonal."""
+    rng = np.random.default_rng(5)
+    c, h, w = 10, 9, 12
+    x = rng.normal(size=(c, h, w)).astype(np.float32)
+    bias = rng.uniform(-0.5, 0.5, c).astype(np.float32)
+    wk = rng.normal(size=(c, 3, 3)).astype(np.float32)
+    bn = np.concatenate([rng.uniform(0.5, 1.5, c), rng.uniform(-0.2, 0.2, c)]).astype(np.float32)
+    full = np.zeros((c, 3, 3, c), np.float32)
+    for i in range(c):
+        full[i, :, :, i] = wk[i]
+    for ds, post_bn, pad, act in [(1, False, 1, fo.ACT_NONE), (2, False, 1, fo.ACT_RELU), (1, True, 1, fo.ACT_NONE), (1, False, 0, fo.ACT_NONE)]:
+        if deep and pad == 0:
+            continue   # un-padded deep tensors bleed into the neighbouring tile; covered below
+        wb_dw = np.concatenate([bias, wk.reshape(-1)] + ([bn] if post_bn else []))
+        wb_full = np.concatenate([bias, full.reshape(-1)] + ([bn] if post_bn else []))
+        ref = fo.conv2d(x, wb_full, c, 3, downsample=ds, in_pad=pad, flags=fo.POST_BATCHNORM if post_bn else 0, deep=deep, act=act)
+        got = fo.dwconv3x3(x, wb_dw, downsample=ds, in_pad=pad, deep=deep, post_bn=post_bn, act=act)
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_dwconv_quirk_and_precision():
+    rng = np.random.default_rng(6)
+    c, h, w = 6, 5, 7
+    x = rng.normal(size=(c, h, w)).astype(np.float32)
+    bias = rng.uniform(0.5, 1.5, c).astype(np.float32)
+    wk = rng.normal(size=(c, 3, 3)).astype(np.float32)
+    bn = np.concatenate([rng.uniform(0.5, 1.5, c), rng.uniform(-0.2, 0.2, c)]).astype(np.float32)
+    wb = np.concatenate([bias, wk.reshape(-1), bn])
+    plain = fo.dwconv3x3(x, wb[: c * 10], in_pad=1) - bias[:, None, None]
+    # reference read position (convlayer_dw_3x3_vanilla.cpp:66): scale = the bias values, beta = the first C weights
+    q = fo.dwconv3x3(x, wb, in_pad=1, post_bn=True, quirks=fo.QUIRK_DW_BN_OFFSET)
+    s, beta = bias, wk.reshape(-1)[:c]
+    np.testing.assert_allclose(q, plain * s[:, None, None] + (bias * s + beta)[:, None, None], rtol=1e-5, atol=1e-5)
+    sane = fo.dwconv3x3(x, wb, in_pad=1, post_bn=True)
+    np.testing.assert_allclose(sane, plain * bn[:c, None, None] + (bias * bn[:c] + bn[c:])[:, None, None], rtol=1e-5, atol=1e-5)
+    # the deep layer ignores the quirk, dilates, and reduces its parameters to fp16 unless storage is fp32
+    d1 = fo.dwconv3x3(x, wb, in_pad=2, deep=True, post_bn=True, dilation=2, quirks=fo.QUIRK_DW_BN_OFFSET)
+    d2 = fo.dwconv3x3(x, wb, in_pad=2, deep=True, post_bn=True, dilation=2)
+    np.testing.assert_array_equal(d1, d2)
+    assert not np.allclose(d2, fo.dwconv3x3(x, wb, in_pad=2, deep=True, post_bn=True, dilation=1))
+    h16 = fo.dwconv3x3(fo.half_round(x), wb, in_pad=1, deep=True, prec=fo.FP16_STORE)
+    np.testing.assert_allclose(h16, fo.dwconv3x3(fo.half_round(x), wb, in_pad=1, deep=True), rtol=4e-3, atol=4e-3)
+    with pytest.raises(RuntimeError):
+        fo.dwconv3x3(x, wb, dilation=2)   # conv_dw_3x3.frag has no dilation
