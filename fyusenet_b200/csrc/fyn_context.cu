@@ -76,7 +76,7 @@ int fyn_get_device_info(fyn_ctx *ctx, fyn_device_info *info) {
     info->cc_minor = ctx->prop.minor;
     info->total_mem = ctx->prop.totalGlobalMem;
     info->smem_per_block_optin = ctx->prop.sharedMemPerBlockOptin;
-    snprintf(info->name, sizeof(info->name), "%s", ctx->prop.name);
+    strncpy(info->name, ctx->prop.name, sizeof(info->name) - 1);   // (memset above keeps it terminated)
     return FYN_OK;
 }
 
