@@ -1,6 +1,7 @@
 // fyn_context.cu -- device context, streams, events, pinned memory.
 // Replaces the roles of GfxContextManager / GfxContextLink (fyusenet/gpu/gfxcontextmanager.h),
 // GLsync fences (fyusenet/base/engine.cpp:779-780) and PBOPool (fyusenet/gl/pbopool.cpp).
+#include <algorithm>
 #include <cstring>
 
 #include "fyn_internal.h"
@@ -76,7 +77,7 @@ int fyn_get_device_info(fyn_ctx *ctx, fyn_device_info *info) {
     info->cc_minor = ctx->prop.minor;
     info->total_mem = ctx->prop.totalGlobalMem;
     info->smem_per_block_optin = ctx->prop.sharedMemPerBlockOptin;
-    strncpy(info->name, ctx->prop.name, sizeof(info->name) - 1);   // (memset above keeps it terminated)
+    memcpy(info->name, ctx->prop.name, std::min(sizeof(info->name) - 1, strlen(ctx->prop.name)));   // (memset above keeps it terminated)
     return FYN_OK;
 }
 
