@@ -59,6 +59,8 @@ if __name__ == "__main__":
     faulthandler.dump_traceback_later(40, exit=True)        # a stuck configuration reports where instead of hanging the box
     which = sys.argv[1:] if len(sys.argv) > 1 else ["all"]
     jobs = {"s3": lambda: stylenet(3, 512, 624, 200), "s9": lambda: stylenet(9, 1524, 1856, 50), "s9_4096": lambda: stylenet(9, 4096, 4096, 10),
-            "r1": lambda: resnet(1, 20), "r32": lambda: resnet(32, 5)}
-    for k in (list(jobs) if which == ["all"] else which):
+            "r1": lambda: resnet(1, 20), "r32": lambda: resnet(32, 5), "r128": lambda: resnet(128, 3), "r512": lambda: resnet(512, 2)}
+    if which == ["all"]:
+        which = ["s3", "s9", "s9_4096", "r1", "r32"]
+    for k in which:
         print(json.dumps(jobs[k]()), flush=True)
