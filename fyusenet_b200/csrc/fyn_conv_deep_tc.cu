@@ -384,7 +384,7 @@ int fyn_conv_deep_tc_create(fyn_op *op, const float *wb) {
     a.nsets = kLoadSets;
     a.ring = std::min(kMaxRing, a.nstages);
     if (const char *e = getenv("FYN_DEEP_SETS")) a.nsets = std::max(1, std::min(kLoadSets, atoi(e)));
-    if (const char *e = getenv("FYN_DEEP_RING")) a.ring = std::max(1, std::min(std::min(kMaxRing, a.nstages), atoi(e)));
+    if (const char *e = getenv("FYN_DEEP_RING")) a.ring = std::min(std::min(kMaxRing, a.nstages), std::max(std::min(a.nsets, a.nstages), atoi(e)));   // ring >= sets: a set must never be two ring uses ahead of the MMA warp (mbarrier parity)
     plan->smemBytes = (size_t)a.ring * kAStageBytes + (size_t)a.ring * a.NT * kKC * 2 + ((size_t)a.nInPlanes + 2 * (a.NT / 4) + 64) * 4 + 8 + (2 * kMaxRing + 1) * 8 + 16;
     static size_t maxSmem[64] = {0};
     size_t &cur = maxSmem[op->ctx->device & 63];
