@@ -186,6 +186,10 @@ __global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmemBase;
+    // programmatic dependent launch: the set-up above overlapped the tail of the previous layer's kernel; its results (this
+    // layer's input / residual) are only touched behind the wait (fetching the first weights ahead of it gained nothing)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp < loadWarps) {
         // ===================== loaders (then epilogue): thread = GEMM row = output pixel =====================
@@ -423,7 +427,18 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     a.scale = a.bias + (size_t)nOut * 4;
     const long long mtiles = (a.Mtotal + kM - 1) / kM;
     dim3 grid((unsigned)mtiles, (unsigned)plan->ntiles);
-    k_conv_deep_tc<<<grid, (4 * a.nsets + 1) * 32, plan->smemBytes, stream>>>(a);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((4 * a.nsets + 1) * 32);
+    cfg.dynamicSmemBytes = plan->smemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static const bool noPdl = getenv("FYN_TC_NO_PDL") != nullptr;   // debugging aid: plain stream-ordered launches
+    cfg.numAttrs = noPdl ? 0 : 1;
+    FYN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_deep_tc, a));
     FYN_CHECK_LAUNCH(op->ctx);
     return FYN_OK;
 }
