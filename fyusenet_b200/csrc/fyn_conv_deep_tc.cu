@@ -430,7 +430,18 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3((4 * a.nsets + 1) * 32);
-    cfg.dynamicSmemBytes = plan->smemBytes;
+    size_t smemBytes = plan->smemBytes;
+    // Large grids of multi-stage layers: three sets and a ring of three (96 KB) let two CTAs share an SM, so that one CTA's
+    // set-up and epilogue overlap the other's gathers; small grids keep four sets (more gathers in flight per CTA).
+    static const int altMode = getenv("FYN_DEEP_ALT") ? atoi(getenv("FYN_DEEP_ALT")) : 1;
+    if (altMode && a.nstages >= 4 && a.nsets == kLoadSets && a.ring == kMaxRing &&
+        mtiles * plan->ntiles >= 2ll * op->ctx->prop.multiProcessorCount) {
+        a.nsets = 3;
+        a.ring = 3;
+        smemBytes -= (size_t)(kMaxRing - 3) * (kAStageBytes + (size_t)a.NT * kKC * 2);
+        cfg.blockDim = dim3((4 * a.nsets + 1) * 32);
+    }
+    cfg.dynamicSmemBytes = smemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
