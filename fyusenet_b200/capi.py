@@ -115,7 +115,7 @@ EXPORTS = [
     "fyn_tensor_wrap", "fyn_tensor_destroy", "fyn_tensor_clear", "fyn_tensor_get_desc", "fyn_tensor_device_ptr",
     "fyn_upload_f32_async", "fyn_download_f32_async", "fyn_download_f32_elems", "fyn_tensor_write_chw_f32",
     "fyn_tensor_read_chw_f32", "fyn_conv2d_output_size", "fyn_conv2d_create", "fyn_conv2d_load_weights",
-    "fyn_conv2d_run", "fyn_conv2d_backend", "fyn_conv2d_set_epilogue", "fyn_conv2d_plan_query", "fyn_pool2d_create", "fyn_pool2d_run", "fyn_batchnorm_create",
+    "fyn_conv2d_run", "fyn_conv2d_backend", "fyn_conv2d_set_epilogue", "fyn_conv2d_set_input_norm", "fyn_conv2d_plan_query", "fyn_pool2d_create", "fyn_pool2d_run", "fyn_batchnorm_create",
     "fyn_batchnorm_load", "fyn_batchnorm_run", "fyn_sigmoid_create", "fyn_sigmoid_run", "fyn_op_destroy",
     "fyn_scale_create", "fyn_scale_out_size", "fyn_scale_run", "fyn_arith_create", "fyn_arith_run", "fyn_concat_create",
     "fyn_concat_run", "fyn_dwconv3x3_create", "fyn_dwconv3x3_load_weights", "fyn_dwconv3x3_run", "fyn_rgb2bgr_create", "fyn_rgb2bgr_run", "fyn_relayout_create", "fyn_relayout_run",
@@ -335,6 +335,14 @@ class Conv2d(_Op):
     def load_weights(self, weights):
         w = np.ascontiguousarray(weights, np.float32)
         check(lib().fyn_conv2d_load_weights(self._h, _fptr(w)))
+
+    def set_input_norm(self, scale_bias):
+        """Fuse the batch-norm layer in front of this (deep 1x1) convolution: scale[Cin], bias[Cin]; None switches it off."""
+        if scale_bias is None:
+            check(lib().fyn_conv2d_set_input_norm(self._h, None))
+        else:
+            sb = np.ascontiguousarray(scale_bias, np.float32)
+            check(lib().fyn_conv2d_set_input_norm(self._h, _fptr(sb)))
 
     def set_epilogue(self, function: int):
         """Fuse the element-wise layer that follows (EPILOGUE_SIGMOID) into the convolution's epilogue."""

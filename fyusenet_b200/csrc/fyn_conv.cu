@@ -151,6 +151,29 @@ int fyn_conv2d_create(fyn_ctx *ctx, const fyn_conv_desc *desc, const float *wb, 
 
 int fyn_conv2d_backend(const fyn_op *op) { return (op && op->kind == FYN_OP_CONV) ? op->backend : 0; }
 
+int fyn_conv2d_set_input_norm(fyn_op *op, const float *sb) {
+    if (!op || op->kind != FYN_OP_CONV) FYN_FAIL(FYN_ERR_INVALID, "not a convolution op");
+    if (!sb) {
+        op->innorm = 0;
+        return FYN_OK;
+    }
+    const fyn_conv_desc &d = op->conv;
+    // padding texels of the stand-alone layer's output are zero, not bn(0): only kernels that never read padding qualify
+    if (!op->dtc || d.kernel != 1 || d.in_channels % 64 != 0 || (d.flags & FYN_FLAG_PRE_CLIP))
+        FYN_FAIL(FYN_ERR_UNSUPPORTED, "conv: input batch-norm fusion needs a 1x1 layer of the deep-tiled tcgen05 family");
+    const int C = d.in_channels;
+    std::vector<float> h((size_t)2 * C);
+    for (int c = 0; c < C; c++) {
+        h[c] = sb[c];
+        h[(size_t)C + c] = sb[(size_t)C + c];
+    }
+    FYN_CUDA(cudaSetDevice(op->ctx->device));
+    if (!op->d_innorm) FYN_CUDA(cudaMalloc((void **)&op->d_innorm, h.size() * sizeof(float)));
+    FYN_CUDA(cudaMemcpy(op->d_innorm, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    op->innorm = 1;
+    return FYN_OK;
+}
+
 int fyn_conv2d_set_epilogue(fyn_op *op, int function) {
     if (!op || op->kind != FYN_OP_CONV) FYN_FAIL(FYN_ERR_INVALID, "not a convolution op");
     if (function != FYN_EPILOGUE_NONE && function != FYN_EPILOGUE_SIGMOID) FYN_FAIL(FYN_ERR_INVALID, "conv: unknown epilogue function %d", function);
@@ -194,6 +217,7 @@ int fyn_conv2d_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn_
         rc = op->dtc ? fyn_conv_deep_tc_run(op, in, res, out, s) : fyn_conv_tc_run(op, in, res, out, s);
         if (rc <= 0) return rc;
     }
+    if (op->innorm) FYN_FAIL(FYN_ERR_UNSUPPORTED, "conv: a fused input batch-norm needs the deep-tiled tcgen05 kernel (fp16 tensors)");
     // direct family; deep layers on fp16 tensors use the fp16-truncated weight / fp16 bias sets
     fyn_op view = *op;
     if (deep && in->desc.dtype == FYN_F16) {
@@ -212,6 +236,7 @@ int fyn_op_destroy(fyn_op *op) {
     if (op->dtc) fyn_conv_deep_tc_destroy(op);
     if (op->d_w) cudaFree(op->d_w);
     if (op->d_bias) cudaFree(op->d_bias);
+    if (op->d_innorm) cudaFree(op->d_innorm);
     delete op;
     return FYN_OK;
 }

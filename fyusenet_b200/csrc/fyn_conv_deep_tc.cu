@@ -41,6 +41,7 @@ struct DeepTcArgs {
     TView in, out, res;
     const uint4 *wimg;           // [ntile][stage][8 chunks][NT][8 halfs]
     const float *bias, *scale;   // per output channel (padded to planes), the fp16-rounded parameter set
+    const float4 *inNorm;        // fused input batch-norm: scale per input plane, then bias per input plane; or NULL
     int K, ds, mh, Wo, Ho, batch;
     int nInPlanes, Cout4;        // input planes; output channels rounded up to a multiple of 4
     int NT, nstages, kcs;        // columns per N tile, stages = K*K*kcs, kcs = Cin / 64
@@ -143,7 +144,9 @@ __device__ __forceinline__ uint2 act_h4(uint2 v, const ActParams &a) {
 }
 
 // dynamic shared memory: [A stages][B stages][plane origin tables][barriers][tmem base]
-__global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_constant__ DeepTcArgs a) {
+// NORM: the input batch-norm fusion (its own instantiation, so that the plain kernel keeps its register budget); two CTAs per SM
+template <bool NORM>
+__global__ void __launch_bounds__(kThreadsDeep, 2) k_conv_deep_tc(const __grid_constant__ DeepTcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int bStageBytes = a.NT * kKC * 2;
     unsigned char *sA = smem;
@@ -219,6 +222,18 @@ __global__ void __launch_bounds__(kThreadsDeep) k_conv_deep_tc(const __grid_cons
                 const int *org = inOrigin + kc * (kKC / 4);
 #pragma unroll
                 for (int j = 0; j < kKC / 4; j++) v[j] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + org[j])) : make_uint2(0u, 0u);
+                if (NORM) {
+                    // the stand-alone batch-norm layer in front of this convolution, evaluated at the fetch: x * s + b in
+                    // fp32, rounded to fp16 like that layer's store (deepbatchnorm.frag:57-58)
+                    const float4 *sc = a.inNorm + kc * (kKC / 4), *bi = sc + a.nInPlanes;
+#pragma unroll
+                    for (int j = 0; j < kKC / 4; j++) {
+                        const float4 s4 = __ldg(sc + j), b4 = __ldg(bi + j);
+                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&v[j].x));
+                        const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&v[j].y));
+                        v[j] = make_uint2(pack_half2(fmaf(f0.x, s4.x, b4.x), fmaf(f0.y, s4.y, b4.y)), pack_half2(fmaf(f1.x, s4.z, b4.z), fmaf(f1.y, s4.w, b4.w)));
+                    }
+                }
             } else {
                 // one plane, sixteen taps per stage; the texture clamps at its edge (base/buffermanager.cpp:657-670), which is
                 // how the under-padded 7x7 stem (P = 1 < 3) still sees a zero border: the outermost texels are padding
@@ -393,7 +408,8 @@ int fyn_conv_deep_tc_create(fyn_op *op, const float *wb) {
     static size_t maxSmem[64] = {0};
     size_t &cur = maxSmem[op->ctx->device & 63];
     if (plan->smemBytes > cur) {
-        FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smemBytes));
+        FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smemBytes));
+        FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smemBytes));
         cur = plan->smemBytes;
     }
     return FYN_OK;
@@ -425,6 +441,7 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     const int nOut = (d.out_channels + 3) / 4;
     a.bias = op->d_bias + (size_t)nOut * 8;
     a.scale = a.bias + (size_t)nOut * 4;
+    a.inNorm = op->innorm ? reinterpret_cast<const float4 *>(op->d_innorm) : nullptr;
     const long long mtiles = (a.Mtotal + kM - 1) / kM;
     dim3 grid((unsigned)mtiles, (unsigned)plan->ntiles);
     cudaLaunchConfig_t cfg{};
@@ -449,7 +466,8 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     cfg.attrs = attr;
     static const bool noPdl = getenv("FYN_TC_NO_PDL") != nullptr;   // debugging aid: plain stream-ordered launches
     cfg.numAttrs = noPdl ? 0 : 1;
-    FYN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_deep_tc, a));
+    if (a.inNorm) FYN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_deep_tc<true>, a));
+    else FYN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_deep_tc<false>, a));
     FYN_CHECK_LAUNCH(op->ctx);
     return FYN_OK;
 }

@@ -244,6 +244,37 @@ __global__ void __launch_bounds__(256) k_eltwise_h4(const EltArgs a, unsigned W,
     }
 }
 
+// small planes (H*W <= 128, e.g. the 7x7 layers of ResNet-50): several planes per block, `sub` (a power of two >= H*W)
+// threads per plane, so that a block of 256 threads is not left four-fifths idle
+__global__ void __launch_bounds__(256) k_eltwise_h4_small(const EltArgs a, unsigned W, unsigned HW, unsigned sub, unsigned planes) {
+    const unsigned plane = blockIdx.x * (256u / sub) + threadIdx.x / sub, p = threadIdx.x % sub;
+    if (plane >= planes || p >= HW) return;
+    const unsigned t = plane % (unsigned)a.tiles, n = plane / (unsigned)a.tiles;
+    long long ib = (long long)n * a.in.imageElems, ob = (long long)n * a.out.imageElems;
+    unsigned ix = a.in.P, iy = a.in.P, ox = a.outP, oy = a.outP;
+    if (a.in.deep) {
+        ix += (t % a.in.tx) * a.in.tileW;
+        iy += (t / a.in.tx) * a.in.tileH;
+    } else {
+        ib += (long long)t * a.in.planeElems;
+    }
+    if (a.out.deep) {
+        ox += (t % a.out.tx) * a.out.tileW;
+        oy += (t / a.out.tx) * a.out.tileH;
+    } else {
+        ob += (long long)t * a.out.planeElems;
+    }
+    const unsigned y = p / W, x = p - y * W;
+    const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const __half *>(a.in.ptr) + ib + ((long long)(iy + y) * a.in.texW + ix + x) * 4));
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+    const float4 r = elt_apply(a, make_float4(f0.x, f0.y, f1.x, f1.y), (int)t);
+    __half2 h0 = __floats2half2_rn(r.x, r.y), h1 = __floats2half2_rn(r.z, r.w);
+    uint2 o;
+    o.x = *reinterpret_cast<unsigned *>(&h0);
+    o.y = *reinterpret_cast<unsigned *>(&h1);
+    *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(a.out.ptr) + ob + ((long long)(oy + y) * a.out.texW + ox + x) * 4) = o;
+}
+
 // launches the fast path when its alignment conditions hold, else the generic kernel
 static int launch_eltwise(fyn_ctx *ctx, const EltArgs &a, int W, int H, cudaStream_t stream) {
     const bool fast = a.in.dtype == FYN_F16 && a.out.dtype == FYN_F16 && a.in.packing == 4 && a.out.packing == 4 && !a.in.deep &&
@@ -259,6 +290,13 @@ static int launch_eltwise(fyn_ctx *ctx, const EltArgs &a, int W, int H, cudaStre
     } else if (a.in.dtype == FYN_F16 && a.out.dtype == FYN_F16 && a.in.packing == 4 && a.out.packing == 4 &&
                (long long)a.in.texW * a.in.texH < (1 << 28) && (long long)a.out.texW * a.out.texH < (1 << 28)) {
         const unsigned HW = (unsigned)W * (unsigned)H;
+        if (HW <= 128) {
+            unsigned sub = 1;
+            while (sub < HW) sub <<= 1;
+            const unsigned planes = (unsigned)a.tiles * (unsigned)a.batch, ppb = 256u / sub;
+            k_eltwise_h4_small<<<(planes + ppb - 1) / ppb, 256, 0, stream>>>(a, (unsigned)W, HW, sub, planes);
+            return 0;
+        }
         const int U = HW > 1024 ? 8 : (HW > 512 ? 4 : (HW > 256 ? 2 : 1));
         const unsigned chunks = (HW + 256u * U - 1) / (256u * U);
         const unsigned blocks = chunks * (unsigned)a.tiles * (unsigned)a.batch;

@@ -43,11 +43,18 @@ class ConvLayerBase : public GPULayerBase, public ConvLayerInterface {
     bool fuseFunction(int function, TensorHandle target);
     void unfuse();
     bool fused() const { return fusedTarget_ != nullptr; }
+    // Fusion of the stand-alone batch-norm layer that produces this layer's input (deep 1x1 convolutions): read `source`
+    // (the batch-norm layer's input tensor) and apply scale / bias at the fetch.  Returns false when the kernel family
+    // cannot do it (the batch-norm layer then simply runs).
+    bool fuseInputNorm(const float *scaleAndBias, TensorHandle source);
+    void unfuseInput();
+    bool inputFused() const { return fusedInput_ != nullptr; }
 
  protected:
     void init(int kernel, int dilation, float sourceStep, bool fractional);
     int fusedFunction_ = 0;
     TensorHandle fusedTarget_ = nullptr;
+    TensorHandle fusedInput_ = nullptr;
     fyn_conv_desc desc_{};
     fyn_op *op_ = nullptr;
     std::vector<float> pendingWeights_;  // weights handed over before setup()
@@ -105,8 +112,15 @@ class BatchNormLayer : public GPULayerBase, public BatchNormInterface {
     std::vector<BufferSpec> getRequiredInputBuffers() const override;
     std::vector<BufferSpec> getRequiredOutputBuffers() const override;
     void loadScaleAndBias(const float *scaleAndBias, size_t sbOffset = 0) override;
+    // fusion support (Engine::updateFusion): a batch-norm layer without prefix activation whose only consumer is a
+    // convolution can be evaluated at that convolution's fetch; a bypassed layer does nothing in forward()
+    bool plainFunction() const { return (flags_ & (LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP)) == 0; }
+    const std::vector<float> &parameters() const { return params_; }
+    void setBypass(ConvLayerBase *consumer) { fusedConsumer_ = consumer; }
+    bool bypassed() const { return fusedConsumer_ != nullptr; }
 
  protected:
+    ConvLayerBase *fusedConsumer_ = nullptr;
     fyn_bn_desc desc_{};
     fyn_op *op_ = nullptr;
     std::vector<float> params_;

@@ -44,6 +44,23 @@ void Engine::updateFusion() {
             fusedLayers_++;
         }
     }
+    // batch-norm -> convolution pairs (the batch-norm layer's only consumer reads it on port 0): the convolution fetches the
+    // batch-norm layer's input and normalises at the fetch (ResNet-50: BN9 ... BN66 in front of the 1x1 reduce convolutions)
+    for (auto it = layers_.begin(); it != layers_.end(); ++it) {
+        auto *bn = dynamic_cast<gpu::BatchNormLayer *>(it.second);
+        if (!bn) continue;
+        const auto &recv = bn->receivers();
+        auto *conv = (recv.size() == 1 && recv[0].second == 0) ? dynamic_cast<gpu::ConvLayerBase *>(recv[0].first) : nullptr;
+        if (!conv) continue;
+        conv->unfuseInput();
+        bn->setBypass(nullptr);
+        // (consecutive layer numbers: nothing can run, and reuse the batch-norm layer's input tensor, between the two)
+        if (want && conv->getNumber() == bn->getNumber() + 1 && bn->plainFunction() && bn->hasInputTexture(0) && !bn->parameters().empty() &&
+            conv->fuseInputNorm(bn->parameters().data(), bn->getInputTexture(0))) {
+            bn->setBypass(conv);
+            fusedLayers_++;
+        }
+    }
 }
 
 void Engine::cleanup() {

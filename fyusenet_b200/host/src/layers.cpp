@@ -142,7 +142,7 @@ void ConvLayerBase::forward(uint64_t) {
             THROW_EXCEPTION_ARGS(FynException, "Residual flag configured, but no such texture found.");
         res = residuals_[0];
     }
-    FYN_ABI_CALL(fyn_conv2d_run(op_, in(0), res, fusedTarget_ ? fusedTarget_ : out(), context_.stream()));
+    FYN_ABI_CALL(fyn_conv2d_run(op_, fusedInput_ ? fusedInput_ : in(0), res, fusedTarget_ ? fusedTarget_ : out(), context_.stream()));
 }
 
 bool ConvLayerBase::fuseFunction(int function, TensorHandle target) {
@@ -157,6 +157,24 @@ bool ConvLayerBase::fuseFunction(int function, TensorHandle target) {
     fusedFunction_ = function;
     fusedTarget_ = target;
     return true;
+}
+
+bool ConvLayerBase::fuseInputNorm(const float *scaleAndBias, TensorHandle source) {
+    if (!op_ || !source || !scaleAndBias || !hasInputTexture(0) || hasOutputTexture(0) == false) return false;
+    // the batch-norm layer's input must be laid out exactly like its output (our regular input), in fp16 storage
+    fyn_tensor_desc mine{}, theirs{};
+    FYN_ABI_CALL(fyn_tensor_get_desc(in(0), &mine, nullptr));
+    FYN_ABI_CALL(fyn_tensor_get_desc(source, &theirs, nullptr));
+    if (memcmp(&mine, &theirs, sizeof(mine)) != 0 || mine.dtype != FYN_F16) return false;
+    if (source == out() || source == fusedTarget_) return false;
+    if (fyn_conv2d_set_input_norm(op_, scaleAndBias) != 0) return false;
+    fusedInput_ = source;
+    return true;
+}
+
+void ConvLayerBase::unfuseInput() {
+    if (op_) fyn_conv2d_set_input_norm(op_, nullptr);
+    fusedInput_ = nullptr;
 }
 
 void ConvLayerBase::unfuse() {
@@ -241,6 +259,10 @@ void BatchNormLayer::loadScaleAndBias(const float *scaleAndBias, size_t sbOffset
     if (!scaleAndBias) THROW_EXCEPTION_ARGS(FynException, "Layer %s: null parameter pointer", name_.c_str());
     params_.assign(scaleAndBias + sbOffset, scaleAndBias + sbOffset + 2 * (size_t)outputChannels_);
     if (op_) FYN_ABI_CALL(fyn_batchnorm_load(op_, params_.data()));
+    if (fusedConsumer_ && hasInputTexture(0) && !fusedConsumer_->fuseInputNorm(params_.data(), in(0))) {
+        fusedConsumer_->unfuseInput();   // new parameters could not be handed over: run as a layer again
+        fusedConsumer_ = nullptr;
+    }
 }
 void BatchNormLayer::setup() {
     if (params_.empty()) THROW_EXCEPTION_ARGS(FynException, "Layer %s: loadScaleAndBias() must be called before setup()", name_.c_str());
@@ -255,6 +277,7 @@ void BatchNormLayer::cleanup() {
 void BatchNormLayer::forward(uint64_t) {
     if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
     std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    if (fusedConsumer_) return;   // evaluated at the consumer's fetch
     FYN_ABI_CALL(fyn_batchnorm_run(op_, in(0), out(), context_.stream()));
 }
 

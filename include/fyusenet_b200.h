@@ -220,6 +220,12 @@ int fyn_conv2d_create(fyn_ctx *ctx, const fyn_conv_desc *desc, const float *bias
 /* hot-swap weights (StyleNet9x9::loadWeightsAndBiases after setup, stylenet9x9.cpp:87-95) */
 int fyn_conv2d_load_weights(fyn_op *op, const float *bias_weights_bn);
 int fyn_conv2d_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *residual, fyn_tensor *out, void *stream);
+/* Engine-level fusion of a DeepBatchNormLayer (fyusenet/gpu/deep/deepbatchnormlayer.cpp:78-147) into the 1x1 convolution
+ * that consumes it: the convolution reads the batch-norm layer's INPUT tensor and applies x*scale+bias, rounded to the
+ * storage precision exactly like the stand-alone layer's store, before its own prefix activation.  scale_bias = scale[Cin],
+ * bias[Cin] (base/batchnorminterface.h:33-48); NULL switches it off.  Only the deep-tiled tcgen05 family with fp16 storage
+ * implements it: FYN_ERR_UNSUPPORTED otherwise (the caller keeps the separate layer). */
+int fyn_conv2d_set_input_norm(fyn_op *op, const float *scale_bias);
 /* which kernel family the op resolved to: 1 = direct, 2 = tcgen05 */
 int fyn_conv2d_backend(const fyn_op *op);
 /* Fuses the element-wise FunctionLayer that consumes this convolution into its epilogue (engine-level layer

@@ -225,3 +225,55 @@ def test_deep_conv_tcgen05(k, ds, ci, co, inp, outp, postbn, res, relures, bnres
     # same operands as the oracle (truncated fp16 weights, fp16 activations), fp32 accumulation in a different order
     assert_close_f16(y, ref, None, ulps=1.01, extra_abs=1e-4 * max(1.0, float(np.abs(ref).max()) / 8))
     assert rel_l2(y, yd) <= 1e-3
+
+
+def test_deep_conv_fused_input_batchnorm():
+    """fyn_conv2d_set_input_norm: a deep 1x1 convolution that evaluates the batch-norm layer in front of it at the fetch is
+    bit-identical to running fyn_batchnorm_run first (same fp32 fma, same fp16 rounding); layers outside the deep-tiled
+    tcgen05 family refuse, and so does a run on fp32 tensors."""
+    c = ctx()
+    rng = np.random.default_rng(31)
+    for ci, co, size, relu, res in [(256, 64, 14, True, False), (64, 72, 9, False, True), (512, 128, 7, True, False)]:
+        x = rng.normal(size=(3, ci, size, size)).astype(np.float32)
+        sb = np.concatenate([rng.uniform(0.5, 1.5, ci), rng.uniform(-0.5, 0.5, ci)]).astype(np.float32)
+        wb = np.concatenate([rng.uniform(-0.5, 0.5, co), rng.normal(0, np.sqrt(2.0 / ci), co * ci)]).astype(np.float32)
+        flags = capi.FLAG_DEEP | (capi.FLAG_PRE_RELU if relu else 0) | (capi.FLAG_RESIDUAL_INPUT if res else 0)
+        conv = capi.Conv2d(c, wb, width=size, height=size, in_channels=ci, out_channels=co, kernel=1, flags=flags)
+        assert conv.backend == capi.BACKEND_TC
+        bn = capi.BatchNorm(c, sb, width=size, height=size, channels=ci, flags=capi.FLAG_DEEP)
+        tin, tbn = (c.tensor(size, size, ci, 0, capi.ORDER_DEEP, capi.F16, 3) for _ in range(2))
+        t1, t2 = (c.tensor(size, size, co, 0, capi.ORDER_DEEP, capi.F16, 3) for _ in range(2))
+        tres = c.tensor(size, size, co, 0, capi.ORDER_DEEP, capi.F16, 3) if res else None
+        tin.write_chw(x)
+        if res:
+            tres.write_chw(rng.normal(size=(3, co, size, size)).astype(np.float32))
+        bn.run(tin, tbn)
+        conv.run(tbn, t1, tres)
+        conv.set_input_norm(sb)
+        conv.run(tin, t2, tres)
+        np.testing.assert_array_equal(t1.read_chw(), t2.read_chw())
+        conv.set_input_norm(None)
+        conv.run(tbn, t2, tres)
+        np.testing.assert_array_equal(t1.read_chw(), t2.read_chw())
+        for o in (conv, bn, tin, tbn, t1, t2, tres):
+            if o is not None:
+                o.destroy()
+    # 3x3 layers read padding texels (zero in the stand-alone layer's output, bn(0) at a fused fetch): refused
+    wb = np.zeros(64 + 64 * 9 * 64, np.float32)
+    conv3 = capi.Conv2d(c, wb, width=8, height=8, in_channels=64, out_channels=64, kernel=3, in_padding=1, flags=capi.FLAG_DEEP)
+    with pytest.raises(capi.FynError):
+        conv3.set_input_norm(np.ones(128, np.float32))
+    conv3.destroy()
+    shallow = capi.Conv2d(c, np.zeros(8 + 8 * 8, np.float32), width=8, height=8, in_channels=8, out_channels=8, kernel=1)
+    with pytest.raises(capi.FynError):
+        shallow.set_input_norm(np.ones(16, np.float32))
+    shallow.destroy()
+    # fp32 tensors take the direct kernel, which does not implement the fusion: the run fails loudly
+    wb = np.concatenate([np.zeros(64), rng.normal(size=64 * 64)]).astype(np.float32)
+    conv = capi.Conv2d(c, wb, width=6, height=6, in_channels=64, out_channels=64, kernel=1, flags=capi.FLAG_DEEP)
+    conv.set_input_norm(np.ones(128, np.float32))
+    a, b = (c.tensor(6, 6, 64, 0, capi.ORDER_DEEP, capi.F32) for _ in range(2))
+    with pytest.raises(capi.FynError):
+        conv.run(a, b)
+    for o in (conv, a, b):
+        o.destroy()

@@ -298,3 +298,32 @@ def test_layerzoo_network_matches_oracle(fp32, tmp_path):
         net.destroy()
     finally:
         hostapi.set_storage_precision(False)
+
+
+def test_resnet50_batchnorm_fusion_is_exact():
+    """Engine-level fusion of the stand-alone batch-norm layers into the 1x1 convolutions that consume them: identical
+    logits, bit for bit, with the fusion on and off (the fused fetch rounds to fp16 exactly where the layer stored), and the
+    usual agreement with the oracle.  BN2 (feeds the 7x7 stem) and BN5 (two consumers) stay layers: 12 of 14 fuse."""
+    weights = fo.resnet50_synthetic_weights()
+    imgs = np.stack([fo.synthetic_image(224, 224, 200 + i) for i in range(2)])
+    out = {}
+    for fusion in (True, False):
+        net = hostapi.ResNet50(batch=2)
+        net.load_weights(weights)
+        net.setup()
+        net.enable_fusion(fusion)
+        assert net.fused_layers == (12 if fusion else 0)
+        net.set_input(imgs)
+        net.forward()
+        out[fusion] = net.logits().copy()
+        if fusion:
+            # new weights after setup reach the fused convolutions as well
+            net.load_weights(fo.resnet50_synthetic_weights(seed=51))
+            net.load_weights(weights)
+            net.forward()
+            np.testing.assert_array_equal(net.logits(), out[True])
+        net.destroy()
+    np.testing.assert_array_equal(out[True], out[False])
+    ref = fo.resnet50_forward(weights, imgs[0], prec=fo.FP16_STORE)
+    assert rel_l2(out[True][0], ref) <= 5e-3
+    assert set(np.argsort(-out[True][0])[:5]) == set(np.argsort(-ref)[:5])
