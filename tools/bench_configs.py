@@ -50,8 +50,17 @@ def resnet(batch, steps):
     for _ in range(steps):
         net.forward()            # synchronous API: upload + layers + download
     dt = (time.perf_counter() - t0) / steps
+    # device-resident figure: the same step without the two PCIe layers, from per-layer CUDA events of a second pass
+    net.enable_timings(True)
+    for _ in range(2):
+        net.forward()
+    net.finish()
+    io_ms = sum(net.layer_timing(l["number"])[0] / 2 for l in net.layers() if l["name"] in ("upload", "download"))
+    all_ms = sum(net.layer_timing(l["number"])[0] / 2 for l in net.layers())
     net.destroy()
-    return {"workload": f"ResNet-50 224x224 batch {batch} (end to end, synchronous API)", "img_per_s": batch / dt, "ms_per_step": dt * 1e3}
+    return {"workload": f"ResNet-50 224x224 batch {batch} (end to end, synchronous API)", "img_per_s": batch / dt, "ms_per_step": dt * 1e3,
+            "upload_download_ms": io_ms, "img_per_s_device_resident": batch / ((all_ms - io_ms) * 1e-3),
+            "note": "device-resident = sum of the per-layer CUDA-event times without the upload / download layers"}
 
 
 if __name__ == "__main__":
