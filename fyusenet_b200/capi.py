@@ -17,7 +17,7 @@ LIB_PATH = _PKG / "lib" / "libfyusenet_b200.so"
 # flags / enums (include/fyusenet_b200.h)
 FLAG_RESIDUAL_INPUT, FLAG_RELU_ON_RESIDUAL, FLAG_BATCHNORM_ON_RESIDUAL = 1, 2, 4
 FLAG_POST_BATCHNORM, FLAG_DEEP, FLAG_PRE_RELU, FLAG_PRE_CLIP = 8, 16, 64, 128
-QUIRK_FRAC3_ASYM, QUIRK_FRAC_ACT_FIRST, QUIRK_MAXPOOL3_COL, QUIRK_DW_BN_OFFSET, QUIRKS_REFERENCE = 1, 2, 4, 8, 15
+QUIRK_FRAC3_ASYM, QUIRK_FRAC_ACT_FIRST, QUIRK_MAXPOOL3_COL, QUIRK_DW_BN_OFFSET, QUIRK_TRANS2X2_NEXT, QUIRKS_REFERENCE = 1, 2, 4, 8, 16, 31
 ORDER_SHALLOW, ORDER_DEEP = 0, 1
 F16, F32 = 0, 1
 BACKEND_AUTO, BACKEND_DIRECT, BACKEND_TC = 0, 1, 2
@@ -98,6 +98,12 @@ class ConcatDesc(C.Structure):
 ARITH_ADD, ARITH_SUB, ARITH_MUL, ARITH_DIV = 0, 1, 2, 3
 
 
+class TransConvDesc(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("in_channels", C.c_int), ("out_channels", C.c_int), ("kernel", C.c_int),
+                ("in_padding", C.c_int), ("out_padding", C.c_int), ("flags", C.c_uint), ("leaky", C.c_float), ("clip_lo", C.c_float),
+                ("clip_hi", C.c_float), ("quirks", C.c_int)]
+
+
 class DwConvDesc(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("downsample", C.c_int), ("dilation", C.c_int),
                 ("in_padding", C.c_int), ("out_padding", C.c_int), ("flags", C.c_uint), ("leaky", C.c_float), ("clip_lo", C.c_float),
@@ -118,7 +124,7 @@ EXPORTS = [
     "fyn_conv2d_run", "fyn_conv2d_backend", "fyn_conv2d_set_epilogue", "fyn_conv2d_set_input_norm", "fyn_conv2d_plan_query", "fyn_pool2d_create", "fyn_pool2d_run", "fyn_batchnorm_create",
     "fyn_batchnorm_load", "fyn_batchnorm_run", "fyn_sigmoid_create", "fyn_sigmoid_run", "fyn_op_destroy",
     "fyn_scale_create", "fyn_scale_out_size", "fyn_scale_run", "fyn_arith_create", "fyn_arith_run", "fyn_concat_create",
-    "fyn_concat_run", "fyn_dwconv3x3_create", "fyn_dwconv3x3_load_weights", "fyn_dwconv3x3_run", "fyn_rgb2bgr_create", "fyn_rgb2bgr_run", "fyn_relayout_create", "fyn_relayout_run",
+    "fyn_concat_run", "fyn_dwconv3x3_create", "fyn_dwconv3x3_load_weights", "fyn_dwconv3x3_run", "fyn_transconv2d_create", "fyn_transconv2d_load_weights", "fyn_transconv2d_run", "fyn_rgb2bgr_create", "fyn_rgb2bgr_run", "fyn_relayout_create", "fyn_relayout_run",
 ]
 
 _lib = None
@@ -404,6 +410,26 @@ class DwConv3x3(_Op):
 
     def run(self, x, out, stream=None):
         check(lib().fyn_dwconv3x3_run(self._h, x._h, out._h, _s(stream)))
+
+
+class TransConv2d(_Op):
+    """Stride-2 transpose convolution, 2x2 / 3x3, shallow (vanilla::TransConvLayer2x2 / TransConvLayer3x3)."""
+
+    def __init__(self, ctx, wb, *, width, height, in_channels, out_channels, kernel, in_padding=0, out_padding=0, flags=0, leaky=0.0,
+                 quirks=None):
+        super().__init__(ctx)
+        self.desc = TransConvDesc(width, height, in_channels, out_channels, kernel, in_padding, out_padding, flags, leaky, 0.0, 0.0,
+                                  QUIRKS_REFERENCE if quirks is None else quirks)
+        self.out_width, self.out_height = 2 * width, 2 * height
+        w = np.ascontiguousarray(wb, np.float32)
+        check(lib().fyn_transconv2d_create(ctx._h, C.byref(self.desc), _fptr(w), C.byref(self._h)))
+
+    def load_weights(self, wb):
+        w = np.ascontiguousarray(wb, np.float32)
+        check(lib().fyn_transconv2d_load_weights(self._h, _fptr(w)))
+
+    def run(self, x, out, stream=None):
+        check(lib().fyn_transconv2d_run(self._h, x._h, out._h, _s(stream)))
 
 
 class Scale(_Op):

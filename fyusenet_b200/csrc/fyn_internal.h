@@ -61,7 +61,7 @@ struct fyn_tensor {
     size_t staging_bytes = 0;
 };
 
-enum fyn_op_kind { FYN_OP_CONV = 1, FYN_OP_POOL, FYN_OP_BN, FYN_OP_SIGMOID, FYN_OP_SCALE, FYN_OP_ARITH, FYN_OP_CONCAT, FYN_OP_RGB2BGR, FYN_OP_RELAYOUT, FYN_OP_DWCONV };
+enum fyn_op_kind { FYN_OP_CONV = 1, FYN_OP_POOL, FYN_OP_BN, FYN_OP_SIGMOID, FYN_OP_SCALE, FYN_OP_ARITH, FYN_OP_CONCAT, FYN_OP_RGB2BGR, FYN_OP_RELAYOUT, FYN_OP_DWCONV, FYN_OP_TRANSCONV };
 
 // Device-side view of a tensor: everything a kernel needs to address texels.
 struct TView {
@@ -114,6 +114,7 @@ struct fyn_op {
     fyn_arith_desc arith{};
     fyn_concat_desc concat{};
     fyn_dwconv_desc dw{};
+    fyn_transconv_desc tconv{};
 };
 
 // tcgen05 path (fyn_conv_tc.cu)

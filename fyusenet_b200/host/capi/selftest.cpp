@@ -162,6 +162,9 @@ extern "C" int fynhost_selftest(char *report, int cap) {
         gpu::ConvLayerBuilder grouped(3, "grouped");
         grouped.groupSize(4).shape(8, 4, 4, 8).type(LayerType::CONVOLUTION2D).number(1);
         r.check(throws([&] { backend.createLayer(LayerType::CONVOLUTION2D, reinterpret_cast<LayerBuilder *>(&grouped), 1); }), "grouped (non-depthwise) convolution throws");
+        gpu::ConvLayerBuilder tc1(3, "tc1");
+        tc1.shape(8, 4, 4, 8).type(LayerType::TRANSCONVOLUTION2D).number(1);   // upsample defaults to 1
+        r.check(throws([&] { backend.createLayer(LayerType::TRANSCONVOLUTION2D, reinterpret_cast<LayerBuilder *>(&tc1), 1); }), "transpose convolution needs stride 2");
         gpu::ConvLayerBuilder dw5(5, "dw5");
         dw5.groupSize(8).shape(8, 4, 4, 8).type(LayerType::CONVOLUTION2D).number(1);
         r.check(throws([&] { backend.createLayer(LayerType::CONVOLUTION2D, reinterpret_cast<LayerBuilder *>(&dw5), 1); }), "5x5 depthwise convolution throws");

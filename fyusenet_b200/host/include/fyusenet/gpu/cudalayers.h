@@ -3,6 +3,7 @@
 //   ConvLayer        <- vanilla::ConvLayer1x1 / ConvLayerNxN / FractionalConvLayerNxN (gpu/vanilla/*),
 //                       deep::DeepConvLayer1x1 / DeepConvLayerNxN / DeepGEMMLayer (gpu/deep/*)
 //   DepthwiseConvLayer <- vanilla::DepthwiseConvLayer3x3, deep::DeepDepthwiseConvLayer3x3
+//   TransConvLayer   <- vanilla::TransConvLayer2x2 / TransConvLayer3x3 (stride 2, shallow)
 //   PoolingLayer     <- deep::DeepMaxPoolLayer / DeepAvgPoolLayer, MaxPoolLayer / AvgPoolLayer
 //   BatchNormLayer   <- BatchNormLayer, deep::DeepBatchNormLayer
 //   SigmoidLayer     <- SigmoidLayer
@@ -62,11 +63,14 @@ class ConvLayerBase : public GPULayerBase, public ConvLayerInterface {
 };
 
 class DepthwiseConvLayer;
+class TransConvLayer;
 namespace vanilla {
 using ConvLayerNxN = gpu::ConvLayerBase;
 using ConvLayer1x1 = gpu::ConvLayerBase;
 using FractionalConvLayerNxN = gpu::ConvLayerBase;
 using DepthwiseConvLayer3x3 = gpu::DepthwiseConvLayer;
+using TransConvLayer2x2 = gpu::TransConvLayer;
+using TransConvLayer3x3 = gpu::TransConvLayer;
 }  // namespace vanilla
 
 // vanilla::DepthwiseConvLayer3x3 (gpu/vanilla/convlayer_dw_3x3_vanilla.cpp) / deep::DeepDepthwiseConvLayer3x3
@@ -86,6 +90,23 @@ class DepthwiseConvLayer : public GPULayerBase, public ConvLayerInterface {
     fyn_op *op_ = nullptr;
     std::vector<float> pendingWeights_;
     int outWidth_ = 0, outHeight_ = 0;
+};
+
+// vanilla::TransConvLayer2x2 / TransConvLayer3x3 (gpu/vanilla/transconvlayerbase_vanilla.cpp): stride-2 transpose convolution
+class TransConvLayer : public GPULayerBase, public ConvLayerInterface {
+ public:
+    TransConvLayer(const ConvLayerBuilder &builder, int layerNumber);
+    void setup() override;
+    void cleanup() override;
+    void forward(uint64_t sequence = 0) override;
+    std::vector<BufferSpec> getRequiredInputBuffers() const override;
+    std::vector<BufferSpec> getRequiredOutputBuffers() const override;
+    void loadWeightsAndBiases(const float *biasAndWeights, size_t offset = 0) override;
+
+ protected:
+    fyn_transconv_desc desc_{};
+    fyn_op *op_ = nullptr;
+    std::vector<float> pendingWeights_;
 };
 
 class PoolingLayer : public GPULayerBase {

@@ -62,6 +62,8 @@ LayerBase *CUDALayerFactoryBackend::createLayer(LayerType type, LayerBuilder *bu
             }
             return new ConvLayerBase(cb, layerNumber, false);
         }
+        case LayerType::TRANSCONVOLUTION2D:
+            return new TransConvLayer(as<ConvLayerBuilder>(data, "ConvLayerBuilder"), layerNumber);
         case LayerType::FRACCONVOLUTION2D: {
             const ConvLayerBuilder &cb = as<ConvLayerBuilder>(data, "ConvLayerBuilder");
             if (cb.isDeep()) THROW_EXCEPTION_ARGS(FynException, "Layer %s: fractional convolution has no deep variant", data->name_.c_str());

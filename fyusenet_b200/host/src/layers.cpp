@@ -384,6 +384,68 @@ void DepthwiseConvLayer::forward(uint64_t) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// TransConvLayer
+// ------------------------------------------------------------------------------------------------
+TransConvLayer::TransConvLayer(const ConvLayerBuilder &b, int layerNumber) : GPULayerBase(b, layerNumber) {
+    // transconvlayerbase_vanilla.cpp:44-62
+    if (b.upsample_[0] != 2 || b.upsample_[1] != 2) THROW_EXCEPTION_ARGS(FynException, "Only stride 2 transpose conv layers are supported for now");
+    if (b.kernel_ != 2 && b.kernel_ != 3) THROW_EXCEPTION_ARGS(FynException, "Layer %s: transpose convolution supports 2x2 and 3x3 kernels", name_.c_str());
+    if (flags_ & LayerFlags::DEEP) THROW_EXCEPTION_ARGS(FynException, "Layer %s: deep transpose convolutions are not supported by the CUDA backend", name_.c_str());
+    if (flags_ & LayerFlags::RESIDUAL_INPUT)
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: residual input on transpose convolutions is not supported by the CUDA backend", name_.c_str());
+    desc_.width = width_;
+    desc_.height = height_;
+    desc_.in_channels = inputChannels_;
+    desc_.out_channels = outputChannels_;
+    desc_.kernel = b.kernel_;
+    desc_.in_padding = inputPadding_;
+    desc_.out_padding = outputPadding_;
+    desc_.flags = flags_ & (LayerFlags::POST_BATCHNORM | LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP);
+    desc_.leaky = leakyReLU_;
+    desc_.clip_lo = lowClip_;
+    desc_.clip_hi = highClip_;
+    desc_.quirks = envInt("FYN_QUIRKS", FYN_QUIRKS_REFERENCE);
+    viewport_[0] = 2 * width_ + 2 * outputPadding_;
+    viewport_[1] = 2 * height_ + 2 * outputPadding_;
+}
+std::vector<BufferSpec> TransConvLayer::getRequiredInputBuffers() const {
+    BufferSpec in0(0, width_, height_, inputChannels_, inputPadding_, order(), storagePrecision(), BufferSpec::CONVOLUTION_SOURCE);
+    if (inputChannels_ < PIXEL_PACKING) in0.anyType();
+    return {in0};
+}
+std::vector<BufferSpec> TransConvLayer::getRequiredOutputBuffers() const {
+    return {BufferSpec(0, 2 * width_, 2 * height_, outputChannels_, outputPadding_, order(), storagePrecision(), BufferSpec::CONVOLUTION_DEST)};
+}
+void TransConvLayer::loadWeightsAndBiases(const float *biasAndWeights, size_t offset) {
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    if (!biasAndWeights) THROW_EXCEPTION_ARGS(FynException, "Layer %s: null weight pointer", name_.c_str());
+    size_t n = (size_t)outputChannels_ + (size_t)desc_.kernel * desc_.kernel * inputChannels_ * outputChannels_;
+    if (flags_ & LayerFlags::POST_BATCHNORM) n += 2 * (size_t)outputChannels_;
+    const float *src = biasAndWeights + offset;
+    if (op_) FYN_ABI_CALL(fyn_transconv2d_load_weights(op_, src));
+    else pendingWeights_.assign(src, src + n);
+}
+void TransConvLayer::setup() {
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    if (pendingWeights_.empty())
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: loadWeightsAndBiases() must be called before setup()", name_.c_str());
+    FYN_ABI_CALL(fyn_transconv2d_create(context_.handle(), &desc_, pendingWeights_.data(), &op_));
+    pendingWeights_.clear();
+    pendingWeights_.shrink_to_fit();
+    valid_ = true;
+}
+void TransConvLayer::cleanup() {
+    if (op_) fyn_op_destroy(op_);
+    op_ = nullptr;
+    GPULayerBase::cleanup();
+}
+void TransConvLayer::forward(uint64_t) {
+    if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    std::lock_guard<std::recursive_mutex> lck(processingLock_);
+    FYN_ABI_CALL(fyn_transconv2d_run(op_, in(0), out(), context_.stream()));
+}
+
+// ------------------------------------------------------------------------------------------------
 // ScaleLayer (+ PADDING2D / RELU / CLIP), ArithLayer, ConcatLayer, UnaryCopyLayer
 // ------------------------------------------------------------------------------------------------
 static unsigned gatherFlags(layerflags f) { return f & (LayerFlags::DEEP | LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP); }

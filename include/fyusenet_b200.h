@@ -60,7 +60,8 @@ enum {
     FYN_QUIRK_FRAC_ACT_FIRST = 2,  /* fractional.inc:11-12 vs :69-70: activation on the first tap only */
     FYN_QUIRK_MAXPOOL3_COL = 4,    /* deepmaxpool.frag: 3rd column of a 3x3 max-pool bypasses activate() */
     FYN_QUIRK_DW_BN_OFFSET = 8,    /* convlayer_dw_3x3_vanilla.cpp:66: the shallow depthwise layer reads its post-BN data at the block start */
-    FYN_QUIRKS_REFERENCE = 15
+    FYN_QUIRK_TRANS2X2_NEXT = 16,  /* convtrans2x2_stride2.frag: odd output rows read input row j+1, odd/odd reads (i+1, j+1) */
+    FYN_QUIRKS_REFERENCE = 31
 };
 
 typedef enum { FYN_ORDER_SHALLOW = 0, FYN_ORDER_DEEP = 1 } fyn_order;
@@ -315,6 +316,31 @@ typedef struct {
 int fyn_dwconv3x3_create(fyn_ctx *ctx, const fyn_dwconv_desc *desc, const float *bias_weights_bn, fyn_op **op);
 int fyn_dwconv3x3_load_weights(fyn_op *op, const float *bias_weights_bn);
 int fyn_dwconv3x3_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream);
+
+/* Transpose convolution, stride 2, kernels 2x2 and 3x3, shallow tensors: vanilla::TransConvLayer2x2 / TransConvLayer3x3
+ * (fyusenet/gpu/vanilla/transconvlayerbase_vanilla.cpp:44-62,195-215,360-420,499-506, transconvlayer{2x2,3x3}_vanilla.cpp,
+ * shaders/vanilla/convtrans{2x2,3x3}_stride2.frag, weights gpu/transconvweightarray{2x2,3x3}xNxM.cpp).  The output is
+ * 2W x 2H; output texel o samples the input at texel coordinate P + (o + 0.5) / 2 -+ half a texel, so with i = o / 2:
+ *   3x3: even o uses the centre tap on input i; odd o uses tap 0 on input i and tap 2 on input i + 1 (per axis) -- the
+ *        correlation of the kernel with the zero-stuffed input; input W (one past the edge) is the padding texel (zero
+ *        with in_padding >= 1, the clamped edge texel without).
+ *   2x2: out[2j+b][2i+a] = W[b][a] * in[j][i]; with FYN_QUIRK_TRANS2X2_NEXT (reference behaviour) odd rows read input
+ *        row j + 1 and odd/odd output texels input (i + 1, j + 1), while odd columns of even rows read column i.
+ * Data: bias[Co], W[Co][K][K][Ci], then with POST_BATCHNORM bnScale[Co], bnBias[Co] (b' = b*s + beta).  The deep-tiled
+ * variants (gpu/deep/deeptransconvlayer*.cpp) and the residual input are not implemented: FYN_ERR_UNSUPPORTED. */
+typedef struct {
+    int width, height;
+    int in_channels, out_channels;
+    int kernel;                 /* 2 or 3 */
+    int in_padding, out_padding;
+    unsigned flags;
+    float leaky, clip_lo, clip_hi;
+    int quirks;
+} fyn_transconv_desc;
+
+int fyn_transconv2d_create(fyn_ctx *ctx, const fyn_transconv_desc *desc, const float *bias_weights_bn, fyn_op **op);
+int fyn_transconv2d_load_weights(fyn_op *op, const float *bias_weights_bn);
+int fyn_transconv2d_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream);
 
 /* ScaleLayer / DeepScaleLayer (fyusenet/gpu/scalelayer.cpp:40-60,120-140, gpu/deep/deepscalelayer.cpp:30-75,
  * shaders/scaling.frag, geometry of gpu/functionlayer.cpp:194-204): output texel o samples the input at the

@@ -705,6 +705,54 @@ int fyo_dwconv3x3(const float *in_chw, int C, int H, int W, int in_pad, int deep
     return 0;
 }
 
+/* Transpose convolution, stride 2, shallow: gpu/vanilla/transconvlayerbase_vanilla.cpp (viewport 2W x 2H :60-62; quad maps
+ * the output interior onto the input interior :365-372, so output texel o samples texel coordinate P + (o+0.5)/2; texStep =
+ * half a texel :206-209; strata by output parity via the stencil :499-506, stratum s+1 = (x&1) + 2*(y&1) + 1 :233),
+ * shaders/vanilla/convtrans3x3_stride2.frag / convtrans2x2_stride2.frag (taps per stratum), weights
+ * gpu/transconvweightarray3x3xNxM.cpp:261-420 (stratum 1: tap 4; 2: taps 3,5; 3: taps 1,7; 4: taps 0,2,6,8 of
+ * W[Co][ky][kx][Ci]) and transconvweightarray2x2xNxM.cpp:277-414 (stratum s: tap s-1), bias fold :168-179.
+ * quirks & 16: the 2x2 shader samples tc - hstep in stratum 2 (column i) but tc + vstep / tc + step in strata 3 / 4 (row
+ * j+1, column i+1 for odd/odd); without the bit every stratum reads input (i, j). */
+int fyo_transconv(const float *in_chw, int Ci, int H, int W, int in_pad, int Co, int K, int post_bn, int quirks, const float *wb,
+                  const fyo_act *act, int prec, float *out_chw) {
+    fyo_act none = {FYO_ACT_NONE, 0, 0, 0};
+    const fyo_act *a = act ? act : &none;
+    if (K != 2 && K != 3) return -1;
+    const float *wsrc = wb + Co, *bn = wsrc + (size_t)Co * K * K * Ci;
+    int Wo = 2 * W, Ho = 2 * H;
+    for (int o = 0; o < Co; o++) {
+        float b = wb[o], s = 1.f;
+        if (post_bn) {
+            s = bn[o];
+            b = b * s + bn[Co + o];
+        }
+        for (int yo = 0; yo < Ho; yo++)
+            for (int xo = 0; xo < Wo; xo++) {
+                int i = xo / 2, j = yo / 2, ox = xo & 1, oy = yo & 1;
+                int kxs[2], dxs[2], nx, kys[2], dys[2], ny;
+                if (K == 3) {
+                    if (ox) { nx = 2; kxs[0] = 0; dxs[0] = 0; kxs[1] = 2; dxs[1] = 1; } else { nx = 1; kxs[0] = 1; dxs[0] = 0; }
+                    if (oy) { ny = 2; kys[0] = 0; dys[0] = 0; kys[1] = 2; dys[1] = 1; } else { ny = 1; kys[0] = 1; dys[0] = 0; }
+                } else {
+                    nx = ny = 1;
+                    kxs[0] = ox;
+                    kys[0] = oy;
+                    dxs[0] = ((quirks & 16) && ox && oy) ? 1 : 0;
+                    dys[0] = ((quirks & 16) && oy) ? 1 : 0;
+                }
+                float acc = 0.f;
+                for (int ty = 0; ty < ny; ty++)
+                    for (int tx = 0; tx < nx; tx++)
+                        for (int c = 0; c < Ci; c++) {
+                            float v = act1(tex_lane(in_chw, Ci, H, W, in_pad, 0, c, in_pad + i + dxs[tx], in_pad + j + dys[ty]), a);
+                            acc += v * wsrc[(((size_t)o * K + kys[ty]) * K + kxs[tx]) * Ci + c];
+                        }
+                out_chw[((size_t)o * Ho + yo) * Wo + xo] = store(acc * s + b, prec);
+            }
+    }
+    return 0;
+}
+
 /* AddSubLayer: gpu/addsublayer.cpp + shaders/add.frag:84-135 (fetch = activate(texture)); SingletonArithmeticLayer:
  * gpu/singleton_arithlayer.cpp + shaders/singleton_arith.frag (activate(texture) op operand).
  * op: 0 add, 1 sub, 2 mul, 3 div; in2 == NULL: scalar operand. */

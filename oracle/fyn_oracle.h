@@ -29,7 +29,8 @@ enum {
     FYO_Q2_FRAC_ACT_FIRST = 2,  /* fractional.inc:11-12 vs :69-70 activation on first tap only */
     FYO_Q7_MAXPOOL3_COL = 4,    /* deepmaxpool.frag: 3rd column of a 3x3 max-pool not activated */
     FYO_Q8_DW_BN_OFFSET = 8,    /* convlayer_dw_3x3_vanilla.cpp:66: shallow depthwise conv reads its BN data at the block start */
-    FYO_QUIRKS_REFERENCE = 15
+    FYO_Q16_TRANS2X2_NEXT = 16, /* convtrans2x2_stride2.frag: strata 3 / 4 sample the NEXT input row / texel */
+    FYO_QUIRKS_REFERENCE = 31
 };
 
 typedef struct {
@@ -83,6 +84,8 @@ int fyo_scale(const float *in_chw, int C, int H, int W, int in_pad, int deep, in
 int fyo_arith(const float *in1, const float *in2, size_t n, int op, float operand, const fyo_act *act, int prec, float *out);
 int fyo_dwconv3x3(const float *in_chw, int C, int H, int W, int in_pad, int deep, int ds, int dil, int post_bn, int quirks,
                   const float *wb, const fyo_act *act, int prec, float *out_chw);
+int fyo_transconv(const float *in_chw, int Ci, int H, int W, int in_pad, int Co, int K, int post_bn, int quirks, const float *wb,
+                  const fyo_act *act, int prec, float *out_chw);
 int fyo_rgb2bgr(const float *in_chw, int C, int H, int W, int prec, float *out_chw);
 void fyo_upload_hwc_to_chw(const float *hwc, int C, int H, int W, float *chw);
 void fyo_download_shallow(const float *chw, int C, int H, int W, float fill, float *host);

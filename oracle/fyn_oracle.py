@@ -31,7 +31,7 @@ _LIB_PATH = _HERE / "_build" / "libfyn_oracle.so"
 RESIDUAL_INPUT, RELU_ON_RESIDUAL, BATCHNORM_ON_RESIDUAL, POST_BATCHNORM, DEEP = 1, 2, 4, 8, 16
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_CLIP = 0, 1, 2, 3
 FP32, FP16_STORE, FP16_BLEND = 0, 1, 2
-Q1_FRAC3_ASYM, Q2_FRAC_ACT_FIRST, Q7_MAXPOOL3_COL, QUIRKS_REFERENCE = 1, 2, 4, 15
+Q1_FRAC3_ASYM, Q2_FRAC_ACT_FIRST, Q7_MAXPOOL3_COL, QUIRKS_REFERENCE = 1, 2, 4, 31
 
 
 class _Act(C.Structure):
@@ -244,6 +244,22 @@ def scale(x, *, up=(1, 1), down=(1, 1), linear=False, in_pad=0, deep=False, act=
 
 ARITH_ADD, ARITH_SUB, ARITH_MUL, ARITH_DIV = 0, 1, 2, 3
 QUIRK_DW_BN_OFFSET = 8
+QUIRK_TRANS2X2_NEXT = 16
+
+
+def transconv(x, wb, out_channels, kernel, *, in_pad=0, post_bn=False, quirks=QUIRKS_REFERENCE, act=ACT_NONE, leak=0.0, prec=FP32):
+    """Stride-2 transpose convolution (transconvlayerbase_vanilla.cpp, convtrans{2x2,3x3}_stride2.frag); shallow layout."""
+    x = _f32(x)
+    wb = _f32(wb)
+    ci, h, w = x.shape
+    assert wb.size >= out_channels * (1 + kernel * kernel * ci) + (2 * out_channels if post_bn else 0)
+    out = np.zeros((out_channels, 2 * h, 2 * w), np.float32)
+    a = _act(act, leak)
+    rc = lib().fyo_transconv(_fp(x), ci, h, w, int(in_pad), int(out_channels), int(kernel), int(bool(post_bn)), int(quirks), _fp(wb),
+                             C.byref(a), int(prec), _fp(out))
+    if rc != 0:
+        raise RuntimeError(f"fyo_transconv failed rc={rc}")
+    return out
 
 
 def dwconv3x3(x, wb, *, downsample=1, dilation=1, in_pad=0, deep=False, post_bn=False, quirks=0, act=ACT_NONE, leak=0.0, prec=FP32):

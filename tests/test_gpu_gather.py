@@ -232,3 +232,41 @@ def test_depthwise_conv3x3(deep, dtype):
             assert_close_f16(tout.read_chw(), ref2)
         for o in (tin, tout, op):
             o.destroy()
+
+
+@pytest.mark.parametrize("dtype", [capi.F16, capi.F32])
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_transpose_conv_stride2(kernel, dtype):
+    """vanilla::TransConvLayer2x2 / 3x3 against the oracle (3x3: checked against the pinned convolution oracle on the
+    zero-stuffed input; 2x2: against the closed form per output parity class).  The reference holds no test for these layers:
+    parity of the strata conventions rests on the code citations in the oracle.  Tolerance: FYN_F32 2e-5, FYN_F16 1 fp16 ulp."""
+    c = ctx()
+    rng = np.random.default_rng(41 + kernel)
+    for ci, co, h, w, ip, op_, bn, relu, quirks in [(6, 5, 7, 9, 1, 0, False, False, None), (12, 20, 16, 10, 1, 1, True, True, None),
+                                                     (3, 8, 5, 6, 0, 0, False, True, None), (8, 3, 9, 9, 1, 0, False, False, 0)]:
+        x = rng.normal(size=(2, ci, h, w)).astype(np.float32)
+        wb = np.concatenate([rng.uniform(-0.5, 0.5, co), rng.normal(size=co * kernel * kernel * ci) * 0.3, rng.uniform(0.5, 1.5, co),
+                             rng.uniform(-0.2, 0.2, co)]).astype(np.float32)
+        flags = (capi.FLAG_POST_BATCHNORM if bn else 0) | (capi.FLAG_PRE_RELU if relu else 0)
+        op = capi.TransConv2d(c, wb, width=w, height=h, in_channels=ci, out_channels=co, kernel=kernel, in_padding=ip, out_padding=op_,
+                              flags=flags, quirks=quirks)
+        tin = c.tensor(w, h, ci, ip, capi.ORDER_SHALLOW, dtype, 2)
+        tout = c.tensor(2 * w, 2 * h, co, op_, capi.ORDER_SHALLOW, dtype, 2)
+        tin.write_chw(x)
+        op.run(tin, tout)
+        y = tout.read_chw()
+        xs, prec = _prep(x, dtype)
+        kw = dict(in_pad=ip, post_bn=bn, quirks=capi.QUIRKS_REFERENCE if quirks is None else quirks, act=fo.ACT_RELU if relu else fo.ACT_NONE)
+        ref = np.stack([fo.transconv(xs[i], wb, co, kernel, prec=prec, **kw) for i in range(2)])
+        assert y.shape == ref.shape == (2, co, 2 * h, 2 * w)
+        if dtype == capi.F32:
+            np.testing.assert_allclose(y, ref, rtol=2e-5, atol=2e-5)
+        else:
+            assert_close_f16(y, ref)
+        _border_is_zero(tout, op_)
+        for o in (tin, tout, op):
+            o.destroy()
+    with pytest.raises(capi.FynError):
+        capi.TransConv2d(c, np.zeros(1000, np.float32), width=4, height=4, in_channels=4, out_channels=4, kernel=3, flags=capi.FLAG_DEEP)
+    with pytest.raises(capi.FynError):
+        capi.TransConv2d(c, np.zeros(1000, np.float32), width=4, height=4, in_channels=4, out_channels=4, kernel=5)

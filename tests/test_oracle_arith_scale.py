@@ -146,3 +146,47 @@ def test_dwconv_quirk_and_precision():
     np.testing.assert_allclose(h16, fo.dwconv3x3(fo.half_round(x), wb, in_pad=1, deep=True), rtol=4e-3, atol=4e-3)
     with pytest.raises(RuntimeError):
         fo.dwconv3x3(x, wb, dilation=2)   # conv_dw_3x3.frag has no dilation
+
+
+def test_transconv3x3_is_convolution_of_zero_stuffed_input():
+    """The 3x3 stride-2 transpose convolution of the reference (strata by output parity, convtrans3x3_stride2.frag) is the
+    pinned regular-convolution oracle applied to the zero-stuffed input (up[2j][2i] = in[j][i]) with zero padding 1."""
+    rng = np.random.default_rng(8)
+    ci, co, h, w = 6, 5, 7, 9
+    x = rng.normal(size=(ci, h, w)).astype(np.float32)
+    wb = np.concatenate([rng.uniform(-0.5, 0.5, co), rng.normal(size=co * 9 * ci) * 0.3, rng.uniform(0.5, 1.5, co), rng.uniform(-0.2, 0.2, co)]).astype(np.float32)
+    up = np.zeros((ci, 2 * h, 2 * w), np.float32)
+    for act in (fo.ACT_NONE, fo.ACT_RELU):
+        up[:, ::2, ::2] = np.maximum(x, 0) if act == fo.ACT_RELU else x
+        for post_bn in (False, True):
+            ref = fo.conv2d(up, wb, co, 3, in_pad=1, flags=fo.POST_BATCHNORM if post_bn else 0)
+            got = fo.transconv(x, wb, co, 3, in_pad=1, post_bn=post_bn, act=act)
+            np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)
+    # without input padding the texel one past the edge is the clamped edge texel instead of zero
+    got0 = fo.transconv(x, wb, co, 3, in_pad=0)
+    np.testing.assert_allclose(got0[:, :-1, :-1], fo.transconv(x, wb, co, 3, in_pad=1)[:, :-1, :-1], rtol=1e-6, atol=1e-6)
+    assert not np.allclose(got0[:, :, -1], fo.transconv(x, wb, co, 3, in_pad=1)[:, :, -1])
+
+
+def test_transconv2x2_strata():
+    rng = np.random.default_rng(9)
+    ci, co, h, w = 5, 4, 6, 7
+    x = rng.normal(size=(ci, h, w)).astype(np.float32)
+    wk = rng.normal(size=(co, 2, 2, ci)).astype(np.float32)
+    bias = rng.uniform(-0.5, 0.5, co).astype(np.float32)
+    wb = np.concatenate([bias, wk.reshape(-1)])
+    # every output parity class (b, a) is a 1x1 convolution with W[:, b, a, :] ...
+    plain = fo.transconv(x, wb, co, 2, in_pad=1, quirks=0)
+    for b in (0, 1):
+        for a in (0, 1):
+            ref = np.einsum("oc,chw->ohw", wk[:, b, a, :], x) + bias[:, None, None]
+            np.testing.assert_allclose(plain[:, b::2, a::2], ref, rtol=1e-5, atol=1e-5)
+    # ... of input (i, j); the reference's shader reads row j+1 for odd rows and (i+1, j+1) for odd/odd texels
+    # (convtrans2x2_stride2.frag STEP 3 / 4: tc + texStep), with zero padding past the last row / column
+    q = fo.transconv(x, wb, co, 2, in_pad=1)
+    xp = np.pad(x, ((0, 0), (0, 1), (0, 1)))
+    np.testing.assert_allclose(q[:, 0::2, :], plain[:, 0::2, :], rtol=0, atol=0)
+    np.testing.assert_allclose(q[:, 1::2, 0::2], np.einsum("oc,chw->ohw", wk[:, 1, 0, :], xp[:, 1:, :-1]) + bias[:, None, None], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(q[:, 1::2, 1::2], np.einsum("oc,chw->ohw", wk[:, 1, 1, :], xp[:, 1:, 1:]) + bias[:, None, None], rtol=1e-5, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        fo.transconv(x, np.zeros(co * (1 + 16 * ci), np.float32), co, 4)
