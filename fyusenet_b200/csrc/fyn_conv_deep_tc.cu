@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(kThreadsDeep, 2) k_conv_deep_tc(const __grid_c
         mbar_init(done, 1);
         fence_barrier_init();
     }
-    if (warp == loadWarps) tmem_alloc(tmemBase, 128);
+    const uint32_t tmemCols = a.NT > 128 ? 256u : 128u;
+    if (warp == loadWarps) tmem_alloc(tmemBase, tmemCols);
     // tile origins: plane q sits at tile (q % tx, q / tx), tiles are tileW x tileH texels apart (deeptiler.cpp:91-94)
     for (int q = threadIdx.x; q < a.nInPlanes && !a.tapPacked; q += nthreads) inOrigin[q] = ((q / a.in.tx) * a.in.tileH * a.in.texW + (q % a.in.tx) * a.in.tileW) * 4;
     for (int k = threadIdx.x; k < (a.NT >> 2); k += nthreads) {
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(kThreadsDeep, 2) k_conv_deep_tc(const __grid_c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == loadWarps) tmem_dealloc(tmem, 128);
+    if (warp == loadWarps) tmem_dealloc(tmem, tmemCols);
 }
 
 }  // namespace
@@ -321,6 +322,9 @@ struct DeepTcPlan {
     size_t wimgBytes = 0;
     size_t smemBytes = 0;
     int ntiles = 0;
+    // second operand image with 256 columns per CTA (short-K layers with >= 256 outputs), chosen at run time for large grids
+    size_t wideOff = 0, wideSmemBytes = 0;   // offset into d_wimg in uint4 units; 0 = not available
+    int wideNtiles = 0;
 };
 
 int fyn_conv_deep_tc_supported(const fyn_conv_desc *d) {
@@ -345,6 +349,11 @@ int fyn_conv_deep_tc_create(fyn_op *op, const float *wb) {
     const int K = d.kernel, Ci = d.in_channels, Co = d.out_channels;
     const int co16 = ((Co + 15) / 16) * 16;
     a.NT = std::min(128, co16);
+    // short-K layers with many outputs (1x1 expansions on 64 / 128 channels): 256 columns per CTA halve the number of CTAs and
+    // of input gathers; their ring of <= 2 stages (<= 96 KB) still lets two CTAs (2 x 256 TMEM columns) share an SM.  Small
+    // grids (batch 1) prefer the 128-column tiles, so both operand images are kept and the run picks one.
+    static const int wideN = getenv("FYN_DEEP_WIDE") ? atoi(getenv("FYN_DEEP_WIDE")) : 1;
+    const bool wide = wideN && Ci > 4 && K * K * (Ci / kKC) <= 2 && co16 >= 256;
     plan->ntiles = (co16 + a.NT - 1) / a.NT;
     a.K = K;
     a.ds = d.downsample;
@@ -373,18 +382,29 @@ int fyn_conv_deep_tc_create(fyn_op *op, const float *wb) {
                 }
             }
     }
-    for (int nt = 0; nt < plan->ntiles && !a.tapPacked; nt++)
-        for (int tap = 0; tap < K * K; tap++)
-            for (int kc = 0; kc < a.kcs; kc++) {
-                __half *dst = img.data() + ((size_t)nt * a.nstages + (size_t)tap * a.kcs + kc) * stageHalfs;
-                for (int n = 0; n < a.NT; n++) {
-                    const int o = nt * a.NT + n;
-                    if (o >= Co) continue;
-                    const float *w = W + ((size_t)o * K * K + tap) * Ci + (size_t)kc * kKC;
-                    for (int c = 0; c < 8; c++)
-                        for (int e = 0; e < 8; e++) dst[((size_t)c * a.NT + n) * 8 + e] = __float2half_rz(fyn_half_trunc_host(w[c * 8 + e]));
+    auto packImage = [&](__half *base, int NT, int ntiles) {
+        const size_t sh = (size_t)8 * NT * 8;
+        for (int nt = 0; nt < ntiles; nt++)
+            for (int tap = 0; tap < K * K; tap++)
+                for (int kc = 0; kc < a.kcs; kc++) {
+                    __half *dst = base + ((size_t)nt * a.nstages + (size_t)tap * a.kcs + kc) * sh;
+                    for (int n = 0; n < NT; n++) {
+                        const int o = nt * NT + n;
+                        if (o >= Co) continue;
+                        const float *w = W + ((size_t)o * K * K + tap) * Ci + (size_t)kc * kKC;
+                        for (int c = 0; c < 8; c++)
+                            for (int e = 0; e < 8; e++) dst[((size_t)c * NT + n) * 8 + e] = __float2half_rz(fyn_half_trunc_host(w[c * 8 + e]));
+                    }
                 }
-            }
+    };
+    if (!a.tapPacked) packImage(img.data(), a.NT, plan->ntiles);
+    plan->wideOff = 0;
+    if (wide) {
+        plan->wideNtiles = (co16 + 255) / 256;
+        plan->wideOff = img.size() / 8;                                  // halfs -> uint4
+        img.resize(img.size() + (size_t)plan->wideNtiles * a.nstages * 8 * 256 * 8, __float2half(0.f));
+        packImage(img.data() + plan->wideOff * 8, 256, plan->wideNtiles);
+    }
     const size_t bytes = img.size() * sizeof(__half);
     FYN_CUDA(cudaSetDevice(op->ctx->device));
     if (plan->d_wimg && plan->wimgBytes < bytes) {
@@ -405,8 +425,14 @@ int fyn_conv_deep_tc_create(fyn_op *op, const float *wb) {
     if (const char *e = getenv("FYN_DEEP_SETS")) a.nsets = std::max(1, std::min(kLoadSets, atoi(e)));
     if (const char *e = getenv("FYN_DEEP_RING")) a.ring = std::min(std::min(kMaxRing, a.nstages), std::max(std::min(a.nsets, a.nstages), atoi(e)));   // ring >= sets: a set must never be two ring uses ahead of the MMA warp (mbarrier parity)
     plan->smemBytes = (size_t)a.ring * kAStageBytes + (size_t)a.ring * a.NT * kKC * 2 + ((size_t)a.nInPlanes + 2 * (a.NT / 4) + 64) * 4 + 8 + (2 * kMaxRing + 1) * 8 + 16;
+    plan->wideSmemBytes = plan->smemBytes + (size_t)a.ring * (256 - a.NT) * kKC * 2 + 2 * ((256 - a.NT) / 4) * 4;
     static size_t maxSmem[64] = {0};
     size_t &cur = maxSmem[op->ctx->device & 63];
+    if (plan->wideOff && plan->wideSmemBytes > cur) {
+        FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->wideSmemBytes));
+        FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->wideSmemBytes));
+        cur = plan->wideSmemBytes;
+    }
     if (plan->smemBytes > cur) {
         FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smemBytes));
         FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smemBytes));
@@ -443,16 +469,25 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     a.scale = a.bias + (size_t)nOut * 4;
     a.inNorm = op->innorm ? reinterpret_cast<const float4 *>(op->d_innorm) : nullptr;
     const long long mtiles = (a.Mtotal + kM - 1) / kM;
-    dim3 grid((unsigned)mtiles, (unsigned)plan->ntiles);
+    int ntiles = plan->ntiles;
+    size_t planSmem = plan->smemBytes;
+    if (plan->wideOff && mtiles * plan->ntiles >= 2ll * op->ctx->prop.multiProcessorCount) {
+        a.NT = 256;
+        a.wimg = plan->d_wimg + plan->wideOff;
+        a.idesc = (1u << 4) | ((uint32_t)(a.NT >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+        ntiles = plan->wideNtiles;
+        planSmem = plan->wideSmemBytes;
+    }
+    dim3 grid((unsigned)mtiles, (unsigned)ntiles);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3((4 * a.nsets + 1) * 32);
-    size_t smemBytes = plan->smemBytes;
+    size_t smemBytes = planSmem;
     // Large grids of multi-stage layers: three sets and a ring of three (96 KB) let two CTAs share an SM, so that one CTA's
     // set-up and epilogue overlap the other's gathers; small grids keep four sets (more gathers in flight per CTA).
     static const int altMode = getenv("FYN_DEEP_ALT") ? atoi(getenv("FYN_DEEP_ALT")) : 1;
     if (altMode && a.nstages >= 4 && a.nsets == kLoadSets && a.ring == kMaxRing &&
-        mtiles * plan->ntiles >= 2ll * op->ctx->prop.multiProcessorCount) {
+        mtiles * ntiles >= 2ll * op->ctx->prop.multiProcessorCount) {
         a.nsets = 3;
         a.ring = 3;
         smemBytes -= (size_t)(kMaxRing - 3) * (kAStageBytes + (size_t)a.NT * kKC * 2);

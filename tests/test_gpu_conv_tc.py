@@ -277,3 +277,24 @@ def test_deep_conv_fused_input_batchnorm():
         conv.run(a, b)
     for o in (conv, a, b):
         o.destroy()
+
+
+def test_deep_conv_wide_tiles_on_large_grids():
+    """Short-K layers with >= 256 outputs switch to 256-column CTAs once the grid is large (fyn_conv_deep_tc.cu: second
+    operand image, chosen at run time): the result must not depend on the tile width.  Checked against the direct kernel on the
+    whole batch and against the oracle on one image (tolerance of the deep tcgen05 tests)."""
+    rng = np.random.default_rng(61)
+    for ci, co, size, batch, res, bn in [(64, 256, 56, 8, True, False), (128, 512, 28, 16, False, True), (64, 300, 40, 12, True, True)]:
+        x = half(rng.normal(size=(batch, ci, size, size)).astype(np.float32))
+        wb = random_wb(rng, ci, co, 1, post_bn=bn)
+        r = half(rng.normal(size=(batch, co, size, size)).astype(np.float32)) if res else None
+        flags = capi.FLAG_PRE_RELU | (capi.FLAG_POST_BATCHNORM if bn else 0) | (capi.FLAG_RELU_ON_RESIDUAL if res else 0)
+        y_small, be = conv_gpu(x[:1], wb, out_channels=co, kernel=1, deep=True, flags=flags, residual=None if r is None else r[:1], want_op=True)[:2]
+        y, be = conv_gpu(x, wb, out_channels=co, kernel=1, deep=True, flags=flags, residual=r, want_op=True)[:2]
+        assert be == capi.BACKEND_TC
+        yd = conv_gpu(x, wb, out_channels=co, kernel=1, deep=True, flags=flags, residual=r, backend=capi.BACKEND_DIRECT)
+        assert rel_l2(y, yd) <= 1e-4
+        np.testing.assert_array_equal(y[0], y_small)            # 128-column tiles (small grid) == 256-column tiles
+        ref = fo.conv2d(x[0], wb, co, 1, flags=(fo.POST_BATCHNORM if bn else 0) | (fo.RELU_ON_RESIDUAL if res else 0), deep=True,
+                        residual=None if r is None else r[0], act=fo.ACT_RELU, prec=fo.FP16_STORE)
+        assert_close_f16(y[0], ref, extra_abs=2e-4)
