@@ -352,8 +352,10 @@ int fyn_conv_deep_tc_create(fyn_op *op, const float *wb) {
     // short-K layers with many outputs (1x1 expansions on 64 / 128 channels): 256 columns per CTA halve the number of CTAs and
     // of input gathers; their ring of <= 2 stages (<= 96 KB) still lets two CTAs (2 x 256 TMEM columns) share an SM.  Small
     // grids (batch 1) prefer the 128-column tiles, so both operand images are kept and the run picks one.
-    static const int wideN = getenv("FYN_DEEP_WIDE") ? atoi(getenv("FYN_DEEP_WIDE")) : 1;
-    const bool wide = wideN && Ci > 4 && K * K * (Ci / kKC) <= 2 && co16 >= 256;
+    // (FYN_DEEP_WIDE: 0 = never, 1 = short-K layers only, 2 = every layer with >= 256 outputs: multi-stage layers then run one
+    // CTA per SM on a ring of four 48 KB stages, but gather every input tile half as often -- +4 % at batch 128)
+    static const int wideN = getenv("FYN_DEEP_WIDE") ? atoi(getenv("FYN_DEEP_WIDE")) : 2;
+    const bool wide = wideN && Ci > 4 && (K * K * (Ci / kKC) <= 2 || wideN == 2) && co16 >= 256;
     plan->ntiles = (co16 + a.NT - 1) / a.NT;
     a.K = K;
     a.ds = d.downsample;
@@ -486,7 +488,7 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     // Large grids of multi-stage layers: three sets and a ring of three (96 KB) let two CTAs share an SM, so that one CTA's
     // set-up and epilogue overlap the other's gathers; small grids keep four sets (more gathers in flight per CTA).
     static const int altMode = getenv("FYN_DEEP_ALT") ? atoi(getenv("FYN_DEEP_ALT")) : 1;
-    if (altMode && a.nstages >= 4 && a.nsets == kLoadSets && a.ring == kMaxRing &&
+    if (altMode && a.NT <= 128 && a.nstages >= 4 && a.nsets == kLoadSets && a.ring == kMaxRing &&
         mtiles * ntiles >= 2ll * op->ctx->prop.multiProcessorCount) {
         a.nsets = 3;
         a.ring = 3;

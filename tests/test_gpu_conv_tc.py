@@ -284,7 +284,8 @@ def test_deep_conv_wide_tiles_on_large_grids():
     operand image, chosen at run time): the result must not depend on the tile width.  Checked against the direct kernel on the
     whole batch and against the oracle on one image (tolerance of the deep tcgen05 tests)."""
     rng = np.random.default_rng(61)
-    for ci, co, size, batch, res, bn in [(64, 256, 56, 8, True, False), (128, 512, 28, 16, False, True), (64, 300, 40, 12, True, True)]:
+    for ci, co, size, batch, res, bn in [(64, 256, 56, 8, True, False), (128, 512, 28, 16, False, True), (64, 300, 40, 12, True, True),
+                                         (256, 1024, 14, 32, True, True)]:   # multi-stage: one 256-column CTA per SM
         x = half(rng.normal(size=(batch, ci, size, size)).astype(np.float32))
         wb = random_wb(rng, ci, co, 1, post_bn=bn)
         r = half(rng.normal(size=(batch, co, size, size)).astype(np.float32)) if res else None
@@ -298,3 +299,10 @@ def test_deep_conv_wide_tiles_on_large_grids():
         ref = fo.conv2d(x[0], wb, co, 1, flags=(fo.POST_BATCHNORM if bn else 0) | (fo.RELU_ON_RESIDUAL if res else 0), deep=True,
                         residual=None if r is None else r[0], act=fo.ACT_RELU, prec=fo.FP16_STORE)
         assert_close_f16(y[0], ref, extra_abs=2e-4)
+    # 3x3, 256 -> 256 on 14x14 at batch 128 (the grid size at which ResNet-50's stage-3 layers switch)
+    x = half(rng.normal(size=(128, 256, 14, 14)).astype(np.float32))
+    wb = random_wb(rng, 256, 256, 3, post_bn=True)
+    kw = dict(out_channels=256, kernel=3, in_pad=1, deep=True, flags=capi.FLAG_PRE_RELU | capi.FLAG_POST_BATCHNORM)
+    y = conv_gpu(x, wb, **kw)
+    assert rel_l2(y, conv_gpu(x, wb, backend=capi.BACKEND_DIRECT, **kw)) <= 1e-4
+    np.testing.assert_array_equal(y[:2], conv_gpu(x[:2], wb, **kw))
