@@ -69,7 +69,6 @@ if __name__ == "__main__":
     which = sys.argv[1:] if len(sys.argv) > 1 else ["all"]
     jobs = {"s3": lambda: stylenet(3, 512, 624, 200), "s9": lambda: stylenet(9, 1524, 1856, 50), "s9_4096": lambda: stylenet(9, 4096, 4096, 10),
             "r1": lambda: resnet(1, 20), "r32": lambda: resnet(32, 5), "r128": lambda: resnet(128, 3), "r512": lambda: resnet(512, 2)}
-    if which == ["all"]:
-        which = ["s3", "s9", "s9_4096", "r1", "r32"]
+    which = [k for w in which for k in (["s3", "s9", "s9_4096", "r1", "r32"] if w == "all" else [w])]
     for k in which:
         print(json.dumps(jobs[k]()), flush=True)
