@@ -195,6 +195,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = None
+    if world > 1 and os.environ.get("FYN_BENCH_NO_NUMA_BIND") is None:
+        from fyusenet_b200 import multigpu
+        numa = multigpu.bind_to_gpu_numa_node(local_rank)      # before any pinned buffer is allocated
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -367,6 +371,8 @@ def main():
             "config": {"workload": "StyleNet 9x9 (stylenet9x9 layout, synthetic He weights) 1524x1856 RGB frame, BASELINE configs[1]",
                        "storage": "fp16 activations (reference default), fp32 accumulate", "frames_per_step": 1,
                        "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "cpu_binding": (f"every rank bound to the NUMA node of its GPU (rank 0: node {numa[0]}, {numa[1]} CPUs)" if numa and numa[0] >= 0
+                                       else "none (single NUMA node or single process)"),
                        "l2": "per-step working set 713 MB >> 126 MB L2, no explicit flush"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(img.nbytes), "d2h_bytes_per_step": out_bytes,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "finite": finite, "delivered": int(delivered),
