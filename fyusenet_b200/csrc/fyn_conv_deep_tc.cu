@@ -488,7 +488,8 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     // Large grids of multi-stage layers: three sets and a ring of three (96 KB) let two CTAs share an SM, so that one CTA's
     // set-up and epilogue overlap the other's gathers; small grids keep four sets (more gathers in flight per CTA).
     static const int altMode = getenv("FYN_DEEP_ALT") ? atoi(getenv("FYN_DEEP_ALT")) : 1;
-    if (altMode && a.NT <= 128 && a.nstages >= 4 && a.nsets == kLoadSets && a.ring == kMaxRing &&
+    // (only where the ring of four keeps a second CTA out: narrow tiles, e.g. the 64-column stem, already fit twice)
+    if (altMode && a.NT <= 128 && planSmem > 113 * 1024 && a.nstages >= 4 && a.nsets == kLoadSets && a.ring == kMaxRing &&
         mtiles * ntiles >= 2ll * op->ctx->prop.multiProcessorCount) {
         a.nsets = 3;
         a.ring = 3;
