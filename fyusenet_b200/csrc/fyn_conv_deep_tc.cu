@@ -257,12 +257,24 @@ __global__ void __launch_bounds__(kThreadsDeep, 2) k_conv_deep_tc(const __grid_c
             mbar_arrive(&full[st]);
         }
         // ===================== epilogue =====================
+        __half *outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((a.outP + yo) * a.out.texW + a.outP + xo) * 4;
+        const __half *resp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems + ((a.resP + yo) * a.res.texW + a.resP + xo) * 4;
+        // the residual texels of this thread's first column groups are fetched while the last MMAs are still running
+        constexpr int kPre = 2;
+        uint2 rpre[kPre][4];
+#pragma unroll
+        for (int g = 0; g < kPre; g++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int cg = set + g * a.nsets;
+                rpre[g][k] = (a.hasRes && valid && cg < (a.NT >> 4) && ntile * a.NT + cg * 16 + 4 * k < a.Cout4)
+                                 ? __ldg(reinterpret_cast<const uint2 *>(resp + resOrigin[cg * 4 + k])) : make_uint2(0u, 0u);
+            }
         mbar_wait(done, 0);
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // TMEM lane quarter of this warp
-        __half *outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((a.outP + yo) * a.out.texW + a.outP + xo) * 4;
-        const __half *resp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems + ((a.resP + yo) * a.res.texW + a.resP + xo) * 4;
-        for (int cg = set; cg < (a.NT >> 4); cg += a.nsets) {             // the sets split the column groups
+        int g = 0;
+        for (int cg = set; cg < (a.NT >> 4); cg += a.nsets, g++) {        // the sets split the column groups
             uint32_t acc[16];
             tmem_ld16(taddr + cg * 16, acc);
             tmem_ld_wait();
@@ -275,7 +287,7 @@ __global__ void __launch_bounds__(kThreadsDeep, 2) k_conv_deep_tc(const __grid_c
                                        fmaf(__uint_as_float(acc[4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[4 * k + 3]), sc.w, bi.w));
                 const int pk = cg * 4 + k;                             // plane inside this N tile
                 if (a.hasRes) {
-                    const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(resp + resOrigin[pk]));
+                    const uint2 raw = g == 0 ? rpre[0][k] : (g == 1 ? rpre[1][k] : __ldg(reinterpret_cast<const uint2 *>(resp + resOrigin[pk])));
                     const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
                     const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
                     float4 q = make_float4(f0.x, f0.y, f1.x, f1.y);
