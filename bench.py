@@ -169,6 +169,193 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# secondary workloads: the other half of BASELINE.json's metric (ResNet-50 img/s) and the sharded configs C4 / C5.
+# They ride in the `secondary` block of the same JSON line; the headline metric stays StyleNet 9x9 @1524x1856.
+# ----------------------------------------------------------------------------------------------------------------------
+RESNET_B512_ROOFLINE_IMG_S = 77700.0     # 6.59 ms per 512 images on one GPU
+RESNET_B1_ROOFLINE_IMG_S = 51100.0
+S9_4096_ROOFLINE_FPS = 1477.0
+
+
+def _timed_wall(fn, steps, barrier):
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    return time.perf_counter() - t0
+
+
+def secondary_resnet_sharded(ctx, comm, rank, world, local_rank, barrier, max_over_ranks, total=512, steps=5, warmup=3):
+    """BASELINE configs[3]: ResNet-50 224x224, 512 images sharded contiguously over the ranks (strong scaling), weights
+    replicated, one NCCL all-gather of the [512/world, 1000] logits per step INSIDE the timed region (fyn_allgather_logits).
+    Device-resident: images resident in HBM (upload / download layers skipped), logits gathered into device memory.
+    e2e: every step uploads this rank's images from pinned host memory, runs the layers, gathers and copies the [512, 1000]
+    logits to pinned host memory."""
+    from fyusenet_b200 import hostapi, multigpu
+    b, e = multigpu.shard_range(total, rank, world)
+    n_local = e - b
+    nmax = (total + world - 1) // world
+    rng = np.random.default_rng(50 + rank)
+    net = hostapi.ResNet50(device=local_rank, batch=n_local)
+    net.load_weights((np.random.default_rng(50).standard_normal(net.weight_floats) * 0.02).astype(np.float32))
+    net.setup()
+    net.input_buffer()[:] = rng.random(n_local * 224 * 224 * 3, dtype=np.float32)
+    gathered = ctx.device_alloc(world * nmax * 1000 * 4)
+    host_logits = ctx.host_alloc(world * nmax * 1000)
+    logits_t = net.layer_tensor(72)
+    stream = net.stream
+
+    def step_e2e():
+        net.forward()                                                   # H2D of the images + 70 layers + D2H of the local logits + sync
+        comm.allgather_logits(logits_t, nmax, gathered, stream)
+        ctx.memcpy_d2h(host_logits, gathered, stream)
+        ctx.stream_sync(stream)
+
+    def step_dev():
+        net.forward()                                                   # layers only (skip_io)
+        comm.allgather_logits(logits_t, nmax, gathered, stream)
+
+    for _ in range(warmup):
+        step_e2e()
+    e2e_s = max_over_ranks(_timed_wall(step_e2e, steps, barrier))
+    finite = bool(np.isfinite(host_logits).all())
+    net.skip_io(True)
+    for _ in range(2):
+        step_dev()
+    ctx.stream_sync(stream)
+    ev0, ev1 = ctx.event_create(), ctx.event_create()
+    barrier()
+    ctx.event_record(ev0, stream)
+    for _ in range(steps):
+        step_dev()
+    ctx.event_record(ev1, stream)
+    ctx.event_sync(ev1)
+    dev_ms = max_over_ranks(ctx.elapsed_ms(ev0, ev1))
+    barrier()
+    net.destroy()
+    ctx.device_free(gathered)
+    value = total * steps / (dev_ms / 1e3)
+    return {"workload": f"ResNet-50 224x224, {total} images batch-sharded over {world} GPU(s), NCCL all-gather of the logits inside the timed region (BASELINE configs[3])",
+            "scaling": "strong", "value": value, "unit": "img/s", "ms_per_step": dev_ms / steps, "steps": steps, "images_per_rank": n_local,
+            "collective": f"fyn_allgather_logits: NCCL all-gather of float32 [{nmax}, 1000] per rank" if world > 1 else "none (one rank): logits converted to float32 on the device",
+            "roofline_frac": value / (RESNET_B512_ROOFLINE_IMG_S * world),
+            "e2e": {"value": total * steps / e2e_s, "unit": "img/s", "ms_per_step": 1e3 * e2e_s / steps,
+                    "h2d_bytes_per_step": int(n_local * 224 * 224 * 3 * 4), "d2h_bytes_per_step": int(n_local * 1000 * 4 + world * nmax * 1000 * 4), "finite": finite}}
+
+
+def secondary_resnet_b1(ctx, rank, world, local_rank, barrier, max_over_ranks, steps=200, warmup=20):
+    """BASELINE configs[2]: ResNet-50 batch 1 (replicas for N > 1).  59 launches per image: the device layers are replayed from
+    a CUDA graph (Engine::enableGraph); the eager figure is reported beside it."""
+    from fyusenet_b200 import hostapi
+    net = hostapi.ResNet50(device=local_rank, batch=1)
+    net.load_weights((np.random.default_rng(50).standard_normal(net.weight_floats) * 0.02).astype(np.float32))
+    net.setup()
+    net.input_buffer()[:] = np.random.default_rng(7 + rank).random(224 * 224 * 3, dtype=np.float32)
+    out = {}
+    for mode in ("eager", "graph"):
+        net.skip_io(False)
+        net.enable_graph(mode == "graph")
+        for _ in range(warmup):
+            net.forward()
+        e2e_s = max_over_ranks(_timed_wall(net.forward, steps, barrier))
+        net.skip_io(True)
+        for _ in range(3):
+            net.forward()
+        net.finish()
+        ev0, ev1 = ctx.event_create(), ctx.event_create()
+        barrier()
+        ctx.event_record(ev0, net.stream)
+        for _ in range(steps):
+            net.forward()
+        ctx.event_record(ev1, net.stream)
+        ctx.event_sync(ev1)
+        dev_ms = max_over_ranks(ctx.elapsed_ms(ev0, ev1))
+        out[mode] = {"value": world * steps / (dev_ms / 1e3), "ms_per_step": dev_ms / steps, "e2e_value": world * steps / e2e_s,
+                     "e2e_ms_per_step": 1e3 * e2e_s / steps, "graph_active": net.graph_active}
+    finite = bool(np.isfinite(net.logits()).all())
+    net.destroy()
+    best = "graph" if out["graph"]["value"] >= out["eager"]["value"] else "eager"
+    return {"workload": f"ResNet-50 224x224 batch 1 (BASELINE configs[2]), {'replicas x' + str(world) if world > 1 else 'single GPU'}",
+            "scaling": "weak", "value": out[best]["value"], "unit": "img/s", "ms_per_step": out[best]["ms_per_step"], "mode": best, "steps": steps,
+            "roofline_frac": out[best]["value"] / (RESNET_B1_ROOFLINE_IMG_S * world), "eager": out["eager"], "graph": out["graph"],
+            "e2e": {"value": out[best]["e2e_value"], "unit": "img/s", "ms_per_step": out[best]["e2e_ms_per_step"],
+                    "h2d_bytes_per_step": 224 * 224 * 3 * 4, "d2h_bytes_per_step": 1008 * 4, "finite": finite}}
+
+
+def secondary_stylenet_bands(ctx, comm, rank, world, local_rank, barrier, max_over_ranks, size=4096, steps=10, warmup=3):
+    """BASELINE configs[4]: StyleNet 9x9 on one 4096x4096 frame, row-banded over the ranks (strong scaling) with the per-layer
+    halo exchange over NVLink (fyn_halo_exchange: peer stores, one kernel per layer); one rank runs the whole frame."""
+    from fyusenet_b200 import hostapi, multigpu, synthetic
+    margin = multigpu.HALO_MARGIN
+    ib, ie, skip, keep = multigpu.stylenet_halo_band_plan(size, world, margin)[rank]
+    h = ie - ib
+    net = hostapi.StyleNet(KSIZE, size, h, upload=True, download=True, device=local_rank)
+    net.load_weights(synthetic.stylenet_weights(KSIZE))
+    net.setup()
+    if world > 1:
+        net.set_halo_exchange(comm, margin, h)
+    # this rank's rows of the synthetic frame (generated per rank: only the shape matters for the timing)
+    net.input_buffer()[:] = np.random.default_rng(4096 + rank).random(h * size * 3, dtype=np.float32)
+    for _ in range(warmup):
+        net.forward()
+    e2e_s = max_over_ranks(_timed_wall(net.forward, steps, barrier))       # band upload + layers + exchanges + band download per step
+    out_bytes = int(net.output_rgba()[0].nbytes)
+    finite = bool(np.isfinite(net.output_rgba()[0]).all())
+    net.skip_io(True)
+    for _ in range(2):
+        net.forward()
+    net.finish()
+    ev0, ev1 = ctx.event_create(), ctx.event_create()
+    barrier()
+    ctx.event_record(ev0, net.stream)
+    for _ in range(steps):
+        net.forward()
+    ctx.event_record(ev1, net.stream)
+    ctx.event_sync(ev1)
+    dev_ms = max_over_ranks(ctx.elapsed_ms(ev0, ev1))
+    barrier()
+    pushed = comm.info()["halo_bytes_pushed"] if world > 1 else 0
+    frames = warmup + steps + 2 + steps
+    net.destroy()
+    value = steps / (dev_ms / 1e3)
+    return {"workload": f"StyleNet 9x9 {size}x{size} frame, {world} row band(s) of {keep} rows + {margin}-row margins, per-layer halo exchange (BASELINE configs[4])",
+            "scaling": "strong", "value": value, "unit": "frames/s", "ms_per_step": dev_ms / steps, "steps": steps,
+            "exchange": "fyn_halo_exchange: peer stores over NVLink (CUDA IPC), one kernel per layer, 15 exchanges per frame" if world > 1 else "none (one rank)",
+            "nvlink_bytes_pushed_per_frame_rank0": int(pushed // max(frames, 1)),
+            "roofline_frac": value / (S9_4096_ROOFLINE_FPS * world),
+            "e2e": {"value": steps / e2e_s, "unit": "frames/s", "ms_per_step": 1e3 * e2e_s / steps,
+                    "h2d_bytes_per_step": int(h * size * 3 * 4), "d2h_bytes_per_step": out_bytes, "finite": finite}}
+
+
+def sustained_run(net, ctx, local_rank, seconds=3.0):
+    """>= `seconds` of back-to-back device-resident forwards with the clock sampler running: the sustained figure next to the
+    burst `value` (the kernels are issue / latency bound, i.e. clock sensitive; this box settles well below its boost clock)."""
+    sampler = ClockSampler(local_rank)
+    # calibrate the chunk so that the host stays ahead of the device without queueing minutes of work
+    ev0, ev1 = ctx.event_create(), ctx.event_create()
+    sampler.start()
+    t_start = time.perf_counter()
+    frames, dev_ms = 0, 0.0
+    while time.perf_counter() - t_start < seconds:
+        ctx.event_record(ev0, net.stream)
+        for _ in range(500):
+            net.forward()
+        ctx.event_record(ev1, net.stream)
+        ctx.event_sync(ev1)
+        dev_ms += ctx.elapsed_ms(ev0, ev1)
+        frames += 500
+    clocks = sampler.stop()
+    power = []
+    for r in sampler.rows:
+        try:
+            power.append(float(r[3]))
+        except Exception:
+            pass
+    return {"value": frames / (dev_ms / 1e3), "unit": "frames/s", "frames": frames, "seconds": dev_ms / 1e3, "ms_per_step": dev_ms / frames,
+            "clocks": clocks, "power_w_median": float(np.median(power)) if power else None, "power_w_max": max(power) if power else None}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,6 +363,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the ResNet-50 / banded StyleNet / sustained blocks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -281,6 +469,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = world * args.steps / (ms / 1e3)
+    sustained = None
+    if not args.no_secondary:
+        try:
+            sustained = sustained_run(net, ctx, local_rank)
+            if world > 1:
+                t = torch.tensor([sustained["ms_per_step"]], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sustained["ms_per_step"] = float(t.item())
+                sustained["value"] = world * 1e3 / sustained["ms_per_step"]
+        except Exception as exc:                                          # a secondary block never costs the headline line
+            sustained = {"error": repr(exc)}
 
     # ------------------------------------------------------------------ end-to-end arm ("e2e")
     # (a) synchronous API, one frame at a time: setInputBuffer/forward/getOutputBuffer like samples/desktop/stylenet.cpp
@@ -328,6 +527,39 @@ def main():
     barrier()
     e2e = world * args.steps / e2e_s
     e2e_sync = world * args.steps / sync_s
+
+    # ------------------------------------------------------------------ secondary workloads
+    secondary = {}
+    if not args.no_secondary:
+        from fyusenet_b200 import multigpu
+
+        def max_over_ranks(v):
+            if world == 1:
+                return float(v)
+            t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        comm = None
+        try:
+            comm = multigpu.make_comm(ctx, rank, world)
+        except Exception as exc:
+            secondary["comm_error"] = repr(exc)
+        jobs = [("resnet50_b512", lambda: secondary_resnet_sharded(ctx, comm, rank, world, local_rank, barrier, max_over_ranks)),
+                ("resnet50_b1", lambda: secondary_resnet_b1(ctx, rank, world, local_rank, barrier, max_over_ranks)),
+                ("stylenet9x9_4096_bands", lambda: secondary_stylenet_bands(ctx, comm, rank, world, local_rank, barrier, max_over_ranks))]
+        for name, job in jobs:
+            try:
+                if comm is None:
+                    raise RuntimeError("no communicator")
+                secondary[name] = job()
+            except Exception as exc:
+                secondary[name] = {"error": repr(exc)}
+                if world > 1:
+                    break                                                  # ranks may be out of step after a failure: stop here
+        if comm is not None:
+            secondary["nccl_version"] = comm.info()["nccl_version"]
+            comm.destroy()
 
     if rank == 0:
         hbm, tf_burst, tf_sust, which = peaks()
@@ -386,6 +618,8 @@ def main():
             "layers_ms": {k: round(v, 4) for k, v in layer_ms.items()},
             "layer_kernel_family": families,
             "layer_ms_sum": total_layer_ms,
+            "sustained": sustained,
+            "secondary": secondary,
         }
         if not args.no_cpu_baseline and world == 1:
             # bounded sample: full frames until ~12 s of CPU work have been spent

@@ -125,6 +125,8 @@ EXPORTS = [
     "fyn_batchnorm_load", "fyn_batchnorm_run", "fyn_sigmoid_create", "fyn_sigmoid_run", "fyn_op_destroy",
     "fyn_scale_create", "fyn_scale_out_size", "fyn_scale_run", "fyn_arith_create", "fyn_arith_run", "fyn_concat_create",
     "fyn_concat_run", "fyn_dwconv3x3_create", "fyn_dwconv3x3_load_weights", "fyn_dwconv3x3_run", "fyn_transconv2d_create", "fyn_transconv2d_load_weights", "fyn_transconv2d_run", "fyn_rgb2bgr_create", "fyn_rgb2bgr_run", "fyn_relayout_create", "fyn_relayout_run",
+    "fyn_graph_begin_capture", "fyn_graph_end_capture", "fyn_graph_launch", "fyn_graph_destroy",
+    "fyn_comm_unique_id", "fyn_comm_init", "fyn_comm_destroy", "fyn_comm_info", "fyn_allgather_logits", "fyn_comm_register_tensor", "fyn_halo_exchange",
 ]
 
 _lib = None
@@ -218,6 +220,19 @@ class Context:
         arr = np.frombuffer(buf, dtype=np.float32)
         self._pinned = getattr(self, "_pinned", []) + [(p, buf)]
         return arr
+
+    def device_alloc(self, nbytes: int) -> int:
+        """Raw device memory (fyn_device_alloc); returns the device pointer as an integer."""
+        p = C.c_void_p()
+        check(lib().fyn_device_alloc(self._h, C.c_size_t(int(nbytes)), C.byref(p)))
+        return p.value
+
+    def device_free(self, ptr: int):
+        check(lib().fyn_device_free(self._h, C.c_void_p(int(ptr))))
+
+    def memcpy_d2h(self, host: np.ndarray, device_ptr: int, stream=None):
+        """Asynchronous device -> host copy into a (pinned) numpy array."""
+        check(lib().fyn_memcpy_async(self._h, host.ctypes.data_as(C.c_void_p), C.c_void_p(int(device_ptr)), C.c_size_t(host.nbytes), 1, _s(stream)))
 
     def tensor(self, width, height, channels, padding=0, order=ORDER_SHALLOW, dtype=F16, batch=1, packing=0):
         return Tensor(self, TensorDesc(width, height, channels, padding, order, dtype, batch, packing))
@@ -494,3 +509,47 @@ class Relayout(_Op):
 
     def run(self, x, out, stream=None):
         check(lib().fyn_relayout_run(self._h, x._h, out._h, _s(stream)))
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """Rank 0: the 128-byte bootstrap id (an ncclUniqueId) every rank passes to Comm()."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    check(lib().fyn_comm_unique_id(buf))
+    return buf.raw
+
+
+class Comm:
+    """fyn_comm: NCCL communicator + CUDA-IPC peer mappings of one process-per-GPU job (include/fyusenet_b200.h, multi-GPU)."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, unique_id: bytes | None):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._h = C.c_void_p()
+        idbuf = C.create_string_buffer(unique_id, COMM_ID_BYTES) if unique_id is not None else None
+        check(lib().fyn_comm_init(ctx._h, int(rank), int(world), idbuf, C.byref(self._h)))
+
+    def info(self):
+        r, w, v, b = C.c_int(), C.c_int(), C.c_int(), C.c_uint64()
+        check(lib().fyn_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v), C.byref(b)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value, "halo_bytes_pushed": b.value}
+
+    def allgather_logits(self, logits_tensor, images_per_rank: int, device_out: int, stream=None):
+        """logits_tensor: fyn_tensor* (Tensor or integer handle); device_out: device pointer to float32 [world][images_per_rank][C]."""
+        h = logits_tensor._h if isinstance(logits_tensor, Tensor) else C.c_void_p(int(logits_tensor))
+        check(lib().fyn_allgather_logits(self._h, h, int(images_per_rank), C.c_void_p(int(device_out)), _s(stream)))
+
+    def register_tensor(self, tensor) -> int:
+        h = tensor._h if isinstance(tensor, Tensor) else C.c_void_p(int(tensor))
+        slot = C.c_int()
+        check(lib().fyn_comm_register_tensor(self._h, h, C.byref(slot)))
+        return slot.value
+
+    def halo_exchange(self, slot: int, rows: int, stream=None):
+        check(lib().fyn_halo_exchange(self._h, int(slot), int(rows), _s(stream)))
+
+    def destroy(self):
+        if self._h:
+            check(lib().fyn_comm_destroy(self._h))
+            self._h = C.c_void_p()

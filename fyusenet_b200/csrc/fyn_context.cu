@@ -155,6 +155,38 @@ int fyn_stream_add_callback(fyn_ctx *ctx, void *stream, fyn_host_fn fn, void *us
     return FYN_OK;
 }
 
+int fyn_graph_begin_capture(fyn_ctx *ctx, void *stream) {
+    if (!ctx) FYN_FAIL(FYN_ERR_INVALID, "ctx is NULL");
+    FYN_CUDA(cudaSetDevice(ctx->device));
+    FYN_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+    return FYN_OK;
+}
+
+int fyn_graph_end_capture(fyn_ctx *ctx, void *stream, void **graph_exec) {
+    if (!ctx || !graph_exec) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
+    *graph_exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    FYN_CUDA(cudaStreamEndCapture((cudaStream_t)stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) FYN_FAIL(FYN_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    *graph_exec = (void *)exec;
+    return FYN_OK;
+}
+
+int fyn_graph_launch(fyn_ctx *ctx, void *graph_exec, void *stream) {
+    if (!ctx || !graph_exec) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
+    FYN_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+    return FYN_OK;
+}
+
+int fyn_graph_destroy(fyn_ctx *ctx, void *graph_exec) {
+    if (!ctx) FYN_FAIL(FYN_ERR_INVALID, "ctx is NULL");
+    if (graph_exec) FYN_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    return FYN_OK;
+}
+
 int fyn_device_alloc(fyn_ctx *ctx, size_t bytes, void **ptr) {
     if (!ctx || !ptr) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
     FYN_CUDA(cudaSetDevice(ctx->device));

@@ -75,6 +75,10 @@ int fyn_conv2d_load_weights(fyn_op *op, const float *wb) {
     if (!op || op->kind != FYN_OP_CONV || !wb) FYN_FAIL(FYN_ERR_INVALID, "bad conv op / weights");
     const fyn_conv_desc &d = op->conv;
     FYN_CUDA(cudaSetDevice(op->ctx->device));
+    // Hot swap (weights reloaded after set-up): the images below are overwritten in place with blocking copies on the legacy
+    // stream, which is NOT ordered against the engine's non-blocking streams -- wait until every forward pass that may
+    // still read the old images has left the device (the reference serialises the swap on the GL command stream).
+    if (op->d_w) FYN_CUDA(cudaDeviceSynchronize());
     const int Ci = d.in_channels, Co = d.out_channels, K = d.kernel;
     const int nIn = (Ci + 3) / 4, nOut = (Co + 3) / 4;
     const bool deep = (d.flags & FYN_FLAG_DEEP) != 0;
@@ -159,6 +163,7 @@ int fyn_conv2d_set_input_norm(fyn_op *op, const float *sb) {
     }
     const fyn_conv_desc &d = op->conv;
     // padding texels of the stand-alone layer's output are zero, not bn(0): only kernels that never read padding qualify
+    if (op->epilogue != FYN_EPILOGUE_NONE) FYN_FAIL(FYN_ERR_UNSUPPORTED, "conv: input batch-norm fusion and a fused epilogue function exclude each other");
     if (!op->dtc || d.kernel != 1 || d.in_channels % 64 != 0 || (d.flags & FYN_FLAG_PRE_CLIP))
         FYN_FAIL(FYN_ERR_UNSUPPORTED, "conv: input batch-norm fusion needs a 1x1 layer of the deep-tiled tcgen05 family");
     const int C = d.in_channels;
@@ -168,6 +173,7 @@ int fyn_conv2d_set_input_norm(fyn_op *op, const float *sb) {
         h[(size_t)C + c] = sb[(size_t)C + c];
     }
     FYN_CUDA(cudaSetDevice(op->ctx->device));
+    if (op->d_innorm) FYN_CUDA(cudaDeviceSynchronize());   // parameters of a live op: see fyn_conv2d_load_weights
     if (!op->d_innorm) FYN_CUDA(cudaMalloc((void **)&op->d_innorm, h.size() * sizeof(float)));
     FYN_CUDA(cudaMemcpy(op->d_innorm, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
     op->innorm = 1;
@@ -177,6 +183,10 @@ int fyn_conv2d_set_input_norm(fyn_op *op, const float *sb) {
 int fyn_conv2d_set_epilogue(fyn_op *op, int function) {
     if (!op || op->kind != FYN_OP_CONV) FYN_FAIL(FYN_ERR_INVALID, "not a convolution op");
     if (function != FYN_EPILOGUE_NONE && function != FYN_EPILOGUE_SIGMOID) FYN_FAIL(FYN_ERR_INVALID, "conv: unknown epilogue function %d", function);
+    // the deep-tiled tcgen05 family has no fused function: fusing would silently drop the layer to the CUDA-core kernel
+    // (and collide with a fused input batch-norm, which only that family implements)
+    if (function != FYN_EPILOGUE_NONE && (op->dtc || op->innorm))
+        FYN_FAIL(FYN_ERR_UNSUPPORTED, "conv: no fused epilogue function in the deep-tiled tcgen05 family");
     op->epilogue = function;
     return FYN_OK;
 }

@@ -25,6 +25,8 @@
 #include <cstring>
 #include <vector>
 
+#include <mutex>
+
 #include "fyn_internal.h"
 
 namespace {
@@ -441,6 +443,8 @@ int fyn_conv_deep_tc_create(fyn_op *op, const float *wb) {
     plan->smemBytes = (size_t)a.ring * kAStageBytes + (size_t)a.ring * a.NT * kKC * 2 + ((size_t)a.nInPlanes + 2 * (a.NT / 4) + 64) * 4 + 8 + (2 * kMaxRing + 1) * 8 + 16;
     plan->wideSmemBytes = plan->smemBytes + (size_t)a.ring * (256 - a.NT) * kKC * 2 + 2 * ((256 - a.NT) / 4) * 4;
     static size_t maxSmem[64] = {0};
+    static std::mutex smemLock;                  // ops may be created from one thread per context
+    std::lock_guard<std::mutex> guard(smemLock);
     size_t &cur = maxSmem[op->ctx->device & 63];
     if (plan->wideOff && plan->wideSmemBytes > cur) {
         FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->wideSmemBytes));

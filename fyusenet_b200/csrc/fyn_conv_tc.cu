@@ -43,6 +43,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -1067,6 +1068,8 @@ TcKernel tc_kernel(int mode, int act, int res, int epi) {
 // footprint any plan has needed so far
 int tc_ensure_smem(TcKernel fn, int mode, int act, int res, int epi, int device, size_t bytes) {
     static size_t cur[64][2][3][4] = {};
+    static std::mutex lock;                      // ops may be created / run from one thread per context
+    std::lock_guard<std::mutex> guard(lock);
     size_t &c = cur[device & 63][mode][act][epi ? 3 : res];
     if (bytes > c) {
         FYN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));

@@ -399,6 +399,7 @@ int fyn_batchnorm_load(fyn_op *op, const float *sb) {
         h[(size_t)tiles * 4 + c] = sb[C + c];  // bias block
     }
     FYN_CUDA(cudaSetDevice(op->ctx->device));
+    if (op->d_bias) FYN_CUDA(cudaDeviceSynchronize());   // reload of a live op: not ordered against the engine's streams otherwise
     if (!op->d_bias) FYN_CUDA(cudaMalloc((void **)&op->d_bias, h.size() * sizeof(float)));
     FYN_CUDA(cudaMemcpy(op->d_bias, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
     return FYN_OK;

@@ -370,6 +370,43 @@ int fynhost_net_layer_timing(void *handle, int layerNumber, float *deviceMs, uns
     });
 }
 
+// CUDA-graph replay of the device layers of the synchronous path (Engine::enableGraph)
+int fynhost_net_enable_graph(void *handle, int on) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] { h->net()->engine()->enableGraph(on != 0); });
+}
+
+int fynhost_net_graph_active(void *handle) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    int v = 0;
+    guarded([&] { v = h->net()->engine()->graphActive() ? 1 : 0; });
+    return v;
+}
+
+// device-resident operation of a network with upload / download layers: both are skipped (Engine::skipIO)
+int fynhost_net_skip_io(void *handle, int on) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] { h->net()->engine()->skipIO(on != 0); });
+}
+
+// output tensor of a layer (device-side consumers: fyn_allgather_logits on ResNet-50's GEMM72 output)
+fyn_tensor *fynhost_net_layer_tensor(void *handle, int layerNumber) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    fyn_tensor *t = nullptr;
+    guarded([&] {
+        auto *g = dynamic_cast<gpu::GPULayerBase *>(h->net()->engine()->getLayers()[layerNumber]);
+        if (!g || !g->hasOutputTexture(0)) THROW_EXCEPTION_ARGS(FynException, "Layer %d has no device output", layerNumber);
+        t = g->getOutputTexture(0);
+    });
+    return t;
+}
+
+// row-banded operation over several GPUs: margin rows refreshed from the band neighbours after every layer (Engine::setHaloExchange)
+int fynhost_net_set_halo_exchange(void *handle, fyn_comm *comm, int marginRows, int inputHeight) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] { h->net()->engine()->setHaloExchange(comm, marginRows, inputHeight); });
+}
+
 size_t fynhost_net_device_bytes(void *handle) {
     NetHandle *h = static_cast<NetHandle *>(handle);
     return h->net()->bufferManager() ? h->net()->bufferManager()->estimateTextureMemory() : 0;

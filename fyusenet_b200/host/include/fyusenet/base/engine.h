@@ -20,13 +20,18 @@ namespace fyusion {
 namespace fyusenet {
 
 class NeuralNetwork;
+namespace gpu {
+class UploadLayer;
+class DownloadLayer;
+}
 
 class Engine : public GfxContextTracker {
  public:
     enum execstate { EXEC_DONE = 0, EXEC_DEFERRED, EXEC_STOPPED, EXEC_ERROR };
     constexpr static int ASYNC_SLOTS = 3;       // buffers per pipeline interface == max sequences in flight
     constexpr static int MAX_IN_FLIGHT = ASYNC_SLOTS;
-    struct Completion { Engine *engine; uint64_t sequence; cpu::CPUBuffer *buffer; };
+    struct Completion { Engine *engine; uint64_t sequence; cpu::CPUBuffer *buffer; gpu::DownloadLayer *download; };
+    struct UploadNote { gpu::UploadLayer *layer; uint64_t sequence; };
 
     explicit Engine(const GfxContextLink &ctx = GfxContextLink(), bool async = false);
     ~Engine();
@@ -55,8 +60,19 @@ class Engine : public GfxContextTracker {
     // results are written, so that every layer's dump shows that layer's own output.
     void enableFusion(bool on) { fusion_ = on; updateFusion(); }
     int fusedLayers() const { return fusedLayers_; }
-    // capture the layer sequence into a CUDA graph on the next forward and replay it afterwards
-    void enableGraph(bool on) { useGraph_ = on; }
+    // Synchronous path: capture the device layers (everything between the upload and the download layer) into a CUDA graph on
+    // the next forward and replay it afterwards; re-captured when tensor bindings, weights or fusions change.  Suspended
+    // while timings, dumps or a halo exchange are active.
+    void enableGraph(bool on) { useGraph_ = on; dropGraph(); }
+    bool graphActive() const { return graphExec_ != nullptr; }
+    // Device-resident operation of a network WITH upload / download layers: both are skipped, the upload tensor keeps the
+    // data of the last real upload and the result stays in the last layer's output tensor (bench.py's `value` arm).
+    void skipIO(bool on) { skipIO_ = on; }
+    // Row-banded operation over several GPUs (BASELINE configs[4]): this rank's network runs on its band plus
+    // `marginRows` full-resolution rows towards each neighbour; after every layer whose output feeds a layer with spatial
+    // taps the margin rows of the output tensor are replaced by the neighbours' band-edge rows (fyn_halo_exchange: peer
+    // stores over NVLink).  Registers the output tensors with the communicator: a collective, same order on every rank.
+    void setHaloExchange(fyn_comm *comm, int marginRows, int inputHeight);
     // asynchronous operation: callbacks fired from a driver thread when a sequence's download has landed
     using DownloadCallback = std::function<void(uint64_t sequence, cpu::CPUBuffer *buffer)>;
     void setDownloadCallback(const DownloadCallback &cb) { downloadCallback_ = cb; }
@@ -78,6 +94,7 @@ class Engine : public GfxContextTracker {
     void dumpTrace();
     bool slotUsed_[ASYNC_SLOTS] = {};
     Completion completions_[ASYNC_SLOTS];
+    UploadNote uploadNotes_[ASYNC_SLOTS];
     std::mutex flightLock_;
     std::condition_variable flightCv_;
     int inFlight_ = 0;
@@ -97,6 +114,15 @@ class Engine : public GfxContextTracker {
     int fusedLayers_ = 0;
     void updateFusion();
     bool useGraph_ = false;
+    void *graphExec_ = nullptr;
+    uint64_t graphEpoch_ = 0;
+    bool graphWarm_ = false;                           // one eager forward has run at the current epoch
+    void dropGraph();
+    bool skipIO_ = false;
+    fyn_comm *haloComm_ = nullptr;
+    int haloMargin_ = 0, haloInputHeight_ = 0;
+    struct HaloStep { int slot; int rows; };
+    std::unordered_map<int, HaloStep> haloSteps_;      // layer number -> exchange issued after that layer
     std::string outputDir_;
     std::unordered_map<int, uint32_t> timingData_;
     std::unordered_map<int, float> deviceTimingData_;

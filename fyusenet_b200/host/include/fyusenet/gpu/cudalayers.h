@@ -261,9 +261,15 @@ class UploadLayer : public GPULayerBase, public cpu::CPULayerInterface {
     // asynchronous path (reference: gpu/uploadlayer.cpp:395-541): copy the current input buffer into output buffer
     // `slot` on `stream`; returns the tensor that now carries the sequence
     TensorHandle asyncUpload(uint64_t sequence, int slot, void *stream);
+    // Fires UPLOAD_COMMENCED ("input buffer may be changed") and UPLOAD_DONE once the host->device copy of `sequence` has
+    // completed; the asynchronous engine calls it from a host function queued behind the copy (reference contract:
+    // gpu/uploadlayer.cpp:395-541, AsyncLayer::state)
+    void notifyUploaded(uint64_t sequence);
+    bool hasCallback() const { return (bool)callback_; }
 
  protected:
     CPUBuffer *input_ = nullptr;
+    CPUBuffer *pendingInput_ = nullptr;     // buffer of the most recent asynchronous upload (callback argument)
     bool async_ = false;
     BufferSpec::dtype dataType_ = BufferSpec::FLOAT32;
     UpDownLayerBuilder::callback_t callback_;
@@ -280,6 +286,8 @@ class DownloadLayer : public GPULayerBase, public cpu::CPULayerInterface {
     CPUBuffer *getInputBuffer(int = 0) const override { return nullptr; }
     void addOutputBuffer(CPUBuffer *buf, int = 0) override { output_ = buf; }
     void updateOutputBuffer(CPUBuffer *buf, int = 0) { output_ = buf; }
+    // DOWNLOAD_DONE of the asynchronous path, fired by the engine's completion function once the copy has landed
+    void notifyDownloaded(uint64_t sequence, CPUBuffer *buf) { if (callback_) callback_(sequence, buf, AsyncLayer::DOWNLOAD_DONE); }
     CPUBuffer *getOutputBuffer(int = 0) const override { return output_; }
     bool hasOutputBuffer(int = 0) const override { return output_ != nullptr; }
     void clearOutputBuffers(int = -1) override { output_ = nullptr; }

@@ -4,6 +4,7 @@
 // gpulayerbase.cpp:443-564 (writeResult / copyResult).  A "texture" here is a device tensor of the C ABI that
 // holds ALL channel planes of a port, so the per-plane channelIndex of the reference collapses to 0.
 #pragma once
+#include <atomic>
 #include <cstdio>
 #include <mutex>
 #include <vector>
@@ -23,6 +24,13 @@ using TensorHandle = fyn_tensor *;
 BufferSpec::dtype storagePrecision();
 void setStoragePrecision(BufferSpec::dtype dt);
 
+// Bumped whenever something a captured CUDA graph may have baked in changes (tensor bindings, weight images, fusions):
+// the engine re-captures when its graph is older than this (Engine::enableGraph).
+inline std::atomic<uint64_t> &graphEpoch() {
+    static std::atomic<uint64_t> epoch{1};
+    return epoch;
+}
+
 class GPULayerBase : public LayerBase, public GfxContextTracker {
  public:
     template <typename B>
@@ -41,13 +49,18 @@ class GPULayerBase : public LayerBase, public GfxContextTracker {
         valid_ = false;
     }
 
-    virtual void addInputTexture(TensorHandle t, int port) { put(inputs_, port, t); }
-    virtual void addResidualTexture(TensorHandle t, int index = 0) { put(residuals_, index, t); }
+    virtual void addInputTexture(TensorHandle t, int port) { put(inputs_, port, t); graphEpoch()++; }
+    virtual void addResidualTexture(TensorHandle t, int index = 0) { put(residuals_, index, t); graphEpoch()++; }
     virtual void addOutputTexture(TensorHandle t, int index = 0, int shadowIndex = 0) {
         if (shadowIndex == 0) put(outputs_, index, t);
         else put(shadowOutputs_, shadowIndex - 1, t);
+        graphEpoch()++;
     }
-    virtual void updateInputTexture(TensorHandle t, int port) { put(inputs_, port, t); }
+    virtual void updateInputTexture(TensorHandle t, int port) {
+        if (port < (int)inputs_.size() && inputs_[port] == t) return;
+        put(inputs_, port, t);
+        graphEpoch()++;
+    }
     virtual bool hasInputTexture(int port = 0) const { return port < (int)inputs_.size() && inputs_[port]; }
     virtual bool hasOutputTexture(int index = 0) const { return index < (int)outputs_.size() && outputs_[index]; }
     virtual TensorHandle getOutputTexture(int index = 0) const { return hasOutputTexture(index) ? outputs_[index] : nullptr; }

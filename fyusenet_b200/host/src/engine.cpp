@@ -39,7 +39,8 @@ void Engine::updateFusion() {
         if (!sig) continue;
         conv->unfuse();
         sig->setBypass(false);
-        if (want && sig->plainFunction() && sig->hasOutputTexture(0) && conv->fuseFunction(FYN_EPILOGUE_SIGMOID, sig->getOutputTexture(0))) {
+        // (consecutive layer numbers: no layer in between can still read the pooled tensor the sigmoid layer writes)
+        if (want && sig->getNumber() == conv->getNumber() + 1 && sig->plainFunction() && sig->hasOutputTexture(0) && conv->fuseFunction(FYN_EPILOGUE_SIGMOID, sig->getOutputTexture(0))) {
             sig->setBypass(true);
             fusedLayers_++;
         }
@@ -63,7 +64,47 @@ void Engine::updateFusion() {
     }
 }
 
+void Engine::dropGraph() {
+    if (graphExec_) fyn_graph_destroy(context_.handle(), graphExec_);
+    graphExec_ = nullptr;
+}
+
+void Engine::setHaloExchange(fyn_comm *comm, int marginRows, int inputHeight) {
+    if (!setup_) THROW_EXCEPTION_ARGS(FynException, "setHaloExchange() needs a network that has been set up");
+    dropGraph();
+    haloSteps_.clear();
+    haloComm_ = comm;
+    haloMargin_ = marginRows;
+    haloInputHeight_ = inputHeight;
+    if (!comm) return;
+    if (async_) THROW_EXCEPTION_ARGS(FynException, "Row-banded operation is synchronous");
+    if (marginRows <= 0 || marginRows % 4 || inputHeight <= 0)
+        THROW_EXCEPTION_ARGS(FynException, "Halo margin must be a positive multiple of 4 full-resolution rows (got %d)", marginRows);
+    for (auto it = layers_.begin(); it != layers_.end(); ++it) {
+        auto *g = dynamic_cast<gpu::GPULayerBase *>(it.second);
+        if (!g || dynamic_cast<gpu::UploadLayer *>(g) || dynamic_cast<gpu::DownloadLayer *>(g) || !g->hasOutputTexture(0)) continue;
+        // only outputs that a layer with spatial taps reads need their margins refreshed
+        bool spatial = false;
+        for (auto &rcv : g->receivers())
+            if (!dynamic_cast<gpu::SigmoidLayer *>(rcv.first) && !dynamic_cast<gpu::DownloadLayer *>(rcv.first)) spatial = true;
+        if (auto *conv = dynamic_cast<gpu::ConvLayerBase *>(g))
+            if (conv->fused()) spatial = false;              // conv + function: the pair's consumer decides (handled at the function layer)
+        if (!spatial) continue;
+        fyn_tensor_desc d{};
+        FYN_ABI_CALL(fyn_tensor_get_desc(g->getOutputTexture(0), &d, nullptr));
+        if (d.order != FYN_ORDER_SHALLOW) THROW_EXCEPTION_ARGS(FynException, "Layer %s: row bands need shallow tensors", g->getName().c_str());
+        // this tensor's resolution relative to the network input: margin rows scale with it
+        const long long num = (long long)marginRows * d.height;
+        if (num % inputHeight) THROW_EXCEPTION_ARGS(FynException, "Layer %s: margin %d does not map to whole rows at height %d / %d", g->getName().c_str(), marginRows, d.height, inputHeight);
+        HaloStep st{};
+        st.rows = (int)(num / inputHeight);
+        FYN_ABI_CALL(fyn_comm_register_tensor(comm, g->getOutputTexture(0), &st.slot));
+        haloSteps_[it.first] = st;
+    }
+}
+
 void Engine::cleanup() {
+    dropGraph();
     if (setup_) {
         if (async_) finish();
         FYN_ABI_CALL(fyn_stream_sync(context_.handle(), context_.stream()));
@@ -122,7 +163,13 @@ void Engine::sequenceCompleted(uint64_t sequence, cpu::CPUBuffer *buffer) {
 
 static void engineCompletionTrampoline(void *user) {
     auto *c = static_cast<Engine::Completion *>(user);
+    if (c->download) c->download->notifyDownloaded(c->sequence, c->buffer);
     c->engine->sequenceCompleted(c->sequence, c->buffer);
+}
+
+static void engineUploadTrampoline(void *user) {
+    auto *n = static_cast<Engine::UploadNote *>(user);
+    n->layer->notifyUploaded(n->sequence);
 }
 
 // Pipelined execution on three streams (upload / compute / download), double-buffered at both ends:
@@ -165,6 +212,12 @@ Engine::execstate Engine::executeAsync(uint64_t sequence) {
         gpu::TensorHandle t = upload->asyncUpload(sequence, slot, sU);
         FYN_ABI_CALL(fyn_event_record(ctx, uploadDone_[slot], sU));
         FYN_ABI_CALL(fyn_stream_wait_event(ctx, sC, uploadDone_[slot]));
+        if (upload->hasCallback()) {
+            // UPLOAD_COMMENCED / UPLOAD_DONE once the data has left the caller's buffer (host function behind the copy)
+            uploadNotes_[slot] = UploadNote{upload, sequence};
+            FYN_ABI_CALL(fyn_stream_wait_event(ctx, cc->notifyStream(), uploadDone_[slot]));
+            FYN_ABI_CALL(fyn_stream_add_callback(ctx, cc->notifyStream(), engineUploadTrampoline, &uploadNotes_[slot]));
+        }
         for (auto &rcv : upload->receivers())
             if (auto *g = dynamic_cast<gpu::GPULayerBase *>(rcv.first)) g->updateInputTexture(t, rcv.second);
     }
@@ -191,7 +244,7 @@ Engine::execstate Engine::executeAsync(uint64_t sequence) {
     mark(5, sD);
     if (traceOn) trace_.push_back(te);
     FYN_ABI_CALL(fyn_event_record(ctx, copyDone_[slot], sD));
-    completions_[slot] = Completion{this, sequence, buffer};
+    completions_[slot] = Completion{this, sequence, buffer, download};
     void *sN = cc->notifyStream();
     FYN_ABI_CALL(fyn_stream_wait_event(ctx, sN, copyDone_[slot]));
     FYN_ABI_CALL(fyn_stream_add_callback(ctx, sN, engineCompletionTrampoline, &completions_[slot]));
@@ -205,8 +258,43 @@ Engine::execstate Engine::executeAsync(uint64_t sequence) {
 // (collectTimings) once the stream has been synchronised, so enabling timings does not serialise the step.
 Engine::execstate Engine::execute(uint64_t sequence) {
     size_t slot = 0;
+    static const bool debugSyncOn = getenv("FYN_DEBUG_SYNC") != nullptr;
+    // CUDA-graph replay of the device layers (launch-latency-bound networks: ResNet-50 at batch 1 is 59 launches)
+    const bool graphOk = useGraph_ && !timings_ && !writeResults_ && !haloComm_ && !debugSyncOn;
+    const uint64_t epochNow = gpu::graphEpoch().load();
+    if (!graphOk || graphEpoch_ != epochNow) {
+        dropGraph();
+        graphWarm_ = false;
+        graphEpoch_ = epochNow;
+    }
+    // the first forward after a change runs eagerly (lazy per-kernel attribute set-up must not happen inside a capture), the
+    // second one is captured, later ones replay
+    const bool capturing = graphOk && !graphExec_ && graphWarm_;
+    bool inCapture = false;
+    auto isIO = [](LayerBase *l) { return dynamic_cast<gpu::UploadLayer *>(l) || dynamic_cast<gpu::DownloadLayer *>(l); };
+    bool replayed = false;
     for (auto it = layers_.begin(); it != layers_.end(); ++it) {
         LayerBase *layer = it.second;
+        const bool io = isIO(layer);
+        if (io && skipIO_) continue;
+        if (graphOk && !io) {
+            if (graphExec_) {
+                if (!replayed) {
+                    FYN_ABI_CALL(fyn_graph_launch(context_.handle(), graphExec_, context_.stream()));
+                    replayed = true;
+                }
+                continue;
+            }
+            if (capturing && !inCapture && !graphExec_) {
+                FYN_ABI_CALL(fyn_graph_begin_capture(context_.handle(), context_.stream()));
+                inCapture = true;
+            }
+        } else if (inCapture) {
+            // an I/O layer ends the captured run of device layers (the download synchronises the stream)
+            FYN_ABI_CALL(fyn_graph_end_capture(context_.handle(), context_.stream(), &graphExec_));
+            FYN_ABI_CALL(fyn_graph_launch(context_.handle(), graphExec_, context_.stream()));
+            inCapture = false;
+        }
         if (timings_ && (timingOnly_ < 0 || timingOnly_ == it.first)) {
             if (pendingEvents_.size() >= 4096) collectTimings(true);
             void *evA = nullptr, *evB = nullptr;
@@ -227,8 +315,12 @@ Engine::execstate Engine::execute(uint64_t sequence) {
         } else {
             layer->forward(sequence);
         }
+        if (haloComm_) {
+            auto hs = haloSteps_.find(it.first);
+            if (hs != haloSteps_.end()) FYN_ABI_CALL(fyn_halo_exchange(haloComm_, hs->second.slot, hs->second.rows, context_.stream()));
+        }
         // FYN_DEBUG_SYNC=1: synchronise after every layer and name it (finds the layer a device fault or hang belongs to)
-        static const bool debugSync = getenv("FYN_DEBUG_SYNC") != nullptr;
+        const bool debugSync = debugSyncOn;
         if (debugSync) {
             fprintf(stderr, "[fyn debug] seq %llu layer %s ...", (unsigned long long)sequence, layer->getName().c_str());
             fflush(stderr);
@@ -242,6 +334,11 @@ Engine::execstate Engine::execute(uint64_t sequence) {
         }
         slot++;
     }
+    if (inCapture) {
+        FYN_ABI_CALL(fyn_graph_end_capture(context_.handle(), context_.stream(), &graphExec_));
+        FYN_ABI_CALL(fyn_graph_launch(context_.handle(), graphExec_, context_.stream()));
+    }
+    if (graphOk && !graphExec_) graphWarm_ = true;
     if (timings_) runs_++;
     return EXEC_DONE;
 }

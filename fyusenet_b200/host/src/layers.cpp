@@ -111,7 +111,10 @@ void ConvLayerBase::loadWeightsAndBiases(const float *biasAndWeights, size_t off
     if (flags_ & LayerFlags::POST_BATCHNORM) n += 2 * (size_t)outputChannels_;
     const float *src = biasAndWeights + offset;
     if (op_) {
-        FYN_ABI_CALL(fyn_conv2d_load_weights(op_, src));  // hot swap (reference: stylenet9x9.cpp:87-95)
+        // hot swap (reference: stylenet9x9.cpp:87-95, serialised there by the GL command stream): the library waits for the
+        // device before it overwrites live weight images (fyn_conv2d_load_weights)
+        FYN_ABI_CALL(fyn_conv2d_load_weights(op_, src));
+        graphEpoch()++;
     } else {
         pendingWeights_.assign(src, src + n);              // weights are only read during the call
     }
@@ -153,7 +156,8 @@ bool ConvLayerBase::fuseFunction(int function, TensorHandle target) {
     FYN_ABI_CALL(fyn_tensor_get_desc(target, &theirs, nullptr));
     if (memcmp(&mine, &theirs, sizeof(mine)) != 0) return false;
     if (target == in(0) || (!residuals_.empty() && target == residuals_[0])) return false;
-    if (fyn_conv2d_set_epilogue(op_, function) != 0) return false;
+    if (fusedInput_) return false;                       // one fusion per convolution: the kernel families implement either
+    if (fyn_conv2d_set_epilogue(op_, function) != 0) return false;   // (fails for the deep-tiled tcgen05 family: no fused function there)
     fusedFunction_ = function;
     fusedTarget_ = target;
     return true;
@@ -166,7 +170,7 @@ bool ConvLayerBase::fuseInputNorm(const float *scaleAndBias, TensorHandle source
     FYN_ABI_CALL(fyn_tensor_get_desc(in(0), &mine, nullptr));
     FYN_ABI_CALL(fyn_tensor_get_desc(source, &theirs, nullptr));
     if (memcmp(&mine, &theirs, sizeof(mine)) != 0 || mine.dtype != FYN_F16) return false;
-    if (source == out() || source == fusedTarget_) return false;
+    if (source == out() || source == fusedTarget_ || fusedFunction_ != 0) return false;
     if (fyn_conv2d_set_input_norm(op_, scaleAndBias) != 0) return false;
     fusedInput_ = source;
     return true;
@@ -258,7 +262,10 @@ void BatchNormLayer::loadScaleAndBias(const float *scaleAndBias, size_t sbOffset
     std::lock_guard<std::recursive_mutex> lck(processingLock_);
     if (!scaleAndBias) THROW_EXCEPTION_ARGS(FynException, "Layer %s: null parameter pointer", name_.c_str());
     params_.assign(scaleAndBias + sbOffset, scaleAndBias + sbOffset + 2 * (size_t)outputChannels_);
-    if (op_) FYN_ABI_CALL(fyn_batchnorm_load(op_, params_.data()));
+    if (op_) {
+        FYN_ABI_CALL(fyn_batchnorm_load(op_, params_.data()));
+        graphEpoch()++;
+    }
     if (fusedConsumer_ && hasInputTexture(0) && !fusedConsumer_->fuseInputNorm(params_.data(), in(0))) {
         fusedConsumer_->unfuseInput();   // new parameters could not be handed over: run as a layer again
         fusedConsumer_ = nullptr;
@@ -360,7 +367,10 @@ void DepthwiseConvLayer::loadWeightsAndBiases(const float *biasAndWeights, size_
     size_t n = (size_t)outputChannels_ * 10;
     if (flags_ & LayerFlags::POST_BATCHNORM) n += 2 * (size_t)outputChannels_;
     const float *src = biasAndWeights + offset;
-    if (op_) FYN_ABI_CALL(fyn_dwconv3x3_load_weights(op_, src));
+    if (op_) {
+        FYN_ABI_CALL(fyn_dwconv3x3_load_weights(op_, src));
+        graphEpoch()++;
+    }
     else pendingWeights_.assign(src, src + n);
 }
 void DepthwiseConvLayer::setup() {
@@ -422,7 +432,10 @@ void TransConvLayer::loadWeightsAndBiases(const float *biasAndWeights, size_t of
     size_t n = (size_t)outputChannels_ + (size_t)desc_.kernel * desc_.kernel * inputChannels_ * outputChannels_;
     if (flags_ & LayerFlags::POST_BATCHNORM) n += 2 * (size_t)outputChannels_;
     const float *src = biasAndWeights + offset;
-    if (op_) FYN_ABI_CALL(fyn_transconv2d_load_weights(op_, src));
+    if (op_) {
+        FYN_ABI_CALL(fyn_transconv2d_load_weights(op_, src));
+        graphEpoch()++;
+    }
     else pendingWeights_.assign(src, src + n);
 }
 void TransConvLayer::setup() {
@@ -680,9 +693,18 @@ TensorHandle UploadLayer::asyncUpload(uint64_t sequence, int slot, void *stream)
     if (!target) THROW_EXCEPTION_ARGS(FynException, "Upload layer %s has no output buffer %d", name_.c_str(), slot);
     const float *src = input_->map<float>();
     input_->unmap();
-    if (callback_) callback_(sequence, input_, AsyncLayer::UPLOAD_COMMENCED);
+    // the copy reads the caller's pinned buffer asynchronously: UPLOAD_COMMENCED / UPLOAD_DONE are fired by
+    // notifyUploaded() once it has completed, never before (a caller may refill its buffer on UPLOAD_COMMENCED)
+    (void)sequence;
+    pendingInput_ = input_;
     FYN_ABI_CALL(fyn_upload_f32_async(target, src, stream));
     return target;
+}
+
+void UploadLayer::notifyUploaded(uint64_t sequence) {
+    if (!callback_) return;
+    callback_(sequence, pendingInput_, AsyncLayer::UPLOAD_COMMENCED);
+    callback_(sequence, pendingInput_, AsyncLayer::UPLOAD_DONE);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -43,6 +43,7 @@ def lib():
         L.fynhost_net_context.restype = C.c_void_p
         L.fynhost_net_stream.restype = C.c_void_p
         L.fynhost_net_device_bytes.restype = C.c_size_t
+        L.fynhost_net_layer_tensor.restype = C.c_void_p
         _lib = L
     return _lib
 
@@ -180,6 +181,30 @@ class Network:
         return ms.value, us.value
 
     @property
+    def enable_graph(self, on=True):
+        """Replay the device layers of the synchronous path from a CUDA graph (Engine::enableGraph)."""
+        _check(lib().fynhost_net_enable_graph(self._h, int(bool(on))))
+
+    @property
+    def graph_active(self) -> bool:
+        return bool(lib().fynhost_net_graph_active(self._h))
+
+    def skip_io(self, on=True):
+        """Skip the upload / download layers: the input of the last real upload stays resident in HBM, the result stays in
+        the last layer's tensor (device-resident timing of a network built with I/O layers)."""
+        _check(lib().fynhost_net_skip_io(self._h, int(bool(on))))
+
+    def layer_tensor(self, number: int) -> int:
+        """fyn_tensor* (as an integer) of a layer's output tensor."""
+        t = lib().fynhost_net_layer_tensor(self._h, int(number))
+        if not t:
+            raise HostError(lib().fynhost_last_error().decode(errors="replace"))
+        return t
+
+    def set_halo_exchange(self, comm, margin_rows: int, input_height: int):
+        """Row-banded operation: `comm` is a capi.Comm (or None to switch it off); collective."""
+        _check(lib().fynhost_net_set_halo_exchange(self._h, comm._h if comm is not None else None, int(margin_rows), int(input_height)))
+
     def device_bytes(self) -> int:
         return lib().fynhost_net_device_bytes(self._h)
 

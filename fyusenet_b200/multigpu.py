@@ -122,6 +122,51 @@ def stylenet_band_plan(height: int, world: int, ksize: int = 9, margin: int | No
     return plan
 
 
+# ------------------------------------------------------------------------------------------------
+# StyleNet row bands WITH the per-layer halo exchange over NVLink (fyn_halo_exchange, include/fyusenet_b200.h)
+# ------------------------------------------------------------------------------------------------
+
+HALO_MARGIN = 8     # full-resolution rows per band side: 8 / 4 / 2 rows at the /1, /2, /4 levels
+
+
+def stylenet_halo_margin(ksize: int = 9) -> int:
+    """Smallest margin (full-resolution rows, multiple of 4) that covers every layer's taps at that layer's own resolution
+    (stylenet_halo_plan): conv1 needs (k-1)/2 rows at /1, deconv3 up to 2 rows at /2, everything else 1 row at its level."""
+    need = 4
+    for _, div, above, below in stylenet_halo_plan(ksize):
+        need = max(need, div * max(above, below))
+    return ((need + 3) // 4) * 4
+
+
+def stylenet_halo_band_plan(height: int, world: int, margin: int = HALO_MARGIN):
+    """Per rank: (input row begin, input row end, first output row to keep, rows to keep).  Every rank runs the network on
+    its band plus `margin` rows towards each existing neighbour; after every layer the margin rows are replaced by the
+    neighbours' band-edge rows, so `margin` only has to cover ONE layer's taps (8 rows instead of the 60 of the
+    overlapped-band plan)."""
+    plan = []
+    for r, (b, e) in enumerate(band_rows(height, world)):
+        ib = b - (margin if r > 0 else 0)
+        ie = e + (margin if r < world - 1 else 0)
+        plan.append((ib, ie, b - ib, e - b))
+    return plan
+
+
+def make_comm(ctx, rank: int | None = None, world: int | None = None):
+    """capi.Comm for this process: rank 0 draws the NCCL unique id, torch.distributed (any backend) carries the 128 bytes."""
+    import torch.distributed as dist
+    from . import capi
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    uid = None
+    if world > 1:
+        box = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+    return capi.Comm(ctx, rank, world, uid)
+
+
 def bind_to_gpu_numa_node(device_index: int):
     """Pin the calling process to the CPUs that are local to GPU `device_index` (its PCIe root / NUMA node), so that the pinned
     upload / download buffers it allocates afterwards live in that node's memory.  With one process per GPU the end-to-end

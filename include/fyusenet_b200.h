@@ -109,6 +109,14 @@ int fyn_stream_wait_event(fyn_ctx *ctx, void *stream, void *event);
 typedef void (*fyn_host_fn)(void *user);
 int fyn_stream_add_callback(fyn_ctx *ctx, void *stream, fyn_host_fn fn, void *user);
 
+/* CUDA-graph capture / replay of a fixed launch sequence (static networks at small batch are launch-latency bound: ResNet-50
+ * batch 1 is 59 kernels; the reference pays the same price per GL draw call, README.md:293-295).  Everything the library
+ * enqueues on `stream` between begin and end becomes one graph; programmatic dependent launches are kept as such. */
+int fyn_graph_begin_capture(fyn_ctx *ctx, void *stream);
+int fyn_graph_end_capture(fyn_ctx *ctx, void *stream, void **graph_exec);
+int fyn_graph_launch(fyn_ctx *ctx, void *graph_exec, void *stream);
+int fyn_graph_destroy(fyn_ctx *ctx, void *graph_exec);
+
 /* pinned host memory (replaces PBOPool / ManagedPBO, fyusenet/gl/pbopool.cpp) */
 int fyn_host_alloc(fyn_ctx *ctx, size_t bytes, void **ptr);
 int fyn_host_free(fyn_ctx *ctx, void *ptr);
@@ -413,6 +421,44 @@ int fyn_relayout_create(fyn_ctx *ctx, const fyn_unary_desc *desc, fyn_op **op);
 int fyn_relayout_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream);
 
 int fyn_op_destroy(fyn_op *op);
+
+/* ----------------------------------------------------------------------------------------- */
+/* multi-GPU: one process per GPU.  The reference is a single-GPU, batch-1  */
+/* engine (README.md:72); these entry points serve the two workloads that shard naturally.      */
+/* ----------------------------------------------------------------------------------------- */
+typedef struct fyn_comm fyn_comm;
+#define FYN_COMM_ID_BYTES 128
+
+/* Bootstrap: rank 0 creates the id (an ncclUniqueId), the caller hands the 128 bytes to every rank over any channel it has
+ * (torch.distributed, MPI, a file), every rank then calls fyn_comm_init -- a collective.  world == 1 needs no id and no NCCL.
+ * NCCL is loaded with dlopen("libnccl.so.2") (inside a torch process: the copy torch already loaded).  The communicator also
+ * exchanges the CUDA IPC handles of the flag blocks the halo exchange hand-shakes through. */
+int fyn_comm_unique_id(void *id128);
+int fyn_comm_init(fyn_ctx *ctx, int rank, int world, const void *id128, fyn_comm **comm);
+int fyn_comm_destroy(fyn_comm *comm);
+int fyn_comm_info(const fyn_comm *comm, int *rank, int *world, int *nccl_version, uint64_t *halo_bytes_pushed);
+
+/* Batch-sharded ResNet-50 (BASELINE configs[3]): every rank holds the logits of its image shard in the DeepGEMMLayer's output
+ * tensor (deep layout, 1x1 spatial, C channels, batch = local images; fyusenet/gpu/deep/deepgemmlayer.cpp:66-140).  Converts
+ * them to float32 [images_per_rank][C] (rows beyond the local batch are zero: shards may differ by one image) and all-gathers
+ * over NCCL into `device_out` = float32 [world][images_per_rank][C] in DEVICE memory, on `stream`.  What DeepDownloadLayer +
+ * CPUBuffer::toChannelWise deliver for one image (deepdownloadlayer.cpp:136-160, cpu/cpubuffer.cpp:131-142), for the job. */
+int fyn_allgather_logits(fyn_comm *comm, const fyn_tensor *logits, int images_per_rank, float *device_out, void *stream);
+
+/* Row-banded StyleNet (BASELINE configs[4]): rank r holds rows [b_r - m, e_r + m) of every layer's tensor -- its band plus a
+ * margin of m rows towards each existing neighbour (none at the true image border, where the reference's clamp-to-edge
+ * applies).  A layer computes its band rows exactly as long as its taps stay inside band + margin (tap geometry:
+ * fyusenet/gpu/vanilla/convlayerbase_vanilla.cpp:347-371, fractionalconvlayerNxN_vanilla.cpp:43-51); its margin rows are then
+ * REPLACED by the neighbours' band-edge rows.
+ *   fyn_comm_register_tensor  collective, set-up time: publishes the tensor's CUDA IPC handle and maps the tensors the ranks
+ *                             r-1 / r+1 registered in the same call (same order on all ranks).  Shallow RGBA tensors
+ *                             allocated by this library only.  Returns the slot to pass to fyn_halo_exchange.
+ *   fyn_halo_exchange         enqueues ONE kernel on `stream`: pushes the first / last `rows` band rows of the tensor into the
+ *                             neighbours' margins with peer stores over NVLink (no NCCL, no host copy), hand-shaking through
+ *                             flag words in peer memory; when the kernel ends this rank's margins hold the neighbours' rows.
+ *                             Every rank must issue the same sequence of exchanges. */
+int fyn_comm_register_tensor(fyn_comm *comm, fyn_tensor *tensor, int *slot);
+int fyn_halo_exchange(fyn_comm *comm, int slot, int rows, void *stream);
 
 #ifdef __cplusplus
 }

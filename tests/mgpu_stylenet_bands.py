@@ -4,8 +4,10 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 \
         tests/mgpu_stylenet_bands.py --width 4096 --height 4096 --steps 5
 
-Overlapped bands (fyusenet_b200.multigpu.stylenet_band_plan): rank r uploads its band plus 60 rows of context per side
+Default: overlapped bands (fyusenet_b200.multigpu.stylenet_band_plan): rank r uploads its band plus 60 rows of context per side
 from the host frame, runs the whole network on it and keeps its own rows; nothing crosses GPUs on the data path.
+--halo: per-layer halo exchange over NVLink (multigpu.stylenet_halo_band_plan + Engine::setHaloExchange -> fyn_halo_exchange):
+8-row margins that the neighbours refresh with peer stores after every layer.
 Rank 0 gathers the bands' checksums (NCCL all_gather) and, with --verify, compares its band with the rows of a
 whole-frame run on its own GPU (bit-exact).  Throughput = frames / max-over-ranks device time.
 """
@@ -28,23 +30,31 @@ def main():
     ap.add_argument("--height", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--verify", action="store_true")
+    ap.add_argument("--halo", action="store_true", help="per-layer NVLink halo exchange instead of recomputed context rows")
+    ap.add_argument("--kernel", type=int, default=9)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
 
-    from fyusenet_b200 import hostapi, multigpu, synthetic
+    from fyusenet_b200 import capi, hostapi, multigpu, synthetic
 
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    weights = synthetic.stylenet_weights(9)
+    K = args.kernel
+    weights = synthetic.stylenet_weights(K)
     img = synthetic.image(args.height, args.width, 7)
-    ib, ie, skip, keep = multigpu.stylenet_band_plan(args.height, world)[rank]
-    net = hostapi.StyleNet(9, args.width, ie - ib, device=local)
+    plan = multigpu.stylenet_halo_band_plan(args.height, world) if args.halo else multigpu.stylenet_band_plan(args.height, world, K)
+    ib, ie, skip, keep = plan[rank]
+    net = hostapi.StyleNet(K, args.width, ie - ib, device=local)
     net.load_weights(weights)
     net.setup()
+    comm = None
+    if args.halo:
+        comm = multigpu.make_comm(capi.Context(local), rank, world)
+        net.set_halo_exchange(comm, multigpu.HALO_MARGIN, ie - ib)
     net.set_input(img[ib:ie])
     net.forward()
     band = net.output_rgba()[0][skip:skip + keep].copy()
@@ -56,7 +66,10 @@ def main():
         net.forward()                                    # upload of the band + layers + download, synchronous API
     torch.cuda.synchronize()
     ms = multigpu.max_over_ranks((time.perf_counter() - t0) * 1e3, device=dev)
+    pushed = comm.info()["halo_bytes_pushed"] // (args.steps + 1) if comm is not None else 0
     net.destroy()
+    if comm is not None:
+        comm.destroy()
     sums = torch.tensor([float(band[..., :3].astype(np.float64).sum())], dtype=torch.float64, device=dev)
     parts = [torch.zeros_like(sums) for _ in range(world)]
     if world > 1:
@@ -65,7 +78,7 @@ def main():
         parts = [sums]
     exact = None
     if args.verify:
-        whole = hostapi.StyleNet(9, args.width, args.height, device=local)
+        whole = hostapi.StyleNet(K, args.width, args.height, device=local)
         whole.load_weights(weights)
         whole.setup()
         whole.set_input(img)
@@ -78,8 +91,10 @@ def main():
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         exact = bool(flag.item())
     if rank == 0:
-        print(json.dumps({"workload": f"StyleNet 9x9 {args.width}x{args.height}, {world} overlapped row bands", "n_gpus": world,
-                          "frames_per_s": args.steps / (ms / 1e3), "ms_per_frame": ms / args.steps, "band_rows": keep, "context_rows": multigpu.stylenet_margin(9),
+        mode = "row bands with per-layer NVLink halo exchange" if args.halo else "overlapped row bands"
+        print(json.dumps({"workload": f"StyleNet {K}x{K} {args.width}x{args.height}, {world} {mode}", "n_gpus": world,
+                          "frames_per_s": args.steps / (ms / 1e3), "ms_per_frame": ms / args.steps, "band_rows": keep,
+                          "context_rows": multigpu.HALO_MARGIN if args.halo else multigpu.stylenet_margin(K), "nvlink_bytes_pushed_per_frame_rank0": int(pushed),
                           "rgb_checksum": float(sum(p.item() for p in parts)), "bit_exact_vs_whole_frame": exact}))
     if world > 1:
         dist.destroy_process_group()

@@ -327,3 +327,210 @@ def test_resnet50_batchnorm_fusion_is_exact():
     ref = fo.resnet50_forward(weights, imgs[0], prec=fo.FP16_STORE)
     assert rel_l2(out[True][0], ref) <= 5e-3
     assert set(np.argsort(-out[True][0])[:5]) == set(np.argsort(-ref)[:5])
+
+
+# ------------------------------------------------------------------------------------------------
+# Parity at the benchmarked sizes
+# ------------------------------------------------------------------------------------------------
+def _psnr8(a, b):
+    a8, b8 = (a * 255).astype(np.uint8).astype(np.float64), (b * 255).astype(np.uint8).astype(np.float64)
+    mse = float(((a8 - b8) ** 2).mean())
+    return 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+def test_stylenet9x9_headline_frame_matches_oracle(tmp_path):
+    """BASELINE configs[1], the benchmarked shape: StyleNet 9x9 on one 1524x1856 frame through the host engine, fp16 storage,
+    every layer (rel-L2 / max-abs) and the final RGB against the CPU oracle run on the whole frame -- FP16_STORE (the exact
+    storage model of this backend), FP32 (SURVEY 8d's parity metric) and FP16_BLEND (the reference's default arithmetic: one
+    fp16 rounding per blend pass, README.md:61-67).  Measured distances are recorded in DESIGN.md section 5."""
+    w, h, k = 1524, 1856, 9
+    weights = fo.stylenet_synthetic_weights(k)
+    img = fo.synthetic_image(h, w, 0)
+    net = hostapi.StyleNet(k, w, h)
+    net.load_weights(weights)
+    net.setup()
+    net.set_input(img)
+    net.enable_dumps(tmp_path)
+    net.forward()
+    got = net.output_rgba()[0].copy()
+    layers = {l["name"]: l for l in net.layers()}
+    dump = {}
+    ref = fo.stylenet_forward(weights, img, k, prec=fo.FP16_STORE, dump=dump)
+    report = []
+    for name in _style_layer_names(k):
+        l = layers[name]
+        y = _read_dump(tmp_path, name, 1, (l["channels"], l["height"], l["width"]))
+        r = dump[name]
+        e2, emax = rel_l2(y, r), float(np.abs(y - r).max())
+        report.append(f"{name}: rel-L2 {e2:.2e} max-abs {emax:.2e} (max|ref| {float(np.abs(r).max()):.2f})")
+        assert e2 <= 3e-3 and emax <= 2e-2 * max(1.0, float(np.abs(r).max())), report[-1]
+    del dump
+    net.destroy()
+    ref32 = fo.stylenet_forward(weights, img, k, prec=fo.FP32)
+    refbl = fo.stylenet_forward(weights, img, k, prec=fo.FP16_BLEND)
+    d_store = float(np.abs(got[..., :3] - ref[..., :3]).max())
+    d_32 = float(np.abs(got[..., :3] - ref32[..., :3]).max())
+    d_blend = float(np.abs(got[..., :3] - refbl[..., :3]).max())
+    ref_spread = float(np.abs(refbl[..., :3] - ref32[..., :3]).max())     # how far the reference's own two precisions are apart
+    report.append(f"final RGB max-abs: vs FP16_STORE {d_store:.2e}, vs FP32 {d_32:.2e}, vs FP16_BLEND {d_blend:.2e}; "
+                  f"FP16_BLEND vs FP32 oracle {ref_spread:.2e}; rel-L2 vs FP32 {rel_l2(got[..., :3], ref32[..., :3]):.2e}; "
+                  f"PSNR8 vs FP32 {_psnr8(got[..., :3], ref32[..., :3]):.1f} dB, vs FP16_BLEND {_psnr8(got[..., :3], refbl[..., :3]):.1f} dB")
+    (tmp_path / "report.txt").write_text("\n".join(report))
+    print("\n".join(report))
+    assert d_store <= 6e-3 and d_32 <= 8e-3, report[-1]
+    # the reference's default arithmetic rounds more often than this backend (once per pass instead of once per layer): the GPU
+    # result must be at least as close to the fp32 result as the reference's own default mode is, within the store tolerance
+    assert d_blend <= max(8e-3, 2.0 * ref_spread), report[-1]
+    assert _psnr8(got[..., :3], ref32[..., :3]) > 45.0 and _psnr8(got[..., :3], refbl[..., :3]) > 40.0, report[-1]
+    np.testing.assert_allclose(got[..., 3], 0.5)
+
+
+def test_stylenet_vs_reference_default_blend_precision():
+    """GPU output vs the oracle's FP16_BLEND mode (the reference's default: RGBA16F render targets, one rounding per blend
+    pass) on BASELINE configs[0] (StyleNet 3x3, 512x624), per statistic; bounds stated here and in DESIGN.md section 5."""
+    w, h, k = 512, 624, 3
+    weights = fo.stylenet_synthetic_weights(k)
+    img = fo.synthetic_image(h, w, 3)
+    net = hostapi.StyleNet(k, w, h)
+    net.load_weights(weights)
+    net.setup()
+    net.set_input(img)
+    net.forward()
+    got = net.output_rgba()[0][..., :3].copy()
+    net.destroy()
+    refbl = fo.stylenet_forward(weights, img, k, prec=fo.FP16_BLEND)[..., :3]
+    ref32 = fo.stylenet_forward(weights, img, k, prec=fo.FP32)[..., :3]
+    d_blend, spread = float(np.abs(got - refbl).max()), float(np.abs(refbl - ref32).max())
+    print(f"StyleNet3x3 512x624: GPU vs FP16_BLEND max-abs {d_blend:.2e} rel-L2 {rel_l2(got, refbl):.2e}; FP16_BLEND vs FP32 {spread:.2e}")
+    assert d_blend <= max(8e-3, 2.0 * spread) and rel_l2(got, refbl) <= 5e-3
+    assert _psnr8(got, refbl) > 40.0
+
+
+def test_resnet50_top5_on_64_images():
+    """identical top-5 index set vs the oracle on >= 64 synthetic images -- one batch-64 forward through the host
+    engine (BASELINE configs[2]/[3] path).  Synthetic weights give logits whose 5th / 6th ranks can be closer than the fp16
+    storage error; such an image passes if every index that differs has a reference logit within 2 x max|logit error| of the
+    reference's 5th logit (a tie at the stated tolerance).  At least 90 % of the images must match exactly, and argmax always."""
+    n = 64
+    weights = fo.resnet50_synthetic_weights()
+    imgs = np.stack([fo.synthetic_image(224, 224, 1000 + i) for i in range(n)])
+    net = hostapi.ResNet50(batch=n)
+    net.load_weights(weights)
+    net.setup()
+    net.set_input(imgs)
+    net.forward()
+    logits = net.logits().copy()
+    net.destroy()
+    assert logits.shape == (n, 1000) and np.isfinite(logits).all()
+    exact, worst = 0, 0.0
+    for i in range(n):
+        ref = fo.resnet50_forward(weights, imgs[i], prec=fo.FP32)
+        e2 = rel_l2(logits[i], ref)
+        worst = max(worst, e2)
+        assert e2 <= 2e-2, f"image {i}: logits rel-L2 vs fp32 oracle {e2:.2e}"
+        assert int(np.argmax(logits[i])) == int(np.argmax(ref)), f"image {i}: argmax differs"
+        tg, tr = set(np.argsort(-logits[i])[:5].tolist()), set(np.argsort(-ref)[:5].tolist())
+        if tg == tr:
+            exact += 1
+            continue
+        err = float(np.abs(logits[i] - ref).max())
+        fifth = float(np.sort(ref)[-5])
+        for idx in tg ^ tr:
+            assert abs(float(ref[idx]) - fifth) <= 2.0 * err, f"image {i}: top-5 differs beyond a tie (index {idx})"
+    print(f"ResNet-50 batch {n}: top-5 identical on {exact}/{n} images, worst logits rel-L2 {worst:.2e}")
+    assert exact >= int(0.9 * n)
+
+
+def test_fusions_exclude_each_other_at_the_abi():
+    """a deep 1x1 convolution of the tcgen05 family accepts the fused input batch-norm but no fused function, and
+    never both (the engine's two fusion passes used to claim the same layer, after which every forward() failed)."""
+    ctx = capi.Context(0)
+    rng = np.random.default_rng(3)
+    ci = co = 64
+    wb = np.concatenate([rng.uniform(-0.5, 0.5, co), rng.normal(0, 0.1, co * ci)]).astype(np.float32)
+    op = capi.Conv2d(ctx, wb, width=14, height=14, in_channels=ci, out_channels=co, kernel=1, flags=capi.FLAG_DEEP | capi.FLAG_PRE_RELU)
+    assert op.backend == capi.BACKEND_TC
+    with pytest.raises(capi.FynError):
+        op.set_epilogue(capi.EPILOGUE_SIGMOID)
+    sb = np.concatenate([rng.uniform(0.5, 1.5, ci), rng.uniform(-0.2, 0.2, ci)]).astype(np.float32)
+    op.set_input_norm(sb)
+    with pytest.raises(capi.FynError):
+        op.set_epilogue(capi.EPILOGUE_SIGMOID)
+    x = rng.normal(size=(ci, 14, 14)).astype(np.float32)
+    tin, tout = ctx.tensor(14, 14, ci, 0, capi.ORDER_DEEP), ctx.tensor(14, 14, co, 0, capi.ORDER_DEEP)
+    tin.write_chw(x)
+    op.run(tin, tout)                                     # still runs, with the fused norm
+    xn = (x.astype(np.float16).astype(np.float32) * sb[:ci, None, None] + sb[ci:, None, None]).astype(np.float16).astype(np.float32)
+    ref = fo.conv2d(xn, wb, co, 1, deep=True, act=fo.ACT_RELU, prec=fo.FP16_STORE)
+    assert rel_l2(tout.read_chw(), ref) <= 3e-3
+    # a shallow convolution takes the fused function, then refuses the input norm
+    wb3 = np.concatenate([rng.uniform(-0.5, 0.5, 12), rng.normal(0, 0.1, 12 * 9 * 12)]).astype(np.float32)
+    op2 = capi.Conv2d(ctx, wb3, width=32, height=16, in_channels=12, out_channels=12, kernel=3)
+    op2.set_epilogue(capi.EPILOGUE_SIGMOID)
+    with pytest.raises(capi.FynError):
+        op2.set_input_norm(np.ones(24, np.float32))
+    op.destroy()
+    op2.destroy()
+
+
+def test_resnet50_graph_replay_skip_io_and_logit_gather():
+    """Engine::enableGraph (CUDA-graph replay of the 59 device layers), Engine::skipIO (device-resident operation) and
+    fyn_allgather_logits at world size 1: identical logits in every mode, bit for bit."""
+    weights = fo.resnet50_synthetic_weights()
+    imgs = np.stack([fo.synthetic_image(224, 224, 300 + i) for i in range(2)])
+    net = hostapi.ResNet50(batch=2)
+    net.load_weights(weights)
+    net.setup()
+    net.set_input(imgs)
+    net.forward()
+    want = net.logits().copy()
+    net.enable_graph(True)
+    for i in range(3):                                    # eager warm-up, capture, replay
+        net.forward()
+        np.testing.assert_array_equal(net.logits(), want)
+    assert net.graph_active
+    # new weights invalidate the captured graph; the old ones bring the old result back
+    net.load_weights(fo.resnet50_synthetic_weights(seed=51))
+    net.forward()
+    assert not np.array_equal(net.logits(), want)
+    net.load_weights(weights)
+    for i in range(3):
+        net.forward()
+    assert net.graph_active
+    np.testing.assert_array_equal(net.logits(), want)
+    # device-resident + gather into device memory through the C ABI
+    ctx = capi.Context(0)
+    comm = capi.Comm(ctx, 0, 1, None)
+    dev = ctx.device_alloc(3 * 1000 * 4)
+    host = ctx.host_alloc(3 * 1000)
+    net.skip_io(True)
+    net.forward()
+    comm.allgather_logits(net.layer_tensor(72), 3, dev, net.stream)      # room for 3 images per rank: the third row is zero
+    ctx.memcpy_d2h(host, dev, net.stream)
+    ctx.stream_sync(net.stream)
+    got = host.reshape(3, 1000)
+    np.testing.assert_array_equal(got[:2], want)
+    assert not got[2].any()
+    comm.destroy()
+    ctx.device_free(dev)
+    net.destroy()
+
+
+def test_halo_exchange_single_rank_is_a_no_op():
+    """World size 1: registration and exchanges succeed without neighbours and leave the frame untouched."""
+    weights = fo.stylenet_synthetic_weights(3)
+    img = fo.synthetic_image(64, 96, 9)
+    net = hostapi.StyleNet(3, 96, 64)
+    net.load_weights(weights)
+    net.setup()
+    net.set_input(img)
+    net.forward()
+    want = net.output_rgba()[0].copy()
+    ctx = capi.Context(0)
+    comm = capi.Comm(ctx, 0, 1, None)
+    net.set_halo_exchange(comm, 8, 64)
+    net.forward()
+    np.testing.assert_array_equal(net.output_rgba()[0], want)
+    net.set_halo_exchange(None, 0, 0)
+    comm.destroy()
+    net.destroy()

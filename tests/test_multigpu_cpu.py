@@ -42,6 +42,29 @@ def test_band_rows_and_halo_plan():
     assert bp[0] == (0, 1084, 0, 1024) and bp[1] == (964, 2108, 60, 1024) and bp[3] == (3012, 4096, 60, 1024)
 
 
+def test_halo_band_plan_covers_every_layer():
+    """Row bands with the per-layer exchange: the 8-row margin must cover every layer's taps at that layer's resolution, the
+    bands must tile the frame, and every level (/1, /2, /4) must see whole rows."""
+    for k in (3, 9):
+        assert multigpu.stylenet_halo_margin(k) <= multigpu.HALO_MARGIN
+        for _, div, above, below in multigpu.stylenet_halo_plan(k):
+            assert max(above, below) <= multigpu.HALO_MARGIN // div
+    m = multigpu.HALO_MARGIN
+    assert m % 4 == 0
+    for height, world in ((4096, 2), (4096, 8), (1856, 3), (64, 2)):
+        plan = multigpu.stylenet_halo_band_plan(height, world)
+        kept = 0
+        for r, (ib, ie, skip, keep) in enumerate(plan):
+            assert ib % 4 == 0 and ie % 4 == 0 and keep % 4 == 0
+            assert skip == (m if r > 0 else 0) and ie - ib == keep + skip + (m if r < world - 1 else 0)
+            assert ib + skip == kept
+            kept += keep
+        assert kept == height
+    assert multigpu.stylenet_halo_band_plan(4096, 8)[3] == (1536 - 8, 2048 + 8, 8, 512)
+    # against the overlapped-band plan: 8 rows of margin instead of 60
+    assert multigpu.stylenet_margin(9) // multigpu.HALO_MARGIN >= 7
+
+
 def _worker(rank, world, port, total, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
