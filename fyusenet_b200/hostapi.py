@@ -180,7 +180,6 @@ class Network:
         _check(lib().fynhost_net_layer_timing(self._h, int(number), C.byref(ms), C.byref(us)))
         return ms.value, us.value
 
-    @property
     def enable_graph(self, on=True):
         """Replay the device layers of the synchronous path from a CUDA graph (Engine::enableGraph)."""
         _check(lib().fynhost_net_enable_graph(self._h, int(bool(on))))
