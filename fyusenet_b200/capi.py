@@ -121,7 +121,8 @@ EXPORTS = [
     "fyn_tensor_wrap", "fyn_tensor_destroy", "fyn_tensor_clear", "fyn_tensor_get_desc", "fyn_tensor_device_ptr",
     "fyn_upload_f32_async", "fyn_download_f32_async", "fyn_download_f32_elems", "fyn_tensor_write_chw_f32",
     "fyn_tensor_read_chw_f32", "fyn_conv2d_output_size", "fyn_conv2d_create", "fyn_conv2d_load_weights",
-    "fyn_conv2d_run", "fyn_conv2d_backend", "fyn_conv2d_set_epilogue", "fyn_conv2d_set_input_norm", "fyn_conv2d_plan_query", "fyn_pool2d_create", "fyn_pool2d_run", "fyn_batchnorm_create",
+    "fyn_conv2d_run", "fyn_conv2d_backend", "fyn_conv2d_set_epilogue", "fyn_conv2d_set_input_norm", "fyn_conv2d_plan_query",
+    "fyn_conv_chain_create", "fyn_conv_chain_layers", "fyn_conv_chain_run", "fyn_conv_chain_destroy", "fyn_pool2d_create", "fyn_pool2d_run", "fyn_batchnorm_create",
     "fyn_batchnorm_load", "fyn_batchnorm_run", "fyn_sigmoid_create", "fyn_sigmoid_run", "fyn_op_destroy",
     "fyn_scale_create", "fyn_scale_out_size", "fyn_scale_run", "fyn_arith_create", "fyn_arith_run", "fyn_concat_create",
     "fyn_concat_run", "fyn_dwconv3x3_create", "fyn_dwconv3x3_load_weights", "fyn_dwconv3x3_run", "fyn_transconv2d_create", "fyn_transconv2d_load_weights", "fyn_transconv2d_run", "fyn_rgb2bgr_create", "fyn_rgb2bgr_run", "fyn_relayout_create", "fyn_relayout_run",
@@ -136,10 +137,12 @@ def lib():
     """Load libfyusenet_b200.so (built in-tree by __graft_entry__.build() / csrc/Makefile)."""
     global _lib
     if _lib is None:
-        if not LIB_PATH.exists():
-            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+        import os
+        path = Path(os.environ.get("FYN_B200_LIB", LIB_PATH))   # (profiling builds: csrc/Makefile PROF=1)
+        if not path.exists():
+            raise ImportError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
                               " (there is no CPU or PyTorch fallback)")
-        L = C.CDLL(str(LIB_PATH))
+        L = C.CDLL(str(path))
         L.fyn_last_error.restype = C.c_char_p
         L.fyn_tensor_device_ptr.restype = C.c_void_p
         L.fyn_download_f32_elems.restype = C.c_size_t
@@ -371,6 +374,33 @@ class Conv2d(_Op):
 
     def run(self, x: Tensor, out: Tensor, residual: Tensor | None = None, stream=None):
         check(lib().fyn_conv2d_run(self._h, x._h, residual._h if residual is not None else None, out._h, _s(stream)))
+
+
+class ConvChain:
+    """fyn_conv_chain: n >= 2 Conv2d ops of identical geometry run by one persistent kernel (bit-identical to running them one
+    by one).  residual_from[i] = index of the layer whose output layer i adds (must be i - 2; -1 = the chain input)."""
+
+    def __init__(self, ctx, ops, residual_from=None):
+        self.ctx, self.ops = ctx, list(ops)
+        arr = (C.c_void_p * len(self.ops))(*[o._h for o in self.ops])
+        rf = None
+        if residual_from is not None:
+            rf = (C.c_int * len(self.ops))(*[int(v) for v in residual_from])
+        self._h = C.c_void_p()
+        check(lib().fyn_conv_chain_create(ctx._h, arr, rf, len(self.ops), C.byref(self._h)))
+
+    def run(self, x, out, stream=None) -> bool:
+        """False: the tensors' formats are not covered (nothing was enqueued)."""
+        rc = lib().fyn_conv_chain_run(self._h, x._h, out._h, _s(stream))
+        if rc == 1:
+            return False
+        check(rc)
+        return True
+
+    def destroy(self):
+        if self._h:
+            lib().fyn_conv_chain_destroy(self._h)
+            self._h = C.c_void_p()
 
 
 class Pool2d(_Op):

@@ -1,0 +1,907 @@
+// fyn_conv_chain.cu -- one persistent tcgen05 kernel for a CHAIN of shallow NxN convolutions of identical geometry
+// (StyleNet's residual trunk: res1_1 ... res5_2, ten 3x3 40->40 layers on the same 381x464 tensor).
+//
+// The reference renders every layer as its own sequence of blend passes (fyusenet/gpu/vanilla/convlayerNxN_vanilla.cpp:72-145,
+// residual input: shaders/vanilla/residual.inc); fyn_conv_tc.cu turned a layer into one kernel.  For thin layers on
+// L2-resident tensors that kernel spends a third of its time before its first epilogue (prologue, first rows' copy
+// latency, first transform) and another ~2 us between launches, because a dependent launch needs the WHOLE previous
+// grid.  Here one launch walks all layers; a strip of layer l+1 only waits for the strips of layer l it reads.
+//
+// What changes against fyn_conv_tc.cu (the arithmetic does not: same step table, same weight images, same epilogue, so the
+// result is bit-identical to the unfused layers):
+//  * Intermediate tensors are private to the chain and stored in the OPERAND layout of the next layer:
+//      image[n][row + P][8-channel chunk][pixel + mh][8 x fp16]   (P = tensor padding, mh = kernel / 2),
+//    whose border rows / columns are zero like the padding texels of a tensor; with P = 0 (StyleNet: CLAMP_TO_EDGE reads
+//    at the borders, base/buffermanager.cpp:657-670) the border columns replicate the edge pixel and rows clamp,
+//    with the consumer's prefix activation already applied (activation-at-fetch, base/layerbase.h:50-59, moved to the
+//    producer's store: the value is computed from the fp16-rounded result exactly as the loader warps would).  A row of a
+//    strip therefore arrives in the ring slot by `nchunks` bulk copies (TMA unit) and is a valid UMMA operand as it
+//    lands: no loader warps, no staging buffers, no generic-proxy transform, no fence.proxy.async on shared memory.
+//    The un-activated values a later layer adds as its residual live in one more image that every thread updates in
+//    place (it is read and written by the same thread).
+//  * Work: the image is cut into strips of SH rows x 128 columns; a CTA owns one strip in the upper and one in the lower
+//    half of the image and processes (layer 0: upper, lower), (layer 1: upper, lower), ...  While a CTA works on its lower
+//    strip every neighbour of its upper strip finishes the same layer, so the next layer's rows can be fetched without a
+//    bubble.  Rows and jobs are numbered cumulatively over the whole program, so the ring of row slots, the two TMEM
+//    accumulators and all mbarrier phases simply run on across strips and layers.
+//  * Cross-CTA dependencies: progress[image of layer l][strip][image n][column block] = rows of that strip stored so far,
+//    tagged with a per-launch epoch (no reset between launches).  Epilogue threads count themselves into a shared-memory
+//    counter per accumulator buffer after their stores (red.release); a publisher warp polls the two counters, derives
+//    the number of completed jobs and turns it into `fence; st.release` of the strips' counters -- it may skip values
+//    when it falls behind and never holds the epilogue up.  The producer warp
+//    polls (ld.acquire, cached) the counters of the <= 3 column blocks a row spans before it issues the row's copies,
+//    followed by fence.proxy.async (generic-proxy stores of other CTAs -> async-proxy reads of the bulk copies).
+//    All CTAs of the grid must be co-resident (grid <= SM count, one CTA per SM): checked on the host.
+//  * The weight image of layer l+1 is fetched while layer l runs (two buffers).
+//
+// Warp roles ((E + 4) x 32 threads, E = 8 or 12): warps [0, E) epilogue, E producer, E+1 / E+2 MMA issuers (even / odd
+// jobs, one TMEM accumulator each), E+3 publisher.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "fyn_internal.h"
+#include "fyn_tc_common.cuh"
+
+namespace {
+
+constexpr int kMaxChain = 16;
+constexpr int kChainBufs = 4;     // rotating input images: layer l writes image (l+1) % 4 while neighbours may still read images l and l-1
+
+struct ChainLayer {
+    const uint4 *wimg;   // weight image of the layer (ConvTcPlan::d_wimg)
+    ActParams act;       // prefix activation of the layer: applied by whoever stores the layer's input image
+    int resSrc;          // 0 no residual, 1 the chain input (plane layout), 2 the raw image
+    int reluRes, bnRes;
+    int writeRaw;        // a later layer adds this layer's un-activated output: keep it in the raw image
+};
+
+struct ChainArgs {
+    TView in, out;                    // chain input / output tensors (shallow plane layout, fp16, packing 4)
+    __half *A[kChainBufs];
+    __half *R;
+    unsigned long long *progress;
+    unsigned long long epoch;
+    int nlayers;
+    ChainLayer layer[kMaxChain];
+    uint32_t wbytes, idesc, b_lbo;
+    int nsteps;
+    TcStep steps[kMaxSteps];
+    int N, nchunks, rowpx, K, mh, slotBytes, nslots, nmirror;
+    int biasFolded;
+    uint32_t biasB16, onesOff, epiOff;
+    int Wj, Hj, P;
+    int nxs, nG, SH, nsub, batch, NS;
+    int pitchPx, imgRows;
+    long long imgElems;               // halves per image n of an internal image
+    int epiWarps;
+    int nInPlanes, nOutPlanes;
+    int rawInput;                     // layer 1 adds the chain input: the input relayout also fills the raw image
+    int simpleAct;
+};
+
+// (gpu-scope acquire / release operations flush the SM's L1 and drain its store queue: measured, a polling loop of
+// ld.acquire.gpu more than doubled the time of the epilogue's stores on the same SM.  Polls are relaxed; ONE fence follows.)
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// generic-proxy writes (of other CTAs, made visible by the acquire) before async-proxy reads of global memory
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ uint4 ld_global_16(const __half *p) {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_cta_shared_inc(uint32_t *p) {
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
+}
+
+#ifdef FYN_CHAIN_PROFILE
+// event trace of three blocks (0, the middle one and its right neighbour): [block][segment][event] in ns (%globaltimer)
+__device__ unsigned long long g_ctrace[3][64][8];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define CTRACE(seg, ev) do { if (tb >= 0 && (seg) < 64) g_ctrace[tb][seg][ev] = gtimer(); } while (0)
+#define CPROF_DECL(n) long long n = 0
+#define CPROF_T() clock64()
+#define CPROF_ADD(acc, t0) acc += clock64() - (t0)
+#define CPROF_ON(x) x
+#else
+#define CPROF_DECL(n)
+#define CPROF_T() 0
+#define CPROF_ADD(acc, t0)
+#define CPROF_ON(x)
+#define CTRACE(seg, ev)
+#endif
+
+struct Ring {
+    int slot, fill;
+    __device__ __forceinline__ void next(int nslots) {
+        if (++slot == nslots) {
+            slot = 0;
+            fill++;
+        }
+    }
+};
+
+// NOCT: accumulator octets (= 8-channel chunks) per epilogue thread, (N / 8) / (epilogue warps / 4).  SIMPLE: every prefix
+// activation of the chain is ReLU or none.
+template <int NOCT, bool SIMPLE>
+__global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant__ ChainArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t wpad = (a.wbytes + 127u) & ~127u;
+    unsigned char *sW = smem;                                                                    // [2] weight images
+    unsigned char *sRing = smem + 2 * (size_t)wpad;                                              // [nslots + nmirror] rows
+    float4 *sEpi = reinterpret_cast<float4 *>(sRing + (size_t)(a.nslots + a.nmirror) * a.slotBytes);   // [2][32]: bias[16], scale[16]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sEpi + 64);
+    uint64_t *full = bars;                    // [nslots] row landed             (bulk copies -> MMA)
+    uint64_t *empty = bars + a.nslots;        // [nslots] row retired            (both MMA warps -> producer)
+    uint64_t *tfull = bars + 2 * a.nslots;    // [2]
+    uint64_t *tempty = tfull + 2;             // [2]
+    uint64_t *wbar = tempty + 2;              // [2] weight image landed
+    uint32_t *sCnt = reinterpret_cast<uint32_t *>(wbar + 2);   // [2] epilogue threads that have stored their part of a job, per buffer
+    uint32_t *tmemBase = sCnt + 2;
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int E = a.epiWarps, prodWarp = E, mmaWarp0 = E + 1, pubWarp = E + 3;
+
+    // CTA -> (image n, row group g, column block xb); the CTA owns strips t = h * nG + g, h = 0 .. nsub-1
+    int bid = blockIdx.x;
+    const int xb = bid % a.nxs;
+    bid /= a.nxs;
+    const int g = bid % a.nG;
+    const int n = bid / a.nG;
+    const int j0 = xb * kTileM;
+#ifdef FYN_CHAIN_PROFILE
+    const int tb = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x / 2 ? 1 : (blockIdx.x == gridDim.x / 2 + 1 ? 2 : -1));
+#endif
+    auto strip = [&](int h, int &t, int &ja, int &nj) {
+        t = h * a.nG + g;
+        ja = t * a.SH;
+        nj = max(0, min(a.Hj, ja + a.SH) - ja);
+    };
+    auto prog = [&](int image, int t, int xq) -> unsigned long long * {
+        return a.progress + (((size_t)image * a.NS + t) * a.batch + n) * a.nxs + xq;
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.nslots; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kMmaWarps);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], E * 32);
+            mbar_init(&wbar[b], 1);
+            sCnt[b] = 0;
+        }
+        fence_barrier_init();
+        // weights are not produced by the previous kernel: both buffers are filled before the grid dependency resolves
+        for (int l = 0; l < 2 && l < a.nlayers; l++) {
+            mbar_expect_tx(&wbar[l], a.wbytes);
+            bulk_g2s(sW + (size_t)l * wpad, a.layer[l].wimg, a.wbytes, &wbar[l]);
+        }
+    }
+    if (warp == mmaWarp0) tmem_alloc(tmemBase, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmemBase;
+    grid_dep_launch();
+    grid_dep_wait();
+
+    if (warp == prodWarp) {
+        // ===================== producer: rows of the input images -> ring slots =====================
+        // Per segment (strip of a layer): (1) lanes 0..8 poll the nine counters the segment's rows depend on -- the strips
+        // above, of and below the segment in the three column blocks a row spans -- until each has reached the last row
+        // the segment reads from it; normally the first look suffices (those rows were stored half a layer ago).
+        // (2) The rows are issued `batch` at a time, ONE ROW PER LANE: wait for the ring slot, announce the bytes, `nchunks`
+        // bulk copies (twice for mirrored slots).  A batch is short enough that no slot it waits for can depend on a row of
+        // the same batch (batch <= nslots - K + 1), so the lanes never wait for each other.
+        const uint32_t chunkBytes = (uint32_t)a.rowpx * 16u;
+        const uint32_t mirrorOff = (uint32_t)a.nslots * (uint32_t)a.slotBytes;
+        const unsigned long long epochTag = a.epoch << 32;
+        const int batch = min(32, a.nslots - a.K + 1);
+        int rowCum = 0;
+        CPROF_DECL(pPoll); CPROF_DECL(pIssue); CPROF_DECL(nPolls);
+        [[maybe_unused]] const long long pStart = CPROF_T();
+        for (int l = 0; l < a.nlayers; l++) {
+            const __half *img = a.A[l % kChainBufs] + (long long)n * a.imgElems;
+            for (int h = 0; h < a.nsub; h++) {
+                int t, ja, nj;
+                strip(h, t, ja, nj);
+                if (nj == 0) continue;
+                const int R = nj + a.K - 1;
+                {
+                    // data rows the segment reads: texture rows with CLAMP_TO_EDGE, as the samplers of the reference address
+                    // them, minus the padding rows (which nobody writes)
+                    const int dFirst = max(min(max(ja - a.mh + a.P, 0), a.imgRows - 1) - a.P, 0);
+                    const int dLast = min(min(max(ja + nj - 1 + a.mh + a.P, 0), a.imgRows - 1) - a.P, a.Hj - 1);
+                    const int t2 = t - 1 + lane / 3, xq = xb - 1 + lane % 3;
+                    bool mine = lane < 9 && t2 >= 0 && xq >= 0 && xq < a.nxs;
+                    unsigned long long want = 0;
+                    if (mine) {
+                        const int lo = max(dFirst, t2 * a.SH), hi = min(dLast, t2 * a.SH + a.SH - 1);
+                        mine = hi >= lo;
+                        want = epochTag | (unsigned)(hi - t2 * a.SH + 1);
+                    }
+                    const unsigned long long *p = mine ? prog(l, t2, xq) : nullptr;
+                    const long long t0 = clock64();
+                    if (lane == 0) CTRACE(l * a.nsub + h, 0);
+                    bool ok = !mine;
+                    for (;;) {
+                        if (!ok) ok = ld_relaxed_gpu(p) >= want;
+                        CPROF_ON(nPolls++);
+                        if (__all_sync(0xffffffffu, ok)) break;
+                        __nanosleep(100);
+                        if (clock64() - t0 > 6000000000ll) {     // ~3 s: a lost dependency must not hang the device
+                            if (!ok) printf("[fyn chain] block %d: layer %d strip %d never got strip %d of column block %d\n", (int)blockIdx.x, l, t, t2, xq);
+                            __trap();
+                        }
+                    }
+                    // acquire: the relaxed loads above saw the counters' release stores.  The stores the counters cover were made
+                    // through the generic proxy (by other SMs); the bulk copies below read through the async proxy.
+                    fence_acq_rel_gpu();
+                    fence_proxy_async_all();
+                    CPROF_ADD(pPoll, t0);
+                    if (lane == 0) CTRACE(l * a.nsub + h, 1);
+                }
+                [[maybe_unused]] const long long pt = CPROF_T();
+                // one (row, chunk) copy per lane: a batch of rows costs ceil(rows * nchunks / 32) copy instructions
+                for (int r0 = 0; r0 < R; r0 += batch) {
+                    const int items = min(batch, R - r0) * a.nchunks;
+                    for (int it = lane; it < items; it += 32) {
+                        const int rr = it / a.nchunks, c = it - rr * a.nchunks, r = r0 + rr;
+                        const int cum = rowCum + r, fill = cum / a.nslots, slot = cum - fill * a.nslots;
+                        const int yr = min(max(ja - a.mh + r + a.P, 0), a.imgRows - 1);
+                        mbar_wait(&empty[slot], (fill & 1) ^ 1);
+                        const bool mir = slot < a.nmirror;
+                        if (c == 0) mbar_expect_tx(&full[slot], (uint32_t)a.nchunks * chunkBytes * (mir ? 2u : 1u));
+                        const __half *src = img + (((long long)yr * a.nchunks + c) * a.pitchPx + j0) * 8;
+                        unsigned char *dst = sRing + (size_t)slot * a.slotBytes + (size_t)c * chunkBytes;
+                        bulk_g2s(dst, src, chunkBytes, &full[slot]);
+                        if (mir) bulk_g2s(dst + mirrorOff, src, chunkBytes, &full[slot]);
+                    }
+                    __syncwarp();
+                }
+                CPROF_ADD(pIssue, pt);
+                if (lane == 0) CTRACE(l * a.nsub + h, 2);
+                rowCum += R;
+            }
+        }
+#ifdef FYN_CHAIN_PROFILE
+        if ((blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && lane == 0)
+            printf("[chain prof] block %d producer: total %lld poll %lld (%lld looks) issue incl. waitEmpty %lld\n", (int)blockIdx.x, (long long)(clock64() - pStart), pPoll, nPolls,
+                   pIssue);
+#endif
+    } else if (warp == mmaWarp0 || warp == mmaWarp0 + 1) {
+        // ===================== MMA issuers =====================
+        // As in fyn_conv_tc.cu: warp w issues the jobs with (cumulative index & 1) == w into TMEM buffer w.  Row bookkeeping
+        // is cumulative: a warp waits for the rows [waited, window end) and, before it issues a job, releases the rows
+        // below that job's window -- all of which it has waited for, and which only its earlier MMAs (covered by the
+        // commit) can still be reading.
+        const int mw = warp - mmaWarp0;
+        const uint32_t rbase16 = smem_u32(sRing) >> 4, slot16 = (uint32_t)a.slotBytes >> 4;
+        const uint64_t hiA = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
+        const uint32_t d = tmem + (uint32_t)mw * 64u;
+        Ring wt{0, 0}, rl{0, 0}, st{0, 0};     // next row to wait for / to release; first row of the current segment
+        int waited = 0, released = 0, rowBase = 0, Q = 0;
+        CPROF_DECL(pWaitT); CPROF_DECL(pWaitF); CPROF_DECL(pIss);
+        [[maybe_unused]] const long long pStart = CPROF_T();
+        for (int l = 0; l < a.nlayers; l++) {
+            const uint32_t sWl = smem_u32(sW) + (uint32_t)(l & 1) * wpad;
+            const uint32_t bconst = (sWl >> 4) | ((a.b_lbo >> 4) << 16);
+            const uint32_t onesDesc = ((sWl + a.onesOff) >> 4) | ((16u >> 4) << 16);
+            bool haveW = false;
+            for (int h = 0; h < a.nsub; h++) {
+                int t, ja, nj;
+                strip(h, t, ja, nj);
+                if (nj == 0) continue;
+                const int R = nj + a.K - 1;
+                Ring win = st;
+                for (int q = 0; q < nj; q++, win.next(a.nslots)) {
+                    const int Qg = Q + q;
+                    if ((Qg & 1) != mw) continue;
+                    const int use = Qg >> 1;
+                    const int start = rowBase + q, needTo = start + a.K;
+                    if (elect_one()) {
+                        // rows below this job's window that this warp has already seen land go back first (a short ring
+                        // would otherwise deadlock at a strip boundary, where the window jumps by K rows) ...
+                        Ring rr = rl;
+                        int k = released;
+                        for (; k < start && k < waited; k++, rr.next(a.nslots)) umma_commit(&empty[rr.slot]);
+                        [[maybe_unused]] long long pt = CPROF_T();
+                        mbar_wait(&tempty[mw], (use & 1) ^ 1);
+                        CPROF_ADD(pWaitT, pt);
+                        pt = CPROF_T();
+                        Ring w = wt;
+                        for (int kk = waited; kk < needTo; kk++, w.next(a.nslots)) mbar_wait(&full[w.slot], w.fill & 1);
+                        if (!haveW) mbar_wait(&wbar[l & 1], (l >> 1) & 1);
+                        CPROF_ADD(pWaitF, pt);
+                        pt = CPROF_T();
+                        tc_fence_after();
+                        // ... the rest (rows the other warp's windows needed, this warp's did not) once they have been seen
+                        for (; k < start; k++, rr.next(a.nslots)) umma_commit(&empty[rr.slot]);
+                        if (q == 0) CTRACE(l * a.nsub + h, 3);
+                        const uint32_t winBase = rbase16 + (uint32_t)win.slot * slot16;
+#pragma unroll 4
+                        for (int s = 0; s < a.nsteps; s++) {
+                            const TcStep stp = a.steps[s];
+                            umma_f16(d, hiA | (uint64_t)(stp.a_lo + winBase), hiA | (uint64_t)(stp.b_off16 + bconst), a.idesc, stp.accumulate);
+                        }
+                        if (a.biasFolded) umma_f16(d, hiA | (uint64_t)onesDesc, hiA | (uint64_t)(a.biasB16 + bconst), a.idesc, 1u);
+                        umma_commit(&tfull[mw]);
+                        CPROF_ADD(pIss, pt);
+                        if (q == nj - 1) CTRACE(l * a.nsub + h, 4);
+                    }
+                    haveW = true;
+                    for (; waited < needTo; waited++) wt.next(a.nslots);
+                    for (; released < start; released++) rl.next(a.nslots);
+                    __syncwarp();
+                }
+                rowBase += R;
+                Q += nj;
+                for (int k = 0; k < R; k++) st.next(a.nslots);
+            }
+        }
+        // rows this warp never needed (the other warp's last windows) still owe its share of the release
+        if (elect_one()) {
+            for (int k = waited; k < rowBase; k++, wt.next(a.nslots)) mbar_wait(&full[wt.slot], wt.fill & 1);
+            for (int k = released; k < rowBase; k++, rl.next(a.nslots)) umma_commit(&empty[rl.slot]);
+        }
+        __syncwarp();
+#ifdef FYN_CHAIN_PROFILE
+        if (mw == 0 && elect_one()) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            printf("[chain prof] block %3d xb %d g %2d sm %3u mma0: total %lld waitTempty %lld waitFull %lld issue %lld jobs %d\n", (int)blockIdx.x, xb, g, smid, (long long)(clock64() - pStart), pWaitT, pWaitF,
+                   pIss, Q);
+        }
+#endif
+    } else if (warp == pubWarp) {
+        // ===================== publisher: completed jobs -> progress counters =====================
+        // sCnt[b] / T = jobs on accumulator buffer b whose stores have all been issued (a thread only counts itself into
+        // job Q once job Q - 2 is complete, so the quotient is exact); jobs alternate between the buffers, hence the
+        // number of jobs completed IN ORDER is 2 * min + (1 if buffer 0 is ahead).
+        if (lane == 0) {
+            const unsigned long long epochTag = a.epoch << 32;
+            const uint32_t T = (uint32_t)E * 32u;
+            int total = 0;                                   // jobs of the layers that publish (all but the last)
+            for (int h = 0; h < a.nsub; h++) {
+                int t, ja, nj;
+                strip(h, t, ja, nj);
+                total += nj;
+            }
+            total *= a.nlayers - 1;
+            // Consumers wait for two values per strip only: its first mh rows (the halo of the strip above) and all of its
+            // rows (its own next layer and the halo of the strip below), so those are the counts worth a release store.
+            int l = 0, h = 0, segStart = 0, pubInSeg = 0;    // current segment, its first job, rows of it published so far
+            long long t0 = clock64();
+            CPROF_DECL(pFence); CPROF_DECL(nPub);
+            while (segStart < total) {
+                int t, ja, nj;
+                strip(h, t, ja, nj);
+                if (nj == 0) {
+                    if (++h == a.nsub) {
+                        h = 0;
+                        l++;
+                    }
+                    continue;
+                }
+                const uint32_t c0 = ld_acquire_cta_shared(&sCnt[0]) / T, c1 = ld_acquire_cta_shared(&sCnt[1]) / T;
+                const int prefix = (int)((c0 > c1) ? 2 * c1 + 1 : 2 * c0);
+                const int cur = min(prefix - segStart, nj);
+                const int first = min(a.mh, nj);
+                const int threshold = pubInSeg < first ? first : nj;
+                if (cur < threshold) {
+                    __nanosleep(32);
+                    if (clock64() - t0 > 20000000000ll) __trap();
+                    continue;
+                }
+                [[maybe_unused]] const long long pf = CPROF_T();
+                st_release_gpu(prog(l + 1, t, xb), epochTag | (unsigned)cur);
+                CPROF_ADD(pFence, pf);
+                CPROF_ON(nPub++);
+                pubInSeg = cur;
+                if (cur == nj) {
+                    CTRACE(l * a.nsub + h, 6);
+                    segStart += nj;
+                    pubInSeg = 0;
+                    if (++h == a.nsub) {
+                        h = 0;
+                        l++;
+                    }
+                }
+                t0 = clock64();
+            }
+#ifdef FYN_CHAIN_PROFILE
+            if (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) printf("[chain prof] block %d publisher: %lld publishes for %d jobs, %lld cycles in fences\n", (int)blockIdx.x, nPub, total, pFence);
+#endif
+        }
+    } else {
+        // ===================== epilogue: warps [0, E) =====================
+        // The job loop is kept SMALL on purpose: the first version of this role (run-time octet count, three residual
+        // sources, generic activation; ~2k instructions per job) was bound by instruction fetch -- 2-4k cycles per job against
+        // 1.1k of tensor-pipe time (role profile, make PROF=1).  Hence the template parameters, the hoisted per-thread
+        // constants, and a raw image that also holds the chain input (one residual source).
+        const int m = threadIdx.x & 127;
+        const int part = warp >> 2;
+        const int jx = j0 + m;
+        const bool valid = jx < a.Wj;
+        const int etid = threadIdx.x;
+        const unsigned long long epochTag = a.epoch << 32;
+        const long long chunkRow = (long long)a.pitchPx * 8;           // halves per (row, chunk) of an internal image
+        const long long rowStride = chunkRow * a.nchunks;              // halves per row
+        // this thread's chunks (= accumulator octets part * NOCT + o): offset inside a row of an internal image, or -1
+        long long coff[NOCT];
+        int plane0[NOCT];
+#pragma unroll
+        for (int o = 0; o < NOCT; o++) {
+            const int c = part * NOCT + o;
+            coff[o] = (valid && c < a.nchunks) ? (long long)c * chunkRow + (long long)(jx + a.mh) * 8 : -1;
+            plane0[o] = 2 * c;
+        }
+        // P = 0: reads beyond the left / right edge see the edge pixel (CLAMP_TO_EDGE): the threads of the first and last
+        // image column keep the mh border columns of the input images equal to their pixel
+        const int edge = (a.P == 0 && valid) ? ((jx == 0 ? 1 : 0) | (jx == a.Wj - 1 ? 2 : 0)) : 0;
+        auto store_image = [&](__half *p, uint4 v) {
+            *reinterpret_cast<uint4 *>(p) = v;
+            if (edge) {
+                if (edge & 1) {
+#pragma unroll 1
+                    for (int e = 1; e <= a.mh; e++) *reinterpret_cast<uint4 *>(p - e * 8) = v;
+                }
+                if (edge & 2) {
+#pragma unroll 1
+                    for (int e = 1; e <= a.mh; e++) *reinterpret_cast<uint4 *>(p + e * 8) = v;
+                }
+            }
+        };
+        // prefix activation of the consumer, applied to the fp16 values as the loader warps of fyn_conv_tc.cu do.  SIMPLE:
+        // every layer has ReLU or none: max(v, floor) with floor = 0 or -inf
+        auto activate = [&](uint4 v, const ActParams &act, __half2 floor2) -> uint4 {
+            if (SIMPLE) {
+                __half2 *q = reinterpret_cast<__half2 *>(&v);
+#pragma unroll
+                for (int i = 0; i < 4; i++) q[i] = __hmax2(q[i], floor2);
+                return v;
+            }
+            return act_h8(v, act);
+        };
+        auto floor_of = [](const ActParams &act) { return act.type == 1 ? __float2half2_rn(0.f) : __half2half2(__ushort_as_half((unsigned short)0xfc00)); };
+        __half *rawImg = a.R + (long long)n * a.imgElems;
+        // ---- chain input (plane layout) -> input image of layer 0 with that layer's prefix activation, and (if layer 1 adds the
+        //      chain input) its un-activated copy in the raw image
+        {
+            const __half *inp = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems + ((long long)a.P * a.in.texW + a.P + jx) * 4;
+            __half *img = a.A[0] + (long long)n * a.imgElems;
+            const ActParams act0 = a.layer[0].act;
+            const __half2 floor0 = floor_of(act0);
+            const int parts = E >> 2;
+            for (int h = 0; h < a.nsub; h++) {
+                int t, ja, nj;
+                strip(h, t, ja, nj);
+                if (nj == 0) continue;
+                if (valid)
+                    for (int i = ja; i < ja + nj; i++)
+                        for (int c = part; c < a.nchunks; c += parts) {
+                            const __half *p = inp + (long long)i * a.in.texW * 4 + (long long)(2 * c) * a.in.planeElems;
+                            const uint2 lo = __ldg(reinterpret_cast<const uint2 *>(p));
+                            const uint2 hi = (2 * c + 1 < a.nInPlanes) ? __ldg(reinterpret_cast<const uint2 *>(p + a.in.planeElems)) : make_uint2(0u, 0u);
+                            const uint4 raw = make_uint4(lo.x, lo.y, hi.x, hi.y);
+                            const long long off = (long long)(i + a.P) * rowStride + (long long)c * chunkRow + (long long)(jx + a.mh) * 8;
+                            store_image(img + off, activate(raw, act0, floor0));
+                            if (a.rawInput) *reinterpret_cast<uint4 *>(rawImg + off) = raw;
+                        }
+                asm volatile("bar.sync 1, %0;" ::"r"(E * 32) : "memory");
+                if (etid == 0) st_release_gpu(prog(0, t, xb), epochTag | (unsigned)nj);
+            }
+        }
+        __half *outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((long long)a.P * a.out.texW + a.P + jx) * 4;
+        int Q = 0;
+        CPROF_DECL(pWaitTf); CPROF_DECL(pWaitW); CPROF_DECL(pCnt); CPROF_DECL(pLd); CPROF_DECL(pSt);
+        [[maybe_unused]] const long long pStart = CPROF_T();
+        [[maybe_unused]] long long pLayer0 = 0;
+        for (int l = 0; l < a.nlayers; l++) {
+            CPROF_ON(if (l == 1) pLayer0 = clock64() - pStart);
+            const bool last = l + 1 == a.nlayers;
+            const bool resOn = a.layer[l].resSrc != 0, reluRes = a.layer[l].reluRes != 0, bnRes = a.layer[l].bnRes != 0, writeRaw = a.layer[l].writeRaw != 0;
+            const ActParams actNext = a.layer[last ? l : l + 1].act;
+            const __half2 floorNext = floor_of(actNext);
+            __half *nextImg = a.A[(l + 1) % kChainBufs] + (long long)n * a.imgElems;
+            // epilogue parameters ride at the tail of the weight image: copy them out of the region the tensor core streams
+            [[maybe_unused]] long long ptw = CPROF_T();
+            mbar_wait(&wbar[l & 1], (l >> 1) & 1);
+            CPROF_ADD(pWaitW, ptw);
+            if (etid < 32) sEpi[(l & 1) * 32 + etid] = reinterpret_cast<const float4 *>(sW + (size_t)(l & 1) * wpad + a.epiOff)[etid];
+            asm volatile("bar.sync 1, %0;" ::"r"(E * 32) : "memory");
+            // every MMA of layer l-1 has completed (this thread has seen its last accumulator): its weight buffer is free
+            if (etid == 0 && l >= 1 && l + 1 < a.nlayers) {
+                fence_proxy_async_all();
+                mbar_expect_tx(&wbar[(l + 1) & 1], a.wbytes);
+                bulk_g2s(sW + (size_t)((l + 1) & 1) * wpad, a.layer[l + 1].wimg, a.wbytes, &wbar[(l + 1) & 1]);
+            }
+            const float4 *ep = sEpi + (l & 1) * 32;
+            // One strip of the layer.  RES / LAST are compile-time so that each variant of the job loop stays short (the role is
+            // bound by instruction issue: 12 warps x instructions per job / 4 schedulers).
+            auto run_strip = [&](auto resTag, auto lastTag, int ja, int nj, int segIdx) {
+                constexpr bool RES = decltype(resTag)::value, LAST = decltype(lastTag)::value;
+                __half *nextRow = nextImg + (long long)(ja + a.P) * rowStride;      // row of the next layer's input image
+                __half *rawRow = rawImg + (long long)(ja + a.P) * rowStride;        // row of the raw image
+                __half *outRow = outp + (long long)ja * a.out.texW * 4;             // row of the chain output (plane layout)
+                const long long outStride = (long long)a.out.texW * 4;
+                uint4 rres[NOCT];
+                if (RES) {
+#pragma unroll
+                    for (int o = 0; o < NOCT; o++)
+                        if (coff[o] >= 0) rres[o] = ld_global_16(rawRow + coff[o]);
+                }
+                for (int q = 0; q < nj; q++, nextRow += rowStride, rawRow += rowStride, outRow += outStride) {
+                    const int Qg = Q + q, buf = Qg & 1, use = Qg >> 1;
+                    [[maybe_unused]] long long pt = CPROF_T();
+                    mbar_wait(&tfull[buf], use & 1);
+                    CPROF_ADD(pWaitTf, pt);
+                    pt = CPROF_T();
+                    tc_fence_after();
+                    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * 64u + (uint32_t)(part * NOCT) * 8u;
+                    uint32_t acc[NOCT][8];
+#pragma unroll
+                    for (int o = 0; o < NOCT; o++) tmem_ld8(taddr + o * 8, acc[o]);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(&tempty[buf]);
+                    CPROF_ADD(pLd, pt);
+                    pt = CPROF_T();
+                    // this job's residual texels were requested one job ago; request the next job's now
+                    uint4 rcur[NOCT];
+                    if (RES) {
+#pragma unroll
+                        for (int o = 0; o < NOCT; o++) rcur[o] = rres[o];
+                        if (q + 1 < nj) {
+#pragma unroll
+                            for (int o = 0; o < NOCT; o++)
+                                if (coff[o] >= 0) rres[o] = ld_global_16(rawRow + rowStride + coff[o]);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 0; o < NOCT; o++) {
+                        if (coff[o] < 0) continue;
+                        uint32_t w[4];
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            float4 v = make_float4(__uint_as_float(acc[o][4 * k + 0]), __uint_as_float(acc[o][4 * k + 1]), __uint_as_float(acc[o][4 * k + 2]),
+                                                   __uint_as_float(acc[o][4 * k + 3]));
+                            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+                            if (!a.biasFolded) {
+                                const int p = (plane0[o] + k) & 15;
+                                const float4 bi = ep[p];
+                                sc = ep[16 + p];
+                                v = make_float4(fmaf(v.x, sc.x, bi.x), fmaf(v.y, sc.y, bi.y), fmaf(v.z, sc.z, bi.z), fmaf(v.w, sc.w, bi.w));
+                            }
+                            if (RES) {
+                                const uint32_t r0 = k ? rcur[o].z : rcur[o].x, r1 = k ? rcur[o].w : rcur[o].y;
+                                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&r0));
+                                const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&r1));
+                                float4 rs = make_float4(f0.x, f0.y, f1.x, f1.y);
+                                if (reluRes) rs = make_float4(fmaxf(rs.x, 0.f), fmaxf(rs.y, 0.f), fmaxf(rs.z, 0.f), fmaxf(rs.w, 0.f));
+                                if (bnRes) rs = make_float4(rs.x * sc.x, rs.y * sc.y, rs.z * sc.z, rs.w * sc.w);
+                                v.x += rs.x;
+                                v.y += rs.y;
+                                v.z += rs.z;
+                                v.w += rs.w;
+                            }
+                            // (channels that only pad a chunk come out as zero: zero weights, zero bias, zero residual)
+                            w[2 * k] = pack_half2(v.x, v.y);
+                            w[2 * k + 1] = pack_half2(v.z, v.w);
+                        }
+                        const uint4 raw = make_uint4(w[0], w[1], w[2], w[3]);
+                        if (LAST) {
+                            __half *o0 = outRow + (long long)plane0[o] * a.out.planeElems;
+                            *reinterpret_cast<uint2 *>(o0) = make_uint2(w[0], w[1]);
+                            if (plane0[o] + 1 < a.nOutPlanes) *reinterpret_cast<uint2 *>(o0 + a.out.planeElems) = make_uint2(w[2], w[3]);
+                        } else {
+                            store_image(nextRow + coff[o], activate(raw, actNext, floorNext));
+                            if (writeRaw) *reinterpret_cast<uint4 *>(rawRow + coff[o]) = raw;
+                        }
+                    }
+                    CPROF_ADD(pSt, pt);
+                    if (!LAST) {
+                        // hand the job's stores to the publisher: count this thread into the job once the buffer's previous
+                        // job (two jobs back) is complete -- which it practically always is
+                        const uint32_t before = (uint32_t)use * (uint32_t)(E * 32);
+                        pt = CPROF_T();
+                        while (ld_acquire_cta_shared(&sCnt[buf]) < before) {}
+                        red_release_cta_shared_inc(&sCnt[buf]);
+                        CPROF_ADD(pCnt, pt);
+                        if (etid == 0 && q == nj - 1) CTRACE(segIdx, 5);
+                    }
+                }
+            };
+            for (int h = 0; h < a.nsub; h++) {
+                int t, ja, nj;
+                strip(h, t, ja, nj);
+                if (nj == 0) continue;
+                const int segIdx = l * a.nsub + h;
+                if (last) {
+                    if (resOn) run_strip(std::true_type{}, std::true_type{}, ja, nj, segIdx);
+                    else run_strip(std::false_type{}, std::true_type{}, ja, nj, segIdx);
+                } else {
+                    if (resOn) run_strip(std::true_type{}, std::false_type{}, ja, nj, segIdx);
+                    else run_strip(std::false_type{}, std::false_type{}, ja, nj, segIdx);
+                }
+                Q += nj;
+            }
+        }
+#ifdef FYN_CHAIN_PROFILE
+        if (tb >= 0 && (etid == 0 || etid == 100 || etid == E * 32 - 1))
+            printf("[chain prof] block %d epilogue thread %d: total %lld (first layer incl. input relayout %lld) waitTfull %lld tmemLd %lld math+stores %lld countIn %lld waitWeights %lld jobs %d\n", (int)blockIdx.x, etid,
+                   (long long)(clock64() - pStart), pLayer0, pWaitTf, pLd, pSt, pCnt, pWaitW, Q);
+#endif
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == mmaWarp0) tmem_dealloc(tmem, 128);
+#ifdef FYN_CHAIN_PROFILE
+    if (tb >= 0 && threadIdx.x == 0) {
+        const unsigned long long base = g_ctrace[0][0][0];
+        for (int sg = 0; sg < a.nlayers * a.nsub && sg < 64; sg++)
+            printf("[chain trace] block %d seg %2d: poll %7lld - %7lld  issued %7lld | mma %7lld - %7lld | epilogue done %7lld  published %7lld (ns)\n", (int)blockIdx.x, sg,
+                   (long long)(g_ctrace[tb][sg][0] - base), (long long)(g_ctrace[tb][sg][1] - base), (long long)(g_ctrace[tb][sg][2] - base), (long long)(g_ctrace[tb][sg][3] - base),
+                   (long long)(g_ctrace[tb][sg][4] - base), (long long)(g_ctrace[tb][sg][5] - base), (long long)(g_ctrace[tb][sg][6] - base));
+    }
+#endif
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct fyn_conv_chain {
+    fyn_ctx *ctx = nullptr;
+    std::vector<fyn_op *> ops;
+    std::vector<int> resFrom;
+    ChainArgs args{};
+    __half *images = nullptr;            // kChainBufs input images + the raw image, one allocation
+    unsigned long long *progress = nullptr;
+    int batchAlloc = 0;
+    unsigned long long epoch = 0;
+    size_t smemBytes = 0;
+};
+
+namespace {
+
+int chain_fail_unsupported(const char *why) {
+    fyn_set_error("conv chain: %s", why);
+    return FYN_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fyn_conv_chain_create(fyn_ctx *ctx, fyn_op *const *ops, const int *residual_from, int n, fyn_conv_chain **out) {
+    if (!ctx || !ops || !out || n < 2) FYN_FAIL(FYN_ERR_INVALID, "conv chain: bad argument");
+    *out = nullptr;
+    if (n > kMaxChain) return chain_fail_unsupported("too many layers");
+    const fyn_op *first = ops[0];
+    if (!first || first->kind != FYN_OP_CONV || !first->tc) return chain_fail_unsupported("layers must run on the shallow tcgen05 family");
+    const fyn_conv_desc &d0 = first->conv;
+    const TcArgs &p0 = first->tc->chainArgs();
+    const int K = d0.kernel, mh = (K - 1) / 2;
+    if (d0.in_channels != d0.out_channels || d0.downsample != 1 || d0.dilation != 1 || d0.fractional || K < 3)
+        return chain_fail_unsupported("layers must be plain stride-1 NxN convolutions with as many outputs as inputs");
+    const int P = d0.in_padding;
+    if (P > mh || d0.out_padding != P) return chain_fail_unsupported("tensor padding must be the same on both sides and at most the kernel's half width");
+    if (p0.mode != 0 || p0.opx != 1 || p0.opy != 1 || p0.nver != 1 || p0.ds != 1 || p0.rowAdvance != 1 || p0.x_lead != mh || p0.nrows != K)
+        return chain_fail_unsupported("plan is not a single-phase stride-1 plan");
+    for (int i = 0; i < n; i++) {
+        const fyn_op *op = ops[i];
+        if (!op || op->kind != FYN_OP_CONV || !op->tc || op->ctx != ctx) return chain_fail_unsupported("layers must run on the shallow tcgen05 family");
+        const fyn_conv_desc &d = op->conv;
+        if (d.width != d0.width || d.height != d0.height || d.in_channels != d0.in_channels || d.out_channels != d0.out_channels || d.kernel != K ||
+            d.downsample != 1 || d.dilation != 1 || d.fractional || d.in_padding != P || d.out_padding != P)
+            return chain_fail_unsupported("layers differ in geometry");
+        if (d.flags & (FYN_FLAG_DEEP | FYN_FLAG_PRE_CLIP)) return chain_fail_unsupported("deep tensors / clip activations are not chained");
+        if ((d.flags & FYN_FLAG_POST_BATCHNORM) != (d0.flags & FYN_FLAG_POST_BATCHNORM)) return chain_fail_unsupported("layers differ in post-batchnorm");
+        if (op->epilogue != FYN_EPILOGUE_NONE || op->innorm) return chain_fail_unsupported("layers with fused functions are not chained");
+        const TcArgs &p = op->tc->chainArgs();
+        if (p.nsteps != p0.nsteps || p.N != p0.N || p.wbytes != p0.wbytes || p.biasFolded != p0.biasFolded || p.slotBytes != p0.slotBytes || p.rowpx != p0.rowpx ||
+            memcmp(p.steps, p0.steps, sizeof(TcStep) * p0.nsteps) != 0)
+            return chain_fail_unsupported("layers differ in their tcgen05 plan");
+        if (d.flags & FYN_FLAG_RESIDUAL_INPUT) {
+            if (d.res_padding != P) return chain_fail_unsupported("residual padding differs");
+            if (!residual_from || i < 1 || residual_from[i] != i - 2) return chain_fail_unsupported("a residual must be the input of the previous layer");
+        }
+    }
+    fyn_conv_chain *c = new fyn_conv_chain();
+    c->ctx = ctx;
+    c->ops.assign(ops, ops + n);
+    c->resFrom.assign(n, -2);
+    if (residual_from) c->resFrom.assign(residual_from, residual_from + n);
+    ChainArgs &a = c->args;
+    a.nlayers = n;
+    a.wbytes = p0.wbytes;
+    a.idesc = p0.idesc;
+    a.b_lbo = p0.b_lbo;
+    a.nsteps = p0.nsteps;
+    memcpy(a.steps, p0.steps, sizeof(TcStep) * p0.nsteps);
+    a.N = p0.N;
+    a.nchunks = p0.nchunks;
+    a.rowpx = p0.rowpx;
+    a.K = K;
+    a.mh = mh;
+    a.slotBytes = p0.slotBytes;
+    a.nmirror = K - 1;
+    a.biasFolded = p0.biasFolded;
+    a.biasB16 = p0.biasB16;
+    a.onesOff = p0.onesOff;
+    a.epiOff = p0.epiOff;
+    a.P = P;
+    a.Wj = first->Wo;
+    a.Hj = first->Ho;
+    a.nInPlanes = a.nOutPlanes = (d0.out_channels + 3) / 4;
+    a.epiWarps = ((a.N >> 3) % 3 == 0) ? 12 : 8;
+    if (const char *e = getenv("FYN_CHAIN_EPI")) {
+        const int want = atoi(e);
+        if (want == 8 || (want == 12 && (a.N >> 3) % 3 == 0)) a.epiWarps = want;
+    }
+    if ((a.N >> 3) / (a.epiWarps >> 2) > 4 || (a.N >> 3) % (a.epiWarps >> 2) != 0 || (a.N >> 3) < a.nchunks) {
+        delete c;
+        return chain_fail_unsupported("accumulator columns do not split over the epilogue warps");
+    }
+    bool simple = true;
+    a.rawInput = 0;
+    for (int i = 0; i < n; i++) {
+        const fyn_conv_desc &d = ops[i]->conv;
+        ChainLayer &L = a.layer[i];
+        L.act = fyn_act_from_flags(d.flags, d.leaky, d.clip_lo, d.clip_hi);
+        L.resSrc = (d.flags & FYN_FLAG_RESIDUAL_INPUT) ? 2 : 0;
+        if (L.resSrc && i == 1) a.rawInput = 1;
+        if (L.act.type > 1) simple = false;
+        L.reluRes = (d.flags & FYN_FLAG_RELU_ON_RESIDUAL) != 0;
+        L.bnRes = (d.flags & FYN_FLAG_BATCHNORM_ON_RESIDUAL) != 0;
+        L.writeRaw = (i + 2 < n && (ops[i + 2]->conv.flags & FYN_FLAG_RESIDUAL_INPUT)) ? 1 : 0;
+    }
+    a.simpleAct = simple ? 1 : 0;
+    // ring: as many slots as shared memory holds (two weight images, epilogue parameters, barriers)
+    const size_t wpad = ((size_t)a.wbytes + 127) & ~(size_t)127;
+    const size_t optin = (size_t)ctx->prop.sharedMemPerBlockOptin;
+    const size_t fixed = 2 * wpad + 64 * 16 + (2 * 24 + 8) * 8 + 16 + 128;
+    if (optin <= fixed) {
+        delete c;
+        return chain_fail_unsupported("weight images do not fit shared memory twice");
+    }
+    int total = (int)std::min<size_t>((optin - fixed) / (size_t)a.slotBytes, 16 + a.nmirror);
+    if (const char *e = getenv("FYN_CHAIN_SLOTS")) total = std::min(total, atoi(e) + a.nmirror);
+    a.nslots = std::min(24, total - a.nmirror);
+    if (a.nslots < 2 * K) {
+        delete c;
+        return chain_fail_unsupported("ring does not fit shared memory");
+    }
+    c->smemBytes = 2 * wpad + (size_t)(a.nslots + a.nmirror) * a.slotBytes + 64 * 16 + (2 * (size_t)a.nslots + 8) * 8 + 16;
+    *out = c;
+    return FYN_OK;
+}
+
+int fyn_conv_chain_layers(const fyn_conv_chain *c) { return c ? (int)c->ops.size() : 0; }
+
+int fyn_conv_chain_run(fyn_conv_chain *c, const fyn_tensor *in, fyn_tensor *out, void *stream) {
+    if (!c || !in || !out) FYN_FAIL(FYN_ERR_INVALID, "conv chain: NULL argument");
+    fyn_ctx *ctx = c->ctx;
+    const fyn_conv_desc &d0 = c->ops[0]->conv;
+    auto fits = [&](const fyn_tensor *t) {
+        return t->desc.width == d0.width && t->desc.height == d0.height && t->desc.channels == d0.in_channels && t->desc.padding == c->args.P &&
+               t->desc.order == FYN_ORDER_SHALLOW && t->desc.dtype == FYN_F16 && t->geom.packing == 4;
+    };
+    if (!fits(in) || !fits(out)) return 1;          // tensor formats the chain does not cover: run the layers one by one
+    if (in->desc.batch != out->desc.batch || in->dptr == out->dptr) FYN_FAIL(FYN_ERR_INVALID, "conv chain: input and output must be distinct tensors of one batch size");
+    FYN_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    ChainArgs a = c->args;
+    a.batch = in->desc.batch;
+    a.nxs = (a.Wj + kTileM - 1) / kTileM;
+    const int sms = ctx->prop.multiProcessorCount;
+    const long long cols = (long long)a.nxs * a.batch;
+    if (cols > sms) return 1;                        // the grid must be co-resident
+    // Strips: nG row groups (CTAs per column block) x nsub strips per CTA ("zones" of the image), strip height SH.  More
+    // zones hide more of the layer-to-layer dependency latency behind other strips' work but load more halo rows.
+    a.nG = std::max(1, (int)(sms / cols));
+    a.nsub = 2;
+    if (const char *e = getenv("FYN_CHAIN_NSUB")) a.nsub = std::max(1, std::min(8, atoi(e)));
+    int minSH = std::max(3, a.mh);               // (a segment reads from its own strip and the two next to it only: SH >= mh)
+    if (const char *e = getenv("FYN_CHAIN_SH")) minSH = std::max(std::max(1, atoi(e)), a.mh);
+    while (a.nsub > 1 && (a.Hj + a.nsub * a.nG - 1) / (a.nsub * a.nG) < minSH) a.nsub--;
+    a.SH = (a.Hj + a.nsub * a.nG - 1) / (a.nsub * a.nG);
+    if (a.SH < minSH) {
+        a.SH = std::min(minSH, a.Hj);
+        a.nG = (a.Hj + a.SH - 1) / a.SH;          // one strip per CTA
+    }
+    a.NS = a.nsub * a.nG;
+    a.pitchPx = a.nxs * kTileM + (a.rowpx - kTileM);
+    a.imgRows = a.Hj + 2 * a.P;
+    a.imgElems = (long long)a.imgRows * a.nchunks * a.pitchPx * 8;
+    const size_t imgBytes = (size_t)a.imgElems * 2 * a.batch;
+    const size_t progCount = (size_t)a.nlayers * a.NS * a.batch * a.nxs;
+    if (c->batchAlloc != a.batch) {
+        // (re)allocation synchronises; it happens on the first run and when the batch size changes
+        if (c->images) cudaFree(c->images);
+        if (c->progress) cudaFree(c->progress);
+        c->images = nullptr;
+        c->progress = nullptr;
+        FYN_CUDA(cudaMalloc((void **)&c->images, imgBytes * (kChainBufs + 1)));
+        FYN_CUDA(cudaMemset(c->images, 0, imgBytes * (kChainBufs + 1)));          // zero borders, never written afterwards
+        FYN_CUDA(cudaMalloc((void **)&c->progress, progCount * sizeof(unsigned long long)));
+        FYN_CUDA(cudaMemset(c->progress, 0, progCount * sizeof(unsigned long long)));
+        FYN_CUDA(cudaDeviceSynchronize());
+        c->batchAlloc = a.batch;
+        c->epoch = 0;
+    }
+    for (int b = 0; b < kChainBufs; b++) a.A[b] = c->images + (size_t)b * (imgBytes / 2);
+    a.R = c->images + (size_t)kChainBufs * (imgBytes / 2);
+    a.progress = c->progress;
+    a.epoch = ++c->epoch;
+    for (size_t i = 0; i < c->ops.size(); i++) a.layer[i].wimg = c->ops[i]->tc->chainImage();   // (hot-swapped weights re-pack in place)
+    a.in = fyn_make_view(in);
+    a.out = fyn_make_view(out);
+    using ChainKernel = void (*)(ChainArgs);
+    static const ChainKernel kernels[4][2] = {{k_conv_tc_chain<1, false>, k_conv_tc_chain<1, true>}, {k_conv_tc_chain<2, false>, k_conv_tc_chain<2, true>},
+                                              {k_conv_tc_chain<3, false>, k_conv_tc_chain<3, true>}, {k_conv_tc_chain<4, false>, k_conv_tc_chain<4, true>}};
+    const int noct = (a.N >> 3) / (a.epiWarps >> 2);
+    const ChainKernel fn = kernels[noct - 1][a.simpleAct ? 1 : 0];
+    {
+        // the attribute is per function and device: keep it at the largest footprint any chain has needed so far
+        static size_t cur[64][4][2] = {};
+        static std::mutex lock;
+        std::lock_guard<std::mutex> guard(lock);
+        size_t &have = cur[ctx->device & 63][noct - 1][a.simpleAct ? 1 : 0];
+        if (c->smemBytes > have) {
+            FYN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smemBytes));
+            have = c->smemBytes;
+        }
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(cols * a.nG));
+    cfg.blockDim = dim3((unsigned)((a.epiWarps + 4) * 32));
+    cfg.dynamicSmemBytes = c->smemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static const bool noPdl = getenv("FYN_TC_NO_PDL") != nullptr;
+    if (noPdl) cfg.numAttrs = 0;
+    FYN_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
+    FYN_CHECK_LAUNCH(ctx);
+    return FYN_OK;
+}
+
+int fyn_conv_chain_destroy(fyn_conv_chain *c) {
+    if (!c) return FYN_OK;
+    cudaSetDevice(c->ctx->device);
+    if (c->images) cudaFree(c->images);
+    if (c->progress) cudaFree(c->progress);
+    delete c;
+    return FYN_OK;
+}
+
+}  // extern "C"

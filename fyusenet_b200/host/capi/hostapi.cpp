@@ -336,6 +336,19 @@ int fynhost_net_fused_layers(void *handle) {
     return n;
 }
 
+// chains of same-geometry convolutions as one persistent kernel (Engine::enableChains); number of layers running in chains
+int fynhost_net_enable_chains(void *handle, int on) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] { h->net()->engine()->enableChains(on != 0); });
+}
+
+int fynhost_net_chained_layers(void *handle) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    int n = -1;
+    guarded([&] { n = h->net()->engine()->chainedLayers(); });
+    return n;
+}
+
 // like fynhost_net_enable_timings(handle, 1) but with an event pair around one layer only
 int fynhost_net_enable_layer_timing(void *handle, int layerNumber) {
     NetHandle *h = static_cast<NetHandle *>(handle);

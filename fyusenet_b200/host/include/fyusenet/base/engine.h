@@ -60,6 +60,9 @@ class Engine : public GfxContextTracker {
     // results are written, so that every layer's dump shows that layer's own output.
     void enableFusion(bool on) { fusion_ = on; updateFusion(); }
     int fusedLayers() const { return fusedLayers_; }
+    // chains of same-geometry convolutions as one persistent kernel (part of the fusion switch; separately switchable)
+    void enableChains(bool on) { chainFusion_ = on; updateFusion(); }
+    int chainedLayers() const { return chainedLayers_; }
     // Synchronous path: capture the device layers (everything between the upload and the download layer) into a CUDA graph on
     // the next forward and replay it afterwards; re-captured when tensor bindings, weights or fusions change.  Suspended
     // while timings, dumps or a halo exchange are active.
@@ -111,8 +114,11 @@ class Engine : public GfxContextTracker {
     int timingOnly_ = -1;
     bool writeResults_ = false;
     bool fusion_ = true;
-    int fusedLayers_ = 0;
+    int fusedLayers_ = 0, chainedLayers_ = 0;
     void updateFusion();
+    void updateChains(bool want);
+    std::vector<fyn_conv_chain *> chains_;   // persistent multi-layer convolution kernels (fyn_conv_chain), owned here
+    bool chainFusion_ = true;
     bool useGraph_ = false;
     void *graphExec_ = nullptr;
     uint64_t graphEpoch_ = 0;

@@ -50,9 +50,22 @@ class ConvLayerBase : public GPULayerBase, public ConvLayerInterface {
     bool fuseInputNorm(const float *scaleAndBias, TensorHandle source);
     void unfuseInput();
     bool inputFused() const { return fusedInput_ != nullptr; }
+    // Chain fusion (Engine::updateFusion, fyn_conv_chain): the first layer of a run of convolutions of identical geometry
+    // launches one persistent kernel for the whole run and writes the last layer's output tensor; the other layers of
+    // the run do nothing in forward().  If the chain declines the tensors at run time, the layers run one by one.
+    fyn_op *op() const { return op_; }
+    TensorHandle residualTexture() const { return residuals_.empty() ? nullptr : residuals_[0]; }
+    void setChainHead(fyn_conv_chain *chain, const std::vector<ConvLayerBase *> &followers);
+    void setChainMember(bool on) { chainMember_ = on; }
+    void unchain();
+    bool chained() const { return chain_ != nullptr || chainMember_; }
 
  protected:
     void init(int kernel, int dilation, float sourceStep, bool fractional);
+    void forwardSingle();
+    fyn_conv_chain *chain_ = nullptr;                 // owned by the engine
+    std::vector<ConvLayerBase *> chainFollowers_;
+    bool chainMember_ = false;
     int fusedFunction_ = 0;
     TensorHandle fusedTarget_ = nullptr;
     TensorHandle fusedInput_ = nullptr;

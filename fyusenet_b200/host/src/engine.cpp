@@ -62,6 +62,82 @@ void Engine::updateFusion() {
             fusedLayers_++;
         }
     }
+    // (row-banded operation refreshes the margins after every layer: no chains there)
+    updateChains(want && chainFusion_ && !haloComm_ && getenv("FYN_NO_CHAIN") == nullptr);
+}
+
+// Runs of consecutive shallow convolutions of identical geometry (StyleNet: res1_1 ... res5_2) -> one persistent kernel
+// (fyn_conv_chain).  A run qualifies when layer i+1 reads layer i's output on port 0, a residual input is the tensor the
+// previous layer of the run reads, layer numbers are consecutive and no tensor inside the run has a reader outside of it.
+// fyn_conv_chain_create decides whether the kernels can do it; everything else keeps running layer by layer.
+void Engine::updateChains(bool want) {
+    for (auto it = layers_.begin(); it != layers_.end(); ++it)
+        if (auto *conv = dynamic_cast<gpu::ConvLayerBase *>(it.second)) conv->unchain();
+    for (fyn_conv_chain *c : chains_) fyn_conv_chain_destroy(c);
+    chains_.clear();
+    chainedLayers_ = 0;
+    if (!want) return;
+    std::vector<gpu::ConvLayerBase *> convs;
+    for (auto it = layers_.begin(); it != layers_.end(); ++it) convs.push_back(dynamic_cast<gpu::ConvLayerBase *>(it.second));
+    size_t i = 0;
+    while (i < convs.size()) {
+        gpu::ConvLayerBase *head = convs[i];
+        if (!head || !head->op() || head->fused() || head->inputFused() || !head->hasInputTexture(0) || !head->hasOutputTexture(0) ||
+            (head->getFlags() & LayerFlags::RESIDUAL_INPUT)) {
+            i++;
+            continue;
+        }
+        std::vector<gpu::ConvLayerBase *> run{head};
+        std::vector<int> resFrom{-2};
+        while (i + run.size() < convs.size()) {
+            gpu::ConvLayerBase *prev = run.back(), *next = convs[i + run.size()];
+            if (!next || !next->op() || next->fused() || next->inputFused() || next->getNumber() != prev->getNumber() + 1 || !next->hasInputTexture(0) ||
+                !next->hasOutputTexture(0) || next->getInputTexture(0) != prev->getOutputTexture(0))
+                break;
+            {
+                // same geometry as the head (fyn_conv_chain_create checks the rest: plans, flags, padding)
+                const fyn_conv_desc &a = head->descriptor(), &b = next->descriptor();
+                if (a.width != b.width || a.height != b.height || a.in_channels != b.in_channels || a.out_channels != b.out_channels || a.kernel != b.kernel ||
+                    a.downsample != b.downsample || a.fractional != b.fractional || a.dilation != b.dilation)
+                    break;
+            }
+            int rf = -2;
+            if (next->getFlags() & LayerFlags::RESIDUAL_INPUT) {
+                // the residual must be the tensor the previous layer of the run reads
+                if (next->residualTexture() != prev->getInputTexture(0)) break;
+                rf = (int)run.size() - 2;
+            }
+            run.push_back(next);
+            resFrom.push_back(rf);
+        }
+        // Longest prefix of the run that (a) keeps every tensor inside it private -- no layer outside may read the output of
+        // any layer but the last -- and (b) the chain kernel accepts.
+        auto closed = [&](size_t len) {
+            for (size_t k = 0; k + 1 < len; k++)
+                for (auto &rcv : run[k]->receivers()) {
+                    bool inside = false;
+                    for (size_t m = 0; m < len; m++) inside = inside || run[m] == rcv.first;
+                    if (!inside) return false;
+                }
+            return true;
+        };
+        bool done = false;
+        for (size_t len = run.size(); len >= 2 && !done; len--) {
+            if (!closed(len)) continue;
+            std::vector<fyn_op *> ops;
+            for (size_t k = 0; k < len; k++) ops.push_back(run[k]->op());
+            fyn_conv_chain *chain = nullptr;
+            if (fyn_conv_chain_create(context_.handle(), ops.data(), resFrom.data(), (int)len, &chain) == 0) {
+                chains_.push_back(chain);
+                head->setChainHead(chain, std::vector<gpu::ConvLayerBase *>(run.begin() + 1, run.begin() + (long)len));
+                for (size_t k = 1; k < len; k++) run[k]->setChainMember(true);
+                chainedLayers_ += (int)len;
+                i += len;
+                done = true;
+            }
+        }
+        if (!done) i++;
+    }
 }
 
 void Engine::dropGraph() {
@@ -76,6 +152,7 @@ void Engine::setHaloExchange(fyn_comm *comm, int marginRows, int inputHeight) {
     haloComm_ = comm;
     haloMargin_ = marginRows;
     haloInputHeight_ = inputHeight;
+    updateFusion();
     if (!comm) return;
     if (async_) THROW_EXCEPTION_ARGS(FynException, "Row-banded operation is synchronous");
     if (marginRows <= 0 || marginRows % 4 || inputHeight <= 0)
@@ -108,6 +185,7 @@ void Engine::cleanup() {
     if (setup_) {
         if (async_) finish();
         FYN_ABI_CALL(fyn_stream_sync(context_.handle(), context_.stream()));
+        updateChains(false);
         collectTimings(false);
         for (void *e : freeEvents_) fyn_event_destroy(context_.handle(), e);
         freeEvents_.clear();

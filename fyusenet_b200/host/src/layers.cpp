@@ -138,6 +138,35 @@ void ConvLayerBase::cleanup() {
 
 void ConvLayerBase::forward(uint64_t) {
     if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
+    if (chainMember_) return;                          // the head of the chain has computed this layer's output
+    if (chain_) {
+        std::lock_guard<std::recursive_mutex> lck(processingLock_);
+        ConvLayerBase *last = chainFollowers_.back();
+        const int rc = fyn_conv_chain_run(chain_, in(0), last->out(), context_.stream());
+        if (rc == 0) return;
+        if (rc != 1) FYN_ABI_CALL(rc);
+        // tensor formats the chain does not cover (e.g. fp32 storage): the layers run one by one
+        forwardSingle();
+        for (ConvLayerBase *f : chainFollowers_) f->forwardSingle();
+        return;
+    }
+    forwardSingle();
+}
+
+void ConvLayerBase::setChainHead(fyn_conv_chain *chain, const std::vector<ConvLayerBase *> &followers) {
+    chain_ = chain;
+    chainFollowers_ = followers;
+    graphEpoch()++;
+}
+
+void ConvLayerBase::unchain() {
+    if (chain_ || chainMember_) graphEpoch()++;
+    chain_ = nullptr;
+    chainFollowers_.clear();
+    chainMember_ = false;
+}
+
+void ConvLayerBase::forwardSingle() {
     std::lock_guard<std::recursive_mutex> lck(processingLock_);
     TensorHandle res = nullptr;
     if (flags_ & LayerFlags::RESIDUAL_INPUT) {

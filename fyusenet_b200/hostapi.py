@@ -168,6 +168,14 @@ class Network:
     def fused_layers(self) -> int:
         return lib().fynhost_net_fused_layers(self._h)
 
+    def enable_chains(self, on=True):
+        """Runs of same-geometry convolutions as one persistent kernel (Engine::enableChains); on by default."""
+        _check(lib().fynhost_net_enable_chains(self._h, int(bool(on))))
+
+    @property
+    def chained_layers(self) -> int:
+        return lib().fynhost_net_chained_layers(self._h)
+
     def enable_timings(self, on=True):
         _check(lib().fynhost_net_enable_timings(self._h, int(on)))
 

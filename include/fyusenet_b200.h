@@ -246,6 +246,22 @@ int fyn_conv2d_backend(const fyn_op *op);
 #define FYN_EPILOGUE_SIGMOID 1
 int fyn_conv2d_set_epilogue(fyn_op *op, int function);
 
+/* Persistent chain of shallow convolutions (engine-level fusion; no counterpart in the reference, which renders every layer
+ * with its own blend passes: fyusenet/gpu/vanilla/convlayerNxN_vanilla.cpp:72-145 and, for the residual input,
+ * shaders/vanilla/residual.inc).  `ops` = n >= 2 convolution ops of identical geometry (stride 1, as many outputs as inputs,
+ * tensor padding = kernel / 2) that run on the shallow tcgen05 family, layer i+1 reading layer i's output;
+ * residual_from[i] names the layer whose output layer i adds as its residual: it must be i - 2, where -1 stands for the
+ * chain input (ignored for layers without FYN_FLAG_RESIDUAL_INPUT).  One kernel launch runs all layers: a strip of layer
+ * i+1 waits only for the neighbouring strips of layer i.  Results are bit-identical to running the ops one by one.  The ops
+ * stay owned by the caller and must outlive the chain; their weights may be hot-swapped (fyn_conv2d_load_weights).
+ * fyn_conv_chain_create returns FYN_ERR_UNSUPPORTED when the layers cannot be chained; fyn_conv_chain_run returns 1
+ * (nothing enqueued) when the tensors' formats or batch size are not covered -- run the ops one by one then. */
+typedef struct fyn_conv_chain fyn_conv_chain;
+int fyn_conv_chain_create(fyn_ctx *ctx, fyn_op *const *ops, const int *residual_from, int n, fyn_conv_chain **chain);
+int fyn_conv_chain_layers(const fyn_conv_chain *chain);
+int fyn_conv_chain_run(fyn_conv_chain *chain, const fyn_tensor *in, fyn_tensor *out, void *stream);
+int fyn_conv_chain_destroy(fyn_conv_chain *chain);
+
 /* Diagnostics (no device needed): the shared-memory plan the tcgen05 family would use for `desc`.  `stack_rows` = 1 or 2
  * job rows per accumulator.  Returns FYN_ERR_UNSUPPORTED if the family does not cover the layer (the direct kernel runs
  * it).  Used by the device-free planner tests and by tools. */

@@ -197,18 +197,27 @@ def test_stylenet_layer_fusion():
     net.load_weights(weights)
     net.setup()
     assert net.fused_layers == 1
+    assert net.chained_layers == 10              # res1_1 ... res5_2 run as one persistent kernel (fyn_conv_chain)
     net.set_input(img)
     net.forward()
     fused = net.output_rgba()[0].copy()
     net.enable_fusion(False)
-    assert net.fused_layers == 0
+    assert net.fused_layers == 0 and net.chained_layers == 0
     net.forward()
     np.testing.assert_array_equal(net.output_rgba()[0], fused)
     net.enable_fusion(True)
-    assert net.fused_layers == 1
+    assert net.fused_layers == 1 and net.chained_layers == 10
+    net.enable_chains(False)                     # the chain alone
+    assert net.fused_layers == 1 and net.chained_layers == 0
+    net.forward()
+    np.testing.assert_array_equal(net.output_rgba()[0], fused)
+    net.enable_chains(True)
+    for _ in range(3):
+        net.forward()
+        np.testing.assert_array_equal(net.output_rgba()[0], fused)
     with tempfile.TemporaryDirectory() as d:
         net.enable_dumps(d)                      # every layer must show its own output again
-        assert net.fused_layers == 0
+        assert net.fused_layers == 0 and net.chained_layers == 0
         net.forward()
         np.testing.assert_array_equal(net.output_rgba()[0], fused)
     net.destroy()
@@ -533,4 +542,25 @@ def test_halo_exchange_single_rank_is_a_no_op():
     np.testing.assert_array_equal(net.output_rgba()[0], want)
     net.set_halo_exchange(None, 0, 0)
     comm.destroy()
+    net.destroy()
+
+
+def test_stylenet_chain_headline_size_is_exact():
+    """BASELINE configs[1] (StyleNet 9x9, 1524x1856): the residual trunk as one persistent kernel (141 co-resident CTAs, ten
+    layers, cross-CTA row dependencies) gives the same frame, bit for bit, as the layers launched one by one -- repeatedly."""
+    weights = fo.stylenet_synthetic_weights(9)
+    w, h = 1524, 1856
+    img = fo.synthetic_image(h, w, 12)
+    net = hostapi.StyleNet(9, w, h)
+    net.load_weights(weights)
+    net.setup()
+    assert net.chained_layers == 10
+    net.set_input(img)
+    net.enable_chains(False)
+    net.forward()
+    want = net.output_rgba()[0].copy()
+    net.enable_chains(True)
+    for _ in range(5):
+        net.forward()
+        np.testing.assert_array_equal(net.output_rgba()[0], want)
     net.destroy()
