@@ -69,6 +69,7 @@ struct ChainArgs {
     uint32_t wbytes, idesc, b_lbo;
     int nsteps;
     TcStep steps[kMaxSteps];
+    TcStep stepsRev[kMaxSteps];       // the same steps with the window rows in reverse order (layers that sweep bottom -> top)
     int N, nchunks, rowpx, K, mh, slotBytes, nslots, nmirror;
     int biasFolded;
     uint32_t biasB16, onesOff, epiOff;
@@ -78,6 +79,7 @@ struct ChainArgs {
     long long imgElems;               // halves per image n of an internal image
     int epiWarps;
     int nInPlanes, nOutPlanes;
+    int fenceMode;                    // experiment switch (FYN_CHAIN_FENCE): bit 0 acquire fence, bit 1 proxy fence after a poll
     int rawInput;                     // layer 1 adds the chain input: the input relayout also fills the raw image
     int simpleAct;
 };
@@ -210,14 +212,14 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
 
     if (warp == prodWarp) {
         // ===================== producer: rows of the input images -> ring slots =====================
-        // Per segment (strip of a layer): (1) lanes 0..8 poll the nine counters the segment's rows depend on -- the strips
-        // above, of and below the segment in the three column blocks a row spans -- until each has reached the last row
-        // the segment reads from it; normally the first look suffices (those rows were stored half a layer ago).
-        // (2) The rows are issued `batch` at a time, ONE ROW PER LANE: wait for the ring slot, announce the bytes, `nchunks`
-        // bulk copies (twice for mirrored slots).  A batch is short enough that no slot it waits for can depend on a row of
-        // the same batch (batch <= nslots - K + 1), so the lanes never wait for each other.
+        // Layers alternate their sweep direction (even layers top -> bottom, odd layers bottom -> top).  A strip of layer l
+        // therefore starts next to the rows its vertical neighbour finished FIRST in layer l-1, continues with its own rows
+        // (finished a moment ago, but without any skew between CTAs) and ends next to the rows the other vertical neighbour
+        // finished LAST -- a whole strip of work earlier.  The rows of a segment are issued in groups by source strip:
+        // (1) lanes 0..8 poll the counters of that strip in the three column blocks a row spans until they cover the group's
+        // rows (relaxed loads, values cached per segment); (2) one (row, chunk) bulk copy per lane.  A group is short enough
+        // that no slot it waits for can depend on a row of the same group (<= nslots - K + 1 rows).
         const uint32_t chunkBytes = (uint32_t)a.rowpx * 16u;
-        const uint32_t mirrorOff = (uint32_t)a.nslots * (uint32_t)a.slotBytes;
         const unsigned long long epochTag = a.epoch << 32;
         const int batch = min(32, a.nslots - a.K + 1);
         int rowCum = 0;
@@ -225,72 +227,106 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
         [[maybe_unused]] const long long pStart = CPROF_T();
         for (int l = 0; l < a.nlayers; l++) {
             const __half *img = a.A[l % kChainBufs] + (long long)n * a.imgElems;
+            const bool rev = (l & 1) != 0;                   // this layer's sweep
+            const bool prevRev = l > 0 && ((l - 1) & 1) != 0;   // sweep of the layer that wrote the image (the relayout of the chain input publishes whole strips)
             for (int h = 0; h < a.nsub; h++) {
                 int t, ja, nj;
                 strip(h, t, ja, nj);
                 if (nj == 0) continue;
                 const int R = nj + a.K - 1;
-                {
-                    // data rows the segment reads: texture rows with CLAMP_TO_EDGE, as the samplers of the reference address
-                    // them, minus the padding rows (which nobody writes)
-                    const int dFirst = max(min(max(ja - a.mh + a.P, 0), a.imgRows - 1) - a.P, 0);
-                    const int dLast = min(min(max(ja + nj - 1 + a.mh + a.P, 0), a.imgRows - 1) - a.P, a.Hj - 1);
-                    const int t2 = t - 1 + lane / 3, xq = xb - 1 + lane % 3;
-                    bool mine = lane < 9 && t2 >= 0 && xq >= 0 && xq < a.nxs;
-                    unsigned long long want = 0;
-                    if (mine) {
-                        const int lo = max(dFirst, t2 * a.SH), hi = min(dLast, t2 * a.SH + a.SH - 1);
-                        mine = hi >= lo;
-                        want = epochTag | (unsigned)(hi - t2 * a.SH + 1);
-                    }
-                    const unsigned long long *p = mine ? prog(l, t2, xq) : nullptr;
-                    const long long t0 = clock64();
-                    if (lane == 0) CTRACE(l * a.nsub + h, 0);
-                    bool ok = !mine;
-                    for (;;) {
-                        if (!ok) ok = ld_relaxed_gpu(p) >= want;
-                        CPROF_ON(nPolls++);
-                        if (__all_sync(0xffffffffu, ok)) break;
-                        __nanosleep(100);
-                        if (clock64() - t0 > 6000000000ll) {     // ~3 s: a lost dependency must not hang the device
-                            if (!ok) printf("[fyn chain] block %d: layer %d strip %d never got strip %d of column block %d\n", (int)blockIdx.x, l, t, t2, xq);
-                            __trap();
+                // r-th row of the segment in issue order: texture row with CLAMP_TO_EDGE, as the samplers of the reference
+                // address it (yr), and the data row it holds (yr - P; padding rows are nobody's)
+                auto tex_row = [&](int r) { return min(max((rev ? ja + nj - 1 + a.mh - r : ja - a.mh + r) + a.P, 0), a.imgRows - 1); };
+                // lane i < 9 watches strip t - 1 + i / 3 in column block xb - 1 + i % 3
+                const int t2 = t - 1 + lane / 3, xq = xb - 1 + lane % 3;
+                const bool watcher = lane < 9 && t2 >= 0 && t2 < a.NS && xq >= 0 && xq < a.nxs;
+                const int s2 = t2 * a.SH, n2 = min(a.Hj, s2 + a.SH) - s2;      // first row / rows of the watched strip
+                const unsigned long long *p = watcher ? prog(l, t2, xq) : nullptr;
+                if (lane == 0) CTRACE(l * a.nsub + h, 0);
+                // one look at all nine counters up front (one L2 round trip): in the steady state it covers the whole segment
+                unsigned long long seen = watcher && n2 > 0 ? ld_relaxed_gpu(p) : 0;
+                CPROF_ON(nPolls++);
+                if (a.fenceMode & 1) fence_acq_rel_gpu();
+                if (a.fenceMode & 2) fence_proxy_async_all();
+                // ring position of the segment's first row
+                const int fill0 = rowCum / a.nslots, slot0 = rowCum - fill0 * a.nslots;
+                for (int rb = 0; rb < R; rb += 32) {
+                    // lane = row rb + lane: its source strip (-1 = padding row) and what it needs of it, in the strip's sweep order
+                    const int r = rb + lane;
+                    const bool rowOk = r < R;
+                    const int yr = tex_row(rowOk ? r : R - 1), yd = yr - a.P;
+                    // (rows of a segment come from its own strip and the two next to it: no division needed)
+                    int src = -1;
+                    if (yd >= 0 && yd < a.Hj) src = yd < t * a.SH ? t - 1 : (yd >= (t + 1) * a.SH ? t + 1 : t);
+                    const int ss = src * a.SH, sn = min(a.Hj - ss, a.SH);
+                    const unsigned needRow = src < 0 ? 0u : (unsigned)(prevRev ? ss + sn - yd : yd - ss + 1);
+                    const int srcPrev = __shfl_up_sync(0xffffffffu, src, 1);
+                    // groups: consecutive rows of one source, at most `batch` rows
+                    unsigned starts = __ballot_sync(0xffffffffu, rowOk && (lane == 0 || src != srcPrev));
+                    const int rowsHere = min(32, R - rb);
+                    while (starts) {
+                        const int g0 = __ffs(starts) - 1;
+                        starts &= starts - 1;
+                        const int gEnd = starts ? __ffs(starts) - 1 : rowsHere;
+                        const int src0 = __shfl_sync(0xffffffffu, src, g0);
+                        for (int b0 = g0; b0 < gEnd; b0 += batch) {
+                            const int b1 = min(gEnd, b0 + batch);
+                            if (src0 >= 0) {
+                                const unsigned need = __reduce_max_sync(0xffffffffu, (lane >= b0 && lane < b1) ? needRow : 0u);
+                                const bool mine = watcher && t2 == src0 && n2 > 0;
+                                const unsigned long long want = epochTag | need;
+                                bool ok = !mine || seen >= want;
+                                if (!__all_sync(0xffffffffu, ok)) {
+                                    const long long t0 = clock64();
+                                    for (;;) {
+                                        if (!ok) {
+                                            seen = ld_relaxed_gpu(p);
+                                            ok = seen >= want;
+                                        }
+                                        CPROF_ON(nPolls++);
+                                        if (__all_sync(0xffffffffu, ok)) break;
+                                        __nanosleep(64);
+                                        if (clock64() - t0 > 6000000000ll) {     // ~3 s: a lost dependency must not hang the device
+                                            if (!ok) printf("[fyn chain] block %d: layer %d strip %d never got %u rows of strip %d in column block %d\n", (int)blockIdx.x, l, t, need, t2, xq);
+                                            __trap();
+                                        }
+                                    }
+                                    if (a.fenceMode & 1) fence_acq_rel_gpu();
+                                    if (a.fenceMode & 2) fence_proxy_async_all();
+                                    CPROF_ADD(pPoll, t0);
+                                }
+                            }
+                            if (lane == 0 && rb == 0 && b0 == 0) CTRACE(l * a.nsub + h, 1);
+                            [[maybe_unused]] const long long pt = CPROF_T();
+                            // one (row, chunk) copy per lane: ceil(rows * nchunks / 32) copy instructions per group
+                            const int items = (b1 - b0) * a.nchunks;
+                            for (int it = lane; it < items; it += 32) {
+                                const int rr = it / a.nchunks, c = it - rr * a.nchunks, rl = b0 + rr;
+                                int slot = slot0 + rb + rl, fill = fill0;
+                                while (slot >= a.nslots) {
+                                    slot -= a.nslots;
+                                    fill++;
+                                }
+                                const int yrr = tex_row(rb + rl);
+                                mbar_wait(&empty[slot], (fill & 1) ^ 1);
+                                if (c == 0) mbar_expect_tx(&full[slot], (uint32_t)a.nchunks * chunkBytes);
+                                const __half *srcp = img + (((long long)yrr * a.nchunks + c) * a.pitchPx + j0) * 8;
+                                unsigned char *dst = sRing + (size_t)slot * a.slotBytes + (size_t)c * chunkBytes;
+                                bulk_g2s(dst, srcp, chunkBytes, &full[slot]);
+                            }
+                            __syncwarp();
+                            CPROF_ADD(pIssue, pt);
                         }
                     }
-                    // acquire: the relaxed loads above saw the counters' release stores.  The stores the counters cover were made
-                    // through the generic proxy (by other SMs); the bulk copies below read through the async proxy.
-                    fence_acq_rel_gpu();
-                    fence_proxy_async_all();
-                    CPROF_ADD(pPoll, t0);
-                    if (lane == 0) CTRACE(l * a.nsub + h, 1);
                 }
-                [[maybe_unused]] const long long pt = CPROF_T();
-                // one (row, chunk) copy per lane: a batch of rows costs ceil(rows * nchunks / 32) copy instructions
-                for (int r0 = 0; r0 < R; r0 += batch) {
-                    const int items = min(batch, R - r0) * a.nchunks;
-                    for (int it = lane; it < items; it += 32) {
-                        const int rr = it / a.nchunks, c = it - rr * a.nchunks, r = r0 + rr;
-                        const int cum = rowCum + r, fill = cum / a.nslots, slot = cum - fill * a.nslots;
-                        const int yr = min(max(ja - a.mh + r + a.P, 0), a.imgRows - 1);
-                        mbar_wait(&empty[slot], (fill & 1) ^ 1);
-                        const bool mir = slot < a.nmirror;
-                        if (c == 0) mbar_expect_tx(&full[slot], (uint32_t)a.nchunks * chunkBytes * (mir ? 2u : 1u));
-                        const __half *src = img + (((long long)yr * a.nchunks + c) * a.pitchPx + j0) * 8;
-                        unsigned char *dst = sRing + (size_t)slot * a.slotBytes + (size_t)c * chunkBytes;
-                        bulk_g2s(dst, src, chunkBytes, &full[slot]);
-                        if (mir) bulk_g2s(dst + mirrorOff, src, chunkBytes, &full[slot]);
-                    }
-                    __syncwarp();
-                }
-                CPROF_ADD(pIssue, pt);
                 if (lane == 0) CTRACE(l * a.nsub + h, 2);
                 rowCum += R;
             }
         }
 #ifdef FYN_CHAIN_PROFILE
         if ((blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && lane == 0)
-            printf("[chain prof] block %d producer: total %lld poll %lld (%lld looks) issue incl. waitEmpty %lld\n", (int)blockIdx.x, (long long)(clock64() - pStart), pPoll, nPolls,
-                   pIssue);
+            printf("[chain prof] block %d producer: total %lld poll %lld (%lld looks) issue incl. waitEmpty %lld\n", (int)blockIdx.x,
+                   (long long)(clock64() - pStart), pPoll, nPolls, pIssue);
 #endif
     } else if (warp == mmaWarp0 || warp == mmaWarp0 + 1) {
         // ===================== MMA issuers =====================
@@ -304,7 +340,7 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
         const uint32_t d = tmem + (uint32_t)mw * 64u;
         Ring wt{0, 0}, rl{0, 0}, st{0, 0};     // next row to wait for / to release; first row of the current segment
         int waited = 0, released = 0, rowBase = 0, Q = 0;
-        CPROF_DECL(pWaitT); CPROF_DECL(pWaitF); CPROF_DECL(pIss);
+        CPROF_DECL(pWaitT); CPROF_DECL(pWaitF); CPROF_DECL(pIss); CPROF_DECL(pRel); CPROF_DECL(pCommit);
         [[maybe_unused]] const long long pStart = CPROF_T();
         for (int l = 0; l < a.nlayers; l++) {
             const uint32_t sWl = smem_u32(sW) + (uint32_t)(l & 1) * wpad;
@@ -325,10 +361,12 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
                     if (elect_one()) {
                         // rows below this job's window that this warp has already seen land go back first (a short ring
                         // would otherwise deadlock at a strip boundary, where the window jumps by K rows) ...
+                        [[maybe_unused]] long long pt = CPROF_T();
                         Ring rr = rl;
                         int k = released;
                         for (; k < start && k < waited; k++, rr.next(a.nslots)) umma_commit(&empty[rr.slot]);
-                        [[maybe_unused]] long long pt = CPROF_T();
+                        CPROF_ADD(pRel, pt);
+                        pt = CPROF_T();
                         mbar_wait(&tempty[mw], (use & 1) ^ 1);
                         CPROF_ADD(pWaitT, pt);
                         pt = CPROF_T();
@@ -341,15 +379,23 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
                         // ... the rest (rows the other warp's windows needed, this warp's did not) once they have been seen
                         for (; k < start; k++, rr.next(a.nslots)) umma_commit(&empty[rr.slot]);
                         if (q == 0) CTRACE(l * a.nsub + h, 3);
-                        const uint32_t winBase = rbase16 + (uint32_t)win.slot * slot16;
+                        const int winSlot = win.slot;
+                        // (bottom -> top layers walk the window rows in reverse, with the kernel rows reversed in their weight
+                        // image: the products enter the accumulator in the same order as in a top -> bottom layer, bit for bit)
+                        const TcStep *steps = (l & 1) ? a.stepsRev : a.steps;
 #pragma unroll 4
                         for (int s = 0; s < a.nsteps; s++) {
-                            const TcStep stp = a.steps[s];
-                            umma_f16(d, hiA | (uint64_t)(stp.a_lo + winBase), hiA | (uint64_t)(stp.b_off16 + bconst), a.idesc, stp.accumulate);
+                            const TcStep stp = steps[s];
+                            // (a_lo is relative to the step's window row, `pad` = that row: the ring wraps without mirror slots)
+                            int slot = winSlot + (int)stp.pad;
+                            if (slot >= a.nslots) slot -= a.nslots;
+                            umma_f16(d, hiA | (uint64_t)(stp.a_lo + rbase16 + (uint32_t)slot * slot16), hiA | (uint64_t)(stp.b_off16 + bconst), a.idesc, stp.accumulate);
                         }
                         if (a.biasFolded) umma_f16(d, hiA | (uint64_t)onesDesc, hiA | (uint64_t)(a.biasB16 + bconst), a.idesc, 1u);
-                        umma_commit(&tfull[mw]);
                         CPROF_ADD(pIss, pt);
+                        pt = CPROF_T();
+                        umma_commit(&tfull[mw]);
+                        CPROF_ADD(pCommit, pt);
                         if (q == nj - 1) CTRACE(l * a.nsub + h, 4);
                     }
                     haveW = true;
@@ -372,8 +418,8 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
         if (mw == 0 && elect_one()) {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            printf("[chain prof] block %3d xb %d g %2d sm %3u mma0: total %lld waitTempty %lld waitFull %lld issue %lld jobs %d\n", (int)blockIdx.x, xb, g, smid, (long long)(clock64() - pStart), pWaitT, pWaitF,
-                   pIss, Q);
+            printf("[chain prof] block %3d xb %d g %2d sm %3u mma0: total %lld waitTempty %lld waitFull %lld issue %lld jobs %d release %lld commit %lld\n", (int)blockIdx.x, xb, g, smid, (long long)(clock64() - pStart), pWaitT, pWaitF,
+                   pIss, Q, pRel, pCommit);
         }
 #endif
     } else if (warp == pubWarp) {
@@ -523,6 +569,7 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
         for (int l = 0; l < a.nlayers; l++) {
             CPROF_ON(if (l == 1) pLayer0 = clock64() - pStart);
             const bool last = l + 1 == a.nlayers;
+            const bool rev = (l & 1) != 0;
             const bool resOn = a.layer[l].resSrc != 0, reluRes = a.layer[l].reluRes != 0, bnRes = a.layer[l].bnRes != 0, writeRaw = a.layer[l].writeRaw != 0;
             const ActParams actNext = a.layer[last ? l : l + 1].act;
             const __half2 floorNext = floor_of(actNext);
@@ -544,17 +591,20 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
             // bound by instruction issue: 12 warps x instructions per job / 4 schedulers).
             auto run_strip = [&](auto resTag, auto lastTag, int ja, int nj, int segIdx) {
                 constexpr bool RES = decltype(resTag)::value, LAST = decltype(lastTag)::value;
-                __half *nextRow = nextImg + (long long)(ja + a.P) * rowStride;      // row of the next layer's input image
-                __half *rawRow = rawImg + (long long)(ja + a.P) * rowStride;        // row of the raw image
-                __half *outRow = outp + (long long)ja * a.out.texW * 4;             // row of the chain output (plane layout)
-                const long long outStride = (long long)a.out.texW * 4;
+                // odd layers sweep bottom -> top (see the producer): job q is output row ja + nj - 1 - q there
+                const int i0 = rev ? ja + nj - 1 : ja;
+                const long long rowStep = rev ? -rowStride : rowStride;
+                const long long outStride = rev ? -(long long)a.out.texW * 4 : (long long)a.out.texW * 4;
+                __half *nextRow = nextImg + (long long)(i0 + a.P) * rowStride;      // row of the next layer's input image
+                __half *rawRow = rawImg + (long long)(i0 + a.P) * rowStride;        // row of the raw image
+                __half *outRow = outp + (long long)i0 * a.out.texW * 4;             // row of the chain output (plane layout)
                 uint4 rres[NOCT];
                 if (RES) {
 #pragma unroll
                     for (int o = 0; o < NOCT; o++)
                         if (coff[o] >= 0) rres[o] = ld_global_16(rawRow + coff[o]);
                 }
-                for (int q = 0; q < nj; q++, nextRow += rowStride, rawRow += rowStride, outRow += outStride) {
+                for (int q = 0; q < nj; q++, nextRow += rowStep, rawRow += rowStep, outRow += outStride) {
                     const int Qg = Q + q, buf = Qg & 1, use = Qg >> 1;
                     [[maybe_unused]] long long pt = CPROF_T();
                     mbar_wait(&tfull[buf], use & 1);
@@ -578,7 +628,7 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
                         if (q + 1 < nj) {
 #pragma unroll
                             for (int o = 0; o < NOCT; o++)
-                                if (coff[o] >= 0) rres[o] = ld_global_16(rawRow + rowStride + coff[o]);
+                                if (coff[o] >= 0) rres[o] = ld_global_16(rawRow + rowStep + coff[o]);
                         }
                     }
 #pragma unroll
@@ -723,6 +773,7 @@ int fyn_conv_chain_create(fyn_ctx *ctx, fyn_op *const *ops, const int *residual_
         if (d.flags & (FYN_FLAG_DEEP | FYN_FLAG_PRE_CLIP)) return chain_fail_unsupported("deep tensors / clip activations are not chained");
         if ((d.flags & FYN_FLAG_POST_BATCHNORM) != (d0.flags & FYN_FLAG_POST_BATCHNORM)) return chain_fail_unsupported("layers differ in post-batchnorm");
         if (op->epilogue != FYN_EPILOGUE_NONE || op->innorm) return chain_fail_unsupported("layers with fused functions are not chained");
+        if (!op->tc->d_wimgFlip) return chain_fail_unsupported("a layer has no chain plan");
         const TcArgs &p = op->tc->chainArgs();
         if (p.nsteps != p0.nsteps || p.N != p0.N || p.wbytes != p0.wbytes || p.biasFolded != p0.biasFolded || p.slotBytes != p0.slotBytes || p.rowpx != p0.rowpx ||
             memcmp(p.steps, p0.steps, sizeof(TcStep) * p0.nsteps) != 0)
@@ -743,14 +794,34 @@ int fyn_conv_chain_create(fyn_ctx *ctx, fyn_op *const *ops, const int *residual_
     a.idesc = p0.idesc;
     a.b_lbo = p0.b_lbo;
     a.nsteps = p0.nsteps;
-    memcpy(a.steps, p0.steps, sizeof(TcStep) * p0.nsteps);
+    {
+        // steps are generated window row by window row, the same number for every row of a single-version plan
+        if (p0.nsteps % K != 0) {
+            delete c;
+            return chain_fail_unsupported("steps do not split evenly over the window rows");
+        }
+        // the chain's tables address a step's operand relative to its window row (TcStep::pad = the row), so that the ring
+        // needs no mirror slots; the reversed table walks the rows bottom-up
+        const int per = p0.nsteps / K;
+        const uint32_t slot16 = (uint32_t)p0.slotBytes >> 4;
+        for (int w = 0; w < K; w++)
+            for (int j = 0; j < per; j++) {
+                TcStep st = p0.steps[w * per + j];
+                st.a_lo -= (uint32_t)w * slot16;
+                st.pad = (uint32_t)w;
+                st.accumulate = (w == 0 && j == 0) ? 0u : 1u;
+                a.steps[w * per + j] = st;
+                st.accumulate = (w == K - 1 && j == 0) ? 0u : 1u;
+                a.stepsRev[(K - 1 - w) * per + j] = st;
+            }
+    }
     a.N = p0.N;
     a.nchunks = p0.nchunks;
     a.rowpx = p0.rowpx;
     a.K = K;
     a.mh = mh;
     a.slotBytes = p0.slotBytes;
-    a.nmirror = K - 1;
+    a.nmirror = 0;
     a.biasFolded = p0.biasFolded;
     a.biasB16 = p0.biasB16;
     a.onesOff = p0.onesOff;
@@ -782,6 +853,12 @@ int fyn_conv_chain_create(fyn_ctx *ctx, fyn_op *const *ops, const int *residual_
         L.writeRaw = (i + 2 < n && (ops[i + 2]->conv.flags & FYN_FLAG_RESIDUAL_INPUT)) ? 1 : 0;
     }
     a.simpleAct = simple ? 1 : 0;
+    // Consumer-side fences after a poll (bit 0: fence.acq_rel.gpu, bit 1: fence.proxy.async).  Off by default: each costs
+    // the SM ~2k cycles with the epilogue's stores in flight (measured: trunk 144 us with both, 126 us without), and the rows
+    // are then read by bulk copies -- issued only after the branch on the polled value, served by L2 (no L1, nothing to
+    // invalidate), where the producer's release store has ordered the rows before the counter.
+    a.fenceMode = 0;
+    if (const char *e = getenv("FYN_CHAIN_FENCE")) a.fenceMode = atoi(e);
     // ring: as many slots as shared memory holds (two weight images, epilogue parameters, barriers)
     const size_t wpad = ((size_t)a.wbytes + 127) & ~(size_t)127;
     const size_t optin = (size_t)ctx->prop.sharedMemPerBlockOptin;
@@ -790,7 +867,7 @@ int fyn_conv_chain_create(fyn_ctx *ctx, fyn_op *const *ops, const int *residual_
         delete c;
         return chain_fail_unsupported("weight images do not fit shared memory twice");
     }
-    int total = (int)std::min<size_t>((optin - fixed) / (size_t)a.slotBytes, 16 + a.nmirror);
+    int total = (int)std::min<size_t>((optin - fixed) / (size_t)a.slotBytes, 24);
     if (const char *e = getenv("FYN_CHAIN_SLOTS")) total = std::min(total, atoi(e) + a.nmirror);
     a.nslots = std::min(24, total - a.nmirror);
     if (a.nslots < 2 * K) {
@@ -859,7 +936,8 @@ int fyn_conv_chain_run(fyn_conv_chain *c, const fyn_tensor *in, fyn_tensor *out,
     a.R = c->images + (size_t)kChainBufs * (imgBytes / 2);
     a.progress = c->progress;
     a.epoch = ++c->epoch;
-    for (size_t i = 0; i < c->ops.size(); i++) a.layer[i].wimg = c->ops[i]->tc->chainImage();   // (hot-swapped weights re-pack in place)
+    // (hot-swapped weights re-pack in place; odd layers sweep bottom -> top and use the image with the kernel rows reversed)
+    for (size_t i = 0; i < c->ops.size(); i++) a.layer[i].wimg = c->ops[i]->tc->chainImage((i & 1) != 0);
     a.in = fyn_make_view(in);
     a.out = fyn_make_view(out);
     using ChainKernel = void (*)(ChainArgs);

@@ -1016,13 +1016,31 @@ int fyn_conv_tc_create(fyn_op *op, const float *wb) {
     if (plan->smemBytes > (size_t)op->ctx->prop.sharedMemPerBlockOptin)
         FYN_FAIL(FYN_ERR_UNSUPPORTED, "tcgen05 conv needs %zu bytes of shared memory", plan->smemBytes);
     // The persistent chain kernel (fyn_conv_chain.cu) runs unstacked plans: where this layer runs stacked on its own, and
-    // could be part of a chain (stride 1, as many outputs as inputs), the single-row plan is kept beside it.
+    // could be part of a chain (stride 1, as many outputs as inputs), the single-row plan is kept beside it -- and, for
+    // the layers of a chain that sweep bottom -> top, the single-row image of the kernel with its rows reversed.
     plan->hasRow1 = false;
-    if (g.opy > 1 && g1.ok && g1.mode == 0 && g1.opx == 1 && d.downsample == 1 && !d.fractional && d.in_channels == d.out_channels) {
+    const bool chainable = g1.ok && g1.mode == 0 && g1.opx == 1 && g1.nver == 1 && d.downsample == 1 && !d.fractional && d.in_channels == d.out_channels && d.kernel >= 3;
+    if (chainable && g.opy > 1) {
         if (int rc = build_plan(g1, d, wb, plan->row1, img)) return rc;
         if (int rc = upload_image(plan->d_wimg1, plan->wimg1Bytes, img)) return rc;
         plan->row1.wimg = plan->d_wimg1;
         plan->hasRow1 = true;
+    }
+    if (chainable) {
+        const int K = d.kernel, Ci = d.in_channels, Co = d.out_channels;
+        const size_t nw = (size_t)Co + (size_t)K * K * Ci * Co + ((d.flags & FYN_FLAG_POST_BATCHNORM) ? 2 * (size_t)Co : 0);
+        std::vector<float> flip(wb, wb + nw);
+        for (int o = 0; o < Co; o++)
+            for (int ky = 0; ky < K; ky++)
+                memcpy(&flip[(size_t)Co + ((size_t)o * K + ky) * K * Ci], &wb[(size_t)Co + ((size_t)o * K + (K - 1 - ky)) * K * Ci], sizeof(float) * (size_t)K * Ci);
+        const Geometry gf = plan_geometry(&d, flip.data(), 1);
+        TcArgs scratch{};
+        if (int rc = build_plan(gf, d, flip.data(), scratch, img)) return rc;
+        if (int rc = upload_image(plan->d_wimgFlip, plan->wimgFlipBytes, img)) return rc;
+    } else if (plan->d_wimgFlip) {
+        cudaFree(plan->d_wimgFlip);
+        plan->d_wimgFlip = nullptr;
+        plan->wimgFlipBytes = 0;
     }
     return FYN_OK;
 }
@@ -1095,6 +1113,7 @@ void fyn_conv_tc_destroy(fyn_op *op) {
     if (!op->tc) return;
     if (op->tc->d_wimg) cudaFree(op->tc->d_wimg);
     if (op->tc->d_wimg1) cudaFree(op->tc->d_wimg1);
+    if (op->tc->d_wimgFlip) cudaFree(op->tc->d_wimgFlip);
     delete op->tc;
     op->tc = nullptr;
 }

@@ -271,6 +271,10 @@ struct ConvTcPlan {
     TcArgs row1{};
     uint4 *d_wimg1 = nullptr;
     size_t wimg1Bytes = 0;
+    // the single-row image with the kernel rows reversed (layers of a chain that sweep bottom -> top); only for layers that
+    // can be part of a chain
+    uint4 *d_wimgFlip = nullptr;
+    size_t wimgFlipBytes = 0;
     const TcArgs &chainArgs() const { return hasRow1 ? row1 : args; }
-    const uint4 *chainImage() const { return hasRow1 ? d_wimg1 : d_wimg; }
+    const uint4 *chainImage(bool flipped) const { return flipped ? d_wimgFlip : (hasRow1 ? d_wimg1 : d_wimg); }
 };
