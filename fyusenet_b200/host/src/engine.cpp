@@ -9,6 +9,10 @@
 #include "fyusenet/common/performance.h"
 #include "fyusenet/gpu/cudalayers.h"
 
+// NVTX ranges per layer (the reference brackets every layer with GL debug groups / timers, base/engine.cpp:208-233,443-449):
+// header-only NVTX 3, costs nothing unless a tool is attached; FYN_NVTX=0 switches the calls off entirely
+#include <nvtx3/nvToolsExt.h>
+
 namespace fyusion {
 namespace fyusenet {
 
@@ -337,6 +341,13 @@ Engine::execstate Engine::executeAsync(uint64_t sequence) {
 Engine::execstate Engine::execute(uint64_t sequence) {
     size_t slot = 0;
     static const bool debugSyncOn = getenv("FYN_DEBUG_SYNC") != nullptr;
+    static const bool nvtxOn = !(getenv("FYN_NVTX") && atoi(getenv("FYN_NVTX")) == 0);
+    struct NvtxRange {
+        bool on;
+        NvtxRange(bool enabled, const char *name) : on(enabled) { if (on) nvtxRangePushA(name); }
+        ~NvtxRange() { if (on) nvtxRangePop(); }
+    };
+    NvtxRange sequenceRange(nvtxOn, "fyusenet forward");
     // CUDA-graph replay of the device layers (launch-latency-bound networks: ResNet-50 at batch 1 is 59 launches)
     const bool graphOk = useGraph_ && !timings_ && !writeResults_ && !haloComm_ && !debugSyncOn;
     const uint64_t epochNow = gpu::graphEpoch().load();
@@ -373,6 +384,7 @@ Engine::execstate Engine::execute(uint64_t sequence) {
             FYN_ABI_CALL(fyn_graph_launch(context_.handle(), graphExec_, context_.stream()));
             inCapture = false;
         }
+        NvtxRange layerRange(nvtxOn, layer->getName().c_str());
         if (timings_ && (timingOnly_ < 0 || timingOnly_ == it.first)) {
             if (pendingEvents_.size() >= 4096) collectTimings(true);
             void *evA = nullptr, *evB = nullptr;
