@@ -434,6 +434,7 @@ def main():
     layer_ms = {l["name"]: net.layer_timing(l["number"])[0] / args.steps for l in net.layers()}
     families = {l["name"]: l["family"] for l in net.layers()}
     net.enable_timings(False)
+    chained = net.chained_layers
     # the dominant layer once more with an event pair around it alone: the other layers then keep their dependent-launch
     # overlap, which is the situation of the timed region above
     top_name = max(layer_ms, key=layer_ms.get)
@@ -520,6 +521,42 @@ def main():
     e2e_s = time.perf_counter() - t0
     delivered = net3.async_completed()[0] - done0
     net3.destroy()
+    # (c) the same pipeline with 8-bit frames both ways (StyleNetBase::setByteIO: UBYTE upload -- a reference feature,
+    # gpu/uploadlayer.cpp:51-66 -- and RGBA8 download, the samples' host-side quantisation moved to the device): 3 + 4 instead
+    # of 12 + 16 bytes per pixel over PCIe
+    e2e8 = None
+    try:
+        net4 = hostapi.StyleNet(KSIZE, WIDTH, HEIGHT, upload=True, download=True, device=local_rank)
+        net4.asynchronous()
+        net4.set_byte_io(True)
+        net4.load_weights(weights)
+        net4.setup()
+        img8 = np.clip(img * 255.0 + 0.5, 0, 255).astype(np.uint8)
+        for k in range(hostapi.async_slots()):
+            net4.input_buffer_slot(k)[:] = img8.reshape(-1)
+        for _ in range(args.warmup):
+            net4.forward()
+        net4.finish()
+        done8 = net4.async_completed()[0]
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            net4.forward()
+        net4.finish()
+        e2e8_s = time.perf_counter() - t0
+        delivered8 = net4.async_completed()[0] - done8
+        out8 = net4.output_rgba()[0]
+        if world > 1:
+            t = torch.tensor([e2e8_s], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e8_s = float(t[0].item())
+        e2e8 = {"value": world * args.steps / e2e8_s, "unit": "frames/s", "ms_per_step": 1e3 * e2e8_s / args.steps,
+                "h2d_bytes_per_step": int(img8.nbytes), "d2h_bytes_per_step": int(out8.nbytes), "delivered": int(delivered8),
+                "nonzero": bool(out8[..., :3].any()),
+                "api": "StyleNet9x9 asynchronous() + setByteIO(): uint8 RGB frame in (value / 255 on the device), uint8 RGBA frame out"}
+        net4.destroy()
+    except Exception as exc:
+        e2e8 = {"error": repr(exc)}
     if world > 1:
         t = torch.tensor([e2e_s, sync_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -568,6 +605,12 @@ def main():
         conv_ms = {k: v for k, v in layer_ms.items() if k in alg}
         top = top_name if top_name in alg else max(conv_ms, key=conv_ms.get)
         a = alg[top]
+        members = [top]
+        if chained and top.startswith("res"):
+            # the residual trunk runs as ONE kernel (fyn_conv_chain), timed on its first layer: its algorithmic bytes / flops are
+            # those of all the layers it computes, each counted as a layer of its own (input + output + residual + weights)
+            members = [k for k in alg if k.startswith("res")]
+            a = {"bytes": sum(alg[k]["bytes"] for k in members), "flops": sum(alg[k]["flops"] for k in members)}
         t_s = (top_ms if top == top_name else conv_ms[top]) / 1e3
         ai = a["flops"] / a["bytes"]
         ridge = tf_sust * 1e12 / (hbm * 1e9)
@@ -580,13 +623,13 @@ def main():
         roof["traffic_source"] = None
         for f in sorted((ROOT / "profiles").glob("r*_top_kernel_ncu.json"), reverse=True):
             cap = json.loads(f.read_text())
-            if cap.get("layer") == top:
+            if cap.get("layer") == top and (len(members) == 1) == ("chain" not in cap.get("kernel", "")):
                 roof["traffic"] = cap["traffic_bytes_per_launch"]
                 roof["traffic_source"] = f"profiles/{f.name} (ncu --set full, one launch)"
                 break
         roof["algorithmic_bytes_per_launch"] = a["bytes"]
         roof["algorithmic_flops_per_launch"] = a["flops"]
-        roof["kernel"] = top
+        roof["kernel"] = top if len(members) == 1 else f"{members[0]} ... {members[-1]} ({len(members)} layers, one persistent kernel)"
         roof["peak_source"] = f"{which} ({'sustained' if roof['bound'] == 'tensor' else 'copy'} figure, kernel timed inside a long step)"
         roof["ms_per_launch"] = t_s * 1e3
         roof["ms_per_launch_all_layers_timed"] = conv_ms[top]
@@ -609,7 +652,8 @@ def main():
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(img.nbytes), "d2h_bytes_per_step": out_bytes,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "finite": finite, "delivered": int(delivered),
                     "api": "StyleNet9x9 asynchronous(): upload/layers/download pipelined on 3 streams, 3 sequences in flight",
-                    "sync_value": e2e_sync, "sync_ms_per_step": 1e3 * sync_s / args.steps},
+                    "sync_value": e2e_sync, "sync_ms_per_step": 1e3 * sync_s / args.steps,
+                    "byte_io": e2e8},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
@@ -617,6 +661,7 @@ def main():
                                  "gflop_per_frame": FRAME_GFLOP, "mb_per_frame": FRAME_MB},
             "layers_ms": {k: round(v, 4) for k, v in layer_ms.items()},
             "layer_kernel_family": families,
+            "chained_layers": int(chained),
             "layer_ms_sum": total_layer_ms,
             "sustained": sustained,
             "secondary": secondary,

@@ -119,7 +119,8 @@ EXPORTS = [
     "fyn_stream_wait_event", "fyn_stream_add_callback", "fyn_host_alloc", "fyn_host_free", "fyn_device_alloc", "fyn_device_free",
     "fyn_memcpy_async", "fyn_download_convert", "fyn_tensor_geometry", "fyn_tensor_create",
     "fyn_tensor_wrap", "fyn_tensor_destroy", "fyn_tensor_clear", "fyn_tensor_get_desc", "fyn_tensor_device_ptr",
-    "fyn_upload_f32_async", "fyn_download_f32_async", "fyn_download_f32_elems", "fyn_tensor_write_chw_f32",
+    "fyn_upload_f32_async", "fyn_download_f32_async", "fyn_download_f32_elems",
+    "fyn_upload_u8_async", "fyn_download_u8_bytes", "fyn_download_u8_convert", "fyn_download_u8_async", "fyn_tensor_write_chw_f32",
     "fyn_tensor_read_chw_f32", "fyn_conv2d_output_size", "fyn_conv2d_create", "fyn_conv2d_load_weights",
     "fyn_conv2d_run", "fyn_conv2d_backend", "fyn_conv2d_set_epilogue", "fyn_conv2d_set_input_norm", "fyn_conv2d_plan_query",
     "fyn_conv_chain_create", "fyn_conv_chain_layers", "fyn_conv_chain_run", "fyn_conv_chain_destroy", "fyn_pool2d_create", "fyn_pool2d_run", "fyn_batchnorm_create",
@@ -146,6 +147,7 @@ def lib():
         L.fyn_last_error.restype = C.c_char_p
         L.fyn_tensor_device_ptr.restype = C.c_void_p
         L.fyn_download_f32_elems.restype = C.c_size_t
+        L.fyn_download_u8_bytes.restype = C.c_size_t
         for name in EXPORTS:
             getattr(L, name)
         _lib = L
@@ -294,6 +296,24 @@ class Tensor:
         check(lib().fyn_download_f32_async(self._h, _fptr(out), _s(stream)))
         if sync:
             self.ctx.stream_sync(stream)
+        if d.order == ORDER_DEEP:
+            return out.reshape(d.batch, g.tex_height, g.tex_width, 4)
+        return out.reshape(d.batch, g.planes, g.tex_height, g.tex_width, 4)
+
+    def upload_u8(self, host_hwc, stream=None):
+        """UBYTE upload: uint8 [batch][H][W][C]; the tensor receives value / 255."""
+        d = self.desc
+        a = np.ascontiguousarray(host_hwc, np.uint8)
+        assert a.size == d.batch * d.height * d.width * d.channels, (a.shape, d.batch, d.height, d.width, d.channels)
+        check(lib().fyn_upload_u8_async(self._h, a.ctypes.data_as(C.POINTER(C.c_ubyte)), _s(stream)))
+        return a
+
+    def download_u8(self, stream=None) -> np.ndarray:
+        """8-bit download: (uint8)(clamp(v, 0, 1) * 255) in the texel order of download()."""
+        g, d = self.geom, self.desc
+        out = np.zeros(lib().fyn_download_u8_bytes(self._h), np.uint8)
+        check(lib().fyn_download_u8_async(self._h, out.ctypes.data_as(C.POINTER(C.c_ubyte)), _s(stream)))
+        self.ctx.stream_sync(stream)
         if d.order == ORDER_DEEP:
             return out.reshape(d.batch, g.tex_height, g.tex_width, 4)
         return out.reshape(d.batch, g.planes, g.tex_height, g.tex_width, 4)

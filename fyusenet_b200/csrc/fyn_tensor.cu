@@ -142,6 +142,61 @@ __global__ void k_download_widen(TView src, float4 *__restrict__ dst, long long 
     dst[i] = fyn_load_texel(src, i * src.packing);
 }
 
+// host-order uint8 [batch][H][W][C] (staged on the device) -> tensor interior, value / 255: the normalised 8-bit texture of an
+// UBYTE upload (gpu/uploadlayer.cpp:51-66,365-375; the samples divide by 255 on the host instead, samples/desktop/stylenet.cpp:45-47)
+__global__ void k_upload_convert_u8(const unsigned char *__restrict__ src, TView dst, int C, int batch) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    int n = blockIdx.z;
+    if (x >= dst.W || n >= batch) return;
+    const unsigned char *p = src + (((long long)n * dst.H + y) * dst.W + x) * C;
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; c++) r[c] = __fdiv_rn((float)p[c], 255.f);
+    long long idx = fyn_texel_index(dst, n, 0, dst.P + x, dst.P + y);
+    if (dst.dtype == FYN_F16) {
+        __half *o = reinterpret_cast<__half *>(dst.ptr) + idx;
+        for (int c = 0; c < dst.packing; c++) o[c] = __float2half_rn(r[c]);
+    } else {
+        float *o = reinterpret_cast<float *>(dst.ptr) + idx;
+        for (int c = 0; c < dst.packing; c++) o[c] = r[c];
+    }
+}
+
+// RGB bytes -> the unpadded RGB32F upload texture, four pixels (12 bytes in, 48 bytes out) per thread; the texture is one
+// contiguous [batch * H * W][3] array, W % 4 == 0
+__global__ void k_upload_rgb8_to_rgb32f(const uint32_t *__restrict__ src, float4 *__restrict__ dst, long long quads) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= quads) return;
+    const uint32_t w0 = __ldg(src + 3 * i), w1 = __ldg(src + 3 * i + 1), w2 = __ldg(src + 3 * i + 2);
+    auto f = [](uint32_t w, int b) { return __fdiv_rn((float)((w >> (8 * b)) & 0xffu), 255.f); };
+    dst[3 * i] = make_float4(f(w0, 0), f(w0, 1), f(w0, 2), f(w0, 3));
+    dst[3 * i + 1] = make_float4(f(w1, 0), f(w1, 1), f(w1, 2), f(w1, 3));
+    dst[3 * i + 2] = make_float4(f(w2, 0), f(w2, 1), f(w2, 2), f(w2, 3));
+}
+
+// whole tensor (including padding) -> 8-bit RGBA texels in the same texel order: (uint8)(clamp(v, 0, 1) * 255), the
+// conversion of the samples' writeImage (samples/desktop/stylenet.cpp:52-62)
+__device__ __forceinline__ uint32_t fyn_pack_rgba8(float4 v) {
+    auto q = [](float x) { return __float2uint_rz(fminf(fmaxf(x, 0.f), 1.f) * 255.f); };
+    return q(v.x) | (q(v.y) << 8) | (q(v.z) << 16) | (q(v.w) << 24);
+}
+__global__ void k_download_rgba8(TView src, uint32_t *__restrict__ dst, long long texels) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= texels) return;
+    dst[i] = fyn_pack_rgba8(fyn_load_texel(src, i * src.packing));
+}
+// fp16 RGBA tensors: four texels (32 bytes in, 16 bytes out) per thread
+__global__ void k_download_rgba8_h4(const uint4 *__restrict__ src, uint4 *__restrict__ dst, long long quads) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= quads) return;
+    const uint4 a = __ldg(src + 2 * i), b = __ldg(src + 2 * i + 1);
+    auto tex = [](uint32_t lo, uint32_t hi) {
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&lo)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
+        return fyn_pack_rgba8(make_float4(f0.x, f0.y, f1.x, f1.y));
+    };
+    dst[i] = make_uint4(tex(a.x, a.y), tex(a.z, a.w), tex(b.x, b.y), tex(b.z, b.w));
+}
+
 static int ensure_staging(fyn_tensor *t, size_t bytes) {
     if (t->staging_bytes >= bytes) return FYN_OK;
     if (t->staging) cudaFree(t->staging);
@@ -206,6 +261,53 @@ int fyn_upload_f32_async(fyn_tensor *t, const float *host, void *stream) {
     dim3 block(128), grid((d.width + 127) / 128, d.height, d.batch);
     k_upload_convert<<<grid, block, 0, s>>>((const float *)t->staging, fyn_make_view(t), d.channels, d.batch);
     FYN_CHECK_LAUNCH(t->ctx);
+    return FYN_OK;
+}
+
+int fyn_upload_u8_async(fyn_tensor *t, const unsigned char *host, void *stream) {
+    if (!t || !host) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
+    const fyn_tensor_desc &d = t->desc;
+    if (d.channels > 4) FYN_FAIL(FYN_ERR_UNSUPPORTED, "upload supports <= 4 channels (got %d)", d.channels);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)d.batch * d.height * d.width * d.channels;
+    int rc = ensure_staging(t, (n + 15) & ~(size_t)15);
+    if (rc) return rc;
+    FYN_CUDA(cudaMemcpyAsync(t->staging, host, n, cudaMemcpyHostToDevice, s));
+    if (d.dtype == FYN_F32 && d.padding == 0 && t->geom.packing == 3 && d.channels == 3 && d.width % 4 == 0) {
+        const long long quads = (long long)(n / 12);
+        k_upload_rgb8_to_rgb32f<<<(unsigned)((quads + 255) / 256), 256, 0, s>>>((const uint32_t *)t->staging, (float4 *)t->dptr, quads);
+    } else {
+        dim3 block(128), grid((d.width + 127) / 128, d.height, d.batch);
+        k_upload_convert_u8<<<grid, block, 0, s>>>((const unsigned char *)t->staging, fyn_make_view(t), d.channels, d.batch);
+    }
+    FYN_CHECK_LAUNCH(t->ctx);
+    return FYN_OK;
+}
+
+size_t fyn_download_u8_bytes(const fyn_tensor *t) { return fyn_download_f32_elems(t); }   // one byte per element of the RGBA texels
+
+int fyn_download_u8_convert(fyn_tensor *t, unsigned char *device_staging, void *stream) {
+    if (!t || !device_staging) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long texels = (long long)(fyn_download_f32_elems(t) / 4);
+    if (t->desc.dtype == FYN_F16 && t->geom.packing == 4 && texels % 4 == 0 && (((uintptr_t)device_staging) & 15) == 0) {
+        const long long quads = texels / 4;
+        k_download_rgba8_h4<<<(unsigned)((quads + 255) / 256), 256, 0, s>>>((const uint4 *)t->dptr, (uint4 *)device_staging, quads);
+    } else {
+        k_download_rgba8<<<(unsigned)((texels + 255) / 256), 256, 0, s>>>(fyn_make_view(t), (uint32_t *)device_staging, texels);
+    }
+    FYN_CHECK_LAUNCH(t->ctx);
+    return FYN_OK;
+}
+
+int fyn_download_u8_async(fyn_tensor *t, unsigned char *host, void *stream) {
+    if (!t || !host) FYN_FAIL(FYN_ERR_INVALID, "NULL argument");
+    const size_t bytes = fyn_download_u8_bytes(t);
+    int rc = ensure_staging(t, bytes);
+    if (rc) return rc;
+    rc = fyn_download_u8_convert(t, (unsigned char *)t->staging, stream);
+    if (rc) return rc;
+    FYN_CUDA(cudaMemcpyAsync(host, t->staging, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return FYN_OK;
 }
 

@@ -89,6 +89,42 @@ void *fynhost_stylenet_create(int kernel, int width, int height, int upload, int
     return rc == 0 ? h : nullptr;
 }
 
+// 8-bit frames in and out (StyleNetBase::setByteIO; before setup)
+int fynhost_stylenet_set_byte_io(void *handle, int on) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] {
+        if (h->kind != NetHandle::STYLE) THROW_EXCEPTION_ARGS(FynException, "Not a StyleNet");
+        h->style->setByteIO(on != 0);
+    });
+}
+
+// raw views of the pinned input (slot < 0: the synchronous buffer) / output buffers with their size in bytes and element type
+// (0 float32, 1 float16, 2 uint8), for networks with 8-bit I/O
+void *fynhost_net_input_raw(void *handle, int slot, size_t *numBytes, int *dataType) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    void *ptr = nullptr;
+    guarded([&] {
+        cpu::CPUBuffer *buf = (slot >= 0 && h->kind == NetHandle::STYLE) ? h->style->inputBuffer(slot) : h->inputBuffer();
+        if (numBytes) *numBytes = buf->bytes();
+        if (dataType) *dataType = (int)buf->shape().dataType();
+        ptr = buf->raw();
+    });
+    return ptr;
+}
+
+const void *fynhost_net_output_raw(void *handle, size_t *numBytes, int *dataType) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    const void *ptr = nullptr;
+    guarded([&] {
+        cpu::CPUBuffer *buf = h->outputBuffer();
+        if (!buf) THROW_EXCEPTION_ARGS(FynException, "Network has no output buffer");
+        if (numBytes) *numBytes = buf->bytes();
+        if (dataType) *dataType = (int)buf->shape().dataType();
+        ptr = buf->raw();
+    });
+    return ptr;
+}
+
 void *fynhost_resnet50_create(int device, int batch) {
     NetHandle *h = nullptr;
     int rc = guarded([&] {

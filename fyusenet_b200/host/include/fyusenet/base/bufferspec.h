@@ -11,7 +11,8 @@ namespace fyusenet {
 struct BufferSpec {
     enum usage : uint8_t { CONVOLUTION_SOURCE = 0, CONVOLUTION_DEST, FUNCTION_SOURCE, FUNCTION_DEST, RESIDUAL_SOURCE,
                            GPU_DEST /* upload target */, CPU_SOURCE, CPU_DEST };
-    enum dtype : uint8_t { FLOAT16 = 0, FLOAT32 = 1, FLOAT = 1 };
+    // UBYTE: host-side data of upload / download layers only (reference: BufferSpec::UBYTE, gpu/uploadlayer.cpp:51-66)
+    enum dtype : uint8_t { FLOAT16 = 0, FLOAT32 = 1, FLOAT = 1, UBYTE = 2, UINT8 = 2 };
     enum class order : uint8_t { CHANNELWISE = 0, GPU_SHALLOW, GPU_DEEP };
     enum csdevice : uint8_t { COMP_STOR_GPU = 0, COMP_STOR_CPU };
 

@@ -279,8 +279,10 @@ class UploadLayer : public GPULayerBase, public cpu::CPULayerInterface {
     // gpu/uploadlayer.cpp:395-541, AsyncLayer::state)
     void notifyUploaded(uint64_t sequence);
     bool hasCallback() const { return (bool)callback_; }
+    BufferSpec::dtype dataType() const { return dataType_; }
 
  protected:
+    void uploadFrom(CPUBuffer *buffer, TensorHandle target, void *stream);
     CPUBuffer *input_ = nullptr;
     CPUBuffer *pendingInput_ = nullptr;     // buffer of the most recent asynchronous upload (callback argument)
     bool async_ = false;
@@ -288,6 +290,7 @@ class UploadLayer : public GPULayerBase, public cpu::CPULayerInterface {
     UpDownLayerBuilder::callback_t callback_;
 };
 
+// (dataType(UBYTE) on a download layer is an extension: 8-bit RGBA texels, (uint8)(clamp(v, 0, 1) * 255) on the device)
 class DownloadLayer : public GPULayerBase, public cpu::CPULayerInterface {
  public:
     DownloadLayer(const UpDownLayerBuilder &builder, int layerNumber);
@@ -322,6 +325,8 @@ class DownloadLayer : public GPULayerBase, public cpu::CPULayerInterface {
     CPUBuffer *asyncOutputs_[Engine::ASYNC_SLOTS] = {};
     float *staging_[Engine::ASYNC_SLOTS] = {};
     bool async_ = false;
+    BufferSpec::dtype dataType_ = BufferSpec::FLOAT32;
+    size_t hostBytes() const;          // size of one downloaded frame in the layer's host data type
     UpDownLayerBuilder::callback_t callback_;
 };
 

@@ -62,7 +62,7 @@ StyleNetBase::CPUBuffer *StyleNetBase::inputBuffer(int slot) {
     if (!upload_) THROW_EXCEPTION_ARGS(FynException, "Network was created without an upload layer");
     if (slot < 0 || slot >= Engine::ASYNC_SLOTS) THROW_EXCEPTION_ARGS(FynException, "Illegal input buffer %d", slot);
     if (!inBuffers_[slot]) {
-        cpu::CPUBufferShape shape(height_, width_, 3, 0, cpu::CPUBufferShape::FLOAT32, BufferSpec::order::GPU_SHALLOW, batch_);
+        cpu::CPUBufferShape shape(height_, width_, 3, 0, byteIO_ ? cpu::CPUBufferShape::UINT8 : cpu::CPUBufferShape::FLOAT32, BufferSpec::order::GPU_SHALLOW, batch_);
         inBuffers_[slot] = shape.createBuffer(context());
     }
     return inBuffers_[slot];
@@ -86,6 +86,7 @@ CompiledLayers StyleNetBase::buildLayers() {
     if (upload_) {
         auto *up = new gpu::UpDownLayerBuilder(gpu::UpDownLayerBuilder::UPLOAD, "upload");
         up->shape(3, height_, width_, 3).context(context()).number(UPLOAD);
+        if (byteIO_) up->dataType(BufferSpec::UBYTE);
         if (async_) up->async();
         up->push(factory);
     }
@@ -108,6 +109,7 @@ CompiledLayers StyleNetBase::buildLayers() {
     if (download_) {
         auto *down = new gpu::UpDownLayerBuilder(gpu::UpDownLayerBuilder::DOWNLOAD, "download");
         down->shape(4, height_, width_, 4).context(context()).number(downloadLayer_);
+        if (byteIO_) down->dataType(BufferSpec::UBYTE);
         if (async_) down->async();
         down->push(factory);
     }
@@ -137,18 +139,30 @@ StyleNetBase::CPUBuffer *StyleNetBase::inputBuffer() {
     if (!setup_) THROW_EXCEPTION_ARGS(FynException, "Please run setup() before setting input buffers");
     if (!upload_) THROW_EXCEPTION_ARGS(FynException, "Network was created without an upload layer");
     if (!inBuffer_) {
-        cpu::CPUBufferShape shape(height_, width_, 3, 0, cpu::CPUBufferShape::FLOAT32, BufferSpec::order::GPU_SHALLOW, batch_);
+        cpu::CPUBufferShape shape(height_, width_, 3, 0, byteIO_ ? cpu::CPUBufferShape::UINT8 : cpu::CPUBufferShape::FLOAT32, BufferSpec::order::GPU_SHALLOW, batch_);
         inBuffer_ = shape.createBuffer(context());  // pinned staging, the role of the upload PBO
     }
     static_cast<gpu::UploadLayer *>(engine_->getLayers()["upload"])->setInputBuffer(inBuffer_, 0);
     return inBuffer_;
 }
 
+void StyleNetBase::setByteIO(bool on) {
+    if (setup_) THROW_EXCEPTION_ARGS(FynException, "The I/O data type must be chosen before setup()");
+    byteIO_ = on;
+}
+
 void StyleNetBase::setInputBuffer(const float *data) {
+    if (byteIO_) THROW_EXCEPTION_ARGS(FynException, "Network takes 8-bit frames (setByteIO)");
     CPUBuffer *buf = async_ ? inputBuffer((int)(engine_->nextSequenceNo() % Engine::ASYNC_SLOTS)) : inputBuffer();
     float *tgt = buf->map<float>();
     memcpy(tgt, data, buf->bytes());
     buf->unmap();
+}
+
+void StyleNetBase::setInputBuffer(const uint8_t *data) {
+    if (!byteIO_) THROW_EXCEPTION_ARGS(FynException, "Network takes float32 frames (see setByteIO)");
+    CPUBuffer *buf = async_ ? inputBuffer((int)(engine_->nextSequenceNo() % Engine::ASYNC_SLOTS)) : inputBuffer();
+    memcpy(buf->raw(), data, buf->bytes());
 }
 
 StyleNetBase::CPUBuffer *StyleNetBase::getOutputBuffer() {

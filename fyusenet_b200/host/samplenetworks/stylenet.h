@@ -21,7 +21,14 @@ class StyleNetBase : public fyusion::fyusenet::NeuralNetwork {
     ~StyleNetBase() override;
 
     void loadWeightsAndBiases(const float *weightsAndBiases, size_t size);
+    // 8-bit frames in and out (call before setup()): the upload layer takes UBYTE buffers -- UpDownLayerBuilder::dataType(UBYTE),
+    // an 8-bit normalised texture in the reference (gpu/uploadlayer.cpp:51-66) -- and the download layer delivers RGBA8 texels,
+    // quantised on the device the way samples/desktop/stylenet.cpp:52-62 does on the host.  A frame then moves 3 + 4 instead of
+    // 12 + 16 bytes per pixel over PCIe.  Default: float32 both ways, like the reference's sample.
+    void setByteIO(bool on);
+    bool byteIO() const { return byteIO_; }
     void setInputBuffer(const float *data);
+    void setInputBuffer(const uint8_t *data);
     CPUBuffer *getOutputBuffer();
     // the pinned host buffer the upload layer reads from (created on demand and attached to the upload layer)
     CPUBuffer *inputBuffer();
@@ -54,6 +61,7 @@ class StyleNetBase : public fyusion::fyusenet::NeuralNetwork {
 
     int kernel_, resBlocks_, width_, height_;
     bool upload_, download_;
+    bool byteIO_ = false;
     std::vector<ConvSpec> convs_;                       // in layer-number order, layer number = index + CONV1
     std::unordered_map<int, size_t> weightOffsets_;     // layer number -> float offset
     size_t totalWeights_ = 0;

@@ -144,7 +144,8 @@ void BufferManager::createCPUOutput(LayerBase *outputLayer, bool lock) {
     if (outs.empty() || outs[0].device_ != BufferSpec::COMP_STOR_CPU)
         THROW_EXCEPTION_ARGS(FynException, "Layer %s has no CPU output", outputLayer->getName().c_str());
     const BufferSpec &s = outs[0];
-    CPUBufferShape shape(s.height_, s.width_, s.channels_, s.padding_, CPUBufferShape::FLOAT32, s.dataOrder_, batch_);
+    CPUBufferShape shape(s.height_, s.width_, s.channels_, s.padding_, s.type_ == BufferSpec::UBYTE ? CPUBufferShape::UINT8 : CPUBufferShape::FLOAT32,
+                         s.dataOrder_, batch_);
     shape.uploadStyle(false);
     CPUBuffer *buf = shape.createBuffer(context_);  // pinned: the download is a true async copy
     cpuBuffers_.push_back(buf);

@@ -695,7 +695,8 @@ UploadLayer::UploadLayer(const UpDownLayerBuilder &b, int layerNumber)
         THROW_EXCEPTION_ARGS(FynException, "Layer %s: upload supports at most %d channels", name_.c_str(), PIXEL_PACKING);
 }
 std::vector<BufferSpec> UploadLayer::getRequiredInputBuffers() const {
-    return {BufferSpec(0, width_, height_, inputChannels_, 0, BufferSpec::order::GPU_SHALLOW, BufferSpec::FLOAT32, BufferSpec::CPU_SOURCE)
+    return {BufferSpec(0, width_, height_, inputChannels_, 0, BufferSpec::order::GPU_SHALLOW, dataType_ == BufferSpec::UBYTE ? BufferSpec::UBYTE : BufferSpec::FLOAT32,
+                       BufferSpec::CPU_SOURCE)
                 .device(BufferSpec::COMP_STOR_CPU)};
 }
 std::vector<BufferSpec> UploadLayer::getRequiredOutputBuffers() const {
@@ -707,10 +708,8 @@ void UploadLayer::forward(uint64_t sequence) {
     if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
     std::lock_guard<std::recursive_mutex> lck(processingLock_);
     if (!input_) THROW_EXCEPTION_ARGS(FynException, "No input buffer set for upload layer %s", name_.c_str());
-    const float *src = input_->map<float>();
-    input_->unmap();
     if (callback_) callback_(sequence, input_, AsyncLayer::UPLOAD_COMMENCED);
-    FYN_ABI_CALL(fyn_upload_f32_async(out(), src, context_.stream()));
+    uploadFrom(input_, out(), context_.stream());
     if (callback_) callback_(sequence, input_, AsyncLayer::UPLOAD_DONE);
 }
 
@@ -720,14 +719,29 @@ TensorHandle UploadLayer::asyncUpload(uint64_t sequence, int slot, void *stream)
     if (!input_) THROW_EXCEPTION_ARGS(FynException, "No input buffer set for upload layer %s", name_.c_str());
     TensorHandle target = getOutputTexture(0, slot);
     if (!target) THROW_EXCEPTION_ARGS(FynException, "Upload layer %s has no output buffer %d", name_.c_str(), slot);
-    const float *src = input_->map<float>();
-    input_->unmap();
     // the copy reads the caller's pinned buffer asynchronously: UPLOAD_COMMENCED / UPLOAD_DONE are fired by
     // notifyUploaded() once it has completed, never before (a caller may refill its buffer on UPLOAD_COMMENCED)
     (void)sequence;
     pendingInput_ = input_;
-    FYN_ABI_CALL(fyn_upload_f32_async(target, src, stream));
+    uploadFrom(input_, target, stream);
     return target;
+}
+
+// FLOAT32 buffers are copied verbatim into the RGB32F upload texture; UBYTE buffers (reference: gpu/uploadlayer.cpp:51-66,365-375,
+// an 8-bit normalised texture) are converted to value / 255 on the device, so only a quarter of the bytes cross PCIe
+void UploadLayer::uploadFrom(CPUBuffer *buffer, TensorHandle target, void *stream) {
+    const bool bytes = buffer->shape().dataType() == cpu::CPUBufferShape::UINT8;
+    if (bytes != (dataType_ == BufferSpec::UBYTE))
+        THROW_EXCEPTION_ARGS(FynException, "Upload layer %s: input buffer data type does not match the layer's", name_.c_str());
+    if (bytes) {
+        const uint8_t *src = buffer->map<uint8_t>();
+        buffer->unmap();
+        FYN_ABI_CALL(fyn_upload_u8_async(target, src, stream));
+    } else {
+        const float *src = buffer->map<float>();
+        buffer->unmap();
+        FYN_ABI_CALL(fyn_upload_f32_async(target, src, stream));
+    }
 }
 
 void UploadLayer::notifyUploaded(uint64_t sequence) {
@@ -740,7 +754,7 @@ void UploadLayer::notifyUploaded(uint64_t sequence) {
 // DownloadLayer: tensor -> host float32 in texel order (gpu/downloadlayer.cpp:112-131,257-283)
 // ------------------------------------------------------------------------------------------------
 DownloadLayer::DownloadLayer(const UpDownLayerBuilder &b, int layerNumber)
-    : GPULayerBase(b, layerNumber), async_(b.async_), callback_(b.callback_) {
+    : GPULayerBase(b, layerNumber), async_(b.async_), dataType_(b.dataType_ == BufferSpec::UBYTE ? BufferSpec::UBYTE : BufferSpec::FLOAT32), callback_(b.callback_) {
     if (flags_ & LayerFlags::PRE_ACT_MASK) THROW_EXCEPTION_ARGS(FynException, "Activation on download not implemented yet");
     if (flags_ & LayerFlags::RESIDUAL_INPUT) THROW_EXCEPTION_ARGS(FynException, "Residual add on download not implemented yet");
 }
@@ -748,20 +762,22 @@ std::vector<BufferSpec> DownloadLayer::getRequiredInputBuffers() const {
     return {BufferSpec(0, width_, height_, inputChannels_, inputPadding_, order(), storagePrecision(), BufferSpec::FUNCTION_SOURCE)};
 }
 std::vector<BufferSpec> DownloadLayer::getRequiredOutputBuffers() const {
-    return {BufferSpec(0, width_, height_, outputChannels_, inputPadding_, order(), BufferSpec::FLOAT32, BufferSpec::CPU_DEST)
+    return {BufferSpec(0, width_, height_, outputChannels_, inputPadding_, order(), dataType_, BufferSpec::CPU_DEST)
                 .device(BufferSpec::COMP_STOR_CPU)};
+}
+size_t DownloadLayer::hostBytes() const {
+    return dataType_ == BufferSpec::UBYTE ? fyn_download_u8_bytes(in(0)) : fyn_download_f32_elems(in(0)) * sizeof(float);
 }
 void DownloadLayer::forward(uint64_t sequence) {
     if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
     std::lock_guard<std::recursive_mutex> lck(processingLock_);
     if (!output_) THROW_EXCEPTION_ARGS(FynException, "No output buffer set for download layer %s", name_.c_str());
-    size_t need = fyn_download_f32_elems(in(0)) * sizeof(float);
+    size_t need = hostBytes();
     if (output_->bytes() < need)
         THROW_EXCEPTION_ARGS(FynException, "Download buffer too small (%zu < %zu bytes)", output_->bytes(), need);
-    float *dst = output_->map<float>();
-    output_->unmap();
     if (callback_) callback_(sequence, output_, AsyncLayer::DOWNLOAD_COMMENCED);
-    FYN_ABI_CALL(fyn_download_f32_async(in(0), dst, context_.stream()));
+    if (dataType_ == BufferSpec::UBYTE) FYN_ABI_CALL(fyn_download_u8_async(in(0), static_cast<unsigned char *>(output_->raw()), context_.stream()));
+    else FYN_ABI_CALL(fyn_download_f32_async(in(0), static_cast<float *>(output_->raw()), context_.stream()));
     if (!async_) {
         // synchronous path blocks like the reference's glReadPixels + readFromPBO
         FYN_ABI_CALL(fyn_stream_sync(context_.handle(), context_.stream()));
@@ -782,15 +798,16 @@ void DownloadLayer::asyncConvert(int slot, void *stream) {
     if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
     if (!staging_[slot]) {
         void *p = nullptr;
-        FYN_ABI_CALL(fyn_device_alloc(context_.handle(), fyn_download_f32_elems(in(0)) * sizeof(float), &p));
+        FYN_ABI_CALL(fyn_device_alloc(context_.handle(), hostBytes(), &p));
         staging_[slot] = static_cast<float *>(p);
     }
-    FYN_ABI_CALL(fyn_download_convert(in(0), staging_[slot], stream));
+    if (dataType_ == BufferSpec::UBYTE) FYN_ABI_CALL(fyn_download_u8_convert(in(0), reinterpret_cast<unsigned char *>(staging_[slot]), stream));
+    else FYN_ABI_CALL(fyn_download_convert(in(0), staging_[slot], stream));
 }
 
 CPUBuffer *DownloadLayer::asyncCopy(uint64_t sequence, int slot, void *stream) {
     CPUBuffer *buf = asyncBuffer(slot);
-    const size_t bytes = fyn_download_f32_elems(in(0)) * sizeof(float);
+    const size_t bytes = hostBytes();
     if (buf->bytes() < bytes) THROW_EXCEPTION_ARGS(FynException, "Download buffer too small (%zu < %zu bytes)", buf->bytes(), bytes);
     if (callback_) callback_(sequence, buf, AsyncLayer::DOWNLOAD_COMMENCED);
     FYN_ABI_CALL(fyn_memcpy_async(context_.handle(), buf->raw(), staging_[slot], bytes, 1, stream));

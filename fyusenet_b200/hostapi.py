@@ -44,6 +44,8 @@ def lib():
         L.fynhost_net_stream.restype = C.c_void_p
         L.fynhost_net_device_bytes.restype = C.c_size_t
         L.fynhost_net_layer_tensor.restype = C.c_void_p
+        L.fynhost_net_input_raw.restype = C.c_void_p
+        L.fynhost_net_output_raw.restype = C.c_void_p
         _lib = L
     return _lib
 
@@ -229,20 +231,37 @@ class StyleNet(Network):
     def __init__(self, kernel: int, width: int, height: int, upload=True, download=True, device=0):
         super().__init__(lib().fynhost_stylenet_create(int(kernel), int(width), int(height), int(upload), int(download), int(device)))
         self.kernel, self.width, self.height = kernel, width, height
+        self.byte_io = False
+
+    def set_byte_io(self, on=True):
+        """8-bit frames in and out (StyleNetBase::setByteIO, before setup()): UBYTE upload (value / 255 on the device) and RGBA8
+        download ((uint8)(clamp(v, 0, 1) * 255) on the device); input_buffer() / input_buffer_slot() / output_rgba() are uint8."""
+        _check(lib().fynhost_stylenet_set_byte_io(self._h, int(bool(on))))
+        self.byte_io = bool(on)
+
+    def _raw(self, fn, *args):
+        n, dt = C.c_size_t(), C.c_int()
+        p = fn(self._h, *args, C.byref(n), C.byref(dt))
+        if not p:
+            raise HostError(lib().fynhost_last_error().decode(errors="replace"))
+        ctype, count = {0: (C.c_float, n.value // 4), 1: (C.c_uint16, n.value // 2), 2: (C.c_ubyte, n.value)}[dt.value]
+        return np.ctypeslib.as_array(C.cast(C.c_void_p(p), C.POINTER(ctype)), shape=(count,))
+
+    def input_buffer(self) -> np.ndarray:
+        return self._raw(lib().fynhost_net_input_raw, -1)
+
+    def output(self) -> np.ndarray:
+        return self._raw(lib().fynhost_net_output_raw)
 
     def set_input_tensor(self, tensor: capi.Tensor):
         _check(lib().fynhost_stylenet_set_input_tensor(self._h, tensor._h))
 
     def input_buffer_slot(self, slot: int) -> np.ndarray:
         """Pinned input buffer `slot` of an asynchronous network (sequence s reads slot s % async_slots())."""
-        n = C.c_size_t()
-        p = lib().fynhost_stylenet_input_buffer_slot(self._h, int(slot), C.byref(n))
-        if not p:
-            raise HostError(lib().fynhost_last_error().decode(errors="replace"))
-        return np.ctypeslib.as_array(p, shape=(n.value,))
+        return self._raw(lib().fynhost_net_input_raw, int(slot))
 
     def output_rgba(self) -> np.ndarray:
-        """download buffer as [batch?][H][W][4] float32 (RGBA, alpha = 0.5: compare RGB only)."""
+        """download buffer as [batch?][H][W][4] float32 -- uint8 with set_byte_io() -- (RGBA, alpha = 0.5: compare RGB only)."""
         return self.output().reshape(-1, self.height, self.width, 4)
 
 

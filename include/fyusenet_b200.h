@@ -194,6 +194,17 @@ size_t fyn_download_f32_elems(const fyn_tensor *tensor);
  * (fyn_download_f32_elems floats); the host copy is then a plain fyn_memcpy_async on another stream */
 int fyn_download_convert(fyn_tensor *tensor, float *device_staging, void *stream);
 
+/* 8-bit I/O.  Upload: UploadLayer with UpDownLayerBuilder::dataType(UBYTE) (fyusenet/gpu/uploadlayer.cpp:51-66,365-375: the bytes
+ * become a normalised 8-bit texture, i.e. the layers read value / 255); host order [batch][H][W][C] like the float upload.
+ * Download: an extension -- the reference's DownloadLayer reads float32 texels only (gpu/downloadlayer.cpp:257-283) and the
+ * samples quantise on the host, (uint8_t)(v * 255) (samples/desktop/stylenet.cpp:52-62); the same conversion (after a clamp to
+ * [0, 1]) runs on the device here, so an RGBA frame leaves as 4 instead of 16 bytes per pixel.  Texel order and size in
+ * elements are those of the float download (fyn_download_f32_elems). */
+int fyn_upload_u8_async(fyn_tensor *tensor, const unsigned char *host_hwc, void *stream);
+size_t fyn_download_u8_bytes(const fyn_tensor *tensor);
+int fyn_download_u8_convert(fyn_tensor *tensor, unsigned char *device_staging, void *stream);
+int fyn_download_u8_async(fyn_tensor *tensor, unsigned char *host, void *stream);
+
 /* Debug / parity interchange (LayerBase::writeResult format, fyusenet/base/layerbase.h:160-172 and
  * GPULayerBase::copyResult, fyusenet/gpu/gpulayerbase.cpp:525-560): float32 [batch][C][H][W]
  * without padding.  Both calls are BLOCKING and go through pageable host memory. */

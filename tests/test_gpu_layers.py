@@ -262,6 +262,45 @@ def test_upload_download_layouts():
     t.destroy()
 
 
+def test_byte_upload_and_download():
+    """UBYTE upload (gpu/uploadlayer.cpp:51-66: an 8-bit normalised texture, i.e. value / 255) and the RGBA8 download
+    ((uint8)(v * 255) like samples/desktop/stylenet.cpp:52-62, after a clamp): exact against numpy, on the vectorised paths
+    (RGB32F upload texture, fp16 RGBA download) and on the generic ones."""
+    c = ctx()
+    rng = np.random.default_rng(3)
+    for (w, h, batch) in [(16, 9, 1), (1524, 8, 1), (13, 7, 2)]:
+        img = rng.integers(0, 256, size=(batch, h, w, 3), dtype=np.uint8)
+        want = img.astype(np.float32) / np.float32(255.0)
+        # the RGB32F upload texture of the float path (packing 3, no padding): same texels as uploading img / 255 as floats
+        t8 = c.tensor(w, h, 3, 0, capi.ORDER_SHALLOW, capi.F32, batch, packing=3)
+        tf = c.tensor(w, h, 3, 0, capi.ORDER_SHALLOW, capi.F32, batch, packing=3)
+        t8.upload_u8(img)
+        tf.upload(want)
+        c.stream_sync()
+        np.testing.assert_array_equal(t8.read_chw(), tf.read_chw())
+        np.testing.assert_array_equal(np.asarray(t8.read_chw()).reshape(batch, 3, h, w), want.transpose(0, 3, 1, 2))
+        t8.destroy()
+        tf.destroy()
+        # generic path: fp16 RGBA plane with padding
+        t = c.tensor(w, h, 3, 1, capi.ORDER_SHALLOW, capi.F16, batch)
+        t.upload_u8(img)
+        c.stream_sync()
+        np.testing.assert_array_equal(np.asarray(t.read_chw()).reshape(batch, 3, h, w), half(want).transpose(0, 3, 1, 2))
+        t.destroy()
+    # download: fp16 RGBA (vectorised when the texel count allows it), fp32, values outside [0, 1] clamp
+    for (w, h, ch, pad, dt) in [(16, 8, 4, 0, capi.F16), (13, 7, 3, 1, capi.F16), (12, 5, 4, 0, capi.F32)]:
+        x = rng.uniform(-0.2, 1.2, size=(ch, h, w)).astype(np.float32)
+        if dt == capi.F16:
+            x = half(x)
+        t = c.tensor(w, h, ch, pad, capi.ORDER_SHALLOW, dt)
+        t.write_chw(x)
+        f = t.download()
+        b = t.download_u8()
+        assert b.shape == f.shape and b.dtype == np.uint8
+        np.testing.assert_array_equal(b, (np.clip(f, 0.0, 1.0) * np.float32(255.0)).astype(np.uint8))
+        t.destroy()
+
+
 def test_reference_kats_on_gpu():
     """The reference's own layer tests replayed on the CUDA path (convlayertests.cpp:159-305, networktests.cpp)."""
     from test_oracle_kat import antisym_kernel, padded_convolution, stack_convolution

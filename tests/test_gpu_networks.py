@@ -564,3 +564,45 @@ def test_stylenet_chain_headline_size_is_exact():
         net.forward()
         np.testing.assert_array_equal(net.output_rgba()[0], want)
     net.destroy()
+
+
+@pytest.mark.parametrize("asynchronous", [False, True])
+def test_stylenet_byte_io_matches_float_io(asynchronous):
+    """StyleNetBase::setByteIO: an uint8 frame in, an RGBA8 frame out.  Same device arithmetic as the float path fed with
+    img / 255, so the bytes must equal the float result quantised like samples/desktop/stylenet.cpp:52-62 -- exactly."""
+    weights = fo.stylenet_synthetic_weights(9)
+    w, h = 256, 192
+    img8 = np.random.default_rng(2).integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    ref = hostapi.StyleNet(9, w, h)
+    ref.load_weights(weights)
+    ref.setup()
+    ref.set_input(img8.astype(np.float32) / np.float32(255.0))
+    ref.forward()
+    want = (np.clip(ref.output_rgba()[0], 0.0, 1.0) * np.float32(255.0)).astype(np.uint8)
+    ref.destroy()
+    net = hostapi.StyleNet(9, w, h)
+    if asynchronous:
+        net.asynchronous()
+    net.set_byte_io(True)
+    net.load_weights(weights)
+    net.setup()
+    if asynchronous:
+        for k in range(hostapi.async_slots()):
+            buf = net.input_buffer_slot(k)
+            assert buf.dtype == np.uint8 and buf.size == h * w * 3
+            buf[:] = img8.reshape(-1)
+        for _ in range(4):
+            net.forward()
+        net.finish()
+        assert net.async_completed()[0] == 4
+    else:
+        buf = net.input_buffer()
+        assert buf.dtype == np.uint8 and buf.size == h * w * 3
+        buf[:] = img8.reshape(-1)
+        net.forward()
+    got = net.output_rgba()[0]
+    assert got.dtype == np.uint8 and got.shape == (h, w, 4)
+    np.testing.assert_array_equal(got[..., :3], want[..., :3])
+    with pytest.raises(hostapi.HostError):
+        net.set_byte_io(False)              # the data type is fixed at setup()
+    net.destroy()
