@@ -665,7 +665,8 @@ Geometry plan_geometry(const fyn_conv_desc *d, const float *wb, int ys) {
                 }
     } else {
         if (d->downsample != 1 && d->downsample != 2) return g;
-        if (K < 3 || Ci < 8) return g;
+        // (1x1 kernels -- vanilla::ConvLayer1x1, gpu/vanilla/convlayer1x1_vanilla.cpp:81-150 -- are windows of one row and one
+        // tap; inputs with fewer than 8 channels are a single, partly empty chunk)
         g.mode = 0;
         g.opx = 1;
         g.opy = ys;

@@ -306,3 +306,17 @@ def test_deep_conv_wide_tiles_on_large_grids():
     y = conv_gpu(x, wb, **kw)
     assert rel_l2(y, conv_gpu(x, wb, backend=capi.BACKEND_DIRECT, **kw)) <= 1e-4
     np.testing.assert_array_equal(y[:2], conv_gpu(x[:2], wb, **kw))
+
+
+@pytest.mark.parametrize("k,ds,ci,co,relu", [(1, 1, 8, 5, False), (1, 2, 16, 8, True), (1, 1, 40, 40, True), (1, 1, 3, 12, True), (5, 1, 6, 7, True),
+                                              (7, 2, 4, 8, False), (5, 1, 24, 16, True), (7, 1, 12, 12, True), (1, 2, 5, 3, False)])
+def test_tc_1x1_5x5_7x7_and_thin_inputs(k, ds, ci, co, relu):
+    """vanilla::ConvLayer1x1 (gpu/vanilla/convlayer1x1_vanilla.cpp:81-150) and the 5x5 / 7x7 / few-channel shapes of
+    ConvLayerNxN on the tcgen05 family: windows of one row and one tap, inputs that fill only part of an 8-channel chunk."""
+    rng = np.random.default_rng(k * 1000 + ci * 10 + co)
+    h, w = 26, 150
+    x = rng.normal(size=(ci, h, w)).astype(np.float32)
+    wb = random_wb(rng, ci, co, k)
+    _run(x, wb, co, k, ds=ds, relu=relu)
+    res = rng.normal(size=(co, h // ds, w // ds)).astype(np.float32)
+    _run(x, wb, co, k, ds=ds, relu=relu, residual=res, relu_res=True)

@@ -26,11 +26,16 @@ def main():
     ran = skipped = 0
     worst = 0.0
     for case in range(cases):
-        kind = rng.choice(["regular", "stride2", "frac1", "frac2", "rgb"])
+        kw = {}
+        kind = rng.choice(["regular", "stride2", "frac1", "frac2", "rgb", "small"])
         k = int(rng.choice([3, 3, 3, 5, 7, 9]))
         ci = int(rng.choice([8, 12, 16, 20, 24, 32, 40, 48]))
+        if kind == "small":                  # 1x1 kernels and thin inputs on the plane-chunk path
+            k = int(rng.choice([1, 1, 1, 3, 5]))
+            ci = int(rng.choice([1, 2, 3, 5, 6, 7, 8, 16, 40])) if k == 1 else int(rng.choice([5, 6, 7]))
+            if rng.random() < 0.4:
+                kw["downsample"] = 2
         co = int(rng.integers(1, 41))
-        kw = {}
         if kind == "stride2":
             kw["downsample"] = 2
         elif kind == "frac1":
@@ -45,7 +50,7 @@ def main():
         h = int(rng.integers(9, 200))
         batch = int(rng.choice([1, 1, 1, 2]))
         relu = bool(rng.random() < 0.7)
-        in_pad = int(rng.choice([0, 0, 1])) if kind in ("regular", "stride2") else 0
+        in_pad = int(rng.choice([0, 0, 1])) if kind in ("regular", "stride2", "small") else 0
         out_pad = int(rng.choice([0, 0, 1]))
         res = bool(rng.random() < 0.3) and kind != "rgb"
         flags = (capi.FLAG_PRE_RELU if relu else 0) | (capi.FLAG_RESIDUAL_INPUT if res else 0)
