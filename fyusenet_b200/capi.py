@@ -107,7 +107,7 @@ class TransConvDesc(C.Structure):
 class DwConvDesc(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("downsample", C.c_int), ("dilation", C.c_int),
                 ("in_padding", C.c_int), ("out_padding", C.c_int), ("flags", C.c_uint), ("leaky", C.c_float), ("clip_lo", C.c_float),
-                ("clip_hi", C.c_float), ("quirks", C.c_int)]
+                ("clip_hi", C.c_float), ("quirks", C.c_int), ("multiplier", C.c_int), ("res_padding", C.c_int)]
 
 # every symbol include/fyusenet_b200.h declares (tests check that the library exports all of them)
 EPILOGUE_NONE, EPILOGUE_SIGMOID = 0, 1
@@ -126,7 +126,7 @@ EXPORTS = [
     "fyn_conv_chain_create", "fyn_conv_chain_layers", "fyn_conv_chain_run", "fyn_conv_chain_destroy", "fyn_pool2d_create", "fyn_pool2d_run", "fyn_batchnorm_create",
     "fyn_batchnorm_load", "fyn_batchnorm_run", "fyn_sigmoid_create", "fyn_sigmoid_run", "fyn_op_destroy",
     "fyn_scale_create", "fyn_scale_out_size", "fyn_scale_run", "fyn_arith_create", "fyn_arith_run", "fyn_concat_create",
-    "fyn_concat_run", "fyn_dwconv3x3_create", "fyn_dwconv3x3_load_weights", "fyn_dwconv3x3_run", "fyn_transconv2d_create", "fyn_transconv2d_load_weights", "fyn_transconv2d_run", "fyn_rgb2bgr_create", "fyn_rgb2bgr_run", "fyn_relayout_create", "fyn_relayout_run",
+    "fyn_concat_run", "fyn_dwconv3x3_create", "fyn_dwconv3x3_load_weights", "fyn_dwconv3x3_run", "fyn_dwconv3x3_run_residual", "fyn_transconv2d_create", "fyn_transconv2d_load_weights", "fyn_transconv2d_run", "fyn_rgb2bgr_create", "fyn_rgb2bgr_run", "fyn_relayout_create", "fyn_relayout_run",
     "fyn_graph_begin_capture", "fyn_graph_end_capture", "fyn_graph_launch", "fyn_graph_destroy",
     "fyn_comm_unique_id", "fyn_comm_init", "fyn_comm_destroy", "fyn_comm_info", "fyn_allgather_logits", "fyn_comm_register_tensor", "fyn_halo_exchange",
 ]
@@ -461,10 +461,10 @@ class DwConv3x3(_Op):
     """Depthwise 3x3 convolution (vanilla::DepthwiseConvLayer3x3 / deep::DeepDepthwiseConvLayer3x3)."""
 
     def __init__(self, ctx, wb, *, width, height, channels, downsample=1, dilation=1, in_padding=0, out_padding=0, flags=0,
-                 leaky=0.0, quirks=None):
+                 leaky=0.0, quirks=None, multiplier=1, res_padding=0):
         super().__init__(ctx)
         self.desc = DwConvDesc(width, height, channels, downsample, dilation, in_padding, out_padding, flags, leaky, 0.0, 0.0,
-                               QUIRKS_REFERENCE if quirks is None else quirks)
+                               QUIRKS_REFERENCE if quirks is None else quirks, multiplier, res_padding)
         self.out_width, self.out_height = width // downsample, height // downsample
         w = np.ascontiguousarray(wb, np.float32)
         check(lib().fyn_dwconv3x3_create(ctx._h, C.byref(self.desc), _fptr(w), C.byref(self._h)))
@@ -473,8 +473,11 @@ class DwConv3x3(_Op):
         w = np.ascontiguousarray(wb, np.float32)
         check(lib().fyn_dwconv3x3_load_weights(self._h, _fptr(w)))
 
-    def run(self, x, out, stream=None):
-        check(lib().fyn_dwconv3x3_run(self._h, x._h, out._h, _s(stream)))
+    def run(self, x, out, stream=None, residual=None):
+        if residual is None:
+            check(lib().fyn_dwconv3x3_run(self._h, x._h, out._h, _s(stream)))
+        else:
+            check(lib().fyn_dwconv3x3_run_residual(self._h, x._h, residual._h, out._h, _s(stream)))
 
 
 class TransConv2d(_Op):

@@ -358,13 +358,18 @@ void SigmoidLayer::forward(uint64_t) {
 // ------------------------------------------------------------------------------------------------
 DepthwiseConvLayer::DepthwiseConvLayer(const ConvLayerBuilder &b, int layerNumber) : GPULayerBase(b, layerNumber) {
     if (b.kernel_ != 3) THROW_EXCEPTION_ARGS(FynException, "Layer %s: depthwise convolution supports 3x3 kernels only", name_.c_str());
-    // channel multiplier = outputs / group size (convlayer_dw_3x3_vanilla.cpp:24-25)
-    if (b.groupSize_ != inputChannels_ || outputChannels_ != inputChannels_)
-        THROW_EXCEPTION_ARGS(FynException, "Channel multipliers are currently not supported");
+    // channel multiplier = outputs / group size (convlayer_dw_3x3_vanilla.cpp:49-50: shallow layers throw for != 1;
+    // deepdwconvlayerbase.cpp:40-44: deep layers need input channels % 4 == 0)
+    if (b.groupSize_ != inputChannels_ || outputChannels_ % inputChannels_ != 0)
+        THROW_EXCEPTION_ARGS(FynException, "Layer %s: depthwise convolution needs group size == input channels and outputs a multiple of it", name_.c_str());
+    const int multiplier = outputChannels_ / b.groupSize_;
+    if (multiplier != 1 && !(flags_ & LayerFlags::DEEP)) THROW_EXCEPTION_ARGS(FynException, "Channel multipliers are currently not supported");
+    if (multiplier > 1 && (inputChannels_ & 3))
+        THROW_EXCEPTION_ARGS(FynException, "Channel multipliers > 1 are only supported on input channels being a multiple of 4");
     if (b.downsample_[0] != b.downsample_[1] || b.dilation_[0] != b.dilation_[1])
         THROW_EXCEPTION_ARGS(FynException, "Layer %s: anisotropic downsampling / dilation not supported", name_.c_str());
-    if (flags_ & LayerFlags::RESIDUAL_INPUT)
-        THROW_EXCEPTION_ARGS(FynException, "Layer %s: residual input on depthwise convolutions is not supported by the CUDA backend", name_.c_str());
+    desc_.multiplier = multiplier;
+    desc_.res_padding = residualPadding_;
     desc_.width = width_;
     desc_.height = height_;
     desc_.channels = inputChannels_;
@@ -372,7 +377,8 @@ DepthwiseConvLayer::DepthwiseConvLayer(const ConvLayerBuilder &b, int layerNumbe
     desc_.dilation = b.dilation_[0];
     desc_.in_padding = inputPadding_;
     desc_.out_padding = outputPadding_;
-    desc_.flags = flags_ & (LayerFlags::POST_BATCHNORM | LayerFlags::DEEP | LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP);
+    desc_.flags = flags_ & (LayerFlags::POST_BATCHNORM | LayerFlags::DEEP | LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP | LayerFlags::RESIDUAL_INPUT |
+                            LayerFlags::RELU_ON_RESIDUAL | LayerFlags::BATCHNORM_ON_RESIDUAL);
     desc_.leaky = leakyReLU_;
     desc_.clip_lo = lowClip_;
     desc_.clip_hi = highClip_;
@@ -385,7 +391,10 @@ DepthwiseConvLayer::DepthwiseConvLayer(const ConvLayerBuilder &b, int layerNumbe
 std::vector<BufferSpec> DepthwiseConvLayer::getRequiredInputBuffers() const {
     BufferSpec in0(0, width_, height_, inputChannels_, inputPadding_, order(), storagePrecision(), BufferSpec::CONVOLUTION_SOURCE);
     if (inputChannels_ < PIXEL_PACKING) in0.anyType();
-    return {in0};
+    std::vector<BufferSpec> r{in0};
+    if (flags_ & LayerFlags::RESIDUAL_INPUT)
+        r.push_back(BufferSpec(1, outWidth_, outHeight_, outputChannels_, residualPadding_, order(), storagePrecision(), BufferSpec::RESIDUAL_SOURCE));
+    return r;
 }
 std::vector<BufferSpec> DepthwiseConvLayer::getRequiredOutputBuffers() const {
     return {BufferSpec(0, outWidth_, outHeight_, outputChannels_, outputPadding_, order(), storagePrecision(), BufferSpec::CONVOLUTION_DEST)};
@@ -393,7 +402,7 @@ std::vector<BufferSpec> DepthwiseConvLayer::getRequiredOutputBuffers() const {
 void DepthwiseConvLayer::loadWeightsAndBiases(const float *biasAndWeights, size_t offset) {
     std::lock_guard<std::recursive_mutex> lck(processingLock_);
     if (!biasAndWeights) THROW_EXCEPTION_ARGS(FynException, "Layer %s: null weight pointer", name_.c_str());
-    size_t n = (size_t)outputChannels_ * 10;
+    size_t n = (size_t)outputChannels_ + (size_t)outputChannels_ * 9;          // bias[Co], W[Ci][3][3][multiplier]
     if (flags_ & LayerFlags::POST_BATCHNORM) n += 2 * (size_t)outputChannels_;
     const float *src = biasAndWeights + offset;
     if (op_) {
@@ -419,7 +428,12 @@ void DepthwiseConvLayer::cleanup() {
 void DepthwiseConvLayer::forward(uint64_t) {
     if (!valid_) THROW_EXCEPTION_ARGS(FynException, "Trying to invoke forward() on invalid layer");
     std::lock_guard<std::recursive_mutex> lck(processingLock_);
-    FYN_ABI_CALL(fyn_dwconv3x3_run(op_, in(0), out(), context_.stream()));
+    TensorHandle res = nullptr;
+    if (flags_ & LayerFlags::RESIDUAL_INPUT) {
+        if (residuals_.empty() || !residuals_[0]) THROW_EXCEPTION_ARGS(FynException, "Residual flag configured, but no such texture found.");
+        res = residuals_[0];
+    }
+    FYN_ABI_CALL(fyn_dwconv3x3_run_residual(op_, in(0), res, out(), context_.stream()));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -429,9 +443,9 @@ TransConvLayer::TransConvLayer(const ConvLayerBuilder &b, int layerNumber) : GPU
     // transconvlayerbase_vanilla.cpp:44-62
     if (b.upsample_[0] != 2 || b.upsample_[1] != 2) THROW_EXCEPTION_ARGS(FynException, "Only stride 2 transpose conv layers are supported for now");
     if (b.kernel_ != 2 && b.kernel_ != 3) THROW_EXCEPTION_ARGS(FynException, "Layer %s: transpose convolution supports 2x2 and 3x3 kernels", name_.c_str());
-    if (flags_ & LayerFlags::DEEP) THROW_EXCEPTION_ARGS(FynException, "Layer %s: deep transpose convolutions are not supported by the CUDA backend", name_.c_str());
-    if (flags_ & LayerFlags::RESIDUAL_INPUT)
-        THROW_EXCEPTION_ARGS(FynException, "Layer %s: residual input on transpose convolutions is not supported by the CUDA backend", name_.c_str());
+    // (deep::DeepTransConvLayer2x2 / 3x3 are the same class with the DEEP flag; both variants refuse a residual input like
+    // the reference: deeptransconvlayer3x3.cpp:44-46)
+    if (flags_ & LayerFlags::RESIDUAL_INPUT) THROW_EXCEPTION_ARGS(FynException, "Transpose convolutions do not support residuals as of now");
     desc_.width = width_;
     desc_.height = height_;
     desc_.in_channels = inputChannels_;
@@ -439,7 +453,7 @@ TransConvLayer::TransConvLayer(const ConvLayerBuilder &b, int layerNumber) : GPU
     desc_.kernel = b.kernel_;
     desc_.in_padding = inputPadding_;
     desc_.out_padding = outputPadding_;
-    desc_.flags = flags_ & (LayerFlags::POST_BATCHNORM | LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP);
+    desc_.flags = flags_ & (LayerFlags::POST_BATCHNORM | LayerFlags::PRE_RELU | LayerFlags::PRE_CLIP | LayerFlags::DEEP);
     desc_.leaky = leakyReLU_;
     desc_.clip_lo = lowClip_;
     desc_.clip_hi = highClip_;

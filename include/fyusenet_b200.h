@@ -329,7 +329,7 @@ typedef struct {
 int fyn_sigmoid_create(fyn_ctx *ctx, const fyn_unary_desc *desc, fyn_op **op);
 int fyn_sigmoid_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream);
 
-/* Depthwise 3x3 convolution (channel multiplier 1): vanilla::DepthwiseConvLayer3x3
+/* Depthwise 3x3 convolution: vanilla::DepthwiseConvLayer3x3
  * (fyusenet/gpu/vanilla/convlayer_dw_3x3_vanilla.cpp:22-75, shaders/vanilla/conv_dw_3x3.frag, weights
  * gpu/convweightarray_dw_KxKxNxM.cpp:120-150) and deep::DeepDepthwiseConvLayer3x3
  * (gpu/deep/deepdwconvlayer3x3.cpp, deepdwconvlayerbase.cpp:40-75, shaders/deep/deepconv_dw3x3_tiled.frag):
@@ -338,7 +338,14 @@ int fyn_sigmoid_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *str
  * POST_BATCHNORM bnScale[C], bnBias[C]; b' = b*s + beta.  The shallow shader has no dilation (taps are +-1 texel);
  * the deep variant keeps its weights fp16-truncated and its bias / scale fp16-rounded with fp16 storage, like the deep
  * convolutions.  FYN_QUIRK_DW_BN_OFFSET reproduces the shallow layer's batch-norm read position (block start instead
- * of behind the weights).  The residual input of these layers is not supported. */
+ * of behind the weights).
+ * Channel multiplier M > 1 (deep layers with channels % 4 == 0 only: the shallow layer throws, convlayer_dw_3x3_vanilla.cpp:49-50;
+ * deepdwconvlayerbase.cpp:40-44): the output has M * channels channels, output channel m * channels + c is input channel c
+ * filtered with W[c][ky][kx][m] (output tile t + m * tiles reads input tile t, deepdwconvlayerbase.cpp:288-297); data =
+ * bias[Co], W[C][3][3][M], then bnScale[Co], bnBias[Co].
+ * Residual input (FYN_FLAG_RESIDUAL_INPUT): added behind bias / batch-norm, through ReLU with FYN_FLAG_RELU_ON_RESIDUAL
+ * (shaders/vanilla/conv_dw_3x3.frag:133-140, shaders/deep/residual.inc) and, deep layers only, times the batch-norm scale with
+ * FYN_FLAG_BATCHNORM_ON_RESIDUAL. */
 typedef struct {
     int width, height, channels;
     int downsample, dilation;
@@ -346,11 +353,14 @@ typedef struct {
     unsigned flags;
     float leaky, clip_lo, clip_hi;
     int quirks;
+    int multiplier;             /* channel multiplier, 0 or 1 = one output per input channel */
+    int res_padding;
 } fyn_dwconv_desc;
 
 int fyn_dwconv3x3_create(fyn_ctx *ctx, const fyn_dwconv_desc *desc, const float *bias_weights_bn, fyn_op **op);
 int fyn_dwconv3x3_load_weights(fyn_op *op, const float *bias_weights_bn);
 int fyn_dwconv3x3_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stream);
+int fyn_dwconv3x3_run_residual(fyn_op *op, const fyn_tensor *in, const fyn_tensor *residual, fyn_tensor *out, void *stream);
 
 /* Transpose convolution, stride 2, kernels 2x2 and 3x3, shallow tensors: vanilla::TransConvLayer2x2 / TransConvLayer3x3
  * (fyusenet/gpu/vanilla/transconvlayerbase_vanilla.cpp:44-62,195-215,360-420,499-506, transconvlayer{2x2,3x3}_vanilla.cpp,
@@ -361,8 +371,13 @@ int fyn_dwconv3x3_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *s
  *        with in_padding >= 1, the clamped edge texel without).
  *   2x2: out[2j+b][2i+a] = W[b][a] * in[j][i]; with FYN_QUIRK_TRANS2X2_NEXT (reference behaviour) odd rows read input
  *        row j + 1 and odd/odd output texels input (i + 1, j + 1), while odd columns of even rows read column i.
- * Data: bias[Co], W[Co][K][K][Ci], then with POST_BATCHNORM bnScale[Co], bnBias[Co] (b' = b*s + beta).  The deep-tiled
- * variants (gpu/deep/deeptransconvlayer*.cpp) and the residual input are not implemented: FYN_ERR_UNSUPPORTED. */
+ * Data: bias[Co], W[Co][K][K][Ci], then with POST_BATCHNORM bnScale[Co], bnBias[Co] (b' = b*s + beta).
+ * FYN_FLAG_DEEP selects deep::DeepTransConvLayer2x2 / 3x3 (gpu/deep/deeptransconvlayerbase.cpp:44-232, deeptransconvlayer{2x2,3x3}.cpp,
+ * shaders/deep/deeptransconv{2x2,3x3}_stride2.{vert,frag}) on deep-tiled tensors, whose passes align the taps differently:
+ *   3x3: even o uses tap 0 on input i and tap 2 on input i - 1, odd o tap 1 on input i (per axis); 2x2: tap (o & 1) on input i
+ *   -- the full convolution of the zero-stuffed input with the kernel; reads outside the image are zero whatever the padding;
+ *   with fp16 storage the weights are fp16-truncated and bias / scale fp16-rounded like the other deep layers.
+ * A residual input is refused like in the reference ("Transpose convolutions do not support residuals as of now"). */
 typedef struct {
     int width, height;
     int in_channels, out_channels;

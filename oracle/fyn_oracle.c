@@ -661,25 +661,34 @@ int fyo_scale(const float *in_chw, int C, int H, int W, int in_pad, int deep, in
  *          applyBN then += bias), weights fp16-truncated and bias / scale through an RGBA16F texture when prec != FP32
  *          (gpu/deep/deepdwconvlayerbase.cpp:40-75,255-262).
  * data: bias[C], W[C][3][3], (bnScale[C], bnBias[C]). */
-int fyo_dwconv3x3(const float *in_chw, int C, int H, int W, int in_pad, int deep, int ds, int dil, int post_bn, int quirks,
-                  const float *wb, const fyo_act *act, int prec, float *out_chw) {
+int fyo_dwconv3x3_ex(const float *in_chw, int C, int H, int W, int in_pad, int deep, int ds, int dil, int post_bn, int quirks,
+                     const float *wb, const fyo_act *act, int prec, int mult, const float *res_chw, int res_flags, float *out_chw) {
+    /* Channel multiplier (deep layers only; the shallow layer throws for multipliers != 1, convlayer_dw_3x3_vanilla.cpp:49-50):
+     * output tile t + m * tiles(C) is input tile t filtered with multiplier m (deepdwconvlayerbase.cpp:288-297), i.e. output
+     * channel m * C + c reads input channel c with W[c][ky][kx][m] (weights [C][3][3][mult], :234-246); bias / batch-norm data
+     * are indexed by output channel (:96-125).  Residual: added after bias / batch-norm, optionally through ReLU
+     * (shaders/vanilla/conv_dw_3x3.frag:133-140; shaders/deep/residual.inc) and, for deep layers, scaled by the batch-norm
+     * scale (BATCHNORM_ON_RESIDUAL, residual.inc:9-11).  res_flags: bit 0 = ReLU on the residual, bit 1 = batch-norm on it. */
     fyo_act none = {FYO_ACT_NONE, 0, 0, 0};
     const fyo_act *a = act ? act : &none;
-    if (ds < 1 || dil < 1 || (!deep && dil != 1)) return -1;
+    if (ds < 1 || dil < 1 || (!deep && dil != 1) || mult < 1) return -1;
+    if (mult > 1 && (!deep || (C & 3))) return -1;
     int Wo = W / ds, Ho = H / ds;
     if (Wo < 1 || Ho < 1) return -1;
     int tx = 1, ty = 1;
     if (deep) fyo_deep_tiling(C, &tx, &ty);
-    const float *bn = (!deep && (quirks & 8)) ? wb : wb + C + (size_t)C * 9;
+    const int Co = C * mult;
+    const float *bn = (!deep && (quirks & 8)) ? wb : wb + Co + (size_t)C * 9 * mult;
     int reduced = deep && prec != FYO_FP32;
-    for (int c = 0; c < C; c++) {
+    for (int o = 0; o < Co; o++) {
+        const int m = o / C, c = o - m * C;
         int t = c / 4;
         int ox = deep ? in_pad + (t % tx) * (W + in_pad) : in_pad;
         int oy = deep ? in_pad + (t / tx) * (H + in_pad) : in_pad;
-        float b = wb[c], s = 1.f;
+        float b = wb[o], s = 1.f;
         if (post_bn) {
-            s = bn[c];
-            b = b * s + bn[C + c];
+            s = bn[o];
+            b = b * s + bn[Co + o];
         }
         if (reduced) {
             b = h_rn(b);
@@ -691,7 +700,7 @@ int fyo_dwconv3x3(const float *in_chw, int C, int H, int W, int in_pad, int deep
                 for (int ky = 0; ky < 3; ky++) {
                     float row = 0.f;
                     for (int kx = 0; kx < 3; kx++) {
-                        float w = wb[C + (size_t)c * 9 + ky * 3 + kx];
+                        float w = wb[Co + ((size_t)c * 9 + ky * 3 + kx) * mult + m];
                         if (reduced) w = fyo_half_trunc(w);
                         float v = act1(tex_lane(in_chw, C, H, W, in_pad, deep, c, ox + ds * xo + (kx - 1) * dil, oy + ds * yo + (ky - 1) * dil), a);
                         if (deep) row += v * w;
@@ -699,10 +708,22 @@ int fyo_dwconv3x3(const float *in_chw, int C, int H, int W, int in_pad, int deep
                     }
                     if (deep) acc += row;
                 }
-                out_chw[((size_t)c * Ho + yo) * Wo + xo] = store(acc * s + b, prec);
+                float r = acc * s + b;
+                if (res_chw) {
+                    float q = res_chw[((size_t)o * Ho + yo) * Wo + xo];
+                    if (res_flags & 1) q = q > 0.f ? q : 0.f;
+                    if ((res_flags & 2) && deep) q *= s;
+                    r += q;
+                }
+                out_chw[((size_t)o * Ho + yo) * Wo + xo] = store(r, prec);
             }
     }
     return 0;
+}
+
+int fyo_dwconv3x3(const float *in_chw, int C, int H, int W, int in_pad, int deep, int ds, int dil, int post_bn, int quirks,
+                  const float *wb, const fyo_act *act, int prec, float *out_chw) {
+    return fyo_dwconv3x3_ex(in_chw, C, H, W, in_pad, deep, ds, dil, post_bn, quirks, wb, act, prec, 1, NULL, 0, out_chw);
 }
 
 /* Transpose convolution, stride 2, shallow: gpu/vanilla/transconvlayerbase_vanilla.cpp (viewport 2W x 2H :60-62; quad maps
@@ -750,6 +771,67 @@ int fyo_transconv(const float *in_chw, int Ci, int H, int W, int in_pad, int Co,
                 out_chw[((size_t)o * Ho + yo) * Wo + xo] = store(acc * s + b, prec);
             }
     }
+    return 0;
+}
+
+/* Transpose convolution, stride 2, deep-tiled: gpu/deep/deeptransconvlayerbase.cpp (four passes selected by a stencil of the
+ * output parity, pass = (x & 1) + 2 (y & 1), :376-383 and deeptransconvlayer3x3.cpp:68-71; weights W[Co][fy][fx][Ci] as 4x4
+ * blocks per (output tile, kernel row, input tile, fx), :150-170; fp16-truncated with fp16 storage :177-186; bias RGBA16F
+ * :228-232), shaders/deep/deeptransconv3x3_stride2.{vert,frag} and deeptransconv2x2_stride2.{vert,frag}.  With texStep = half
+ * an input texel (deeptransconvlayer3x3.cpp:124-128) output texel o = 2 i + a samples
+ *   3x3: a = 0: tap 0 on input i and tap 2 on input i - 1 (vert pass 0 / 2 columns intile+0,+4; frag tc, tc - 2 step);
+ *        a = 1: tap 1 on input i (columns intile+2; frag tc - step)                       -- per axis;
+ *   2x2: tap a on input i (vert pass & 1 -> column intile + TSTEP; frag tc - step * (pass & 1)),
+ * i.e. out = the full convolution of the zero-stuffed input with the kernel, out[o] = sum_k W[k] u[o - k].  Reads outside the
+ * tile's image are ZERO whatever the padding (clampedTexture, deeptransconv3x3_stride2.frag:21-25), the prefix activation is
+ * applied to the (masked) texel (computeconv.inc).  POST_BATCHNORM: the reference writes the scales past the end of its bias
+ * array and never uploads them (deeptransconvlayerbase.cpp:219-232: the buffer has 1 + tiles texels, the scale index starts at
+ * bs / 2); this restatement uses the documented meaning, out = acc * s + (b * s + beta) -- unpinned for that flag. */
+int fyo_transconv_deep(const float *in_chw, int Ci, int H, int W, int in_pad, int Co, int K, int post_bn, const float *wb,
+                       const fyo_act *act, int prec, float *out_chw) {
+    fyo_act none = {FYO_ACT_NONE, 0, 0, 0};
+    const fyo_act *a = act ? act : &none;
+    if (K != 2 && K != 3) return -1;
+    const float *wsrc = wb + Co, *bn = wsrc + (size_t)Co * K * K * Ci;
+    const int Wo = 2 * W, Ho = 2 * H, reduced = prec != FYO_FP32;
+    for (int o = 0; o < Co; o++) {
+        float b = wb[o], s = 1.f;
+        if (post_bn) {
+            s = bn[o];
+            b = b * s + bn[Co + o];
+        }
+        if (reduced) {
+            b = h_rn(b);
+            s = h_rn(s);
+        }
+        for (int yo = 0; yo < Ho; yo++)
+            for (int xo = 0; xo < Wo; xo++) {
+                const int i = xo / 2, j = yo / 2, ox = xo & 1, oy = yo & 1;
+                int kxs[2], dxs[2], nx, kys[2], dys[2], ny;
+                if (K == 3) {
+                    if (ox) { nx = 1; kxs[0] = 1; dxs[0] = 0; } else { nx = 2; kxs[0] = 0; dxs[0] = 0; kxs[1] = 2; dxs[1] = -1; }
+                    if (oy) { ny = 1; kys[0] = 1; dys[0] = 0; } else { ny = 2; kys[0] = 0; dys[0] = 0; kys[1] = 2; dys[1] = -1; }
+                } else {
+                    nx = ny = 1;
+                    kxs[0] = ox;
+                    kys[0] = oy;
+                    dxs[0] = dys[0] = 0;
+                }
+                float acc = 0.f;
+                for (int ty = 0; ty < ny; ty++)
+                    for (int tx = 0; tx < nx; tx++) {
+                        const int x = i + dxs[tx], y = j + dys[ty];
+                        for (int c = 0; c < Ci; c++) {
+                            float v = (x < 0 || y < 0) ? 0.f : in_chw[((size_t)c * H + y) * W + x];
+                            float w = wsrc[(((size_t)o * K + kys[ty]) * K + kxs[tx]) * Ci + c];
+                            if (reduced) w = fyo_half_trunc(w);
+                            acc += act1(v, a) * w;
+                        }
+                    }
+                out_chw[((size_t)o * Ho + yo) * Wo + xo] = store(acc * s + b, prec);
+            }
+    }
+    (void)in_pad;
     return 0;
 }
 

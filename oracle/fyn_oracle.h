@@ -82,8 +82,12 @@ void fyo_scale_outdims(int W, int H, int upx, int upy, int dnx, int dny, int *Wo
 int fyo_scale(const float *in_chw, int C, int H, int W, int in_pad, int deep, int upx, int upy, int dnx, int dny,
               int linear, const fyo_act *act, int prec, float *out_chw);
 int fyo_arith(const float *in1, const float *in2, size_t n, int op, float operand, const fyo_act *act, int prec, float *out);
+int fyo_dwconv3x3_ex(const float *in_chw, int C, int H, int W, int in_pad, int deep, int ds, int dil, int post_bn, int quirks,
+                     const float *wb, const fyo_act *act, int prec, int mult, const float *res_chw, int res_flags, float *out_chw);
 int fyo_dwconv3x3(const float *in_chw, int C, int H, int W, int in_pad, int deep, int ds, int dil, int post_bn, int quirks,
                   const float *wb, const fyo_act *act, int prec, float *out_chw);
+int fyo_transconv_deep(const float *in_chw, int Ci, int H, int W, int in_pad, int Co, int K, int post_bn, const float *wb,
+                       const fyo_act *act, int prec, float *out_chw);
 int fyo_transconv(const float *in_chw, int Ci, int H, int W, int in_pad, int Co, int K, int post_bn, int quirks, const float *wb,
                   const fyo_act *act, int prec, float *out_chw);
 int fyo_rgb2bgr(const float *in_chw, int C, int H, int W, int prec, float *out_chw);

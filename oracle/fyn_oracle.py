@@ -247,14 +247,21 @@ QUIRK_DW_BN_OFFSET = 8
 QUIRK_TRANS2X2_NEXT = 16
 
 
-def transconv(x, wb, out_channels, kernel, *, in_pad=0, post_bn=False, quirks=QUIRKS_REFERENCE, act=ACT_NONE, leak=0.0, prec=FP32):
-    """Stride-2 transpose convolution (transconvlayerbase_vanilla.cpp, convtrans{2x2,3x3}_stride2.frag); shallow layout."""
+def transconv(x, wb, out_channels, kernel, *, in_pad=0, post_bn=False, quirks=QUIRKS_REFERENCE, act=ACT_NONE, leak=0.0, prec=FP32, deep=False):
+    """Stride-2 transpose convolution; shallow layout (transconvlayerbase_vanilla.cpp, convtrans{2x2,3x3}_stride2.frag) or, with
+    deep=True, the deep-tiled variant (deeptransconvlayerbase.cpp, deeptransconv{2x2,3x3}_stride2.*: other tap alignment, zero
+    outside the image, fp16-truncated weights with fp16 storage)."""
     x = _f32(x)
     wb = _f32(wb)
     ci, h, w = x.shape
     assert wb.size >= out_channels * (1 + kernel * kernel * ci) + (2 * out_channels if post_bn else 0)
     out = np.zeros((out_channels, 2 * h, 2 * w), np.float32)
     a = _act(act, leak)
+    if deep:
+        rc = lib().fyo_transconv_deep(_fp(x), ci, h, w, int(in_pad), int(out_channels), int(kernel), int(bool(post_bn)), _fp(wb), C.byref(a), int(prec), _fp(out))
+        if rc != 0:
+            raise RuntimeError(f"fyo_transconv_deep failed rc={rc}")
+        return out
     rc = lib().fyo_transconv(_fp(x), ci, h, w, int(in_pad), int(out_channels), int(kernel), int(bool(post_bn)), int(quirks), _fp(wb),
                              C.byref(a), int(prec), _fp(out))
     if rc != 0:
@@ -262,16 +269,24 @@ def transconv(x, wb, out_channels, kernel, *, in_pad=0, post_bn=False, quirks=QU
     return out
 
 
-def dwconv3x3(x, wb, *, downsample=1, dilation=1, in_pad=0, deep=False, post_bn=False, quirks=0, act=ACT_NONE, leak=0.0, prec=FP32):
-    """Depthwise 3x3 convolution (convlayer_dw_3x3_vanilla.cpp / deepdwconvlayer3x3.cpp); wb = bias[C], W[C][3][3], (bn)."""
+def dwconv3x3(x, wb, *, downsample=1, dilation=1, in_pad=0, deep=False, post_bn=False, quirks=0, act=ACT_NONE, leak=0.0, prec=FP32,
+              multiplier=1, residual=None, relu_on_residual=False, bn_on_residual=False):
+    """Depthwise 3x3 convolution (convlayer_dw_3x3_vanilla.cpp / deepdwconvlayer3x3.cpp); wb = bias[Co], W[C][3][3][mult], (bn) with
+    Co = C * mult; output channel m * C + c = input channel c through multiplier m (deep layers only for mult > 1)."""
     x = _f32(x)
     wb = _f32(wb)
     c, h, w = x.shape
-    assert wb.size >= c * 10 + (2 * c if post_bn and not (quirks & QUIRK_DW_BN_OFFSET and not deep) else 0)
-    out = np.zeros((c, h // downsample, w // downsample), np.float32)
+    co = c * multiplier
+    assert wb.size >= co + c * 9 * multiplier + (2 * co if post_bn and not (quirks & QUIRK_DW_BN_OFFSET and not deep) else 0)
+    out = np.zeros((co, h // downsample, w // downsample), np.float32)
     a = _act(act, leak)
-    rc = lib().fyo_dwconv3x3(_fp(x), c, h, w, int(in_pad), int(bool(deep)), int(downsample), int(dilation), int(bool(post_bn)),
-                             int(quirks), _fp(wb), C.byref(a), int(prec), _fp(out))
+    res = None
+    if residual is not None:
+        res = _f32(residual)
+        assert res.shape == out.shape
+    rc = lib().fyo_dwconv3x3_ex(_fp(x), c, h, w, int(in_pad), int(bool(deep)), int(downsample), int(dilation), int(bool(post_bn)),
+                                int(quirks), _fp(wb), C.byref(a), int(prec), int(multiplier), _fp(res) if res is not None else None,
+                                (1 if relu_on_residual else 0) | (2 if bn_on_residual else 0), _fp(out))
     if rc != 0:
         raise RuntimeError(f"fyo_dwconv3x3 failed rc={rc}")
     return out

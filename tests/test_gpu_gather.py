@@ -235,6 +235,48 @@ def test_depthwise_conv3x3(deep, dtype):
 
 
 @pytest.mark.parametrize("dtype", [capi.F16, capi.F32])
+@pytest.mark.parametrize("deep,mult", [(False, 1), (True, 1), (True, 2), (True, 3)])
+def test_depthwise_conv3x3_multiplier_and_residual(deep, mult, dtype):
+    """Channel multiplier > 1 (deep layers, deepdwconvlayerbase.cpp:40-44,234-246,288-297) and the residual input with its
+    ReLU / batch-norm options (conv_dw_3x3.frag:133-140, shaders/deep/residual.inc) against the oracle."""
+    c = ctx()
+    rng = np.random.default_rng(33 + mult)
+    ch, h, w = (16, 14, 18) if deep else (10, 9, 12)
+    co = ch * mult
+    x = rng.normal(size=(2, ch, h, w)).astype(np.float32)
+    res = rng.normal(size=(2, co, h, w)).astype(np.float32)
+    wb = np.concatenate([rng.uniform(-0.5, 0.5, co), rng.normal(size=ch * 9 * mult) * 0.4, rng.uniform(0.5, 1.5, co), rng.uniform(-0.2, 0.2, co)]).astype(np.float32)
+    for bn, relu_res, bn_res, rp in [(False, False, False, 0), (True, True, False, 1), (True, False, True, 0)]:
+        if bn_res and not deep:
+            with pytest.raises(capi.FynError):
+                capi.DwConv3x3(c, wb, width=w, height=h, channels=ch, in_padding=1, flags=capi.FLAG_RESIDUAL_INPUT | capi.FLAG_BATCHNORM_ON_RESIDUAL)
+            continue
+        flags = (capi.FLAG_DEEP if deep else 0) | (capi.FLAG_POST_BATCHNORM if bn else 0) | capi.FLAG_PRE_RELU | capi.FLAG_RESIDUAL_INPUT | \
+                (capi.FLAG_RELU_ON_RESIDUAL if relu_res else 0) | (capi.FLAG_BATCHNORM_ON_RESIDUAL if bn_res else 0)
+        op = capi.DwConv3x3(c, wb, width=w, height=h, channels=ch, in_padding=1, out_padding=1, flags=flags, quirks=0, multiplier=mult, res_padding=rp)
+        tin = c.tensor(w, h, ch, 1, ORDER[deep], dtype, 2)
+        tres = c.tensor(w, h, co, rp, ORDER[deep], dtype, 2)
+        tout = c.tensor(w, h, co, 1, ORDER[deep], dtype, 2)
+        tin.write_chw(x)
+        tres.write_chw(res)
+        op.run(tin, tout, residual=tres)
+        y = tout.read_chw()
+        xs, prec = _prep(x, dtype)
+        rs, _ = _prep(res, dtype)
+        kw = dict(in_pad=1, deep=deep, post_bn=bn, quirks=0, act=fo.ACT_RELU, multiplier=mult, relu_on_residual=relu_res, bn_on_residual=bn_res)
+        ref = np.stack([fo.dwconv3x3(xs[i], wb, prec=prec, residual=rs[i], **kw) for i in range(2)])
+        if dtype == capi.F32:
+            np.testing.assert_allclose(y, ref, rtol=2e-5, atol=2e-5)
+        else:
+            assert_close_f16(y, ref, np.stack([fo.dwconv3x3(xs[i], wb, prec=fo.FP32, residual=rs[i], **kw) for i in range(2)]), rl2=3e-3)
+        for o in (tin, tres, tout, op):
+            o.destroy()
+    if not deep:
+        with pytest.raises(capi.FynError):          # the shallow layer has no channel multiplier (convlayer_dw_3x3_vanilla.cpp:49-50)
+            capi.DwConv3x3(c, np.zeros(ch * 2 * 12, np.float32), width=w, height=h, channels=ch, multiplier=2)
+
+
+@pytest.mark.parametrize("dtype", [capi.F16, capi.F32])
 @pytest.mark.parametrize("kernel", [2, 3])
 def test_transpose_conv_stride2(kernel, dtype):
     """vanilla::TransConvLayer2x2 / 3x3 against the oracle (3x3: checked against the pinned convolution oracle on the
@@ -266,7 +308,40 @@ def test_transpose_conv_stride2(kernel, dtype):
         _border_is_zero(tout, op_)
         for o in (tin, tout, op):
             o.destroy()
-    with pytest.raises(capi.FynError):
-        capi.TransConv2d(c, np.zeros(1000, np.float32), width=4, height=4, in_channels=4, out_channels=4, kernel=3, flags=capi.FLAG_DEEP)
+    with pytest.raises(capi.FynError):               # no residual input, like the reference (deeptransconvlayer3x3.cpp:44-46)
+        capi.TransConv2d(c, np.zeros(1000, np.float32), width=4, height=4, in_channels=4, out_channels=4, kernel=3, flags=capi.FLAG_RESIDUAL_INPUT)
     with pytest.raises(capi.FynError):
         capi.TransConv2d(c, np.zeros(1000, np.float32), width=4, height=4, in_channels=4, out_channels=4, kernel=5)
+
+
+@pytest.mark.parametrize("dtype", [capi.F16, capi.F32])
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_deep_transpose_conv_stride2(kernel, dtype):
+    """deep::DeepTransConvLayer2x2 / 3x3 (deeptransconvlayerbase.cpp, deeptransconv{2x2,3x3}_stride2.*) on deep-tiled tensors against
+    the oracle, which tests/test_oracle_arith_scale.py checks against the pinned convolution oracle on the zero-stuffed input.
+    Several input / output tiles, padded and un-padded tensors (reads outside the image are zero either way).  Tolerance:
+    FYN_F32 2e-5, FYN_F16 1 fp16 ulp of the fp16-store oracle (truncated weights, rounded bias)."""
+    c = ctx()
+    rng = np.random.default_rng(51 + kernel)
+    for ci, co, h, w, ip, op_, bn, relu in [(6, 5, 7, 9, 1, 0, False, False), (12, 20, 8, 10, 1, 1, True, True), (64, 32, 14, 14, 0, 1, False, True),
+                                            (3, 8, 5, 6, 0, 0, False, True)]:
+        x = rng.normal(size=(2, ci, h, w)).astype(np.float32)
+        wb = np.concatenate([rng.uniform(-0.5, 0.5, co), rng.normal(size=co * kernel * kernel * ci) * (0.6 / np.sqrt(ci)), rng.uniform(0.5, 1.5, co),
+                             rng.uniform(-0.2, 0.2, co)]).astype(np.float32)
+        flags = capi.FLAG_DEEP | (capi.FLAG_POST_BATCHNORM if bn else 0) | (capi.FLAG_PRE_RELU if relu else 0)
+        op = capi.TransConv2d(c, wb, width=w, height=h, in_channels=ci, out_channels=co, kernel=kernel, in_padding=ip, out_padding=op_, flags=flags)
+        tin = c.tensor(w, h, ci, ip, capi.ORDER_DEEP, dtype, 2)
+        tout = c.tensor(2 * w, 2 * h, co, op_, capi.ORDER_DEEP, dtype, 2)
+        tin.write_chw(x)
+        op.run(tin, tout)
+        y = tout.read_chw()
+        xs, prec = _prep(x, dtype)
+        kw = dict(in_pad=ip, post_bn=bn, act=fo.ACT_RELU if relu else fo.ACT_NONE, deep=True)
+        ref = np.stack([fo.transconv(xs[i], wb, co, kernel, prec=prec, **kw) for i in range(2)])
+        assert y.shape == ref.shape == (2, co, 2 * h, 2 * w)
+        if dtype == capi.F32:
+            np.testing.assert_allclose(y, ref, rtol=2e-5, atol=2e-5)
+        else:
+            assert_close_f16(y, ref, np.stack([fo.transconv(xs[i], wb, co, kernel, prec=fo.FP32, **kw) for i in range(2)]), rl2=4e-3)
+        for o in (tin, tout, op):
+            o.destroy()

@@ -122,6 +122,36 @@ def test_dwconv_equals_block_diagonal_convolution(deep):
         np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("deep,mult", [(False, 1), (True, 1), (True, 2), (True, 3)])
+def test_dwconv_multiplier_and_residual_equal_sparse_convolution(deep, mult):
+    """Channel multiplier (deep only: output channel m * C + c = input channel c through W[c][.][.][m], deepdwconvlayerbase.cpp:234-246,
+    288-297) and the residual input (conv_dw_3x3.frag:133-140, shaders/deep/residual.inc) against the pinned regular convolution with
+    the corresponding sparse weight matrix."""
+    rng = np.random.default_rng(9 + mult)
+    c, h, w = 8, 9, 11
+    co = c * mult
+    x = rng.normal(size=(c, h, w)).astype(np.float32)
+    bias = rng.uniform(-0.5, 0.5, co).astype(np.float32)
+    wk = rng.normal(size=(c, 3, 3, mult)).astype(np.float32)
+    bn = np.concatenate([rng.uniform(0.5, 1.5, co), rng.uniform(-0.2, 0.2, co)]).astype(np.float32)
+    res = rng.normal(size=(co, h, w)).astype(np.float32)
+    full = np.zeros((co, 3, 3, c), np.float32)
+    for m in range(mult):
+        for i in range(c):
+            full[m * c + i, :, :, i] = wk[i, :, :, m]
+    for post_bn, relu_res, bn_res in [(False, False, False), (False, True, False), (True, True, False), (True, False, True)]:
+        if bn_res and not deep:
+            continue                             # the shallow shader has no batch-norm on its residual
+        wb_dw = np.concatenate([bias, wk.reshape(-1)] + ([bn] if post_bn else []))
+        wb_full = np.concatenate([bias, full.reshape(-1)] + ([bn] if post_bn else []))
+        fl = (fo.POST_BATCHNORM if post_bn else 0) | (fo.RELU_ON_RESIDUAL if relu_res else 0) | (fo.BATCHNORM_ON_RESIDUAL if bn_res else 0)
+        ref = fo.conv2d(x, wb_full, co, 3, in_pad=1, flags=fl, deep=deep, residual=res)
+        got = fo.dwconv3x3(x, wb_dw, in_pad=1, deep=deep, post_bn=post_bn, multiplier=mult, residual=res, relu_on_residual=relu_res, bn_on_residual=bn_res)
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        fo.dwconv3x3(x, np.zeros(co * 10 * 2, np.float32), multiplier=2, deep=False)      # shallow layers have no multiplier
+
+
 def test_dwconv_quirk_and_precision():
     rng = np.random.default_rng(6)
     c, h, w = 6, 5, 7
@@ -190,3 +220,31 @@ def test_transconv2x2_strata():
     np.testing.assert_allclose(q[:, 1::2, 1::2], np.einsum("oc,chw->ohw", wk[:, 1, 1, :], xp[:, 1:, 1:]) + bias[:, None, None], rtol=1e-5, atol=1e-5)
     with pytest.raises(RuntimeError):
         fo.transconv(x, np.zeros(co * (1 + 16 * ci), np.float32), co, 4)
+
+
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_deep_transconv_is_the_full_convolution_of_the_zero_stuffed_input(kernel):
+    """deep::DeepTransConvLayer2x2 / 3x3 (deeptransconv{2x2,3x3}_stride2.{vert,frag}): out[o] = sum_k W[k] u[o - k] with u the
+    zero-stuffed input -- checked against the pinned regular-convolution oracle run with the flipped kernel on u shifted by one
+    texel (zero padding supplies the texels outside the image, which the deep shader masks to zero)."""
+    rng = np.random.default_rng(41 + kernel)
+    ci, co, h, w = 6, 5, 5, 7
+    x = rng.normal(size=(ci, h, w)).astype(np.float32)
+    bias = rng.uniform(-0.5, 0.5, co).astype(np.float32)
+    wk = rng.normal(size=(co, kernel, kernel, ci)).astype(np.float32)
+    wb = np.concatenate([bias, wk.reshape(-1)])
+    got = fo.transconv(x, wb, co, kernel, deep=True)
+    # 3x3 kernel holding the (2x2 or 3x3) taps, flipped; zero-stuffed input with one leading zero row / column
+    k3 = np.zeros((co, 3, 3, ci), np.float32)
+    k3[:, :kernel, :kernel] = wk
+    flipped = k3[:, ::-1, ::-1].copy()
+    u = np.zeros((ci, 2 * h + 1, 2 * w + 1), np.float32)
+    u[:, 1::2, 1::2] = x
+    ref = fo.conv2d(u, np.concatenate([bias, flipped.reshape(-1)]), co, 3, in_pad=1)[:, :2 * h, :2 * w]
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)
+    # prefix activation applies to the fetched (and masked) texel; fp16 storage truncates the weights
+    relu = fo.transconv(x, wb, co, kernel, deep=True, act=fo.ACT_RELU)
+    np.testing.assert_allclose(relu, fo.transconv(np.maximum(x, 0), wb, co, kernel, deep=True), rtol=1e-6, atol=1e-6)
+    h16 = fo.transconv(fo.half_round(x), wb, co, kernel, deep=True, prec=fo.FP16_STORE)
+    np.testing.assert_allclose(h16, got, rtol=2e-2, atol=2e-2)
+    assert not np.array_equal(h16, got)
