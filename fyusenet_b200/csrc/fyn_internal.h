@@ -72,6 +72,7 @@ struct TView {
     int texW, texH;  // clamp bounds
     int W, H, P;
     int tx;          // tiles per texture row (deep)
+    int tileRows;    // rows of tiles (deep)
     int tileW, tileH;  // W+P, H+P (deep)
     long long planeElems, imageElems;
 };

@@ -1,7 +1,9 @@
 // fyn_layers.cu -- bandwidth-bound layers: pooling, batch-norm, sigmoid.
 // One thread per output texel (4 channels), 8-byte (fp16) / 16-byte (fp32) vector accesses,
 // consecutive threads on consecutive x so every warp touches contiguous texel runs.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "fyn_internal.h"
@@ -60,6 +62,139 @@ __global__ void __launch_bounds__(128) k_pool(const PoolArgs a) {
         }
     if (!a.isMax) r = make_float4(r.x * a.inv, r.y * a.inv, r.z * a.inv, r.w * a.inv);
     fyn_store_texel(a.out, n, t, a.outP + xo, a.outP + yo, r);
+}
+
+// fp16 RGBA tensors, windows up to 3x3: a block stages the input rows of a strip of output rows of ONE tile / plane in shared
+// memory with consecutive lanes on consecutive texels (every texel crosses L2 -> SM once, whole 32-byte sectors), then
+// computes the strip from shared memory.  k_pool above fetches the window per output texel: with stride 2 every load
+// instruction uses half of each sector and a texel is requested ~2.25 times (measured on ResNet-50's MaxPool4 at batch 128:
+// 151 us = 27 % of the copy bandwidth; this kernel: see profiles/r02_bandwidth_layers.md).
+template <int PX, int PY>
+__global__ void __launch_bounds__(256) k_pool_rows(const PoolArgs a, int RO, int NC) {
+    extern __shared__ uint2 sPool[];
+    const int strips = (a.Ho + RO - 1) / RO;
+    unsigned bid = blockIdx.x;
+    const int strip = bid % strips;
+    bid /= strips;
+    const int t = bid % a.tiles, n = bid / a.tiles;
+    const int yo0 = strip * RO, ro = min(RO, a.Ho - yo0);
+    const int NR = a.dy * (ro - 1) + PY;
+    const int bx0 = a.in.P + a.off + (a.in.deep ? (t % a.in.tx) * a.in.tileW : 0);
+    const int by0 = a.in.P + a.dy * yo0 + a.off + (a.in.deep ? (t / a.in.tx) * a.in.tileH : 0);
+    const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems + (a.in.deep ? 0ll : (long long)t * a.in.planeElems);
+    // staging: consecutive threads on consecutive texels of the staged window, eight loads in flight per thread (with one load
+    // per thread and iteration the SMs held ~14 KB in flight and the kernel waited on the long scoreboard)
+    const unsigned total = (unsigned)(NR * NC), magicNC = (unsigned)((1ull << 32) / (unsigned)NC) + 1u;   // total * NC < 2^32
+    for (unsigned base = threadIdx.x; base < total; base += 256u * 8u) {
+        uint2 raw[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const unsigned idx = base + u * 256u;
+            if (idx < total) {
+                const unsigned r = __umulhi(idx, magicNC), c = idx - r * (unsigned)NC;
+                const int Y = min(max(by0 + (int)r, 0), a.in.texH - 1), X = min(max(bx0 + (int)c, 0), a.in.texW - 1);
+                raw[u] = __ldg(reinterpret_cast<const uint2 *>(src + ((long long)Y * a.in.texW + X) * 4));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const unsigned idx = base + u * 256u;
+            if (idx < total) sPool[idx] = raw[u];
+        }
+    }
+    __syncthreads();
+    __half *dst = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + (a.out.deep ? 0ll : (long long)t * a.out.planeElems);
+    const int ox0 = a.outP + (a.out.deep ? (t % a.out.tx) * a.out.tileW : 0), oy0 = a.outP + (a.out.deep ? (t / a.out.tx) * a.out.tileH : 0);
+    // Max pooling with ReLU / no prefix activation stays in fp16: the maximum of fp16 values is exact, and
+    // max_i relu(x_i) = max(max_i x_i, 0) -- also with the reference's un-activated third column (deepmaxpool.frag:12-61), since
+    // at least one column is activated.  Four packed min/max instructions per tap instead of a dozen fp32 ones: the kernel was
+    // issue-bound (ncu: issue active 53 %, 430 instructions per output texel).
+    if (a.isMax && a.act.type <= 1) {
+        const __half2 floor2 = a.act.type == 1 ? __float2half2_rn(0.f) : __half2half2(__ushort_as_half((unsigned short)0xfc00));
+        for (int o = threadIdx.x; o < ro * a.Wo; o += 256) {
+            const int yl = o / a.Wo, xo = o - yl * a.Wo;
+            const uint2 *w = sPool + (a.dy * yl) * NC + a.dx * xo;
+            __half2 m0 = floor2, m1 = floor2;
+#pragma unroll
+            for (int j = 0; j < PY; j++)
+#pragma unroll
+                for (int i = 0; i < PX; i++) {
+                    const uint2 raw = w[j * NC + i];
+                    m0 = __hmax2(m0, *reinterpret_cast<const __half2 *>(&raw.x));
+                    m1 = __hmax2(m1, *reinterpret_cast<const __half2 *>(&raw.y));
+                }
+            uint2 q;
+            q.x = *reinterpret_cast<const unsigned *>(&m0);
+            q.y = *reinterpret_cast<const unsigned *>(&m1);
+            *reinterpret_cast<uint2 *>(dst + ((long long)(oy0 + yo0 + yl) * a.out.texW + ox0 + xo) * 4) = q;
+        }
+        return;
+    }
+    for (int o = threadIdx.x; o < ro * a.Wo; o += 256) {
+        const int yl = o / a.Wo, xo = o - yl * a.Wo;
+        float4 r = a.isMax ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < PY; j++)
+#pragma unroll
+            for (int i = 0; i < PX; i++) {
+                const uint2 raw = sPool[(a.dy * yl + j) * NC + a.dx * xo + i];
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+                float4 v = make_float4(f0.x, f0.y, f1.x, f1.y);
+                if (!(a.quirk3 && i == 2)) v = fyn_act4(v, a.act);
+                if (a.isMax) {
+                    r.x = fmaxf(r.x, v.x);
+                    r.y = fmaxf(r.y, v.y);
+                    r.z = fmaxf(r.z, v.z);
+                    r.w = fmaxf(r.w, v.w);
+                } else {
+                    r.x += v.x;
+                    r.y += v.y;
+                    r.z += v.z;
+                    r.w += v.w;
+                }
+            }
+        if (!a.isMax) r = make_float4(r.x * a.inv, r.y * a.inv, r.z * a.inv, r.w * a.inv);
+        const __half2 h0 = __floats2half2_rn(r.x, r.y), h1 = __floats2half2_rn(r.z, r.w);
+        uint2 q;
+        q.x = *reinterpret_cast<const unsigned *>(&h0);
+        q.y = *reinterpret_cast<const unsigned *>(&h1);
+        *reinterpret_cast<uint2 *>(dst + ((long long)(oy0 + yo0 + yl) * a.out.texW + ox0 + xo) * 4) = q;
+    }
+}
+
+// Global pooling of fp16 deep-tiled tensors (ResNet-50: 7x7x2048 -> 1x1): a block owns one ROW of tiles of one image, thread =
+// texture column; it sums its column over the tile's rows (consecutive lanes read consecutive texels of a texture row), the
+// per-tile reduction over the tile's columns goes through shared memory.  k_pool_warp below reads a tile as H runs of W
+// texels (56-byte runs for 7x7) with one warp per output: 11 % of the copy bandwidth at batch 512.
+__global__ void __launch_bounds__(256) k_pool_global_deep(const PoolArgs a) {
+    extern __shared__ float4 sCol[];
+    const int trow = blockIdx.x % a.in.tileRows, n = blockIdx.x / a.in.tileRows;
+    const int W = a.in.W, H = a.in.H, P = a.in.P;
+    const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems + ((long long)(P + trow * a.in.tileH) * a.in.texW) * 4;
+    for (int X = threadIdx.x; X < a.in.texW; X += 256) {
+        float4 acc = a.isMax ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int y = 0; y < H; y++) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(src + ((long long)y * a.in.texW + X) * 4));
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+            const float4 v = fyn_act4(make_float4(f0.x, f0.y, f1.x, f1.y), a.act);
+            if (a.isMax) acc = make_float4(fmaxf(acc.x, v.x), fmaxf(acc.y, v.y), fmaxf(acc.z, v.z), fmaxf(acc.w, v.w));
+            else acc = make_float4(acc.x + v.x, acc.y + v.y, acc.z + v.z, acc.w + v.w);
+        }
+        sCol[X] = acc;
+    }
+    __syncthreads();
+    for (int tc = threadIdx.x; tc < a.in.tx; tc += 256) {
+        const int t = trow * a.in.tx + tc;
+        if (t >= a.tiles) break;
+        float4 acc = sCol[P + tc * a.in.tileW];
+        for (int x = 1; x < W; x++) {
+            const float4 v = sCol[P + tc * a.in.tileW + x];
+            if (a.isMax) acc = make_float4(fmaxf(acc.x, v.x), fmaxf(acc.y, v.y), fmaxf(acc.z, v.z), fmaxf(acc.w, v.w));
+            else acc = make_float4(acc.x + v.x, acc.y + v.y, acc.z + v.z, acc.w + v.w);
+        }
+        if (!a.isMax) acc = make_float4(acc.x * a.inv, acc.y * a.inv, acc.z * a.inv, acc.w * a.inv);
+        fyn_store_texel(a.out, n, t, a.outP, a.outP, acc);
+    }
 }
 
 // large windows (global pooling): one warp per output texel, lanes stride over the window, shuffle reduction
@@ -192,11 +327,45 @@ __global__ void __launch_bounds__(256) k_eltwise_h8(const EltArgs a, long long p
     }
 }
 
+// fp16 shallow tensors WITHOUT padding and with identical geometry on both sides are one flat array: 16 bytes (two texels) per
+// access, four accesses in flight per thread, one 32-bit division per access (batch-norm only: the plane selects the
+// parameters).  k_eltwise_h8 above spends three 64-bit divisions per access on its (row, plane, image) decomposition.
+__global__ void __launch_bounds__(256) k_eltwise_flat(const EltArgs a, unsigned units, unsigned unitsPerPlane) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.in.ptr);
+    uint4 *dst = reinterpret_cast<uint4 *>(a.out.ptr);
+    for (unsigned base = blockIdx.x * 1024u + threadIdx.x; base < units; base += gridDim.x * 1024u) {
+        uint4 raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned i = base + u * 256u;
+            if (i < units) raw[u] = __ldg(src + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned i = base + u * 256u;
+            if (i >= units) break;
+            const int t = a.mode == 0 ? (int)((i / unitsPerPlane) % (unsigned)a.tiles) : 0;
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[u].x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[u].y));
+            const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[u].z)), f3 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[u].w));
+            const float4 r0 = elt_apply(a, make_float4(f0.x, f0.y, f1.x, f1.y), t);
+            const float4 r1 = elt_apply(a, make_float4(f2.x, f2.y, f3.x, f3.y), t);
+            const __half2 h0 = __floats2half2_rn(r0.x, r0.y), h1 = __floats2half2_rn(r0.z, r0.w), h2 = __floats2half2_rn(r1.x, r1.y), h3 = __floats2half2_rn(r1.z, r1.w);
+            uint4 o;
+            o.x = *reinterpret_cast<const unsigned *>(&h0);
+            o.y = *reinterpret_cast<const unsigned *>(&h1);
+            o.z = *reinterpret_cast<const unsigned *>(&h2);
+            o.w = *reinterpret_cast<const unsigned *>(&h3);
+            dst[i] = o;
+        }
+    }
+}
+
 // fp16 path for everything else (deep-tiled textures, odd paddings): a block owns a chunk of one 4-channel plane, so the
 // plane / tile arithmetic is block-uniform and a texel costs one division; one texel (8 bytes) per access, U accesses
 // in flight per thread.
+// (p / W through a multiplication: magic = floor(2^32 / W) + 1 is exact while p * W < 2^32, which the launcher checks)
 template <int U>
-__global__ void __launch_bounds__(256) k_eltwise_h4(const EltArgs a, unsigned W, unsigned HW, unsigned chunks) {
+__global__ void __launch_bounds__(256) k_eltwise_h4(const EltArgs a, unsigned W, unsigned HW, unsigned chunks, unsigned magic) {
     unsigned bid = blockIdx.x;
     const unsigned chunk = bid % chunks;
     bid /= chunks;
@@ -225,7 +394,7 @@ __global__ void __launch_bounds__(256) k_eltwise_h4(const EltArgs a, unsigned W,
         const unsigned p = p0 + u * 256u;
         oo[u] = ~0u;
         if (p < HW) {
-            const unsigned y = p / W, x = p - y * W;
+            const unsigned y = magic ? __umulhi(p, magic) : p / W, x = p - y * W;
             oo[u] = (y * a.out.texW + x) * 4;
             raw[u] = __ldg(reinterpret_cast<const uint2 *>(src + (y * a.in.texW + x) * 4));
         }
@@ -280,7 +449,16 @@ static int launch_eltwise(fyn_ctx *ctx, const EltArgs &a, int W, int H, cudaStre
     const bool fast = a.in.dtype == FYN_F16 && a.out.dtype == FYN_F16 && a.in.packing == 4 && a.out.packing == 4 && !a.in.deep &&
                       !a.out.deep && (W % 2 == 0) && (a.in.texW % 2 == 0) && (a.out.texW % 2 == 0) && (a.in.P % 2 == 0) && (a.outP % 2 == 0) &&
                       (a.in.planeElems % 8 == 0) && (a.out.planeElems % 8 == 0);
-    if (fast) {
+    const long long flatUnits = (long long)a.batch * a.in.imageElems / 8;
+    const bool flat = a.in.dtype == FYN_F16 && a.out.dtype == FYN_F16 && a.in.packing == 4 && a.out.packing == 4 && !a.in.deep && !a.out.deep && a.in.P == 0 &&
+                      a.outP == 0 && a.in.texW == a.out.texW && a.in.texH == a.out.texH && a.in.planeElems == a.out.planeElems &&
+                      a.in.imageElems == a.out.imageElems && a.in.imageElems == (long long)a.tiles * a.in.planeElems && (a.in.planeElems % 8) == 0 &&
+                      flatUnits < (1ll << 31) && (((uintptr_t)a.in.ptr | (uintptr_t)a.out.ptr) & 15) == 0;
+    if (flat) {
+        const long long cap = (long long)ctx->prop.multiProcessorCount * 8;
+        const long long blocks = std::min<long long>((flatUnits + 1023) / 1024, cap);
+        k_eltwise_flat<<<(unsigned)blocks, 256, 0, stream>>>(a, (unsigned)flatUnits, (unsigned)(a.in.planeElems / 8));
+    } else if (fast) {
         const long long pairsPerRow = W / 2, rows = (long long)a.batch * a.tiles * H;
         const long long total = pairsPerRow * rows;
         long long blocks = (total + 1023) / 1024;
@@ -300,10 +478,11 @@ static int launch_eltwise(fyn_ctx *ctx, const EltArgs &a, int W, int H, cudaStre
         const int U = HW > 1024 ? 8 : (HW > 512 ? 4 : (HW > 256 ? 2 : 1));
         const unsigned chunks = (HW + 256u * U - 1) / (256u * U);
         const unsigned blocks = chunks * (unsigned)a.tiles * (unsigned)a.batch;
-        if (U == 8) k_eltwise_h4<8><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks);
-        else if (U == 4) k_eltwise_h4<4><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks);
-        else if (U == 2) k_eltwise_h4<2><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks);
-        else k_eltwise_h4<1><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks);
+        const unsigned magic = ((unsigned long long)(HW + 256u * U) * (unsigned)W < (1ull << 32) && W > 1) ? (unsigned)((1ull << 32) / (unsigned)W) + 1u : 0u;
+        if (U == 8) k_eltwise_h4<8><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks, magic);
+        else if (U == 4) k_eltwise_h4<4><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks, magic);
+        else if (U == 2) k_eltwise_h4<2><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks, magic);
+        else k_eltwise_h4<1><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks, magic);
     } else {
         long long blocks = (long long)((W + 31) / 32) * ((H + 3) / 4) * a.tiles * a.batch;
         k_eltwise<<<(unsigned)blocks, dim3(32, 4), 0, stream>>>(a);
@@ -378,6 +557,29 @@ int fyn_pool2d_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stre
     a.act = fyn_act_from_flags(d.flags, d.leaky, d.clip_lo, d.clip_hi);
     long long blocks = grid_blocks(a.Wo, a.Ho, a.tiles, a.batch);
     const long long outs = (long long)a.Wo * a.Ho * a.tiles * a.batch;
+    const bool h4 = in->desc.dtype == FYN_F16 && out->desc.dtype == FYN_F16 && in->geom.packing == 4 && out->geom.packing == 4;
+    static const bool noRows = getenv("FYN_POOL_SIMPLE") != nullptr;       // (measurement knob: the per-texel kernels)
+    if (h4 && !noRows && d.global && deep && a.in.deep && a.out.deep && !a.quirk3 && a.px * a.py >= 16 && (size_t)a.in.texW * 16 <= 48 * 1024) {
+        // (the order of the additions differs from k_pool_warp's; both are within the 1-ulp bound of the fp16-store oracle)
+        k_pool_global_deep<<<(unsigned)(a.in.tileRows * a.batch), 256, (size_t)a.in.texW * 16, (cudaStream_t)stream>>>(a);
+        FYN_CHECK_LAUNCH(op->ctx);
+        return FYN_OK;
+    }
+    if (h4 && !noRows && !d.global && a.px <= 3 && a.py <= 3 && a.px == a.py && a.px >= 2) {
+        const int NC = a.dx * (a.Wo - 1) + a.px;
+        int RO = (int)((32 * 1024 / ((size_t)NC * 8) - a.py) / a.dy) + 1;
+        RO = std::max(1, std::min(RO, a.Ho));
+        // enough blocks for every SM: shorter strips on small grids
+        while (RO > 2 && (long long)((a.Ho + RO - 1) / RO) * a.tiles * a.batch < 4ll * op->ctx->prop.multiProcessorCount) RO = (RO + 1) / 2;
+        const size_t smem = (size_t)(a.dy * (RO - 1) + a.py) * NC * 8;
+        if (smem <= 48 * 1024) {
+            const unsigned grid = (unsigned)(((a.Ho + RO - 1) / RO) * (long long)a.tiles * a.batch);
+            if (a.px == 3) k_pool_rows<3, 3><<<grid, 256, smem, (cudaStream_t)stream>>>(a, RO, NC);
+            else k_pool_rows<2, 2><<<grid, 256, smem, (cudaStream_t)stream>>>(a, RO, NC);
+            FYN_CHECK_LAUNCH(op->ctx);
+            return FYN_OK;
+        }
+    }
     if (a.px * a.py >= 32 && !a.quirk3)
         k_pool_warp<<<(unsigned)((outs + 3) / 4), dim3(32, 4), 0, (cudaStream_t)stream>>>(a);
     else if (a.px == 3 && a.py == 3)

@@ -71,6 +71,7 @@ TView fyn_make_view(const fyn_tensor *t) {
     v.H = t->desc.height;
     v.P = t->desc.padding;
     v.tx = t->geom.tiles_x;
+    v.tileRows = t->geom.tiles_y;
     v.tileW = t->desc.width + t->desc.padding;
     v.tileH = t->desc.height + t->desc.padding;
     v.planeElems = (long long)t->geom.plane_elems;

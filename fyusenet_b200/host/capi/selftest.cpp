@@ -168,6 +168,16 @@ extern "C" int fynhost_selftest(char *report, int cap) {
         gpu::ConvLayerBuilder dw5(5, "dw5");
         dw5.groupSize(8).shape(8, 4, 4, 8).type(LayerType::CONVOLUTION2D).number(1);
         r.check(throws([&] { backend.createLayer(LayerType::CONVOLUTION2D, reinterpret_cast<LayerBuilder *>(&dw5), 1); }), "5x5 depthwise convolution throws");
+        // channel multipliers: deep layers with input channels % 4 == 0 only (convlayer_dw_3x3_vanilla.cpp:49-50, deepdwconvlayerbase.cpp:40-44)
+        gpu::ConvLayerBuilder dwm(3, "dwm");
+        dwm.groupSize(8).shape(16, 4, 4, 8).type(LayerType::CONVOLUTION2D).number(1);
+        r.check(throws([&] { backend.createLayer(LayerType::CONVOLUTION2D, reinterpret_cast<LayerBuilder *>(&dwm), 1); }), "shallow depthwise convolution with a channel multiplier throws");
+        gpu::ConvLayerBuilder dwm6(3, "dwm6");
+        dwm6.groupSize(6).shape(12, 4, 4, 6).deep().type(LayerType::CONVOLUTION2D).number(1);
+        r.check(throws([&] { backend.createLayer(LayerType::CONVOLUTION2D, reinterpret_cast<LayerBuilder *>(&dwm6), 1); }), "deep channel multiplier needs input channels % 4 == 0");
+        gpu::ConvLayerBuilder tcr(3, "tcr");
+        tcr.shape(8, 4, 4, 8).deep().upsample(2).residual(ActType::NONE).type(LayerType::TRANSCONVOLUTION2D).number(1);
+        r.check(throws([&] { backend.createLayer(LayerType::TRANSCONVOLUTION2D, reinterpret_cast<LayerBuilder *>(&tcr), 1); }), "transpose convolution with a residual input throws");
     }
     // ---- host tensors (cpubuffershape.cpp:430-447, cpubuffer.cpp:121-158)
     {
