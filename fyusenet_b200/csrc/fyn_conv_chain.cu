@@ -42,6 +42,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda.h>      // CUtensorMap and the cuTensorMapEncodeTiled prototype (resolved at run time through cudaGetDriverEntryPoint)
+
 #include "fyn_internal.h"
 #include "fyn_tc_common.cuh"
 
@@ -59,6 +61,12 @@ struct ChainLayer {
 };
 
 struct ChainArgs {
+    // tensor maps of the rotating input images: [rows of all images][chunk][pixel][8 x fp16], box = one strip row
+    // (all chunks x rowpx pixels): a row arrives by ONE cp.async.bulk.tensor (SASS UTMALDG)
+    // (in global memory, written once by the host: with the maps inside this struct the kernel parameters exceeded 4 KB and
+    // the whole kernel ran 13 % slower -- the MMA issuers read their step table from the parameter bank)
+    const CUtensorMap *tmap;
+    int useTma;
     TView in, out;                    // chain input / output tensors (shallow plane layout, fp16, packing 4)
     __half *A[kChainBufs];
     __half *R;
@@ -121,6 +129,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
     return t;
 }
 #define CTRACE(seg, ev) do { if (tb >= 0 && (seg) < 64) g_ctrace[tb][seg][ev] = gtimer(); } while (0)
+__device__ unsigned long long g_jtrace[128][4];
+#define JTRACE(job, ev) do { if (tb == 1 && (job) < 128) g_jtrace[job][ev] = gtimer(); } while (0)
 #define CPROF_DECL(n) long long n = 0
 #define CPROF_T() clock64()
 #define CPROF_ADD(acc, t0) acc += clock64() - (t0)
@@ -131,7 +141,15 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define CPROF_ADD(acc, t0)
 #define CPROF_ON(x)
 #define CTRACE(seg, ev)
+#define JTRACE(job, ev)
 #endif
+
+// one strip row through the tensor map: box [1 row][nchunks][rowpx pixels][8 halves] -> one ring slot, completion on `bar`
+__device__ __forceinline__ void tma_load_row(void *dst, const CUtensorMap *map, uint64_t *bar, int px, int row) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(0), "r"(px), "r"(0), "r"(row)
+                 : "memory");
+}
 
 struct Ring {
     int slot, fill;
@@ -298,6 +316,23 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
                             }
                             if (lane == 0 && rb == 0 && b0 == 0) CTRACE(l * a.nsub + h, 1);
                             [[maybe_unused]] const long long pt = CPROF_T();
+                            if (a.useTma) {
+                                // one tensor copy per row (one lane each): box = all chunks x rowpx pixels of image row yr
+                                const int rl = b0 + lane;
+                                if (rl < b1) {
+                                    int slot = slot0 + rb + rl, fill = fill0;
+                                    while (slot >= a.nslots) {
+                                        slot -= a.nslots;
+                                        fill++;
+                                    }
+                                    mbar_wait(&empty[slot], (fill & 1) ^ 1);
+                                    mbar_expect_tx(&full[slot], (uint32_t)a.nchunks * chunkBytes);
+                                    tma_load_row(sRing + (size_t)slot * a.slotBytes, &a.tmap[l % kChainBufs], &full[slot], j0, n * a.imgRows + tex_row(rb + rl));
+                                }
+                                __syncwarp();
+                                CPROF_ADD(pIssue, pt);
+                                continue;
+                            }
                             // one (row, chunk) copy per lane: ceil(rows * nchunks / 32) copy instructions per group
                             const int items = (b1 - b0) * a.nchunks;
                             for (int it = lane; it < items; it += 32) {
@@ -379,6 +414,7 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
                         // ... the rest (rows the other warp's windows needed, this warp's did not) once they have been seen
                         for (; k < start; k++, rr.next(a.nslots)) umma_commit(&empty[rr.slot]);
                         if (q == 0) CTRACE(l * a.nsub + h, 3);
+                        JTRACE(Qg, 0);
                         const int winSlot = win.slot;
                         // (bottom -> top layers walk the window rows in reverse, with the kernel rows reversed in their weight
                         // image: the products enter the accumulator in the same order as in a top -> bottom layer, bit for bit)
@@ -393,6 +429,7 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
                         }
                         if (a.biasFolded) umma_f16(d, hiA | (uint64_t)onesDesc, hiA | (uint64_t)(a.biasB16 + bconst), a.idesc, 1u);
                         CPROF_ADD(pIss, pt);
+                        JTRACE(Qg, 1);
                         pt = CPROF_T();
                         umma_commit(&tfull[mw]);
                         CPROF_ADD(pCommit, pt);
@@ -609,6 +646,7 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
                     [[maybe_unused]] long long pt = CPROF_T();
                     mbar_wait(&tfull[buf], use & 1);
                     CPROF_ADD(pWaitTf, pt);
+                    if (etid == 0) JTRACE(Qg, 2);
                     pt = CPROF_T();
                     tc_fence_after();
                     const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * 64u + (uint32_t)(part * NOCT) * 8u;
@@ -673,6 +711,7 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
                         }
                     }
                     CPROF_ADD(pSt, pt);
+                    if (etid == 0) JTRACE(Qg, 3);
                     if (!LAST) {
                         // hand the job's stores to the publisher: count this thread into the job once the buffer's previous
                         // job (two jobs back) is complete -- which it practically always is
@@ -710,6 +749,11 @@ __global__ void __launch_bounds__(512, 1) k_conv_tc_chain(const __grid_constant_
     __syncthreads();
     if (warp == mmaWarp0) tmem_dealloc(tmem, 128);
 #ifdef FYN_CHAIN_PROFILE
+    if (tb == 1 && threadIdx.x == 0) {
+        for (int j = 40; j < 62; j++)
+            printf("[chain job] %3d: mma ready %7lld issued %7lld | epilogue sees %7lld stored %7lld (ns)\n", j, (long long)(g_jtrace[j][0] - g_jtrace[40][0]),
+                   (long long)(g_jtrace[j][1] - g_jtrace[40][0]), (long long)(g_jtrace[j][2] - g_jtrace[40][0]), (long long)(g_jtrace[j][3] - g_jtrace[40][0]));
+    }
     if (tb >= 0 && threadIdx.x == 0) {
         const unsigned long long base = g_ctrace[0][0][0];
         for (int sg = 0; sg < a.nlayers * a.nsub && sg < 64; sg++)
@@ -732,6 +776,8 @@ struct fyn_conv_chain {
     ChainArgs args{};
     __half *images = nullptr;            // kChainBufs input images + the raw image, one allocation
     unsigned long long *progress = nullptr;
+    CUtensorMap *tmaps = nullptr;        // device copy of the tensor maps of the input images
+    bool tmapsOk = false;
     int batchAlloc = 0;
     unsigned long long epoch = 0;
     size_t smemBytes = 0;
@@ -820,7 +866,8 @@ int fyn_conv_chain_create(fyn_ctx *ctx, fyn_op *const *ops, const int *residual_
     a.rowpx = p0.rowpx;
     a.K = K;
     a.mh = mh;
-    a.slotBytes = p0.slotBytes;
+    a.slotBytes = (p0.slotBytes + 127) & ~127;     // ring slots start on 128-byte boundaries (destination of the tensor copies)
+    if (getenv("FYN_CHAIN_ALIGN") && atoi(getenv("FYN_CHAIN_ALIGN")) == 0) a.slotBytes = p0.slotBytes;   // (measurement knob; implies plain bulk copies)
     a.nmirror = 0;
     a.biasFolded = p0.biasFolded;
     a.biasB16 = p0.biasB16;
@@ -862,19 +909,16 @@ int fyn_conv_chain_create(fyn_ctx *ctx, fyn_op *const *ops, const int *residual_
     // ring: as many slots as shared memory holds (two weight images, epilogue parameters, barriers)
     const size_t wpad = ((size_t)a.wbytes + 127) & ~(size_t)127;
     const size_t optin = (size_t)ctx->prop.sharedMemPerBlockOptin;
-    const size_t fixed = 2 * wpad + 64 * 16 + (2 * 24 + 8) * 8 + 16 + 128;
-    if (optin <= fixed) {
-        delete c;
-        return chain_fail_unsupported("weight images do not fit shared memory twice");
-    }
-    int total = (int)std::min<size_t>((optin - fixed) / (size_t)a.slotBytes, 24);
-    if (const char *e = getenv("FYN_CHAIN_SLOTS")) total = std::min(total, atoi(e) + a.nmirror);
-    a.nslots = std::min(24, total - a.nmirror);
+    auto footprint = [&](int ns) { return 2 * wpad + (size_t)ns * a.slotBytes + 64 * 16 + (2 * (size_t)ns + 8) * 8 + 16; };
+    int ns = 24;
+    if (const char *e = getenv("FYN_CHAIN_SLOTS")) ns = std::max(1, std::min(24, atoi(e)));
+    while (ns > 0 && footprint(ns) > optin) ns--;
+    a.nslots = ns;
     if (a.nslots < 2 * K) {
         delete c;
         return chain_fail_unsupported("ring does not fit shared memory");
     }
-    c->smemBytes = 2 * wpad + (size_t)(a.nslots + a.nmirror) * a.slotBytes + 64 * 16 + (2 * (size_t)a.nslots + 8) * 8 + 16;
+    c->smemBytes = footprint(a.nslots);
     *out = c;
     return FYN_OK;
 }
@@ -926,6 +970,8 @@ int fyn_conv_chain_run(fyn_conv_chain *c, const fyn_tensor *in, fyn_tensor *out,
         c->progress = nullptr;
         FYN_CUDA(cudaMalloc((void **)&c->images, imgBytes * (kChainBufs + 1)));
         FYN_CUDA(cudaMemset(c->images, 0, imgBytes * (kChainBufs + 1)));          // zero borders, never written afterwards
+        if (!c->tmaps) FYN_CUDA(cudaMalloc((void **)&c->tmaps, sizeof(CUtensorMap) * kChainBufs));
+        c->tmapsOk = false;
         FYN_CUDA(cudaMalloc((void **)&c->progress, progCount * sizeof(unsigned long long)));
         FYN_CUDA(cudaMemset(c->progress, 0, progCount * sizeof(unsigned long long)));
         FYN_CUDA(cudaDeviceSynchronize());
@@ -936,6 +982,40 @@ int fyn_conv_chain_run(fyn_conv_chain *c, const fyn_tensor *in, fyn_tensor *out,
     a.R = c->images + (size_t)kChainBufs * (imgBytes / 2);
     a.progress = c->progress;
     a.epoch = ++c->epoch;
+    // tensor maps of the input images: encoded once per allocation, kept in device memory
+    {
+        using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                      const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = [] {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+            return reinterpret_cast<EncodeFn>(fn);
+        }();
+        // FYN_CHAIN_TMA=1: rows through the tensor map (cp.async.bulk.tensor, one instruction per row).  Default: `nchunks` plain
+        // bulk copies per row issued by as many lanes -- measured faster (trunk 123.9 us against 128.8 us with the tensor
+        // map): the box is a handful of 2 KB runs either way, and the plain copies of a group of rows go out in parallel.
+        static const bool tmaOn = getenv("FYN_CHAIN_TMA") && atoi(getenv("FYN_CHAIN_TMA")) != 0;
+        const bool want = encode && tmaOn && a.rowpx <= 256 && a.nchunks <= 256 && (a.slotBytes & 127) == 0;
+        if (want && !c->tmapsOk) {
+            alignas(64) CUtensorMap maps[kChainBufs];
+            bool ok = true;
+            for (int b = 0; b < kChainBufs && ok; b++) {
+                const cuuint64_t dims[4] = {8, (cuuint64_t)a.pitchPx, (cuuint64_t)a.nchunks, (cuuint64_t)a.imgRows * a.batch};
+                const cuuint64_t strides[3] = {16, (cuuint64_t)a.pitchPx * 16, (cuuint64_t)a.nchunks * a.pitchPx * 16};
+                const cuuint32_t box[4] = {8, (cuuint32_t)a.rowpx, (cuuint32_t)a.nchunks, 1};
+                const cuuint32_t estr[4] = {1, 1, 1, 1};
+                ok = encode(&maps[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.A[b], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            }
+            if (ok) {
+                FYN_CUDA(cudaMemcpy(c->tmaps, maps, sizeof(maps), cudaMemcpyHostToDevice));
+                c->tmapsOk = true;
+            }
+        }
+        a.useTma = (want && c->tmapsOk) ? 1 : 0;
+        a.tmap = c->tmaps;
+    }
     // (hot-swapped weights re-pack in place; odd layers sweep bottom -> top and use the image with the kernel rows reversed)
     for (size_t i = 0; i < c->ops.size(); i++) a.layer[i].wimg = c->ops[i]->tc->chainImage((i & 1) != 0);
     a.in = fyn_make_view(in);
@@ -978,6 +1058,7 @@ int fyn_conv_chain_destroy(fyn_conv_chain *c) {
     cudaSetDevice(c->ctx->device);
     if (c->images) cudaFree(c->images);
     if (c->progress) cudaFree(c->progress);
+    if (c->tmaps) cudaFree(c->tmaps);
     delete c;
     return FYN_OK;
 }

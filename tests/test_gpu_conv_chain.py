@@ -116,7 +116,7 @@ def test_chain_batch_and_strip_variants(monkeypatch):
     want = _run_one_by_one(c, ops, rfrom, x, 2, w, h, ch, 0)
     np.testing.assert_array_equal(_run_chain(c, ops, rfrom, x, 2, w, h, ch, 0)[0], want)
     for env in ({"FYN_CHAIN_SH": "13"}, {"FYN_CHAIN_NSUB": "1"}, {"FYN_CHAIN_SH": "1"}, {"FYN_CHAIN_SLOTS": "6"}, {"FYN_CHAIN_SLOTS": "8", "FYN_CHAIN_SH": "2"},
-                {"FYN_CHAIN_EPI": "8"}, {"FYN_CHAIN_NSUB": "3", "FYN_CHAIN_SH": "2"}, {"FYN_CHAIN_NSUB": "4", "FYN_CHAIN_SH": "1"}, {"FYN_CHAIN_NSUB": "4", "FYN_CHAIN_SH": "3"}):
+                {"FYN_CHAIN_EPI": "8"}, {"FYN_CHAIN_TMA": "1"}, {"FYN_CHAIN_FENCE": "3"}, {"FYN_CHAIN_NSUB": "3", "FYN_CHAIN_SH": "2"}, {"FYN_CHAIN_NSUB": "4", "FYN_CHAIN_SH": "1"}, {"FYN_CHAIN_NSUB": "4", "FYN_CHAIN_SH": "3"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         np.testing.assert_array_equal(_run_chain(c, ops, rfrom, x, 2, w, h, ch, 0)[0], want, err_msg=str(env))
