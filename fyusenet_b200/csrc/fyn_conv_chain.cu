@@ -995,7 +995,7 @@ int fyn_conv_chain_run(fyn_conv_chain *c, const fyn_tensor *in, fyn_tensor *out,
         // FYN_CHAIN_TMA=1: rows through the tensor map (cp.async.bulk.tensor, one instruction per row).  Default: `nchunks` plain
         // bulk copies per row issued by as many lanes -- measured faster (trunk 123.9 us against 128.8 us with the tensor
         // map): the box is a handful of 2 KB runs either way, and the plain copies of a group of rows go out in parallel.
-        static const bool tmaOn = getenv("FYN_CHAIN_TMA") && atoi(getenv("FYN_CHAIN_TMA")) != 0;
+        const bool tmaOn = getenv("FYN_CHAIN_TMA") && atoi(getenv("FYN_CHAIN_TMA")) != 0;      // (read per run: tests switch it)
         const bool want = encode && tmaOn && a.rowpx <= 256 && a.nchunks <= 256 && (a.slotBytes & 127) == 0;
         if (want && !c->tmapsOk) {
             alignas(64) CUtensorMap maps[kChainBufs];
