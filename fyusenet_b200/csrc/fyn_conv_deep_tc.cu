@@ -55,6 +55,9 @@ struct DeepTcArgs {
     ActParams act;
     int hasRes, reluRes, bnRes;
     int inP, outP, resP;
+    // persistent kernel: tiles (m tile, n tile) are numbered n-fastest and taken round robin by the CTAs
+    int ntilesN, epiWarps;
+    long long totalTiles;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -328,6 +331,282 @@ __global__ void __launch_bounds__(kThreadsDeep, 2) k_conv_deep_tc(const __grid_c
     if (warp == loadWarps) tmem_dealloc(tmem, tmemCols);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent variant for large grids (batched inference): ONE CTA per SM walks the output tiles (n tile fastest, round
+// robin over the CTAs, so that the CTAs working on the N tiles of one pixel tile run at the same time and share its texels
+// through L2).  The roles no longer share threads, so the three phases of a tile overlap with those of its neighbours:
+//   * loader sets (4 x 128 threads) gather stage after stage, across tile boundaries, as far ahead as the ring allows;
+//   * the MMA warp accumulates tile i into one half of TMEM (2 x NT columns) while
+//   * eight epilogue warps (two per TMEM lane quarter, splitting the column groups) drain tile i-1 from the other half:
+//     tcgen05.ld -> *scale + bias (+ residual, fetched two column groups ahead) -> fp16 texels.
+// Same arithmetic and accumulation order as k_conv_deep_tc: the two kernels produce identical bits (tests compare them).
+// ---------------------------------------------------------------------------------------------
+constexpr int kWarpsP = 25;          // 4 x loader sets + 1 MMA warp + epilogue warps; the split is chosen per layer (args.nsets / args.epiWarps)
+constexpr int kMaxRingP = 8;
+constexpr int kThreadsDeepP = kWarpsP * 32;
+
+// tile -> (pixel tile, n tile) of a CTA's tile sequence b, b + G, b + 2G, ... without a division per tile
+struct TileWalk {
+    int mt, nt, dM, dN, ntilesN;
+    long long tile, total, G;
+    __device__ __forceinline__ TileWalk(const DeepTcArgs &a) {
+        ntilesN = a.ntilesN;
+        G = gridDim.x;
+        total = a.totalTiles;
+        tile = blockIdx.x;
+        mt = (int)(blockIdx.x / (unsigned)ntilesN);
+        nt = (int)(blockIdx.x % (unsigned)ntilesN);
+        dM = (int)(gridDim.x / (unsigned)ntilesN);
+        dN = (int)(gridDim.x % (unsigned)ntilesN);
+    }
+    __device__ __forceinline__ bool done() const { return tile >= total; }
+    __device__ __forceinline__ void next() {
+        tile += G;
+        mt += dM;
+        nt += dN;
+        if (nt >= ntilesN) {
+            nt -= ntilesN;
+            mt++;
+        }
+    }
+};
+
+template <bool NORM>
+__global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __grid_constant__ DeepTcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int bStageBytes = a.NT * kKC * 2;
+    const int nOutPlanes = a.Cout4 >> 2;
+    unsigned char *sA = smem;
+    unsigned char *sB = sA + a.ring * kAStageBytes;
+    float4 *sScale = reinterpret_cast<float4 *>(sB + a.ring * bStageBytes);   // [nOutPlanes] scale, then [nOutPlanes] bias
+    float4 *sBias = sScale + nOutPlanes;
+    int *inOrigin = reinterpret_cast<int *>(sBias + nOutPlanes);             // [nInPlanes]
+    int *outOrigin = inOrigin + a.nInPlanes;                                  // [nOutPlanes] output tensor, then [nOutPlanes] residual tensor
+    int *resOrigin = outOrigin + nOutPlanes;
+    int *tapTab = resOrigin + nOutPlanes;                                     // [64]
+    int *stageTab = tapTab + 64;                                              // [nstages] ky | kx << 8 | kc << 16
+    uint64_t *full = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(stageTab + a.nstages) + 7) & ~uintptr_t(7));
+    uint64_t *empty = full + kMaxRingP;
+    uint64_t *accFull = empty + kMaxRingP;
+    uint64_t *accEmpty = accFull + 2;
+    uint32_t *tmemBase = reinterpret_cast<uint32_t *>(accEmpty + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int loadWarps = 4 * a.nsets, nthreads = kThreadsDeepP;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.ring; s++) {
+            mbar_init(&full[s], kM + 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&accFull[b], 1);
+            mbar_init(&accEmpty[b], (uint32_t)a.epiWarps);
+        }
+        fence_barrier_init();
+    }
+    const uint32_t tmemCols = a.NT > 128 ? 512u : (a.NT > 64 ? 256u : 128u);
+    if (warp == loadWarps) tmem_alloc(tmemBase, tmemCols);
+    for (int q = threadIdx.x; q < a.nInPlanes && !a.tapPacked; q += nthreads) inOrigin[q] = ((q / a.in.tx) * a.in.tileH * a.in.texW + (q % a.in.tx) * a.in.tileW) * 4;
+    for (int p = threadIdx.x; p < nOutPlanes; p += nthreads) {
+        outOrigin[p] = ((p / a.out.tx) * a.out.tileH * a.out.texW + (p % a.out.tx) * a.out.tileW) * 4;
+        resOrigin[p] = a.hasRes ? ((p / a.res.tx) * a.res.tileH * a.res.texW + (p % a.res.tx) * a.res.tileW) * 4 : 0;
+        // (the parameters are constants of the layer, not results of the previous kernel: read ahead of griddepcontrol.wait)
+        sScale[p] = __ldg(reinterpret_cast<const float4 *>(a.scale) + p);
+        sBias[p] = __ldg(reinterpret_cast<const float4 *>(a.bias) + p);
+    }
+    if (a.tapPacked && threadIdx.x < 64) {
+        const int tp = min((int)threadIdx.x, a.K * a.K - 1);
+        tapTab[threadIdx.x] = (tp / a.K) | ((tp % a.K) << 8);
+    }
+    for (int st = threadIdx.x; st < a.nstages; st += nthreads) {
+        const int tap = st / a.kcs, kc = st - tap * a.kcs;
+        stageTab[st] = (tap / a.K) | ((tap % a.K) << 8) | (kc << 16);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmemBase;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const unsigned hw = (unsigned)(a.Ho * a.Wo), Mtotal = (unsigned)a.Mtotal;
+
+    if (warp < loadWarps) {
+        // ===================== loaders: thread = GEMM row = output pixel; set `set` takes every nsets-th stage of the CTA's stage stream
+        const int t = threadIdx.x & (kM - 1), set = warp >> 2;
+        int s = set;                                       // tile-local index of the set's next stage
+        int slot = set;                                    // ring slot / phase of that stage (nsets <= ring)
+        uint32_t phase = 0;
+        for (TileWalk w(a); !w.done(); w.next(), s -= a.nstages) {
+            if (s >= a.nstages) continue;                  // (tiles of fewer stages than sets: nothing of this tile is ours)
+            const unsigned m = (unsigned)w.mt * kM + t;
+            const bool valid = m < Mtotal;
+            const unsigned n = valid ? m / hw : 0u;
+            const unsigned rem = valid ? m - n * hw : 0u;
+            const int yo = (int)(rem / (unsigned)a.Wo), xo = (int)rem - yo * a.Wo;
+            const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems;
+            const uint4 *wsrc = a.wimg + (size_t)w.nt * a.nstages * (bStageBytes >> 4);
+            const __half *px0 = src + ((a.inP + a.ds * yo - a.mh) * a.in.texW + a.inP + a.ds * xo - a.mh) * 4;
+            for (; s < a.nstages; s += a.nsets) {
+                const int st = slot;
+                const int tab = stageTab[s];
+                const int ky = tab & 255, kx = (tab >> 8) & 255, kc = tab >> 16;
+                mbar_wait(&empty[st], phase ^ 1);
+                if (t == 0) {
+                    mbar_expect_tx(&full[st], (uint32_t)bStageBytes);
+                    bulk_g2s(sB + (size_t)st * bStageBytes, wsrc + (size_t)s * (bStageBytes >> 4), (uint32_t)bStageBytes, &full[st]);
+                }
+                uint2 v[kKC / 4];
+                if (!a.tapPacked) {
+                    const __half *px = px0 + (ky * a.in.texW + kx) * 4;
+                    const int *org = inOrigin + kc * (kKC / 4);
+#pragma unroll
+                    for (int j = 0; j < kKC / 4; j++) v[j] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + org[j])) : make_uint2(0u, 0u);
+                    if (NORM) {
+                        const float4 *sc = a.inNorm + kc * (kKC / 4), *bi = sc + a.nInPlanes;
+#pragma unroll
+                        for (int j = 0; j < kKC / 4; j++) {
+                            const float4 s4 = __ldg(sc + j), b4 = __ldg(bi + j);
+                            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&v[j].x));
+                            const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&v[j].y));
+                            v[j] = make_uint2(pack_half2(fmaf(f0.x, s4.x, b4.x), fmaf(f0.y, s4.y, b4.y)), pack_half2(fmaf(f1.x, s4.z, b4.z), fmaf(f1.y, s4.w, b4.w)));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kKC / 4; j++) {
+                        const int tt = tapTab[s * (kKC / 4) + j];
+                        const int tky = tt & 255, tkx = tt >> 8;
+                        const int iy = min(max(a.inP + a.ds * yo + tky - a.mh, 0), a.in.texH - 1);
+                        const int ix = min(max(a.inP + a.ds * xo + tkx - a.mh, 0), a.in.texW - 1);
+                        v[j] = valid ? __ldg(reinterpret_cast<const uint2 *>(src + (iy * a.in.texW + ix) * 4)) : make_uint2(0u, 0u);
+                    }
+                }
+                unsigned char *dst = sA + (size_t)st * kAStageBytes + t * 16;
+#pragma unroll
+                for (int c = 0; c < kKC / 8; c++) {
+                    const uint2 lo = act_h4(v[2 * c], a.act), hi = act_h4(v[2 * c + 1], a.act);
+                    *reinterpret_cast<uint4 *>(dst + c * (kM * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+                }
+                fence_proxy_async();
+                mbar_arrive(&full[st]);
+                slot += a.nsets;
+                if (slot >= a.ring) {
+                    slot -= a.ring;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == loadWarps) {
+        // ===================== MMA issuer: tile i accumulates into TMEM half (i & 1)
+        const uint64_t hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
+        const uint32_t aLbo = ((uint32_t)(kM * 16) >> 4) << 16, bLbo = ((uint32_t)(a.NT * 16) >> 4) << 16;
+        if (elect_one()) {
+            int slot = 0;
+            uint32_t phase = 0, tcount = 0;
+            for (TileWalk w(a); !w.done(); w.next(), tcount++) {
+                const uint32_t buf = tcount & 1;
+                mbar_wait(&accEmpty[buf], ((tcount >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem + buf * (uint32_t)a.NT;
+                for (int s = 0; s < a.nstages; s++) {
+                    mbar_wait(&full[slot], phase);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA + (size_t)slot * kAStageBytes) >> 4, b0 = smem_u32(sB + (size_t)slot * bStageBytes) >> 4;
+#pragma unroll
+                    for (int j = 0; j < kKC / 16; j++)
+                        umma_f16(tacc, hi | (uint64_t)(aLbo | (a0 + (uint32_t)(j * 2 * kM))), hi | (uint64_t)(bLbo | (b0 + (uint32_t)(j * 2 * a.NT))), a.idesc,
+                                 (s > 0 || j > 0) ? 1u : 0u);
+                    umma_commit(&empty[slot]);
+                    if (++slot == a.ring) {
+                        slot = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&accFull[buf]);
+            }
+        }
+        __syncwarp();
+    } else if (warp < loadWarps + 1 + a.epiWarps) {
+        // ===================== epilogue: warp quarter = TMEM lanes, the warps of a quarter alternate over the column groups
+        const int e = warp - loadWarps - 1, quarter = warp & 3, part = e >> 2, lane = threadIdx.x & 31;
+        const int parts = a.epiWarps >> 2;
+        const int t = quarter * 32 + lane;
+        const int ngroups = a.NT >> 4;
+        uint32_t tcount = 0;
+        for (TileWalk w(a); !w.done(); w.next(), tcount++) {
+            const uint32_t buf = tcount & 1;
+            const unsigned m = (unsigned)w.mt * kM + t;
+            const bool valid = m < Mtotal;
+            const unsigned n = valid ? m / hw : 0u;
+            const unsigned rem = valid ? m - n * hw : 0u;
+            const int yo = (int)(rem / (unsigned)a.Wo), xo = (int)rem - yo * a.Wo;
+            __half *outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((a.outP + yo) * a.out.texW + a.outP + xo) * 4;
+            const __half *resp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems + ((a.resP + yo) * a.res.texW + a.resP + xo) * 4;
+            const int plane0 = w.nt * (a.NT >> 2);
+            auto fetch_res = [&](int cg, uint2 (&rq)[4]) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int pk = plane0 + cg * 4 + k;
+                    rq[k] = (a.hasRes && valid && cg < ngroups && pk < nOutPlanes) ? __ldg(reinterpret_cast<const uint2 *>(resp + resOrigin[pk])) : make_uint2(0u, 0u);
+                }
+            };
+            uint2 rq0[4], rq1[4];
+            fetch_res(part, rq0);
+            fetch_res(part + parts, rq1);
+            mbar_wait(&accFull[buf], (tcount >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)a.NT;
+            bool released = false;
+            auto do_group = [&](int cg, uint2 (&rq)[4]) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + cg * 16, acc);
+                tmem_ld_wait();
+                if (cg + parts >= ngroups) {
+                    // last column group of this warp: the accumulator half may be overwritten once every warp has read its share
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&accEmpty[buf]);
+                    released = true;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int pk = plane0 + cg * 4 + k;
+                    if (!valid || pk >= nOutPlanes) continue;
+                    const float4 sc = sScale[pk], bi = sBias[pk];
+                    float4 r = make_float4(fmaf(__uint_as_float(acc[4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[4 * k + 1]), sc.y, bi.y),
+                                           fmaf(__uint_as_float(acc[4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[4 * k + 3]), sc.w, bi.w));
+                    if (a.hasRes) {
+                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&rq[k].x));
+                        const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&rq[k].y));
+                        float4 q = make_float4(f0.x, f0.y, f1.x, f1.y);
+                        if (a.reluRes) q = make_float4(fmaxf(q.x, 0.f), fmaxf(q.y, 0.f), fmaxf(q.z, 0.f), fmaxf(q.w, 0.f));
+                        if (a.bnRes) q = make_float4(q.x * sc.x, q.y * sc.y, q.z * sc.z, q.w * sc.w);
+                        r.x += q.x;
+                        r.y += q.y;
+                        r.z += q.z;
+                        r.w += q.w;
+                    }
+                    *reinterpret_cast<uint2 *>(outp + outOrigin[pk]) = make_uint2(pack_half2(r.x, r.y), pack_half2(r.z, r.w));
+                }
+                fetch_res(cg + 2 * parts, rq);
+            };
+            for (int cg = part; cg < ngroups; cg += 2 * parts) {
+                do_group(cg, rq0);
+                if (cg + parts < ngroups) do_group(cg + parts, rq1);
+            }
+            if (!released) {   // (fewer column groups than warps per quarter: this warp had nothing to read)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&accEmpty[buf]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == loadWarps) tmem_dealloc(tmem, tmemCols);
+}
+
 }  // namespace
 
 struct DeepTcPlan {
@@ -496,6 +775,57 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
         ntiles = plan->wideNtiles;
         planSmem = plan->wideSmemBytes;
     }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool noPdl = getenv("FYN_TC_NO_PDL") != nullptr;   // debugging aid: plain stream-ordered launches
+    // Large grids: the persistent kernel (one CTA per SM, gathers / MMAs / epilogues of neighbouring tiles overlapped).
+    // FYN_DEEP_PERSIST=0 keeps the one-tile-per-CTA kernel (read per run: tests compare the two).
+    const char *pe = getenv("FYN_DEEP_PERSIST");
+    const int sms = op->ctx->prop.multiProcessorCount;
+    if ((!pe || atoi(pe) != 0) && mtiles * ntiles >= (pe && atoi(pe) == 2 ? 1ll : 2ll * sms)) {
+        a.ntilesN = ntiles;
+        a.totalTiles = mtiles * ntiles;
+        const size_t stageBytes = (size_t)kAStageBytes + (size_t)a.NT * kKC * 2;
+        const size_t fixed = (size_t)(a.Cout4 / 4) * 32 + ((size_t)a.nInPlanes + 2 * (size_t)(a.Cout4 / 4) + 64 + a.nstages) * 4 + 8 + (2 * kMaxRingP + 4) * 8 + 16;
+        const size_t budget = (size_t)op->ctx->prop.sharedMemPerBlockOptin - 1024;
+        int ring = (int)std::min<size_t>(kMaxRingP, fixed < budget ? (budget - fixed) / stageBytes : 0);
+        if (const char *e = getenv("FYN_DEEP_PRING")) ring = std::max(1, std::min(ring, atoi(e)));
+        if (ring >= 2 && a.totalTiles < (1ll << 31) - 2 * sms && a.Mtotal < (1ll << 31) - 2 * kM) {
+            a.ring = ring;
+            // 24 worker warps split between gathering and draining: a tile costs the loaders nstages gathers of 16 KB and the
+            // epilogue NT / 16 column groups of 4 texels per pixel (plus as many residual texels)
+            const double loadWork = (double)a.nstages, epiWork = (a.NT / 16) * (a.hasRes ? 1.5 : 1.0) * 0.5;
+            a.nsets = epiWork > 2.0 * loadWork ? 2 : (epiWork > loadWork ? 3 : 4);
+            if (const char *e = getenv("FYN_DEEP_SETS")) a.nsets = std::max(1, std::min(4, atoi(e)));
+            a.nsets = std::min(a.nsets, ring);
+            a.epiWarps = 24 - 4 * a.nsets;
+            if (a.nsets < 2) a.epiWarps = 16;   // (a TMEM lane quarter is drained by at most four warps here)
+            const size_t smemP = (size_t)ring * stageBytes + fixed;
+            static size_t maxSmemP[64] = {0};
+            static std::mutex lockP;
+            {
+                std::lock_guard<std::mutex> guard(lockP);
+                size_t &cur = maxSmemP[op->ctx->device & 63];
+                if (smemP > cur) {
+                    FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_p<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
+                    FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
+                    cur = smemP;
+                }
+            }
+            cudaLaunchConfig_t pc{};
+            pc.gridDim = dim3((unsigned)std::min<long long>(a.totalTiles, sms));
+            pc.blockDim = dim3(kThreadsDeepP);
+            pc.dynamicSmemBytes = smemP;
+            pc.stream = stream;
+            pc.attrs = attr;
+            pc.numAttrs = noPdl ? 0 : 1;
+            if (a.inNorm) FYN_CUDA(cudaLaunchKernelEx(&pc, k_conv_deep_tc_p<true>, a));
+            else FYN_CUDA(cudaLaunchKernelEx(&pc, k_conv_deep_tc_p<false>, a));
+            FYN_CHECK_LAUNCH(op->ctx);
+            return FYN_OK;
+        }
+    }
     dim3 grid((unsigned)mtiles, (unsigned)ntiles);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
@@ -514,11 +844,7 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     }
     cfg.dynamicSmemBytes = smemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    static const bool noPdl = getenv("FYN_TC_NO_PDL") != nullptr;   // debugging aid: plain stream-ordered launches
     cfg.numAttrs = noPdl ? 0 : 1;
     if (a.inNorm) FYN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_deep_tc<true>, a));
     else FYN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_deep_tc<false>, a));

@@ -4,6 +4,8 @@
 // One thread per output texel (4 channels); every source texel goes through fyn_fetch(), i.e. the clamp-to-edge
 // sampler of the reference's textures (base/buffermanager.cpp:657-670) in the tensor's own (planar or tiled) layout.
 #include <cmath>
+#include <cstdlib>
+#include <cstdint>
 #include <cstring>
 
 #include "fyn_internal.h"
@@ -109,6 +111,176 @@ __global__ void __launch_bounds__(128) k_gather(const __grid_constant__ GatherAr
         r = fyn_act4(fyn_fetch(a.in[0], n, t, P + xo, P + yo), a.act);
     }
     fyn_store_texel(a.out, n, t, a.outP + xo, a.outP + yo, r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp16 fast path of the 1:1 modes (add / sub / singleton arithmetic, concatenation of 4-aligned inputs, RGB<->BGR, layout
+// conversion): a block owns a chunk of ONE 4-channel plane, so tile origins are block-uniform and a texel costs one
+// multiplication instead of the five divisions of k_gather; U 8-byte accesses per tensor in flight per thread.
+// Arithmetic as in k_gather (fp32, one rounding to fp16 at the store), so both kernels give the same bits.
+// ---------------------------------------------------------------------------------------------
+enum { PL_COPY = 0, PL_ADD, PL_SUB, PL_MUL, PL_DIV, PL_BGR };
+
+struct PlaneArgs {
+    TView in0, in1, out;
+    int tiles, batch, outTile0, outP;   // block (n, t) writes output tile outTile0 + t
+    int mode, two;
+    float operand;
+    ActParams act;
+};
+
+__device__ __forceinline__ long long plane_origin(const TView &v, unsigned n, unsigned t, int P) {
+    long long b = (long long)n * v.imageElems;
+    unsigned x0 = P, y0 = P;
+    if (v.deep) {
+        x0 += (t % v.tx) * v.tileW;
+        y0 += (t / v.tx) * v.tileH;
+    } else {
+        b += (long long)t * v.planeElems;
+    }
+    return b + ((long long)y0 * v.texW + x0) * 4;
+}
+
+__device__ __forceinline__ float4 h4_to_f4(uint2 raw) {
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+    return make_float4(f0.x, f0.y, f1.x, f1.y);
+}
+
+template <int U>
+__global__ void __launch_bounds__(256) k_plane_h4(const __grid_constant__ PlaneArgs a, unsigned W, unsigned HW, unsigned chunks, unsigned magic) {
+    unsigned bid = blockIdx.x;
+    const unsigned chunk = bid % chunks;
+    bid /= chunks;
+    const unsigned t = bid % (unsigned)a.tiles, n = bid / (unsigned)a.tiles;
+    const __half *s0 = reinterpret_cast<const __half *>(a.in0.ptr) + plane_origin(a.in0, n, t, a.in0.P);
+    const __half *s1 = a.two ? reinterpret_cast<const __half *>(a.in1.ptr) + plane_origin(a.in1, n, t, a.in1.P) : nullptr;
+    __half *dst = reinterpret_cast<__half *>(a.out.ptr) + plane_origin(a.out, n, a.outTile0 + t, a.outP);
+    const unsigned p0 = chunk * (256u * U) + threadIdx.x;
+    uint2 r0[U], r1[U];
+    unsigned oo[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const unsigned p = p0 + u * 256u;
+        oo[u] = ~0u;
+        if (p < HW) {
+            const unsigned y = magic ? __umulhi(p, magic) : p / W, x = p - y * W;
+            oo[u] = (y * a.out.texW + x) * 4;
+            r0[u] = __ldg(reinterpret_cast<const uint2 *>(s0 + (y * a.in0.texW + x) * 4));
+            if (a.two) r1[u] = __ldg(reinterpret_cast<const uint2 *>(s1 + (y * a.in1.texW + x) * 4));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (oo[u] == ~0u) continue;
+        float4 r;
+        if (a.mode == PL_BGR) {
+            const float4 v = h4_to_f4(r0[u]);
+            r = make_float4(v.z, v.y, v.x, v.w);
+        } else {
+            const float4 p = fyn_act4(h4_to_f4(r0[u]), a.act);
+            if (a.mode == PL_COPY) {
+                r = p;
+            } else {
+                const float4 q = a.two ? fyn_act4(h4_to_f4(r1[u]), a.act) : make_float4(a.operand, a.operand, a.operand, a.operand);
+                if (a.mode == PL_ADD) r = make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w);
+                else if (a.mode == PL_SUB) r = make_float4(p.x - q.x, p.y - q.y, p.z - q.z, p.w - q.w);
+                else if (a.mode == PL_MUL) r = make_float4(p.x * q.x, p.y * q.y, p.z * q.z, p.w * q.w);
+                else r = make_float4(p.x / q.x, p.y / q.y, p.z / q.z, p.w / q.w);
+            }
+        }
+        const __half2 h0 = __floats2half2_rn(r.x, r.y), h1 = __floats2half2_rn(r.z, r.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const unsigned *>(&h0);
+        o.y = *reinterpret_cast<const unsigned *>(&h1);
+        *reinterpret_cast<uint2 *>(dst + oo[u]) = o;
+    }
+}
+
+// Two-tensor add / sub on fp16 tensors of IDENTICAL geometry (same padding, same tiling): the whole texture is one flat array,
+// 16 bytes per access and four accesses per tensor in flight. Border / unused texels hold zeros on both sides and
+// act(0) +- act(0) = 0 keeps them zero (the launcher refuses a clip range that excludes 0).
+__global__ void __launch_bounds__(256) k_addsub_flat(const uint4 *__restrict__ s0, const uint4 *__restrict__ s1, uint4 *__restrict__ dst,
+                                                      unsigned long long units, int sub, ActParams act) {
+    for (unsigned long long base = (unsigned long long)blockIdx.x * 1024u + threadIdx.x; base < units; base += (unsigned long long)gridDim.x * 1024u) {
+        uint4 r0[4], r1[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned long long i = base + u * 256u;
+            if (i < units) {
+                r0[u] = __ldg(s0 + i);
+                r1[u] = __ldg(s1 + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned long long i = base + u * 256u;
+            if (i >= units) break;
+            const float4 p0 = fyn_act4(h4_to_f4(make_uint2(r0[u].x, r0[u].y)), act), p1 = fyn_act4(h4_to_f4(make_uint2(r0[u].z, r0[u].w)), act);
+            float4 q0 = fyn_act4(h4_to_f4(make_uint2(r1[u].x, r1[u].y)), act), q1 = fyn_act4(h4_to_f4(make_uint2(r1[u].z, r1[u].w)), act);
+            if (sub) {
+                q0 = make_float4(-q0.x, -q0.y, -q0.z, -q0.w);
+                q1 = make_float4(-q1.x, -q1.y, -q1.z, -q1.w);
+            }
+            const __half2 h0 = __floats2half2_rn(p0.x + q0.x, p0.y + q0.y), h1 = __floats2half2_rn(p0.z + q0.z, p0.w + q0.w);
+            const __half2 h2 = __floats2half2_rn(p1.x + q1.x, p1.y + q1.y), h3 = __floats2half2_rn(p1.z + q1.z, p1.w + q1.w);
+            uint4 o;
+            o.x = *reinterpret_cast<const unsigned *>(&h0);
+            o.y = *reinterpret_cast<const unsigned *>(&h1);
+            o.z = *reinterpret_cast<const unsigned *>(&h2);
+            o.w = *reinterpret_cast<const unsigned *>(&h3);
+            dst[i] = o;
+        }
+    }
+}
+
+bool same_geometry(const TView &a, const TView &b) {
+    return a.dtype == b.dtype && a.packing == b.packing && a.deep == b.deep && a.texW == b.texW && a.texH == b.texH && a.P == b.P && a.tx == b.tx &&
+           a.tileW == b.tileW && a.tileH == b.tileH && a.planeElems == b.planeElems && a.imageElems == b.imageElems;
+}
+
+bool plane_view_ok(const TView &v) { return v.dtype == FYN_F16 && v.packing == 4 && (long long)v.texW * v.texH < (1 << 28); }
+
+// true if the fast path took the launch (FYN_GATHER_GENERIC=1 forces the generic kernel: tests compare the two)
+bool launch_plane(fyn_ctx *ctx, PlaneArgs &a, int W, int H, void *stream, int *rc) {
+    const char *env = getenv("FYN_GATHER_GENERIC");   // per launch, so that a test can toggle it
+    const bool generic = env && atoi(env) != 0;
+    if (generic || !plane_view_ok(a.in0) || !plane_view_ok(a.out) || (a.two && !plane_view_ok(a.in1))) return false;
+    const long long halves = (long long)a.batch * a.out.imageElems;
+    const bool zeroStays = a.act.type != 3 || (a.act.lo <= 0.f && a.act.hi >= 0.f);
+    if (a.two && (a.mode == PL_ADD || a.mode == PL_SUB) && a.outTile0 == 0 && zeroStays && same_geometry(a.in0, a.out) && same_geometry(a.in1, a.out) &&
+        a.out.P == a.outP && (halves % 8) == 0 && (((uintptr_t)a.in0.ptr | (uintptr_t)a.in1.ptr | (uintptr_t)a.out.ptr) & 15) == 0) {
+        const unsigned long long units = (unsigned long long)halves / 8;
+        const unsigned long long want = (units + 1023) / 1024, cap = (unsigned long long)ctx->prop.multiProcessorCount * 8;
+        k_addsub_flat<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const uint4 *>(a.in0.ptr), reinterpret_cast<const uint4 *>(a.in1.ptr), reinterpret_cast<uint4 *>(a.out.ptr), units, a.mode == PL_SUB, a.act);
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        *rc = FYN_OK;
+        if (e != cudaSuccess) {
+            fyn_set_error("gather: launch failed: %s", cudaGetErrorString(e));
+            *rc = FYN_ERR_CUDA;
+        }
+        return true;
+    }
+    const unsigned HW = (unsigned)W * (unsigned)H;
+    const int U = HW > 1024 ? 8 : (HW > 512 ? 4 : (HW > 256 ? 2 : 1));
+    const unsigned chunks = (HW + 256u * U - 1) / (256u * U);
+    const long long blocks = (long long)chunks * a.tiles * a.batch;
+    if (blocks <= 0 || blocks > 0x7fffffffll) return false;
+    const unsigned magic = ((unsigned long long)(HW + 256u * U) * (unsigned)W < (1ull << 32) && W > 1) ? (unsigned)((1ull << 32) / (unsigned)W) + 1u : 0u;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (U == 8) k_plane_h4<8><<<(unsigned)blocks, 256, 0, s>>>(a, (unsigned)W, HW, chunks, magic);
+    else if (U == 4) k_plane_h4<4><<<(unsigned)blocks, 256, 0, s>>>(a, (unsigned)W, HW, chunks, magic);
+    else if (U == 2) k_plane_h4<2><<<(unsigned)blocks, 256, 0, s>>>(a, (unsigned)W, HW, chunks, magic);
+    else k_plane_h4<1><<<(unsigned)blocks, 256, 0, s>>>(a, (unsigned)W, HW, chunks, magic);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    *rc = FYN_OK;
+    if (e != cudaSuccess) {
+        fyn_set_error("gather: launch failed: %s", cudaGetErrorString(e));
+        *rc = FYN_ERR_CUDA;
+    }
+    return true;
 }
 
 int check_tensor(const char *who, const fyn_tensor *t, int w, int h, int c, int pad, int deep /* -1: any order */) {
@@ -240,6 +412,20 @@ int fyn_arith_run(fyn_op *op, const fyn_tensor *in1, const fyn_tensor *in2, fyn_
     a.batch = in1->desc.batch;
     a.outP = d.out_padding;
     a.act = fyn_act_from_flags(d.flags, d.leaky, d.clip_lo, d.clip_hi);
+    {
+        PlaneArgs pa{};
+        pa.in0 = a.in[0];
+        pa.in1 = a.in[1];
+        pa.out = a.out;
+        pa.tiles = a.tiles;
+        pa.batch = a.batch;
+        pa.outP = a.outP;
+        pa.mode = PL_ADD + (d.op - FYN_ARITH_ADD);
+        pa.two = in2 ? 1 : 0;
+        pa.operand = d.operand;
+        pa.act = a.act;
+        if (launch_plane(op->ctx, pa, d.width, d.height, stream, &rc)) return rc;
+    }
     return launch(op->ctx, a, stream);
 }
 
@@ -288,6 +474,28 @@ int fyn_concat_run(fyn_op *op, const fyn_tensor *const *inputs, int num_inputs, 
     a.batch = out->desc.batch;
     a.outP = d.out_padding;
     a.act = fyn_act_from_flags(d.flags, d.leaky, d.clip_lo, d.clip_hi);
+    // inputs of whole texels: every output plane is one input plane -> one plane-copy launch per input
+    bool aligned = plane_view_ok(a.out);
+    for (int i = 0; i < d.num_inputs; i++) aligned = aligned && (d.channels[i] % 4) == 0 && plane_view_ok(a.in[i]);
+    if (aligned) {
+        for (int i = 0; i < d.num_inputs; i++) {
+            PlaneArgs pa{};
+            pa.in0 = a.in[i];
+            pa.out = a.out;
+            pa.tiles = d.channels[i] / 4;
+            pa.batch = a.batch;
+            pa.outTile0 = a.chOff[i] / 4;
+            pa.outP = a.outP;
+            pa.mode = PL_COPY;
+            pa.act = a.act;
+            if (!launch_plane(op->ctx, pa, d.width, d.height, stream, &rc)) {
+                if (i == 0) break;   // fast path disabled: the generic kernel writes everything
+                FYN_FAIL(FYN_ERR_CUDA, "concat: plane copy refused after the first input");
+            }
+            if (rc) return rc;
+            if (i == d.num_inputs - 1) return FYN_OK;
+        }
+    }
     return launch(op->ctx, a, stream);
 }
 
@@ -322,6 +530,17 @@ static int unary_run(fyn_op *op, int mode, int inDeep, int outDeep, const fyn_te
     a.batch = in->desc.batch;
     a.outP = d.out_padding;
     a.act = fyn_act_from_flags(d.flags, d.leaky, d.clip_lo, d.clip_hi);
+    {
+        PlaneArgs pa{};
+        pa.in0 = a.in[0];
+        pa.out = a.out;
+        pa.tiles = a.tiles;
+        pa.batch = a.batch;
+        pa.outP = a.outP;
+        pa.mode = mode == G_RGB2BGR ? PL_BGR : PL_COPY;
+        pa.act = a.act;
+        if (launch_plane(op->ctx, pa, d.width, d.height, stream, &rc)) return rc;
+    }
     return launch(op->ctx, a, stream);
 }
 

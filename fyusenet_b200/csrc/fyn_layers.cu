@@ -173,12 +173,20 @@ __global__ void __launch_bounds__(256) k_pool_global_deep(const PoolArgs a) {
     const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems + ((long long)(P + trow * a.in.tileH) * a.in.texW) * 4;
     for (int X = threadIdx.x; X < a.in.texW; X += 256) {
         float4 acc = a.isMax ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int y = 0; y < H; y++) {
-            const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(src + ((long long)y * a.in.texW + X) * 4));
-            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
-            const float4 v = fyn_act4(make_float4(f0.x, f0.y, f1.x, f1.y), a.act);
-            if (a.isMax) acc = make_float4(fmaxf(acc.x, v.x), fmaxf(acc.y, v.y), fmaxf(acc.z, v.z), fmaxf(acc.w, v.w));
-            else acc = make_float4(acc.x + v.x, acc.y + v.y, acc.z + v.z, acc.w + v.w);
+        // (eight rows of loads in flight before the first use: the window height is a run-time value)
+        for (int y0 = 0; y0 < H; y0 += 8) {
+            uint2 raw[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (y0 + u < H) raw[u] = __ldg(reinterpret_cast<const uint2 *>(src + ((long long)(y0 + u) * a.in.texW + X) * 4));
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (y0 + u >= H) break;
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[u].x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[u].y));
+                const float4 v = fyn_act4(make_float4(f0.x, f0.y, f1.x, f1.y), a.act);
+                if (a.isMax) acc = make_float4(fmaxf(acc.x, v.x), fmaxf(acc.y, v.y), fmaxf(acc.z, v.z), fmaxf(acc.w, v.w));
+                else acc = make_float4(acc.x + v.x, acc.y + v.y, acc.z + v.z, acc.w + v.w);
+            }
         }
         sCol[X] = acc;
     }

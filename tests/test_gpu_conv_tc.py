@@ -227,6 +227,40 @@ def test_deep_conv_tcgen05(k, ds, ci, co, inp, outp, postbn, res, relures, bnres
     assert rel_l2(y, yd) <= 1e-3
 
 
+DEEP_CASES = [(1, 1, 64, 256, 0, 0, True, False, False, False, 14, 2), (1, 1, 256, 64, 0, 1, True, False, False, False, 14, 1),
+              (3, 1, 64, 64, 1, 0, True, False, False, False, 28, 2), (3, 2, 128, 128, 1, 0, True, False, False, False, 14, 3),
+              (1, 1, 128, 512, 0, 0, True, True, True, True, 7, 3), (1, 1, 2048, 1000, 0, 0, False, False, False, False, 1, 3),
+              (3, 1, 512, 512, 1, 0, True, False, False, False, 7, 1), (7, 2, 3, 64, 1, 1, True, False, False, False, 32, 2),
+              (3, 1, 4, 24, 1, 0, False, False, False, False, 9, 1), (1, 1, 64, 16, 0, 0, False, True, False, False, 20, 5),
+              (1, 1, 64, 256, 0, 0, True, True, True, False, 56, 12), (3, 1, 64, 64, 1, 0, True, False, False, False, 56, 10)]
+
+
+@pytest.mark.parametrize("k,ds,ci,co,inp,outp,postbn,res,relures,bnres,size,batch", DEEP_CASES)
+def test_deep_conv_persistent_kernel_is_bit_identical(k, ds, ci, co, inp, outp, postbn, res, relures, bnres, size, batch, monkeypatch):
+    """Large grids run the persistent kernel (k_conv_deep_tc_p: one CTA per SM, tiles of one CTA pipelined through two TMEM
+    halves), small ones the one-tile-per-CTA kernel.  FYN_DEEP_PERSIST=2 forces the persistent kernel on any grid, =0 forbids it:
+    same operands, same accumulation order, so every layer shape must give the same bits -- single-tile grids, ragged N tiles,
+    a single column group (16 outputs: half of the epilogue warps have nothing to read), the tap-packed stem, 72 K stages, and
+    grids of several tiles per CTA with residual."""
+    rng = np.random.default_rng(k * 100 + ci + co + size)
+    x = half(rng.normal(size=(batch, ci, size, size)).astype(np.float32))
+    wb = random_wb(rng, ci, co, k, post_bn=postbn)
+    so = size // ds
+    residual = half(rng.normal(size=(batch, co, so, so)).astype(np.float32)) if res else None
+    fl = capi.FLAG_PRE_RELU | (capi.FLAG_POST_BATCHNORM if postbn else 0) | (capi.FLAG_RELU_ON_RESIDUAL if relures else 0) | \
+         (capi.FLAG_BATCHNORM_ON_RESIDUAL if bnres else 0)
+    kw = dict(out_channels=co, kernel=k, downsample=ds, in_pad=inp, out_pad=outp, flags=fl, residual=residual, deep=True, backend=capi.BACKEND_TC)
+    outs = []
+    for mode in ("0", "2"):
+        monkeypatch.setenv("FYN_DEEP_PERSIST", mode)
+        outs.append(conv_gpu(x, wb, **kw))
+    np.testing.assert_array_equal(outs[0], outs[1])
+    for ring, sets in (("2", "2"), ("3", "1"), ("5", "4")):      # short rings / fewer loader sets: the stage stream wraps inside and across tiles
+        monkeypatch.setenv("FYN_DEEP_PRING", ring)
+        monkeypatch.setenv("FYN_DEEP_SETS", sets)
+        np.testing.assert_array_equal(outs[0], conv_gpu(x, wb, **kw))
+
+
 def test_deep_conv_fused_input_batchnorm():
     """fyn_conv2d_set_input_norm: a deep 1x1 convolution that evaluates the batch-norm layer in front of it at the fetch is
     bit-identical to running fyn_batchnorm_run first (same fp32 fma, same fp16 rounding); layers outside the deep-tiled

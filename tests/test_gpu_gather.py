@@ -181,6 +181,38 @@ def test_rgb2bgr_and_relayout(dtype):
             o.destroy()
 
 
+@pytest.mark.parametrize("deep", [False, True])
+def test_plane_fast_path_matches_generic_kernel(deep, monkeypatch):
+    """fp16 add / sub / singleton / concat / relayout run the plane-chunk kernel (k_plane_h4); FYN_GATHER_GENERIC=1 forces the
+    one-thread-per-texel gather kernel. Same arithmetic, so the bits must agree -- at every unroll width (H*W of 30 ... 2.5k)."""
+    c = ctx()
+    rng = np.random.default_rng(99)
+    flag = capi.FLAG_DEEP if deep else 0
+    for w, h, ch, ip, op_ in [(6, 5, 12, 1, 0), (19, 17, 24, 0, 1), (31, 23, 8, 1, 1), (57, 45, 20, 0, 0)]:
+        x1, x2 = (rng.normal(size=(2, ch, h, w)).astype(np.float32) for _ in range(2))
+        t1, t2 = (c.tensor(w, h, ch, ip, ORDER[deep], capi.F16, 2) for _ in range(2))
+        tout = c.tensor(w, h, ch, op_, ORDER[deep], capi.F16, 2)
+        tcat = c.tensor(w, h, 2 * ch, op_, ORDER[deep], capi.F16, 2)
+        tre = c.tensor(w, h, ch, op_, ORDER[not deep], capi.F16, 2)
+        t1.write_chw(x1)
+        t2.write_chw(x2)
+        ops = [(capi.Arith(c, width=w, height=h, channels=ch, op=capi.ARITH_ADD, in_padding=ip, out_padding=op_, flags=flag | capi.FLAG_PRE_RELU), (t1, t2, tout)),
+               (capi.Arith(c, width=w, height=h, channels=ch, op=capi.ARITH_SUB, in_padding=ip, out_padding=op_, flags=flag), (t1, t2, tout)),
+               (capi.Arith(c, width=w, height=h, channels=ch, op=capi.ARITH_DIV, operand=3.0, in_padding=ip, out_padding=op_, flags=flag), (t1, None, tout)),
+               (capi.Concat(c, width=w, height=h, channels=(ch, ch), in_padding=ip, out_padding=op_, flags=flag | capi.FLAG_PRE_RELU), ([t1, t2], tcat)),
+               (capi.Relayout(c, width=w, height=h, channels=ch, in_padding=ip, out_padding=op_), (t1, tre))]
+        for op, args in ops:
+            got = []
+            for generic in ("0", "1"):
+                monkeypatch.setenv("FYN_GATHER_GENERIC", generic)
+                op.run(*args)
+                got.append(args[-1].download().copy())
+            np.testing.assert_array_equal(got[0], got[1])
+            op.destroy()
+        for o in (t1, t2, tout, tcat, tre):
+            o.destroy()
+
+
 @pytest.mark.parametrize("dtype", [capi.F16, capi.F32])
 @pytest.mark.parametrize("deep", [False, True])
 def test_depthwise_conv3x3(deep, dtype):

@@ -70,7 +70,10 @@ def main():
     ta = ctx.tensor(56, 56, 256, 0, D, capi.F16, B)
     add = capi.Arith(ctx, width=56, height=56, channels=256, op=capi.ARITH_ADD, flags=capi.FLAG_DEEP)
     timed("deep add 56x56x256 (two inputs), batch 128", lambda: add.run(tin, ta, tout), 3 * tbytes(tin))
-    for o in (tin, tout, ta, op, add):
+    tcat = ctx.tensor(56, 56, 512, 0, D, capi.F16, B)
+    cat = capi.Concat(ctx, width=56, height=56, channels=(256, 256), flags=capi.FLAG_DEEP)
+    timed("deep concat 2 x 56x56x256, batch 128", lambda: cat.run([tin, ta], tcat), 4 * tbytes(tin))
+    for o in (tin, tout, ta, tcat, op, add, cat):
         o.destroy()
     # ---- StyleNet shapes (1524x1856), batch 8 so that the working set exceeds L2
     W, H, NB = 1524, 1856, 8
