@@ -148,6 +148,19 @@ __device__ __forceinline__ uint2 act_h4(uint2 v, const ActParams &a) {
     return make_uint2(pack_half2(fyn_act(f0.x, a), fyn_act(f0.y, a)), pack_half2(fyn_act(f1.x, a), fyn_act(f1.y, a)));
 }
 
+template <int ACT>
+__device__ __forceinline__ uint2 act_h4_t(uint2 v, const ActParams &a) {
+    if (ACT == 0) return v;
+    if (ACT == 1) {
+        const __half2 z = __float2half2_rn(0.f);
+        __half2 *q = reinterpret_cast<__half2 *>(&v);
+        q[0] = __hmax2(q[0], z);
+        q[1] = __hmax2(q[1], z);
+        return v;
+    }
+    return act_h4(v, a);
+}
+
 // dynamic shared memory: [A stages][B stages][plane origin tables][barriers][tmem base]
 // NORM: the input batch-norm fusion (its own instantiation, so that the plain kernel keeps its register budget); two CTAs per SM
 template <bool NORM>
@@ -348,11 +361,11 @@ constexpr int kThreadsDeepP = kWarpsP * 32;
 // tile -> (pixel tile, n tile) of a CTA's tile sequence b, b + G, b + 2G, ... without a division per tile
 struct TileWalk {
     int mt, nt, dM, dN, ntilesN;
-    long long tile, total, G;
+    unsigned tile, total, G;      // (the launcher keeps totalTiles + gridDim below 2^31)
     __device__ __forceinline__ TileWalk(const DeepTcArgs &a) {
         ntilesN = a.ntilesN;
         G = gridDim.x;
-        total = a.totalTiles;
+        total = (unsigned)a.totalTiles;
         tile = blockIdx.x;
         mt = (int)(blockIdx.x / (unsigned)ntilesN);
         nt = (int)(blockIdx.x % (unsigned)ntilesN);
@@ -371,7 +384,8 @@ struct TileWalk {
     }
 };
 
-template <bool NORM>
+// ACT: activation at the fetch as a compile-time constant (0 none, 1 ReLU, 2 whatever args.act says)
+template <bool NORM, int ACT>
 __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __grid_constant__ DeepTcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int bStageBytes = a.NT * kKC * 2;
@@ -380,11 +394,12 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
     unsigned char *sB = sA + a.ring * kAStageBytes;
     float4 *sScale = reinterpret_cast<float4 *>(sB + a.ring * bStageBytes);   // [nOutPlanes] scale, then [nOutPlanes] bias
     float4 *sBias = sScale + nOutPlanes;
-    int *inOrigin = reinterpret_cast<int *>(sBias + nOutPlanes);             // [nInPlanes]
+    int *tapTab = reinterpret_cast<int *>(sBias + nOutPlanes);               // [64] (16-byte aligned: read as int4)
+    int *tapOff = tapTab + 64;                                                // [64] element offset of a tap-packed stage's taps (interior pixels)
+    int *inOrigin = tapOff + 64;                                              // [nInPlanes] (16-byte aligned)
     int *outOrigin = inOrigin + a.nInPlanes;                                  // [nOutPlanes] output tensor, then [nOutPlanes] residual tensor
     int *resOrigin = outOrigin + nOutPlanes;
-    int *tapTab = resOrigin + nOutPlanes;                                     // [64]
-    int *stageTab = tapTab + 64;                                              // [nstages] ky | kx << 8 | kc << 16
+    int *stageTab = resOrigin + nOutPlanes;                                   // [nstages] ky | kx << 8 | kc << 16
     uint64_t *full = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(stageTab + a.nstages) + 7) & ~uintptr_t(7));
     uint64_t *empty = full + kMaxRingP;
     uint64_t *accFull = empty + kMaxRingP;
@@ -418,6 +433,7 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
     if (a.tapPacked && threadIdx.x < 64) {
         const int tp = min((int)threadIdx.x, a.K * a.K - 1);
         tapTab[threadIdx.x] = (tp / a.K) | ((tp % a.K) << 8);
+        tapOff[threadIdx.x] = ((tp / a.K) * a.in.texW + (tp % a.K)) * 4;
     }
     for (int st = threadIdx.x; st < a.nstages; st += nthreads) {
         const int tap = st / a.kcs, kc = st - tap * a.kcs;
@@ -446,7 +462,9 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
             const int yo = (int)(rem / (unsigned)a.Wo), xo = (int)rem - yo * a.Wo;
             const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems;
             const uint4 *wsrc = a.wimg + (size_t)w.nt * a.nstages * (bStageBytes >> 4);
-            const __half *px0 = src + ((a.inP + a.ds * yo - a.mh) * a.in.texW + a.inP + a.ds * xo - a.mh) * 4;
+            const int iy0 = a.inP + a.ds * yo - a.mh, ix0 = a.inP + a.ds * xo - a.mh;
+            const __half *px0 = src + (iy0 * a.in.texW + ix0) * 4;
+            const bool interior = valid && iy0 >= 0 && ix0 >= 0 && iy0 + a.K <= a.in.texH && ix0 + a.K <= a.in.texW;
             for (; s < a.nstages; s += a.nsets) {
                 const int st = slot;
                 const int tab = stageTab[s];
@@ -459,9 +477,15 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
                 uint2 v[kKC / 4];
                 if (!a.tapPacked) {
                     const __half *px = px0 + (ky * a.in.texW + kx) * 4;
-                    const int *org = inOrigin + kc * (kKC / 4);
+                    const int4 *org4 = reinterpret_cast<const int4 *>(inOrigin + kc * (kKC / 4));
 #pragma unroll
-                    for (int j = 0; j < kKC / 4; j++) v[j] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + org[j])) : make_uint2(0u, 0u);
+                    for (int j4 = 0; j4 < kKC / 16; j4++) {
+                        const int4 o = org4[j4];
+                        v[4 * j4 + 0] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + o.x)) : make_uint2(0u, 0u);
+                        v[4 * j4 + 1] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + o.y)) : make_uint2(0u, 0u);
+                        v[4 * j4 + 2] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + o.z)) : make_uint2(0u, 0u);
+                        v[4 * j4 + 3] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + o.w)) : make_uint2(0u, 0u);
+                    }
                     if (NORM) {
                         const float4 *sc = a.inNorm + kc * (kKC / 4), *bi = sc + a.nInPlanes;
 #pragma unroll
@@ -471,6 +495,17 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
                             const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&v[j].y));
                             v[j] = make_uint2(pack_half2(fmaf(f0.x, s4.x, b4.x), fmaf(f0.y, s4.y, b4.y)), pack_half2(fmaf(f1.x, s4.z, b4.z), fmaf(f1.y, s4.w, b4.w)));
                         }
+                    }
+                } else if (interior) {
+                    // every tap of this pixel lies inside the texture: base + tap offset, no clamping
+                    const int4 *off4 = reinterpret_cast<const int4 *>(tapOff + s * (kKC / 4));
+#pragma unroll
+                    for (int j4 = 0; j4 < kKC / 16; j4++) {
+                        const int4 o = off4[j4];
+                        v[4 * j4 + 0] = __ldg(reinterpret_cast<const uint2 *>(px0 + o.x));
+                        v[4 * j4 + 1] = __ldg(reinterpret_cast<const uint2 *>(px0 + o.y));
+                        v[4 * j4 + 2] = __ldg(reinterpret_cast<const uint2 *>(px0 + o.z));
+                        v[4 * j4 + 3] = __ldg(reinterpret_cast<const uint2 *>(px0 + o.w));
                     }
                 } else {
 #pragma unroll
@@ -485,7 +520,7 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
                 unsigned char *dst = sA + (size_t)st * kAStageBytes + t * 16;
 #pragma unroll
                 for (int c = 0; c < kKC / 8; c++) {
-                    const uint2 lo = act_h4(v[2 * c], a.act), hi = act_h4(v[2 * c + 1], a.act);
+                    const uint2 lo = act_h4_t<ACT>(v[2 * c], a.act), hi = act_h4_t<ACT>(v[2 * c + 1], a.act);
                     *reinterpret_cast<uint4 *>(dst + c * (kM * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
                 }
                 fence_proxy_async();
@@ -534,6 +569,92 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
         const int t = quarter * 32 + lane;
         const int ngroups = a.NT >> 4;
         uint32_t tcount = 0;
+        const int myGroups = part < ngroups ? (ngroups - part + parts - 1) / parts : 0;
+        if (myGroups <= 4) {
+            // At most four column groups per warp and tile (the usual split): the residual texels of the NEXT tile are fetched while
+            // this one is drained -- up to sixteen 8-byte loads in flight per thread, a whole tile ahead of their use.
+            struct Px {
+                bool valid;
+                int plane0;
+                __half *outp;
+                const __half *resp;
+            };
+            auto locate = [&](const TileWalk &w) {
+                Px p;
+                const unsigned m = (unsigned)w.mt * kM + t;
+                p.valid = !w.done() && m < Mtotal;
+                const unsigned n = p.valid ? m / hw : 0u;
+                const unsigned rem = p.valid ? m - n * hw : 0u;
+                const int yo = (int)(rem / (unsigned)a.Wo), xo = (int)rem - yo * a.Wo;
+                p.outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((a.outP + yo) * a.out.texW + a.outP + xo) * 4;
+                p.resp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems + ((a.resP + yo) * a.res.texW + a.resP + xo) * 4;
+                p.plane0 = w.nt * (a.NT >> 2);
+                return p;
+            };
+            auto fetch = [&](const Px &p, int cg, uint2 (&rq)[4]) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int pk = p.plane0 + cg * 4 + k;
+                    rq[k] = (a.hasRes && p.valid && pk < nOutPlanes) ? __ldg(reinterpret_cast<const uint2 *>(p.resp + resOrigin[pk])) : make_uint2(0u, 0u);
+                }
+            };
+            TileWalk w(a);
+            Px cur = locate(w);
+            uint2 rq[4][4];
+#pragma unroll
+            for (int g = 0; g < 4; g++)
+                if (g < myGroups) fetch(cur, part + g * parts, rq[g]);
+            for (; !w.done(); tcount++) {
+                const uint32_t buf = tcount & 1;
+                TileWalk wn = w;
+                wn.next();
+                const Px nxt = locate(wn);
+                mbar_wait(&accFull[buf], (tcount >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)a.NT;
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    if (g == myGroups) {   // every column group of this warp has been read: the accumulator half may be overwritten
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&accEmpty[buf]);
+                    }
+                    if (g >= myGroups) continue;
+                    const int cg = part + g * parts;
+                    uint32_t acc[16];
+                    tmem_ld16(taddr + cg * 16, acc);
+                    tmem_ld_wait();
+                    if (g == myGroups - 1 && g == 3) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&accEmpty[buf]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int pk = cur.plane0 + cg * 4 + k;
+                        if (!cur.valid || pk >= nOutPlanes) continue;
+                        const float4 sc = sScale[pk], bi = sBias[pk];
+                        float4 r = make_float4(fmaf(__uint_as_float(acc[4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[4 * k + 1]), sc.y, bi.y),
+                                               fmaf(__uint_as_float(acc[4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[4 * k + 3]), sc.w, bi.w));
+                        if (a.hasRes) {
+                            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&rq[g][k].x));
+                            const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&rq[g][k].y));
+                            float4 q = make_float4(f0.x, f0.y, f1.x, f1.y);
+                            if (a.reluRes) q = make_float4(fmaxf(q.x, 0.f), fmaxf(q.y, 0.f), fmaxf(q.z, 0.f), fmaxf(q.w, 0.f));
+                            if (a.bnRes) q = make_float4(q.x * sc.x, q.y * sc.y, q.z * sc.z, q.w * sc.w);
+                            r.x += q.x;
+                            r.y += q.y;
+                            r.z += q.z;
+                            r.w += q.w;
+                        }
+                        *reinterpret_cast<uint2 *>(cur.outp + outOrigin[pk]) = make_uint2(pack_half2(r.x, r.y), pack_half2(r.z, r.w));
+                    }
+                    fetch(nxt, cg, rq[g]);
+                }
+                cur = nxt;
+                w = wn;
+            }
+        } else
         for (TileWalk w(a); !w.done(); w.next(), tcount++) {
             const uint32_t buf = tcount & 1;
             const unsigned m = (unsigned)w.mt * kM + t;
@@ -557,18 +678,13 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
             mbar_wait(&accFull[buf], (tcount >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)a.NT;
-            bool released = false;
-            auto do_group = [&](int cg, uint2 (&rq)[4]) {
-                uint32_t acc[16];
-                tmem_ld16(taddr + cg * 16, acc);
-                tmem_ld_wait();
-                if (cg + parts >= ngroups) {
-                    // last column group of this warp: the accumulator half may be overwritten once every warp has read its share
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&accEmpty[buf]);
-                    released = true;
-                }
+            auto release = [&]() {
+                // every column group of this warp has been read: the accumulator half may be overwritten once all warps say so
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&accEmpty[buf]);
+            };
+            auto finish_group = [&](int cg, const uint32_t (&acc)[16], uint2 (&rq)[4]) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const int pk = plane0 + cg * 4 + k;
@@ -591,15 +707,22 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
                 }
                 fetch_res(cg + 2 * parts, rq);
             };
+            bool released = false;
+            auto do_group = [&](int cg, uint2 (&rq)[4]) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + cg * 16, acc);
+                tmem_ld_wait();
+                if (cg + parts >= ngroups) {
+                    release();
+                    released = true;
+                }
+                finish_group(cg, acc, rq);
+            };
             for (int cg = part; cg < ngroups; cg += 2 * parts) {
                 do_group(cg, rq0);
                 if (cg + parts < ngroups) do_group(cg + parts, rq1);
             }
-            if (!released) {   // (fewer column groups than warps per quarter: this warp had nothing to read)
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&accEmpty[buf]);
-            }
+            if (!released) release();   // (fewer column groups than warps per quarter: this warp had nothing to read)
         }
     }
     tc_fence_before();
@@ -787,7 +910,7 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
         a.ntilesN = ntiles;
         a.totalTiles = mtiles * ntiles;
         const size_t stageBytes = (size_t)kAStageBytes + (size_t)a.NT * kKC * 2;
-        const size_t fixed = (size_t)(a.Cout4 / 4) * 32 + ((size_t)a.nInPlanes + 2 * (size_t)(a.Cout4 / 4) + 64 + a.nstages) * 4 + 8 + (2 * kMaxRingP + 4) * 8 + 16;
+        const size_t fixed = (size_t)(a.Cout4 / 4) * 32 + ((size_t)a.nInPlanes + 2 * (size_t)(a.Cout4 / 4) + 128 + a.nstages) * 4 + 8 + (2 * kMaxRingP + 4) * 8 + 16;
         const size_t budget = (size_t)op->ctx->prop.sharedMemPerBlockOptin - 1024;
         int ring = (int)std::min<size_t>(kMaxRingP, fixed < budget ? (budget - fixed) / stageBytes : 0);
         if (const char *e = getenv("FYN_DEEP_PRING")) ring = std::max(1, std::min(ring, atoi(e)));
@@ -808,8 +931,12 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
                 std::lock_guard<std::mutex> guard(lockP);
                 size_t &cur = maxSmemP[op->ctx->device & 63];
                 if (smemP > cur) {
-                    FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_p<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
-                    FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
+                    FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_p<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
+                    FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_p<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
+                    FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_p<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
+                    FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_p<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
+                    FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_p<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
+                    FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_p<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
                     cur = smemP;
                 }
             }
@@ -820,8 +947,16 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
             pc.stream = stream;
             pc.attrs = attr;
             pc.numAttrs = noPdl ? 0 : 1;
-            if (a.inNorm) FYN_CUDA(cudaLaunchKernelEx(&pc, k_conv_deep_tc_p<true>, a));
-            else FYN_CUDA(cudaLaunchKernelEx(&pc, k_conv_deep_tc_p<false>, a));
+            const int actT = a.act.type <= 1 ? a.act.type : 2;
+            if (a.inNorm) {
+                if (actT == 0) FYN_CUDA(cudaLaunchKernelEx(&pc, k_conv_deep_tc_p<true, 0>, a));
+                else if (actT == 1) FYN_CUDA(cudaLaunchKernelEx(&pc, k_conv_deep_tc_p<true, 1>, a));
+                else FYN_CUDA(cudaLaunchKernelEx(&pc, k_conv_deep_tc_p<true, 2>, a));
+            } else {
+                if (actT == 0) FYN_CUDA(cudaLaunchKernelEx(&pc, k_conv_deep_tc_p<false, 0>, a));
+                else if (actT == 1) FYN_CUDA(cudaLaunchKernelEx(&pc, k_conv_deep_tc_p<false, 1>, a));
+                else FYN_CUDA(cudaLaunchKernelEx(&pc, k_conv_deep_tc_p<false, 2>, a));
+            }
             FYN_CHECK_LAUNCH(op->ctx);
             return FYN_OK;
         }

@@ -42,7 +42,7 @@ def main():
             net.forward()
         net.finish()
         rows = sorted(((net.layer_timing(l["number"])[0] / 2 * 1e3, l["name"]) for l in net.layers()), reverse=True)
-        out["top_layers_us"] = [(n, round(t, 1)) for t, n in rows[:24]]
+        out["top_layers_us"] = [(n, round(t, 1)) for t, n in rows[:60]]
     print(json.dumps(out))
     net.destroy()
 
