@@ -57,6 +57,8 @@ struct DeepTcArgs {
     int inP, outP, resP;
     // persistent kernel: tiles (m tile, n tile) are numbered n-fastest and taken round robin by the CTAs
     int ntilesN, epiWarps;
+    // halo-tile 3x3 kernel: virtual raster width (W + 1), halo pixels per stage (multiple of 8), weight ring depth
+    int Wv, HPp, ringB;
     long long totalTiles;
 };
 
@@ -384,6 +386,153 @@ struct TileWalk {
     }
 };
 
+// position of a GEMM row (output pixel) in the output / residual tensors
+struct Px {
+    bool valid;
+    int plane0;
+    __half *outp;
+    const __half *resp;
+};
+
+// HALO = false: GEMM rows are the flattened output pixels (image, y, x).
+// HALO = true (k_conv_deep_tc_h3): rows walk a virtual raster of Wv = W + 1 columns and H + 1 rows per image whose extra column /
+// row stand for the zero border; those rows are computed but not stored.
+template <bool HALO>
+__device__ __forceinline__ Px locate_row(const DeepTcArgs &a, const TileWalk &w, int t) {
+    Px p;
+    const unsigned m = (unsigned)w.mt * kM + t;
+    unsigned n, yo, xo;
+    if (HALO) {
+        const unsigned vr = m / (unsigned)a.Wv;
+        xo = m - vr * (unsigned)a.Wv;
+        n = vr / (unsigned)(a.Ho + 1);
+        yo = vr - n * (unsigned)(a.Ho + 1);
+        p.valid = !w.done() && m < (unsigned)a.Mtotal && xo < (unsigned)a.Wo && yo < (unsigned)a.Ho;
+    } else {
+        const unsigned hw = (unsigned)(a.Ho * a.Wo);
+        p.valid = !w.done() && m < (unsigned)a.Mtotal;
+        n = p.valid ? m / hw : 0u;
+        const unsigned rem = p.valid ? m - n * hw : 0u;
+        yo = rem / (unsigned)a.Wo;
+        xo = rem - yo * (unsigned)a.Wo;
+    }
+    if (!p.valid) n = yo = xo = 0u;
+    p.outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((a.outP + (int)yo) * a.out.texW + a.outP + (int)xo) * 4;
+    p.resp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems + ((a.resP + (int)yo) * a.res.texW + a.resP + (int)xo) * 4;
+    p.plane0 = w.nt * (a.NT >> 2);
+    return p;
+}
+
+// Epilogue warp of the persistent kernels: drains the CTA's tiles from the two TMEM halves.  `e` = index among the epilogue
+// warps, `quarter` = TMEM lane quarter of the warp (warp index & 3); the warps of a quarter alternate over the column groups.
+template <bool HALO>
+__device__ __forceinline__ void epilogue_tiles(const DeepTcArgs &a, int e, int quarter, uint32_t tmem, uint64_t *accFull, uint64_t *accEmpty,
+                                               const float4 *sScale, const float4 *sBias, const int *outOrigin, const int *resOrigin) {
+    const int part = e >> 2, lane = threadIdx.x & 31, parts = a.epiWarps >> 2;
+    const int t = quarter * 32 + lane;
+    const int ngroups = a.NT >> 4, nOutPlanes = a.Cout4 >> 2;
+    const int myGroups = part < ngroups ? (ngroups - part + parts - 1) / parts : 0;
+    uint32_t tcount = 0;
+    auto fetch = [&](const Px &p, int cg, uint2 (&rq)[4]) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int pk = p.plane0 + cg * 4 + k;
+            rq[k] = (a.hasRes && p.valid && cg < ngroups && pk < nOutPlanes) ? __ldg(reinterpret_cast<const uint2 *>(p.resp + resOrigin[pk])) : make_uint2(0u, 0u);
+        }
+    };
+    auto finish = [&](const Px &p, int cg, const uint32_t (&acc)[16], const uint2 (&rq)[4]) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int pk = p.plane0 + cg * 4 + k;
+            if (!p.valid || pk >= nOutPlanes) continue;
+            const float4 sc = sScale[pk], bi = sBias[pk];
+            float4 r = make_float4(fmaf(__uint_as_float(acc[4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[4 * k + 1]), sc.y, bi.y),
+                                   fmaf(__uint_as_float(acc[4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[4 * k + 3]), sc.w, bi.w));
+            if (a.hasRes) {
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&rq[k].x));
+                const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&rq[k].y));
+                float4 q = make_float4(f0.x, f0.y, f1.x, f1.y);
+                if (a.reluRes) q = make_float4(fmaxf(q.x, 0.f), fmaxf(q.y, 0.f), fmaxf(q.z, 0.f), fmaxf(q.w, 0.f));
+                if (a.bnRes) q = make_float4(q.x * sc.x, q.y * sc.y, q.z * sc.z, q.w * sc.w);
+                r.x += q.x;
+                r.y += q.y;
+                r.z += q.z;
+                r.w += q.w;
+            }
+            *reinterpret_cast<uint2 *>(p.outp + outOrigin[pk]) = make_uint2(pack_half2(r.x, r.y), pack_half2(r.z, r.w));
+        }
+    };
+    TileWalk w(a);
+    Px cur = locate_row<HALO>(a, w, t);
+    if (myGroups <= 4) {
+        // At most four column groups per warp and tile (the usual split): the residual texels of the NEXT tile are fetched while
+        // this one is drained -- up to sixteen 8-byte loads in flight per thread, a whole tile ahead of their use.
+        uint2 rq[4][4];
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+            if (g < myGroups) fetch(cur, part + g * parts, rq[g]);
+        for (; !w.done(); tcount++) {
+            const uint32_t buf = tcount & 1;
+            TileWalk wn = w;
+            wn.next();
+            const Px nxt = locate_row<HALO>(a, wn, t);
+            mbar_wait(&accFull[buf], (tcount >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)a.NT;
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                if (g == myGroups) {   // every column group of this warp has been read: the accumulator half may be overwritten
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&accEmpty[buf]);
+                }
+                if (g >= myGroups) continue;
+                const int cg = part + g * parts;
+                uint32_t acc[16];
+                tmem_ld16(taddr + cg * 16, acc);
+                tmem_ld_wait();
+                if (g == myGroups - 1 && g == 3) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&accEmpty[buf]);
+                }
+                finish(cur, cg, acc, rq[g]);
+                fetch(nxt, cg, rq[g]);
+            }
+            cur = nxt;
+            w = wn;
+        }
+    } else {
+        // more column groups per warp: the residual texels run two groups ahead inside the tile
+        for (; !w.done(); w.next(), cur = locate_row<HALO>(a, w, t), tcount++) {
+            const uint32_t buf = tcount & 1;
+            uint2 rq0[4], rq1[4];
+            fetch(cur, part, rq0);
+            fetch(cur, part + parts, rq1);
+            mbar_wait(&accFull[buf], (tcount >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)a.NT;
+            auto do_group = [&](int cg, uint2 (&rq)[4]) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + cg * 16, acc);
+                tmem_ld_wait();
+                if (cg + parts >= ngroups) {   // last column group of this warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&accEmpty[buf]);
+                }
+                finish(cur, cg, acc, rq);
+                fetch(cur, cg + 2 * parts, rq);
+            };
+            for (int cg = part; cg < ngroups; cg += 2 * parts) {
+                do_group(cg, rq0);
+                if (cg + parts < ngroups) do_group(cg + parts, rq1);
+            }
+        }
+    }
+}
+
+
 // ACT: activation at the fetch as a compile-time constant (0 none, 1 ReLU, 2 whatever args.act says)
 template <bool NORM, int ACT>
 __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __grid_constant__ DeepTcArgs a) {
@@ -563,167 +712,199 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
         }
         __syncwarp();
     } else if (warp < loadWarps + 1 + a.epiWarps) {
-        // ===================== epilogue: warp quarter = TMEM lanes, the warps of a quarter alternate over the column groups
-        const int e = warp - loadWarps - 1, quarter = warp & 3, part = e >> 2, lane = threadIdx.x & 31;
-        const int parts = a.epiWarps >> 2;
-        const int t = quarter * 32 + lane;
-        const int ngroups = a.NT >> 4;
-        uint32_t tcount = 0;
-        const int myGroups = part < ngroups ? (ngroups - part + parts - 1) / parts : 0;
-        if (myGroups <= 4) {
-            // At most four column groups per warp and tile (the usual split): the residual texels of the NEXT tile are fetched while
-            // this one is drained -- up to sixteen 8-byte loads in flight per thread, a whole tile ahead of their use.
-            struct Px {
-                bool valid;
-                int plane0;
-                __half *outp;
-                const __half *resp;
-            };
-            auto locate = [&](const TileWalk &w) {
-                Px p;
-                const unsigned m = (unsigned)w.mt * kM + t;
-                p.valid = !w.done() && m < Mtotal;
-                const unsigned n = p.valid ? m / hw : 0u;
-                const unsigned rem = p.valid ? m - n * hw : 0u;
-                const int yo = (int)(rem / (unsigned)a.Wo), xo = (int)rem - yo * a.Wo;
-                p.outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((a.outP + yo) * a.out.texW + a.outP + xo) * 4;
-                p.resp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems + ((a.resP + yo) * a.res.texW + a.resP + xo) * 4;
-                p.plane0 = w.nt * (a.NT >> 2);
-                return p;
-            };
-            auto fetch = [&](const Px &p, int cg, uint2 (&rq)[4]) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int pk = p.plane0 + cg * 4 + k;
-                    rq[k] = (a.hasRes && p.valid && pk < nOutPlanes) ? __ldg(reinterpret_cast<const uint2 *>(p.resp + resOrigin[pk])) : make_uint2(0u, 0u);
-                }
-            };
-            TileWalk w(a);
-            Px cur = locate(w);
-            uint2 rq[4][4];
-#pragma unroll
-            for (int g = 0; g < 4; g++)
-                if (g < myGroups) fetch(cur, part + g * parts, rq[g]);
-            for (; !w.done(); tcount++) {
-                const uint32_t buf = tcount & 1;
-                TileWalk wn = w;
-                wn.next();
-                const Px nxt = locate(wn);
-                mbar_wait(&accFull[buf], (tcount >> 1) & 1);
-                tc_fence_after();
-                const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)a.NT;
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    if (g == myGroups) {   // every column group of this warp has been read: the accumulator half may be overwritten
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&accEmpty[buf]);
-                    }
-                    if (g >= myGroups) continue;
-                    const int cg = part + g * parts;
-                    uint32_t acc[16];
-                    tmem_ld16(taddr + cg * 16, acc);
-                    tmem_ld_wait();
-                    if (g == myGroups - 1 && g == 3) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&accEmpty[buf]);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int pk = cur.plane0 + cg * 4 + k;
-                        if (!cur.valid || pk >= nOutPlanes) continue;
-                        const float4 sc = sScale[pk], bi = sBias[pk];
-                        float4 r = make_float4(fmaf(__uint_as_float(acc[4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[4 * k + 1]), sc.y, bi.y),
-                                               fmaf(__uint_as_float(acc[4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[4 * k + 3]), sc.w, bi.w));
-                        if (a.hasRes) {
-                            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&rq[g][k].x));
-                            const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&rq[g][k].y));
-                            float4 q = make_float4(f0.x, f0.y, f1.x, f1.y);
-                            if (a.reluRes) q = make_float4(fmaxf(q.x, 0.f), fmaxf(q.y, 0.f), fmaxf(q.z, 0.f), fmaxf(q.w, 0.f));
-                            if (a.bnRes) q = make_float4(q.x * sc.x, q.y * sc.y, q.z * sc.z, q.w * sc.w);
-                            r.x += q.x;
-                            r.y += q.y;
-                            r.z += q.z;
-                            r.w += q.w;
-                        }
-                        *reinterpret_cast<uint2 *>(cur.outp + outOrigin[pk]) = make_uint2(pack_half2(r.x, r.y), pack_half2(r.z, r.w));
-                    }
-                    fetch(nxt, cg, rq[g]);
-                }
-                cur = nxt;
-                w = wn;
-            }
-        } else
-        for (TileWalk w(a); !w.done(); w.next(), tcount++) {
-            const uint32_t buf = tcount & 1;
-            const unsigned m = (unsigned)w.mt * kM + t;
-            const bool valid = m < Mtotal;
-            const unsigned n = valid ? m / hw : 0u;
-            const unsigned rem = valid ? m - n * hw : 0u;
-            const int yo = (int)(rem / (unsigned)a.Wo), xo = (int)rem - yo * a.Wo;
-            __half *outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((a.outP + yo) * a.out.texW + a.outP + xo) * 4;
-            const __half *resp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems + ((a.resP + yo) * a.res.texW + a.resP + xo) * 4;
-            const int plane0 = w.nt * (a.NT >> 2);
-            auto fetch_res = [&](int cg, uint2 (&rq)[4]) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int pk = plane0 + cg * 4 + k;
-                    rq[k] = (a.hasRes && valid && cg < ngroups && pk < nOutPlanes) ? __ldg(reinterpret_cast<const uint2 *>(resp + resOrigin[pk])) : make_uint2(0u, 0u);
-                }
-            };
-            uint2 rq0[4], rq1[4];
-            fetch_res(part, rq0);
-            fetch_res(part + parts, rq1);
-            mbar_wait(&accFull[buf], (tcount >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)a.NT;
-            auto release = [&]() {
-                // every column group of this warp has been read: the accumulator half may be overwritten once all warps say so
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&accEmpty[buf]);
-            };
-            auto finish_group = [&](int cg, const uint32_t (&acc)[16], uint2 (&rq)[4]) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int pk = plane0 + cg * 4 + k;
-                    if (!valid || pk >= nOutPlanes) continue;
-                    const float4 sc = sScale[pk], bi = sBias[pk];
-                    float4 r = make_float4(fmaf(__uint_as_float(acc[4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[4 * k + 1]), sc.y, bi.y),
-                                           fmaf(__uint_as_float(acc[4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[4 * k + 3]), sc.w, bi.w));
-                    if (a.hasRes) {
-                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&rq[k].x));
-                        const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&rq[k].y));
-                        float4 q = make_float4(f0.x, f0.y, f1.x, f1.y);
-                        if (a.reluRes) q = make_float4(fmaxf(q.x, 0.f), fmaxf(q.y, 0.f), fmaxf(q.z, 0.f), fmaxf(q.w, 0.f));
-                        if (a.bnRes) q = make_float4(q.x * sc.x, q.y * sc.y, q.z * sc.z, q.w * sc.w);
-                        r.x += q.x;
-                        r.y += q.y;
-                        r.z += q.z;
-                        r.w += q.w;
-                    }
-                    *reinterpret_cast<uint2 *>(outp + outOrigin[pk]) = make_uint2(pack_half2(r.x, r.y), pack_half2(r.z, r.w));
-                }
-                fetch_res(cg + 2 * parts, rq);
-            };
-            bool released = false;
-            auto do_group = [&](int cg, uint2 (&rq)[4]) {
-                uint32_t acc[16];
-                tmem_ld16(taddr + cg * 16, acc);
-                tmem_ld_wait();
-                if (cg + parts >= ngroups) {
-                    release();
-                    released = true;
-                }
-                finish_group(cg, acc, rq);
-            };
-            for (int cg = part; cg < ngroups; cg += 2 * parts) {
-                do_group(cg, rq0);
-                if (cg + parts < ngroups) do_group(cg + parts, rq1);
-            }
-            if (!released) release();   // (fewer column groups than warps per quarter: this warp had nothing to read)
+        epilogue_tiles<false>(a, warp - loadWarps - 1, warp & 3, tmem, accFull, accEmpty, sScale, sBias, outOrigin, resOrigin);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == loadWarps) tmem_dealloc(tmem, tmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Halo-tile kernel for 3x3 stride-1 layers on large grids.  k_conv_deep_tc_p gathers every input texel nine times (one A
+// stage per tap); here a stage holds the HALO of a tile -- its 128 GEMM rows plus one virtual row and one pixel on either
+// side -- for 64 input channels, gathered ONCE, and the nine taps are nine tcgen05.mma groups whose A descriptors start
+// (ky * Wv + kx) pixels into that stage (SWIZZLE_NONE K-major: a pixel is 16 bytes in every 8-channel chunk, so any
+// pixel shift is a legal descriptor start).  For the shift to be the same for every row, the GEMM rows walk a VIRTUAL
+// raster: Wv = W + 1 columns and H + 1 rows per image, the extra column / row being the zero border that both neighbours
+// share (the deep layout's own idea, deeptiler.cpp:63-95); border rows are computed and dropped by the epilogue
+// (W = 56: 3.4 % of the rows, W = 7: 23 %).  Weights travel in their own ring, one (tap, 64 channels) block per entry,
+// fetched by a dedicated producer warp.  K order: channel stages outermost, taps inside (k_conv_deep_tc walks taps
+// outermost): same products, different fp32 summation order -- not bit-identical to the other kernels, same tolerance.
+// ---------------------------------------------------------------------------------------------
+constexpr int kThreadsDeepH = (kWarpsP + 1) * 32;
+
+template <int ACT>
+__global__ void __launch_bounds__(kThreadsDeepH, 1) k_conv_deep_tc_h3(const __grid_constant__ DeepTcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int aStageBytes = a.HPp * 128, bStageBytes = a.NT * kKC * 2;
+    const int nOutPlanes = a.Cout4 >> 2;
+    unsigned char *sA = smem;
+    unsigned char *sB = sA + a.ring * aStageBytes;
+    float4 *sScale = reinterpret_cast<float4 *>(sB + a.ringB * bStageBytes);
+    float4 *sBias = sScale + nOutPlanes;
+    int *inOrigin = reinterpret_cast<int *>(sBias + nOutPlanes);             // [nInPlanes] (16-byte aligned)
+    int *outOrigin = inOrigin + a.nInPlanes;
+    int *resOrigin = outOrigin + nOutPlanes;
+    uint64_t *fullA = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(resOrigin + nOutPlanes) + 7) & ~uintptr_t(7));
+    uint64_t *emptyA = fullA + kMaxRingP;
+    uint64_t *fullB = emptyA + kMaxRingP;
+    uint64_t *emptyB = fullB + kMaxRingP;
+    uint64_t *accFull = emptyB + kMaxRingP;
+    uint64_t *accEmpty = accFull + 2;
+    uint32_t *tmemBase = reinterpret_cast<uint32_t *>(accEmpty + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int loadWarps = 4 * a.nsets, nthreads = kThreadsDeepH;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.ring; s++) {
+            mbar_init(&fullA[s], kM);
+            mbar_init(&emptyA[s], 1);
         }
+        for (int s = 0; s < a.ringB; s++) {
+            mbar_init(&fullB[s], 1);
+            mbar_init(&emptyB[s], 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&accFull[b], 1);
+            mbar_init(&accEmpty[b], (uint32_t)a.epiWarps);
+        }
+        fence_barrier_init();
+    }
+    const uint32_t tmemCols = a.NT > 128 ? 512u : (a.NT > 64 ? 256u : 128u);
+    if (warp == loadWarps) tmem_alloc(tmemBase, tmemCols);
+    for (int q = threadIdx.x; q < a.nInPlanes; q += nthreads) inOrigin[q] = ((q / a.in.tx) * a.in.tileH * a.in.texW + (q % a.in.tx) * a.in.tileW) * 4;
+    for (int p = threadIdx.x; p < nOutPlanes; p += nthreads) {
+        outOrigin[p] = ((p / a.out.tx) * a.out.tileH * a.out.texW + (p % a.out.tx) * a.out.tileW) * 4;
+        resOrigin[p] = a.hasRes ? ((p / a.res.tx) * a.res.tileH * a.res.texW + (p % a.res.tx) * a.res.tileW) * 4 : 0;
+        sScale[p] = __ldg(reinterpret_cast<const float4 *>(a.scale) + p);
+        sBias[p] = __ldg(reinterpret_cast<const float4 *>(a.bias) + p);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmemBase;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    if (warp < loadWarps) {
+        // ===================== loaders: a set gathers the halo of one (tile, 64-channel stage): thread = halo pixel t and t + 128
+        const int t = threadIdx.x & (kM - 1), set = warp >> 2;
+        const int Hv = a.Ho + 1;
+        int s = set;                                       // tile-local index of the set's next channel stage
+        int slot = set;
+        uint32_t phase = 0;
+        for (TileWalk w(a); !w.done(); w.next(), s -= a.kcs) {
+            if (s >= a.kcs) continue;
+            // virtual raster position of halo pixel h: j = tile start - Wv - 1 + h
+            const __half *px[2];
+            bool ok[2];
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int h = t + r * kM;
+                const int j = w.mt * kM - a.Wv - 1 + h;
+                ok[r] = h < a.HPp && j >= 0 && j < (int)a.Mtotal;
+                const unsigned ju = ok[r] ? (unsigned)j : 0u;
+                const unsigned vr = ju / (unsigned)a.Wv, c = ju - vr * (unsigned)a.Wv;
+                const unsigned n = vr / (unsigned)Hv, y = vr - n * (unsigned)Hv;
+                ok[r] = ok[r] && c < (unsigned)a.Wo && y < (unsigned)a.Ho;
+                px[r] = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems + ((a.inP + (int)y) * a.in.texW + a.inP + (int)c) * 4;
+            }
+            for (; s < a.kcs; s += a.nsets) {
+                const int st = slot;
+                mbar_wait(&emptyA[st], phase ^ 1);
+                const int4 *org4 = reinterpret_cast<const int4 *>(inOrigin + s * (kKC / 4));
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const int h = t + r * kM;
+                    if (h >= a.HPp) continue;
+                    uint2 v[kKC / 4];
+#pragma unroll
+                    for (int j4 = 0; j4 < kKC / 16; j4++) {
+                        const int4 o = org4[j4];
+                        v[4 * j4 + 0] = ok[r] ? __ldg(reinterpret_cast<const uint2 *>(px[r] + o.x)) : make_uint2(0u, 0u);
+                        v[4 * j4 + 1] = ok[r] ? __ldg(reinterpret_cast<const uint2 *>(px[r] + o.y)) : make_uint2(0u, 0u);
+                        v[4 * j4 + 2] = ok[r] ? __ldg(reinterpret_cast<const uint2 *>(px[r] + o.z)) : make_uint2(0u, 0u);
+                        v[4 * j4 + 3] = ok[r] ? __ldg(reinterpret_cast<const uint2 *>(px[r] + o.w)) : make_uint2(0u, 0u);
+                    }
+                    unsigned char *dst = sA + (size_t)st * aStageBytes + h * 16;
+#pragma unroll
+                    for (int c = 0; c < kKC / 8; c++) {
+                        const uint2 lo = act_h4_t<ACT>(v[2 * c], a.act), hi = act_h4_t<ACT>(v[2 * c + 1], a.act);
+                        *reinterpret_cast<uint4 *>(dst + c * (a.HPp * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&fullA[st]);
+                slot += a.nsets;
+                if (slot >= a.ring) {
+                    slot -= a.ring;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == loadWarps) {
+        // ===================== MMA issuer: per channel stage nine tap groups of four K16 MMAs on the same halo
+        const uint64_t hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
+        const uint32_t aLbo = ((uint32_t)(a.HPp * 16) >> 4) << 16, bLbo = ((uint32_t)(a.NT * 16) >> 4) << 16;
+        if (elect_one()) {
+            int slotA = 0, slotB = 0;
+            uint32_t phaseA = 0, phaseB = 0, tcount = 0;
+            for (TileWalk w(a); !w.done(); w.next(), tcount++) {
+                const uint32_t buf = tcount & 1;
+                mbar_wait(&accEmpty[buf], ((tcount >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem + buf * (uint32_t)a.NT;
+                for (int kc = 0; kc < a.kcs; kc++) {
+                    mbar_wait(&fullA[slotA], phaseA);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA + (size_t)slotA * aStageBytes) >> 4;
+                    for (int tap = 0; tap < 9; tap++) {
+                        mbar_wait(&fullB[slotB], phaseB);
+                        tc_fence_after();
+                        const uint32_t b0 = smem_u32(sB + (size_t)slotB * bStageBytes) >> 4;
+                        const uint32_t shift = (uint32_t)((tap / 3) * a.Wv + tap % 3);     // pixels = 16-byte units
+#pragma unroll
+                        for (int j = 0; j < kKC / 16; j++)
+                            umma_f16(tacc, hi | (uint64_t)(aLbo | (a0 + shift + (uint32_t)(j * 2 * a.HPp))), hi | (uint64_t)(bLbo | (b0 + (uint32_t)(j * 2 * a.NT))),
+                                     a.idesc, (kc > 0 || tap > 0 || j > 0) ? 1u : 0u);
+                        umma_commit(&emptyB[slotB]);
+                        if (++slotB == a.ringB) {
+                            slotB = 0;
+                            phaseB ^= 1;
+                        }
+                    }
+                    umma_commit(&emptyA[slotA]);
+                    if (++slotA == a.ring) {
+                        slotA = 0;
+                        phaseA ^= 1;
+                    }
+                }
+                umma_commit(&accFull[buf]);
+            }
+        }
+        __syncwarp();
+    } else if (warp < loadWarps + 1 + a.epiWarps) {
+        epilogue_tiles<true>(a, warp - loadWarps - 1, warp & 3, tmem, accFull, accEmpty, sScale, sBias, outOrigin, resOrigin);
+    } else if (warp == kWarpsP) {
+        // ===================== weight producer: one (tap, 64 channels) block per ring entry, in the MMA issuer's order
+        if (elect_one()) {
+            int slotB = 0;
+            uint32_t phaseB = 0;
+            for (TileWalk w(a); !w.done(); w.next()) {
+                const uint4 *wsrc = a.wimg + (size_t)w.nt * a.nstages * (bStageBytes >> 4);
+                for (int kc = 0; kc < a.kcs; kc++)
+                    for (int tap = 0; tap < 9; tap++) {
+                        mbar_wait(&emptyB[slotB], phaseB ^ 1);
+                        mbar_expect_tx(&fullB[slotB], (uint32_t)bStageBytes);
+                        bulk_g2s(sB + (size_t)slotB * bStageBytes, wsrc + (size_t)(tap * a.kcs + kc) * (bStageBytes >> 4), (uint32_t)bStageBytes, &fullB[slotB]);
+                        if (++slotB == a.ringB) {
+                            slotB = 0;
+                            phaseB ^= 1;
+                        }
+                    }
+            }
+        }
+        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();
@@ -906,6 +1087,67 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     // FYN_DEEP_PERSIST=0 keeps the one-tile-per-CTA kernel (read per run: tests compare the two).
     const char *pe = getenv("FYN_DEEP_PERSIST");
     const int sms = op->ctx->prop.multiProcessorCount;
+    const char *he = getenv("FYN_DEEP_HALO");          // 0: every layer on the stage-per-tap kernels (read per run)
+    // 3x3 stride-1 layers take the halo-tile kernel on ANY grid: on small ones (batch 1) a CTA's chain of K stages is what
+    // the layer takes, and one gather per 64 channels instead of nine shortens it ninefold
+    const bool halo = a.K == 3 && a.ds == 1 && !a.tapPacked && !a.inNorm && a.inP >= 1 && (!he || atoi(he) != 0) && (!pe || atoi(pe) != 0);
+    if (halo) {
+        a.ntilesN = ntiles;
+        a.totalTiles = mtiles * ntiles;
+        {
+            DeepTcArgs h = a;
+            h.Wv = a.Wo + 1;
+            const long long J = (long long)a.batch * (a.Ho + 1) * h.Wv;      // virtual raster rows of the whole batch
+            h.Mtotal = J;
+            const long long mt3 = (J + kM - 1) / kM;
+            h.totalTiles = mt3 * ntiles;
+            h.HPp = (kM + 2 * h.Wv + 2 + 7) & ~7;
+            const size_t aStage = (size_t)h.HPp * 128, bStage = (size_t)a.NT * kKC * 2;
+            const size_t fixedH = (size_t)(a.Cout4 / 4) * 32 + ((size_t)a.nInPlanes + 2 * (size_t)(a.Cout4 / 4)) * 4 + 8 + (4 * kMaxRingP + 4) * 8 + 16;
+            const size_t budgetH = (size_t)op->ctx->prop.sharedMemPerBlockOptin - 1024;
+            // weight ring: at least four entries (the nine tap groups of a stage stream through it), halo ring: what is left, at most four
+            int ringB = 6, ringA = 0;
+            for (; ringB >= 3; ringB--) {
+                const size_t left = budgetH > fixedH + ringB * bStage ? budgetH - fixedH - ringB * bStage : 0;
+                ringA = (int)std::min<size_t>(4, left / aStage);
+                if (ringA >= 2) break;
+            }
+            if (ringB >= 3 && ringA >= 2 && h.HPp <= 2 * kM && h.totalTiles < (1ll << 31) - 2 * sms && J < (1ll << 31) - 4 * kM) {
+                h.ring = ringA;
+                h.ringB = ringB;
+                h.nsets = std::min(ringA, a.NT >= 256 ? 2 : 3);
+                if (const char *e = getenv("FYN_DEEP_SETS")) h.nsets = std::max(1, std::min(std::min(4, ringA), atoi(e)));
+                h.epiWarps = 24 - 4 * h.nsets;
+                if (h.nsets < 2) h.epiWarps = 16;
+                const size_t smemH = ringA * aStage + ringB * bStage + fixedH;
+                static size_t maxSmemH[64] = {0};
+                static std::mutex lockH;
+                {
+                    std::lock_guard<std::mutex> guard(lockH);
+                    size_t &cur = maxSmemH[op->ctx->device & 63];
+                    if (smemH > cur) {
+                        FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_h3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemH));
+                        FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_h3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemH));
+                        FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_h3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemH));
+                        cur = smemH;
+                    }
+                }
+                cudaLaunchConfig_t hc{};
+                hc.gridDim = dim3((unsigned)std::min<long long>(h.totalTiles, sms));
+                hc.blockDim = dim3(kThreadsDeepH);
+                hc.dynamicSmemBytes = smemH;
+                hc.stream = stream;
+                hc.attrs = attr;
+                hc.numAttrs = noPdl ? 0 : 1;
+                const int actT = h.act.type <= 1 ? h.act.type : 2;
+                if (actT == 0) FYN_CUDA(cudaLaunchKernelEx(&hc, k_conv_deep_tc_h3<0>, h));
+                else if (actT == 1) FYN_CUDA(cudaLaunchKernelEx(&hc, k_conv_deep_tc_h3<1>, h));
+                else FYN_CUDA(cudaLaunchKernelEx(&hc, k_conv_deep_tc_h3<2>, h));
+                FYN_CHECK_LAUNCH(op->ctx);
+                return FYN_OK;
+            }
+        }
+    }
     if ((!pe || atoi(pe) != 0) && mtiles * ntiles >= (pe && atoi(pe) == 2 ? 1ll : 2ll * sms)) {
         a.ntilesN = ntiles;
         a.totalTiles = mtiles * ntiles;
