@@ -543,7 +543,9 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
     unsigned char *sB = sA + a.ring * kAStageBytes;
     float4 *sScale = reinterpret_cast<float4 *>(sB + a.ring * bStageBytes);   // [nOutPlanes] scale, then [nOutPlanes] bias
     float4 *sBias = sScale + nOutPlanes;
-    int *tapTab = reinterpret_cast<int *>(sBias + nOutPlanes);               // [64] (16-byte aligned: read as int4)
+    float4 *sInScale = sBias + nOutPlanes;                                    // fused input batch-norm: [nInPlanes] scale, [nInPlanes] bias (NORM only)
+    float4 *sInBias = sInScale + (NORM ? a.nInPlanes : 0);
+    int *tapTab = reinterpret_cast<int *>(sInBias + (NORM ? a.nInPlanes : 0));   // [64] (16-byte aligned: read as int4)
     int *tapOff = tapTab + 64;                                                // [64] element offset of a tap-packed stage's taps (interior pixels)
     int *inOrigin = tapOff + 64;                                              // [nInPlanes] (16-byte aligned)
     int *outOrigin = inOrigin + a.nInPlanes;                                  // [nOutPlanes] output tensor, then [nOutPlanes] residual tensor
@@ -579,6 +581,8 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
         sScale[p] = __ldg(reinterpret_cast<const float4 *>(a.scale) + p);
         sBias[p] = __ldg(reinterpret_cast<const float4 *>(a.bias) + p);
     }
+    if (NORM)
+        for (int q = threadIdx.x; q < 2 * a.nInPlanes; q += nthreads) sInScale[q] = __ldg(a.inNorm + q);   // (scale planes, then bias planes)
     if (a.tapPacked && threadIdx.x < 64) {
         const int tp = min((int)threadIdx.x, a.K * a.K - 1);
         tapTab[threadIdx.x] = (tp / a.K) | ((tp % a.K) << 8);
@@ -636,10 +640,10 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
                         v[4 * j4 + 3] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + o.w)) : make_uint2(0u, 0u);
                     }
                     if (NORM) {
-                        const float4 *sc = a.inNorm + kc * (kKC / 4), *bi = sc + a.nInPlanes;
+                        const float4 *sc = sInScale + kc * (kKC / 4), *bi = sInBias + kc * (kKC / 4);
 #pragma unroll
                         for (int j = 0; j < kKC / 4; j++) {
-                            const float4 s4 = __ldg(sc + j), b4 = __ldg(bi + j);
+                            const float4 s4 = sc[j], b4 = bi[j];
                             const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&v[j].x));
                             const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&v[j].y));
                             v[j] = make_uint2(pack_half2(fmaf(f0.x, s4.x, b4.x), fmaf(f0.y, s4.y, b4.y)), pack_half2(fmaf(f1.x, s4.z, b4.z), fmaf(f1.y, s4.w, b4.w)));
@@ -1152,7 +1156,8 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
         a.ntilesN = ntiles;
         a.totalTiles = mtiles * ntiles;
         const size_t stageBytes = (size_t)kAStageBytes + (size_t)a.NT * kKC * 2;
-        const size_t fixed = (size_t)(a.Cout4 / 4) * 32 + ((size_t)a.nInPlanes + 2 * (size_t)(a.Cout4 / 4) + 128 + a.nstages) * 4 + 8 + (2 * kMaxRingP + 4) * 8 + 16;
+        const size_t fixed = (size_t)(a.Cout4 / 4) * 32 + (a.inNorm ? (size_t)a.nInPlanes * 32 : 0) + ((size_t)a.nInPlanes + 2 * (size_t)(a.Cout4 / 4) + 128 + a.nstages) * 4 + 8 +
+                             (2 * kMaxRingP + 4) * 8 + 16;
         const size_t budget = (size_t)op->ctx->prop.sharedMemPerBlockOptin - 1024;
         int ring = (int)std::min<size_t>(kMaxRingP, fixed < budget ? (budget - fixed) / stageBytes : 0);
         if (const char *e = getenv("FYN_DEEP_PRING")) ring = std::max(1, std::min(ring, atoi(e)));
@@ -1162,7 +1167,7 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
             // epilogue NT / 16 column groups of 4 texels per pixel (plus as many residual texels)
             const double loadWork = (double)a.nstages, epiWork = (a.NT / 16) * (a.hasRes ? 1.5 : 1.0) * 0.5;
             a.nsets = epiWork > 2.0 * loadWork ? 2 : (epiWork > loadWork ? 3 : 4);
-            if (const char *e = getenv("FYN_DEEP_SETS")) a.nsets = std::max(1, std::min(4, atoi(e)));
+            if (const char *e = getenv("FYN_DEEP_SETS")) a.nsets = std::max(1, std::min(5, atoi(e)));
             a.nsets = std::min(a.nsets, ring);
             a.epiWarps = 24 - 4 * a.nsets;
             if (a.nsets < 2) a.epiWarps = 16;   // (a TMEM lane quarter is drained by at most four warps here)

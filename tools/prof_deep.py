@@ -17,7 +17,7 @@ from fyusenet_b200 import capi  # noqa: E402
 CASES = {  # k, ds, ci, co, size, residual
     "expand": (1, 1, 64, 256, 56, True), "reduce": (1, 1, 256, 64, 56, False), "c3": (3, 1, 64, 64, 56, False),
     "expand28": (1, 1, 128, 512, 28, True), "c3_14": (3, 1, 256, 256, 14, False), "reduce7": (1, 1, 2048, 512, 7, False),
-    "stem": (7, 2, 3, 64, 224, False),
+    "stem": (7, 2, 3, 64, 224, False), "reduce_bn": (1, 1, 256, 64, 56, False),
 }
 
 
@@ -29,6 +29,8 @@ def run(name, batch, reps):
     wb = np.concatenate([rng.uniform(-.1, .1, co), rng.normal(0, np.sqrt(2.0 / (k * k * ci)), co * k * k * ci), rng.uniform(0.5, 1.5, co), rng.uniform(-.1, .1, co)]).astype(np.float32)
     fl = capi.FLAG_DEEP | capi.FLAG_PRE_RELU | capi.FLAG_POST_BATCHNORM | (capi.FLAG_RESIDUAL_INPUT | capi.FLAG_RELU_ON_RESIDUAL if res else 0)
     op = capi.Conv2d(ctx, wb, width=size, height=size, in_channels=ci, out_channels=co, kernel=k, downsample=ds, in_padding=pad, flags=fl)
+    if name.endswith("_bn"):    # the batch-norm layer in front of the convolution, evaluated at the fetch (fyn_conv2d_set_input_norm)
+        op.set_input_norm(np.concatenate([rng.uniform(0.5, 1.5, ci), rng.uniform(-0.5, 0.5, ci)]).astype(np.float32))
     order = capi.ORDER_DEEP
     tin = ctx.tensor(size, size, ci, pad, order, capi.F16, batch)
     so = size // ds
