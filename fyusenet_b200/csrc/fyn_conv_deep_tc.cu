@@ -425,9 +425,12 @@ __device__ __forceinline__ Px locate_row(const DeepTcArgs &a, const TileWalk &w,
 
 // Epilogue warp of the persistent kernels: drains the CTA's tiles from the two TMEM halves.  `e` = index among the epilogue
 // warps, `quarter` = TMEM lane quarter of the warp (warp index & 3); the warps of a quarter alternate over the column groups.
-template <bool HALO>
-__device__ __forceinline__ void epilogue_tiles(const DeepTcArgs &a, int e, int quarter, uint32_t tmem, uint64_t *accFull, uint64_t *accEmpty,
-                                               const float4 *sScale, const float4 *sBias, const int *outOrigin, const int *resOrigin) {
+// RES: residual handling at compile time (the epilogue is issue-bound: ~70 instructions per texel with run-time flags):
+// 0 = no residual, 1 = residual with ReLU (every ResNet bottleneck output), 2 = whatever the arguments say
+template <bool HALO, int RES>
+__device__ __forceinline__ void epilogue_tiles_t(const DeepTcArgs &a, int e, int quarter, uint32_t tmem, uint64_t *accFull, uint64_t *accEmpty,
+                                                 const float4 *sScale, const float4 *sBias, const int *outOrigin, const int *resOrigin) {
+    const bool hasRes = RES == 2 ? a.hasRes != 0 : RES == 1, reluRes = RES == 2 ? a.reluRes != 0 : true, bnRes = RES == 2 ? a.bnRes != 0 : false;
     const int part = e >> 2, lane = threadIdx.x & 31, parts = a.epiWarps >> 2;
     const int t = quarter * 32 + lane;
     const int ngroups = a.NT >> 4, nOutPlanes = a.Cout4 >> 2;
@@ -437,7 +440,7 @@ __device__ __forceinline__ void epilogue_tiles(const DeepTcArgs &a, int e, int q
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int pk = p.plane0 + cg * 4 + k;
-            rq[k] = (a.hasRes && p.valid && cg < ngroups && pk < nOutPlanes) ? __ldg(reinterpret_cast<const uint2 *>(p.resp + resOrigin[pk])) : make_uint2(0u, 0u);
+            rq[k] = (hasRes && p.valid && cg < ngroups && pk < nOutPlanes) ? __ldg(reinterpret_cast<const uint2 *>(p.resp + resOrigin[pk])) : make_uint2(0u, 0u);
         }
     };
     auto finish = [&](const Px &p, int cg, const uint32_t (&acc)[16], const uint2 (&rq)[4]) {
@@ -448,12 +451,12 @@ __device__ __forceinline__ void epilogue_tiles(const DeepTcArgs &a, int e, int q
             const float4 sc = sScale[pk], bi = sBias[pk];
             float4 r = make_float4(fmaf(__uint_as_float(acc[4 * k + 0]), sc.x, bi.x), fmaf(__uint_as_float(acc[4 * k + 1]), sc.y, bi.y),
                                    fmaf(__uint_as_float(acc[4 * k + 2]), sc.z, bi.z), fmaf(__uint_as_float(acc[4 * k + 3]), sc.w, bi.w));
-            if (a.hasRes) {
+            if (hasRes) {
                 const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&rq[k].x));
                 const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&rq[k].y));
                 float4 q = make_float4(f0.x, f0.y, f1.x, f1.y);
-                if (a.reluRes) q = make_float4(fmaxf(q.x, 0.f), fmaxf(q.y, 0.f), fmaxf(q.z, 0.f), fmaxf(q.w, 0.f));
-                if (a.bnRes) q = make_float4(q.x * sc.x, q.y * sc.y, q.z * sc.z, q.w * sc.w);
+                if (reluRes) q = make_float4(fmaxf(q.x, 0.f), fmaxf(q.y, 0.f), fmaxf(q.z, 0.f), fmaxf(q.w, 0.f));
+                if (bnRes) q = make_float4(q.x * sc.x, q.y * sc.y, q.z * sc.z, q.w * sc.w);
                 r.x += q.x;
                 r.y += q.y;
                 r.z += q.z;
@@ -532,6 +535,14 @@ __device__ __forceinline__ void epilogue_tiles(const DeepTcArgs &a, int e, int q
     }
 }
 
+
+template <bool HALO>
+__device__ __forceinline__ void epilogue_tiles(const DeepTcArgs &a, int e, int quarter, uint32_t tmem, uint64_t *accFull, uint64_t *accEmpty,
+                                               const float4 *sScale, const float4 *sBias, const int *outOrigin, const int *resOrigin) {
+    if (!a.hasRes) epilogue_tiles_t<HALO, 0>(a, e, quarter, tmem, accFull, accEmpty, sScale, sBias, outOrigin, resOrigin);
+    else if (a.reluRes && !a.bnRes) epilogue_tiles_t<HALO, 1>(a, e, quarter, tmem, accFull, accEmpty, sScale, sBias, outOrigin, resOrigin);
+    else epilogue_tiles_t<HALO, 2>(a, e, quarter, tmem, accFull, accEmpty, sScale, sBias, outOrigin, resOrigin);
+}
 
 // ACT: activation at the fetch as a compile-time constant (0 none, 1 ReLU, 2 whatever args.act says)
 template <bool NORM, int ACT>
