@@ -68,17 +68,46 @@ def layer_algorithmic(ksize=KSIZE, w=WIDTH, h=HEIGHT):
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi DURING the timed region (B200_PROFILING.md)."""
+    """Samples SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  The timed region of the
+    headline is a few milliseconds, shorter than one period of `nvidia-smi -lms`, so the samples come from NVML in this
+    process (the same counters nvidia-smi prints: clocks.sm, clocks.max.sm, power.draw, clocks_event_reasons.*), every 2 ms
+    from a thread; `nvidia-smi -lms 100` is the fallback when NVML cannot be loaded.  rows: [index, sm, max sm, power W, ...]."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, device_index: int):
         self.idx = device_index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.t = None
+        self._stop = threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        # CUDA_VISIBLE_DEVICES renumbers the devices NVML sees in board order: go through the PCI bus id when torch knows it
+        try:
+            import torch
+            bus = torch.cuda.get_device_properties(self.idx).pci_bus_id
+            dom = torch.cuda.get_device_properties(self.idx).pci_domain_id
+            dev = torch.cuda.get_device_properties(self.idx).pci_device_id
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0")
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.idx)
 
     def start(self):
         try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.source = "nvidia-smi"
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -86,32 +115,57 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+        bits = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown, n.nvmlClocksEventReasonSwThermalSlowdown,
+                n.nvmlClocksEventReasonSwPowerCap]
+        it, watts = 0, float("nan")
+        while True:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                if it % 8 == 1:     # (the power query is the slow one: every 8th sample, and not the first)
+                    try:
+                        watts = n.nvmlDeviceGetPowerUsage(self.handle) / 1e3
+                    except Exception:
+                        watts = float("nan")
+                it += 1
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.rows.append([str(self.idx), sm, mx, watts, hex(mask)] + ["Active" if mask & b else "Not Active" for b in bits])
+            except Exception:
+                pass
+            if self._stop.wait(0.002):
+                return
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=2)
+        elif self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                for nme, v in zip(self.NAMES, r[5:9]):
+                    if str(v).lower().startswith("active"):
+                        reasons.add(nme)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def peaks():
@@ -349,7 +403,8 @@ def sustained_run(net, ctx, local_rank, seconds=3.0):
     power = []
     for r in sampler.rows:
         try:
-            power.append(float(r[3]))
+            if np.isfinite(float(r[3])):
+                power.append(float(r[3]))
         except Exception:
             pass
     return {"value": frames / (dev_ms / 1e3), "unit": "frames/s", "frames": frames, "seconds": dev_ms / 1e3, "ms_per_step": dev_ms / frames,
