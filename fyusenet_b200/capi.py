@@ -122,7 +122,7 @@ EXPORTS = [
     "fyn_upload_f32_async", "fyn_download_f32_async", "fyn_download_f32_elems",
     "fyn_upload_u8_async", "fyn_download_u8_bytes", "fyn_download_u8_convert", "fyn_download_u8_async", "fyn_tensor_write_chw_f32",
     "fyn_tensor_read_chw_f32", "fyn_conv2d_output_size", "fyn_conv2d_create", "fyn_conv2d_load_weights",
-    "fyn_conv2d_run", "fyn_conv2d_backend", "fyn_conv2d_set_epilogue", "fyn_conv2d_set_input_norm", "fyn_conv2d_plan_query",
+    "fyn_conv2d_run", "fyn_conv2d_backend", "fyn_conv2d_last_kernel", "fyn_conv2d_set_epilogue", "fyn_conv2d_set_input_norm", "fyn_conv2d_plan_query",
     "fyn_conv_chain_create", "fyn_conv_chain_layers", "fyn_conv_chain_run", "fyn_conv_chain_destroy", "fyn_pool2d_create", "fyn_pool2d_run", "fyn_batchnorm_create",
     "fyn_batchnorm_load", "fyn_batchnorm_run", "fyn_sigmoid_create", "fyn_sigmoid_run", "fyn_op_destroy",
     "fyn_scale_create", "fyn_scale_out_size", "fyn_scale_run", "fyn_arith_create", "fyn_arith_run", "fyn_concat_create",
@@ -375,6 +375,12 @@ class Conv2d(_Op):
     @property
     def backend(self) -> int:
         return lib().fyn_conv2d_backend(self._h)
+
+    @property
+    def last_kernel(self) -> int:
+        """kernel of the last run (fyn_conv2d_last_kernel): 1 direct, 2 shallow tcgen05, 10 / 11 / 12 deep one-tile / persistent /
+        halo-tile, 13 | cluster << 8 | columns << 16 deep split-K cluster kernel"""
+        return lib().fyn_conv2d_last_kernel(self._h)
 
     def load_weights(self, weights):
         w = np.ascontiguousarray(weights, np.float32)

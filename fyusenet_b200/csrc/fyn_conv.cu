@@ -154,6 +154,7 @@ int fyn_conv2d_create(fyn_ctx *ctx, const fyn_conv_desc *desc, const float *wb, 
 }
 
 int fyn_conv2d_backend(const fyn_op *op) { return (op && op->kind == FYN_OP_CONV) ? op->backend : 0; }
+int fyn_conv2d_last_kernel(const fyn_op *op) { return (op && op->kind == FYN_OP_CONV) ? op->lastKernel : 0; }
 
 int fyn_conv2d_set_input_norm(fyn_op *op, const float *sb) {
     if (!op || op->kind != FYN_OP_CONV) FYN_FAIL(FYN_ERR_INVALID, "not a convolution op");
@@ -225,8 +226,10 @@ int fyn_conv2d_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res, fyn_
     if (op->backend == 2 && (op->tc || op->dtc)) {
         // > 0 means "tensor formats not covered by the tcgen05 family": use the direct kernel
         rc = op->dtc ? fyn_conv_deep_tc_run(op, in, res, out, s) : fyn_conv_tc_run(op, in, res, out, s);
+        if (rc == 0 && !op->dtc) op->lastKernel = 2;
         if (rc <= 0) return rc;
     }
+    op->lastKernel = 1;
     if (op->innorm) FYN_FAIL(FYN_ERR_UNSUPPORTED, "conv: a fused input batch-norm needs the deep-tiled tcgen05 kernel (fp16 tensors)");
     // direct family; deep layers on fp16 tensors use the fp16-truncated weight / fp16 bias sets
     fyn_op view = *op;

@@ -60,6 +60,9 @@ struct DeepTcArgs {
     // halo-tile 3x3 kernel: virtual raster width (W + 1), halo pixels per stage (multiple of 8), weight ring depth
     int Wv, HPp, ringB;
     long long totalTiles;
+    // split-K cluster kernel (small grids): columns per CTA (a sub-tile of the NT-column operand image), cluster size along K,
+    // output planes finished per CTA of a cluster
+    int skNT, skSplit, skPpr;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -339,6 +342,248 @@ __global__ void __launch_bounds__(kThreadsDeep, 2) k_conv_deep_tc(const __grid_c
                 if (s == a.nstages - 1) umma_commit(done);
             }
             __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == loadWarps) tmem_dealloc(tmem, tmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split-K cluster kernel for SMALL grids (batch 1: a layer is 1 ... 50 output tiles on 148 SMs, and the time of a layer is the
+// length of one CTA's chain of K stages -- 2048 -> 512 @7x7 took 42 us as 4 CTAs of 32 stages).  Here the K stages of one output
+// tile are split over the CTAs of a thread-block CLUSTER (<= 8, gridDim.z) and the tile is narrowed to skNT <= 64 columns (a
+// sub-tile of the NT-column operand image, fetched as eight 16 * skNT-byte bulk copies per stage), so that a layer spreads over
+// ~100 CTAs of <= 5 stages, all of them in flight at once.  Every CTA accumulates its K slice in TMEM; the partial tiles
+// are then REDUCE-SCATTERED through distributed shared memory: CTA r owns skPpr output planes, every CTA stores its fp32 partials
+// of those planes into r's buffer (st.shared::cluster, one float4 = one texel per thread, rows contiguous), a cluster barrier,
+// and r sums the partials in rank order (deterministic) and runs the usual epilogue on its planes.  Same operands as the other
+// kernels, another fp32 summation order (K slices summed separately): same tolerance against the oracle, not the same bits.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_cluster_f4(uint32_t localAddr, uint32_t rank, float4 v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(localAddr), "r"(rank));
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <bool NORM>
+__global__ void __launch_bounds__(kThreadsDeep, 1) k_conv_deep_tc_sk(const __grid_constant__ DeepTcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int NTs = a.skNT, ks = a.skSplit, ppr = a.skPpr;
+    const int bStageBytes = NTs * kKC * 2;
+    unsigned char *sA = smem;
+    unsigned char *sB = sA + a.ring * kAStageBytes;
+    float4 *red = reinterpret_cast<float4 *>(sB + a.ring * bStageBytes);   // [source rank][plane of this CTA][GEMM row]
+    int *inOrigin = reinterpret_cast<int *>(red + (size_t)ks * ppr * kM);   // [nInPlanes]
+    int *outOrigin = inOrigin + a.nInPlanes;                               // [ppr] output tensor, then [ppr] residual tensor
+    int *resOrigin = outOrigin + ppr;
+    uint64_t *full = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(resOrigin + ppr) + 7) & ~uintptr_t(7));
+    uint64_t *empty = full + kMaxRing;
+    uint64_t *done = empty + kMaxRing;
+    uint32_t *tmemBase = reinterpret_cast<uint32_t *>(done + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int loadWarps = 4 * a.nsets, nthreads = (loadWarps + 1) * 32;
+    const int rank = ks > 1 ? (int)cluster_ctarank() : 0;                  // cluster = (1, 1, ks): the CTAs of one output tile
+#ifdef FYN_SK_DEBUG
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+        uint32_t nr, cx, cy, cz;
+        asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nr));
+        asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(cx));
+        asm volatile("mov.u32 %0, %%cluster_nctaid.y;" : "=r"(cy));
+        asm volatile("mov.u32 %0, %%cluster_nctaid.z;" : "=r"(cz));
+        printf("sk: block z %d rank %d nctarank %u cluster dims %u %u %u ks %d NTs %d ppr %d smem %x red %x\n", blockIdx.z, rank, nr, cx, cy, cz, ks, NTs, ppr, smem_u32(smem), smem_u32(red));
+    }
+#endif
+    const int sub = blockIdx.y;                                            // sub-tile of skNT columns
+    const int s0 = rank * a.nstages / ks, nloc = (rank + 1) * a.nstages / ks - s0;   // this CTA's K stages
+    const int plane0 = sub * (NTs >> 2) + rank * ppr;                      // first output plane this CTA finishes
+    const int nOutPlanes = a.Cout4 >> 2;
+    const long long m0 = (long long)blockIdx.x * kM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.ring; s++) {
+            mbar_init(&full[s], kM + 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    const uint32_t tmemCols = NTs > 64 ? 128u : (NTs > 32 ? 64u : 32u);
+    if (warp == loadWarps) tmem_alloc(tmemBase, tmemCols);
+    for (int q = threadIdx.x; q < a.nInPlanes; q += nthreads) inOrigin[q] = ((q / a.in.tx) * a.in.tileH * a.in.texW + (q % a.in.tx) * a.in.tileW) * 4;
+    for (int k = threadIdx.x; k < ppr; k += nthreads) {
+        const int p = plane0 + k;
+        outOrigin[k] = ((p / a.out.tx) * a.out.tileH * a.out.texW + (p % a.out.tx) * a.out.tileW) * 4;
+        resOrigin[k] = a.hasRes ? ((p / a.res.tx) * a.res.tileH * a.res.texW + (p % a.res.tx) * a.res.tileW) * 4 : 0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmemBase;
+    // "this CTA runs": nobody stores into a peer's shared memory before every CTA of the cluster has arrived here
+    if (ks > 1) cluster_arrive_relaxed();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    if (warp < loadWarps) {
+        // ===================== loaders: thread = GEMM row = output pixel =====================
+        const int t = threadIdx.x & (kM - 1), set = warp >> 2;
+        const long long m = m0 + t;
+        const bool valid = m < a.Mtotal;
+        const int hw = a.Ho * a.Wo;
+        const int n = valid ? (int)(m / hw) : 0;
+        const int rem = valid ? (int)(m - (long long)n * hw) : 0;
+        const int yo = rem / a.Wo, xo = rem - yo * a.Wo;
+        const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems;
+        // the sub-tile's columns inside the NT-column operand image: [n tile][stage][chunk][NT][8 halfs]
+        const int col0 = sub * NTs, ntile = col0 / a.NT, colIn = col0 - ntile * a.NT;
+        const uint4 *wsrc = a.wimg + (size_t)ntile * a.nstages * (a.NT * kKC * 2 >> 4) + colIn;
+        for (int i = set; i < nloc; i += a.nsets) {
+            const int s = s0 + i;
+            const int st = i % a.ring, use = i / a.ring;
+            const int tap = s / a.kcs, kc = s - tap * a.kcs;
+            const int ky = tap / a.K, kx = tap - ky * a.K;
+            mbar_wait(&empty[st], (use & 1) ^ 1);
+            if (t < 8) {
+                if (t == 0) mbar_expect_tx(&full[st], (uint32_t)bStageBytes);
+                __syncwarp(0xffu);
+                bulk_g2s(sB + (size_t)st * bStageBytes + t * (NTs * 16), wsrc + (size_t)s * (a.NT * kKC * 2 >> 4) + t * a.NT, (uint32_t)(NTs * 16), &full[st]);
+            }
+            uint2 v[kKC / 4];
+            const int iy = a.inP + a.ds * yo + ky - a.mh, ix = a.inP + a.ds * xo + kx - a.mh;
+            const __half *px = src + (iy * a.in.texW + ix) * 4;
+            const int4 *org4 = reinterpret_cast<const int4 *>(inOrigin + kc * (kKC / 4));
+#pragma unroll
+            for (int j4 = 0; j4 < kKC / 16; j4++) {
+                const int4 o = org4[j4];
+                v[4 * j4 + 0] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + o.x)) : make_uint2(0u, 0u);
+                v[4 * j4 + 1] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + o.y)) : make_uint2(0u, 0u);
+                v[4 * j4 + 2] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + o.z)) : make_uint2(0u, 0u);
+                v[4 * j4 + 3] = valid ? __ldg(reinterpret_cast<const uint2 *>(px + o.w)) : make_uint2(0u, 0u);
+            }
+            if (NORM) {
+                // the stand-alone batch-norm layer in front of this convolution, evaluated at the fetch (see k_conv_deep_tc)
+                const float4 *sc = a.inNorm + kc * (kKC / 4), *bi = sc + a.nInPlanes;
+#pragma unroll
+                for (int j = 0; j < kKC / 4; j++) {
+                    const float4 s4 = __ldg(sc + j), b4 = __ldg(bi + j);
+                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&v[j].x));
+                    const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&v[j].y));
+                    v[j] = make_uint2(pack_half2(fmaf(f0.x, s4.x, b4.x), fmaf(f0.y, s4.y, b4.y)), pack_half2(fmaf(f1.x, s4.z, b4.z), fmaf(f1.y, s4.w, b4.w)));
+                }
+            }
+            unsigned char *dst = sA + (size_t)st * kAStageBytes + t * 16;
+#pragma unroll
+            for (int c = 0; c < kKC / 8; c++) {
+                const uint2 lo = act_h4(v[2 * c], a.act), hi = act_h4(v[2 * c + 1], a.act);
+                *reinterpret_cast<uint4 *>(dst + c * (kM * 16)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            }
+            fence_proxy_async();
+            mbar_arrive(&full[st]);
+        }
+        // ===================== partial tile -> owners' buffers =====================
+        // epilogue operands of this thread's first planes travel while the MMAs finish
+        __half *outp = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((a.outP + yo) * a.out.texW + a.outP + xo) * 4;
+        const __half *resp = reinterpret_cast<const __half *>(a.res.ptr) + (long long)n * a.res.imageElems + ((a.resP + yo) * a.res.texW + a.resP + xo) * 4;
+        constexpr int kPre = 2;
+        float4 scPre[kPre], biPre[kPre];
+        uint2 rqPre[kPre];
+#pragma unroll
+        for (int g = 0; g < kPre; g++) {
+            const int lp = set + g * a.nsets;
+            const bool ok = valid && lp < ppr && rank * ppr + lp < (NTs >> 2) && plane0 + lp < nOutPlanes;
+            scPre[g] = ok ? __ldg(reinterpret_cast<const float4 *>(a.scale) + plane0 + lp) : make_float4(0.f, 0.f, 0.f, 0.f);
+            biPre[g] = ok ? __ldg(reinterpret_cast<const float4 *>(a.bias) + plane0 + lp) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rqPre[g] = (ok && a.hasRes) ? __ldg(reinterpret_cast<const uint2 *>(resp + resOrigin[lp])) : make_uint2(0u, 0u);
+        }
+        mbar_wait(done, 0);
+        tc_fence_after();
+        if (ks > 1) cluster_wait_acquire();            // every CTA of the cluster is running: its buffer may be written
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // TMEM lane quarter of this warp
+        for (int cg = set; cg < (NTs >> 4); cg += a.nsets) {
+            uint32_t acc[16];
+            tmem_ld16(taddr + cg * 16, acc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int p = cg * 4 + k, owner = p / ppr, lp = p - owner * ppr;
+                const float4 val = make_float4(__uint_as_float(acc[4 * k + 0]), __uint_as_float(acc[4 * k + 1]), __uint_as_float(acc[4 * k + 2]), __uint_as_float(acc[4 * k + 3]));
+                float4 *slot = red + ((size_t)rank * ppr + lp) * kM + t;
+                if (ks > 1) st_cluster_f4(smem_u32(slot) & 0xffffffu, (uint32_t)owner, val);
+                else *slot = val;
+            }
+        }
+        tc_fence_before();
+        if (ks > 1) {
+            cluster_arrive_release();
+            cluster_wait_acquire();
+        } else {
+            asm volatile("bar.sync 1, %0;" ::"r"(loadWarps * 32) : "memory");
+        }
+        // ===================== epilogue of this CTA's planes: partials summed in rank order =====================
+        int g = 0;
+        for (int lp = set; lp < ppr; lp += a.nsets, g++) {
+            const int plane = plane0 + lp;
+            if (!valid || rank * ppr + lp >= (NTs >> 2) || plane >= nOutPlanes) continue;
+            float4 acc = red[(size_t)lp * kM + t];
+            for (int r = 1; r < ks; r++) {
+                const float4 q = red[((size_t)r * ppr + lp) * kM + t];
+                acc.x += q.x;
+                acc.y += q.y;
+                acc.z += q.z;
+                acc.w += q.w;
+            }
+            const float4 sc = g == 0 ? scPre[0] : (g == 1 ? scPre[1] : __ldg(reinterpret_cast<const float4 *>(a.scale) + plane));
+            const float4 bi = g == 0 ? biPre[0] : (g == 1 ? biPre[1] : __ldg(reinterpret_cast<const float4 *>(a.bias) + plane));
+            float4 r = make_float4(fmaf(acc.x, sc.x, bi.x), fmaf(acc.y, sc.y, bi.y), fmaf(acc.z, sc.z, bi.z), fmaf(acc.w, sc.w, bi.w));
+            if (a.hasRes) {
+                const uint2 raw = g == 0 ? rqPre[0] : (g == 1 ? rqPre[1] : __ldg(reinterpret_cast<const uint2 *>(resp + resOrigin[lp])));
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+                const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+                float4 q = make_float4(f0.x, f0.y, f1.x, f1.y);
+                if (a.reluRes) q = make_float4(fmaxf(q.x, 0.f), fmaxf(q.y, 0.f), fmaxf(q.z, 0.f), fmaxf(q.w, 0.f));
+                if (a.bnRes) q = make_float4(q.x * sc.x, q.y * sc.y, q.z * sc.z, q.w * sc.w);
+                r.x += q.x;
+                r.y += q.y;
+                r.z += q.z;
+                r.w += q.w;
+            }
+            *reinterpret_cast<uint2 *>(outp + outOrigin[lp]) = make_uint2(pack_half2(r.x, r.y), pack_half2(r.z, r.w));
+        }
+    } else {
+        // ===================== MMA issuer =====================
+        const uint64_t hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;   // SBO = 128 B, descriptor version 1
+        const uint32_t aLbo = ((uint32_t)(kM * 16) >> 4) << 16, bLbo = ((uint32_t)(NTs * 16) >> 4) << 16;
+        for (int i = 0; i < nloc; i++) {
+            const int st = i % a.ring, use = i / a.ring;
+            if (elect_one()) {
+                mbar_wait(&full[st], use & 1);
+                tc_fence_after();
+                // (in a cluster launch the shared-window address of a CTA carries its rank above bit 24: a matrix descriptor takes
+                // the CTA-relative offset, 14 bits of 16-byte units)
+                const uint32_t a0 = (smem_u32(sA + (size_t)st * kAStageBytes) & 0x3ffffu) >> 4, b0 = (smem_u32(sB + (size_t)st * bStageBytes) & 0x3ffffu) >> 4;
+#pragma unroll
+                for (int j = 0; j < kKC / 16; j++)
+                    umma_f16(tmem, hi | (uint64_t)(aLbo | (a0 + (uint32_t)(j * 2 * kM))), hi | (uint64_t)(bLbo | (b0 + (uint32_t)(j * 2 * NTs))), a.idesc,
+                             (i > 0 || j > 0) ? 1u : 0u);
+                umma_commit(&empty[st]);
+                if (i == nloc - 1) umma_commit(done);
+            }
+            __syncwarp();
+        }
+        if (ks > 1) {   // the cluster barriers count every thread
+            cluster_wait_acquire();
+            cluster_arrive_release();
+            cluster_wait_acquire();
         }
     }
     tc_fence_before();
@@ -1085,6 +1330,86 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     a.scale = a.bias + (size_t)nOut * 4;
     a.inNorm = op->innorm ? reinterpret_cast<const float4 *>(op->d_innorm) : nullptr;
     const long long mtiles = (a.Mtotal + kM - 1) / kM;
+    static const bool noPdl = getenv("FYN_TC_NO_PDL") != nullptr;   // debugging aid: plain stream-ordered launches
+    const char *pe = getenv("FYN_DEEP_PERSIST");
+    const int sms = op->ctx->prop.multiProcessorCount;
+    // Small grids (batch 1): the split-K cluster kernel -- narrower tiles and the K stages of a tile spread over a cluster, so that
+    // a layer of 1 ... 50 tiles still occupies ~100 SMs with <= 5 stages each.  FYN_DEEP_SPLITK: 0 = off, 1 = leave 3x3 stride-1
+    // layers to the halo-tile kernel, 2 = every layer (read per run; FYN_DEEP_PERSIST=0 also switches it off: the one-tile kernel
+    // is the bit-exact reference of the family's tests)
+    const char *ske = getenv("FYN_DEEP_SPLITK");
+    const int skMode = ske ? atoi(ske) : 2;
+    const bool haloShape = a.K == 3 && a.ds == 1 && !a.inNorm && a.inP >= 1;
+    if (skMode && (!pe || atoi(pe) != 0) && !a.tapPacked && a.NT <= 128 && 2 * mtiles * plan->ntiles <= sms && !(skMode == 1 && haloShape)) {
+        const int co16 = ((d.out_channels + 15) / 16) * 16;
+        int NTs = a.NT % 64 == 0 ? 64 : a.NT, ks = 1;
+        long long nsub = 0;
+        auto choose = [&]() {
+            nsub = (co16 + NTs - 1) / NTs;
+            for (ks = 1; ks * 2 <= 8 && ks * 2 <= a.nstages && mtiles * nsub * ks * 2 <= sms;) ks *= 2;
+        };
+        choose();
+        if (NTs == 64 && 2 * mtiles * nsub * ks <= sms) {
+            NTs = 32;
+            choose();
+        }
+        if (const char *e = getenv("FYN_DEEP_SK_NT")) {      // experiments: force the tile width / the split
+            const int v = atoi(e);
+            if (v >= 16 && v <= a.NT && a.NT % v == 0 && v % 16 == 0) {
+                NTs = v;
+                choose();
+            }
+        }
+        if (const char *e = getenv("FYN_DEEP_SK_SPLIT")) ks = std::max(1, std::min(std::min(8, a.nstages), atoi(e)));
+        DeepTcArgs k = a;
+        k.skNT = NTs;
+        k.skSplit = ks;
+        k.skPpr = ((NTs >> 2) + ks - 1) / ks;
+        k.idesc = (1u << 4) | ((uint32_t)(NTs >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+        k.nsets = kLoadSets;
+        k.ring = std::min(kMaxRing, (a.nstages + ks - 1) / ks);
+        const size_t smemK = (size_t)k.ring * (kAStageBytes + (size_t)NTs * kKC * 2) + (size_t)ks * k.skPpr * kM * 16 + ((size_t)a.nInPlanes + 2 * k.skPpr) * 4 + 8 +
+                             (2 * kMaxRing + 1) * 8 + 16;
+        if (smemK <= (size_t)op->ctx->prop.sharedMemPerBlockOptin) {
+            static bool attrSet[64] = {false};
+            static std::mutex lockK;
+            {
+                std::lock_guard<std::mutex> guard(lockK);
+                if (!attrSet[op->ctx->device & 63]) {
+                    const int optin = (int)op->ctx->prop.sharedMemPerBlockOptin;
+                    FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_sk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+                    FYN_CUDA(cudaFuncSetAttribute(k_conv_deep_tc_sk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+                    attrSet[op->ctx->device & 63] = true;
+                }
+            }
+            cudaLaunchAttribute kattr[2];
+            int na = 0;
+            if (!noPdl) {
+                kattr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                kattr[na].val.programmaticStreamSerializationAllowed = 1;
+                na++;
+            }
+            if (ks > 1) {
+                kattr[na].id = cudaLaunchAttributeClusterDimension;
+                kattr[na].val.clusterDim.x = 1;
+                kattr[na].val.clusterDim.y = 1;
+                kattr[na].val.clusterDim.z = (unsigned)ks;
+                na++;
+            }
+            cudaLaunchConfig_t kc{};
+            kc.gridDim = dim3((unsigned)mtiles, (unsigned)nsub, (unsigned)ks);
+            kc.blockDim = dim3(kThreadsDeep);
+            kc.dynamicSmemBytes = smemK;
+            kc.stream = stream;
+            kc.attrs = kattr;
+            kc.numAttrs = (unsigned)na;
+            if (k.inNorm) FYN_CUDA(cudaLaunchKernelEx(&kc, k_conv_deep_tc_sk<true>, k));
+            else FYN_CUDA(cudaLaunchKernelEx(&kc, k_conv_deep_tc_sk<false>, k));
+            op->lastKernel = 13 | (ks << 8) | (NTs << 16);
+            FYN_CHECK_LAUNCH(op->ctx);
+            return FYN_OK;
+        }
+    }
     int ntiles = plan->ntiles;
     size_t planSmem = plan->smemBytes;
     if (plan->wideOff && mtiles * plan->ntiles >= 2ll * op->ctx->prop.multiProcessorCount) {
@@ -1097,11 +1422,8 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    static const bool noPdl = getenv("FYN_TC_NO_PDL") != nullptr;   // debugging aid: plain stream-ordered launches
     // Large grids: the persistent kernel (one CTA per SM, gathers / MMAs / epilogues of neighbouring tiles overlapped).
     // FYN_DEEP_PERSIST=0 keeps the one-tile-per-CTA kernel (read per run: tests compare the two).
-    const char *pe = getenv("FYN_DEEP_PERSIST");
-    const int sms = op->ctx->prop.multiProcessorCount;
     const char *he = getenv("FYN_DEEP_HALO");          // 0: every layer on the stage-per-tap kernels (read per run)
     // 3x3 stride-1 layers take the halo-tile kernel on ANY grid: on small ones (batch 1) a CTA's chain of K stages is what
     // the layer takes, and one gather per 64 channels instead of nine shortens it ninefold
@@ -1158,6 +1480,7 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
                 if (actT == 0) FYN_CUDA(cudaLaunchKernelEx(&hc, k_conv_deep_tc_h3<0>, h));
                 else if (actT == 1) FYN_CUDA(cudaLaunchKernelEx(&hc, k_conv_deep_tc_h3<1>, h));
                 else FYN_CUDA(cudaLaunchKernelEx(&hc, k_conv_deep_tc_h3<2>, h));
+                op->lastKernel = 12;
                 FYN_CHECK_LAUNCH(op->ctx);
                 return FYN_OK;
             }
@@ -1215,6 +1538,7 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
                 else if (actT == 1) FYN_CUDA(cudaLaunchKernelEx(&pc, k_conv_deep_tc_p<false, 1>, a));
                 else FYN_CUDA(cudaLaunchKernelEx(&pc, k_conv_deep_tc_p<false, 2>, a));
             }
+            op->lastKernel = 11;
             FYN_CHECK_LAUNCH(op->ctx);
             return FYN_OK;
         }
@@ -1241,6 +1565,7 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     cfg.numAttrs = noPdl ? 0 : 1;
     if (a.inNorm) FYN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_deep_tc<true>, a));
     else FYN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_deep_tc<false>, a));
+    op->lastKernel = 10;
     FYN_CHECK_LAUNCH(op->ctx);
     return FYN_OK;
 }

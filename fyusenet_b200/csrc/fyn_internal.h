@@ -99,6 +99,7 @@ struct fyn_op {
     float *d_bias = nullptr;   // [nOut*4] folded bias
     float *d_scale = nullptr;  // [nOut*4] BN scale (1 without post-BN)
     int backend = 0;           // 1 direct, 2 tcgen05
+    int lastKernel = 0;        // fyn_conv2d_last_kernel
     int epilogue = 0;          // FYN_EPILOGUE_*: element-wise function fused behind the convolution
     float *d_innorm = nullptr; // fused input batch-norm: scale[Cin4], bias[Cin4] (fyn_conv2d_set_input_norm)
     int innorm = 0;

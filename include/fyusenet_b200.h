@@ -248,6 +248,10 @@ int fyn_conv2d_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *residual,
 int fyn_conv2d_set_input_norm(fyn_op *op, const float *scale_bias);
 /* which kernel family the op resolved to: 1 = direct, 2 = tcgen05 */
 int fyn_conv2d_backend(const fyn_op *op);
+/* which kernel the op's LAST run launched (diagnostics / tests; 0 = not run yet): 1 = direct (CUDA cores), 2 = tcgen05 shallow
+ * row-ring kernel, 10 = deep one-tile-per-CTA, 11 = deep persistent, 12 = deep halo-tile 3x3,
+ * 13 | cluster size << 8 | columns per CTA << 16 = deep split-K cluster kernel (small grids) */
+int fyn_conv2d_last_kernel(const fyn_op *op);
 /* Fuses the element-wise FunctionLayer that consumes this convolution into its epilogue (engine-level layer
  * fusion; the reference runs it as its own render pass, fyusenet/gpu/functionlayer.cpp:145-179).  `function`:
  * FYN_EPILOGUE_NONE or FYN_EPILOGUE_SIGMOID (fyusenet/gpu/sigmoidlayer.cpp:77-112, shaders/sigmoid.frag:10-17).

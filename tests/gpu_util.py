@@ -5,6 +5,7 @@ import fyn_oracle as fo
 from fyusenet_b200 import capi
 
 _ctx = None
+LAST_KERNEL = 0   # fyn_conv2d_last_kernel of the most recent conv_gpu call
 
 
 def ctx():
@@ -68,6 +69,8 @@ def conv_gpu(x, wb, *, out_channels, kernel, dtype=capi.F16, downsample=1, dilat
     y = tout.read_chw()
     raw = tout.download()
     be = op.backend
+    global LAST_KERNEL
+    LAST_KERNEL = op.last_kernel
     for t in (tin, tout, tres):
         if t is not None:
             t.destroy()

@@ -11,6 +11,7 @@ import pytest
 
 import fyn_oracle as fo
 from fyusenet_b200 import capi
+import gpu_util
 from gpu_util import assert_close_f16, conv_gpu, ctx, half, random_wb, rel_l2
 
 pytestmark = pytest.mark.gpu
@@ -275,6 +276,59 @@ def test_deep_conv_persistent_kernel_is_bit_identical(k, ds, ci, co, inp, outp, 
             y = conv_gpu(x, wb, **kw).reshape(outs[0].shape)
             assert_close_f16(y.reshape((batch,) + ref.shape[1:])[:ref.shape[0]], ref, None, ulps=1.01, extra_abs=1e-4 * max(1.0, float(np.abs(ref).max()) / 8))
             assert rel_l2(y, outs[0]) <= 2e-4
+
+
+SPLITK_CASES = [  # k, ds, ci, co, inp, outp, postbn, res, relures, bnres, size, batch -- ResNet-50's layers at batch 1 ... 3
+    (1, 1, 2048, 512, 0, 1, True, False, False, False, 7, 1),     # deepest reduction: 32 K stages over a cluster of 8, 32-column tiles
+    (1, 1, 512, 2048, 0, 0, True, True, True, False, 7, 1),       # expansion + residual: cluster of 4
+    (3, 1, 512, 512, 1, 0, True, False, False, False, 7, 1),      # 72 stages: nine per CTA, the ring wraps
+    (1, 1, 1024, 256, 0, 1, True, False, False, False, 14, 1),    # two pixel tiles, the second partly empty
+    (3, 1, 256, 256, 1, 0, True, False, False, False, 14, 1),     # 36 stages: uneven K slices (4 / 5 per CTA)
+    (1, 2, 1024, 2048, 0, 0, False, False, False, False, 14, 1),  # projection shortcut, stride 2
+    (1, 1, 2048, 1000, 0, 0, False, False, False, False, 1, 3),   # GEMM72: ragged last sub-tile (1000 = 15 x 64 + 40)
+    (1, 1, 64, 64, 0, 1, True, False, False, False, 56, 1),       # single stage: no cluster, reduction buffer only
+    (1, 1, 64, 256, 0, 0, True, True, True, False, 56, 1),        # single stage + residual
+    (1, 1, 256, 64, 0, 1, True, False, False, False, 56, 1),      # one stage per CTA of a cluster of 4
+    (3, 1, 128, 128, 1, 1, True, True, True, True, 28, 1),        # BN on the residual
+    (1, 1, 128, 80, 0, 0, False, False, False, False, 9, 2),      # 80 outputs: the operand image's tile is not a multiple of 64
+    (1, 1, 192, 24, 0, 0, False, True, False, False, 5, 3),       # three stages, 24 outputs (32-column TMEM tile, six planes)
+]
+
+
+@pytest.mark.parametrize("k,ds,ci,co,inp,outp,postbn,res,relures,bnres,size,batch", SPLITK_CASES)
+def test_deep_conv_splitk_cluster_kernel(k, ds, ci, co, inp, outp, postbn, res, relures, bnres, size, batch, monkeypatch):
+    """Small grids run k_conv_deep_tc_sk: the K stages of an output tile split over a thread-block cluster, partial tiles
+    reduce-scattered through distributed shared memory, tiles narrowed to <= 64 columns.  Same operands as the one-tile kernel,
+    K slices summed separately: checked against the oracle (1 fp16 ulp + summation noise) and against the one-tile kernel
+    (FYN_DEEP_SPLITK=0), for the default plan and for forced tile widths / cluster sizes."""
+    rng = np.random.default_rng(k * 100 + ci + co + size)
+    x = half(rng.normal(size=(batch, ci, size, size)).astype(np.float32))
+    wb = random_wb(rng, ci, co, k, post_bn=postbn)
+    so = size // ds
+    residual = half(rng.normal(size=(batch, co, so, so)).astype(np.float32)) if res else None
+    fl = capi.FLAG_PRE_RELU | (capi.FLAG_POST_BATCHNORM if postbn else 0) | (capi.FLAG_RELU_ON_RESIDUAL if relures else 0) | \
+         (capi.FLAG_BATCHNORM_ON_RESIDUAL if bnres else 0)
+    kw = dict(out_channels=co, kernel=k, downsample=ds, in_pad=inp, out_pad=outp, flags=fl, residual=residual, deep=True, backend=capi.BACKEND_TC)
+    ofl = (fo.POST_BATCHNORM if postbn else 0) | (fo.RELU_ON_RESIDUAL if relures else 0) | (fo.BATCHNORM_ON_RESIDUAL if bnres else 0)
+    ref = np.stack([fo.conv2d(x[i], wb, co, k, downsample=ds, in_pad=inp, out_pad=outp, act=fo.ACT_RELU, flags=ofl, deep=True,
+                              residual=None if residual is None else residual[i], prec=fo.FP16_STORE) for i in range(batch)])
+    monkeypatch.setenv("FYN_DEEP_SPLITK", "0")
+    monkeypatch.setenv("FYN_DEEP_HALO", "0")
+    base = conv_gpu(x, wb, **kw)
+    assert gpu_util.LAST_KERNEL == 10
+    monkeypatch.setenv("FYN_DEEP_SPLITK", "2")
+    for nt, split in ((None, None), ("64", "2"), ("32", "8"), ("16", "3"), ("64", "1")):
+        for name, v in (("FYN_DEEP_SK_NT", nt), ("FYN_DEEP_SK_SPLIT", split)):
+            if v is None:
+                monkeypatch.delenv(name, raising=False)
+            else:
+                monkeypatch.setenv(name, v)
+        y = conv_gpu(x, wb, **kw)
+        assert gpu_util.LAST_KERNEL & 255 == 13, "the split-K cluster kernel must have run"
+        if split is not None:
+            assert (gpu_util.LAST_KERNEL >> 8) & 255 == min(int(split), k * k * (ci // 64))
+        assert_close_f16(y.reshape(ref.shape), ref, None, ulps=1.01, extra_abs=1e-4 * max(1.0, float(np.abs(ref).max()) / 8))
+        assert rel_l2(y, base) <= 2e-4
 
 
 def test_deep_conv_fused_input_batchnorm():
