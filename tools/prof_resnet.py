@@ -25,7 +25,9 @@ def main():
     net.input_buffer()[:] = np.random.default_rng(1).random(batch * 224 * 224 * 3, dtype=np.float32)
     net.forward()
     net.skip_io(True)
-    for _ in range(2):
+    if os.environ.get("FYN_PROF_GRAPH"):
+        net.enable_graph(True)
+    for _ in range(4):
         net.forward()
     net.finish()
     e0, e1 = ctx.event_create(), ctx.event_create()
@@ -35,7 +37,7 @@ def main():
     ctx.event_record(e1, net.stream)
     ctx.event_sync(e1)
     ms = ctx.elapsed_ms(e0, e1) / reps
-    out = {"batch": batch, "ms": round(ms, 3), "img_per_s": round(batch / ms * 1e3, 1), "persist": os.environ.get("FYN_DEEP_PERSIST", "default")}
+    out = {"batch": batch, "ms": round(ms, 3), "img_per_s": round(batch / ms * 1e3, 1), "persist": os.environ.get("FYN_DEEP_PERSIST", "default"), "graph": net.graph_active}
     if len(sys.argv) > 3:
         net.enable_timings(True)
         for _ in range(2):
