@@ -587,9 +587,18 @@ __global__ void __launch_bounds__(kThreadsDeep, 1) k_conv_deep_tc_sk(const __gri
         }
         SK_STAMP(5);
         // ===================== epilogue of this CTA's planes: partials summed in rank order =====================
-        int g = 0;
+        // (the residual texels run four planes ahead of their use: rqPre rotates)
 #pragma unroll 1
-        for (int lp = set; lp < ppr; lp += a.nsets, g++) {
+        for (int lp = set; lp < ppr; lp += a.nsets) {
+            const uint2 raw = rqPre[0];
+            rqPre[0] = rqPre[1];
+            rqPre[1] = rqPre[2];
+            rqPre[2] = rqPre[3];
+            {
+                const int ln = lp + kPre * a.nsets;
+                const bool ok = a.hasRes && valid && ln < ppr && rank * ppr + ln < (NTs >> 2) && plane0 + ln < nOutPlanes;
+                rqPre[3] = ok ? __ldg(reinterpret_cast<const uint2 *>(resp + resOrigin[ok ? ln : 0])) : make_uint2(0u, 0u);
+            }
             if (!valid || rank * ppr + lp >= (NTs >> 2) || plane0 + lp >= nOutPlanes) continue;
             float4 acc = red[(size_t)lp * kM + t];
             for (int r = 1; r < ks; r++) {
@@ -602,7 +611,6 @@ __global__ void __launch_bounds__(kThreadsDeep, 1) k_conv_deep_tc_sk(const __gri
             const float4 sc = sScale[lp], bi = sBias[lp];
             float4 r = make_float4(fmaf(acc.x, sc.x, bi.x), fmaf(acc.y, sc.y, bi.y), fmaf(acc.z, sc.z, bi.z), fmaf(acc.w, sc.w, bi.w));
             if (a.hasRes) {
-                const uint2 raw = g == 0 ? rqPre[0] : (g == 1 ? rqPre[1] : (g == 2 ? rqPre[2] : (g == 3 ? rqPre[3] : __ldg(reinterpret_cast<const uint2 *>(resp + resOrigin[lp])))));
                 const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
                 const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
                 float4 q = make_float4(f0.x, f0.y, f1.x, f1.y);
