@@ -64,65 +64,49 @@ __global__ void __launch_bounds__(128) k_pool(const PoolArgs a) {
     fyn_store_texel(a.out, n, t, a.outP + xo, a.outP + yo, r);
 }
 
-// fp16 RGBA tensors, windows up to 3x3: a block stages the input rows of a strip of output rows of ONE tile / plane in shared
-// memory with consecutive lanes on consecutive texels (every texel crosses L2 -> SM once, whole 32-byte sectors), then
-// computes the strip from shared memory.  k_pool above fetches the window per output texel: with stride 2 every load
-// instruction uses half of each sector and a texel is requested ~2.25 times (measured on ResNet-50's MaxPool4 at batch 128:
-// 151 us = 27 % of the copy bandwidth; this kernel: see profiles/r02_bandwidth_layers.md).
+// The strip of output rows [yo0, yo0 + ro) of one tile / plane from its staged window (NCs texels per staged row; a row may carry
+// one leading texel: parity o0 + row * tw1, see k_pool_rows)
 template <int PX, int PY>
-__global__ void __launch_bounds__(256) k_pool_rows(const PoolArgs a, int RO, int NC) {
-    extern __shared__ uint2 sPool[];
-    const int strips = (a.Ho + RO - 1) / RO;
-    unsigned bid = blockIdx.x;
-    const int strip = bid % strips;
-    bid /= strips;
-    const int t = bid % a.tiles, n = bid / a.tiles;
-    const int yo0 = strip * RO, ro = min(RO, a.Ho - yo0);
-    const int NR = a.dy * (ro - 1) + PY;
-    const int bx0 = a.in.P + a.off + (a.in.deep ? (t % a.in.tx) * a.in.tileW : 0);
-    const int by0 = a.in.P + a.dy * yo0 + a.off + (a.in.deep ? (t / a.in.tx) * a.in.tileH : 0);
-    const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems + (a.in.deep ? 0ll : (long long)t * a.in.planeElems);
-    // staging: consecutive threads on consecutive texels of the staged window, eight loads in flight per thread (with one load
-    // per thread and iteration the SMs held ~14 KB in flight and the kernel waited on the long scoreboard)
-    const unsigned total = (unsigned)(NR * NC), magicNC = (unsigned)((1ull << 32) / (unsigned)NC) + 1u;   // total * NC < 2^32
-    for (unsigned base = threadIdx.x; base < total; base += 256u * 8u) {
-        uint2 raw[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const unsigned idx = base + u * 256u;
-            if (idx < total) {
-                const unsigned r = __umulhi(idx, magicNC), c = idx - r * (unsigned)NC;
-                const int Y = min(max(by0 + (int)r, 0), a.in.texH - 1), X = min(max(bx0 + (int)c, 0), a.in.texW - 1);
-                raw[u] = __ldg(reinterpret_cast<const uint2 *>(src + ((long long)Y * a.in.texW + X) * 4));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const unsigned idx = base + u * 256u;
-            if (idx < total) sPool[idx] = raw[u];
-        }
-    }
-    __syncthreads();
-    __half *dst = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + (a.out.deep ? 0ll : (long long)t * a.out.planeElems);
-    const int ox0 = a.outP + (a.out.deep ? (t % a.out.tx) * a.out.tileW : 0), oy0 = a.outP + (a.out.deep ? (t / a.out.tx) * a.out.tileH : 0);
+__device__ __forceinline__ void pool_strip_compute(const PoolArgs &a, const uint2 *sPool, int NCs, int o0, int tw1, int ro, int yo0, __half *dst, int ox0, int oy0) {
     // Max pooling with ReLU / no prefix activation stays in fp16: the maximum of fp16 values is exact, and
     // max_i relu(x_i) = max(max_i x_i, 0) -- also with the reference's un-activated third column (deepmaxpool.frag:12-61), since
     // at least one column is activated.  Four packed min/max instructions per tap instead of a dozen fp32 ones: the kernel was
     // issue-bound (ncu: issue active 53 %, 430 instructions per output texel).
     if (a.isMax && a.act.type <= 1) {
+        // (the kernel is issue-bound -- 120 instructions per output texel with one 8-byte load per tap and a division per texel:
+        // 16-byte loads where two taps share an aligned pair, the (row, column) walk by increments)
         const __half2 floor2 = a.act.type == 1 ? __float2half2_rn(0.f) : __half2half2(__ushort_as_half((unsigned short)0xfc00));
-        for (int o = threadIdx.x; o < ro * a.Wo; o += 256) {
-            const int yl = o / a.Wo, xo = o - yl * a.Wo;
-            const uint2 *w = sPool + (a.dy * yl) * NC + a.dx * xo;
+        const int stepY = 256 / a.Wo, stepX = 256 - stepY * a.Wo;
+        int yl = (int)threadIdx.x / a.Wo, xo = (int)threadIdx.x - yl * a.Wo;
+        for (; yl < ro; yl += stepY, xo += stepX) {
+            if (xo >= a.Wo) {
+                xo -= a.Wo;
+                if (++yl >= ro) break;
+            }
+            const uint2 *w = sPool + (a.dy * yl) * NCs + a.dx * xo;
             __half2 m0 = floor2, m1 = floor2;
 #pragma unroll
-            for (int j = 0; j < PY; j++)
-#pragma unroll
-                for (int i = 0; i < PX; i++) {
-                    const uint2 raw = w[j * NC + i];
-                    m0 = __hmax2(m0, *reinterpret_cast<const __half2 *>(&raw.x));
-                    m1 = __hmax2(m1, *reinterpret_cast<const __half2 *>(&raw.y));
+            for (int j = 0; j < PY; j++) {
+                const uint2 *p = w + j * NCs + ((o0 + (a.dy * yl + j) * tw1) & 1);
+                const bool even = (reinterpret_cast<uintptr_t>(p) & 8) == 0;
+                uint2 t0, t1, t2 = make_uint2(0xfc00fc00u, 0xfc00fc00u);      // (-inf, -inf): neutral for a 2-wide window
+                if (even) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(p);
+                    t0 = make_uint2(q.x, q.y);
+                    t1 = make_uint2(q.z, q.w);
+                    if (PX == 3) t2 = p[2];
+                } else if (PX == 3) {
+                    t0 = p[0];
+                    const uint4 q = *reinterpret_cast<const uint4 *>(p + 1);
+                    t1 = make_uint2(q.x, q.y);
+                    t2 = make_uint2(q.z, q.w);
+                } else {
+                    t0 = p[0];
+                    t1 = p[1];
                 }
+                m0 = __hmax2(m0, __hmax2(__hmax2(*reinterpret_cast<const __half2 *>(&t0.x), *reinterpret_cast<const __half2 *>(&t1.x)), *reinterpret_cast<const __half2 *>(&t2.x)));
+                m1 = __hmax2(m1, __hmax2(__hmax2(*reinterpret_cast<const __half2 *>(&t0.y), *reinterpret_cast<const __half2 *>(&t1.y)), *reinterpret_cast<const __half2 *>(&t2.y)));
+            }
             uint2 q;
             q.x = *reinterpret_cast<const unsigned *>(&m0);
             q.y = *reinterpret_cast<const unsigned *>(&m1);
@@ -137,7 +121,7 @@ __global__ void __launch_bounds__(256) k_pool_rows(const PoolArgs a, int RO, int
         for (int j = 0; j < PY; j++)
 #pragma unroll
             for (int i = 0; i < PX; i++) {
-                const uint2 raw = sPool[(a.dy * yl + j) * NC + a.dx * xo + i];
+                const uint2 raw = sPool[(a.dy * yl + j) * NCs + a.dx * xo + i + ((o0 + (a.dy * yl + j) * tw1) & 1)];
                 const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
                 float4 v = make_float4(f0.x, f0.y, f1.x, f1.y);
                 if (!(a.quirk3 && i == 2)) v = fyn_act4(v, a.act);
@@ -159,6 +143,200 @@ __global__ void __launch_bounds__(256) k_pool_rows(const PoolArgs a, int RO, int
         q.x = *reinterpret_cast<const unsigned *>(&h0);
         q.y = *reinterpret_cast<const unsigned *>(&h1);
         *reinterpret_cast<uint2 *>(dst + ((long long)(oy0 + yo0 + yl) * a.out.texW + ox0 + xo) * 4) = q;
+    }
+}
+
+// fp16 RGBA tensors, windows up to 3x3: a block stages the input rows of a strip of output rows of ONE tile / plane in shared
+// memory with consecutive lanes on consecutive texels (every texel crosses L2 -> SM once, whole 32-byte sectors), then
+// computes the strip from shared memory.  k_pool above fetches the window per output texel: with stride 2 every load
+// instruction uses half of each sector and a texel is requested ~2.25 times (measured on ResNet-50's MaxPool4 at batch 128:
+// 151 us = 27 % of the copy bandwidth; this kernel: see profiles/r02_bandwidth_layers.md).
+template <int PX, int PY>
+__global__ void __launch_bounds__(256) k_pool_rows(const PoolArgs a, int RO, int NC, int bulk) {
+    extern __shared__ uint2 sPool[];
+    const int strips = (a.Ho + RO - 1) / RO;
+    unsigned bid = blockIdx.x;
+    const int strip = bid % strips;
+    bid /= strips;
+    const int t = bid % a.tiles, n = bid / a.tiles;
+    const int yo0 = strip * RO, ro = min(RO, a.Ho - yo0);
+    const int NR = a.dy * (ro - 1) + PY, RO_NRmax = a.dy * (RO - 1) + PY;
+    const int bx0 = a.in.P + a.off + (a.in.deep ? (t % a.in.tx) * a.in.tileW : 0);
+    const int by0 = a.in.P + a.dy * yo0 + a.off + (a.in.deep ? (t / a.in.tx) * a.in.tileH : 0);
+    const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems + (a.in.deep ? 0ll : (long long)t * a.in.planeElems);
+    // Staging.  Windows that lie inside the texture travel as BULK COPIES (cp.async.bulk, one per window row, completion on an
+    // mbarrier): no registers or load/store-unit slots are spent on the global latency and a block has its whole window in
+    // flight at once (the register-staged loop below: 16 KB per block and iteration, 48 % of the copy bandwidth on ResNet-50's
+    // MaxPool4).  A row starts on an even texel (16-byte alignment of source and size), so a staged row may carry one leading
+    // texel: `o0` / `tw1` give the parity of a row's first texel.  Windows that touch the texture edge (clamping) keep the loop.
+    const int NCs = bulk ? ((NC + 2) & ~1) : NC;
+    const long long e0 = (long long)by0 * a.in.texW + bx0;       // first texel of the window inside the image
+    const bool inside = bulk && bx0 >= 0 && by0 >= 0 && bx0 + NC <= a.in.texW && by0 + NR <= a.in.texH &&
+                        e0 + (long long)(NR - 1) * a.in.texW + NCs <= (long long)a.in.texW * a.in.texH;
+    const int o0 = inside ? (int)(e0 & 1) : 0, tw1 = inside ? (a.in.texW & 1) : 0;
+    if (inside) {
+        uint64_t *bar = reinterpret_cast<uint64_t *>(sPool + (size_t)RO_NRmax * NCs);
+        const uint32_t barAddr = (uint32_t)__cvta_generic_to_shared(bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barAddr), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"((uint32_t)(NR * NCs * 8)) : "memory");
+        }
+        __syncthreads();
+        for (int r = threadIdx.x; r < NR; r += 256) {
+            const long long e = (e0 + (long long)r * a.in.texW) & ~1ll;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(sPool + (size_t)r * NCs)),
+                         "l"(src + e * 4), "r"((uint32_t)(NCs * 8)), "r"(barAddr)
+                         : "memory");
+        }
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "PWAIT_LOOP:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+            "@P1 bra PWAIT_DONE;\n\t"
+            "bra PWAIT_LOOP;\n\t"
+            "PWAIT_DONE:\n\t"
+            "}" ::"r"(barAddr), "r"(0u), "r"(0x989680u)
+            : "memory");
+    } else {
+        // consecutive threads on consecutive texels of the staged window, eight loads in flight per thread (with one load
+        // per thread and iteration the SMs held ~14 KB in flight and the kernel waited on the long scoreboard)
+        const unsigned total = (unsigned)(NR * NC), magicNC = (unsigned)((1ull << 32) / (unsigned)NC) + 1u;   // total * NC < 2^32
+        for (unsigned base = threadIdx.x; base < total; base += 256u * 8u) {
+            uint2 raw[8];
+            unsigned sidx[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const unsigned idx = base + u * 256u;
+                if (idx < total) {
+                    const unsigned r = __umulhi(idx, magicNC), c = idx - r * (unsigned)NC;
+                    const int Y = min(max(by0 + (int)r, 0), a.in.texH - 1), X = min(max(bx0 + (int)c, 0), a.in.texW - 1);
+                    raw[u] = __ldg(reinterpret_cast<const uint2 *>(src + ((long long)Y * a.in.texW + X) * 4));
+                    sidx[u] = r * (unsigned)NCs + c;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const unsigned idx = base + u * 256u;
+                if (idx < total) sPool[sidx[u]] = raw[u];
+            }
+        }
+        __syncthreads();
+    }
+    __half *dst = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + (a.out.deep ? 0ll : (long long)t * a.out.planeElems);
+    const int ox0 = a.outP + (a.out.deep ? (t % a.out.tx) * a.out.tileW : 0), oy0 = a.outP + (a.out.deep ? (t / a.out.tx) * a.out.tileH : 0);
+    pool_strip_compute<PX, PY>(a, sPool, NCs, o0, tw1, ro, yo0, dst, ox0, oy0);
+}
+
+// Persistent version of k_pool_rows for large grids whose windows all lie inside the texture.  A window is the FULL WIDTH of the
+// texture -- the rows of a strip of one row of tiles (deep) or of one plane (shallow) are contiguous in memory, so a window is
+// ONE bulk copy (cp.async.bulk; per-tile windows are 0.9 KB rows, and the copy engine spent ~70 ns on each: 55 % of the copy
+// bandwidth on ResNet-50's MaxPool4) -- and a block walks its windows through a RING of three: two in flight while the third is
+// computed (with one window per block the load and compute phases of the blocks of an SM ran in step and HBM idled during
+// the compute phase; a B200 wants > 100 KB in flight per SM all the time).  A window starts on a 16-byte boundary, i.e. it
+// may carry one leading texel (`lead`).
+template <int PX, int PY>
+__global__ void __launch_bounds__(256) k_pool_rows_ring(const PoolArgs a, int RO, unsigned total) {
+    extern __shared__ uint2 sPool[];
+    const int texW = a.in.texW, NRmax = a.dy * (RO - 1) + PY;
+    const size_t bufTexels = ((size_t)NRmax * texW + 3) & ~(size_t)1;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sPool + 3 * bufTexels);
+    const int strips = (a.Ho + RO - 1) / RO;
+    const int rowsOfTiles = a.in.deep ? a.in.tileRows : a.tiles, tcols = a.in.deep ? a.in.tx : 1;
+    // (x / d through a multiplication: exact for the few thousand outputs of a window)
+    const unsigned magicRow = (unsigned)((1ull << 32) / (unsigned)(tcols * a.Wo)) + 1u, magicWo = (unsigned)((1ull << 32) / (unsigned)a.Wo) + 1u;
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 3; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar + b)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    struct Item {
+        int trow, n, yo0, ro, NR;
+        long long e0;           // first texel of the window, relative to the tensor
+    };
+    auto decode = [&](unsigned item) {
+        Item it;
+        const int strip = (int)(item % (unsigned)strips);
+        item /= (unsigned)strips;
+        it.trow = (int)(item % (unsigned)rowsOfTiles);
+        it.n = (int)(item / (unsigned)rowsOfTiles);
+        it.yo0 = strip * RO;
+        it.ro = min(RO, a.Ho - it.yo0);
+        it.NR = a.dy * (it.ro - 1) + PY;
+        const int by0 = a.in.P + a.dy * it.yo0 + a.off + (a.in.deep ? it.trow * a.in.tileH : 0);
+        it.e0 = ((long long)it.n * a.in.imageElems + (a.in.deep ? 0ll : (long long)it.trow * a.in.planeElems)) / 4 + (long long)by0 * texW;
+        return it;
+    };
+    auto issue = [&](unsigned item, int b) {
+        if (threadIdx.x != 0) return;
+        const Item it = decode(item);
+        const long long e = it.e0 & ~1ll;
+        const uint32_t bytes = (uint32_t)((((it.e0 - e) + (long long)it.NR * texW) * 8 + 15) & ~15ll);
+        const uint32_t barAddr = (uint32_t)__cvta_generic_to_shared(bar + b);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(sPool + (size_t)b * bufTexels)),
+                     "l"(reinterpret_cast<const __half *>(a.in.ptr) + e * 4), "r"(bytes), "r"(barAddr)
+                     : "memory");
+    };
+    const unsigned G = gridDim.x;
+    if (blockIdx.x < total) issue(blockIdx.x, 0);
+    if (blockIdx.x + G < total) issue(blockIdx.x + G, 1);
+    int k = 0;
+    for (unsigned item = blockIdx.x; item < total; item += G, k++) {
+        const int b = k % 3;
+        __syncthreads();                               // everybody is through with window k - 1: its buffer takes window k + 2
+        if (item + 2 * G < total) issue(item + 2 * G, (k + 2) % 3);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "RWAIT_LOOP:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+            "@P1 bra RWAIT_DONE;\n\t"
+            "bra RWAIT_LOOP;\n\t"
+            "RWAIT_DONE:\n\t"
+            "}" ::"r"((uint32_t)__cvta_generic_to_shared(bar + b)), "r"((uint32_t)((k / 3) & 1)), "r"(0x989680u)
+            : "memory");
+        const Item it = decode(item);
+        const uint2 *win = sPool + (size_t)b * bufTexels + (int)(it.e0 & 1);     // texel (row r, texture column X) = win[r * texW + X]
+        if (a.isMax && a.act.type <= 1) {
+            // the outputs of all tiles of the window as one index space (row, tile column, column): the kernel is issue-bound, and
+            // a call per tile spent more instructions on its set-up than on its 224 outputs.  Output tiles sit in the same grid as
+            // input tiles (same channel count; checked by the launcher).
+            const __half2 floor2 = a.act.type == 1 ? __float2half2_rn(0.f) : __half2half2(__ushort_as_half((unsigned short)0xfc00));
+            const unsigned rowOuts = (unsigned)(tcols * a.Wo), nOut = (unsigned)it.ro * rowOuts;
+            __half *dst = reinterpret_cast<__half *>(a.out.ptr) + (long long)it.n * a.out.imageElems + (a.out.deep ? 0ll : (long long)it.trow * a.out.planeElems) +
+                          ((long long)(a.outP + (a.out.deep ? it.trow * a.out.tileH : 0) + it.yo0) * a.out.texW + a.outP) * 4;
+            const uint2 *w0 = win + a.in.P + a.off;
+            for (unsigned o = threadIdx.x; o < nOut; o += 256u) {
+                const unsigned yl = __umulhi(o, magicRow), c = o - yl * rowOuts;
+                const unsigned tc = __umulhi(c, magicWo), xo = c - tc * (unsigned)a.Wo;
+                if (a.in.deep && it.trow * a.in.tx + (int)tc >= a.tiles) continue;
+                const uint2 *p = w0 + (a.dy * yl) * texW + tc * a.in.tileW + a.dx * xo;
+                __half2 m0 = floor2, m1 = floor2;
+#pragma unroll
+                for (int j = 0; j < PY; j++) {
+                    const uint2 t0 = p[j * texW], t1 = p[j * texW + 1], t2 = PX == 3 ? p[j * texW + 2] : t1;
+                    m0 = __hmax2(m0, __hmax2(__hmax2(*reinterpret_cast<const __half2 *>(&t0.x), *reinterpret_cast<const __half2 *>(&t1.x)), *reinterpret_cast<const __half2 *>(&t2.x)));
+                    m1 = __hmax2(m1, __hmax2(__hmax2(*reinterpret_cast<const __half2 *>(&t0.y), *reinterpret_cast<const __half2 *>(&t1.y)), *reinterpret_cast<const __half2 *>(&t2.y)));
+                }
+                uint2 q;
+                q.x = *reinterpret_cast<const unsigned *>(&m0);
+                q.y = *reinterpret_cast<const unsigned *>(&m1);
+                *reinterpret_cast<uint2 *>(dst + ((long long)yl * a.out.texW + tc * a.out.tileW + xo) * 4) = q;
+            }
+            continue;
+        }
+        // the tiles of this row of tiles, one after the other (tile-uniform addressing, as in k_pool_rows)
+        for (int tc = 0; tc < tcols; tc++) {
+            const int t = a.in.deep ? it.trow * a.in.tx + tc : it.trow;
+            if (t >= a.tiles) break;
+            __half *dst = reinterpret_cast<__half *>(a.out.ptr) + (long long)it.n * a.out.imageElems + (a.out.deep ? 0ll : (long long)t * a.out.planeElems);
+            const int ox0 = a.outP + (a.out.deep ? (t % a.out.tx) * a.out.tileW : 0), oy0 = a.outP + (a.out.deep ? (t / a.out.tx) * a.out.tileH : 0);
+            pool_strip_compute<PX, PY>(a, win + a.in.P + a.off + tc * a.in.tileW, texW, 0, 0, it.ro, it.yo0, dst, ox0, oy0);
+        }
     }
 }
 
@@ -202,6 +380,62 @@ __global__ void __launch_bounds__(256) k_pool_global_deep(const PoolArgs a) {
         }
         if (!a.isMax) acc = make_float4(acc.x * a.inv, acc.y * a.inv, acc.z * a.inv, acc.w * a.inv);
         fyn_store_texel(a.out, n, t, a.outP, a.outP, acc);
+    }
+}
+
+// Windows of at most eight rows (ResNet-50's 7x7): a block owns R consecutive rows of tiles of one image and takes them two
+// at a time -- sixteen 8-byte loads in flight per thread, the column sums of both rows of tiles go to shared memory behind ONE
+// barrier (two buffers, alternating), then the per-tile reduction.  k_pool_global_deep above (one row of tiles per block, 12 KB
+// per block, 8192 short-lived blocks at batch 512) reached 35 % of the copy bandwidth.
+__global__ void __launch_bounds__(256) k_pool_global_deep8(const PoolArgs a, int R) {
+    extern __shared__ float4 sCol[];                       // [2 buffers][2 rows of tiles][texW]
+    const int groups = (a.in.tileRows + R - 1) / R;
+    const int grp = blockIdx.x % groups, n = blockIdx.x / groups;
+    const int W = a.in.W, H = a.in.H, P = a.in.P, texW = a.in.texW;
+    const int tr0 = grp * R, tr1 = min(tr0 + R, a.in.tileRows);
+    const __half *img = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems;
+    int buf = 0;
+    for (int tr = tr0; tr < tr1; tr += 2, buf ^= 1) {
+        float4 *col = sCol + (size_t)buf * 2 * texW;
+        for (int X = threadIdx.x; X < texW; X += 256) {
+            uint2 raw[2][8];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const __half *src = img + ((long long)(P + (tr + h) * a.in.tileH) * texW + X) * 4;
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    raw[h][u] = (tr + h < tr1 && u < H) ? __ldg(reinterpret_cast<const uint2 *>(src + (long long)u * texW * 4)) : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                float4 acc = a.isMax ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (u >= H) break;
+                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[h][u].x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[h][u].y));
+                    const float4 v = fyn_act4(make_float4(f0.x, f0.y, f1.x, f1.y), a.act);
+                    if (a.isMax) acc = make_float4(fmaxf(acc.x, v.x), fmaxf(acc.y, v.y), fmaxf(acc.z, v.z), fmaxf(acc.w, v.w));
+                    else acc = make_float4(acc.x + v.x, acc.y + v.y, acc.z + v.z, acc.w + v.w);
+                }
+                col[h * texW + X] = acc;
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * a.in.tx; i += 256) {
+            const int h = i / a.in.tx, tc = i - h * a.in.tx;
+            const int t = (tr + h) * a.in.tx + tc;
+            if (tr + h >= tr1 || t >= a.tiles) continue;
+            const float4 *c = col + h * texW + P + tc * a.in.tileW;
+            float4 acc = c[0];
+            for (int x = 1; x < W; x++) {
+                const float4 v = c[x];
+                if (a.isMax) acc = make_float4(fmaxf(acc.x, v.x), fmaxf(acc.y, v.y), fmaxf(acc.z, v.z), fmaxf(acc.w, v.w));
+                else acc = make_float4(acc.x + v.x, acc.y + v.y, acc.z + v.z, acc.w + v.w);
+            }
+            if (!a.isMax) acc = make_float4(acc.x * a.inv, acc.y * a.inv, acc.z * a.inv, acc.w * a.inv);
+            fyn_store_texel(a.out, n, t, a.outP, a.outP, acc);
+        }
+        // (the next pair of rows writes the other buffer; this one is rewritten two iterations later, behind the next barrier)
     }
 }
 
@@ -421,6 +655,67 @@ __global__ void __launch_bounds__(256) k_eltwise_h4(const EltArgs a, unsigned W,
     }
 }
 
+// Pair version of k_eltwise_h4 for tensors whose texel pairs are 16-byte aligned (even widths / paddings / tile pitches: every
+// padding-free deep tensor of ResNet-50): two texels per access, up to eight accesses in flight per thread, and the plane is cut
+// into EQUAL chunks (k_eltwise_h4 on a 56x56 plane ran one full and one half-empty block: 65 % of the copy bandwidth).
+__global__ void __launch_bounds__(256) k_eltwise_p8(const EltArgs a, unsigned Wp, unsigned HWp, unsigned chunks, unsigned len, unsigned magic) {
+    unsigned bid = blockIdx.x;
+    const unsigned chunk = bid % chunks;
+    bid /= chunks;
+    const unsigned t = bid % (unsigned)a.tiles, n = bid / (unsigned)a.tiles;
+    long long ib = (long long)n * a.in.imageElems, ob = (long long)n * a.out.imageElems;
+    unsigned ix0 = a.in.P, iy0 = a.in.P, ox0 = a.outP, oy0 = a.outP;
+    if (a.in.deep) {
+        ix0 += (t % a.in.tx) * a.in.tileW;
+        iy0 += (t / a.in.tx) * a.in.tileH;
+    } else {
+        ib += (long long)t * a.in.planeElems;
+    }
+    if (a.out.deep) {
+        ox0 += (t % a.out.tx) * a.out.tileW;
+        oy0 += (t / a.out.tx) * a.out.tileH;
+    } else {
+        ob += (long long)t * a.out.planeElems;
+    }
+    const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + ib + ((long long)iy0 * a.in.texW + ix0) * 4;
+    __half *dst = reinterpret_cast<__half *>(a.out.ptr) + ob + ((long long)oy0 * a.out.texW + ox0) * 4;
+    const unsigned lo = chunk * len, hi = min(lo + len, HWp);
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.mode == 0) {
+        sc = __ldg(a.scale + t);
+        bi = __ldg(a.bias + t);
+    }
+    uint4 raw[8];
+    unsigned oo[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const unsigned p = lo + u * 256u + threadIdx.x;
+        oo[u] = ~0u;
+        if (p < hi) {
+            const unsigned y = __umulhi(p, magic), x = p - y * Wp;
+            oo[u] = (y * a.out.texW + 2u * x) * 4;
+            raw[u] = __ldg(reinterpret_cast<const uint4 *>(src + (y * a.in.texW + 2u * x) * 4));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        if (oo[u] == ~0u) continue;
+        const unsigned w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+        unsigned o[4];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&w[2 * h])), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w[2 * h + 1]));
+            float4 v = fyn_act4(make_float4(f0.x, f0.y, f1.x, f1.y), a.act);
+            if (a.mode == 0) v = make_float4(fmaf(v.x, sc.x, bi.x), fmaf(v.y, sc.y, bi.y), fmaf(v.z, sc.z, bi.z), fmaf(v.w, sc.w, bi.w));
+            else v = make_float4(fyn_sigmoid(v.x), fyn_sigmoid(v.y), fyn_sigmoid(v.z), fyn_sigmoid(v.w));
+            const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+            o[2 * h] = *reinterpret_cast<const unsigned *>(&h0);
+            o[2 * h + 1] = *reinterpret_cast<const unsigned *>(&h1);
+        }
+        *reinterpret_cast<uint4 *>(dst + oo[u]) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // small planes (H*W <= 128, e.g. the 7x7 layers of ResNet-50): several planes per block, `sub` (a power of two >= H*W)
 // threads per plane, so that a block of 256 threads is not left four-fifths idle
 __global__ void __launch_bounds__(256) k_eltwise_h4_small(const EltArgs a, unsigned W, unsigned HW, unsigned sub, unsigned planes) {
@@ -481,6 +776,17 @@ static int launch_eltwise(fyn_ctx *ctx, const EltArgs &a, int W, int H, cudaStre
             while (sub < HW) sub <<= 1;
             const unsigned planes = (unsigned)a.tiles * (unsigned)a.batch, ppb = 256u / sub;
             k_eltwise_h4_small<<<(planes + ppb - 1) / ppb, 256, 0, stream>>>(a, (unsigned)W, HW, sub, planes);
+            return 0;
+        }
+        // texel pairs on 16-byte boundaries in both tensors: the pair kernel
+        auto pairAligned = [](const TView &v, int pad) {
+            if ((v.texW & 1) || (pad & 1) || (((uintptr_t)v.ptr) & 15) || (v.imageElems & 7)) return false;
+            return v.deep ? (v.tileW & 1) == 0 : (v.planeElems & 7) == 0;
+        };
+        if ((W & 1) == 0 && HW >= 512 && pairAligned(a.in, a.in.P) && pairAligned(a.out, a.outP) && (unsigned long long)HW * (unsigned)W < (1ull << 32)) {
+            const unsigned Wp = (unsigned)W / 2, HWp = HW / 2;
+            const unsigned chunks = (HWp + 2047u) / 2048u, len = (HWp + chunks - 1) / chunks;
+            k_eltwise_p8<<<chunks * (unsigned)a.tiles * (unsigned)a.batch, 256, 0, stream>>>(a, Wp, HWp, chunks, len, (unsigned)((1ull << 32) / Wp) + 1u);
             return 0;
         }
         const int U = HW > 1024 ? 8 : (HW > 512 ? 4 : (HW > 256 ? 2 : 1));
@@ -569,7 +875,15 @@ int fyn_pool2d_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stre
     static const bool noRows = getenv("FYN_POOL_SIMPLE") != nullptr;       // (measurement knob: the per-texel kernels)
     if (h4 && !noRows && d.global && deep && a.in.deep && a.out.deep && !a.quirk3 && a.px * a.py >= 16 && (size_t)a.in.texW * 16 <= 48 * 1024) {
         // (the order of the additions differs from k_pool_warp's; both are within the 1-ulp bound of the fp16-store oracle)
-        k_pool_global_deep<<<(unsigned)(a.in.tileRows * a.batch), 256, (size_t)a.in.texW * 16, (cudaStream_t)stream>>>(a);
+        if (a.in.H <= 8 && (size_t)a.in.texW * 64 <= 48 * 1024) {
+            // rows of tiles per block: enough blocks for every SM (eight resident blocks each), at most the whole image
+            int R = a.in.tileRows;
+            while (R > 2 && (long long)((a.in.tileRows + R - 1) / R) * a.batch < 8ll * op->ctx->prop.multiProcessorCount) R = (R + 1) / 2;
+            R = (R + 1) & ~1;
+            k_pool_global_deep8<<<(unsigned)(((a.in.tileRows + R - 1) / R) * a.batch), 256, (size_t)a.in.texW * 64, (cudaStream_t)stream>>>(a, R);
+        } else {
+            k_pool_global_deep<<<(unsigned)(a.in.tileRows * a.batch), 256, (size_t)a.in.texW * 16, (cudaStream_t)stream>>>(a);
+        }
         FYN_CHECK_LAUNCH(op->ctx);
         return FYN_OK;
     }
@@ -579,11 +893,44 @@ int fyn_pool2d_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stre
         RO = std::max(1, std::min(RO, a.Ho));
         // enough blocks for every SM: shorter strips on small grids
         while (RO > 2 && (long long)((a.Ho + RO - 1) / RO) * a.tiles * a.batch < 4ll * op->ctx->prop.multiProcessorCount) RO = (RO + 1) / 2;
-        const size_t smem = (size_t)(a.dy * (RO - 1) + a.py) * NC * 8;
+        // bulk-copy staging needs 16-byte aligned images (even texel counts) -- see k_pool_rows
+        const bool noBulk = getenv("FYN_POOL_NO_BULK") != nullptr;     // (measurement / test knobs, read per run)
+        const int bulk = (!noBulk && ((uintptr_t)a.in.ptr & 15) == 0 && (a.in.imageElems & 7) == 0 && (a.in.deep || (a.in.planeElems & 7) == 0)) ? 1 : 0;
+        const int NCs = bulk ? ((NC + 2) & ~1) : NC;
+        // large grids with every window inside the texture (no clamping, no read past the tensor): the persistent ring kernel
+        {
+            const int tcolMax = a.in.deep ? a.in.tx - 1 : 0, trowMax = a.in.deep ? (a.tiles - 1) / a.in.tx : 0;
+            const long long bx0min = a.in.P + a.off, bx0max = bx0min + (long long)tcolMax * a.in.tileW;
+            const long long by0min = a.in.P + a.off, byEnd = by0min + (long long)a.dy * (a.Ho - 1) + a.py + (long long)trowMax * a.in.tileH;   // one past the last window row
+            // strips of a few output rows: a window of the full texture width must fit a third of ~100 KB
+            int ROr = (int)((32 * 1024 / ((size_t)a.in.texW * 8) - a.py) / a.dy) + 1;
+            ROr = std::min(ROr, a.Ho);
+            const long long rowsOfTiles = a.in.deep ? a.in.tileRows : a.tiles;
+            const long long totalItems = ROr >= 1 ? (long long)((a.Ho + ROr - 1) / ROr) * rowsOfTiles * a.batch : 0;
+            const size_t ringSmem = ROr >= 1 ? (size_t)3 * ((((size_t)(a.dy * (ROr - 1) + a.py) * a.in.texW + 3) & ~(size_t)1) * 8) + 32 : 0;
+            const bool noRing = getenv("FYN_POOL_NO_RING") != nullptr;
+            static bool ringAttr[64] = {false};
+            // (a window is rounded to 16 bytes at both ends: tensors allocated here carry that slack, wrapped memory may not)
+            if (!noBulk && ((uintptr_t)a.in.ptr & 15) == 0 && !noRing && in->owns && ROr >= 2 && bx0min >= 0 && by0min >= 0 && bx0max + NC <= a.in.texW && byEnd <= a.in.texH &&
+                (a.in.deep || a.in.texH * (long long)a.in.texW * 4 == a.in.planeElems) && a.in.deep == a.out.deep && (!a.in.deep || a.in.tx == a.out.tx) && (long long)a.Ho * a.in.tx * a.Wo < 65536 && totalItems >= 6ll * op->ctx->prop.multiProcessorCount &&
+                totalItems < (1ll << 31) && ringSmem <= 110 * 1024) {
+                if (!ringAttr[op->ctx->device & 63]) {
+                    FYN_CUDA(cudaFuncSetAttribute(k_pool_rows_ring<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+                    FYN_CUDA(cudaFuncSetAttribute(k_pool_rows_ring<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+                    ringAttr[op->ctx->device & 63] = true;
+                }
+                const unsigned grid = (unsigned)std::min<long long>(totalItems, 2ll * op->ctx->prop.multiProcessorCount);
+                if (a.px == 3) k_pool_rows_ring<3, 3><<<grid, 256, ringSmem, (cudaStream_t)stream>>>(a, ROr, (unsigned)totalItems);
+                else k_pool_rows_ring<2, 2><<<grid, 256, ringSmem, (cudaStream_t)stream>>>(a, ROr, (unsigned)totalItems);
+                FYN_CHECK_LAUNCH(op->ctx);
+                return FYN_OK;
+            }
+        }
+        const size_t smem = (size_t)(a.dy * (RO - 1) + a.py) * NCs * 8 + 16;
         if (smem <= 48 * 1024) {
             const unsigned grid = (unsigned)(((a.Ho + RO - 1) / RO) * (long long)a.tiles * a.batch);
-            if (a.px == 3) k_pool_rows<3, 3><<<grid, 256, smem, (cudaStream_t)stream>>>(a, RO, NC);
-            else k_pool_rows<2, 2><<<grid, 256, smem, (cudaStream_t)stream>>>(a, RO, NC);
+            if (a.px == 3) k_pool_rows<3, 3><<<grid, 256, smem, (cudaStream_t)stream>>>(a, RO, NC, bulk);
+            else k_pool_rows<2, 2><<<grid, 256, smem, (cudaStream_t)stream>>>(a, RO, NC, bulk);
             FYN_CHECK_LAUNCH(op->ctx);
             return FYN_OK;
         }

@@ -179,6 +179,71 @@ def test_pooling(deep, dtype):
             o.destroy()
 
 
+def test_large_grid_bandwidth_kernels_are_bit_identical(monkeypatch):
+    """Large grids take other kernels than the small shapes of the oracle tests: the persistent ring pooling kernel (three staged
+    windows per block, bulk copies), bulk-copy staging, the multi-row global pooling kernel and the pair-access element-wise kernel.
+    Same arithmetic in the same order as the simple kernels (FYN_POOL_SIMPLE-free knobs FYN_POOL_NO_RING / FYN_POOL_NO_BULK), so
+    the bits must agree; one image is also checked against the oracle."""
+    c = ctx()
+    rng = np.random.default_rng(77)
+    for size, ch, batch, pool, ds, pad, is_max, relu, odd in [(112, 64, 24, 3, 2, 1, True, True, False), (56, 40, 48, 2, 2, 0, True, False, False),
+                                                            (57, 24, 40, 3, 2, 1, True, True, True), (60, 32, 40, 2, 2, 0, False, True, False)]:
+        x = rng.normal(size=(batch, ch, size, size)).astype(np.float32)
+        so = size // ds
+        op = capi.Pool2d(c, width=size, height=size, channels=ch, pool=pool, downsample=ds, in_padding=pad, is_max=is_max,
+                         flags=capi.FLAG_DEEP | (capi.FLAG_PRE_RELU if relu else 0))
+        tin = c.tensor(size, size, ch, pad, capi.ORDER_DEEP, capi.F16, batch)
+        tout = c.tensor(so, so, ch, 0, capi.ORDER_DEEP, capi.F16, batch)
+        tin.write_chw(x)
+        outs = []
+        for knobs in ((), ("FYN_POOL_NO_RING",), ("FYN_POOL_NO_RING", "FYN_POOL_NO_BULK")):
+            for k in ("FYN_POOL_NO_RING", "FYN_POOL_NO_BULK"):
+                monkeypatch.delenv(k, raising=False)
+            for k in knobs:
+                monkeypatch.setenv(k, "1")
+            tout.write_chw(np.zeros((batch, ch, so, so), np.float32))
+            op.run(tin, tout)
+            outs.append(tout.read_chw())
+        for k in ("FYN_POOL_NO_RING", "FYN_POOL_NO_BULK"):
+            monkeypatch.delenv(k, raising=False)
+        np.testing.assert_array_equal(outs[0], outs[1])
+        np.testing.assert_array_equal(outs[0], outs[2])
+        ref = fo.pool2d(half(x[-1]), pool=pool, downsample=ds, in_pad=pad, is_max=is_max, act=fo.ACT_RELU if relu else fo.ACT_NONE, prec=fo.FP16_STORE)
+        if is_max:
+            np.testing.assert_allclose(outs[0][-1], ref, rtol=1e-6, atol=1e-6)
+        else:
+            assert_close_f16(outs[0][-1], ref)
+        for o in (tin, tout, op):
+            o.destroy()
+    # global average pooling over several rows of tiles per block, odd and even tile grids
+    for size, ch, batch in [(7, 2048, 40), (7, 100, 9), (5, 512, 64), (8, 260, 17)]:
+        x = rng.normal(size=(batch, ch, size, size)).astype(np.float32)
+        op = capi.Pool2d(c, width=size, height=size, channels=ch, pool=size, downsample=size, is_max=False, global_=True, flags=capi.FLAG_DEEP | capi.FLAG_PRE_RELU)
+        tin = c.tensor(size, size, ch, 0, capi.ORDER_DEEP, capi.F16, batch)
+        tout = c.tensor(1, 1, ch, 0, capi.ORDER_DEEP, capi.F16, batch)
+        tin.write_chw(x)
+        op.run(tin, tout)
+        y = tout.read_chw()
+        ref = np.maximum(half(x), 0).astype(np.float64).mean(axis=(2, 3)).reshape(y.shape)
+        assert_close_f16(y, half(ref), extra_abs=1e-4)
+        for o in (tin, tout, op):
+            o.destroy()
+    # batch-norm on pair-aligned deep tensors (even width, no padding) against the texel-wise kernel's shapes (odd width)
+    for size, ch, batch in [(56, 256, 6), (28, 64, 5), (24, 12, 3)]:
+        x = rng.normal(size=(batch, ch, size, size)).astype(np.float32)
+        sb = np.concatenate([rng.uniform(0.5, 1.5, ch), rng.uniform(-0.5, 0.5, ch)]).astype(np.float32)
+        op = capi.BatchNorm(c, sb, width=size, height=size, channels=ch, flags=capi.FLAG_DEEP | capi.FLAG_PRE_RELU)
+        tin = c.tensor(size, size, ch, 0, capi.ORDER_DEEP, capi.F16, batch)
+        tout = c.tensor(size, size, ch, 0, capi.ORDER_DEEP, capi.F16, batch)
+        tin.write_chw(x)
+        op.run(tin, tout)
+        y = tout.read_chw()
+        ref = half(np.maximum(half(x), 0) * sb[:ch, None, None] + sb[ch:, None, None])
+        assert_close_f16(y, ref)
+        for o in (tin, tout, op):
+            o.destroy()
+
+
 @pytest.mark.parametrize("dtype", [capi.F16, capi.F32])
 def test_batchnorm_and_sigmoid(dtype):
     """BN2 (shallow, outputPadding 1, no activation), deep BN (resnet50.cpp BN5..BN66), SigmoidLayer."""
