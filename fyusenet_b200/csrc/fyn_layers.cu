@@ -383,62 +383,6 @@ __global__ void __launch_bounds__(256) k_pool_global_deep(const PoolArgs a) {
     }
 }
 
-// Windows of at most eight rows (ResNet-50's 7x7): a block owns R consecutive rows of tiles of one image and takes them two
-// at a time -- sixteen 8-byte loads in flight per thread, the column sums of both rows of tiles go to shared memory behind ONE
-// barrier (two buffers, alternating), then the per-tile reduction.  k_pool_global_deep above (one row of tiles per block, 12 KB
-// per block, 8192 short-lived blocks at batch 512) reached 35 % of the copy bandwidth.
-__global__ void __launch_bounds__(256) k_pool_global_deep8(const PoolArgs a, int R) {
-    extern __shared__ float4 sCol[];                       // [2 buffers][2 rows of tiles][texW]
-    const int groups = (a.in.tileRows + R - 1) / R;
-    const int grp = blockIdx.x % groups, n = blockIdx.x / groups;
-    const int W = a.in.W, H = a.in.H, P = a.in.P, texW = a.in.texW;
-    const int tr0 = grp * R, tr1 = min(tr0 + R, a.in.tileRows);
-    const __half *img = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems;
-    int buf = 0;
-    for (int tr = tr0; tr < tr1; tr += 2, buf ^= 1) {
-        float4 *col = sCol + (size_t)buf * 2 * texW;
-        for (int X = threadIdx.x; X < texW; X += 256) {
-            uint2 raw[2][8];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const __half *src = img + ((long long)(P + (tr + h) * a.in.tileH) * texW + X) * 4;
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-                    raw[h][u] = (tr + h < tr1 && u < H) ? __ldg(reinterpret_cast<const uint2 *>(src + (long long)u * texW * 4)) : make_uint2(0u, 0u);
-            }
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                float4 acc = a.isMax ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    if (u >= H) break;
-                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[h][u].x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[h][u].y));
-                    const float4 v = fyn_act4(make_float4(f0.x, f0.y, f1.x, f1.y), a.act);
-                    if (a.isMax) acc = make_float4(fmaxf(acc.x, v.x), fmaxf(acc.y, v.y), fmaxf(acc.z, v.z), fmaxf(acc.w, v.w));
-                    else acc = make_float4(acc.x + v.x, acc.y + v.y, acc.z + v.z, acc.w + v.w);
-                }
-                col[h * texW + X] = acc;
-            }
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < 2 * a.in.tx; i += 256) {
-            const int h = i / a.in.tx, tc = i - h * a.in.tx;
-            const int t = (tr + h) * a.in.tx + tc;
-            if (tr + h >= tr1 || t >= a.tiles) continue;
-            const float4 *c = col + h * texW + P + tc * a.in.tileW;
-            float4 acc = c[0];
-            for (int x = 1; x < W; x++) {
-                const float4 v = c[x];
-                if (a.isMax) acc = make_float4(fmaxf(acc.x, v.x), fmaxf(acc.y, v.y), fmaxf(acc.z, v.z), fmaxf(acc.w, v.w));
-                else acc = make_float4(acc.x + v.x, acc.y + v.y, acc.z + v.z, acc.w + v.w);
-            }
-            if (!a.isMax) acc = make_float4(acc.x * a.inv, acc.y * a.inv, acc.z * a.inv, acc.w * a.inv);
-            fyn_store_texel(a.out, n, t, a.outP, a.outP, acc);
-        }
-        // (the next pair of rows writes the other buffer; this one is rewritten two iterations later, behind the next barrier)
-    }
-}
-
 // large windows (global pooling): one warp per output texel, lanes stride over the window, shuffle reduction
 __global__ void __launch_bounds__(128) k_pool_warp(const PoolArgs a) {
     const long long o = (long long)blockIdx.x * 4 + threadIdx.y;
@@ -875,15 +819,10 @@ int fyn_pool2d_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stre
     static const bool noRows = getenv("FYN_POOL_SIMPLE") != nullptr;       // (measurement knob: the per-texel kernels)
     if (h4 && !noRows && d.global && deep && a.in.deep && a.out.deep && !a.quirk3 && a.px * a.py >= 16 && (size_t)a.in.texW * 16 <= 48 * 1024) {
         // (the order of the additions differs from k_pool_warp's; both are within the 1-ulp bound of the fp16-store oracle)
-        if (a.in.H <= 8 && (size_t)a.in.texW * 64 <= 48 * 1024) {
-            // rows of tiles per block: enough blocks for every SM (eight resident blocks each), at most the whole image
-            int R = a.in.tileRows;
-            while (R > 2 && (long long)((a.in.tileRows + R - 1) / R) * a.batch < 8ll * op->ctx->prop.multiProcessorCount) R = (R + 1) / 2;
-            R = (R + 1) & ~1;
-            k_pool_global_deep8<<<(unsigned)(((a.in.tileRows + R - 1) / R) * a.batch), 256, (size_t)a.in.texW * 64, (cudaStream_t)stream>>>(a, R);
-        } else {
-            k_pool_global_deep<<<(unsigned)(a.in.tileRows * a.batch), 256, (size_t)a.in.texW * 16, (cudaStream_t)stream>>>(a);
-        }
+        // (measured and dropped in round 2: two / four rows of tiles per block with sixteen loads in flight per thread, 33 %; a
+        // bulk-copy ring of whole rows of tiles like k_pool_rows_ring with column sums behind a barrier, 22 - 28 %, or with one
+        // thread per tile, 11 % -- few long dependent chains per window; this kernel: 35 % of the copy bandwidth at batch 512)
+        k_pool_global_deep<<<(unsigned)(a.in.tileRows * a.batch), 256, (size_t)a.in.texW * 16, (cudaStream_t)stream>>>(a);
         FYN_CHECK_LAUNCH(op->ctx);
         return FYN_OK;
     }

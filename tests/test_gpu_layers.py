@@ -216,7 +216,7 @@ def test_large_grid_bandwidth_kernels_are_bit_identical(monkeypatch):
         for o in (tin, tout, op):
             o.destroy()
     # global average pooling over several rows of tiles per block, odd and even tile grids
-    for size, ch, batch in [(7, 2048, 40), (7, 100, 9), (5, 512, 64), (8, 260, 17)]:
+    for size, ch, batch in [(7, 2048, 40), (7, 2048, 256), (7, 100, 9), (5, 512, 64), (5, 512, 700), (8, 260, 17)]:
         x = rng.normal(size=(batch, ch, size, size)).astype(np.float32)
         op = capi.Pool2d(c, width=size, height=size, channels=ch, pool=size, downsample=size, is_max=False, global_=True, flags=capi.FLAG_DEEP | capi.FLAG_PRE_RELU)
         tin = c.tensor(size, size, ch, 0, capi.ORDER_DEEP, capi.F16, batch)
