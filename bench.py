@@ -341,14 +341,17 @@ def secondary_stylenet_bands(ctx, comm, rank, world, local_rank, barrier, max_ov
     """BASELINE configs[4]: StyleNet 9x9 on one 4096x4096 frame, row-banded over the ranks (strong scaling) with the per-layer
     halo exchange over NVLink (fyn_halo_exchange: peer stores, one kernel per layer); one rank runs the whole frame."""
     from fyusenet_b200 import hostapi, multigpu, synthetic
-    margin = multigpu.HALO_MARGIN
+    margin = int(os.environ.get("FYN_HALO_MARGIN", multigpu.HALO_MARGIN_SPARSE))
     ib, ie, skip, keep = multigpu.stylenet_halo_band_plan(size, world, margin)[rank]
     h = ie - ib
     net = hostapi.StyleNet(KSIZE, size, h, upload=True, download=True, device=local_rank)
     net.load_weights(synthetic.stylenet_weights(KSIZE))
     net.setup()
+    exchanges = 0
     if world > 1:
         net.set_halo_exchange(comm, margin, h)
+        exchanges = net.halo_exchanges
+    chained = net.chained_layers
     # this rank's rows of the synthetic frame (generated per rank: only the shape matters for the timing)
     net.input_buffer()[:] = np.random.default_rng(4096 + rank).random(h * size * 3, dtype=np.float32)
     for _ in range(warmup):
@@ -375,7 +378,8 @@ def secondary_stylenet_bands(ctx, comm, rank, world, local_rank, barrier, max_ov
     value = steps / (dev_ms / 1e3)
     return {"workload": f"StyleNet 9x9 {size}x{size} frame, {world} row band(s) of {keep} rows + {margin}-row margins, per-layer halo exchange (BASELINE configs[4])",
             "scaling": "strong", "value": value, "unit": "frames/s", "ms_per_step": dev_ms / steps, "steps": steps,
-            "exchange": "fyn_halo_exchange: peer stores over NVLink (CUDA IPC), one kernel per layer, 15 exchanges per frame" if world > 1 else "none (one rank)",
+            "exchange": f"fyn_halo_exchange: peer stores over NVLink (CUDA IPC), {exchanges} exchange(s) per frame where a layer would reach spoilt margin rows (Engine::planHalo)" if world > 1 else "none (one rank)",
+            "exchanges_per_frame": exchanges, "chained_layers": chained,
             "nvlink_bytes_pushed_per_frame_rank0": int(pushed // max(frames, 1)),
             "roofline_frac": value / (S9_4096_ROOFLINE_FPS * world),
             "e2e": {"value": steps / e2e_s, "unit": "frames/s", "ms_per_step": 1e3 * e2e_s / steps,

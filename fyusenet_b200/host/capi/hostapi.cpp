@@ -385,6 +385,13 @@ int fynhost_net_chained_layers(void *handle) {
     return n;
 }
 
+int fynhost_net_halo_exchanges(void *handle) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    int n = -1;
+    guarded([&] { n = h->net()->engine()->haloExchanges(); });
+    return n;
+}
+
 // like fynhost_net_enable_timings(handle, 1) but with an event pair around one layer only
 int fynhost_net_enable_layer_timing(void *handle, int layerNumber) {
     NetHandle *h = static_cast<NetHandle *>(handle);

@@ -63,6 +63,7 @@ class Engine : public GfxContextTracker {
     // chains of same-geometry convolutions as one persistent kernel (part of the fusion switch; separately switchable)
     void enableChains(bool on) { chainFusion_ = on; updateFusion(); }
     int chainedLayers() const { return chainedLayers_; }
+    int haloExchanges() const { return (int)haloSteps_.size(); }   // exchanges per forward in row-banded operation (setHaloExchange)
     // Synchronous path: capture the device layers (everything between the upload and the download layer) into a CUDA graph on
     // the next forward and replay it afterwards; re-captured when tensor bindings, weights or fusions change.  Suspended
     // while timings, dumps or a halo exchange are active.
@@ -128,7 +129,10 @@ class Engine : public GfxContextTracker {
     fyn_comm *haloComm_ = nullptr;
     int haloMargin_ = 0, haloInputHeight_ = 0;
     struct HaloStep { int slot; int rows; };
-    std::unordered_map<int, HaloStep> haloSteps_;      // layer number -> exchange issued after that layer
+    std::unordered_map<int, HaloStep> haloSteps_;      // layer number -> exchange issued after that layer (the active ones)
+    std::unordered_map<int, HaloStep> haloSlots_;      // layer number -> registered tensor (every candidate)
+    bool haloNoChains_ = false;                        // the margin does not cover a whole chain: layers run one by one
+    bool planHalo();
     std::string outputDir_;
     std::unordered_map<int, uint32_t> timingData_;
     std::unordered_map<int, float> deviceTimingData_;

@@ -59,6 +59,7 @@ class ConvLayerBase : public GPULayerBase, public ConvLayerInterface {
     void setChainMember(bool on) { chainMember_ = on; }
     void unchain();
     bool chained() const { return chain_ != nullptr || chainMember_; }
+    int chainLength() const { return chain_ ? 1 + (int)chainFollowers_.size() : 0; }   // > 0: this layer launches the chain
 
  protected:
     void init(int kernel, int dilation, float sourceStep, bool fractional);

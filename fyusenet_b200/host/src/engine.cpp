@@ -1,4 +1,5 @@
 // Engine + NeuralNetwork.
+#include <cmath>
 #include <cstdlib>
 #include <cstdio>
 #include "fyusenet/base/engine.h"
@@ -66,8 +67,13 @@ void Engine::updateFusion() {
             fusedLayers_++;
         }
     }
-    // (row-banded operation refreshes the margins after every layer: no chains there)
-    updateChains(want && chainFusion_ && !haloComm_ && getenv("FYN_NO_CHAIN") == nullptr);
+    // (row-banded operation: chains stay as long as the margin covers a whole chain's taps, see planHalo)
+    updateChains(want && chainFusion_ && !(haloComm_ && haloNoChains_) && getenv("FYN_NO_CHAIN") == nullptr);
+    if (haloComm_ && !haloSlots_.empty() && !planHalo()) {
+        haloNoChains_ = true;
+        updateChains(false);
+        if (!planHalo()) THROW_EXCEPTION_ARGS(FynException, "Halo margin of %d rows does not cover the taps of a single layer", haloMargin_);
+    }
 }
 
 // Runs of consecutive shallow convolutions of identical geometry (StyleNet: res1_1 ... res5_2) -> one persistent kernel
@@ -153,14 +159,20 @@ void Engine::setHaloExchange(fyn_comm *comm, int marginRows, int inputHeight) {
     if (!setup_) THROW_EXCEPTION_ARGS(FynException, "setHaloExchange() needs a network that has been set up");
     dropGraph();
     haloSteps_.clear();
+    haloSlots_.clear();
+    haloNoChains_ = false;
     haloComm_ = comm;
     haloMargin_ = marginRows;
     haloInputHeight_ = inputHeight;
-    updateFusion();
-    if (!comm) return;
+    if (!comm) {
+        updateFusion();
+        return;
+    }
     if (async_) THROW_EXCEPTION_ARGS(FynException, "Row-banded operation is synchronous");
     if (marginRows <= 0 || marginRows % 4 || inputHeight <= 0)
         THROW_EXCEPTION_ARGS(FynException, "Halo margin must be a positive multiple of 4 full-resolution rows (got %d)", marginRows);
+    // every tensor whose margins may have to be refreshed is registered once (a collective over the communicator: the same
+    // sequence on every rank); planHalo() then picks the exchanges that are needed
     for (auto it = layers_.begin(); it != layers_.end(); ++it) {
         auto *g = dynamic_cast<gpu::GPULayerBase *>(it.second);
         if (!g || dynamic_cast<gpu::UploadLayer *>(g) || dynamic_cast<gpu::DownloadLayer *>(g) || !g->hasOutputTexture(0)) continue;
@@ -168,8 +180,6 @@ void Engine::setHaloExchange(fyn_comm *comm, int marginRows, int inputHeight) {
         bool spatial = false;
         for (auto &rcv : g->receivers())
             if (!dynamic_cast<gpu::SigmoidLayer *>(rcv.first) && !dynamic_cast<gpu::DownloadLayer *>(rcv.first)) spatial = true;
-        if (auto *conv = dynamic_cast<gpu::ConvLayerBase *>(g))
-            if (conv->fused()) spatial = false;              // conv + function: the pair's consumer decides (handled at the function layer)
         if (!spatial) continue;
         fyn_tensor_desc d{};
         FYN_ABI_CALL(fyn_tensor_get_desc(g->getOutputTexture(0), &d, nullptr));
@@ -180,8 +190,120 @@ void Engine::setHaloExchange(fyn_comm *comm, int marginRows, int inputHeight) {
         HaloStep st{};
         st.rows = (int)(num / inputHeight);
         FYN_ABI_CALL(fyn_comm_register_tensor(comm, g->getOutputTexture(0), &st.slot));
-        haloSteps_[it.first] = st;
+        haloSlots_[it.first] = st;
     }
+    updateFusion();            // (re)builds the chains and plans the exchanges
+}
+
+// Which margins have to be refreshed, and when.  A band carries `haloMargin_` full-resolution rows of its neighbours on either
+// side; they are exact after an exchange (or in the uploaded input) and every layer with spatial taps spoils the outermost
+// ones -- the texture edge of a band is not the image edge.  `valid` follows, per tensor, how many full-resolution rows
+// beyond the band edge are still exact; an exchange (fyn_halo_exchange, peer stores over NVLink) is issued on a layer's
+// input only when the layer would otherwise reach into spoilt rows.  With the 8-row margin of round 2's first version that is
+// after every layer (15 exchanges per StyleNet frame); 44 rows cover the ten 3x3 layers of the residual trunk at 1/4
+// resolution, so the trunk runs as ONE chain kernel between two exchanges.  Returns false when an exchange would fall
+// inside a chain (its inner tensors are private to the kernel) even with the chain's input freshly exchanged.
+bool Engine::planHalo() {
+    using gpu::TensorHandle;
+    haloSteps_.clear();
+    const long long M = haloMargin_;
+    std::vector<int> forcedBefore;                 // chain heads whose input is exchanged whatever its state
+    for (int attempt = 0; attempt < 16; attempt++) {
+        haloSteps_.clear();
+        std::unordered_map<TensorHandle, long long> valid;
+        std::unordered_map<TensorHandle, int> producer;
+        int conflictHead = -1;
+        int chainHead = -1, chainLeft = 0;          // inside a chain: its head, layers still to come (this one included)
+        auto scaleOf = [&](TensorHandle t) {
+            fyn_tensor_desc d{};
+            FYN_ABI_CALL(fyn_tensor_get_desc(t, &d, nullptr));
+            if (d.height <= 0 || haloInputHeight_ % d.height) THROW_EXCEPTION_ARGS(FynException, "Row bands: tensor height %d does not divide the band height %d", d.height, haloInputHeight_);
+            return (long long)(haloInputHeight_ / d.height);
+        };
+        auto validOf = [&](TensorHandle t) {
+            auto f = valid.find(t);
+            return f == valid.end() ? M : f->second;          // (a tensor handed in by the caller: margins as uploaded)
+        };
+        auto refresh = [&](TensorHandle t) {                   // exchange on t, issued behind its producer
+            auto pr = producer.find(t);
+            if (pr == producer.end()) return false;            // the network input: nothing to exchange with
+            auto slot = haloSlots_.find(pr->second);
+            if (slot == haloSlots_.end()) return false;
+            haloSteps_[pr->second] = slot->second;
+            const long long sc = scaleOf(t);
+            valid[t] = (M / sc) * sc;
+            // an exchange behind an inner layer of a chain cannot be issued
+            auto *pc = dynamic_cast<gpu::ConvLayerBase *>(layers_[pr->second]);
+            if (pc && pc->chained() && chainHead >= 0 && pr->second >= chainHead && chainLeft > 0) conflictHead = chainHead;
+            return true;
+        };
+        for (auto it = layers_.begin(); it != layers_.end() && conflictHead < 0; ++it) {
+            auto *g = dynamic_cast<gpu::GPULayerBase *>(it.second);
+            if (!g || dynamic_cast<gpu::DownloadLayer *>(g) || !g->hasOutputTexture(0)) continue;
+            TensorHandle out = g->getOutputTexture(0);
+            producer[out] = it.first;
+            if (dynamic_cast<gpu::UploadLayer *>(g)) {
+                valid[out] = M;
+                continue;
+            }
+            auto *conv = dynamic_cast<gpu::ConvLayerBase *>(g);
+            if (conv && conv->chainLength() > 0) {
+                chainHead = it.first;
+                chainLeft = conv->chainLength();
+                for (int f : forcedBefore)
+                    if (f == it.first && conv->hasInputTexture(0)) refresh(conv->getInputTexture(0));
+                conflictHead = -1;                               // (refreshing the head's own input is no conflict)
+            }
+            const long long so = scaleOf(out);
+            auto evaluate = [&]() -> long long {
+                long long vo;
+                if (conv) {
+                    const fyn_conv_desc &d = conv->descriptor();
+                    TensorHandle in = conv->getInputTexture(0);
+                    const long long si = scaleOf(in), viRows = validOf(in) / si;
+                    const long long mh = (long long)((d.kernel - 1) / 2) * std::max(1, d.dilation);
+                    long long voRows;
+                    if (!d.fractional) {
+                        const long long ds = std::max(1, d.downsample);
+                        const long long num = viRows - mh - (ds - 1);
+                        voRows = ds == 1 ? viRows - mh : (num >= 0 ? num / ds : -1);
+                    } else {
+                        // source rows floor(s * (ds * o + 0.5 + tap)), |tap| <= mh (gpu/vanilla/convlayerbase_vanilla.cpp:352-371): at most
+                        // ceil(s * (mh + 1)) source rows around the source position of the output row, one more for the floor
+                        const long long reach = (long long)std::ceil((double)d.source_step * (double)(mh + 1));
+                        const long long left = viRows - reach - 1;
+                        voRows = left >= 0 ? left * si / so : -1;
+                    }
+                    vo = voRows * so;
+                    if (TensorHandle res = conv->residualTexture()) vo = std::min(vo, (validOf(res) / so) * so);
+                } else if (dynamic_cast<gpu::SigmoidLayer *>(g) || dynamic_cast<gpu::BatchNormLayer *>(g)) {
+                    vo = validOf(g->getInputTexture(0));
+                } else {
+                    // any other layer: assume it uses up the margin (an exchange behind every such layer, the conservative rule)
+                    vo = validOf(g->getInputTexture(0)) >= M ? 0 : -1;
+                }
+                return vo;
+            };
+            long long vo = evaluate();
+            if (vo < 0) {
+                bool any = false;
+                if (g->hasInputTexture(0) && validOf(g->getInputTexture(0)) < (M / scaleOf(g->getInputTexture(0))) * scaleOf(g->getInputTexture(0))) any = refresh(g->getInputTexture(0)) || any;
+                if (conv && conv->residualTexture() && validOf(conv->residualTexture()) < (M / so) * so) any = refresh(conv->residualTexture()) || any;
+                vo = any ? evaluate() : vo;
+                if (vo < 0) {
+                    if (chainHead >= 0 && chainLeft > 0 && it.first != chainHead) conflictHead = chainHead;   // only a shorter chain would do
+                    else THROW_EXCEPTION_ARGS(FynException, "Layer %s: a halo margin of %d rows does not cover its taps", g->getName().c_str(), haloMargin_);
+                }
+            }
+            valid[out] = vo;
+            if (chainLeft > 0 && --chainLeft == 0) chainHead = -1;
+        }
+        if (conflictHead < 0) return true;
+        for (int f : forcedBefore)
+            if (f == conflictHead) return false;                 // already tried with a fresh input: the chain is too long for this margin
+        forcedBefore.push_back(conflictHead);
+    }
+    return false;
 }
 
 void Engine::cleanup() {

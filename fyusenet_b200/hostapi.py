@@ -178,6 +178,11 @@ class Network:
     def chained_layers(self) -> int:
         return lib().fynhost_net_chained_layers(self._h)
 
+    @property
+    def halo_exchanges(self) -> int:
+        """Exchanges per forward in row-banded operation (Engine::planHalo): margins are refreshed only where a layer would reach spoilt rows."""
+        return lib().fynhost_net_halo_exchanges(self._h)
+
     def enable_timings(self, on=True):
         _check(lib().fynhost_net_enable_timings(self._h, int(on)))
 

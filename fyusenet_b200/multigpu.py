@@ -126,7 +126,10 @@ def stylenet_band_plan(height: int, world: int, ksize: int = 9, margin: int | No
 # StyleNet row bands WITH the per-layer halo exchange over NVLink (fyn_halo_exchange, include/fyusenet_b200.h)
 # ------------------------------------------------------------------------------------------------
 
-HALO_MARGIN = 8     # full-resolution rows per band side: 8 / 4 / 2 rows at the /1, /2, /4 levels
+HALO_MARGIN = 8     # full-resolution rows per band side: 8 / 4 / 2 rows at the /1, /2, /4 levels (an exchange after every layer)
+# 44 rows = 11 rows at the /4 level: they cover the ten 3x3 layers of the residual trunk, so the engine (Engine::planHalo) keeps the
+# trunk as ONE chain kernel and refreshes the margins twice per frame (behind conv3 and behind res5_2) instead of fifteen times
+HALO_MARGIN_SPARSE = 44
 
 
 def stylenet_halo_margin(ksize: int = 9) -> int:

@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--halo", action="store_true", help="per-layer NVLink halo exchange instead of recomputed context rows")
     ap.add_argument("--kernel", type=int, default=9)
+    ap.add_argument("--margin", type=int, default=0, help="halo margin in full-resolution rows (default: multigpu.HALO_MARGIN_SPARSE; 8 = an exchange after every layer)")
+    ap.add_argument("--device-resident", action="store_true", help="time the layers + exchanges only (upload / download layers skipped)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -46,7 +48,8 @@ def main():
     K = args.kernel
     weights = synthetic.stylenet_weights(K)
     img = synthetic.image(args.height, args.width, 7)
-    plan = multigpu.stylenet_halo_band_plan(args.height, world) if args.halo else multigpu.stylenet_band_plan(args.height, world, K)
+    margin = args.margin or multigpu.HALO_MARGIN_SPARSE
+    plan = multigpu.stylenet_halo_band_plan(args.height, world, margin) if args.halo else multigpu.stylenet_band_plan(args.height, world, K)
     ib, ie, skip, keep = plan[rank]
     net = hostapi.StyleNet(K, args.width, ie - ib, device=local)
     net.load_weights(weights)
@@ -54,10 +57,14 @@ def main():
     comm = None
     if args.halo:
         comm = multigpu.make_comm(capi.Context(local), rank, world)
-        net.set_halo_exchange(comm, multigpu.HALO_MARGIN, ie - ib)
+        net.set_halo_exchange(comm, margin, ie - ib)
+    exchanges, chained = (net.halo_exchanges if args.halo else 0), net.chained_layers
     net.set_input(img[ib:ie])
     net.forward()
     band = net.output_rgba()[0][skip:skip + keep].copy()
+    if args.device_resident:
+        net.skip_io(True)
+        net.forward()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -94,7 +101,8 @@ def main():
         mode = "row bands with per-layer NVLink halo exchange" if args.halo else "overlapped row bands"
         print(json.dumps({"workload": f"StyleNet {K}x{K} {args.width}x{args.height}, {world} {mode}", "n_gpus": world,
                           "frames_per_s": args.steps / (ms / 1e3), "ms_per_frame": ms / args.steps, "band_rows": keep,
-                          "context_rows": multigpu.HALO_MARGIN if args.halo else multigpu.stylenet_margin(K), "nvlink_bytes_pushed_per_frame_rank0": int(pushed),
+                          "context_rows": margin if args.halo else multigpu.stylenet_margin(K), "exchanges_per_frame": exchanges, "chained_layers": chained,
+                          "device_resident": bool(args.device_resident), "nvlink_bytes_pushed_per_frame_rank0": int(pushed),
                           "rgb_checksum": float(sum(p.item() for p in parts)), "bit_exact_vs_whole_frame": exact}))
     if world > 1:
         dist.destroy_process_group()
