@@ -545,6 +545,40 @@ def test_halo_exchange_single_rank_is_a_no_op():
     net.destroy()
 
 
+def test_halo_plan_exchanges_only_where_margins_are_spent():
+    """Engine::planHalo follows how many margin rows are still exact behind every layer: with the 8-row margin of the per-layer
+    scheme almost every layer is followed by an exchange and the residual trunk cannot run as a chain; 44 rows (11 at the /4
+    level) cover the trunk's ten 3x3 layers, so the chain kernel stays and the margins are refreshed twice per frame.  (The
+    bit-exactness of the banded frame on 2 GPUs is tests/mgpu_stylenet_bands.py --halo --verify; here: the plan, and that a
+    single rank's frame does not change.)"""
+    weights = fo.stylenet_synthetic_weights(9)
+    img = fo.synthetic_image(256, 512, 5)
+    net = hostapi.StyleNet(9, 512, 256)
+    net.load_weights(weights)
+    net.setup()
+    net.set_input(img)
+    net.forward()
+    want = net.output_rgba()[0].copy()
+    assert net.chained_layers == 10
+    comm = capi.Comm(capi.Context(0), 0, 1, None)
+    plans = {}
+    for margin in (8, 24, 44, 60):
+        net.set_halo_exchange(comm, margin, 256)
+        plans[margin] = (net.halo_exchanges, net.chained_layers)
+        net.forward()
+        np.testing.assert_array_equal(net.output_rgba()[0], want)
+    assert plans[8][1] == 0 and plans[8][0] >= 12          # the per-layer scheme: no chain
+    assert plans[24][1] == 0 and plans[24][0] < plans[8][0]
+    assert plans[44] == (2, 10)                            # behind conv3 and behind res5_2
+    assert plans[60][1] == 10 and plans[60][0] <= 2
+    with pytest.raises(hostapi.HostError if hasattr(hostapi, "HostError") else Exception):
+        net.set_halo_exchange(comm, 4, 256)                # conv1's 9x9 taps need more than 4 rows
+    net.set_halo_exchange(None, 0, 0)
+    assert net.chained_layers == 10
+    comm.destroy()
+    net.destroy()
+
+
 def test_stylenet_chain_headline_size_is_exact():
     """BASELINE configs[1] (StyleNet 9x9, 1524x1856): the residual trunk as one persistent kernel (141 co-resident CTAs, ten
     layers, cross-CTA row dependencies) gives the same frame, bit for bit, as the layers launched one by one -- repeatedly."""
