@@ -50,6 +50,7 @@ struct DeepTcArgs {
     int ring;                    // stage ring depth <= min(kMaxRing, nstages)
     int nsets;                   // loader sets of this layer (<= kLoadSets): blockDim = (4 * nsets + 1) warps
     int tapPacked;               // 1: single input plane (<= 4 channels): a stage holds 16 kernel taps x 4 channels (ResNet stem)
+    int lastQuads;               // tap-packed: K16 steps (groups of four taps) of the LAST stage that hold kernel taps (7x7: one of four)
     long long Mtotal;            // batch * Ho * Wo
     uint32_t idesc;
     ActParams act;
@@ -265,13 +266,17 @@ __global__ void __launch_bounds__(kThreadsDeep, 2) k_conv_deep_tc(const __grid_c
             } else {
                 // one plane, sixteen taps per stage; the texture clamps at its edge (base/buffermanager.cpp:657-670), which is
                 // how the under-padded 7x7 stem (P = 1 < 3) still sees a zero border: the outermost texels are padding
+                // (the last stage of a 7x7 kernel holds one tap: only its first K16 step is gathered and multiplied)
+                const int ntaps = (s == a.nstages - 1) ? 4 * a.lastQuads : kKC / 4;
 #pragma unroll
                 for (int j = 0; j < kKC / 4; j++) {
+                    v[j] = make_uint2(0u, 0u);
+                    if (j >= ntaps) continue;
                     const int tt = tapTab[s * (kKC / 4) + j];
                     const int tky = tt & 255, tkx = tt >> 8;
                     const int iy = min(max(a.inP + a.ds * yo + tky - a.mh, 0), a.in.texH - 1);
                     const int ix = min(max(a.inP + a.ds * xo + tkx - a.mh, 0), a.in.texW - 1);
-                    v[j] = valid ? __ldg(reinterpret_cast<const uint2 *>(src + (iy * a.in.texW + ix) * 4)) : make_uint2(0u, 0u);
+                    if (valid) v[j] = __ldg(reinterpret_cast<const uint2 *>(src + (iy * a.in.texW + ix) * 4));
                 }
             }
             unsigned char *dst = sA + (size_t)st * kAStageBytes + t * 16;
@@ -338,10 +343,12 @@ __global__ void __launch_bounds__(kThreadsDeep, 2) k_conv_deep_tc(const __grid_c
                 mbar_wait(&full[st], use & 1);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(sA + (size_t)st * kAStageBytes) >> 4, b0 = smem_u32(sB + (size_t)st * bStageBytes) >> 4;
+                const int nq = (a.tapPacked && s == a.nstages - 1) ? a.lastQuads : kKC / 16;
 #pragma unroll
                 for (int j = 0; j < kKC / 16; j++)
-                    umma_f16(tmem, hi | (uint64_t)(aLbo | (a0 + (uint32_t)(j * 2 * kM))), hi | (uint64_t)(bLbo | (b0 + (uint32_t)(j * 2 * a.NT))), a.idesc,
-                             (s > 0 || j > 0) ? 1u : 0u);
+                    if (j < nq)
+                        umma_f16(tmem, hi | (uint64_t)(aLbo | (a0 + (uint32_t)(j * 2 * kM))), hi | (uint64_t)(bLbo | (b0 + (uint32_t)(j * 2 * a.NT))), a.idesc,
+                                 (s > 0 || j > 0) ? 1u : 0u);
                 umma_commit(&empty[st]);
                 if (s == a.nstages - 1) umma_commit(done);
             }
@@ -1000,23 +1007,32 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
                     }
                 } else if (interior) {
                     // every tap of this pixel lies inside the texture: base + tap offset, no clamping
+                    // (the last stage of a 7x7 kernel holds one tap: only its first K16 step is gathered and multiplied)
+                    const int nq = (s == a.nstages - 1) ? a.lastQuads : kKC / 16;
                     const int4 *off4 = reinterpret_cast<const int4 *>(tapOff + s * (kKC / 4));
 #pragma unroll
                     for (int j4 = 0; j4 < kKC / 16; j4++) {
-                        const int4 o = off4[j4];
-                        v[4 * j4 + 0] = __ldg(reinterpret_cast<const uint2 *>(px0 + o.x));
-                        v[4 * j4 + 1] = __ldg(reinterpret_cast<const uint2 *>(px0 + o.y));
-                        v[4 * j4 + 2] = __ldg(reinterpret_cast<const uint2 *>(px0 + o.z));
-                        v[4 * j4 + 3] = __ldg(reinterpret_cast<const uint2 *>(px0 + o.w));
+                        if (j4 < nq) {
+                            const int4 o = off4[j4];
+                            v[4 * j4 + 0] = __ldg(reinterpret_cast<const uint2 *>(px0 + o.x));
+                            v[4 * j4 + 1] = __ldg(reinterpret_cast<const uint2 *>(px0 + o.y));
+                            v[4 * j4 + 2] = __ldg(reinterpret_cast<const uint2 *>(px0 + o.z));
+                            v[4 * j4 + 3] = __ldg(reinterpret_cast<const uint2 *>(px0 + o.w));
+                        } else {
+                            v[4 * j4 + 0] = v[4 * j4 + 1] = v[4 * j4 + 2] = v[4 * j4 + 3] = make_uint2(0u, 0u);
+                        }
                     }
                 } else {
+                    const int ntaps = (s == a.nstages - 1) ? 4 * a.lastQuads : kKC / 4;
 #pragma unroll
                     for (int j = 0; j < kKC / 4; j++) {
+                        v[j] = make_uint2(0u, 0u);
+                        if (j >= ntaps) continue;
                         const int tt = tapTab[s * (kKC / 4) + j];
                         const int tky = tt & 255, tkx = tt >> 8;
                         const int iy = min(max(a.inP + a.ds * yo + tky - a.mh, 0), a.in.texH - 1);
                         const int ix = min(max(a.inP + a.ds * xo + tkx - a.mh, 0), a.in.texW - 1);
-                        v[j] = valid ? __ldg(reinterpret_cast<const uint2 *>(src + (iy * a.in.texW + ix) * 4)) : make_uint2(0u, 0u);
+                        if (valid) v[j] = __ldg(reinterpret_cast<const uint2 *>(src + (iy * a.in.texW + ix) * 4));
                     }
                 }
                 unsigned char *dst = sA + (size_t)st * kAStageBytes + t * 16;
@@ -1050,10 +1066,12 @@ __global__ void __launch_bounds__(kThreadsDeepP, 1) k_conv_deep_tc_p(const __gri
                     mbar_wait(&full[slot], phase);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(sA + (size_t)slot * kAStageBytes) >> 4, b0 = smem_u32(sB + (size_t)slot * bStageBytes) >> 4;
+                    const int nq = (a.tapPacked && s == a.nstages - 1) ? a.lastQuads : kKC / 16;
 #pragma unroll
                     for (int j = 0; j < kKC / 16; j++)
-                        umma_f16(tacc, hi | (uint64_t)(aLbo | (a0 + (uint32_t)(j * 2 * kM))), hi | (uint64_t)(bLbo | (b0 + (uint32_t)(j * 2 * a.NT))), a.idesc,
-                                 (s > 0 || j > 0) ? 1u : 0u);
+                        if (j < nq)
+                            umma_f16(tacc, hi | (uint64_t)(aLbo | (a0 + (uint32_t)(j * 2 * kM))), hi | (uint64_t)(bLbo | (b0 + (uint32_t)(j * 2 * a.NT))), a.idesc,
+                                     (s > 0 || j > 0) ? 1u : 0u);
                     umma_commit(&empty[slot]);
                     if (++slot == a.ring) {
                         slot = 0;
@@ -1313,6 +1331,8 @@ int fyn_conv_deep_tc_create(fyn_op *op, const float *wb) {
     a.tapPacked = Ci <= 4 ? 1 : 0;
     a.kcs = a.tapPacked ? 1 : Ci / kKC;
     a.nstages = a.tapPacked ? (K * K + 15) / 16 : K * K * a.kcs;
+    a.lastQuads = a.tapPacked ? (K * K - 16 * (a.nstages - 1) + 3) / 4 : kKC / 16;
+    if (getenv("FYN_DEEP_STEM_FULL")) a.lastQuads = kKC / 16;      // (measurement knob: gather and multiply the zero-weight taps too)
     a.nInPlanes = (Ci + 3) / 4;
     a.Cout4 = ((Co + 3) / 4) * 4;
     a.idesc = (1u << 4) | ((uint32_t)(a.NT >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);   // F32 accum, F16 x F16, K-major A/B

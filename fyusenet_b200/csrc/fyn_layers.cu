@@ -660,6 +660,39 @@ __global__ void __launch_bounds__(256) k_eltwise_p8(const EltArgs a, unsigned Wp
     }
 }
 
+// The upload texture (three fp32 channels per pixel, gpu/uploadlayer.cpp:371-375) -> one fp16 RGBA plane: ResNet-50's first
+// batch-norm (BN2).  Four pixels per thread: 48 bytes in as three 16-byte loads, four 8-byte texels out (the padded output rows
+// start on odd texels).  The generic one-texel-per-thread kernel took 177 us at batch 512 (44 % of the copy bandwidth).
+// Same arithmetic as elt_apply on (r, g, b, 0).
+__global__ void __launch_bounds__(256) k_eltwise_rgb32f(const EltArgs a, unsigned quadsPerRow, unsigned totalQuads) {
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.mode == 0) {
+        sc = __ldg(a.scale);
+        bi = __ldg(a.bias);
+    }
+    const unsigned rowsPerImage = (unsigned)a.in.H;
+    const unsigned magicQ = (unsigned)((1ull << 32) / quadsPerRow) + 1u, magicR = (unsigned)((1ull << 32) / rowsPerImage) + 1u;
+    for (unsigned q = blockIdx.x * 256u + threadIdx.x; q < totalQuads; q += gridDim.x * 256u) {
+        const unsigned row = __umulhi(q, magicQ), xq = q - row * quadsPerRow;        // row over the whole batch
+        const unsigned n = __umulhi(row, magicR), y = row - n * rowsPerImage;
+        const float *src = reinterpret_cast<const float *>(a.in.ptr) + (long long)n * a.in.imageElems + ((long long)(a.in.P + y) * a.in.texW + a.in.P + 4u * xq) * 3;
+        const float4 f0 = __ldg(reinterpret_cast<const float4 *>(src)), f1 = __ldg(reinterpret_cast<const float4 *>(src) + 1), f2 = __ldg(reinterpret_cast<const float4 *>(src) + 2);
+        const float px[4][3] = {{f0.x, f0.y, f0.z}, {f0.w, f1.x, f1.y}, {f1.z, f1.w, f2.x}, {f2.y, f2.z, f2.w}};
+        __half *dst = reinterpret_cast<__half *>(a.out.ptr) + (long long)n * a.out.imageElems + ((long long)(a.outP + y) * a.out.texW + a.outP + 4u * xq) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float4 v = fyn_act4(make_float4(px[k][0], px[k][1], px[k][2], 0.f), a.act);
+            if (a.mode == 0) v = make_float4(fmaf(v.x, sc.x, bi.x), fmaf(v.y, sc.y, bi.y), fmaf(v.z, sc.z, bi.z), fmaf(v.w, sc.w, bi.w));
+            else v = make_float4(fyn_sigmoid(v.x), fyn_sigmoid(v.y), fyn_sigmoid(v.z), fyn_sigmoid(v.w));
+            const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+            uint2 o;
+            o.x = *reinterpret_cast<const unsigned *>(&h0);
+            o.y = *reinterpret_cast<const unsigned *>(&h1);
+            *reinterpret_cast<uint2 *>(dst + 4 * k) = o;
+        }
+    }
+}
+
 // small planes (H*W <= 128, e.g. the 7x7 layers of ResNet-50): several planes per block, `sub` (a power of two >= H*W)
 // threads per plane, so that a block of 256 threads is not left four-fifths idle
 __global__ void __launch_bounds__(256) k_eltwise_h4_small(const EltArgs a, unsigned W, unsigned HW, unsigned sub, unsigned planes) {
@@ -701,6 +734,14 @@ static int launch_eltwise(fyn_ctx *ctx, const EltArgs &a, int W, int H, cudaStre
                       a.outP == 0 && a.in.texW == a.out.texW && a.in.texH == a.out.texH && a.in.planeElems == a.out.planeElems &&
                       a.in.imageElems == a.out.imageElems && a.in.imageElems == (long long)a.tiles * a.in.planeElems && (a.in.planeElems % 8) == 0 &&
                       flatUnits < (1ll << 31) && (((uintptr_t)a.in.ptr | (uintptr_t)a.out.ptr) & 15) == 0;
+    // the RGB32F upload texture -> an fp16 RGBA plane, four pixels per thread (16-byte aligned rows)
+    const long long quads = (long long)a.batch * H * (W / 4);
+    if (a.in.dtype == FYN_F32 && a.in.packing == 3 && !a.in.deep && a.out.dtype == FYN_F16 && a.out.packing == 4 && a.tiles == 1 && (W % 4) == 0 && a.in.P == 0 &&
+        a.in.texW == W && (((uintptr_t)a.in.ptr) & 15) == 0 && quads < (1ll << 31) && (long long)a.batch * H < (1ll << 31)) {
+        const long long cap = (long long)ctx->prop.multiProcessorCount * 8;
+        k_eltwise_rgb32f<<<(unsigned)std::min<long long>((quads + 255) / 256, cap), 256, 0, stream>>>(a, (unsigned)(W / 4), (unsigned)quads);
+        return 0;
+    }
     if (flat) {
         const long long cap = (long long)ctx->prop.multiProcessorCount * 8;
         const long long blocks = std::min<long long>((flatUnits + 1023) / 1024, cap);
