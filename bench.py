@@ -288,6 +288,33 @@ def secondary_resnet_sharded(ctx, comm, rank, world, local_rank, barrier, max_ov
     dev_ms = max_over_ranks(ctx.elapsed_ms(ev0, ev1))
     barrier()
     net.destroy()
+    # the same end-to-end step with 8-bit images (ResNet50::setByteInput: value / 255 on the device, what the reference's sample does
+    # on the host): 3 instead of 12 bytes per pixel over PCIe
+    byte_e2e = None
+    try:
+        bnet = hostapi.ResNet50(device=local_rank, batch=n_local)
+        bnet.set_byte_input(True)
+        bnet.load_weights((np.random.default_rng(50).standard_normal(bnet.weight_floats) * 0.02).astype(np.float32))
+        bnet.setup()
+        bnet.input_buffer()[:] = rng.integers(0, 256, n_local * 224 * 224 * 3, dtype=np.uint8)
+        blogits = bnet.layer_tensor(72)
+        bstream = bnet.stream
+
+        def step_bytes():
+            bnet.forward()
+            comm.allgather_logits(blogits, nmax, gathered, bstream)
+            ctx.memcpy_d2h(host_logits, gathered, bstream)
+            ctx.stream_sync(bstream)
+
+        for _ in range(warmup):
+            step_bytes()
+        b_s = max_over_ranks(_timed_wall(step_bytes, steps, barrier))
+        byte_e2e = {"value": total * steps / b_s, "unit": "img/s", "ms_per_step": 1e3 * b_s / steps, "h2d_bytes_per_step": int(n_local * 224 * 224 * 3),
+                    "d2h_bytes_per_step": int(n_local * 1000 * 4 + world * nmax * 1000 * 4), "finite": bool(np.isfinite(host_logits).all()),
+                    "api": "ResNet50::setByteInput(): uint8 RGB images in (value / 255 on the device)"}
+        bnet.destroy()
+    except Exception as exc:  # noqa: BLE001  (the float path above is the contract; this is an extra)
+        byte_e2e = {"error": str(exc)[:200]}
     ctx.device_free(gathered)
     value = total * steps / (dev_ms / 1e3)
     return {"workload": f"ResNet-50 224x224, {total} images batch-sharded over {world} GPU(s), NCCL all-gather of the logits inside the timed region (BASELINE configs[3])",
@@ -295,7 +322,8 @@ def secondary_resnet_sharded(ctx, comm, rank, world, local_rank, barrier, max_ov
             "collective": f"fyn_allgather_logits: NCCL all-gather of float32 [{nmax}, 1000] per rank" if world > 1 else "none (one rank): logits converted to float32 on the device",
             "roofline_frac": value / (RESNET_B512_ROOFLINE_IMG_S * world),
             "e2e": {"value": total * steps / e2e_s, "unit": "img/s", "ms_per_step": 1e3 * e2e_s / steps,
-                    "h2d_bytes_per_step": int(n_local * 224 * 224 * 3 * 4), "d2h_bytes_per_step": int(n_local * 1000 * 4 + world * nmax * 1000 * 4), "finite": finite}}
+                    "h2d_bytes_per_step": int(n_local * 224 * 224 * 3 * 4), "d2h_bytes_per_step": int(n_local * 1000 * 4 + world * nmax * 1000 * 4), "finite": finite,
+                    "byte_io": byte_e2e}}
 
 
 def secondary_resnet_b1(ctx, rank, world, local_rank, barrier, max_over_ranks, steps=200, warmup=20):

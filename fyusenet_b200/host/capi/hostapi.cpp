@@ -98,6 +98,15 @@ int fynhost_stylenet_set_byte_io(void *handle, int on) {
     });
 }
 
+// 8-bit images in (ResNet50::setByteInput; before setup)
+int fynhost_resnet50_set_byte_input(void *handle, int on) {
+    NetHandle *h = static_cast<NetHandle *>(handle);
+    return guarded([&] {
+        if (h->kind != NetHandle::RESNET) THROW_EXCEPTION_ARGS(FynException, "Not a ResNet-50");
+        h->resnet->setByteInput(on != 0);
+    });
+}
+
 // raw views of the pinned input (slot < 0: the synchronous buffer) / output buffers with their size in bytes and element type
 // (0 float32, 1 float16, 2 uint8), for networks with 8-bit I/O
 void *fynhost_net_input_raw(void *handle, int slot, size_t *numBytes, int *dataType) {

@@ -128,6 +128,7 @@ CompiledLayers ResNet50::buildLayers() {
             case Node::UPLOAD: {
                 auto *b = new gpu::UpDownLayerBuilder(gpu::UpDownLayerBuilder::UPLOAD, name);
                 b->shape(3, n.size, n.size, 3).context(context()).number(n.no);
+                if (byteInput_) b->dataType(BufferSpec::UBYTE);
                 b->push(factory);
                 break;
             }
@@ -196,14 +197,20 @@ void ResNet50::connectLayers(CompiledLayers &layers, BufferManager *bufMgr) {
 ResNet50::CPUBuffer *ResNet50::inputBuffer() {
     if (!setup_) THROW_EXCEPTION_ARGS(FynException, "Please run setup() before setting input buffers");
     if (!inBuffer_) {
-        cpu::CPUBufferShape shape(IMAGE_SIZE, IMAGE_SIZE, 3, 0, cpu::CPUBufferShape::FLOAT32, BufferSpec::order::GPU_SHALLOW, batch_);
+        cpu::CPUBufferShape shape(IMAGE_SIZE, IMAGE_SIZE, 3, 0, byteInput_ ? cpu::CPUBufferShape::UINT8 : cpu::CPUBufferShape::FLOAT32, BufferSpec::order::GPU_SHALLOW, batch_);
         inBuffer_ = shape.createBuffer(context());
     }
     static_cast<gpu::UploadLayer *>(engine_->getLayers()["upload"])->setInputBuffer(inBuffer_, 0);
     return inBuffer_;
 }
 
+void ResNet50::setByteInput(bool on) {
+    if (setup_) THROW_EXCEPTION_ARGS(FynException, "setByteInput() must be called before setup()");
+    byteInput_ = on;
+}
+
 void ResNet50::setInputBuffer(const float *data) {
+    if (byteInput_) THROW_EXCEPTION_ARGS(FynException, "Network takes 8-bit images (setByteInput)");
     CPUBuffer *buf = inputBuffer();
     float *tgt = buf->map<float>();
     memcpy(tgt, data, buf->bytes());

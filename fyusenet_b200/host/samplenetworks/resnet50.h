@@ -19,6 +19,10 @@ class ResNet50 : public fyusion::fyusenet::NeuralNetwork {
     explicit ResNet50(const fyusion::fyusenet::GfxContextLink &ctx = fyusion::fyusenet::GfxContextLink());
     ~ResNet50() override;
     void setInputBuffer(const float *data);
+    // 8-bit images in (before setup()): the upload layer takes UBYTE data and the bytes become value / 255 on the device -- the
+    // conversion samples/desktop/resnet.cpp:48-51 does on the host, bit for bit -- so a batch crosses PCIe as 3 instead of 12 bytes per pixel
+    void setByteInput(bool on);
+    bool byteInput() const { return byteInput_; }
     CPUBuffer *getOutputBuffer();
     // the pinned host buffer the upload layer reads from (created on demand and attached to the upload layer)
     CPUBuffer *inputBuffer();
@@ -47,4 +51,5 @@ class ResNet50 : public fyusion::fyusenet::NeuralNetwork {
     std::vector<float> wbData_;
     size_t totalWeightBytes_ = 0;
     CPUBuffer *inBuffer_ = nullptr;
+    bool byteInput_ = false;
 };

@@ -274,6 +274,23 @@ class ResNet50(Network):
     def __init__(self, device=0, batch=1):
         super().__init__(lib().fynhost_resnet50_create(int(device), int(batch)))
         self.batch = batch
+        self.byte_input = False
+
+    def set_byte_input(self, on=True):
+        """8-bit images in (ResNet50::setByteInput, before setup()): UBYTE upload, value / 255 on the device -- the conversion the
+        reference's sample does on the host (samples/desktop/resnet.cpp:48-51), bit for bit; 3 instead of 12 bytes per pixel over PCIe."""
+        _check(lib().fynhost_resnet50_set_byte_input(self._h, int(bool(on))))
+        self.byte_input = bool(on)
+
+    def input_buffer(self) -> np.ndarray:
+        if not self.byte_input:
+            return super().input_buffer()
+        n, dt = C.c_size_t(), C.c_int()
+        lib().fynhost_net_input_raw.restype = C.c_void_p
+        p = lib().fynhost_net_input_raw(self._h, -1, C.byref(n), C.byref(dt))
+        if not p:
+            raise HostError(lib().fynhost_last_error().decode(errors="replace"))
+        return np.ctypeslib.as_array(C.cast(C.c_void_p(p), C.POINTER(C.c_ubyte)), shape=(n.value,))
 
     def logits(self) -> np.ndarray:
         """[batch][1000]: the deep 18x14 download texture is channel order for 1x1 spatial (cpubuffer.cpp:131-142)."""

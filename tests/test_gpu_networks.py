@@ -450,6 +450,36 @@ def test_resnet50_top5_on_64_images():
     assert exact >= int(0.9 * n)
 
 
+def test_resnet50_byte_input_matches_float_input():
+    """ResNet50::setByteInput: 8-bit images cross PCIe and become value / 255 in the RGB32F upload texture on the device -- exactly
+    the floats the reference's sample computes on the host (samples/desktop/resnet.cpp:48-51), so the logits are bit-identical to
+    uploading those floats; a float frame is refused by a byte network."""
+    weights = fo.resnet50_synthetic_weights()
+    rng = np.random.default_rng(21)
+    for batch in (1, 5):
+        bytes_ = rng.integers(0, 256, size=(batch, 224, 224, 3), dtype=np.uint8)
+        floats = bytes_.astype(np.float32) / np.float32(255.0)
+        a = hostapi.ResNet50(batch=batch)
+        a.load_weights(weights)
+        a.setup()
+        a.set_input(floats)
+        a.forward()
+        want = a.logits().copy()
+        a.destroy()
+        b = hostapi.ResNet50(batch=batch)
+        b.set_byte_input(True)
+        b.load_weights(weights)
+        b.setup()
+        buf = b.input_buffer()
+        assert buf.dtype == np.uint8 and buf.size == bytes_.size
+        buf[:] = bytes_.reshape(-1)
+        b.forward()
+        np.testing.assert_array_equal(b.logits(), want)
+        with pytest.raises(hostapi.HostError):
+            b.set_input(floats)
+        b.destroy()
+
+
 def test_fusions_exclude_each_other_at_the_abi():
     """a deep 1x1 convolution of the tcgen05 family accepts the fused input batch-norm but no fused function, and
     never both (the engine's two fusion passes used to claim the same layer, after which every forward() failed)."""
