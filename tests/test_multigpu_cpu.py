@@ -100,3 +100,22 @@ def test_gather_logits_and_step_time_world2():
     for rank, full, ms in results:
         np.testing.assert_array_equal(full, want)
         assert ms == 11.0                         # max over ranks
+
+
+def test_halo_band_plan_with_sparse_margin():
+    """The 44-row margin of the sparse halo exchange (Engine::planHalo keeps the residual trunk as one chain kernel between two
+    exchanges): bands tile the frame, margins exist only towards neighbours, every band height is a multiple of 4 (the /4 level
+    needs whole rows) and 11 rows at the /4 level cover the trunk's ten 3x3 layers."""
+    m = multigpu.HALO_MARGIN_SPARSE
+    assert m % 4 == 0 and m // 4 >= 10 + 1
+    for height, world in ((4096, 2), (4096, 4), (4096, 8), (1856, 2)):
+        plan = multigpu.stylenet_halo_band_plan(height, world, m)
+        assert len(plan) == world
+        covered = 0
+        for r, (ib, ie, skip, keep) in enumerate(plan):
+            assert (ie - ib) % 4 == 0 and keep > 0
+            assert skip == (m if r > 0 else 0)
+            assert ie - ib == keep + (m if r > 0 else 0) + (m if r < world - 1 else 0)
+            assert ib + skip == covered
+            covered += keep
+        assert covered == height
