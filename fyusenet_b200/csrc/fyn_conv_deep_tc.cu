@@ -1569,7 +1569,12 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     }
     int ntiles = plan->ntiles;
     size_t planSmem = plan->smemBytes;
-    if (plan->wideOff && mtiles * plan->ntiles >= 2ll * op->ctx->prop.multiProcessorCount) {
+    // (the 256-column tiles only where the halved grid still runs the persistent kernel: 1x1 1024 -> 2048 on 7x7 at batch 64 is 400 tiles of
+    // 128 columns -- persistent -- but 200 of 256 columns, i.e. the one-tile kernel with one 192 KB CTA per SM in two uneven waves;
+    // FYN_DEEP_WIDE_MIN: that threshold in tiles per SM, default 2)
+    static const long long wideMin = getenv("FYN_DEEP_WIDE_MIN") ? atoll(getenv("FYN_DEEP_WIDE_MIN")) : 2;
+    if (plan->wideOff && mtiles * plan->ntiles >= 2ll * op->ctx->prop.multiProcessorCount &&
+        (plan->args.nstages <= 2 || mtiles * plan->wideNtiles >= wideMin * op->ctx->prop.multiProcessorCount)) {
         a.NT = 256;
         a.wimg = plan->d_wimg + plan->wideOff;
         a.idesc = (1u << 4) | ((uint32_t)(a.NT >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
