@@ -1,6 +1,6 @@
 import ctypes as C, os, sys
 import numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parent.parent))
 from fyusenet_b200 import capi, hostapi
 ctx = capi.Context(0)
 net = hostapi.ResNet50(device=0, batch=1)
