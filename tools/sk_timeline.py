@@ -1,3 +1,9 @@
+#!/usr/bin/env python
+"""In-kernel timeline of the split-K cluster kernels (k_conv_deep_tc_sk) of one ResNet-50 batch-1 forward.
+
+Needs the instrumented build:  make -C fyusenet_b200/csrc EXTRA=-DFYN_SK_TIMELINE   (touch fyn_conv_deep_tc.cu first; rebuild without EXTRA afterwards)
+Every launch writes %globaltimer stamps into a device buffer (min start / max end over its CTAs, the phases of CTA (0,0,0)'s thread 0);
+this script runs three eager forwards and prints one line per launch of the last one (ns).  Evidence: profiles/r02_resnet_b1_sk_timeline.txt."""
 import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parent.parent))
