@@ -383,6 +383,49 @@ __global__ void __launch_bounds__(256) k_pool_global_deep(const PoolArgs a) {
     }
 }
 
+// Global pooling of small tiles (ResNet-50: 7x7) without shared memory or block barriers: a WARP owns floor(32 / W) horizontally
+// adjacent tiles of one row of tiles, lane = texture column; every lane sums its column over the tile's rows (H <= 8 loads in
+// flight, consecutive lanes on consecutive texels), the lane on a tile's first column then adds the other columns' sums in
+// column order through shuffles -- the summation order of k_pool_global_deep, so the results are bit-identical -- and
+// stores the tile's texel.  k_pool_global_deep (one block per row of tiles, column sums through shared memory behind a barrier,
+// the reduction on tx of 256 threads) reached 35 % of the copy bandwidth at batch 512: independent warps keep more loads in flight.
+__global__ void __launch_bounds__(256) k_pool_global_warp(const PoolArgs a, int tpw, int groups, unsigned totalWarps) {
+    // (one row of tiles per warp; two / four rows per warp with all their loads in flight were measured slower at batch 512 --
+    // 50 / 71 us instead of 39 - 45 us: registers and occupancy)
+    const unsigned wid = blockIdx.x * 8u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (wid >= totalWarps) return;
+    const int W = a.in.W, H = a.in.H, P = a.in.P, texW = a.in.texW;
+    const unsigned g = wid % (unsigned)groups, r = wid / (unsigned)groups;
+    const int trow = (int)(r % (unsigned)a.in.tileRows), n = (int)(r / (unsigned)a.in.tileRows);
+    const int j = (int)lane / W, x = (int)lane - j * W;
+    const int tc = (int)g * tpw + j, t = trow * a.in.tx + tc;
+    const bool active = j < tpw && tc < a.in.tx && t < a.tiles;
+    const __half *src = reinterpret_cast<const __half *>(a.in.ptr) + (long long)n * a.in.imageElems +
+                        ((long long)(P + trow * a.in.tileH) * texW + P + (active ? tc * a.in.tileW + x : 0)) * 4;
+    uint2 raw[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) raw[u] = (active && u < H) ? __ldg(reinterpret_cast<const uint2 *>(src + (long long)u * texW * 4)) : make_uint2(0u, 0u);
+    float4 col = a.isMax ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        if (u >= H) break;
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[u].x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&raw[u].y));
+        const float4 v = fyn_act4(make_float4(f0.x, f0.y, f1.x, f1.y), a.act);
+        if (a.isMax) col = make_float4(fmaxf(col.x, v.x), fmaxf(col.y, v.y), fmaxf(col.z, v.z), fmaxf(col.w, v.w));
+        else col = make_float4(col.x + v.x, col.y + v.y, col.z + v.z, col.w + v.w);
+    }
+    float4 acc = col;
+    for (int d = 1; d < W; d++) {
+        const float4 v = make_float4(__shfl_down_sync(0xffffffffu, col.x, d), __shfl_down_sync(0xffffffffu, col.y, d), __shfl_down_sync(0xffffffffu, col.z, d),
+                                     __shfl_down_sync(0xffffffffu, col.w, d));
+        if (a.isMax) acc = make_float4(fmaxf(acc.x, v.x), fmaxf(acc.y, v.y), fmaxf(acc.z, v.z), fmaxf(acc.w, v.w));
+        else acc = make_float4(acc.x + v.x, acc.y + v.y, acc.z + v.z, acc.w + v.w);
+    }
+    if (!active || x != 0) return;
+    if (!a.isMax) acc = make_float4(acc.x * a.inv, acc.y * a.inv, acc.z * a.inv, acc.w * a.inv);
+    fyn_store_texel(a.out, n, t, a.outP, a.outP, acc);
+}
+
 // large windows (global pooling): one warp per output texel, lanes stride over the window, shuffle reduction
 __global__ void __launch_bounds__(128) k_pool_warp(const PoolArgs a) {
     const long long o = (long long)blockIdx.x * 4 + threadIdx.y;
@@ -863,6 +906,15 @@ int fyn_pool2d_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stre
         // (measured and dropped in round 2: two / four rows of tiles per block with sixteen loads in flight per thread, 33 %; a
         // bulk-copy ring of whole rows of tiles like k_pool_rows_ring with column sums behind a barrier, 22 - 28 %, or with one
         // thread per tile, 11 % -- few long dependent chains per window; this kernel: 35 % of the copy bandwidth at batch 512)
+        if (a.in.W <= 16 && a.in.H <= 8 && !getenv("FYN_POOL_GLOBAL_BLOCK")) {
+            const int tpw = 32 / a.in.W, groups = (a.in.tx + tpw - 1) / tpw;
+            const long long warps = (long long)groups * a.in.tileRows * a.batch;   // (kRows = 1 row of tiles per warp)
+            if (warps < (1ll << 31)) {
+                k_pool_global_warp<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(a, tpw, groups, (unsigned)warps);
+                FYN_CHECK_LAUNCH(op->ctx);
+                return FYN_OK;
+            }
+        }
         k_pool_global_deep<<<(unsigned)(a.in.tileRows * a.batch), 256, (size_t)a.in.texW * 16, (cudaStream_t)stream>>>(a);
         FYN_CHECK_LAUNCH(op->ctx);
         return FYN_OK;

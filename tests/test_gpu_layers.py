@@ -226,6 +226,12 @@ def test_large_grid_bandwidth_kernels_are_bit_identical(monkeypatch):
         y = tout.read_chw()
         ref = np.maximum(half(x), 0).astype(np.float64).mean(axis=(2, 3)).reshape(y.shape)
         assert_close_f16(y, half(ref), extra_abs=1e-4)
+        # the warp-per-tile-group kernel (default for small tiles) adds in the order of the block kernel: same bits
+        monkeypatch.setenv("FYN_POOL_GLOBAL_BLOCK", "1")
+        tout.write_chw(np.zeros_like(y))
+        op.run(tin, tout)
+        monkeypatch.delenv("FYN_POOL_GLOBAL_BLOCK")
+        np.testing.assert_array_equal(tout.read_chw(), y)
         for o in (tin, tout, op):
             o.destroy()
     # batch-norm on pair-aligned deep tensors (even width, no padding) against the texel-wise kernel's shapes (odd width)
