@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "fyn_internal.h"
 
@@ -946,10 +947,14 @@ int fyn_pool2d_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stre
             if (!noBulk && ((uintptr_t)a.in.ptr & 15) == 0 && !noRing && in->owns && ROr >= 2 && bx0min >= 0 && by0min >= 0 && bx0max + NC <= a.in.texW && byEnd <= a.in.texH &&
                 (a.in.deep || a.in.texH * (long long)a.in.texW * 4 == a.in.planeElems) && a.in.deep == a.out.deep && (!a.in.deep || a.in.tx == a.out.tx) && (long long)a.Ho * a.in.tx * a.Wo < 65536 && totalItems >= 6ll * op->ctx->prop.multiProcessorCount &&
                 totalItems < (1ll << 31) && ringSmem <= 110 * 1024) {
-                if (!ringAttr[op->ctx->device & 63]) {
-                    FYN_CUDA(cudaFuncSetAttribute(k_pool_rows_ring<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-                    FYN_CUDA(cudaFuncSetAttribute(k_pool_rows_ring<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-                    ringAttr[op->ctx->device & 63] = true;
+                {
+                    static std::mutex ringLock;                  // (ops may run from one thread per context)
+                    std::lock_guard<std::mutex> guard(ringLock);
+                    if (!ringAttr[op->ctx->device & 63]) {
+                        FYN_CUDA(cudaFuncSetAttribute(k_pool_rows_ring<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+                        FYN_CUDA(cudaFuncSetAttribute(k_pool_rows_ring<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+                        ringAttr[op->ctx->device & 63] = true;
+                    }
                 }
                 const unsigned grid = (unsigned)std::min<long long>(totalItems, 2ll * op->ctx->prop.multiProcessorCount);
                 if (a.px == 3) k_pool_rows_ring<3, 3><<<grid, 256, ringSmem, (cudaStream_t)stream>>>(a, ROr, (unsigned)totalItems);
