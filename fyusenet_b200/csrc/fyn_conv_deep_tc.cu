@@ -1463,15 +1463,24 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
         long long nsub = 0;
         long long target = sms;                              // CTAs of a layer: at most this many
         if (const char *e = getenv("FYN_DEEP_SK_TARGET")) target = std::max(1, atoi(e));
-        // 64-column tiles, the K split that still fits the target, 32-column tiles if the layer then fills less than half of it
-        // (measured alternatives at batch 1: the K split first and narrower tiles second, 0.345 instead of 0.327 ms per forward; the
-        // kernel on mid-size grids of 74 ... 295 tiles, where the one-tile kernel runs: batch 8 0.60 -> 0.64 / 0.69 ms, batch 64 1.83 -> 1.89 / 2.00 ms)
+        // the K split that still fits the target for a given tile width.  Other measured alternatives at batch 1 (ms per forward): 32 columns
+        // everywhere 0.316; 64 everywhere 0.318; the K split first and narrower tiles second 0.345; the kernel on mid-size grids of 74 ... 295
+        // tiles, where the one-tile kernel runs: batch 8 0.60 -> 0.64 / 0.69 ms, batch 64 1.83 -> 1.89 / 2.00 ms
         auto choose = [&]() {
             nsub = (co16 + NTs - 1) / NTs;
             for (ks = 1; ks * 2 <= 8 && ks * 2 <= a.nstages && mtiles * nsub * ks * 2 <= target;) ks *= 2;
         };
+        // Tile width.  Policy 0: 64 columns, narrowed to 32 when the layer then fills less than half the target.  Policy 1: layers of many
+        // pixel tiles (>= 8) whose 32-column grid still fits the target, or whose K is one or two stages, take 32 columns; layers of one or two
+        // pixel tiles stay at 64 (fewer, fuller clusters); the others follow policy 0.  Measured on one box (ms per ResNet-50 forward, policy
+        // 1 / 0): batch 1 0.309 / 0.327, batch 2 0.399 / 0.392, batch 4 0.508 / 0.469, batch 8 0.730 / 0.609 -- policy 1 keeps the K split
+        // from layers with long K on larger grids.  So: policy 1 at batch 1, policy 0 otherwise (FYN_DEEP_SK_POLICY overrides).
+        static const int skPolicyEnv = getenv("FYN_DEEP_SK_POLICY") ? atoi(getenv("FYN_DEEP_SK_POLICY")) : -1;
+        const int skPolicy = skPolicyEnv >= 0 ? skPolicyEnv : (a.batch == 1 ? 1 : 0);
+        const long long nsub32 = (co16 + 31) / 32;
+        if (skPolicy == 1 && NTs == 64 && mtiles >= 8 && (mtiles * nsub32 <= target || a.nstages <= 2)) NTs = 32;
         choose();
-        if (NTs == 64 && 2 * mtiles * nsub * ks <= target) {
+        if (NTs == 64 && (skPolicy == 0 || mtiles >= 3) && 2 * mtiles * nsub * ks <= target) {
             NTs = 32;
             choose();
         }
