@@ -3,6 +3,7 @@
 
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 #include <cstdarg>
 #include <cstdint>
@@ -31,6 +32,31 @@ void fyn_set_error(const char *fmt, ...);
             return FYN_ERR_CUDA;                                                                  \
         }                                                                                         \
     } while (0)
+
+// Launch with programmatic dependent launch allowed: the kernel may become resident while its predecessor in the stream still runs;
+// it must execute griddepcontrol.wait before its first global-memory access (FYN_PDL_PROLOGUE at the top of the kernel).
+#ifdef __CUDACC__
+#define FYN_PDL_PROLOGUE()                                              \
+    do {                                                                \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+        asm volatile("griddepcontrol.wait;" ::: "memory");              \
+    } while (0)
+template <typename... ExpTypes, typename... ActTypes>
+inline cudaError_t fyn_launch_pdl(void (*kernel)(ExpTypes...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, ActTypes &&...args) {
+    static const bool noPdl = getenv("FYN_TC_NO_PDL") != nullptr;   // debugging aid: plain stream-ordered launches
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = noPdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<ExpTypes>(args)...);
+}
+#endif
 
 #define FYN_CHECK_LAUNCH(ctx)                                                                  \
     do {                                                                                       \

@@ -154,6 +154,7 @@ __device__ __forceinline__ void pool_strip_compute(const PoolArgs &a, const uint
 // 151 us = 27 % of the copy bandwidth; this kernel: see profiles/r02_bandwidth_layers.md).
 template <int PX, int PY>
 __global__ void __launch_bounds__(256) k_pool_rows(const PoolArgs a, int RO, int NC, int bulk) {
+    FYN_PDL_PROLOGUE();
     extern __shared__ uint2 sPool[];
     const int strips = (a.Ho + RO - 1) / RO;
     unsigned bid = blockIdx.x;
@@ -391,6 +392,7 @@ __global__ void __launch_bounds__(256) k_pool_global_deep(const PoolArgs a) {
 // stores the tile's texel.  k_pool_global_deep (one block per row of tiles, column sums through shared memory behind a barrier,
 // the reduction on tx of 256 threads) reached 35 % of the copy bandwidth at batch 512: independent warps keep more loads in flight.
 __global__ void __launch_bounds__(256) k_pool_global_warp(const PoolArgs a, int tpw, int groups, unsigned totalWarps) {
+    FYN_PDL_PROLOGUE();
     // (one row of tiles per warp; two / four rows per warp with all their loads in flight were measured slower at batch 512 --
     // 50 / 71 us instead of 39 - 45 us: registers and occupancy)
     const unsigned wid = blockIdx.x * 8u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
@@ -596,6 +598,7 @@ __global__ void __launch_bounds__(256) k_eltwise_flat(const EltArgs a, unsigned 
 // (p / W through a multiplication: magic = floor(2^32 / W) + 1 is exact while p * W < 2^32, which the launcher checks)
 template <int U>
 __global__ void __launch_bounds__(256) k_eltwise_h4(const EltArgs a, unsigned W, unsigned HW, unsigned chunks, unsigned magic) {
+    FYN_PDL_PROLOGUE();
     unsigned bid = blockIdx.x;
     const unsigned chunk = bid % chunks;
     bid /= chunks;
@@ -647,6 +650,7 @@ __global__ void __launch_bounds__(256) k_eltwise_h4(const EltArgs a, unsigned W,
 // padding-free deep tensor of ResNet-50): two texels per access, up to eight accesses in flight per thread, and the plane is cut
 // into EQUAL chunks (k_eltwise_h4 on a 56x56 plane ran one full and one half-empty block: 65 % of the copy bandwidth).
 __global__ void __launch_bounds__(256) k_eltwise_p8(const EltArgs a, unsigned Wp, unsigned HWp, unsigned chunks, unsigned len, unsigned magic) {
+    FYN_PDL_PROLOGUE();
     unsigned bid = blockIdx.x;
     const unsigned chunk = bid % chunks;
     bid /= chunks;
@@ -709,6 +713,7 @@ __global__ void __launch_bounds__(256) k_eltwise_p8(const EltArgs a, unsigned Wp
 // start on odd texels).  The generic one-texel-per-thread kernel took 177 us at batch 512 (44 % of the copy bandwidth).
 // Same arithmetic as elt_apply on (r, g, b, 0).
 __global__ void __launch_bounds__(256) k_eltwise_rgb32f(const EltArgs a, unsigned quadsPerRow, unsigned totalQuads) {
+    FYN_PDL_PROLOGUE();
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a.mode == 0) {
         sc = __ldg(a.scale);
@@ -783,7 +788,7 @@ static int launch_eltwise(fyn_ctx *ctx, const EltArgs &a, int W, int H, cudaStre
     if (a.in.dtype == FYN_F32 && a.in.packing == 3 && !a.in.deep && a.out.dtype == FYN_F16 && a.out.packing == 4 && a.tiles == 1 && (W % 4) == 0 && a.in.P == 0 &&
         a.in.texW == W && (((uintptr_t)a.in.ptr) & 15) == 0 && quads < (1ll << 31) && (long long)a.batch * H < (1ll << 31)) {
         const long long cap = (long long)ctx->prop.multiProcessorCount * 8;
-        k_eltwise_rgb32f<<<(unsigned)std::min<long long>((quads + 255) / 256, cap), 256, 0, stream>>>(a, (unsigned)(W / 4), (unsigned)quads);
+        fyn_launch_pdl(k_eltwise_rgb32f, dim3((unsigned)std::min<long long>((quads + 255) / 256, cap)), dim3(256), 0, stream, a, (unsigned)(W / 4), (unsigned)quads);
         return 0;
     }
     if (flat) {
@@ -815,17 +820,17 @@ static int launch_eltwise(fyn_ctx *ctx, const EltArgs &a, int W, int H, cudaStre
         if ((W & 1) == 0 && HW >= 512 && pairAligned(a.in, a.in.P) && pairAligned(a.out, a.outP) && (unsigned long long)HW * (unsigned)W < (1ull << 32)) {
             const unsigned Wp = (unsigned)W / 2, HWp = HW / 2;
             const unsigned chunks = (HWp + 2047u) / 2048u, len = (HWp + chunks - 1) / chunks;
-            k_eltwise_p8<<<chunks * (unsigned)a.tiles * (unsigned)a.batch, 256, 0, stream>>>(a, Wp, HWp, chunks, len, (unsigned)((1ull << 32) / Wp) + 1u);
+            fyn_launch_pdl(k_eltwise_p8, dim3(chunks * (unsigned)a.tiles * (unsigned)a.batch), dim3(256), 0, stream, a, Wp, HWp, chunks, len, (unsigned)((1ull << 32) / Wp) + 1u);
             return 0;
         }
         const int U = HW > 1024 ? 8 : (HW > 512 ? 4 : (HW > 256 ? 2 : 1));
         const unsigned chunks = (HW + 256u * U - 1) / (256u * U);
         const unsigned blocks = chunks * (unsigned)a.tiles * (unsigned)a.batch;
         const unsigned magic = ((unsigned long long)(HW + 256u * U) * (unsigned)W < (1ull << 32) && W > 1) ? (unsigned)((1ull << 32) / (unsigned)W) + 1u : 0u;
-        if (U == 8) k_eltwise_h4<8><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks, magic);
-        else if (U == 4) k_eltwise_h4<4><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks, magic);
-        else if (U == 2) k_eltwise_h4<2><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks, magic);
-        else k_eltwise_h4<1><<<blocks, 256, 0, stream>>>(a, (unsigned)W, HW, chunks, magic);
+        if (U == 8) fyn_launch_pdl(k_eltwise_h4<8>, dim3(blocks), dim3(256), 0, stream, a, (unsigned)W, HW, chunks, magic);
+        else if (U == 4) fyn_launch_pdl(k_eltwise_h4<4>, dim3(blocks), dim3(256), 0, stream, a, (unsigned)W, HW, chunks, magic);
+        else if (U == 2) fyn_launch_pdl(k_eltwise_h4<2>, dim3(blocks), dim3(256), 0, stream, a, (unsigned)W, HW, chunks, magic);
+        else fyn_launch_pdl(k_eltwise_h4<1>, dim3(blocks), dim3(256), 0, stream, a, (unsigned)W, HW, chunks, magic);
     } else {
         long long blocks = (long long)((W + 31) / 32) * ((H + 3) / 4) * a.tiles * a.batch;
         k_eltwise<<<(unsigned)blocks, dim3(32, 4), 0, stream>>>(a);
@@ -911,7 +916,7 @@ int fyn_pool2d_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stre
             const int tpw = 32 / a.in.W, groups = (a.in.tx + tpw - 1) / tpw;
             const long long warps = (long long)groups * a.in.tileRows * a.batch;   // (kRows = 1 row of tiles per warp)
             if (warps < (1ll << 31)) {
-                k_pool_global_warp<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(a, tpw, groups, (unsigned)warps);
+                fyn_launch_pdl(k_pool_global_warp, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, a, tpw, groups, (unsigned)warps);
                 FYN_CHECK_LAUNCH(op->ctx);
                 return FYN_OK;
             }
@@ -966,8 +971,8 @@ int fyn_pool2d_run(fyn_op *op, const fyn_tensor *in, fyn_tensor *out, void *stre
         const size_t smem = (size_t)(a.dy * (RO - 1) + a.py) * NCs * 8 + 16;
         if (smem <= 48 * 1024) {
             const unsigned grid = (unsigned)(((a.Ho + RO - 1) / RO) * (long long)a.tiles * a.batch);
-            if (a.px == 3) k_pool_rows<3, 3><<<grid, 256, smem, (cudaStream_t)stream>>>(a, RO, NC, bulk);
-            else k_pool_rows<2, 2><<<grid, 256, smem, (cudaStream_t)stream>>>(a, RO, NC, bulk);
+            if (a.px == 3) fyn_launch_pdl(k_pool_rows<3, 3>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, a, RO, NC, bulk);
+            else fyn_launch_pdl(k_pool_rows<2, 2>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, a, RO, NC, bulk);
             FYN_CHECK_LAUNCH(op->ctx);
             return FYN_OK;
         }
