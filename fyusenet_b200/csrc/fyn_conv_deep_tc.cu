@@ -1466,9 +1466,10 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
         // the K split that still fits the target for a given tile width.  Other measured alternatives at batch 1 (ms per forward): 32 columns
         // everywhere 0.316; 64 everywhere 0.318; the K split first and narrower tiles second 0.345; the kernel on mid-size grids of 74 ... 295
         // tiles, where the one-tile kernel runs: batch 8 0.60 -> 0.64 / 0.69 ms, batch 64 1.83 -> 1.89 / 2.00 ms
+        static const int minStages = getenv("FYN_DEEP_SK_MINK") ? std::max(1, atoi(getenv("FYN_DEEP_SK_MINK"))) : 1;   // K stages per CTA at least
         auto choose = [&]() {
             nsub = (co16 + NTs - 1) / NTs;
-            for (ks = 1; ks * 2 <= 8 && ks * 2 <= a.nstages && mtiles * nsub * ks * 2 <= target;) ks *= 2;
+            for (ks = 1; ks * 2 <= 8 && ks * 2 * minStages <= a.nstages && mtiles * nsub * ks * 2 <= target;) ks *= 2;
         };
         // Tile width.  Policy 0: 64 columns, narrowed to 32 when the layer then fills less than half the target.  Policy 1: layers of many
         // pixel tiles (>= 8) whose 32-column grid still fits the target, or whose K is one or two stages, take 32 columns; layers of one or two
