@@ -1454,7 +1454,8 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     const int skMode = ske ? atoi(ske) : 2;
     const bool haloShape = a.K == 3 && a.ds == 1 && !a.inNorm && a.inP >= 1;
     // (regime: fewer tiles than FYN_DEEP_SK_MAXTILES, default half the SM count; the persistent kernels start at two tiles per SM)
-    long long skMaxTiles = sms / 2;
+    // (a quarter of the SM count, half of it for layers of one or two K stages: measured, see the persistent kernel's threshold below)
+    long long skMaxTiles = a.nstages <= 2 ? sms / 2 : sms / 4;
     if (const char *e = getenv("FYN_DEEP_SK_MAXTILES")) skMaxTiles = std::max(1, atoi(e));
     if (skMode && (!pe || atoi(pe) == 1) && !a.tapPacked && a.NT <= 128 && mtiles * plan->ntiles <= skMaxTiles &&
         a.Mtotal < (1ll << 31) - kM && !(skMode == 1 && haloShape)) {
@@ -1658,7 +1659,14 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
             }
         }
     }
-    if ((!pe || atoi(pe) != 0) && mtiles * ntiles >= (pe && atoi(pe) == 2 ? 1ll : 2ll * sms)) {
+    // The persistent kernel on EVERY grid the split-K kernel does not take (FYN_DEEP_PERSIST_MIN: the smallest grid, in tiles, that takes it).
+    // Round 2 first kept it for grids of at least two tiles per SM and left 75 ... 295 tiles to the one-tile kernel -- one 128 - 192 KB CTA
+    // per SM in uneven waves, no overlap of gather / MMA / epilogue.  Measured (ms per ResNet-50 forward, one-tile kernel below 296 tiles /
+    // persistent everywhere, split-K regime 74 tiles / 37 tiles + 74 for one- and two-stage layers): batch 8 0.607 / 0.560, batch 16 0.80 / 0.731,
+    // batch 32 1.242 / 1.030, batch 64 1.793 / 1.627, batch 128 3.023 / 2.937; batch 1 ... 4 unchanged or slightly better.
+    static const long long persistMinEnv = getenv("FYN_DEEP_PERSIST_MIN") ? atoll(getenv("FYN_DEEP_PERSIST_MIN")) : -1;
+    const long long persistMin = persistMinEnv >= 0 ? persistMinEnv : 1;
+    if ((!pe || atoi(pe) != 0) && mtiles * ntiles >= (pe && atoi(pe) == 2 ? 1ll : persistMin)) {
         a.ntilesN = ntiles;
         a.totalTiles = mtiles * ntiles;
         const size_t stageBytes = (size_t)kAStageBytes + (size_t)a.NT * kKC * 2;

@@ -315,7 +315,7 @@ def test_deep_conv_splitk_cluster_kernel(k, ds, ci, co, inp, outp, postbn, res, 
     monkeypatch.setenv("FYN_DEEP_SPLITK", "0")
     monkeypatch.setenv("FYN_DEEP_HALO", "0")
     base = conv_gpu(x, wb, **kw)
-    assert gpu_util.LAST_KERNEL == 10
+    assert gpu_util.LAST_KERNEL in (10, 11)      # one-tile or persistent kernel: the same K order, bit-identical to each other
     monkeypatch.setenv("FYN_DEEP_SPLITK", "2")
     for nt, split in ((None, None), ("64", "2"), ("32", "8"), ("16", "3"), ("64", "1")):
         for name, v in (("FYN_DEEP_SK_NT", nt), ("FYN_DEEP_SK_SPLIT", split)):
