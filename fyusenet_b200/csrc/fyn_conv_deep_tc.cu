@@ -17,6 +17,10 @@
 //   * four tcgen05.mma (M = 128, N <= 128, K = 16) per stage accumulate in TMEM; after the last stage the loader
 //     warps turn into the epilogue: tcgen05.ld -> *bnScale + bias (fp16-rounded like the reference's RGBA16F bias
 //     texture, deepconvlayerbase.cpp:371-394) (+ residual [ReLU] [*bnScale]) -> fp16 texels of the output tiles.
+// Four kernels share this arithmetic (the launcher picks by grid size, fyn_conv_deep_tc_run): k_conv_deep_tc_sk (small grids:
+// K split over a thread-block cluster, reduce-scatter through distributed shared memory), k_conv_deep_tc_p (persistent, one
+// CTA per SM: every other grid), k_conv_deep_tc_h3 (3x3 stride 1: halo tiles) and k_conv_deep_tc, the one-tile-per-CTA
+// kernel described here, which the others are tested against (FYN_DEEP_PERSIST=0 selects it).
 // One CTA = one (128-pixel, N-tile) output tile; 4 x 4 loader/epilogue warps (stages round robin, so that four gathers
 // are in flight) + 1 MMA warp; stage ring of min(4, stages)
 // entries, so that the many short-K layers (1x1 convs on 64 channels: a single stage) fit several CTAs per SM.
@@ -692,7 +696,7 @@ __global__ void __launch_bounds__(kThreadsDeep, 1) k_conv_deep_tc_sk(const __gri
 }
 
 // ---------------------------------------------------------------------------------------------
-// Persistent variant for large grids (batched inference): ONE CTA per SM walks the output tiles (n tile fastest, round
+// Persistent variant (every grid above the split-K kernel's regime): ONE CTA per SM walks the output tiles (n tile fastest, round
 // robin over the CTAs, so that the CTAs working on the N tiles of one pixel tile run at the same time and share its texels
 // through L2).  The roles no longer share threads, so the three phases of a tile overlap with those of its neighbours:
 //   * loader sets (4 x 128 threads) gather stage after stage, across tile boundaries, as far ahead as the ring allows;
@@ -1595,7 +1599,7 @@ int fyn_conv_deep_tc_run(fyn_op *op, const fyn_tensor *in, const fyn_tensor *res
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    // Large grids: the persistent kernel (one CTA per SM, gathers / MMAs / epilogues of neighbouring tiles overlapped).
+    // The persistent kernel (one CTA per SM, gathers / MMAs / epilogues of neighbouring tiles overlapped).
     // FYN_DEEP_PERSIST=0 keeps the one-tile-per-CTA kernel (read per run: tests compare the two).
     const char *he = getenv("FYN_DEEP_HALO");          // 0: every layer on the stage-per-tap kernels (read per run)
     // 3x3 stride-1 layers take the halo-tile kernel on ANY grid: on small ones (batch 1) a CTA's chain of K stages is what
